@@ -1,0 +1,172 @@
+/* cathy_b200.h -- C ABI of libcathy_b200.so, the B200-native CATHY processor.
+ *
+ * Boundary being replaced: pyCATHY reaches the Fortran processor only as a
+ * child process `./cathy` in a project directory
+ * (pyCATHY/cathy_tools.py:669 `subprocess.run(["./cathy"], ...)`,
+ * pyCATHY/cathy_tools.py:76-98 `subprocess_run_multi`).  The processor's own
+ * entry is PROGRAM CATHY_MAIN (SRC/cathy_main.f:2495-3945) whose time loop
+ * calls FLOW3D (SRC/flow3d.f:8-35, ~200 positional arguments + COMMON blocks).
+ * There is no FFI in the reference; this header is the interface a binding
+ * would target.  Each entry point names the reference routine(s) it stands for.
+ * SRC = pyCATHY/tests/weil_exemple/my_cathy_prj/src.
+ *
+ * Conventions: plain C, caller-owned host buffers, all reals are double
+ * (REAL*8), all integers int32 (INTEGER*4).  Node / cell ids crossing this
+ * boundary are 1-based exactly as in the CATHY files.  Return value 0 =
+ * success, negative = error (text via cathy_last_error()).  A handle owns one
+ * CUDA stream and all device memory of one simulation; handles share nothing,
+ * so many may live in one process (ensemble members) or in many processes.
+ */
+#ifndef CATHY_B200_H
+#define CATHY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CATHY_ABI_VERSION 1
+#define CATHY_MAXIT 64 /* upper bound on ITUNS kept in a step report (CATHY.H MAXIT=30) */
+
+/* Everything DATIN / INITAL read from the project files (SRC/datin.f:80-514,
+ * SRC/atmone.f, SRC/bcone.f), already parsed into flat arrays.  Rasters are
+ * row-major with the NORTH row first, exactly as they appear in the files. */
+typedef struct CathyProblem {
+    int32_t abi_version;
+    /* --- DEM mesh (SRC/datin.f:195-204,266; SRC/triangoli.f; SRC/gen3d.f) */
+    int32_t nrow, ncol, nstr, nzone, nveg;
+    int32_t ivert;
+    int32_t _pad0;
+    double dx, dy, west, south, factor, base;
+    const double *dem;       /* [nrow*ncol] cell elevations (prepro/dem)            */
+    const int32_t *zone;     /* [nrow*ncol] material zone 1..nzone (prepro/zone)    */
+    const double *root_map;  /* [nrow*ncol] vegetation type map (input/root_map)    */
+    const double *zratio;    /* [nstr] layer thickness fractions                    */
+    /* --- soil (SRC/datin.f:421-458,510-514); tables are [nstr][nzone]            */
+    const double *permx, *permy, *permz, *elstor, *poros, *vgn, *vgrmc, *vgpsat;
+    const double *pcana, *pcref, *pcwlt, *zroot, *pz, *omgc; /* [nveg] Feddes      */
+    double pmin, scf;
+    int32_t ivghu;
+    /* --- parm (SRC/datin.f:80-122) */
+    int32_t isimgr, kslope, lump, iopt, nlrelx, l2norm;
+    int32_t ituns, ituns1, ituns2, isolv, itmxcg;
+    double pondh_min, tolksl, tetaf, omega, toluns, tolswi, ernlmx, tolcg;
+    double deltat, dtmin, dtmax, tmax, dtmaga, dtmagm, dtreds, dtredm;
+    /* --- initial conditions (SRC/datin.f:380-403, SRC/icvhe.f, icvhwt.f, icvdwt.f) */
+    int32_t indp, ipond;
+    double wtposition;
+    const double *ic_psi;  /* [N] used when indp = 0 or 1 (already expanded)        */
+    const double *ic_pond; /* [NNOD] initial ponding heads (zeros when ipond = 0)   */
+    /* --- atmospheric forcing table (SRC/atmone.f, SRC/atmnxt.f) */
+    int32_t atm_none; /* 1: HSPATM = 9999 or empty file -> no atmospheric nodes     */
+    int32_t hspatm;   /* 0: one value per surface node, else homogeneous            */
+    int32_t ieto;     /* 0: linear interpolation in time, else piecewise constant   */
+    int32_t natm;     /* number of (time, values) records                           */
+    const double *atm_time; /* [natm]                                               */
+    const double *atm_val;  /* [natm * (hspatm ? 1 : NNOD)] rate per unit area      */
+    /* --- non-atmospheric, non-seepage Dirichlet / Neumann records (SRC/bcone.f, rdndbc.f) */
+    int32_t ndir_rec, nneu_rec;
+    const double *dir_time;  /* [ndir_rec]                                          */
+    const int32_t *dir_ptr;  /* [ndir_rec+1] CSR style offsets into dir_node/val    */
+    const int32_t *dir_node; /* 1-based 3-D node ids                                */
+    const double *dir_val;   /* prescribed pressure heads                           */
+    const double *neu_time;
+    const int32_t *neu_ptr;
+    const int32_t *neu_node;
+    const double *neu_val;   /* volumetric fluxes                                   */
+    const int32_t *neu_n2d;  /* [nneu_rec] NODIN2 (<0: free drainage bottom, SRC/neumann.f) */
+    /* --- surface routing inputs, isimgr = 2 only (SRC/datin.f:325-372) */
+    const int32_t *qoi;      /* [nrow*ncol] cells in descending elevation order (prepro/qoi_a) */
+    const double *dtm_w_1, *dtm_w_2;
+    const double *dtm_p_outflow_1, *dtm_p_outflow_2; /* keypad codes 1..9 stored as double */
+    const double *dtm_local_slope_1, *dtm_local_slope_2;
+    const double *dtm_epl_1, *dtm_epl_2;
+    const double *dtm_kss1_sf_1, *dtm_kss1_sf_2;
+    const double *dtm_ws1_sf_1, *dtm_ws1_sf_2;
+    const double *dtm_b1_sf, *dtm_y1_sf, *dtm_nrc;
+    /* --- implementation knobs (not CATHY inputs) */
+    int32_t precond;    /* 0: default; see DESIGN.md                                */
+    int32_t device;     /* CUDA device ordinal                                      */
+    double tolcg_scale; /* multiplies TOLCG for the device PCG (<=0: 1)            */
+} CathyProblem;
+
+/* One nonlinear iteration line of output/iter (SRC/conver.f:44 FORMAT 1070). */
+typedef struct CathyIterRecord {
+    int32_t niter;   /* linear iterations of this nonlinear iteration */
+    int32_t ikmax;   /* 1-based node of the max-norm change           */
+    double pl2, pinf, pnew_ik, pold_ik, fl2, finf;
+} CathyIterRecord;
+
+/* Everything the time loop prints for one ACCEPTED step: mbeconv FORMAT 1240
+ * (SRC/cathy_main.f:3269), cumflowvol 1199 (:3677), hgatmsf 1190, dtcoupling
+ * 1170 (:3686), plus control flags. */
+typedef struct CathyStepReport {
+    int32_t nstep, iter, nitert, kbackt, nsurf, nsurft, noback, finished;
+    int32_t n_iter_rec, ponding, klsfai_total, kback_total;
+    double deltat, time;
+    double store1, store2, dstore;
+    double vin, vout, erras, errel;
+    double adin, adout, ndin, ndout, anin, anout, nnin, nnout, sfflw;
+    double vsfflw, vndin, vndout, vnnin, vnnout;
+    double apot, aact, ovflow, reflow;
+    double fhort, fdunn, fpond, fsat;
+    double next_deltat, next_time;
+    double ak_max;
+    double q_outlet_1, q_outlet_2; /* Q_OUT_KKP1_SN_1/2 at the outlet cell (SRC/detoutq.f) */
+    double gpu_ms; /* device time of this step (CUDA events), 0 for the CPU oracle */
+    int64_t launches; /* kernels launched during this step                         */
+    CathyIterRecord it[CATHY_MAXIT];
+} CathyStepReport;
+
+typedef struct CathySim CathySim; /* opaque */
+
+/* Sizes of the public structs as compiled, so a binding can check its mirror. */
+int64_t cathy_sizeof_problem(void);
+int64_t cathy_sizeof_report(void);
+int32_t cathy_abi_version(void);
+const char *cathy_last_error(void);
+
+/* DATIN + GRDSYS + STRPIC/TETPIC + INITAL + CHVELO/STORCAL (SRC/cathy_main.f:2508-2660):
+ * builds mesh, sparsity, scatter plan and initial state on the device. */
+int32_t cathy_create(const CathyProblem *prob, CathySim **out);
+void cathy_destroy(CathySim *sim);
+
+/* Mesh counts: NNOD, N, NT, NTERM (symmetric, upper incl. diagonal), nnz of the full matrix. */
+int32_t cathy_get_dims(const CathySim *sim, int64_t dims[5]);
+/* GEN3D output (SRC/gen3d.f:28-77): coordinates [N] each; tetra [NT*5] in GEN3D (unsorted)
+ * order, 1-based nodes + zone -- what `output/grid3d` and `output/xyz` hold.  Any pointer may be NULL. */
+int32_t cathy_get_mesh(const CathySim *sim, double *x, double *y, double *z, int32_t *tetra);
+/* STORE0 of SRC/cathy_main.f:2660 (initial water volume) */
+double cathy_initial_storage(const CathySim *sim);
+
+/* One pass of the time loop body SRC/cathy_main.f:2882-3829 up to and including TIMUPD:
+ * BC update, surface routing, FLOW3D with back-stepping, mass balance, hydrograph terms. */
+int32_t cathy_step(CathySim *sim, CathyStepReport *rep);
+
+/* State after the last accepted step (what DETOUT prints, SRC/detout.f:29-128).
+ * Any pointer may be NULL.  psi,sw,ckrw,qtranie: [N]; pond,atmact,atmpot,ovfl: [NNOD]; ifatm [NNOD]. */
+int32_t cathy_get_state(CathySim *sim, double *psi, double *sw, double *ckrw, double *qtranie,
+                        double *pond, double *atmact, double *atmpot, double *ovfl, int32_t *ifatm);
+/* Overwrite the pressure-head state (DA restart; stands for pyCATHY update_ic(INDP=1) +
+ * relaunch, pyCATHY/cathy_tools.py:1863-1875).  Only valid before the first step. */
+int32_t cathy_set_psi(CathySim *sim, const double *psi);
+
+/* ---- kernel-level entry points used by parity tests and bench.py -------------------- */
+/* Assemble the Picard system at the current state for time step `deltat` without solving
+ * (PICUNS+ASSPIC+RHSPIC+CFMATP+RHSGRV+BCPIC, SRC/picard.f:74-154) and export it as
+ * symmetric upper CSR in the reference layout (diagonal first; SRC/strpic.f:19-96).
+ * topol [N+1], ja [NTERM] are 1-based; coef1 [NTERM]; rhs [N].  Any pointer may be NULL. */
+int32_t cathy_debug_assemble(CathySim *sim, double deltat, int32_t *topol, int32_t *ja,
+                             double *coef1, double *rhs);
+/* y = A x with the currently assembled LHS (the SpMV of GRADDP, SRC/solscal-extended.f:1326-1334).
+ * Runs `reps` launches, returns average device ms per launch in *ms (may be NULL). */
+int32_t cathy_debug_spmv(CathySim *sim, const double *x, double *y, int32_t reps, double *ms);
+/* Solve the currently assembled system (SYMSLV, SRC/solscal-extended.f:4669-4699).
+ * sol [N]; niter, err = relative residual as GRADDP defines it. */
+int32_t cathy_debug_solve(CathySim *sim, double *sol, int32_t *niter, double *err, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CATHY_B200_H */

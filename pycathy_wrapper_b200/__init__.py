@@ -1,0 +1,4 @@
+"""cathy-b200: B200-native CATHY Richards-equation processor behind pyCATHY's run_processor boundary."""
+from .project import CathyInputError, CathyProject, load_project  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,318 @@
+"""ctypes mirror of include/cathy_b200.h and the loader of libcathy_b200.so.
+
+The product path has NO fallback: if the CUDA library is missing or fails to load,
+``load_library()`` raises ``CathyLibraryError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .project import CathyProject
+
+ABI_VERSION = 1
+MAXIT = 64
+_D = C.POINTER(C.c_double)
+_I = C.POINTER(C.c_int32)
+
+
+class CathyLibraryError(RuntimeError):
+    pass
+
+
+class CathyProblem(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("nrow", C.c_int32), ("ncol", C.c_int32), ("nstr", C.c_int32), ("nzone", C.c_int32), ("nveg", C.c_int32),
+        ("ivert", C.c_int32), ("_pad0", C.c_int32),
+        ("dx", C.c_double), ("dy", C.c_double), ("west", C.c_double), ("south", C.c_double),
+        ("factor", C.c_double), ("base", C.c_double),
+        ("dem", _D), ("zone", _I), ("root_map", _D), ("zratio", _D),
+        ("permx", _D), ("permy", _D), ("permz", _D), ("elstor", _D), ("poros", _D), ("vgn", _D),
+        ("vgrmc", _D), ("vgpsat", _D),
+        ("pcana", _D), ("pcref", _D), ("pcwlt", _D), ("zroot", _D), ("pz", _D), ("omgc", _D),
+        ("pmin", C.c_double), ("scf", C.c_double),
+        ("ivghu", C.c_int32),
+        ("isimgr", C.c_int32), ("kslope", C.c_int32), ("lump", C.c_int32), ("iopt", C.c_int32),
+        ("nlrelx", C.c_int32), ("l2norm", C.c_int32),
+        ("ituns", C.c_int32), ("ituns1", C.c_int32), ("ituns2", C.c_int32), ("isolv", C.c_int32),
+        ("itmxcg", C.c_int32),
+        ("pondh_min", C.c_double), ("tolksl", C.c_double), ("tetaf", C.c_double), ("omega", C.c_double),
+        ("toluns", C.c_double), ("tolswi", C.c_double), ("ernlmx", C.c_double), ("tolcg", C.c_double),
+        ("deltat", C.c_double), ("dtmin", C.c_double), ("dtmax", C.c_double), ("tmax", C.c_double),
+        ("dtmaga", C.c_double), ("dtmagm", C.c_double), ("dtreds", C.c_double), ("dtredm", C.c_double),
+        ("indp", C.c_int32), ("ipond", C.c_int32),
+        ("wtposition", C.c_double),
+        ("ic_psi", _D), ("ic_pond", _D),
+        ("atm_none", C.c_int32), ("hspatm", C.c_int32), ("ieto", C.c_int32), ("natm", C.c_int32),
+        ("atm_time", _D), ("atm_val", _D),
+        ("ndir_rec", C.c_int32), ("nneu_rec", C.c_int32),
+        ("dir_time", _D), ("dir_ptr", _I), ("dir_node", _I), ("dir_val", _D),
+        ("neu_time", _D), ("neu_ptr", _I), ("neu_node", _I), ("neu_val", _D), ("neu_n2d", _I),
+        ("qoi", _I),
+        ("dtm_w_1", _D), ("dtm_w_2", _D), ("dtm_p_outflow_1", _D), ("dtm_p_outflow_2", _D),
+        ("dtm_local_slope_1", _D), ("dtm_local_slope_2", _D), ("dtm_epl_1", _D), ("dtm_epl_2", _D),
+        ("dtm_kss1_sf_1", _D), ("dtm_kss1_sf_2", _D), ("dtm_ws1_sf_1", _D), ("dtm_ws1_sf_2", _D),
+        ("dtm_b1_sf", _D), ("dtm_y1_sf", _D), ("dtm_nrc", _D),
+        ("precond", C.c_int32), ("device", C.c_int32),
+        ("tolcg_scale", C.c_double),
+    ]
+
+
+class CathyIterRecord(C.Structure):
+    _fields_ = [("niter", C.c_int32), ("ikmax", C.c_int32), ("pl2", C.c_double), ("pinf", C.c_double),
+                ("pnew_ik", C.c_double), ("pold_ik", C.c_double), ("fl2", C.c_double), ("finf", C.c_double)]
+
+
+class CathyStepReport(C.Structure):
+    _fields_ = [
+        ("nstep", C.c_int32), ("iter", C.c_int32), ("nitert", C.c_int32), ("kbackt", C.c_int32),
+        ("nsurf", C.c_int32), ("nsurft", C.c_int32), ("noback", C.c_int32), ("finished", C.c_int32),
+        ("n_iter_rec", C.c_int32), ("ponding", C.c_int32), ("klsfai_total", C.c_int32), ("kback_total", C.c_int32),
+        ("deltat", C.c_double), ("time", C.c_double),
+        ("store1", C.c_double), ("store2", C.c_double), ("dstore", C.c_double),
+        ("vin", C.c_double), ("vout", C.c_double), ("erras", C.c_double), ("errel", C.c_double),
+        ("adin", C.c_double), ("adout", C.c_double), ("ndin", C.c_double), ("ndout", C.c_double),
+        ("anin", C.c_double), ("anout", C.c_double), ("nnin", C.c_double), ("nnout", C.c_double), ("sfflw", C.c_double),
+        ("vsfflw", C.c_double), ("vndin", C.c_double), ("vndout", C.c_double), ("vnnin", C.c_double), ("vnnout", C.c_double),
+        ("apot", C.c_double), ("aact", C.c_double), ("ovflow", C.c_double), ("reflow", C.c_double),
+        ("fhort", C.c_double), ("fdunn", C.c_double), ("fpond", C.c_double), ("fsat", C.c_double),
+        ("next_deltat", C.c_double), ("next_time", C.c_double),
+        ("ak_max", C.c_double), ("q_outlet_1", C.c_double), ("q_outlet_2", C.c_double), ("gpu_ms", C.c_double),
+        ("launches", C.c_int64),
+        ("it", CathyIterRecord * MAXIT),
+    ]
+
+
+def _dp(a):
+    return a.ctypes.data_as(_D) if a is not None and a.size else C.cast(None, _D)
+
+
+def _ip(a):
+    return a.ctypes.data_as(_I) if a is not None and a.size else C.cast(None, _I)
+
+
+class ProblemHolder:
+    """Owns the numpy buffers a CathyProblem points to (they must outlive the create call)."""
+
+    def __init__(self, prj: CathyProject, precond: int = 0, device: int = 0, tolcg_scale: float = 1.0,
+                 **overrides):
+        p = dict(prj.parm)
+        p.update({k.upper(): v for k, v in overrides.items()})
+        self.parm = p
+        self.keep: list = []
+        s = CathyProblem()
+        s.abi_version = ABI_VERSION
+        s.nrow, s.ncol, s.nstr, s.nzone = prj.nrow, prj.ncol, prj.nstr, prj.nzone
+        veg = prj.soil["VEG"]
+        s.nveg = veg.shape[0]
+        s.ivert = prj.ivert
+        s.dx, s.dy, s.west, s.south, s.factor, s.base = prj.dx, prj.dy, prj.west, prj.south, prj.factor, prj.base
+
+        def fd(a):
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            self.keep.append(a)
+            return _dp(a)
+
+        def fi(a):
+            a = np.ascontiguousarray(a, dtype=np.int32)
+            self.keep.append(a)
+            return _ip(a)
+
+        s.dem, s.zone, s.root_map, s.zratio = fd(prj.dem), fi(prj.zone), fd(prj.root_map), fd(prj.zratio)
+        tab = prj.soil["TABLE"]
+        for k, name in enumerate(["permx", "permy", "permz", "elstor", "poros", "vgn", "vgrmc", "vgpsat"]):
+            setattr(s, name, fd(tab[:, :, k]))
+        for k, name in enumerate(["pcana", "pcref", "pcwlt", "zroot", "pz", "omgc"]):
+            setattr(s, name, fd(veg[:, k]))
+        s.pmin, s.scf, s.ivghu = prj.soil["PMIN"], prj.soil["SCF"], prj.soil["IVGHU"]
+        for name in ["isimgr", "kslope", "lump", "iopt", "nlrelx", "l2norm", "ituns", "ituns1", "ituns2",
+                     "isolv", "itmxcg"]:
+            setattr(s, name, int(p[name.upper()]))
+        for name in ["pondh_min", "tolksl", "tetaf", "omega", "toluns", "tolswi", "ernlmx", "tolcg", "deltat",
+                     "dtmin", "dtmax", "tmax", "dtmaga", "dtmagm", "dtreds", "dtredm"]:
+            setattr(s, name, float(p[name.upper()]))
+        s.indp, s.ipond, s.wtposition = prj.indp, prj.ipond, prj.wtposition
+        s.ic_psi, s.ic_pond = fd(prj.ic_psi), fd(prj.ic_pond)
+        s.atm_none, s.hspatm, s.ieto = int(prj.atm_none), prj.hspatm, prj.ieto
+        s.natm = len(prj.atm_times)
+        s.atm_time, s.atm_val = fd(prj.atm_times), fd(prj.atm_values)
+
+        def table(tab_):
+            n = len(tab_.times)
+            ptr = np.zeros(n + 1, dtype=np.int32)
+            for i, nd in enumerate(tab_.nodes):
+                ptr[i + 1] = ptr[i] + len(nd)
+            nodes = np.concatenate(tab_.nodes) if n else np.zeros(0, dtype=np.int64)
+            vals = np.concatenate(tab_.values) if n else np.zeros(0)
+            return n, fd(np.asarray(tab_.times)), fi(ptr), fi(nodes), fd(vals), fi(np.asarray(tab_.n2d))
+
+        s.ndir_rec, s.dir_time, s.dir_ptr, s.dir_node, s.dir_val, _ = table(prj.dirbc)
+        s.nneu_rec, s.neu_time, s.neu_ptr, s.neu_node, s.neu_val, s.neu_n2d = table(prj.neubc)
+        if prj.surf is not None and int(p["ISIMGR"]) == 2:
+            S = prj.surf
+            s.qoi = fi(S["qoi"])
+            for cname, key in [("dtm_w_1", "w_1"), ("dtm_w_2", "w_2"), ("dtm_p_outflow_1", "p_outflow_1"),
+                               ("dtm_p_outflow_2", "p_outflow_2"), ("dtm_local_slope_1", "local_slope_1"),
+                               ("dtm_local_slope_2", "local_slope_2"), ("dtm_epl_1", "epl_1"), ("dtm_epl_2", "epl_2"),
+                               ("dtm_kss1_sf_1", "kSs1_sf_1"), ("dtm_kss1_sf_2", "kSs1_sf_2"),
+                               ("dtm_ws1_sf_1", "Ws1_sf_1"), ("dtm_ws1_sf_2", "Ws1_sf_2"), ("dtm_b1_sf", "b1_sf"),
+                               ("dtm_y1_sf", "y1_sf"), ("dtm_nrc", "nrc")]:
+                setattr(s, cname, fd(S[key]))
+        elif int(p["ISIMGR"]) == 2:
+            raise ValueError("ISIMGR=2 needs the prepro rasters")
+        s.precond, s.device, s.tolcg_scale = precond, device, tolcg_scale
+        self.struct = s
+
+
+class CathyLib:
+    """Binds one shared library exporting the cathy_b200.h entry points under ``prefix``."""
+
+    SYMBOLS = ["sizeof_problem", "sizeof_report", "last_error", "create", "destroy", "get_dims", "get_mesh",
+               "initial_storage", "step", "get_state", "set_psi", "debug_assemble", "debug_spmv", "debug_solve"]
+
+    def __init__(self, path: str, prefix: str):
+        if not os.path.exists(path):
+            raise CathyLibraryError(f"{path} not found -- run `python -c 'import __graft_entry__ as g; g.build()'`")
+        try:
+            self.lib = C.CDLL(path)
+        except OSError as e:  # missing libcudart etc.
+            raise CathyLibraryError(f"cannot load {path}: {e}") from e
+        self.path, self.prefix = path, prefix
+        f = {}
+        for name in self.SYMBOLS:
+            try:
+                f[name] = getattr(self.lib, prefix + name)
+            except AttributeError as e:
+                raise CathyLibraryError(f"{path} does not export {prefix}{name}") from e
+        self.f = f
+        f["sizeof_problem"].restype = C.c_int64
+        f["sizeof_report"].restype = C.c_int64
+        f["last_error"].restype = C.c_char_p
+        f["create"].argtypes = [C.POINTER(CathyProblem), C.POINTER(C.c_void_p)]
+        f["destroy"].argtypes = [C.c_void_p]
+        f["destroy"].restype = None
+        f["get_dims"].argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        f["get_mesh"].argtypes = [C.c_void_p, _D, _D, _D, _I]
+        f["initial_storage"].argtypes = [C.c_void_p]
+        f["initial_storage"].restype = C.c_double
+        f["step"].argtypes = [C.c_void_p, C.POINTER(CathyStepReport)]
+        f["get_state"].argtypes = [C.c_void_p, _D, _D, _D, _D, _D, _D, _D, _D, _I]
+        f["set_psi"].argtypes = [C.c_void_p, _D]
+        f["debug_assemble"].argtypes = [C.c_void_p, C.c_double, _I, _I, _D, _D]
+        f["debug_spmv"].argtypes = [C.c_void_p, _D, _D, C.c_int32, _D]
+        f["debug_solve"].argtypes = [C.c_void_p, _D, _I, _D, _D]
+        if f["sizeof_problem"]() != C.sizeof(CathyProblem) or f["sizeof_report"]() != C.sizeof(CathyStepReport):
+            raise CathyLibraryError(
+                f"{path}: struct layout mismatch (problem {f['sizeof_problem']()} vs {C.sizeof(CathyProblem)}, "
+                f"report {f['sizeof_report']()} vs {C.sizeof(CathyStepReport)})")
+
+    def error(self) -> str:
+        return (self.f["last_error"]() or b"").decode()
+
+
+class Simulation:
+    """One simulation handle (device resident for the product, host resident for the oracle)."""
+
+    def __init__(self, lib: CathyLib, prj: CathyProject, **kw):
+        self.lib, self.prj = lib, prj
+        self.holder = ProblemHolder(prj, **kw)
+        self.parm = self.holder.parm
+        h = C.c_void_p()
+        rc = lib.f["create"](C.byref(self.holder.struct), C.byref(h))
+        if rc != 0:
+            raise CathyLibraryError(f"{lib.prefix}create failed ({rc}): {lib.error()}")
+        self.h = h
+        dims = (C.c_int64 * 5)()
+        lib.f["get_dims"](h, dims)
+        self.nnod, self.n, self.nt, self.nterm, self.nnz = (int(v) for v in dims)
+
+    def close(self):
+        if self.h:
+            self.lib.f["destroy"](self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def initial_storage(self) -> float:
+        return float(self.lib.f["initial_storage"](self.h))
+
+    def mesh(self, with_tetra=True):
+        x, y, z = np.empty(self.n), np.empty(self.n), np.empty(self.n)
+        tet = np.empty((self.nt, 5), dtype=np.int32) if with_tetra else None
+        self.lib.f["get_mesh"](self.h, _dp(x), _dp(y), _dp(z), _ip(tet) if with_tetra else C.cast(None, _I))
+        return x, y, z, tet
+
+    def step(self) -> CathyStepReport:
+        rep = CathyStepReport()
+        rc = self.lib.f["step"](self.h, C.byref(rep))
+        if rc != 0:
+            raise CathyLibraryError(f"{self.lib.prefix}step failed ({rc}): {self.lib.error()}")
+        return rep
+
+    def state(self) -> dict:
+        n, nn = self.n, self.nnod
+        out = {k: np.empty(n) for k in ("psi", "sw", "ckrw", "qtranie")}
+        out.update({k: np.empty(nn) for k in ("pond", "atmact", "atmpot", "ovfl")})
+        out["ifatm"] = np.empty(nn, dtype=np.int32)
+        rc = self.lib.f["get_state"](self.h, _dp(out["psi"]), _dp(out["sw"]), _dp(out["ckrw"]), _dp(out["qtranie"]),
+                                     _dp(out["pond"]), _dp(out["atmact"]), _dp(out["atmpot"]), _dp(out["ovfl"]),
+                                     _ip(out["ifatm"]))
+        if rc != 0:
+            raise CathyLibraryError(f"get_state failed ({rc}): {self.lib.error()}")
+        return out
+
+    def set_psi(self, psi: np.ndarray):
+        psi = np.ascontiguousarray(psi, dtype=np.float64)
+        assert psi.size == self.n
+        rc = self.lib.f["set_psi"](self.h, _dp(psi))
+        if rc != 0:
+            raise CathyLibraryError(f"set_psi failed ({rc}): {self.lib.error()}")
+
+    def debug_assemble(self, deltat: float):
+        topol = np.empty(self.n + 1, dtype=np.int32)
+        ja = np.empty(self.nterm, dtype=np.int32)
+        coef = np.empty(self.nterm)
+        rhs = np.empty(self.n)
+        rc = self.lib.f["debug_assemble"](self.h, deltat, _ip(topol), _ip(ja), _dp(coef), _dp(rhs))
+        if rc != 0:
+            raise CathyLibraryError(f"debug_assemble failed ({rc}): {self.lib.error()}")
+        return topol, ja, coef, rhs
+
+    def debug_spmv(self, x: np.ndarray, reps: int = 1):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(self.n)
+        ms = C.c_double()
+        rc = self.lib.f["debug_spmv"](self.h, _dp(x), _dp(y), reps, C.byref(ms))
+        if rc != 0:
+            raise CathyLibraryError(f"debug_spmv failed ({rc}): {self.lib.error()}")
+        return y, ms.value
+
+    def debug_solve(self):
+        sol = np.empty(self.n)
+        nit, err, ms = C.c_int32(), C.c_double(), C.c_double()
+        rc = self.lib.f["debug_solve"](self.h, _dp(sol), C.byref(nit), C.byref(err), C.byref(ms))
+        if rc != 0:
+            raise CathyLibraryError(f"debug_solve failed ({rc}): {self.lib.error()}")
+        return sol, nit.value, err.value, ms.value
+
+
+_LIB = None
+
+
+def library_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libcathy_b200.so")
+
+
+def load_library() -> CathyLib:
+    """The product library.  Raises CathyLibraryError when it is missing -- there is no CPU path."""
+    global _LIB
+    if _LIB is None:
+        _LIB = CathyLib(library_path(), "cathy_")
+    return _LIB

@@ -1,0 +1,178 @@
+"""The `./cathy` replacement: run one CATHY forward simulation in a project directory.
+
+Mirrors PROGRAM CATHY_MAIN's observable behaviour (SRC/cathy_main.f:2495-3945) at the
+process boundary pyCATHY uses (pyCATHY/cathy_tools.py:593-740 run_processor;
+:76-98 subprocess_run_multi): read ./cathy.fnames + input/* + prepro/*, write output/*.
+All numerical work happens on the GPU behind libcathy_b200.so (capi.load_library());
+this module only does text I/O, the cumulative book-keeping of the mass-balance columns
+and the DETOUT scheduling.
+
+File-clobbering rules of the reference are kept: a normal run leaves an
+existing output/grid3d and output/xyz untouched; IPRT1=3 writes only the mesh files.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+from . import outputs as O
+from .capi import CathyLib, Simulation, load_library
+from .project import CathyProject, load_project
+
+
+class RunResult:
+    def __init__(self):
+        self.reports = []          # light-weight dict per accepted step
+        self.nstep = 0
+        self.wall_loop = 0.0       # seconds spent in the time loop (steps only)
+        self.wall_setup = 0.0
+        self.wall_io = 0.0
+        self.gpu_ms = 0.0
+        self.launches = 0
+        self.n = 0
+        self.finished_ok = True
+        self.final_state = None
+
+
+def _out(prj: CathyProject, unit: str) -> str:
+    path = prj.fnames[unit]
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    return path
+
+
+def run_processor(project_dir: str, lib: CathyLib | None = None, write_files: bool = True, verbose: bool = False,
+                  max_steps: int | None = None, keep_reports: bool = True, prj: CathyProject | None = None,
+                  **overrides) -> RunResult:
+    """Run the simulation described by `project_dir`.  `overrides` are parm entries
+    (e.g. TMAX=600, DELTAT=1) applied on top of input/parm, like pyCATHY's
+    run_processor(**kwargs) -> update_parm."""
+    t_start = time.perf_counter()
+    if lib is None:
+        lib = load_library()                       # raises if the CUDA library is missing: no CPU path
+    if prj is None:
+        prj = load_project(project_dir)
+    sim_kw = {k: overrides.pop(k) for k in ("precond", "device", "tolcg_scale") if k in overrides}
+    sim = Simulation(lib, prj, **sim_kw, **overrides)
+    parm = sim.parm
+    res = RunResult()
+    res.n = sim.n
+    nnod, n, nstr = sim.nnod, sim.n, prj.nstr
+
+    if parm["IPRT1"] == 3:                          # mesh-only mode, SRC/gen3d.f:89-112
+        x, y, z, tet = sim.mesh()
+        if write_files:
+            O.write_xyz(_out(prj, "IOUT3"), nnod, n, x, y, z)
+            O.write_grid3d(os.path.join(os.path.dirname(_out(prj, "IOUT3")), "grid3d"), nnod, n, sim.nt, tet, x, y, z)
+            with open(_out(prj, "IOUT2"), "w") as fh:
+                fh.write("\n\n IPRT1=3: Program terminating after output of X, Y, Z coordinate values\n")
+        sim.close()
+        return res
+
+    x = y = z = None
+    fh = {}
+    if write_files:
+        x, y, z, _ = sim.mesh(with_tetra=False)
+        for key, unit in (("psi", "IOUT11"), ("sw", "IOUT13"), ("vp", "IOUT6"), ("mbeconv", "IOUT5"),
+                          ("cumflowvol", "IOUT36"), ("iter", "IOUT4"), ("hgraph", "IOUT41"), ("pondhead", "IOUT42")):
+            fh[key] = open(_out(prj, unit), "w")
+        if parm["IPRT"] >= 4:
+            fh["sw"].write("  0   HSPSW\n")
+        fh["iter"].write(O.iter_header(parm))
+        fh["mbeconv"].write(O.MBECONV_HEADER % O.fe(sim.initial_storage(), 13, 5))
+        fh["cumflowvol"].write(O.CUMFLOWVOL_HEADER)
+        fh["hgraph"].write("#%s\n" % O.fi(parm["NUM_QOUT"] + 1, 8))
+        if parm["ISIMGR"] == 2:
+            fh["hgraph"].write("#          TIME %s\n" % "".join(O.fi(v, 16) for v in [int(prj.surf["qoi"][-1])] + parm["ID_QOUT"]))
+
+    def detout(nstep, tim):
+        if not write_files:
+            return
+        st = sim.state()
+        if parm["IPRT"] >= 1:
+            O.write_block(fh["psi"], nstep, tim, st["psi"])
+            O.write_block(fh["pondhead"], nstep, tim, st["pond"])
+            if parm["IPRT"] >= 4:
+                O.write_block(fh["sw"], nstep, tim, st["sw"])
+        if parm["NUMVP"] > 0:
+            O.write_vp(fh["vp"], nstep, tim, parm["NODVP"], nnod, nstr, x, y, z, st["psi"], st["sw"], st["ckrw"],
+                       st["qtranie"])
+
+    detout(0, 0.0)
+    res.wall_setup = time.perf_counter() - t_start
+
+    cum = dict(VSFTOT=0.0, VNDTOT=0.0, VNNTOT=0.0, VNUDTOT=0.0, VTOT=0.0, CVIN=0.0, CVOUT=0.0, CDSTOR=0.0,
+               CERRAS=0.0, CAERAS=0.0)
+    kprt = 1
+    nprt, timprt = parm["NPRT"], parm["TIMPRT"]
+    last = None
+    while True:
+        t0 = time.perf_counter()
+        rep = sim.step()
+        res.wall_loop += time.perf_counter() - t0
+        res.gpu_ms += rep.gpu_ms
+        res.launches += rep.launches
+        last = rep
+        t1 = time.perf_counter()
+        cum["VSFTOT"] += rep.vsfflw
+        cum["VNDTOT"] += rep.vndin + rep.vndout
+        cum["VNNTOT"] += rep.vnnin + rep.vnnout
+        cum["VTOT"] += rep.vin + rep.vout
+        cum["CVIN"] += rep.vin
+        cum["CVOUT"] += rep.vout
+        cum["CDSTOR"] += rep.dstore
+        cum["CERRAS"] += rep.erras
+        cum["CAERAS"] += abs(rep.erras)
+        if keep_reports:
+            res.reports.append(dict(nstep=rep.nstep, deltat=rep.deltat, time=rep.time, iter=rep.iter,
+                                    nitert=rep.nitert, kbackt=rep.kbackt, nsurf=rep.nsurf, store1=rep.store1,
+                                    dstore=rep.dstore, vin=rep.vin, vout=rep.vout, erras=rep.erras, errel=rep.errel,
+                                    pinf=[rep.it[k].pinf for k in range(rep.n_iter_rec)],
+                                    niter=[rep.it[k].niter for k in range(rep.n_iter_rec)],
+                                    q_outlet=rep.q_outlet_1 + rep.q_outlet_2, gpu_ms=rep.gpu_ms))
+        if write_files:
+            # the reference prints one (NSTEP..) header per attempt; back-stepped attempts are not
+            # reported by the library, so only the accepted attempt is listed here
+            fh["iter"].write(O.iter_step_line(rep.nstep, rep.deltat, rep.time))
+            for k in range(rep.n_iter_rec):
+                fh["iter"].write(O.iter_line(k + 1, rep.it[k]))
+            fh["mbeconv"].write(O.mbeconv_line(
+                rep.nstep, rep.deltat, rep.time, rep.iter, float(rep.nitert) / float(rep.iter), rep.store1,
+                rep.store2, rep.dstore, cum["CDSTOR"], rep.vin, cum["CVIN"], rep.vout, cum["CVOUT"],
+                rep.vin + rep.vout, cum["VTOT"], rep.erras, rep.errel, cum["CERRAS"], cum["CAERAS"]))
+            fh["cumflowvol"].write(O.cumflowvol_line(rep.nstep, rep.deltat, rep.time, cum["VSFTOT"], cum["VNDTOT"],
+                                                     cum["VNNTOT"], cum["VNUDTOT"], cum["VTOT"]))
+            if parm["ISIMGR"] == 2:
+                fh["hgraph"].write("".join(O.fe(v, 16, 8) for v in (rep.time, rep.q_outlet_1, rep.q_outlet_2, 0.0, 0.0)) + "\n")
+        if verbose:
+            print(" TIME STEP: %6d  DELTAT: %12.4E  TIME: %12.4E  NL its %2d  lin its %4d  back-steps %d"
+                  % (rep.nstep, rep.deltat, rep.time, rep.iter, rep.nitert, rep.kbackt), flush=True)
+        if nprt > 0 and kprt <= nprt and rep.time >= timprt[kprt - 1]:
+            detout(rep.nstep, rep.time)
+            kprt += 1
+        res.wall_io += time.perf_counter() - t1
+        if rep.finished or (max_steps is not None and rep.nstep >= max_steps):
+            break
+    res.nstep = last.nstep
+    res.finished_ok = not bool(last.noback)
+    t1 = time.perf_counter()
+    if max_steps is None:
+        detout(last.nstep, parm["TMAX"])            # label 300: final DETOUT always carries TIME=TMAX
+    res.final_state = sim.state()
+    for f in fh.values():
+        f.close()
+    res.wall_io += time.perf_counter() - t1
+    sim.close()
+    return res
+
+
+def main(argv=None) -> int:
+    """Entry used by the `cathy` launcher script: no arguments, cwd = project directory."""
+    argv = sys.argv[1:] if argv is None else argv
+    prj_dir = argv[0] if argv else os.getcwd()
+    res = run_processor(prj_dir, verbose=True)
+    return 0 if res.finished_ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
