@@ -73,3 +73,15 @@ def run_reference(project_dir: str, workdir: str, which: str = "20x20x15", timeo
     with open(os.path.join(workdir, "stdout_ref.txt"), "w") as so:
         subprocess.run([exe], cwd=workdir, env=env, stdout=so, stderr=subprocess.STDOUT, timeout=timeout, check=False)
     return time.time() - t0
+
+
+def run_prepro(project_dir: str, timeout: float = 600.0) -> None:
+    """Run the reference's prebuilt pre-processor (oracle/_ref/bin/pycppp) in <project>/prepro so that
+    the surface-routing rasters (dtm_*, qoi_a) of an ISIMGR=2 project are the reference's own."""
+    exe = os.path.join(HERE, "_ref", "bin", "pycppp")
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.join(HERE, "_ref", "lib") + ":" + env.get("LD_LIBRARY_PATH", "")
+    p = subprocess.run([exe], cwd=os.path.join(project_dir, "prepro"), env=env, input="2\n0\n1\n", text=True,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout)
+    if not os.path.exists(os.path.join(project_dir, "prepro", "qoi_a")):
+        raise RuntimeError("pycppp failed:\n" + p.stdout[-2000:])

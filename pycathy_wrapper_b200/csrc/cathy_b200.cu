@@ -1,0 +1,1912 @@
+// cathy_b200.cu -- B200 (sm_100a) implementation of the CATHY Richards hot path.
+//
+// Boundary: include/cathy_b200.h.  Reference routines are cited per kernel as
+// SRC/<file>:<line> (SRC = pyCATHY/tests/weil_exemple/my_cathy_prj/src).
+//
+// Data layout: nodes are numbered layer-major like the reference
+// (k = layer*NNOD + s, SRC/gen3d.f:31-45), and the prism-split DEM mesh gives
+// every matrix row the same 15-point stencil, so the symmetric system matrix is
+// stored as 8 dense "upper" diagonals (offsets 0, 1, NC1, NC1+1, NNOD-NC1-1,
+// NNOD-NC1, NNOD-1, NNOD) -- a SELL/DIA layout with implicit column indices:
+// no index traffic, every load coalesced.  The element -> nonzero scatter map of
+// the reference (TETJA, SRC/tetpic.f) becomes a static, per-slot sorted gather
+// list, so assembly is atomic-free and deterministic.
+//
+// Everything numerical runs on the device; the host code in this file is the
+// control flow of the time step (BC stream bookkeeping, back-stepping, step
+// size control) and reads back a few dozen scalars per nonlinear iteration.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cathy_b200.h"
+
+namespace cg = cooperative_groups;
+
+#define RMAX_ 1.7e100
+#define NDIAG 8
+#define RED_BLOCK 256
+
+static thread_local char g_err[1024] = "";
+#define FAIL(code, ...)                          \
+    do {                                         \
+        snprintf(g_err, sizeof g_err, __VA_ARGS__); \
+        return (code);                           \
+    } while (0)
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) FAIL(-100, "CUDA error %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// device-side parameter blocks
+// ------------------------------------------------------------------------------------------
+struct Diag {           // the 8 upper diagonals of a symmetric matrix
+    double *d[NDIAG];   // d[0] = main diagonal
+    int off[NDIAG];
+};
+
+struct Soil {           // nodal van Genuchten constants (SRC/tpnodi.f, SRC/chparm.f:22-35)
+    const double *vgn, *vgm, *vgpsat, *vgpnot, *rr /* VGRMC/PNODI */, *snodi, *pnodi, *vgn1, *vgnr, *vgpsn, *vgmr;
+};
+
+// scalars that cross to the host once per nonlinear iteration
+struct IterOut {
+    double pl2, pinf, fl2, finf, pnew_ik, pold_ik, dstore;
+    double adin, adout, anin, anout, ndin, ndout;
+    double pcg_err;
+    int ikmax, pcg_niter, ponding, pad;
+};
+struct StepOut {        // once per accepted step
+    double store1, apot, aact, ovflow, reflow, q_out1, q_out2, ak_max;
+    int nhort, ndunn, npond, nsat, nsurf, hgflag[9], pad;
+};
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+// fixed-order block sum: every thread gets nothing, thread 0 gets the total
+template <int NT_>
+__device__ __forceinline__ double block_sum(double v, double *sh /* [32] */)
+{
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (w == 0) {
+        t = lane < (NT_ >> 5) ? sh[lane] : 0.0;
+        t = warp_sum(t);
+    }
+    return t;
+}
+
+// van Genuchten functions, SRC/fvgse.f:9-24, SRC/fvgkr.f, SRC/fvgdse.f (threshold psi < -1e-14)
+__device__ __forceinline__ double fvgse(double psi, double psat, double n, double m)
+{
+    if (psi < -1.0e-14) {
+        double beta = pow(fabs(psi / psat), n);
+        return pow(fabs(1.0 / (beta + 1.0)), m);
+    }
+    return 1.0;
+}
+__device__ __forceinline__ double fvgkr(double psi, double se, double m, double mr)
+{
+    if (psi < -1.0e-14) {
+        double omega = pow(fabs(se), mr);
+        double v1 = 1.0 - pow(fabs(1.0 - omega), m);
+        return sqrt(se) * v1 * v1;
+    }
+    return 1.0;
+}
+__device__ __forceinline__ double fvgdse(double psi, double psat, double n, double n1, double nr, double psn)
+{
+    if (psi < -1.0e-14) {
+        double beta = pow(fabs(psi / psat), n);
+        double b1 = beta + 1.0, b1r = 1.0 / b1;
+        return n1 * (pow(fabs(psi), n1) / psn) * pow(fabs(b1), nr) * b1r * b1r;
+    }
+    return 0.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: moisture curves per node (PICUNS -> CHPIC0, SRC/picuns.f:22-48, SRC/chpic0.f:23-36)
+// ------------------------------------------------------------------------------------------
+__global__ void k_curves(int n, Soil s, const double *__restrict__ ptnew, const double *__restrict__ pnew,
+                         const double *__restrict__ ptimep, int do_timep, double *__restrict__ sw,
+                         double *__restrict__ ckrw, double *__restrict__ et1, double *__restrict__ et2,
+                         double *__restrict__ swnew, double *__restrict__ swtimep)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double n_ = s.vgn[i], m = s.vgm[i], psat = s.vgpsat[i], pnot = s.vgpnot[i], rr = s.rr[i];
+        double psi = ptnew[i];
+        double se = fvgse(psi, psat, n_, m);
+        double w = pnot * se + rr;
+        double dse = fvgdse(psi, psat, n_, s.vgn1[i], s.vgnr[i], s.vgpsn[i]);
+        sw[i] = w;
+        et1[i] = w * s.snodi[i];
+        et2[i] = pnot * dse;
+        ckrw[i] = fvgkr(psi, se, m, s.vgmr[i]);
+        // PNEW can differ from PTNEW at ponded surface nodes even when TETAF = 1 (PONDUPD runs after WEIGHT)
+        double pn = pnew[i];
+        swnew[i] = pn == psi ? w : pnot * fvgse(pn, psat, n_, m) + rr;
+        if (do_timep) swtimep[i] = pnot * fvgse(ptimep[i], psat, n_, m) + rr;
+    }
+}
+// CHVELO (SRC/chvelo.f, IVGHU=0) fused with STORCAL's sum term (SRC/storcal.f)
+__global__ void k_chvelo(int n, Soil s, const double *__restrict__ psiv, const double *__restrict__ volnod,
+                         double *__restrict__ sw, double *__restrict__ ckrw, double *__restrict__ partial)
+{
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double psi = psiv[i], m = s.vgm[i];
+        double se = fvgse(psi, s.vgpsat[i], s.vgn[i], m);
+        double w = s.vgpnot[i] * se + s.rr[i];
+        sw[i] = w;
+        ckrw[i] = fvgkr(psi, se, m, s.vgmr[i]);
+        acc += w * volnod[i] * s.pnodi[i];
+    }
+    double t = block_sum<RED_BLOCK>(acc, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: node -> element averages (NODELT, SRC/nodelt.f:19-26) of kr and ET1
+// ------------------------------------------------------------------------------------------
+__global__ void k_tet_avg(int nt, const int4 *__restrict__ tet, const double *__restrict__ ckrw,
+                          const double *__restrict__ et1, double *__restrict__ krt, double *__restrict__ e1t)
+{
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nt; e += gridDim.x * blockDim.x) {
+        int4 t = tet[e];
+        krt[e] = (((ckrw[t.x] + ckrw[t.y]) + ckrw[t.z]) + ckrw[t.w]) * 0.25;
+        e1t[e] = (((et1[t.x] + et1[t.y]) + et1[t.z]) + et1[t.w]) * 0.25;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: atomic-free assembly (ASSPIC, SRC/asspic.f:26-51; RHSGRV, SRC/rhsgrv.f:20-30).
+// Every matrix slot owns a static list of (tet, coefficient) pairs sorted by tet, i.e. the
+// reference's TETJA scatter turned into a gather; the sum runs in the reference's element order.
+// ------------------------------------------------------------------------------------------
+__global__ void k_assemble(long long nslots, const int *__restrict__ ptr, const int *__restrict__ ctet,
+                           const double *__restrict__ coef, const double *__restrict__ krt, double *__restrict__ out)
+{
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += (long long)gridDim.x * blockDim.x) {
+        int b = ptr[s], e = ptr[s + 1];
+        double acc = 0.0;
+        for (int c = b; c < e; ++c) acc += krt[ctet[c]] * coef[c];
+        out[s] = acc;
+    }
+}
+__global__ void k_assemble_nodes(int n, const int *__restrict__ ptr, const int *__restrict__ ctet,
+                                 const double *__restrict__ gcoef, const double *__restrict__ mcoef,
+                                 const double *__restrict__ krt, const double *__restrict__ e1t,
+                                 double *__restrict__ grav, double *__restrict__ m2)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        int b = ptr[k], e = ptr[k + 1];
+        double g = 0.0, m = 0.0;
+        for (int c = b; c < e; ++c) {
+            int t = ctet[c];
+            g += krt[t] * gcoef[c];
+            m += e1t[t] * mcoef[c];
+        }
+        grav[k] = g;
+        m2[k] = m;
+    }
+}
+
+// symmetric DIA row product: (A x)_k from the 8 upper diagonals
+__device__ __forceinline__ double dia_row(const Diag &A, const double *__restrict__ diag0, const double *__restrict__ x, int k, int n)
+{
+    double acc = diag0[k] * x[k];
+#pragma unroll
+    for (int d = 1; d < NDIAG; ++d) {
+        int j = k + A.off[d];
+        if (j < n) acc += A.d[d][k] * x[j];
+    }
+#pragma unroll
+    for (int d = 1; d < NDIAG; ++d) {
+        int j = k - A.off[d];
+        if (j >= 0) acc += A.d[d][j] * x[j];
+    }
+    return acc;
+}
+
+__device__ __forceinline__ bool is_dirichlet(int k, int nnod, const int *__restrict__ ifatm, const unsigned char *__restrict__ contp_flag)
+{
+    if (contp_flag && contp_flag[k]) return true;
+    if (k < nnod) { int f = ifatm[k]; return f == 1 || f == 2; }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: RHS + LHS diagonal + boundary conditions in one pass
+// (RHSPIC SRC/rhspic.f:22-38, CFMATP SRC/cfmatp.f:21-26, RHSGRV, BCPIC SRC/bcpic.f:33-86)
+// ------------------------------------------------------------------------------------------
+__global__ void k_rhs_lhs(int n, int nnod, Diag A, double tetaf, double rdt, const double *__restrict__ ptnew,
+                          const double *__restrict__ pnew, const double *__restrict__ ptimep,
+                          const double *__restrict__ swnew, const double *__restrict__ swtimep,
+                          const double *__restrict__ m2, const double *__restrict__ m4, const double *__restrict__ et2,
+                          const double *__restrict__ grav, const int *__restrict__ ifatm,
+                          const unsigned char *__restrict__ contp_flag, const double *__restrict__ qneu,
+                          const double *__restrict__ atmact, const double *__restrict__ atmold,
+                          const double *__restrict__ qtranie, double *__restrict__ rhs, double *__restrict__ xt5,
+                          double *__restrict__ diag_true, double *__restrict__ diag_bc)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        double ax = dia_row(A, A.d[0], ptnew, k, n);
+        double b = -ax - m2[k] * rdt * (pnew[k] - ptimep[k]) - m4[k] * rdt * (swnew[k] - swtimep[k]) - grav[k];
+        xt5[k] = b;
+        double dt_ = tetaf * A.d[0][k] + m2[k] * rdt + (m4[k] * et2[k]) * rdt;
+        diag_true[k] = dt_;
+        bool dir = is_dirichlet(k, nnod, ifatm, contp_flag);
+        if (dir) b = 0.0;
+        if (qneu) b += qneu[k];
+        if (k < nnod && ifatm[k] == 0) b = b + (tetaf * atmact[k] + (1.0 - tetaf) * atmold[k]);
+        b = b - qtranie[k];
+        rhs[k] = b;
+        diag_bc[k] = dir ? 1.0e-9 * RMAX_ : dt_;
+    }
+}
+__global__ void k_scale(long long n, double a, double *__restrict__ v)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) v[i] *= a;
+}
+
+// plain SpMV y = A x (used by cathy_debug_spmv and the roofline measurement)
+__global__ void k_spmv(int n, Diag A, const double *__restrict__ diag0, const double *__restrict__ x, double *__restrict__ y)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) y[k] = dia_row(A, diag0, x, k, n);
+}
+
+// ------------------------------------------------------------------------------------------
+// K5-K7: the whole SYMSLV (SRC/solscal-extended.f:4669-4699) as ONE persistent cooperative
+// kernel: preconditioner set-up, x0 = M^-1 b, and the GRADDP recurrence (:1260-1380) with two
+// grid-wide barriers per iteration.  Reductions are fixed-order (block partials, then every block
+// adds the partials in the same order), so results are bit-reproducible run to run.
+//   phase A: p = z + beta p_old (recomputed on the fly for the neighbours), B = A p, (p.r), (p.B)
+//   phase B: r -= alfa B, x += alfa p, z = M^-1 r, (B.z), ||r_free||^2
+// Residual norm excludes Dirichlet rows exactly like GRADDP (:1286-1297, :1356-1371).
+// ------------------------------------------------------------------------------------------
+struct PcgArgs {
+    int n, nnod, itmax;
+    double tol;
+    Diag A;
+    const double *diag;      // main diagonal with the Dirichlet penalty
+    const double *rhs;
+    double *x, *r, *z, *p0, *p1, *bv;
+    const int *ifatm;
+    const unsigned char *contp_flag;
+    double *partial;         // [3][gridDim.x]
+    IterOut *out;
+};
+
+__device__ __forceinline__ void grid_reduce3(cg::grid_group &grid, double a, double b, double c, double *partial, double *sh, double &ra, double &rb, double &rc)
+{
+    int nb = gridDim.x;
+    double ta = block_sum<RED_BLOCK>(a, sh);
+    double tb = block_sum<RED_BLOCK>(b, sh);
+    double tc = block_sum<RED_BLOCK>(c, sh);
+    if (threadIdx.x == 0) { partial[blockIdx.x] = ta; partial[nb + blockIdx.x] = tb; partial[2 * nb + blockIdx.x] = tc; }
+    grid.sync();
+    // every block sums all partials in the same order (warp 0..2 take one quantity each)
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (w < 3) {
+        double s = 0.0;
+        for (int i = lane; i < nb; i += 32) s += partial[w * nb + i];
+        s = warp_sum(s);
+        if (lane == 0) sh[w] = s;
+    }
+    __syncthreads();
+    ra = sh[0]; rb = sh[1]; rc = sh[2];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(RED_BLOCK) k_pcg(PcgArgs a)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[32];
+    const int n = a.n, stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    // x0 = M^-1 b ; xlung = ||b_free||^2   (PRODDP call at :4686, XLUNG at :1286-1297)
+    double xl = 0.0;
+    for (int k = t0; k < n; k += stride) {
+        double b = a.rhs[k];
+        a.x[k] = b / a.diag[k];
+        if (!is_dirichlet(k, a.nnod, a.ifatm, a.contp_flag)) xl += b * b;
+    }
+    double xlung, d1, d2;
+    grid_reduce3(grid, xl, 0.0, 0.0, a.partial, sh, xlung, d1, d2);
+    // r = b - A x0 ; z = M^-1 r ; p_old = 0 so that p = z in the first phase A
+    for (int k = t0; k < n; k += stride) {
+        double r = a.rhs[k] - dia_row(a.A, a.diag, a.x, k, n);
+        a.r[k] = r;
+        a.z[k] = r / a.diag[k];
+        a.p0[k] = 0.0;
+    }
+    grid.sync();
+    double beta = 0.0, err = 0.0;
+    double *pold = a.p0, *pnew = a.p1;
+    int niter = 1;
+    for (;;) {
+        // ---- phase A
+        double s_pr = 0.0, s_pb = 0.0;
+        for (int k = t0; k < n; k += stride) {
+            double pk = a.z[k] + beta * pold[k];
+            double acc = a.diag[k] * pk;
+#pragma unroll
+            for (int d = 1; d < NDIAG; ++d) {
+                int j = k + a.A.off[d];
+                if (j < n) acc += a.A.d[d][k] * (a.z[j] + beta * pold[j]);
+            }
+#pragma unroll
+            for (int d = 1; d < NDIAG; ++d) {
+                int j = k - a.A.off[d];
+                if (j >= 0) acc += a.A.d[d][j] * (a.z[j] + beta * pold[j]);
+            }
+            pnew[k] = pk;
+            a.bv[k] = acc;
+            s_pr += pk * a.r[k];
+            s_pb += pk * acc;
+        }
+        double pr, pb;
+        grid_reduce3(grid, s_pr, s_pb, 0.0, a.partial, sh, pr, pb, d1);
+        double alfa = pr / pb;
+        // ---- phase B
+        double s_bz = 0.0, s_rr = 0.0;
+        for (int k = t0; k < n; k += stride) {
+            double bk = a.bv[k];
+            double r = a.r[k] - alfa * bk;
+            a.r[k] = r;
+            a.x[k] = a.x[k] + alfa * pnew[k];
+            double z = r / a.diag[k];
+            a.z[k] = z;
+            s_bz += bk * z;
+            if (!is_dirichlet(k, a.nnod, a.ifatm, a.contp_flag)) s_rr += r * r;
+        }
+        double bz, rr;
+        grid_reduce3(grid, s_bz, s_rr, 0.0, a.partial, sh, bz, rr, d1);
+        beta = -bz / pb;
+        err = xlung > 0.0 ? sqrt(rr / xlung) : sqrt(rr / n);
+        double *t = pold; pold = pnew; pnew = t;
+        if (err > a.tol && niter < a.itmax) { ++niter; continue; }
+        break;
+    }
+    if (t0 == 0) { a.out->pcg_niter = niter; a.out->pcg_err = err; }
+}
+
+// ------------------------------------------------------------------------------------------
+// after the solve: PNEW += PDIFF and SHLPIC's Dirichlet reset (SRC/picard.f:185-198, SRC/shlpic.f:30-56)
+// ------------------------------------------------------------------------------------------
+__global__ void k_update(int n, int nnod, const double *__restrict__ pdiff, const double *__restrict__ pold,
+                         const int *__restrict__ ifatm, const unsigned char *__restrict__ contp_flag,
+                         const double *__restrict__ contp_val, double *__restrict__ pnew)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        double v = pnew[k] + pdiff[k];
+        if (contp_flag && contp_flag[k]) v = contp_val[k];
+        if (k < nnod) { int f = ifatm[k]; if (f == 1 || f == 2) v = pold[k]; }
+        pnew[k] = v;
+    }
+}
+
+// back-calculated fluxes at atmospheric Dirichlet nodes (BKPIC, SRC/bkpic.f:27-53): only the rows
+// that are read afterwards are formed, i.e. one 15-point row product per Dirichlet node.
+__global__ void k_bkflux(int n, int nnod, Diag A, const double *__restrict__ diag_true, const double *__restrict__ pdiff,
+                         const double *__restrict__ xt5, const int *__restrict__ ifatm, double tetaf,
+                         const double *__restrict__ atmold, double *__restrict__ atmact)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nnod; k += gridDim.x * blockDim.x) {
+        int f = ifatm[k];
+        if (f == 1 || f == 2) {
+            double scr = dia_row(A, diag_true, pdiff, k, n) - xt5[k];
+            atmact[k] = (scr - (1.0 - tetaf) * atmold[k]) * (1.0 / tetaf);
+        }
+    }
+}
+
+// norms (NORMS, SRC/norms.f:18-38) + storage change (STORMB, SRC/stormb.f) block partials
+struct NormPartial { double pl2, fl2, dstore, pinf, finf; int ik; int pad; };
+__global__ void k_norms(int n, const double *__restrict__ pnew, const double *__restrict__ pold,
+                        const double *__restrict__ rhs, const double *__restrict__ ptimep,
+                        const double *__restrict__ swnew, const double *__restrict__ swtimep,
+                        const double *__restrict__ volnod, const double *__restrict__ snodi,
+                        const double *__restrict__ pnodi, NormPartial *__restrict__ part)
+{
+    __shared__ double sh[32];
+    __shared__ double shv[RED_BLOCK / 32];
+    __shared__ int shi[RED_BLOCK / 32];
+    double pl2 = 0, fl2 = 0, ds = 0, pinf = 0, finf = 0;
+    int ik = 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        double d = pnew[k] - pold[k], da = fabs(d), f = rhs[k];
+        pl2 += d * d;
+        fl2 += f * f;
+        if (da > pinf || (da == pinf && k >= ik)) { pinf = da; ik = k; }
+        finf = fmax(finf, fabs(f));
+        ds += volnod[k] * (snodi[k] * (swnew[k] + swtimep[k]) * 0.5 * (pnew[k] - ptimep[k]) + pnodi[k] * (swnew[k] - swtimep[k]));
+    }
+    double t1 = block_sum<RED_BLOCK>(pl2, sh), t2 = block_sum<RED_BLOCK>(fl2, sh), t3 = block_sum<RED_BLOCK>(ds, sh);
+    // max reductions (ties -> larger index, i.e. the LAST node like the sequential >= test)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_down_sync(0xffffffffu, pinf, o);
+        int oi = __shfl_down_sync(0xffffffffu, ik, o);
+        double of = __shfl_down_sync(0xffffffffu, finf, o);
+        if (ov > pinf || (ov == pinf && oi > ik)) { pinf = ov; ik = oi; }
+        finf = fmax(finf, of);
+    }
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) { shv[w] = pinf; shi[w] = ik; sh[w] = finf; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < RED_BLOCK / 32; ++q) {
+            if (shv[q] > pinf || (shv[q] == pinf && shi[q] > ik)) { pinf = shv[q]; ik = shi[q]; }
+            finf = fmax(finf, sh[q]);
+        }
+        NormPartial p;
+        p.pl2 = t1; p.fl2 = t2; p.dstore = t3; p.pinf = pinf; p.finf = finf; p.ik = ik; p.pad = 0;
+        part[blockIdx.x] = p;
+    }
+}
+// final fixed-order reduction + boundary flux sums (FLUXMB, SRC/fluxmb.f:29-88), one block
+__global__ void k_norms_final(int nb, const NormPartial *__restrict__ part, int nnod, const int *__restrict__ ifatm,
+                              const double *__restrict__ atmact, const double *__restrict__ pnew,
+                              const double *__restrict__ pold, IterOut *__restrict__ out)
+{
+    __shared__ double sh[32];
+    __shared__ double shv[RED_BLOCK / 32];
+    __shared__ int shi[RED_BLOCK / 32];
+    double pl2 = 0, fl2 = 0, ds = 0, pinf = 0, finf = 0;
+    int ik = 0;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        NormPartial p = part[b];
+        pl2 += p.pl2; fl2 += p.fl2; ds += p.dstore;
+        if (p.pinf > pinf || (p.pinf == pinf && p.ik > ik)) { pinf = p.pinf; ik = p.ik; }
+        finf = fmax(finf, p.finf);
+    }
+    double adin = 0, adout = 0, anin = 0, anout = 0;
+    for (int k = threadIdx.x; k < nnod; k += blockDim.x) {
+        int f = ifatm[k];
+        if (f == -1) continue;
+        double a = atmact[k];
+        if (f == 1 || f == 2) { if (a > 0.0) adin += a; else adout += a; }
+        else { if (a > 0.0) anin += a; else anout += a; }
+    }
+    double t1 = block_sum<RED_BLOCK>(pl2, sh), t2 = block_sum<RED_BLOCK>(fl2, sh), t3 = block_sum<RED_BLOCK>(ds, sh);
+    double t4 = block_sum<RED_BLOCK>(adin, sh), t5 = block_sum<RED_BLOCK>(adout, sh), t6 = block_sum<RED_BLOCK>(anin, sh), t7 = block_sum<RED_BLOCK>(anout, sh);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_down_sync(0xffffffffu, pinf, o);
+        int oi = __shfl_down_sync(0xffffffffu, ik, o);
+        double of = __shfl_down_sync(0xffffffffu, finf, o);
+        if (ov > pinf || (ov == pinf && oi > ik)) { pinf = ov; ik = oi; }
+        finf = fmax(finf, of);
+    }
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) { shv[w] = pinf; shi[w] = ik; sh[w] = finf; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < RED_BLOCK / 32; ++q) {
+            if (shv[q] > pinf || (shv[q] == pinf && shi[q] > ik)) { pinf = shv[q]; ik = shi[q]; }
+            finf = fmax(finf, sh[q]);
+        }
+        out->pl2 = sqrt(t1); out->fl2 = sqrt(t2); out->dstore = t3; out->pinf = pinf; out->finf = finf;
+        out->ikmax = ik; out->pnew_ik = pnew[ik]; out->pold_ik = pold[ik];
+        out->adin = t4; out->adout = t5; out->anin = t6; out->anout = t7; out->ndin = 0.0; out->ndout = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// atmospheric boundary condition state machine per surface node
+// ------------------------------------------------------------------------------------------
+// SWITCH (SRC/switch.f), condensed branch for branch; sets the PONDING flag through *ponding
+__global__ void k_switch(int nnod, double deltat, double pmin, double ph, const double *__restrict__ arenod,
+                         const double *__restrict__ pondnod, const double *__restrict__ atmpot,
+                         const double *__restrict__ qtranie, int *__restrict__ ifatm, double *__restrict__ atmact,
+                         double *__restrict__ pnew, double *__restrict__ ovfl, int *__restrict__ ponding)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnod; i += gridDim.x * blockDim.x) {
+        int f = ifatm[i];
+        if (f == -1) { ovfl[i] = 0.0; continue; }
+        double pot = atmpot[i], act = atmact[i];
+        double atmdif = pot - (act - qtranie[i]);
+        if (fabs(atmdif) < 1.0e-14) atmdif = 0.0;
+        double pl = pondnod[i] + (atmdif * deltat / arenod[i]);
+        double drain = -pondnod[i] * arenod[i] / deltat;
+        if (f == 2 || f == 1) {
+            bool rain = pot >= 0.0, infl = act >= 0.0;
+            if (f == 1 && !rain) {
+                if (infl) { if (pnew[i] <= pmin) continue; }
+                else if (pnew[i] <= pmin) {
+                    if (act < pot) { ifatm[i] = 0; atmact[i] = pot; pnew[i] = pmin; ovfl[i] = 0.0; }
+                    continue;
+                }
+            }
+            if (pl >= ph) { *ponding = 1; ifatm[i] = 2; pnew[i] = pl; ovfl[i] = atmdif; continue; }
+            if (pl >= 0.0) { ifatm[i] = 1; ovfl[i] = atmdif; if (f == 2 && !rain) pnew[i] = 0.0; continue; }
+            if (rain && !infl) { ifatm[i] = 1; ovfl[i] = atmdif; continue; }
+            ifatm[i] = 0; atmact[i] = pot;
+            if (f == 2 && !rain && pl > pmin) pnew[i] = 0.0;
+            ovfl[i] = drain;
+            continue;
+        }
+        if (f == 0) {
+            double pn = pnew[i];
+            if (pn >= ph) { *ponding = 1; ifatm[i] = 2; ovfl[i] = (pn - pondnod[i]) * arenod[i] / deltat; }
+            else if (pn >= 0.0) { ifatm[i] = 1; ovfl[i] = (pn - pondnod[i]) * arenod[i] / deltat; }
+            else if (pn > pmin) { ifatm[i] = 0; ovfl[i] = drain; }
+            else { ifatm[i] = 1; pnew[i] = pmin; ovfl[i] = drain; }
+        }
+    }
+}
+// SWITCH_OLD (SRC/switch_old.f), subsurface-only runs
+__global__ void k_switch_old(int nnod, double pmin, const double *__restrict__ atmpot, int *__restrict__ ifatm,
+                             double *__restrict__ atmact, double *__restrict__ pnew)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnod; i += gridDim.x * blockDim.x) {
+        int f = ifatm[i];
+        if (f == -1) continue;
+        double pot = atmpot[i], act = atmact[i], pn = pnew[i];
+        if (f == 1 && pn >= 0.0 && (pot < 0.0 || act > pot)) { ifatm[i] = 0; atmact[i] = pot; continue; }
+        if (f == 1 && pn <= pmin && (pot > 0.0 || act < pot)) { ifatm[i] = 0; atmact[i] = pot; continue; }
+        if (f == 0 && pn >= 0.0 && pot >= 0.0) { ifatm[i] = 1; pnew[i] = 0.0; continue; }
+        if (f == 0 && pn <= pmin && pot < 0.0) { ifatm[i] = 1; pnew[i] = pmin; continue; }
+    }
+}
+// ADRSTN (SRC/adrstn.f)
+__global__ void k_adrstn(int nnod, double pmin, const double *__restrict__ atmpot, int *__restrict__ ifatm,
+                         double *__restrict__ atmact, double *__restrict__ pnew)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnod; i += gridDim.x * blockDim.x)
+        if (pnew[i] <= pmin && (atmpot[i] > 0.0 || atmact[i] < atmpot[i])) { ifatm[i] = 0; atmact[i] = atmpot[i]; pnew[i] = pmin; }
+}
+// PONDUPD (SRC/pondupd.f) -- *ponding must be zeroed before the launch
+__global__ void k_pondupd(int nnod, double ph, double dtr, const double *__restrict__ pondnod,
+                          const double *__restrict__ arenod, const double *__restrict__ atmpot,
+                          const int *__restrict__ ifatm, double *__restrict__ atmact, double *__restrict__ pnew,
+                          int *__restrict__ ponding)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnod; i += gridDim.x * blockDim.x) {
+        int f = ifatm[i];
+        if (f == -1) continue;
+        if (pondnod[i] >= ph) {
+            if (f == 1 || f == 2) { pnew[i] = pondnod[i]; *ponding = 1; }
+            else if (f == 0) { *ponding = 1; atmact[i] = atmpot[i] + pondnod[i] * arenod[i] * dtr; }
+        }
+    }
+}
+// ATMNXT / ATMBAK interpolation (SRC/atmnxt.f:46-75, SRC/atmbak.f): values of two table slots
+__global__ void k_atm_interp(int nnod, const double *__restrict__ tab, int stride, int rec_a, int rec_b, int use_b_only,
+                             double ta, double tb, double time, int ieto, double scf, const double *__restrict__ arenod,
+                             const int *__restrict__ ifatm, int set_act, double *__restrict__ atmpot,
+                             double *__restrict__ atmact)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnod; i += gridDim.x * blockDim.x) {
+        double va = rec_a >= 0 ? tab[(size_t)rec_a * stride * nnod + (stride ? i : 0)] : 0.0;
+        double vb = rec_b >= 0 ? tab[(size_t)rec_b * stride * nnod + (stride ? i : 0)] : 0.0;
+        double pot;
+        if (use_b_only) pot = vb * arenod[i];
+        else {
+            double slope = (vb - va) / (tb - ta);
+            if (ieto != 0) slope = 0.0;
+            pot = (va + slope * (time - ta)) * arenod[i];
+        }
+        atmpot[i] = pot;
+        if (set_act && ifatm[i] == 0) atmact[i] = pot >= 0.0 ? pot : (1.0 - scf) * pot;
+    }
+}
+// ETRAN (SRC/etran.f): Feddes root water uptake, one thread per surface column
+__global__ void k_etran(int nnod, int nstr, const double *__restrict__ z, const double *__restrict__ psi,
+                        const double *__restrict__ atmpot, const int *__restrict__ veg, const double *__restrict__ vegpar /* [nveg][6] */,
+                        double scf, double *__restrict__ qtranie, int *__restrict__ errflag)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnod; i += gridDim.x * blockDim.x) {
+        const double *vp = vegpar + 6 * veg[i];
+        double pcana = vp[0], pcref = vp[1], pcwlt = vp[2], zroot = vp[3], pz = vp[4], omgc = vp[5];
+        double etp = atmpot[i] < 0.0 ? -1.0 * scf * atmpot[i] : 0.0;
+        double zsurf = z[i], depth = 0.0, btran = 0.0, omg = 0.0;
+        int j = 1;
+        for (int l = 0; l <= nstr; ++l) qtranie[(size_t)l * nnod + i] = 0.0;
+        while (depth <= zroot) {
+            size_t k = (size_t)(j - 1) * nnod + i;
+            if (j > nstr) { *errflag = 1; break; }
+            double s1 = pcana, s2 = pcana + 1.0e-3;
+            double dz = j == 1 ? (zsurf - z[k + nnod]) / 2.0 : (z[k - nnod] - z[k + nnod]) / 2.0;
+            double sh = psi[k];
+            double gx1 = fmin(1.0, fmax(0.0, (sh - pcwlt) / (pcref - pcwlt)));
+            double gx2 = fmin(1.0, fmax(0.0, 1.0 - (sh - s1) / (s2 - s1)));
+            double gx = fmin(gx1, gx2);
+            double beta = (1 - depth / zroot) * exp(-1.0 * pz * depth / zroot);
+            qtranie[k] = fmax(0.0, beta * dz * gx);   // BTRANI for now
+            btran = btran + beta * dz;
+            omg = omg + gx * beta * dz;
+            ++j;
+            depth = zsurf - z[(size_t)(j - 1) * nnod + i];
+        }
+        btran = fmax(0.0, btran);
+        omg = omg / btran;
+        double den = fmax(omg, omgc);
+        for (int l = 0; l <= nstr; ++l) {
+            size_t k = (size_t)l * nnod + i;
+            qtranie[k] = etp * qtranie[k] / btran / den;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// surface routing (SURF_FLOWTRA, SRC/surf_flowtra.f:38-196)
+// ------------------------------------------------------------------------------------------
+// NOD_CELL + TRANSFER_F3D_SURF (SRC/nod_cell.f, SRC/transfer_f3d_surf.f); OVFLNOD is divided by the
+// nodal area IN PLACE first (separate launch), exactly as the reference does.
+__global__ void k_div_area(int nnod, const double *__restrict__ arenod, double *__restrict__ ovfl)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnod; i += gridDim.x * blockDim.x) ovfl[i] = ovfl[i] / arenod[i];
+}
+__global__ void k_nod_cell(int nrow, int ncol, double dx, double dy, const double *__restrict__ ovfl, double *__restrict__ sw_sn)
+{
+    int ncell = nrow * ncol, nc1 = ncol + 1;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += gridDim.x * blockDim.x) {
+        int i = c / ncol, j = c - i * ncol;
+        int n00 = i * nc1 + j, n10 = n00 + nc1, n11 = n10 + 1, n01 = n00 + 1;
+        double cc = 0.0;
+        cc = cc + ovfl[n00]; cc = cc + ovfl[n10]; cc = cc + ovfl[n11]; cc = cc + ovfl[n01];
+        cc = cc * 0.25;
+        int jr = nrow - 1 - i;                 // row counted from the south
+        sw_sn[j * nrow + jr] = cc * dx * dy;   // routing index (I-1)*NROW+J
+    }
+}
+// CELL_NOD + TRANSFER_SURF_F3D (SRC/cell_nod.f, SRC/transfer_surf_f3d.f): ponding head per node =
+// mean over the adjacent triangles, accumulated in triangle order
+__global__ void k_cell_nod(int nrow, int ncol, const double *__restrict__ h_sn, double *__restrict__ pondnod)
+{
+    int nc1 = ncol + 1, nnod = (nrow + 1) * nc1;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nnod; s += gridDim.x * blockDim.x) {
+        int i = s / nc1, j = s - i * nc1;
+        double acc = 0.0;
+        int cnt = 0;
+        auto cellv = [&](int ci, int cj) { return h_sn[cj * nrow + (nrow - 1 - ci)]; };
+        if (i > 0 && j > 0) { double v = cellv(i - 1, j - 1); acc = acc + v; acc = acc + v; cnt += 2; }
+        if (i > 0 && j < ncol) { acc = acc + cellv(i - 1, j); cnt += 1; }
+        if (i < nrow && j > 0) { acc = acc + cellv(i, j - 1); cnt += 1; }
+        if (i < nrow && j < ncol) { double v = cellv(i, j); acc = acc + v; acc = acc + v; cnt += 2; }
+        pondnod[s] = acc / cnt;
+    }
+}
+
+struct RouteArgs {
+    int ncell, nlevel;
+    const int *level_ptr;     // [nlevel+1] cells grouped by drainage level (level-scheduled tree)
+    const int *level_cell;    // [ncell] routing index I_BASIN (0-based)
+    const int *seq;           // [ncell] position of the cell in QOI order (for the AK_MAX tie rule)
+    const int *don_ptr;       // [ncell+1] donors of each cell in QOI order
+    const int *don_cell;      // donor routing index
+    const unsigned char *don_dir; // 0: donor's direction-1 outflow, 1: direction-2
+    const double *w1, *w2, *sl1, *sl2, *epl1, *epl2, *ks1, *ks2, *ws1, *ws2, *b1, *y1, *nrc;
+    double *sw_sn, *q_in_kk, *q_in_kkp1, *q_out_kk_1, *q_out_kk_2, *q_out_kkp1_1, *q_out_kkp1_2;
+    double *volume_kk, *volume_kkp1, *h_water;
+    double *ak_max;           // in/out
+    int *nsurf_out;
+    double deltat, cellarea;
+};
+// Muskingum-Cunge for one cell and direction (MC, SRC/mc.f)
+__device__ __forceinline__ double mc_cell(double slope, double epl, double ks, double w, double b1, double y1, double dt,
+                                          double q_in_kk, double q_in_kkp1, double q_out_kk, double q_over, double &cu, double &ak)
+{
+    double qc = 1.0 / 3.0 * (q_in_kk + q_in_kkp1 + q_out_kk);
+    if (qc <= 1.0e-05) qc = 1.0e-05;
+    double beta = atan(slope);
+    double g = (1.0 - y1 + 2.0 / 3.0 * b1);
+    double ck = 5.0 / (3.0 * g) * pow(ks, 3.0 / 5.0) * pow(w, -2.0 / 5.0) * pow(sin(beta), 3.0 / 1.0e1) * pow(qc, 1.0 - 3.0 * g / 5.0);
+    ak = ck / epl;
+    cu = ck * dt / epl;
+    double dh = pow(qc, 1.0 - b1) / (2 * g * w * tan(beta));
+    if (dh < (1.0 - cu)) dh = 1.0 - cu;
+    double xx = 0.50 - dh / (ck * epl);
+    double den = 2.0 * (1.0 - xx) + cu;
+    double c1 = (cu - 2.0 * xx) / den, c2 = (cu + 2.0 * xx) / den, c3 = (2.0 * (1.0 - xx) - cu) / den, c4 = (2.0 * ck * dt) / den;
+    return c1 * q_in_kkp1 + c2 * q_in_kk + c3 * q_out_kk + c4 * q_over;
+}
+// All NSURF sub-steps of ROUTE + ALTEZZE (SRC/route.f:47-253, SRC/altezze.f) in ONE launch of one CTA:
+// cells are processed level by level down the drainage tree (a cell's inflow is the ordered sum of its
+// donors' outflows, so the result equals the reference's sequential descending-elevation sweep).
+__global__ void __launch_bounds__(1024) k_route(RouteArgs a)
+{
+    __shared__ double s_cu[32], s_ak[32];
+    __shared__ int s_seq[32];
+    __shared__ double s_akmax;
+    __shared__ int s_nsurf;
+    __shared__ double s_dt;
+    if (threadIdx.x == 0) {
+        double akm = *a.ak_max, cu_max = akm * a.deltat, dts;
+        int ns;
+        if (cu_max > 1.0) { dts = 1.0 / akm; ns = (int)(a.deltat / dts) + 1; dts = a.deltat / ns; }
+        else { dts = a.deltat; ns = 1; }
+        s_nsurf = ns; s_dt = dts; s_akmax = akm;
+    }
+    __syncthreads();
+    const int nsurf = s_nsurf;
+    const double dt = s_dt;
+    for (int sub = 1; sub <= nsurf; ++sub) {
+        double best_cu = -1.0, best_ak = 0.0;
+        int best_seq = -1;
+        for (int lv = 0; lv < a.nlevel; ++lv) {
+            for (int q = a.level_ptr[lv] + threadIdx.x; q < a.level_ptr[lv + 1]; q += blockDim.x) {
+                int ib = a.level_cell[q];
+                double qin = 0.0;
+                for (int dn = a.don_ptr[ib]; dn < a.don_ptr[ib + 1]; ++dn)
+                    qin = qin + (a.don_dir[dn] ? a.q_out_kkp1_2[a.don_cell[dn]] : a.q_out_kkp1_1[a.don_cell[dn]]);
+                a.q_in_kkp1[ib] = qin;
+                double nrc = a.nrc[ib], swv = a.sw_sn[ib] / nrc;
+#pragma unroll
+                for (int dir = 0; dir < 2; ++dir) {
+                    double w = dir ? a.w2[ib] : a.w1[ib];
+                    double *qo_kkp1 = dir ? a.q_out_kkp1_2 : a.q_out_kkp1_1;
+                    if (w == 0.0) continue;
+                    double epl = dir ? a.epl2[ib] : a.epl1[ib];
+                    double q_over = swv * w * (1.0 / epl);
+                    double q_in_kk = a.q_in_kk[ib] * w / nrc, q_out_kk = (dir ? a.q_out_kk_2[ib] : a.q_out_kk_1[ib]) / nrc;
+                    double q_in_kkp1 = qin * w / nrc, cu, ak;
+                    double qo = mc_cell(dir ? a.sl2[ib] : a.sl1[ib], epl, dir ? a.ks2[ib] : a.ks1[ib], dir ? a.ws2[ib] : a.ws1[ib],
+                                        a.b1[ib], a.y1[ib], dt, q_in_kk, q_in_kkp1, q_out_kk, q_over, cu, ak);
+                    if (qo < 0.0) qo = 0.0;
+                    qo_kkp1[ib] = qo * nrc;
+                    int sq = 2 * a.seq[ib] + dir;
+                    if (cu > best_cu || (cu == best_cu && sq > best_seq)) { best_cu = cu; best_ak = ak; best_seq = sq; }
+                }
+            }
+            __syncthreads();
+        }
+        // AK_MAX = celerity of the LAST cell (in sequential order) attaining the max Courant number
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double oc = __shfl_down_sync(0xffffffffu, best_cu, o), oa = __shfl_down_sync(0xffffffffu, best_ak, o);
+            int os = __shfl_down_sync(0xffffffffu, best_seq, o);
+            if (oc > best_cu || (oc == best_cu && os > best_seq)) { best_cu = oc; best_ak = oa; best_seq = os; }
+        }
+        int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (lane == 0) { s_cu[wid] = best_cu; s_ak[wid] = best_ak; s_seq[wid] = best_seq; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int q = 1; q < (int)(blockDim.x >> 5); ++q)
+                if (s_cu[q] > best_cu || (s_cu[q] == best_cu && s_seq[q] > best_seq)) { best_cu = s_cu[q]; best_ak = s_ak[q]; best_seq = s_seq[q]; }
+            if (best_seq >= 0) s_akmax = best_ak;
+        }
+        // ALTEZZE: volume balance and water depth per cell
+        for (int c = threadIdx.x; c < a.ncell; c += blockDim.x) {
+            double dv = (a.q_in_kk[c] + a.q_in_kkp1[c]) / 2 * dt + a.sw_sn[c] * dt - (a.q_out_kk_1[c] + a.q_out_kk_2[c]) / 2 * dt
+                        - (a.q_out_kkp1_1[c] + a.q_out_kkp1_2[c]) / 2 * dt;
+            double v1 = a.volume_kk[c] + dv, h;
+            if (v1 >= 0.0) h = v1 / a.cellarea; else { v1 = 0.0; h = 0.0; }
+            a.volume_kkp1[c] = v1;
+            a.h_water[c] = h;
+            if (nsurf > 1 && sub < nsurf) {      // shift time levels for the next sub-step (:171-195)
+                a.q_in_kk[c] = a.q_in_kkp1[c]; a.q_in_kkp1[c] = 0.0;
+                a.q_out_kk_1[c] = a.q_out_kkp1_1[c]; a.q_out_kkp1_1[c] = 0.0;
+                a.q_out_kk_2[c] = a.q_out_kkp1_2[c]; a.q_out_kkp1_2[c] = 0.0;
+                a.volume_kk[c] = v1; a.volume_kkp1[c] = 0.0;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { *a.ak_max = s_akmax; *a.nsurf_out = nsurf; }
+}
+
+// end-of-step surface bookkeeping: PONDNOD=0 where PNEW<=0 (SRC/cathy_main.f:3181-3184)
+__global__ void k_pond_zero(int nnod, const double *__restrict__ pnew, double *__restrict__ pondnod)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnod; i += gridDim.x * blockDim.x)
+        if (pnew[i] <= 0.0) pondnod[i] = 0.0;
+}
+
+// HGRAPH + SAT_FRAC (SRC/hgraph.f, SRC/sat_frac.f) + final STORE1 sum, one block, fixed order
+__global__ void k_step_final(int nnod, int nstr, double pmin, double ph, int nbpart, const double *__restrict__ store_part,
+                             const int *__restrict__ ifatm, const double *__restrict__ atmpot,
+                             const double *__restrict__ atmact, const double *__restrict__ pnew, StepOut *__restrict__ out)
+{
+    __shared__ double sh[32];
+    __shared__ int shi[13];
+    if (threadIdx.x < 13) shi[threadIdx.x] = 0;
+    __syncthreads();
+    double st = 0.0;
+    for (int b = threadIdx.x; b < nbpart; b += blockDim.x) st += store_part[b];
+    double apot = 0, aact = 0, refl = 0, ovf = 0;
+    int hg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, nh = 0, nd = 0, np = 0, ns = 0;
+    for (int k = threadIdx.x; k < nnod; k += blockDim.x) {
+        double pot = atmpot[k], act = atmact[k], pn = pnew[k];
+        int f = ifatm[k];
+        apot += pot; aact += act;
+        if (f == 2) { if (act < 0.0) refl = refl - act; ovf = ovf - act + pot; }
+        else if (f == 1) {
+            if (pn >= 0.0) {
+                if (act < 0.0) {
+                    if (pot >= 0.0) { refl = refl - act; ovf = ovf - act + pot; }
+                    else { hg[4]++; if (act <= pot) { refl = refl - act + pot; ovf = ovf - act + pot; } }
+                } else {
+                    if (pot >= 0.0) { if (act <= pot) ovf = ovf - act + pot; else hg[0]++; }
+                    else hg[5]++;
+                }
+            } else if (pn <= pmin) {
+                if (act < 0.0) { if (pot >= 0.0) { ovf = ovf + pot; hg[1]++; } }
+                else {
+                    hg[3]++;
+                    if (pot >= 0.0) { if (act <= pot) { ovf = ovf - act + pot; hg[8]++; } else hg[2]++; }
+                    else hg[7]++;
+                }
+            }
+        }
+        if (pn >= 0.0) {
+            ns++;
+            if (pn >= ph) np++;
+            int hd = 0;
+            for (int l = 1; l <= nstr; ++l) if (pnew[(size_t)l * nnod + k] < 0.0) hd = 1;
+            if (hd) nh++; else nd++;
+        }
+    }
+    double t0 = block_sum<RED_BLOCK>(st, sh), t1 = block_sum<RED_BLOCK>(apot, sh), t2 = block_sum<RED_BLOCK>(aact, sh);
+    double t3 = block_sum<RED_BLOCK>(refl, sh), t4 = block_sum<RED_BLOCK>(ovf, sh);
+    for (int q = 0; q < 9; ++q) if (hg[q]) atomicAdd(&shi[q], hg[q]);
+    if (nh) atomicAdd(&shi[9], nh);
+    if (nd) atomicAdd(&shi[10], nd);
+    if (np) atomicAdd(&shi[11], np);
+    if (ns) atomicAdd(&shi[12], ns);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        out->store1 = t0; out->apot = t1; out->aact = t2; out->reflow = t3; out->ovflow = t4;
+        for (int q = 0; q < 9; ++q) out->hgflag[q] = shi[q];
+        out->nhort = shi[9]; out->ndunn = shi[10]; out->npond = shi[11]; out->nsat = shi[12];
+    }
+}
+__global__ void k_weight(int n, double tetaf, const double *__restrict__ pnew, const double *__restrict__ ptimep, double *__restrict__ ptnew)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) ptnew[k] = tetaf * pnew[k] + (1.0 - tetaf) * ptimep[k];
+}
+// ATMONE's classification of surface nodes (SRC/atmone.f label 500 onwards)
+__global__ void k_atmone(int nnod, double pmin, double ph, double scf, const double *__restrict__ atmpot, double *__restrict__ atmold,
+                         double *__restrict__ atmact, double *__restrict__ pnew, double *__restrict__ ptimep, int *__restrict__ ifatm,
+                         int *__restrict__ ifatmp)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnod; i += gridDim.x * blockDim.x) {
+        int f = ifatm[i], fp = ifatmp[i];
+        if (f != -1) {
+            if (pnew[i] >= ph) { f = 2; fp = 2; }
+            else {
+                if (pnew[i] >= 0.0 && atmpot[i] > 0.0) f = 1;
+                if (ptimep[i] >= 0.0 && atmold[i] > 0.0) fp = 1;
+                if (pnew[i] <= pmin && atmpot[i] < 0.0) { pnew[i] = pmin; f = 1; }
+                if (ptimep[i] <= pmin && atmold[i] < 0.0) { ptimep[i] = pmin; fp = 1; }
+            }
+        }
+        ifatm[i] = f; ifatmp[i] = fp;
+        if (f == 0) atmact[i] = atmpot[i] >= 0.0 ? atmpot[i] : (1.0 - scf) * atmpot[i];
+        else atmact[i] = 0.0;
+        if (fp == 1 || fp == 2) atmold[i] = 0.0;
+    }
+}
+__global__ void k_mbinit(int nnod, const int *__restrict__ ifatmp, const double *__restrict__ atmold, double *__restrict__ out3)
+{   // MBINIT sums (SRC/mbinit.f): AACTP, ANINP, ANOUTP -- one block
+    __shared__ double sh[32];
+    double a = 0, b = 0, c = 0;
+    for (int k = threadIdx.x; k < nnod; k += blockDim.x)
+        if (ifatmp[k] == 0) { a += atmold[k]; if (atmold[k] > 0.0) b += atmold[k]; else c += atmold[k]; }
+    double t0 = block_sum<RED_BLOCK>(a, sh), t1 = block_sum<RED_BLOCK>(b, sh), t2 = block_sum<RED_BLOCK>(c, sh);
+    if (threadIdx.x == 0) { out3[0] = t0; out3[1] = t1; out3[2] = t2; }
+}
+
+// ==========================================================================================
+// host side
+// ==========================================================================================
+template <class T>
+struct DBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    int alloc(size_t cnt)
+    {
+        n = cnt;
+        if (cudaMalloc((void **)&p, std::max<size_t>(cnt, 1) * sizeof(T)) != cudaSuccess) return -1;
+        return cudaMemset(p, 0, std::max<size_t>(cnt, 1) * sizeof(T)) == cudaSuccess ? 0 : -1;
+    }
+    int upload(const std::vector<T> &h)
+    {
+        if (alloc(h.size())) return -1;
+        if (h.empty()) return 0;
+        return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -1;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; }
+};
+
+struct CathySim {
+    CathyProblem p;
+    int nrow, ncol, nc1, nstr, nnod, n, ntri, nt, ncell;
+    bool surf;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sms = 148, grid_n = 0, grid_pcg = 0;
+    int64_t launches = 0;
+    // host mesh kept for export
+    std::vector<double> hx, hy, hz, harenod;
+    std::vector<int> htri;       // [ntri*4] sorted nodes + zone
+    std::vector<unsigned char> hexist; // [NDIAG*n] structural mask of the upper diagonals
+    int64_t nterm = 0;
+    int off[NDIAG];
+    // static device data
+    DBuf<double> vgn, vgm, vgpsat, vgpnot, rr, snodi, pnodi, vgn1, vgnr, vgpsn, vgmr, volnod, arenod, z, m4, vegpar;
+    DBuf<int> veg;
+    DBuf<int4> tet;
+    DBuf<int> s_ptr, s_tet, n_ptr, n_tet;
+    DBuf<double> s_coef, n_g, n_m;
+    // matrices / vectors
+    DBuf<double> A;              // 8 diagonals, [NDIAG][n]
+    DBuf<double> diag_true, diag_bc, grav, m2, krt, e1t;
+    DBuf<double> pnew, pold, ptimep, ptnew, pdiff, sw, ckrw, ckrwp, et1, et2, swnew, swtimep, rhs, xt5, qtranie;
+    DBuf<double> wr, wz, wp0, wp1, wbv, partial, store_part;
+    DBuf<NormPartial> npart;
+    DBuf<IterOut> d_iter;
+    DBuf<StepOut> d_step;
+    IterOut *h_iter = nullptr;
+    StepOut *h_step = nullptr;
+    DBuf<int> ifatm, ifatmp, d_flags; // d_flags[0]=ponding, [1]=etran error
+    DBuf<double> atmpot, atmact, atmold, atmtab, pondnod, ovflnod, ovflp, scal3;
+    // atmospheric stream (host bookkeeping of the three-slot window, SRC/atmone.f / atmnxt.f)
+    double atmtim[3] = {0, 0, 0};
+    int atmrec[3] = {-1, -1, -1};
+    int atm_next = 0, htiatm = 0;
+    // surface routing
+    DBuf<int> lv_ptr, lv_cell, seqpos, don_ptr, don_cell;
+    DBuf<unsigned char> don_dir;
+    DBuf<double> r_w1, r_w2, r_sl1, r_sl2, r_epl1, r_epl2, r_ks1, r_ks2, r_ws1, r_ws2, r_b1, r_y1, r_nrc;
+    DBuf<double> sw_sn, q_in_kk, q_in_kkp1, q_out_kk_1, q_out_kk_2, q_out_kkp1_1, q_out_kkp1_2, volume_kk, volume_kkp1, h_water;
+    DBuf<double> q_in_kk_sav, q_out_kk_1_sav, q_out_kk_2_sav, volume_kk_sav, q_in_kk_p, q_out_kk_1_p, q_out_kk_2_p, volume_kk_p;
+    DBuf<double> d_akmax;   // [3]: ak_max, ak_max_p, ak_max_sav
+    DBuf<int> d_nsurf;
+    int nlevel = 0, outlet_cell = 0;
+    // time stepping state (host)
+    double time = 0, timep = 0, deltat = 0, dtmin = 0, dtmax = 0, tmax = 0, tetaf = 1;
+    int dtgmin = 1, nstep = 1, iter = 1, nitert = 0, itlin = 0, itrtot = 0, kbackt = 0, kback = 0, klsfai = 0, nsurft = 0;
+    int finished = 0, lsfail = 0, ponding = 0, pondp = 0, timep_dirty = 1;
+    double adinp = 0, adoutp = 0, ndinp = 0, ndoutp = 0, aninp = 0, anoutp = 0, nninp = 0, nnoutp = 0, aactp = 0;
+    double adin = 0, adout = 0, anin = 0, anout = 0, vin = 0, vout = 0, dstore = 0, erras = 0, errel = 0;
+    double store0 = 0, store1 = 0, store2 = 0;
+    int hgflag[9] = {0};
+    CathyIterRecord itrec[CATHY_MAXIT];
+    int itmax_dev = 0;
+    double tol_dev = 0;
+};
+
+static inline int nblk(long long n, int cap) { long long b = (n + RED_BLOCK - 1) / RED_BLOCK; return (int)std::max<long long>(1, std::min<long long>(b, cap)); }
+#define LAUNCH(S, kern, grid, block, ...)                       \
+    do {                                                        \
+        kern<<<(grid), (block), 0, (S)->st>>>(__VA_ARGS__);     \
+        (S)->launches++;                                        \
+    } while (0)
+
+static Diag make_diag(CathySim *S, double *base)
+{
+    Diag D;
+    for (int d = 0; d < NDIAG; ++d) { D.d[d] = base + (size_t)d * S->n; D.off[d] = S->off[d]; }
+    return D;
+}
+static Soil make_soil(CathySim *S)
+{
+    Soil s;
+    s.vgn = S->vgn.p; s.vgm = S->vgm.p; s.vgpsat = S->vgpsat.p; s.vgpnot = S->vgpnot.p; s.rr = S->rr.p; s.snodi = S->snodi.p;
+    s.pnodi = S->pnodi.p; s.vgn1 = S->vgn1.p; s.vgnr = S->vgnr.p; s.vgpsn = S->vgpsn.p; s.vgmr = S->vgmr.p;
+    return s;
+}
+
+// ---- host mesh + static tables -----------------------------------------------------------
+static void sort4(int *e)
+{
+    for (int k = 0; k < 3; ++k) for (int j = k + 1; j < 4; ++j) if (e[k] > e[j]) std::swap(e[k], e[j]);
+}
+static void gen_tets_of_prism(const int *tri, int top, int bot, int out[3][4])
+{   // SRC/gen3d.f:31-45 (0-based)
+    out[0][0] = top + tri[0]; out[0][1] = top + tri[1]; out[0][2] = top + tri[2]; out[0][3] = bot + tri[0];
+    out[1][0] = bot + tri[0]; out[1][1] = bot + tri[1]; out[1][2] = bot + tri[2]; out[1][3] = top + tri[2];
+    out[2][0] = top + tri[1]; out[2][1] = top + tri[2]; out[2][2] = bot + tri[1]; out[2][3] = bot + tri[0];
+}
+
+static int build_static(CathySim *S)
+{
+    const CathyProblem &p = S->p;
+    const int nrow = S->nrow, ncol = S->ncol, nc1 = S->nc1, nnod = S->nnod, n = S->n, nstr = S->nstr, ntri = S->ntri;
+    const size_t nt = (size_t)S->nt;
+    // --- surface mesh (SRC/triangoli.f, SRC/tpnodi2d.f, SRC/area2d.f)
+    S->hx.assign(n, 0.0); S->hy.assign(n, 0.0); S->hz.assign(n, 0.0); S->harenod.assign(nnod, 0.0);
+    S->htri.resize(4 * (size_t)ntri);
+    std::vector<int> cnt(nnod, 0);
+    for (int i = 0; i <= nrow; ++i)
+        for (int j = 0; j <= ncol; ++j) { int k = i * nc1 + j; S->hx[k] = p.west + j * p.dx; S->hy[k] = p.south + (nrow - i) * p.dy; }
+    for (int i = 0, it = 0; i < nrow; ++i)
+        for (int j = 0; j < ncol; ++j) {
+            int n00 = i * nc1 + j, n10 = n00 + nc1, n11 = n10 + 1, n01 = n00 + 1, zn = p.zone[i * ncol + j];
+            double e = p.dem[i * ncol + j] * p.factor;
+            int t1[3] = {n00, n10, n11}, t2[3] = {n00, n11, n01};
+            for (int q = 0; q < 3; ++q) { S->hz[t1[q]] += e; cnt[t1[q]]++; }
+            for (int q = 0; q < 3; ++q) { S->hz[t2[q]] += e; cnt[t2[q]]++; }
+            int *a = &S->htri[4 * (size_t)it++]; a[0] = n00; a[1] = n10; a[2] = n11; a[3] = zn;
+            int *b = &S->htri[4 * (size_t)it++]; b[0] = n00; b[1] = n01; b[2] = n11; b[3] = zn;
+        }
+    for (int k = 0; k < nnod; ++k) S->hz[k] /= cnt[k];
+    for (int t = 0; t < ntri; ++t) {
+        const int *T = &S->htri[4 * (size_t)t];
+        double a3 = 0, a2 = 0;
+        for (int ii = 0; ii < 3; ++ii) {
+            int I = T[ii], J = T[(ii + 1) % 3], M = T[(ii + 2) % 3];
+            a3 = S->hx[I] * S->hy[J] + a3; a2 = S->hx[I] * S->hy[M] + a2;
+        }
+        double are3 = std::fabs(0.5 * (a3 - a2)) * (1.0 / 3.0);
+        S->harenod[T[0]] += are3; S->harenod[T[1]] += are3; S->harenod[T[2]] += are3;
+    }
+    // --- vertical discretisation (SRC/gen3d.f:52-77)
+    double zmin = RMAX_;
+    for (int i = 0; i < nnod; ++i) zmin = std::min(zmin, S->hz[i]);
+    for (int i = 0; i < nnod; ++i) {
+        double zthick = (S->hz[i] - zmin) + p.base, zrsum = 0.0;
+        for (int j = 1; j <= nstr; ++j) {
+            size_t kk = (size_t)j * nnod + i;
+            S->hx[kk] = S->hx[i]; S->hy[kk] = S->hy[i];
+            zrsum = zrsum + p.zratio[j - 1];
+            double zz;
+            switch (p.ivert) {
+            case 0: zz = S->hz[i] - zrsum * p.base; break;
+            case 1: zz = S->hz[i] - zrsum * zthick; break;
+            case 2: zz = zmin - zrsum * p.base; break;
+            default: zz = S->hz[i] - zrsum * p.base; if (j == nstr) zz = zmin - p.base; break;
+            }
+            S->hz[kk] = zz;
+        }
+    }
+    // --- stencil offsets of the 8 upper diagonals
+    int offs[NDIAG] = {0, 1, nc1, nc1 + 1, nnod - nc1 - 1, nnod - nc1, nnod - 1, nnod};
+    for (int d = 0; d < NDIAG; ++d) S->off[d] = offs[d];
+    if (!(nc1 + 1 < nnod - nc1 - 1)) FAIL(-3, "DEM too small for the diagonal layout (need at least 2 rows)");
+    auto diag_of = [&](int dlt) -> int { for (int d = 0; d < NDIAG; ++d) if (offs[d] == dlt) return d; return -1; };
+    // --- per-tet geometry, nodal soil averages, contribution lists
+    std::vector<int4> tet(nt);
+    std::vector<double> volnod(n, 0.0), pnodi(n, 0.0), snodi(n, 0.0), vgn(n, 0.0), vgrmc(n, 0.0), vgpsat(n, 0.0);
+    std::vector<int> tp(n, 0);
+    const size_t nslots = (size_t)NDIAG * n;
+    std::vector<int> s_cnt(nslots + 1, 0), n_cnt(n + 1, 0);
+    struct TetGeo { double c[10]; double g[4]; double vol; };
+    // pass 1: geometry is recomputed in pass 2 to keep memory low; here only counts + nodal sums
+    auto tet_nodes = [&](size_t e, int T[4]) {
+        size_t lay = e / ((size_t)ntri * 3), rem = e - lay * (size_t)ntri * 3;
+        int tri = (int)(rem / 3), which = (int)(rem % 3), pr[3][4];
+        gen_tets_of_prism(&S->htri[4 * (size_t)tri], (int)lay * nnod, ((int)lay + 1) * nnod, pr);
+        for (int q = 0; q < 4; ++q) T[q] = pr[which][q];
+        if (p.iopt == 1) sort4(T);
+    };
+    static const double amen[5] = {-1.0, 1.0, -1.0, 1.0, -1.0};
+    auto geometry = [&](const int T[4], double b[4], double c[4], double d[4], double &vol) {
+        const double *X = S->hx.data(), *Y = S->hy.data(), *Z = S->hz.data();
+        vol = 0.0;
+        for (int nn = 0; nn < 4; ++nn) {
+            int o3[3] = {(nn + 1) & 3, (nn + 2) & 3, (nn + 3) & 3};
+            double a2, a3;
+            a2 = a3 = 0.0;
+            for (int ii = 0; ii < 3; ++ii) { int I = T[o3[ii]], J = T[o3[(ii + 1) % 3]], M = T[o3[(ii + 2) % 3]]; a3 = Y[I] * Z[J] + a3; a2 = Y[I] * Z[M] + a2; }
+            vol = vol + X[T[nn]] * amen[nn] * (a3 - a2) / 6.0;
+            b[nn] = amen[nn] * (a3 - a2) / 6.0;
+            a2 = a3 = 0.0;
+            for (int ii = 0; ii < 3; ++ii) { int I = T[o3[ii]], J = T[o3[(ii + 1) % 3]], M = T[o3[(ii + 2) % 3]]; a3 = X[I] * Z[J] + a3; a2 = X[I] * Z[M] + a2; }
+            c[nn] = amen[nn + 1] * (a3 - a2) / 6.0;
+            a2 = a3 = 0.0;
+            for (int ii = 0; ii < 3; ++ii) { int I = T[o3[ii]], J = T[o3[(ii + 1) % 3]], M = T[o3[(ii + 2) % 3]]; a3 = X[I] * Y[J] + a3; a2 = X[I] * Y[M] + a2; }
+            d[nn] = amen[nn] * (a3 - a2) / 6.0;
+        }
+    };
+    for (size_t e = 0; e < nt; ++e) {
+        int T[4];
+        tet_nodes(e, T);
+        tet[e] = make_int4(T[0], T[1], T[2], T[3]);
+        int lay = (int)(e / ((size_t)ntri * 3));
+        int zn = S->htri[4 * ((e % ((size_t)ntri * 3)) / 3) + 3] - 1;
+        int idx = lay * p.nzone + zn;
+        for (int q = 0; q < 4; ++q) {
+            int nd = T[q];
+            pnodi[nd] += p.poros[idx]; snodi[nd] += p.elstor[idx]; vgn[nd] += p.vgn[idx]; vgrmc[nd] += p.vgrmc[idx]; vgpsat[nd] += p.vgpsat[idx];
+            tp[nd]++;
+            n_cnt[nd + 1]++;
+        }
+        for (int k = 0; k < 4; ++k)
+            for (int l = k; l < 4; ++l) {
+                int dg = diag_of(T[l] - T[k]);
+                if (dg < 0) FAIL(-3, "unexpected node pair offset %d in tetrahedron %zu", T[l] - T[k], e);
+                s_cnt[(size_t)dg * n + T[k] + 1]++;
+            }
+    }
+    for (int k = 0; k < n; ++k) {
+        if (tp[k] == 0) FAIL(-3, "node %d is not connected to any element", k + 1);
+        pnodi[k] /= tp[k]; snodi[k] /= tp[k]; vgn[k] /= tp[k]; vgpsat[k] /= tp[k]; vgrmc[k] /= tp[k];
+    }
+    for (size_t s = 0; s < nslots; ++s) s_cnt[s + 1] += s_cnt[s];
+    for (int k = 0; k < n; ++k) n_cnt[k + 1] += n_cnt[k];
+    if ((long long)s_cnt[nslots] != (long long)10 * (long long)nt) FAIL(-3, "contribution count mismatch");
+    std::vector<int> s_fill(s_cnt.begin(), s_cnt.end() - 1), n_fill(n_cnt.begin(), n_cnt.end() - 1);
+    std::vector<int> s_tet((size_t)10 * nt), n_tet((size_t)4 * nt);
+    std::vector<double> s_coef((size_t)10 * nt), n_g((size_t)4 * nt), n_m((size_t)4 * nt), m4(n, 0.0);
+    for (size_t e = 0; e < nt; ++e) {
+        int T[4] = {tet[e].x, tet[e].y, tet[e].z, tet[e].w};
+        double b[4], c[4], d[4], vol;
+        geometry(T, b, c, d, vol);
+        if (vol == 0.0) FAIL(-3, "zero volume at element %zu", e + 1);
+        int ivol = vol < 0.0 ? -1 : 1;
+        double V = std::fabs(vol), VR = 1.0 / V;
+        int lay = (int)(e / ((size_t)ntri * 3));
+        int zn = S->htri[4 * ((e % ((size_t)ntri * 3)) / 3) + 3] - 1;
+        int idx = lay * p.nzone + zn;
+        double kx = p.permx[idx] * VR, ky = p.permy[idx] * VR, kz = p.permz[idx] * VR;
+        double pel = (((pnodi[T[0]] + pnodi[T[1]]) + pnodi[T[2]]) + pnodi[T[3]]) * 0.25;   // PICUNS' NODELT(PNODI,PEL)
+        for (int q = 0; q < 4; ++q) {
+            volnod[T[q]] += V * 0.25;
+            int pos = n_fill[T[q]]++;
+            n_tet[pos] = (int)e;
+            n_g[pos] = p.permz[idx] * d[q] * ivol;
+            n_m[pos] = V * 0.25;
+            m4[T[q]] += (V * pel) * 0.25;
+        }
+        for (int k = 0; k < 4; ++k)
+            for (int l = k; l < 4; ++l) {
+                int dg = diag_of(T[l] - T[k]);
+                int pos = s_fill[(size_t)dg * n + T[k]]++;
+                s_tet[pos] = (int)e;
+                s_coef[pos] = (kx * b[k]) * b[l] + (ky * c[k]) * c[l] + (kz * d[k]) * d[l];
+            }
+    }
+    S->hexist.assign(nslots, 0);
+    S->nterm = 0;
+    for (size_t s = 0; s < nslots; ++s) if (s_cnt[s + 1] > s_cnt[s]) { S->hexist[s] = 1; S->nterm++; }
+    // --- derived VG constants (SRC/chparm.f:22-35)
+    std::vector<double> vgm(n), vgn1(n), vgnr(n), vgpsn(n), vgmr(n), vgpnot(n), rr(n);
+    for (int k = 0; k < n; ++k) {
+        vgm[k] = (vgn[k] - 1.0) / vgn[k]; vgn1[k] = vgn[k] - 1.0; vgnr[k] = 1.0 / vgn[k];
+        vgpsn[k] = std::pow(std::fabs(vgpsat[k]), vgn[k]); vgmr[k] = 1.0 / vgm[k];
+        vgpnot[k] = (pnodi[k] - vgrmc[k]) / pnodi[k]; rr[k] = vgrmc[k] / pnodi[k];
+    }
+    // --- vegetation type per surface node (SRC/datin.f:236-246)
+    std::vector<int> veg(nnod);
+    {
+        std::vector<double> acc(nnod, 0.0);
+        std::vector<int> c2(nnod, 0);
+        for (int i = 0; i < nrow; ++i)
+            for (int j = 0; j < ncol; ++j) {
+                int n00 = i * nc1 + j, n10 = n00 + nc1, n11 = n10 + 1, n01 = n00 + 1;
+                double e = p.root_map[i * ncol + j] * p.factor;
+                int t1[3] = {n00, n10, n11}, t2[3] = {n00, n11, n01};
+                for (int q = 0; q < 3; ++q) { acc[t1[q]] += e; c2[t1[q]]++; acc[t2[q]] += e; c2[t2[q]]++; }
+            }
+        for (int k = 0; k < nnod; ++k) { int v = (int)(acc[k] / c2[k]); veg[k] = std::min(std::max(v, 1), p.nveg) - 1; }
+    }
+    std::vector<double> vegpar((size_t)6 * p.nveg);
+    for (int v = 0; v < p.nveg; ++v) {
+        vegpar[6 * v + 0] = p.pcana[v]; vegpar[6 * v + 1] = p.pcref[v]; vegpar[6 * v + 2] = p.pcwlt[v];
+        vegpar[6 * v + 3] = p.zroot[v]; vegpar[6 * v + 4] = p.pz[v]; vegpar[6 * v + 5] = p.omgc[v];
+    }
+    // --- upload
+    int rc = 0;
+    rc |= S->vgn.upload(vgn); rc |= S->vgm.upload(vgm); rc |= S->vgpsat.upload(vgpsat); rc |= S->vgpnot.upload(vgpnot);
+    rc |= S->rr.upload(rr); rc |= S->snodi.upload(snodi); rc |= S->pnodi.upload(pnodi); rc |= S->vgn1.upload(vgn1);
+    rc |= S->vgnr.upload(vgnr); rc |= S->vgpsn.upload(vgpsn); rc |= S->vgmr.upload(vgmr); rc |= S->volnod.upload(volnod);
+    rc |= S->arenod.upload(S->harenod); rc |= S->z.upload(S->hz); rc |= S->m4.upload(m4); rc |= S->veg.upload(veg);
+    rc |= S->vegpar.upload(vegpar); rc |= S->tet.upload(tet);
+    rc |= S->s_ptr.upload(s_cnt); rc |= S->s_tet.upload(s_tet); rc |= S->s_coef.upload(s_coef);
+    rc |= S->n_ptr.upload(n_cnt); rc |= S->n_tet.upload(n_tet); rc |= S->n_g.upload(n_g); rc |= S->n_m.upload(n_m);
+    if (rc) FAIL(-101, "device allocation/upload of static tables failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
+// file raster (north row first) -> routing linearisation I_BASIN = (col)*NROW + (row from south)
+static std::vector<double> to_route(const CathySim *S, const double *north_first)
+{
+    std::vector<double> d(S->ncell);
+    for (int fr = 0; fr < S->nrow; ++fr)
+        for (int c = 0; c < S->ncol; ++c) d[(size_t)c * S->nrow + (S->nrow - 1 - fr)] = north_first[(size_t)fr * S->ncol + c];
+    return d;
+}
+
+static int build_surface(CathySim *S)
+{
+    const CathyProblem &p = S->p;
+    const int nrow = S->nrow, ncol = S->ncol, nc = S->ncell;
+    std::vector<double> w1 = to_route(S, p.dtm_w_1), w2 = to_route(S, p.dtm_w_2), p1 = to_route(S, p.dtm_p_outflow_1), p2 = to_route(S, p.dtm_p_outflow_2);
+    std::vector<int> seq(nc, -1), qoi(nc);
+    for (int q = 0; q < nc; ++q) {
+        int ib = p.qoi[q] - 1;
+        if (ib < 0 || ib >= nc || seq[ib] != -1) FAIL(-4, "qoi_a entry %d is out of range or repeated", q + 1);
+        seq[ib] = q; qoi[q] = ib;
+    }
+    // donors of every cell in sequential (QOI) order, direction 1 before direction 2 (SRC/route.f:165-166,247-248)
+    std::vector<std::vector<std::pair<int, int>>> don(nc);
+    std::vector<int> level(nc, 0);
+    for (int q = 0; q < nc; ++q) {
+        int ib = qoi[q], J = ib % nrow + 1, I = ib / nrow + 1;
+        for (int dir = 0; dir < 2; ++dir) {
+            double w = dir ? w2[ib] : w1[ib];
+            if (w == 0.0) continue;
+            int pout = (int)(dir ? p2[ib] : p1[ib]);
+            int iii = (int)std::lround((float)(pout - 5) / 3.0f), jjj = pout - 5 - 3 * iii;
+            int icv = I + iii, jcv = J + jjj;
+            if (dir == 0 && q == nc - 1) continue;              // the outlet keeps its direction-1 outflow
+            if (icv < 1 || icv > ncol || jcv < 1 || jcv > nrow) continue;
+            int tgt = (icv - 1) * nrow + jcv - 1;
+            if (seq[tgt] <= q) FAIL(-4, "drainage pointer of cell %d goes to a cell that is not later in qoi_a", ib + 1);
+            don[tgt].push_back({ib, dir});
+            level[tgt] = std::max(level[tgt], level[ib] + 1);   // donors precede receivers in QOI order
+        }
+    }
+    int nlev = 0;
+    for (int c = 0; c < nc; ++c) nlev = std::max(nlev, level[c] + 1);
+    std::vector<int> lptr(nlev + 1, 0), lcell(nc), dptr(nc + 1, 0), dcell;
+    std::vector<unsigned char> ddir;
+    for (int c = 0; c < nc; ++c) lptr[level[c] + 1]++;
+    for (int l = 0; l < nlev; ++l) lptr[l + 1] += lptr[l];
+    {
+        std::vector<int> fill(lptr.begin(), lptr.end() - 1);
+        for (int q = 0; q < nc; ++q) { int ib = qoi[q]; lcell[fill[level[ib]]++] = ib; }
+    }
+    for (int c = 0; c < nc; ++c) {
+        dptr[c + 1] = dptr[c] + (int)don[c].size();
+        for (auto &pr : don[c]) { dcell.push_back(pr.first); ddir.push_back((unsigned char)pr.second); }
+    }
+    S->nlevel = nlev; S->outlet_cell = qoi[nc - 1];
+    int rc = 0;
+    rc |= S->lv_ptr.upload(lptr); rc |= S->lv_cell.upload(lcell); rc |= S->seqpos.upload(seq); rc |= S->don_ptr.upload(dptr);
+    rc |= S->don_cell.upload(dcell); rc |= S->don_dir.upload(ddir);
+    rc |= S->r_w1.upload(w1); rc |= S->r_w2.upload(w2);
+    rc |= S->r_sl1.upload(to_route(S, p.dtm_local_slope_1)); rc |= S->r_sl2.upload(to_route(S, p.dtm_local_slope_2));
+    rc |= S->r_epl1.upload(to_route(S, p.dtm_epl_1)); rc |= S->r_epl2.upload(to_route(S, p.dtm_epl_2));
+    rc |= S->r_ks1.upload(to_route(S, p.dtm_kss1_sf_1)); rc |= S->r_ks2.upload(to_route(S, p.dtm_kss1_sf_2));
+    rc |= S->r_ws1.upload(to_route(S, p.dtm_ws1_sf_1)); rc |= S->r_ws2.upload(to_route(S, p.dtm_ws1_sf_2));
+    rc |= S->r_b1.upload(to_route(S, p.dtm_b1_sf)); rc |= S->r_y1.upload(to_route(S, p.dtm_y1_sf)); rc |= S->r_nrc.upload(to_route(S, p.dtm_nrc));
+    DBuf<double> *bufs[] = {&S->sw_sn, &S->q_in_kk, &S->q_in_kkp1, &S->q_out_kk_1, &S->q_out_kk_2, &S->q_out_kkp1_1, &S->q_out_kkp1_2,
+                            &S->volume_kk, &S->volume_kkp1, &S->h_water, &S->q_in_kk_sav, &S->q_out_kk_1_sav, &S->q_out_kk_2_sav,
+                            &S->volume_kk_sav, &S->q_in_kk_p, &S->q_out_kk_1_p, &S->q_out_kk_2_p, &S->volume_kk_p};
+    for (auto *b : bufs) rc |= b->alloc(nc);
+    rc |= S->d_akmax.alloc(3); rc |= S->d_nsurf.alloc(1);
+    if (rc) FAIL(-101, "device allocation of surface routing tables failed");
+    return 0;
+}
+
+// ---- atmospheric stream bookkeeping (host) ------------------------------------------------
+static void atm_shift_read(CathySim *S, double time)
+{   // label 200 of ATMONE / ATMNXT
+    while (!(time <= S->atmtim[2])) {
+        S->atmtim[0] = S->atmtim[1]; S->atmtim[1] = S->atmtim[2];
+        S->atmrec[0] = S->atmrec[1]; S->atmrec[1] = S->atmrec[2];
+        if (S->atm_next >= S->p.natm) { S->htiatm = 1; break; }
+        S->atmtim[2] = S->p.atm_time[S->atm_next];
+        S->atmrec[2] = S->atm_next++;
+    }
+}
+static void atm_interp_launch(CathySim *S, int slot_a, int slot_b, double time, int set_act)
+{
+    int up = S->atmtim[slot_b] > S->atmtim[slot_a];
+    LAUNCH(S, k_atm_interp, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, S->atmtab.p, S->p.hspatm == 0 ? 1 : 0, S->atmrec[slot_a],
+           S->atmrec[slot_b], !up, S->atmtim[slot_a], S->atmtim[slot_b], time, S->p.ieto, S->p.scf, S->arenod.p, S->ifatm.p, set_act,
+           S->atmpot.p, S->atmact.p);
+}
+static void atmnxt(CathySim *S)
+{
+    if (S->htiatm == 0) {
+        atm_shift_read(S, S->time);
+        atm_interp_launch(S, 1, 2, S->time, 1);
+    }
+}
+static void atmbak(CathySim *S)
+{
+    if (S->atmtim[0] >= S->atmtim[1]) return;
+    atm_interp_launch(S, 0, 1, S->time, 1);   // ATMBAK always interpolates between slots 1 and 2 of the shifted window
+}
+
+static void weight_and_copy(CathySim *S)
+{   // POLD <- PNEW ; PTNEW = WEIGHT (SRC/weight.f)
+    size_t b = (size_t)S->n * sizeof(double);
+    cudaMemcpyAsync(S->pold.p, S->pnew.p, b, cudaMemcpyDeviceToDevice, S->st);
+    if (S->tetaf == 1.0) cudaMemcpyAsync(S->ptnew.p, S->pnew.p, b, cudaMemcpyDeviceToDevice, S->st);
+    else LAUNCH(S, k_weight, nblk(S->n, S->grid_n), RED_BLOCK, S->n, S->tetaf, S->pnew.p, S->ptimep.p, S->ptnew.p);
+}
+
+// chvelo + storage sum -> returns STORE1 through h_step later; here just launches
+static void chvelo_launch(CathySim *S, const double *psi)
+{
+    LAUNCH(S, k_chvelo, S->grid_n, RED_BLOCK, S->n, make_soil(S), psi, S->volnod.p, S->sw.p, S->ckrw.p, S->store_part.p);
+}
+static int step_final_sync(CathySim *S)
+{
+    LAUNCH(S, k_step_final, 1, RED_BLOCK, S->nnod, S->nstr, S->p.pmin, S->p.pondh_min, S->grid_n, S->store_part.p, S->ifatm.p, S->atmpot.p,
+           S->atmact.p, S->pnew.p, S->d_step.p);
+    CK(cudaMemcpyAsync(S->h_step, S->d_step.p, sizeof(StepOut), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    return 0;
+}
+
+// ---- one Picard iteration on the device: SRC/picard.f:74-198 + MASBAL + NORMS ------------
+static int assemble_system(CathySim *S, double deltat)
+{
+    const int n = S->n;
+    Diag A = make_diag(S, S->A.p);
+    LAUNCH(S, k_curves, nblk(n, S->grid_n), RED_BLOCK, n, make_soil(S), S->ptnew.p, S->pnew.p, S->ptimep.p, S->timep_dirty, S->sw.p, S->ckrw.p, S->et1.p, S->et2.p, S->swnew.p, S->swtimep.p);
+    S->timep_dirty = 0;
+    LAUNCH(S, k_tet_avg, nblk(S->nt, 4 * S->grid_n), RED_BLOCK, S->nt, S->tet.p, S->ckrw.p, S->et1.p, S->krt.p, S->e1t.p);
+    LAUNCH(S, k_assemble, nblk((long long)NDIAG * n, 8 * S->grid_n), RED_BLOCK, (long long)NDIAG * n, S->s_ptr.p, S->s_tet.p, S->s_coef.p, S->krt.p, S->A.p);
+    LAUNCH(S, k_assemble_nodes, nblk(n, S->grid_n), RED_BLOCK, n, S->n_ptr.p, S->n_tet.p, S->n_g.p, S->n_m.p, S->krt.p, S->e1t.p, S->grav.p, S->m2.p);
+    LAUNCH(S, k_rhs_lhs, nblk(n, S->grid_n), RED_BLOCK, n, S->nnod, A, S->tetaf, 1.0 / deltat, S->ptnew.p, S->pnew.p, S->ptimep.p, S->swnew.p,
+           S->swtimep.p, S->m2.p, S->m4.p, S->et2.p, S->grav.p, S->ifatm.p, (const unsigned char *)nullptr, (const double *)nullptr,
+           S->atmact.p, S->atmold.p, S->qtranie.p, S->rhs.p, S->xt5.p, S->diag_true.p, S->diag_bc.p);
+    if (S->tetaf != 1.0)   // off-diagonals of the LHS are TETAF * stiffness (SRC/cfmatp.f:24-26)
+        LAUNCH(S, k_scale, nblk((long long)(NDIAG - 1) * n, 8 * S->grid_n), RED_BLOCK, (long long)(NDIAG - 1) * n, S->tetaf, S->A.p + n);
+    return 0;
+}
+static int solve_system(CathySim *S)
+{
+    PcgArgs a;
+    a.n = S->n; a.nnod = S->nnod; a.itmax = S->itmax_dev; a.tol = S->tol_dev;
+    a.A = make_diag(S, S->A.p); a.diag = S->diag_bc.p; a.rhs = S->rhs.p;
+    a.x = S->pdiff.p; a.r = S->wr.p; a.z = S->wz.p; a.p0 = S->wp0.p; a.p1 = S->wp1.p; a.bv = S->wbv.p;
+    a.ifatm = S->ifatm.p; a.contp_flag = nullptr; a.partial = S->partial.p; a.out = S->d_iter.p;
+    void *args[] = {&a};
+    CK(cudaLaunchCooperativeKernel((void *)k_pcg, dim3(S->grid_pcg), dim3(RED_BLOCK), args, 0, S->st));
+    S->launches++;
+    return 0;
+}
+static int picard_iteration(CathySim *S, CathyIterRecord *rec)
+{
+    const int n = S->n;
+    int rc = assemble_system(S, S->deltat);
+    if (rc) return rc;
+    rc = solve_system(S);
+    if (rc) return rc;
+    Diag A = make_diag(S, S->A.p);
+    LAUNCH(S, k_update, nblk(n, S->grid_n), RED_BLOCK, n, S->nnod, S->pdiff.p, S->pold.p, S->ifatm.p, (const unsigned char *)nullptr,
+           (const double *)nullptr, S->pnew.p);
+    LAUNCH(S, k_bkflux, nblk(S->nnod, S->grid_n), RED_BLOCK, n, S->nnod, A, S->diag_true.p, S->pdiff.p, S->xt5.p, S->ifatm.p, S->tetaf,
+           S->atmold.p, S->atmact.p);
+    LAUNCH(S, k_norms, S->grid_n, RED_BLOCK, n, S->pnew.p, S->pold.p, S->rhs.p, S->ptimep.p, S->swnew.p, S->swtimep.p, S->volnod.p,
+           S->snodi.p, S->pnodi.p, S->npart.p);
+    LAUNCH(S, k_norms_final, 1, RED_BLOCK, S->grid_n, S->npart.p, S->nnod, S->ifatm.p, S->atmact.p, S->pnew.p, S->pold.p, S->d_iter.p);
+    // atmospheric switching is evaluated every iteration when TOLSWI is large (SRC/conver.f:58-71); when it is
+    // conditional the host decides after the read-back below.
+    bool switch_always = S->p.tolswi >= 1.0e29;
+    auto launch_switch = [&]() {
+        if (!S->surf) LAUNCH(S, k_switch_old, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, S->p.pmin, S->atmpot.p, S->ifatm.p, S->atmact.p, S->pnew.p);
+        else {
+            cudaMemsetAsync(S->d_flags.p, 0, sizeof(int), S->st);
+            LAUNCH(S, k_switch, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, S->deltat, S->p.pmin, S->p.pondh_min, S->arenod.p, S->pondnod.p,
+                   S->atmpot.p, S->qtranie.p, S->ifatm.p, S->atmact.p, S->pnew.p, S->ovflnod.p, S->d_flags.p);
+        }
+    };
+    if (switch_always) launch_switch();
+    CK(cudaMemcpyAsync(S->h_iter, S->d_iter.p, sizeof(IterOut), cudaMemcpyDeviceToHost, S->st));
+    int h_pond = 0;
+    if (switch_always && S->surf) CK(cudaMemcpyAsync(&S->h_iter->ponding, S->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    const IterOut &o = *S->h_iter;
+    rec->niter = o.pcg_niter; rec->ikmax = o.ikmax + 1; rec->pl2 = o.pl2; rec->pinf = o.pinf; rec->pnew_ik = o.pnew_ik;
+    rec->pold_ik = o.pold_ik; rec->fl2 = o.fl2; rec->finf = o.finf;
+    if (!switch_always) {
+        bool sw = (S->p.l2norm == 0 && o.pinf <= S->p.tolswi) || (S->p.l2norm != 0 && o.pl2 <= S->p.tolswi);
+        if (sw) {
+            launch_switch();
+            if (S->surf) { CK(cudaMemcpyAsync(&h_pond, S->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, S->st)); CK(cudaStreamSynchronize(S->st)); S->ponding = h_pond; }
+        }
+    } else if (S->surf) S->ponding = o.ponding;
+    // MASBAL scalars (SRC/masbal.f:69-109); fluxes were summed BEFORE the switch, as in the reference
+    S->adin = o.adin; S->adout = o.adout; S->anin = o.anin; S->anout = o.anout; S->dstore = o.dstore;
+    double dm = 0.5 * S->deltat;
+    double vadin = (S->adin + S->adinp) * dm, vadout = (S->adout + S->adoutp) * dm, vanin = (S->anin + S->aninp) * dm, vanout = (S->anout + S->anoutp) * dm;
+    S->vin = vadin + 0.0 + vanin + 0.0 + 0.0;
+    S->vout = vadout + 0.0 + vanout + 0.0 + 0.0 + 0.0;
+    S->erras = S->vin + S->vout - S->dstore;
+    S->errel = (S->vin + S->vout) != 0.0 ? 100.0 * S->erras / (S->vin + S->vout) : 0.0;
+    S->itlin += o.pcg_niter; S->nitert += o.pcg_niter;
+    if (o.pcg_niter >= S->itmax_dev) { S->lsfail = 1; S->klsfai++; } else S->lsfail = 0;
+    return 0;
+}
+
+// FLOW3D's nonlinear loop and decision logic (SRC/flow3d.f:93-294): 0 converged, 1 back-step, 2 no back-step possible
+static int flow3d(CathySim *S, int *status)
+{
+    const CathyProblem &p = S->p;
+    for (;;) {
+        CathyIterRecord *r = &S->itrec[std::min(S->iter - 1, CATHY_MAXIT - 1)];
+        int rc = picard_iteration(S, r);
+        if (rc) return rc;
+        if (!(r->pinf == r->pinf)) { S->lsfail = 1; }       // NaN guard: treat as solver failure -> back-step
+        bool itagen = S->iter < p.ituns;
+        bool errgmx = (r->pl2 >= p.ernlmx || r->pinf >= p.ernlmx || r->fl2 >= p.ernlmx || r->finf >= p.ernlmx);
+        bool normcv = p.l2norm == 0 ? (r->pinf <= p.toluns) : (r->pl2 <= p.toluns);
+        if (!S->lsfail && !errgmx && !normcv && itagen) {
+            weight_and_copy(S);
+            S->iter++;
+            continue;
+        }
+        S->itrtot += S->iter;
+        if (!S->lsfail && !errgmx && normcv) { *status = 0; return 0; }
+        *status = S->dtgmin ? 1 : 2;
+        return 0;
+    }
+}
+
+static int surf_flowtra(CathySim *S)
+{
+    LAUNCH(S, k_div_area, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, S->arenod.p, S->ovflnod.p);
+    LAUNCH(S, k_nod_cell, nblk(S->ncell, S->grid_n), RED_BLOCK, S->nrow, S->ncol, S->p.dx, S->p.dy, S->ovflnod.p, S->sw_sn.p);
+    RouteArgs a;
+    a.ncell = S->ncell; a.nlevel = S->nlevel; a.level_ptr = S->lv_ptr.p; a.level_cell = S->lv_cell.p; a.seq = S->seqpos.p;
+    a.don_ptr = S->don_ptr.p; a.don_cell = S->don_cell.p; a.don_dir = S->don_dir.p;
+    a.w1 = S->r_w1.p; a.w2 = S->r_w2.p; a.sl1 = S->r_sl1.p; a.sl2 = S->r_sl2.p; a.epl1 = S->r_epl1.p; a.epl2 = S->r_epl2.p;
+    a.ks1 = S->r_ks1.p; a.ks2 = S->r_ks2.p; a.ws1 = S->r_ws1.p; a.ws2 = S->r_ws2.p; a.b1 = S->r_b1.p; a.y1 = S->r_y1.p; a.nrc = S->r_nrc.p;
+    a.sw_sn = S->sw_sn.p; a.q_in_kk = S->q_in_kk.p; a.q_in_kkp1 = S->q_in_kkp1.p; a.q_out_kk_1 = S->q_out_kk_1.p; a.q_out_kk_2 = S->q_out_kk_2.p;
+    a.q_out_kkp1_1 = S->q_out_kkp1_1.p; a.q_out_kkp1_2 = S->q_out_kkp1_2.p; a.volume_kk = S->volume_kk.p; a.volume_kkp1 = S->volume_kkp1.p;
+    a.h_water = S->h_water.p; a.ak_max = S->d_akmax.p; a.nsurf_out = S->d_nsurf.p; a.deltat = S->deltat; a.cellarea = S->p.dx * S->p.dy;
+    LAUNCH(S, k_route, 1, 1024, a);
+    LAUNCH(S, k_cell_nod, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nrow, S->ncol, S->h_water.p, S->pondnod.p);
+    cudaMemsetAsync(S->d_flags.p, 0, sizeof(int), S->st);
+    LAUNCH(S, k_pondupd, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, S->p.pondh_min, 1.0 / S->deltat, S->pondnod.p, S->arenod.p, S->atmpot.p,
+           S->ifatm.p, S->atmact.p, S->pnew.p, S->d_flags.p);
+    int h[2];
+    CK(cudaMemcpyAsync(&h[0], S->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaMemcpyAsync(&h[1], S->d_nsurf.p, sizeof(int), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    S->ponding = h[0];
+    return h[1];
+}
+static void copy_cells(CathySim *S, DBuf<double> &dst, DBuf<double> &src) { cudaMemcpyAsync(dst.p, src.p, (size_t)S->ncell * sizeof(double), cudaMemcpyDeviceToDevice, S->st); }
+static void zero_cells(CathySim *S, DBuf<double> &dst) { cudaMemsetAsync(dst.p, 0, (size_t)S->ncell * sizeof(double), S->st); }
+
+// BKSTEP (SRC/bkstep.f:54-166)
+static void bkstep(CathySim *S)
+{
+    const CathyProblem &p = S->p;
+    size_t bn = (size_t)S->n * sizeof(double), bs = (size_t)S->nnod * sizeof(double);
+    cudaMemcpyAsync(S->pnew.p, S->ptimep.p, bn, cudaMemcpyDeviceToDevice, S->st);
+    cudaMemcpyAsync(S->ifatm.p, S->ifatmp.p, (size_t)S->nnod * sizeof(int), cudaMemcpyDeviceToDevice, S->st);
+    cudaMemcpyAsync(S->atmact.p, S->atmold.p, bs, cudaMemcpyDeviceToDevice, S->st);
+    S->time = S->timep;
+    S->deltat = S->deltat * p.dtredm - p.dtreds;
+    if (S->deltat <= S->dtmin) { S->deltat = S->dtmin; S->dtgmin = 0; } else S->dtgmin = 1;
+    S->time = S->time + S->deltat;
+    S->kbackt++; S->kback++; S->iter = 1; S->nitert = 0;
+    if (S->time > S->atmtim[1]) atmnxt(S); else atmbak(S);
+    if (!S->surf) LAUNCH(S, k_switch_old, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, p.pmin, S->atmpot.p, S->ifatm.p, S->atmact.p, S->pnew.p);
+    else LAUNCH(S, k_adrstn, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, p.pmin, S->atmpot.p, S->ifatm.p, S->atmact.p, S->pnew.p);
+    weight_and_copy(S);
+    if (S->surf) {
+        S->ponding = S->pondp;
+        cudaMemcpyAsync(S->ovflnod.p, S->ovflp.p, bs, cudaMemcpyDeviceToDevice, S->st);
+        cudaMemcpyAsync(S->d_akmax.p, S->d_akmax.p + 1, sizeof(double), cudaMemcpyDeviceToDevice, S->st);   // AK_MAX = AK_MAX_P
+        copy_cells(S, S->q_in_kk, S->q_in_kk_p); copy_cells(S, S->q_out_kk_1, S->q_out_kk_1_p);
+        copy_cells(S, S->q_out_kk_2, S->q_out_kk_2_p); copy_cells(S, S->volume_kk, S->volume_kk_p);
+    }
+}
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+const char *cathy_last_error(void) { return g_err; }
+int64_t cathy_sizeof_problem(void) { return (int64_t)sizeof(CathyProblem); }
+int64_t cathy_sizeof_report(void) { return (int64_t)sizeof(CathyStepReport); }
+int32_t cathy_abi_version(void) { return CATHY_ABI_VERSION; }
+
+void cathy_destroy(CathySim *S)
+{
+    if (!S) return;
+    cudaSetDevice(S->p.device);
+    if (S->st) cudaStreamSynchronize(S->st);
+    // DBuf members are plain pointers: release them explicitly
+    DBuf<double> *dd[] = {&S->vgn, &S->vgm, &S->vgpsat, &S->vgpnot, &S->rr, &S->snodi, &S->pnodi, &S->vgn1, &S->vgnr, &S->vgpsn, &S->vgmr,
+                          &S->volnod, &S->arenod, &S->z, &S->m4, &S->vegpar, &S->s_coef, &S->n_g, &S->n_m, &S->A, &S->diag_true, &S->diag_bc,
+                          &S->grav, &S->m2, &S->krt, &S->e1t, &S->pnew, &S->pold, &S->ptimep, &S->ptnew, &S->pdiff, &S->sw, &S->ckrw, &S->ckrwp,
+                          &S->et1, &S->et2, &S->swnew, &S->swtimep, &S->rhs, &S->xt5, &S->qtranie, &S->wr, &S->wz, &S->wp0, &S->wp1, &S->wbv,
+                          &S->partial, &S->store_part, &S->atmpot, &S->atmact, &S->atmold, &S->atmtab, &S->pondnod, &S->ovflnod, &S->ovflp,
+                          &S->scal3, &S->r_w1, &S->r_w2, &S->r_sl1, &S->r_sl2, &S->r_epl1, &S->r_epl2, &S->r_ks1, &S->r_ks2, &S->r_ws1, &S->r_ws2,
+                          &S->r_b1, &S->r_y1, &S->r_nrc, &S->sw_sn, &S->q_in_kk, &S->q_in_kkp1, &S->q_out_kk_1, &S->q_out_kk_2, &S->q_out_kkp1_1,
+                          &S->q_out_kkp1_2, &S->volume_kk, &S->volume_kkp1, &S->h_water, &S->q_in_kk_sav, &S->q_out_kk_1_sav, &S->q_out_kk_2_sav,
+                          &S->volume_kk_sav, &S->q_in_kk_p, &S->q_out_kk_1_p, &S->q_out_kk_2_p, &S->volume_kk_p, &S->d_akmax};
+    for (auto *b : dd) b->release();
+    DBuf<int> *di[] = {&S->veg, &S->s_ptr, &S->s_tet, &S->n_ptr, &S->n_tet, &S->ifatm, &S->ifatmp, &S->d_flags, &S->lv_ptr, &S->lv_cell,
+                       &S->seqpos, &S->don_ptr, &S->don_cell, &S->d_nsurf};
+    for (auto *b : di) b->release();
+    S->tet.release(); S->don_dir.release(); S->npart.release(); S->d_iter.release(); S->d_step.release();
+    if (S->h_iter) cudaFreeHost(S->h_iter);
+    if (S->h_step) cudaFreeHost(S->h_step);
+    if (S->ev0) cudaEventDestroy(S->ev0);
+    if (S->ev1) cudaEventDestroy(S->ev1);
+    if (S->st) cudaStreamDestroy(S->st);
+    delete[] S->p.atm_time;
+    delete S;
+}
+
+static int create_impl(const CathyProblem *prob, CathySim *S)
+{
+    S->p = *prob;
+    S->p.atm_time = nullptr;   // re-pointed below at an owned copy (cathy_destroy frees it)
+    CathyProblem &p = S->p;
+    S->nrow = p.nrow; S->ncol = p.ncol; S->nc1 = p.ncol + 1; S->nstr = p.nstr;
+    long long nnod = (long long)(p.nrow + 1) * (p.ncol + 1), n = nnod * (p.nstr + 1), nt = 6LL * p.nrow * p.ncol * p.nstr;
+    if (n > 2000000000LL || nt * 10 > 2147000000LL) FAIL(-2, "mesh too large for 32-bit indexing in this build (N=%lld, NT=%lld)", n, nt);
+    S->nnod = (int)nnod; S->n = (int)n; S->ntri = 2 * p.nrow * p.ncol; S->nt = (int)nt; S->ncell = p.nrow * p.ncol;
+    S->surf = p.isimgr == 2;
+    {
+        double *t = new double[std::max(prob->natm, 1)];
+        for (int i = 0; i < prob->natm; ++i) t[i] = prob->atm_time[i];
+        p.atm_time = t;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) FAIL(-102, "no CUDA device available: the CATHY B200 path has no CPU fallback");
+    CK(cudaSetDevice(p.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, p.device));
+    S->sms = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch) FAIL(-102, "device does not support cooperative launches");
+    CK(cudaStreamCreateWithFlags(&S->st, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&S->ev0)); CK(cudaEventCreate(&S->ev1));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pcg, RED_BLOCK, 0));
+    if (occ < 1) FAIL(-102, "PCG kernel does not fit on an SM");
+    S->grid_pcg = S->sms * std::min(occ, 8);
+    S->grid_n = S->sms * 8;                      // grid-stride kernels: a multiple of the SM count
+    // the device PCG is diagonally preconditioned: it needs more (cheaper) iterations than IC(0), so the
+    // failure threshold ITMXCG is scaled; LSFAIL keeps its meaning "did not reach TOLCG"
+    S->itmax_dev = p.itmxcg * 20;
+    S->tol_dev = p.tolcg * (p.tolcg_scale > 0.0 ? p.tolcg_scale : 1.0);
+    int rc = build_static(S);
+    if (rc) return rc;
+    const int N = S->n, NN = S->nnod;
+    int a = 0;
+    a |= S->A.alloc((size_t)NDIAG * N);
+    DBuf<double> *vn[] = {&S->diag_true, &S->diag_bc, &S->grav, &S->m2, &S->pnew, &S->pold, &S->ptimep, &S->ptnew, &S->pdiff, &S->sw, &S->ckrw,
+                          &S->ckrwp, &S->et1, &S->et2, &S->swnew, &S->swtimep, &S->rhs, &S->xt5, &S->qtranie, &S->wr, &S->wz, &S->wp0, &S->wp1, &S->wbv};
+    for (auto *b : vn) a |= b->alloc(N);
+    a |= S->krt.alloc(S->nt); a |= S->e1t.alloc(S->nt);
+    a |= S->partial.alloc(3 * (size_t)S->grid_pcg); a |= S->store_part.alloc(S->grid_n); a |= S->npart.alloc(S->grid_n);
+    a |= S->d_iter.alloc(1); a |= S->d_step.alloc(1); a |= S->ifatm.alloc(NN); a |= S->ifatmp.alloc(NN); a |= S->d_flags.alloc(4);
+    DBuf<double> *vs[] = {&S->atmpot, &S->atmact, &S->atmold, &S->pondnod, &S->ovflnod, &S->ovflp};
+    for (auto *b : vs) a |= b->alloc(NN);
+    a |= S->scal3.alloc(4);
+    if (a) FAIL(-101, "device allocation failed (N=%d): %s", N, cudaGetErrorString(cudaGetLastError()));
+    CK(cudaMallocHost((void **)&S->h_iter, sizeof(IterOut)));
+    CK(cudaMallocHost((void **)&S->h_step, sizeof(StepOut)));
+    {
+        size_t cnt = (size_t)p.natm * (p.hspatm ? 1 : NN);
+        std::vector<double> tab(prob->atm_val, prob->atm_val + cnt);
+        if (S->atmtab.upload(tab)) FAIL(-101, "atmbc table upload failed");
+    }
+    if (S->surf) { rc = build_surface(S); if (rc) return rc; }
+    if (p.ndir_rec > 0 && p.dir_ptr[p.ndir_rec] > 0) FAIL(-2, "non-atmospheric Dirichlet nodes (nansfdirbc) are not implemented on the device yet");
+    if (p.nneu_rec > 0 && p.neu_ptr[p.nneu_rec] > 0) FAIL(-2, "non-atmospheric Neumann nodes (nansfneubc) are not implemented on the device yet");
+    for (int r = 0; r < p.nneu_rec; ++r) if (p.neu_n2d[r] < 0) FAIL(-2, "free-drainage bottom (NODIN2<0) is not implemented on the device yet");
+
+    // ---- initial conditions (SRC/datin.f:380-403, SRC/icvhe.f, icvhwt.f, icvdwt.f) on the host, then upload
+    std::vector<double> pt(N, 0.0), pond(NN, 0.0);
+    if (p.indp == 0 || p.indp == 1) for (int k = 0; k < N; ++k) pt[k] = prob->ic_psi[k];
+    if (p.ipond != 0 && prob->ic_pond) for (int k = 0; k < NN; ++k) { pond[k] = prob->ic_pond[k]; if (pond[k] > 0.0) pt[k] = pond[k]; }
+    const double *Z = S->hz.data();
+    double mult = p.ipond == 0 ? 0.0 : 1.0;
+    for (int i = 0; i < NN && p.indp >= 2; ++i)
+        for (int k = 0; k <= S->nstr; ++k) {
+            size_t kk = (size_t)k * NN + i;
+            if (p.indp == 2) pt[kk] = (Z[i] + mult * pond[i]) - Z[kk];
+            else if (p.indp == 3) pt[kk] = p.wtposition - Z[kk] + Z[(size_t)S->nstr * NN + i];
+            else pt[kk] = Z[i] - Z[kk] - p.wtposition;
+        }
+    CK(cudaMemcpy(S->ptimep.p, pt.data(), (size_t)N * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(S->pnew.p, pt.data(), (size_t)N * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(S->pondnod.p, pond.data(), (size_t)NN * sizeof(double), cudaMemcpyHostToDevice));
+    // SRC/init1.f
+    S->deltat = p.deltat; S->dtmin = p.dtmin; S->dtmax = p.dtmax; S->tmax = p.tmax; S->tetaf = p.tetaf;
+    if (S->deltat > S->dtmax) S->deltat = S->dtmax;
+    if (S->deltat <= S->dtmin) { S->deltat = S->dtmin; S->dtgmin = 0; } else S->dtgmin = 1;
+    S->timep = 0.0; S->time = S->deltat;
+    S->ponding = p.ipond != 0; S->pondp = S->ponding;
+    return 0;
+}
+
+// ATMONE (SRC/atmone.f) + MBINIT + CHVELO/STORCAL (SRC/cathy_main.f:2658-2660); also used by cathy_set_psi
+static int init_atm_and_storage(CathySim *S)
+{
+    const CathyProblem &p = S->p;
+    const int NN = S->nnod, N = S->n;
+    S->htiatm = 0; S->atmtim[0] = S->atmtim[1] = S->atmtim[2] = 0.0; S->atmrec[0] = S->atmrec[1] = S->atmrec[2] = -1; S->atm_next = 0;
+    CK(cudaMemsetAsync(S->atmpot.p, 0, (size_t)NN * sizeof(double), S->st));
+    CK(cudaMemsetAsync(S->atmact.p, 0, (size_t)NN * sizeof(double), S->st));
+    CK(cudaMemsetAsync(S->atmold.p, 0, (size_t)NN * sizeof(double), S->st));
+    if (p.atm_none) {
+        S->htiatm = 1;
+        std::vector<int> m1(NN, -1);
+        CK(cudaMemcpy(S->ifatm.p, m1.data(), (size_t)NN * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(S->ifatmp.p, m1.data(), (size_t)NN * sizeof(int), cudaMemcpyHostToDevice));
+    } else {
+        CK(cudaMemsetAsync(S->ifatm.p, 0, (size_t)NN * sizeof(int), S->st));
+        CK(cudaMemsetAsync(S->ifatmp.p, 0, (size_t)NN * sizeof(int), S->st));
+        if (p.natm == 0) S->htiatm = 1;
+        else {
+            S->atmtim[2] = p.atm_time[0]; S->atmrec[2] = 0; S->atm_next = 1;
+            if (S->atmtim[2] <= 0.0) {   // ATMOLD = first record * area: reuse the interpolation kernel with slot 3 only, into ATMOLD
+                LAUNCH(S, k_atm_interp, nblk(NN, S->grid_n), RED_BLOCK, NN, S->atmtab.p, p.hspatm == 0 ? 1 : 0, -1, 0, 1, 0.0, 0.0, 0.0, p.ieto,
+                       p.scf, S->arenod.p, S->ifatm.p, 0, S->atmold.p, S->atmact.p);
+            }
+            atm_shift_read(S, S->time);
+            atm_interp_launch(S, 1, 2, S->time, 0);
+        }
+        LAUNCH(S, k_atmone, nblk(NN, S->grid_n), RED_BLOCK, NN, p.pmin, p.pondh_min, p.scf, S->atmpot.p, S->atmold.p, S->atmact.p, S->pnew.p,
+               S->ptimep.p, S->ifatm.p, S->ifatmp.p);
+    }
+    weight_and_copy(S);
+    LAUNCH(S, k_mbinit, 1, RED_BLOCK, NN, S->ifatmp.p, S->atmold.p, S->scal3.p);
+    double h3[3];
+    CK(cudaMemcpyAsync(h3, S->scal3.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+    chvelo_launch(S, S->ptimep.p);
+    int rc = step_final_sync(S);
+    if (rc) return rc;
+    S->aactp = h3[0]; S->aninp = h3[1]; S->anoutp = h3[2];
+    S->adinp = S->adoutp = S->ndinp = S->ndoutp = S->nninp = S->nnoutp = 0.0;
+    S->store0 = S->store1 = S->store2 = S->h_step->store1;
+    S->timep_dirty = 1;
+    (void)N;
+    return 0;
+}
+
+int32_t cathy_create(const CathyProblem *prob, CathySim **out)
+{
+    g_err[0] = 0;
+    *out = nullptr;
+    if (!prob || prob->abi_version != CATHY_ABI_VERSION) FAIL(-1, "ABI version mismatch");
+    if (prob->iopt != 1) FAIL(-2, "IOPT=%d: only the Picard scheme (IOPT=1) is implemented on the device so far", prob->iopt);
+    if (prob->kslope != 0) FAIL(-2, "KSLOPE=%d: only analytical moisture-curve derivatives (0) are implemented", prob->kslope);
+    if (prob->ivghu != 0) FAIL(-2, "IVGHU=%d: only van Genuchten curves (0) are implemented", prob->ivghu);
+    if (prob->lump == 0) FAIL(-2, "LUMP=0 (consistent mass matrix) is not implemented on the device");
+    if (prob->nlrelx != 0) FAIL(-2, "NLRELX != 0 (nonlinear relaxation) is not implemented on the device");
+    if (prob->isimgr != 1 && prob->isimgr != 2) FAIL(-2, "ISIMGR=%d not supported", prob->isimgr);
+    if (prob->deltat >= 1.0e15) FAIL(-2, "steady-state runs (DELTAT>=1e15) are not implemented");
+    if (prob->ituns > CATHY_MAXIT) FAIL(-2, "ITUNS larger than %d", CATHY_MAXIT);
+    CathySim *S = new CathySim();
+    int rc = create_impl(prob, S);
+    if (rc == 0) rc = init_atm_and_storage(S);
+    if (rc) { std::string keep = g_err; cathy_destroy(S); snprintf(g_err, sizeof g_err, "%s", keep.c_str()); return rc; }
+    // the caller's arrays are not referenced after this point, except the copied atm_time
+    *out = S;
+    return 0;
+}
+
+int32_t cathy_get_dims(const CathySim *S, int64_t dims[5])
+{
+    dims[0] = S->nnod; dims[1] = S->n; dims[2] = S->nt; dims[3] = S->nterm; dims[4] = 2 * S->nterm - S->n;
+    return 0;
+}
+int32_t cathy_get_mesh(const CathySim *S, double *x, double *y, double *z, int32_t *tetra)
+{
+    if (x) memcpy(x, S->hx.data(), (size_t)S->n * sizeof(double));
+    if (y) memcpy(y, S->hy.data(), (size_t)S->n * sizeof(double));
+    if (z) memcpy(z, S->hz.data(), (size_t)S->n * sizeof(double));
+    if (tetra)
+        for (int j = 0; j < S->nstr; ++j)
+            for (int i = 0; i < S->ntri; ++i) {
+                int pr[3][4];
+                gen_tets_of_prism(&S->htri[4 * (size_t)i], j * S->nnod, (j + 1) * S->nnod, pr);
+                size_t e0 = 3 * ((size_t)j * S->ntri + i);
+                for (int w = 0; w < 3; ++w) {
+                    for (int q = 0; q < 4; ++q) tetra[5 * (e0 + w) + q] = pr[w][q] + 1;
+                    tetra[5 * (e0 + w) + 4] = S->htri[4 * (size_t)i + 3];
+                }
+            }
+    return 0;
+}
+double cathy_initial_storage(const CathySim *S) { return S->store0; }
+
+int32_t cathy_get_state(CathySim *S, double *psi, double *sw, double *ckrw, double *qtranie, double *pond, double *atmact, double *atmpot,
+                        double *ovfl, int32_t *ifatm)
+{
+    CK(cudaSetDevice(S->p.device));
+    CK(cudaStreamSynchronize(S->st));
+    size_t bn = (size_t)S->n * sizeof(double), bs = (size_t)S->nnod * sizeof(double);
+    if (psi) CK(cudaMemcpy(psi, S->pnew.p, bn, cudaMemcpyDeviceToHost));
+    if (sw) CK(cudaMemcpy(sw, S->sw.p, bn, cudaMemcpyDeviceToHost));
+    if (ckrw) CK(cudaMemcpy(ckrw, S->ckrw.p, bn, cudaMemcpyDeviceToHost));
+    if (qtranie) CK(cudaMemcpy(qtranie, S->qtranie.p, bn, cudaMemcpyDeviceToHost));
+    if (pond) CK(cudaMemcpy(pond, S->pondnod.p, bs, cudaMemcpyDeviceToHost));
+    if (atmact) CK(cudaMemcpy(atmact, S->atmact.p, bs, cudaMemcpyDeviceToHost));
+    if (atmpot) CK(cudaMemcpy(atmpot, S->atmpot.p, bs, cudaMemcpyDeviceToHost));
+    if (ovfl) CK(cudaMemcpy(ovfl, S->ovflnod.p, bs, cudaMemcpyDeviceToHost));
+    if (ifatm) CK(cudaMemcpy(ifatm, S->ifatm.p, (size_t)S->nnod * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int32_t cathy_set_psi(CathySim *S, const double *psi)
+{
+    if (S->nstep != 1 || S->kbackt != 0 || S->itrtot != 0) FAIL(-1, "cathy_set_psi is only valid before the first step");
+    CK(cudaSetDevice(S->p.device));
+    CK(cudaMemcpy(S->ptimep.p, psi, (size_t)S->n * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(S->pnew.p, psi, (size_t)S->n * sizeof(double), cudaMemcpyHostToDevice));
+    return init_atm_and_storage(S);
+}
+
+// time loop body, SRC/cathy_main.f:2882-3829
+int32_t cathy_step(CathySim *S, CathyStepReport *rep)
+{
+    const CathyProblem &p = S->p;
+    if (S->finished) FAIL(-1, "simulation already finished");
+    CK(cudaSetDevice(p.device));
+    memset(rep, 0, sizeof *rep);
+    int64_t l0 = S->launches;
+    const int NN = S->nnod, N = S->n;
+    size_t bn = (size_t)N * sizeof(double), bs = (size_t)NN * sizeof(double);
+    CK(cudaEventRecord(S->ev0, S->st));
+    atmnxt(S);
+    CK(cudaMemsetAsync(S->d_flags.p + 1, 0, sizeof(int), S->st));
+    LAUNCH(S, k_etran, nblk(NN, S->grid_n), RED_BLOCK, NN, S->nstr, S->z.p, S->pnew.p, S->atmpot.p, S->veg.p, S->vegpar.p, p.scf, S->qtranie.p, S->d_flags.p + 1);
+    if (!S->surf) LAUNCH(S, k_switch_old, nblk(NN, S->grid_n), RED_BLOCK, NN, p.pmin, S->atmpot.p, S->ifatm.p, S->atmact.p, S->pnew.p);
+    else LAUNCH(S, k_adrstn, nblk(NN, S->grid_n), RED_BLOCK, NN, p.pmin, S->atmpot.p, S->ifatm.p, S->atmact.p, S->pnew.p);
+    weight_and_copy(S);
+    int nsurf = 0, status = 0;
+    for (;;) {
+        nsurf = 0;
+        if (S->surf && S->ponding) {
+            CK(cudaMemcpyAsync(S->d_akmax.p + 2, S->d_akmax.p, sizeof(double), cudaMemcpyDeviceToDevice, S->st));   // AK_MAX_SAV
+            copy_cells(S, S->q_in_kk_sav, S->q_in_kk); copy_cells(S, S->q_out_kk_1_sav, S->q_out_kk_1);
+            copy_cells(S, S->q_out_kk_2_sav, S->q_out_kk_2); copy_cells(S, S->volume_kk_sav, S->volume_kk);
+            nsurf = surf_flowtra(S);
+            if (nsurf < 0) return nsurf;
+            S->nsurft += nsurf;
+        }
+        CK(cudaMemcpyAsync(S->pold.p, S->pnew.p, bs, cudaMemcpyDeviceToDevice, S->st));   // VCOPYR(NNOD,POLD,PNEW), SRC/cathy_main.f:3099
+        int rc = flow3d(S, &status);
+        if (rc) return rc;
+        if (status != 1) break;
+        if (S->surf) {
+            CK(cudaMemcpyAsync(S->d_akmax.p + 1, S->d_akmax.p + 2, sizeof(double), cudaMemcpyDeviceToDevice, S->st));   // AK_MAX_P = AK_MAX_SAV
+            copy_cells(S, S->q_in_kk_p, S->q_in_kk_sav); copy_cells(S, S->q_out_kk_1_p, S->q_out_kk_1_sav);
+            copy_cells(S, S->q_out_kk_2_p, S->q_out_kk_2_sav); copy_cells(S, S->volume_kk_p, S->volume_kk_sav);
+            zero_cells(S, S->q_in_kkp1); zero_cells(S, S->q_out_kkp1_1); zero_cells(S, S->q_out_kkp1_2); zero_cells(S, S->volume_kkp1);
+        }
+        bkstep(S);
+    }
+    if (S->surf) LAUNCH(S, k_pond_zero, nblk(NN, S->grid_n), RED_BLOCK, NN, S->pnew.p, S->pondnod.p);
+    chvelo_launch(S, S->pnew.p);
+    if (S->surf) {
+        CK(cudaMemcpyAsync(&S->d_step.p->q_out1, S->q_out_kkp1_1.p + S->outlet_cell, sizeof(double), cudaMemcpyDeviceToDevice, S->st));
+        CK(cudaMemcpyAsync(&S->d_step.p->q_out2, S->q_out_kkp1_2.p + S->outlet_cell, sizeof(double), cudaMemcpyDeviceToDevice, S->st));
+        CK(cudaMemcpyAsync(&S->d_step.p->ak_max, S->d_akmax.p, sizeof(double), cudaMemcpyDeviceToDevice, S->st));
+    }
+    // end-of-step copies (SRC/cathy_main.f:3762-3790) are queued before the single synchronisation of the step
+    int rc = 0;
+    LAUNCH(S, k_step_final, 1, RED_BLOCK, NN, S->nstr, p.pmin, p.pondh_min, S->grid_n, S->store_part.p, S->ifatm.p, S->atmpot.p, S->atmact.p,
+           S->pnew.p, S->d_step.p);
+    CK(cudaMemcpyAsync(S->h_step, S->d_step.p, sizeof(StepOut), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaMemcpyAsync(S->ifatmp.p, S->ifatm.p, (size_t)NN * sizeof(int), cudaMemcpyDeviceToDevice, S->st));
+    CK(cudaMemcpyAsync(S->atmold.p, S->atmact.p, bs, cudaMemcpyDeviceToDevice, S->st));
+    CK(cudaMemcpyAsync(S->ptimep.p, S->pnew.p, bn, cudaMemcpyDeviceToDevice, S->st));
+    S->timep_dirty = 1;
+    if (S->surf) {
+        S->pondp = S->ponding;
+        CK(cudaMemcpyAsync(S->ovflp.p, S->ovflnod.p, bs, cudaMemcpyDeviceToDevice, S->st));
+        copy_cells(S, S->q_in_kk, S->q_in_kkp1); zero_cells(S, S->q_in_kkp1);
+        copy_cells(S, S->q_out_kk_1, S->q_out_kkp1_1); zero_cells(S, S->q_out_kkp1_1);
+        copy_cells(S, S->q_out_kk_2, S->q_out_kkp1_2); zero_cells(S, S->q_out_kkp1_2);
+        copy_cells(S, S->volume_kk, S->volume_kkp1); zero_cells(S, S->volume_kkp1);
+    }
+    int h_err = 0;
+    CK(cudaMemcpyAsync(&h_err, S->d_flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaEventRecord(S->ev1, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    if (h_err) FAIL(-5, "ETRAN: ZROOT reaches the bottom layer (decrease ZROOT)");
+    (void)rc;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, S->ev0, S->ev1);
+    const StepOut &so = *S->h_step;
+    S->store1 = so.store1; S->store2 = S->store2 + S->dstore;
+    for (int q = 0; q < 9; ++q) S->hgflag[q] += so.hgflag[q];
+    rep->nstep = S->nstep; rep->deltat = S->deltat; rep->time = S->time; rep->iter = S->iter; rep->nitert = S->nitert;
+    rep->kbackt = S->kbackt; rep->nsurf = nsurf; rep->nsurft = S->nsurft; rep->noback = status == 2; rep->ponding = S->ponding;
+    rep->store1 = S->store1; rep->store2 = S->store2; rep->dstore = S->dstore; rep->vin = S->vin; rep->vout = S->vout;
+    rep->erras = S->erras; rep->errel = S->errel; rep->adin = S->adin; rep->adout = S->adout; rep->anin = S->anin; rep->anout = S->anout;
+    rep->apot = so.apot; rep->aact = so.aact; rep->ovflow = so.ovflow; rep->reflow = so.reflow;
+    rep->fhort = (double)so.nhort / NN; rep->fdunn = (double)so.ndunn / NN; rep->fpond = (double)so.npond / NN; rep->fsat = (double)so.nsat / NN;
+    rep->n_iter_rec = std::min(S->iter, CATHY_MAXIT);
+    memcpy(rep->it, S->itrec, sizeof(CathyIterRecord) * rep->n_iter_rec);
+    rep->klsfai_total = S->klsfai; rep->kback_total = S->kback;
+    if (S->surf) { rep->q_outlet_1 = so.q_out1; rep->q_outlet_2 = so.q_out2; rep->ak_max = so.ak_max; }
+    S->adinp = S->adin; S->adoutp = S->adout; S->aninp = S->anin; S->anoutp = S->anout;
+    if (status == 2) S->finished = 1;
+    else if (std::fabs(S->time - S->tmax) <= 0.001 * S->deltat) S->finished = 1;
+    else {   // TIMUPD + TIMNXT (SRC/timupd.f, SRC/timnxt.f)
+        S->timep = S->time;
+        if (S->iter < p.ituns1) { S->deltat = S->deltat * p.dtmagm + p.dtmaga; if (S->deltat > S->dtmax) S->deltat = S->dtmax; }
+        if (S->iter >= p.ituns2) { S->deltat = S->deltat * p.dtredm - p.dtreds; if (S->deltat < S->dtmin) S->deltat = S->dtmin; }
+        if ((S->time + S->deltat) >= S->tmax) { S->deltat = S->tmax - S->time; S->time = S->tmax; }
+        else { if ((S->time + 2 * S->deltat) > S->tmax) S->deltat = (S->tmax - S->time) / 2; S->time = S->time + S->deltat; }
+        S->dtgmin = !(S->deltat <= S->dtmin);
+        S->nstep++; S->iter = 1; S->nitert = 0; S->kbackt = 0; S->nsurft = 0;
+        if (!(S->time <= S->tmax)) S->finished = 1;
+    }
+    rep->finished = S->finished; rep->next_deltat = S->deltat; rep->next_time = S->time;
+    rep->gpu_ms = ms; rep->launches = S->launches - l0;
+    return 0;
+}
+
+// ---- kernel-level entry points ------------------------------------------------------------
+int32_t cathy_debug_assemble(CathySim *S, double deltat, int32_t *topol, int32_t *ja, double *coef1, double *rhs)
+{
+    CK(cudaSetDevice(S->p.device));
+    S->timep_dirty = 1;
+    int rc = assemble_system(S, deltat);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(S->st));
+    const int n = S->n;
+    std::vector<double> hA, hd;
+    if (coef1) {
+        hA.resize((size_t)NDIAG * n); hd.resize(n);
+        CK(cudaMemcpy(hA.data(), S->A.p, hA.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(hd.data(), S->diag_bc.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    int64_t m = 0;
+    for (int k = 0; k < n; ++k) {
+        if (topol) topol[k] = (int32_t)(m + 1);
+        for (int d = 0; d < NDIAG; ++d) {
+            if (d > 0 && !S->hexist[(size_t)d * n + k]) continue;
+            if (ja) ja[m] = k + S->off[d] + 1;
+            if (coef1) coef1[m] = d == 0 ? hd[k] : hA[(size_t)d * n + k];
+            ++m;
+        }
+    }
+    if (topol) topol[n] = (int32_t)(m + 1);
+    if (rhs) CK(cudaMemcpy(rhs, S->rhs.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int32_t cathy_debug_spmv(CathySim *S, const double *x, double *y, int32_t reps, double *ms)
+{
+    CK(cudaSetDevice(S->p.device));
+    const int n = S->n;
+    CK(cudaMemcpy(S->wp0.p, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    Diag A = make_diag(S, S->A.p);
+    reps = std::max(reps, 1);
+    LAUNCH(S, k_spmv, nblk(n, S->grid_n), RED_BLOCK, n, A, S->diag_bc.p, S->wp0.p, S->wbv.p);   // warm-up
+    CK(cudaEventRecord(S->ev0, S->st));
+    for (int r = 0; r < reps; ++r) LAUNCH(S, k_spmv, nblk(n, S->grid_n), RED_BLOCK, n, A, S->diag_bc.p, S->wp0.p, S->wbv.p);
+    CK(cudaEventRecord(S->ev1, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    float t = 0.f;
+    cudaEventElapsedTime(&t, S->ev0, S->ev1);
+    if (ms) *ms = t / reps;
+    CK(cudaMemcpy(y, S->wbv.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int32_t cathy_debug_solve(CathySim *S, double *sol, int32_t *niter, double *err, double *ms)
+{
+    CK(cudaSetDevice(S->p.device));
+    CK(cudaEventRecord(S->ev0, S->st));
+    int rc = solve_system(S);
+    if (rc) return rc;
+    CK(cudaEventRecord(S->ev1, S->st));
+    CK(cudaMemcpyAsync(S->h_iter, S->d_iter.p, sizeof(IterOut), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    float t = 0.f;
+    cudaEventElapsedTime(&t, S->ev0, S->ev1);
+    if (ms) *ms = t;
+    if (niter) *niter = S->h_iter->pcg_niter;
+    if (err) *err = S->h_iter->pcg_err;
+    if (sol) CK(cudaMemcpy(sol, S->pdiff.p, (size_t)S->n * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

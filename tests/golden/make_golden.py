@@ -1,0 +1,84 @@
+"""Generates the committed fixtures under tests/golden/ (run HERE, where /root/reference is mounted).
+
+  weill_exemple/   inputs + prepro rasters of the reference's bundled hillslope (BASELINE config 1,
+                   /root/reference/examples/SSHydro/weill_exemple) and the outputs COMMITTED in the
+                   reference next to them (mbeconv, cumflowvol, hgraph, vp verbatim; psi/sw as .npz).
+  storm20/         a synthetic 20x20x15 storm on a saturated hillslope (rain -> ponding, runoff routing, back-steps);
+                   prepro rasters from the reference's pre-processor ELF, outputs from the reference's
+                   processor ELF (oracle/_ref), both run by this script.
+
+Usage: python tests/golden/make_golden.py
+"""
+import os
+import shutil
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import oracle  # noqa: E402
+from pycathy_wrapper_b200 import synthetic  # noqa: E402
+
+KEEP_PREPRO = ["dem", "zone", "lakes_map", "qoi_a", "dtm_w_1", "dtm_w_2", "dtm_p_outflow_1", "dtm_p_outflow_2",
+               "dtm_local_slope_1", "dtm_local_slope_2", "dtm_epl_1", "dtm_epl_2", "dtm_kSs1_sf_1", "dtm_kSs1_sf_2",
+               "dtm_Ws1_sf_1", "dtm_Ws1_sf_2", "dtm_b1_sf", "dtm_y1_sf", "dtm_nrc", "hap.in"]
+VERBATIM = ["mbeconv", "cumflowvol", "hgraph", "vp"]
+
+
+def read_blocks(path):
+    steps, times, blocks, cur = [], [], [], []
+    with open(path) as fh:
+        for ln in fh:
+            if "NSTEP" in ln:
+                if cur:
+                    blocks.append(np.array(cur))
+                    cur = []
+                a = ln.split()
+                steps.append(int(a[0]))
+                times.append(float(a[1]))
+            elif "HSPSW" in ln:
+                continue
+            else:
+                cur.extend(float(v) for v in ln.split())
+    blocks.append(np.array(cur))
+    return np.array(steps), np.array(times), np.array(blocks)
+
+
+def stash(src_prj, out_dir, dst):
+    for sub in ("input", "prepro", "golden"):
+        os.makedirs(os.path.join(dst, sub), exist_ok=True)
+    shutil.copy(os.path.join(src_prj, "cathy.fnames"), os.path.join(dst, "cathy.fnames"))
+    for f in os.listdir(os.path.join(src_prj, "input")):
+        shutil.copy(os.path.join(src_prj, "input", f), os.path.join(dst, "input", f))
+    for f in KEEP_PREPRO:
+        if os.path.exists(os.path.join(src_prj, "prepro", f)):
+            shutil.copy(os.path.join(src_prj, "prepro", f), os.path.join(dst, "prepro", f))
+    for f in VERBATIM:
+        shutil.copy(os.path.join(out_dir, f), os.path.join(dst, "golden", f))
+    for f in ("psi", "sw"):
+        s, t, b = read_blocks(os.path.join(out_dir, f))
+        np.savez_compressed(os.path.join(dst, "golden", f + ".npz"), nstep=s, time=t, values=b)
+    for r, _d, fs in os.walk(dst):
+        os.chmod(r, 0o755)
+        for f in fs:
+            os.chmod(os.path.join(r, f), 0o644)
+
+
+def main():
+    ref = "/root/reference/examples/SSHydro/weill_exemple"
+    stash(ref, os.path.join(ref, "output"), os.path.join(HERE, "weill_exemple"))
+    tmp = "/tmp/golden_storm20"
+    shutil.rmtree(tmp, ignore_errors=True)
+    synthetic.make_project(tmp, 20, 20, 15, ic=("hydrostatic",), ISIMGR=2, TMAX=1800.0, TIMPRT=[900.0, 1800.0], DELTAT=1.0, DTMIN=1e-4,
+                           NODVP=[441], atmbc=[(0.0, 0.0), (60.0, 1.0e-4), (600.0, 1.0e-4), (660.0, 0.0), (1.0e9, 0.0)],
+                           zratio=[0.002, 0.004, 0.006, 0.008, 0.01, 0.01, 0.02, 0.02, 0.05, 0.05, 0.1, 0.1, 0.2, 0.2, 0.22])
+    oracle.run_prepro(tmp)
+    oracle.run_reference(tmp, tmp + "_ref", "20x20x15")
+    stash(tmp, os.path.join(tmp + "_ref", "output"), os.path.join(HERE, "storm20"))
+    print("golden fixtures written")
+
+
+if __name__ == "__main__":
+    main()
