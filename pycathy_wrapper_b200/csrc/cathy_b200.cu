@@ -601,8 +601,9 @@ __global__ void k_atm_interp(int nnod, const double *__restrict__ tab, int strid
                              double *__restrict__ atmact)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnod; i += gridDim.x * blockDim.x) {
-        double va = rec_a >= 0 ? tab[(size_t)rec_a * stride * nnod + (stride ? i : 0)] : 0.0;
-        double vb = rec_b >= 0 ? tab[(size_t)rec_b * stride * nnod + (stride ? i : 0)] : 0.0;
+        // stride = 1: one value per surface node and record; stride = 0: homogeneous, one value per record
+        double va = rec_a >= 0 ? (stride ? tab[(size_t)rec_a * nnod + i] : tab[rec_a]) : 0.0;
+        double vb = rec_b >= 0 ? (stride ? tab[(size_t)rec_b * nnod + i] : tab[rec_b]) : 0.0;
         double pot;
         if (use_b_only) pot = vb * arenod[i];
         else {

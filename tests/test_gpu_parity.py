@@ -1,0 +1,161 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+Tolerances: pressure head 1e-6 relative or 1e-8 m absolute (BASELINE.json north_star); integer
+quantities (accepted step sequence, nonlinear iteration counts, back-steps) exact."""
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def psi_close(a, b, rtol=1e-6, atol=1e-8):
+    d = np.abs(a - b)
+    return bool(np.all(d <= np.maximum(rtol * np.abs(b), atol))), float(d.max())
+
+
+def full_from_upper(topol, ja, coef, n):
+    import scipy.sparse as sp
+    rows = np.repeat(np.arange(n), np.diff(topol))
+    U = sp.csr_matrix((coef, (rows, ja - 1)), shape=(n, n))
+    return (U + sp.triu(U, 1).T).tocsr()
+
+
+@pytest.fixture(scope="module")
+def weill():
+    from pycathy_wrapper_b200.project import load_project
+    return load_project(os.path.join(GOLDEN, "weill_exemple"))
+
+
+def test_mesh_and_initial_storage(gpu_lib, oracle_mod, weill):
+    from pycathy_wrapper_b200.capi import Simulation
+    g, c = Simulation(gpu_lib, weill), oracle_mod.simulation(weill)
+    assert (g.nnod, g.n, g.nt, g.nterm, g.nnz) == (c.nnod, c.n, c.nt, c.nterm, c.nnz) == (441, 7056, 36000, 52111, 97166)
+    for a, b in zip(g.mesh(), c.mesh()):
+        assert np.array_equal(a, b)
+    assert abs(g.initial_storage() - c.initial_storage()) <= 1e-12 * c.initial_storage()
+
+
+@pytest.mark.parametrize("dt", [0.02, 5.0, 100.0])
+def test_assembled_system_matches_oracle(gpu_lib, oracle_mod, weill, dt):
+    """PICUNS+ASSPIC+RHSPIC+CFMATP+RHSGRV+BCPIC: same CSR pattern (bit exact), values to 1e-12 relative."""
+    from pycathy_wrapper_b200.capi import Simulation
+    g, c = Simulation(gpu_lib, weill), oracle_mod.simulation(weill)
+    tg, jg, ag, bg = g.debug_assemble(dt)
+    tc, jc, ac, bc = c.debug_assemble(dt)
+    assert np.array_equal(tg, tc) and np.array_equal(jg, jc)
+    scale = np.abs(ac).max()
+    big = ac > 1e80
+    assert np.array_equal(big, ag > 1e80)
+    assert np.max(np.abs(ag[~big] - ac[~big])) <= 1e-12 * np.abs(ac[~big]).max()
+    assert np.max(np.abs(bg - bc)) <= 1e-11 * max(np.abs(bc).max(), 1e-30), (np.abs(bg - bc).max(), np.abs(bc).max())
+    assert scale > 0
+
+
+def test_spmv_matches_oracle(gpu_lib, oracle_mod, weill):
+    from pycathy_wrapper_b200.capi import Simulation
+    g, c = Simulation(gpu_lib, weill), oracle_mod.simulation(weill)
+    g.debug_assemble(1.0)
+    c.debug_assemble(1.0)
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(g.n)
+    x[:441] = 0.0                      # Dirichlet rows carry the 1.7e91 penalty: keep them out of the comparison
+    yg, _ = g.debug_spmv(x)
+    yc, _ = c.debug_spmv(x)
+    assert np.max(np.abs(yg[441:] - yc[441:])) <= 1e-12 * np.abs(yc[441:]).max()
+
+
+@pytest.mark.parametrize("dt", [0.02, 50.0])
+def test_pcg_solution_matches_oracle(gpu_lib, oracle_mod, weill, dt):
+    """SYMSLV: the device PCG (different preconditioner) must reach the same solution of the same system."""
+    from pycathy_wrapper_b200.capi import Simulation
+    g, c = Simulation(gpu_lib, weill), oracle_mod.simulation(weill)
+    g.debug_assemble(dt)
+    c.debug_assemble(dt)
+    xg, ng, eg, _ = g.debug_solve()
+    xc, nc, ec, _ = c.debug_solve()
+    assert eg <= 1e-10 and ec <= 1e-10
+    assert ng < 20 * 500
+    assert np.max(np.abs(xg - xc)) <= 1e-7 * max(np.abs(xc).max(), 1e-12), (np.abs(xg - xc).max(), np.abs(xc).max(), ng, nc)
+
+
+def _run_both(gpu_lib, oracle_mod, prj, nsteps=None):
+    from pycathy_wrapper_b200.capi import Simulation
+    g, c = Simulation(gpu_lib, prj), oracle_mod.simulation(prj)
+    k = 0
+    while True:
+        rg, rc = g.step(), c.step()
+        k += 1
+        assert (rg.nstep, rg.iter, rg.kbackt, rg.nsurf) == (rc.nstep, rc.iter, rc.kbackt, rc.nsurf), \
+            f"step {k}: gpu (nstep,iter,back,nsurf)={(rg.nstep, rg.iter, rg.kbackt, rg.nsurf)} oracle={(rc.nstep, rc.iter, rc.kbackt, rc.nsurf)}"
+        assert abs(rg.deltat - rc.deltat) <= 1e-12 * rc.deltat and abs(rg.time - rc.time) <= 1e-12 * rc.time
+        assert abs(rg.store1 - rc.store1) <= 1e-9 * abs(rc.store1)
+        assert abs(rg.erras) <= max(2.0 * abs(rc.erras), 1e-9 * abs(rc.store1)), (rg.erras, rc.erras)
+        assert rg.finished == rc.finished
+        if rg.finished or (nsteps and k >= nsteps):
+            break
+    return g, c, rg, rc
+
+
+def test_hillslope_full_run_same_steps_and_heads(gpu_lib, oracle_mod, weill):
+    """BASELINE config 1 end to end: 235 accepted steps incl. 8 back-steps and 1,793 routing sub-steps."""
+    g, c, rg, rc = _run_both(gpu_lib, oracle_mod, weill)
+    assert rg.nstep == 235
+    sg, sc = g.state(), c.state()
+    ok, dmax = psi_close(sg["psi"], sc["psi"])
+    assert ok, dmax
+    assert np.array_equal(sg["ifatm"], sc["ifatm"])
+    assert np.max(np.abs(sg["sw"] - sc["sw"])) < 1e-6
+    assert abs(rg.q_outlet_1 - rc.q_outlet_1) <= 1e-6 * max(abs(rc.q_outlet_1), 1e-12)
+    gold = np.load(os.path.join(GOLDEN, "weill_exemple", "golden", "psi.npz"))
+    ok, dmax = psi_close(sg["psi"], gold["values"][-1], rtol=2e-6, atol=1e-7)   # file carries 7 significant digits
+    assert ok, dmax
+
+
+def test_storm_full_run(gpu_lib, oracle_mod):
+    from pycathy_wrapper_b200.project import load_project
+    prj = load_project(os.path.join(GOLDEN, "storm20"))
+    g, c, rg, rc = _run_both(gpu_lib, oracle_mod, prj)
+    ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
+    assert ok, dmax
+    assert rg.q_outlet_1 > 0
+
+
+def test_infiltration_subsurface_only(gpu_lib, oracle_mod, tmp_path):
+    """ISIMGR=1 (SWITCH_OLD path), unsaturated start, rain pulse, geometric layers."""
+    from pycathy_wrapper_b200 import synthetic
+    from pycathy_wrapper_b200.project import load_project
+    p = synthetic.make_project(str(tmp_path / "inf"), 12, 17, 8, ic=("uniform", -1.0), TMAX=1200.0, TIMPRT=[1200.0],
+                               atmbc=[(0.0, 0.0), (10.0, 2.0e-5), (600.0, 2.0e-5), (610.0, 0.0), (1e9, 0.0)])
+    prj = load_project(p)
+    g, c, rg, rc = _run_both(gpu_lib, oracle_mod, prj)
+    ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
+    assert ok, dmax
+
+
+def test_run_processor_writes_reference_format(gpu_lib, tmp_path):
+    """Through the plugin-level call: output files parse like the reference's and match the golden ones."""
+    from pycathy_wrapper_b200.processor import run_processor
+    dst = str(tmp_path / "prj")
+    shutil.copytree(os.path.join(GOLDEN, "weill_exemple"), dst)
+    res = run_processor(dst)
+    assert res.nstep == 235 and res.finished_ok
+    got = np.loadtxt(os.path.join(dst, "output", "mbeconv"), skiprows=3)
+    ref = np.loadtxt(os.path.join(GOLDEN, "weill_exemple", "golden", "mbeconv"), skiprows=3)
+    assert got.shape == ref.shape
+    assert np.array_equal(got[:, [0, 3]], ref[:, [0, 3]])            # NSTEP, NLIN (nonlinear its) identical
+    assert np.allclose(got[:, 1:3], ref[:, 1:3], rtol=1e-6)          # DELTAT, TIME
+    assert np.allclose(got[:, 5], ref[:, 5], rtol=1e-6)              # STORE1
+    with open(os.path.join(dst, "output", "psi")) as fh:
+        assert fh.readline().endswith("NSTEP   TIME\n")
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from pycathy_wrapper_b200 import capi
+    monkeypatch.setattr(capi, "_LIB", None)
+    monkeypatch.setattr(capi, "library_path", lambda: "/nonexistent/libcathy_b200.so")
+    with pytest.raises(capi.CathyLibraryError):
+        capi.load_library()
