@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the CATHY Richards hot path on B200.
+
+Metric (BASELINE.json): node-timesteps/s = N x accepted time steps / seconds of the time loop.
+Workload at N=1 (BASELINE.json configs[1]): synthetic 200x200 DEM x 20 layers (848,421 nodes,
+4.8 M tetrahedra), van Genuchten, Picard + PCG, infiltration pulse, fp64.
+A "step" is one ACCEPTED time step of the hot path (all its Picard iterations, linear solves,
+mass balance, boundary switching and any back-stepped attempts).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size NROWxNCOLxNSTR]
+
+N > 1: launched under torchrun, one rank per GPU; every rank advances its own ensemble member on the
+same mesh (the path shards over independent members, no data-path collective) -> "scaling": "weak".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from pycathy_wrapper_b200 import synthetic  # noqa: E402
+from pycathy_wrapper_b200.project import load_project  # noqa: E402
+
+PCG_BYTES_PER_ROW_ITER = 168.0     # phase A 104 B + phase B 64 B per row and iteration (fp64, DIA layout)
+PCG_BYTES_PER_ROW_SETUP = 152.0    # x0, residual and first preconditioner application
+SPMV_BYTES_PER_ROW = 80.0          # 8 diagonals + x + y
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def make_workload(size, member: int = 0):
+    nrow, ncol, nstr = size
+    d = tempfile.mkdtemp(prefix="cathy_bench_")
+    ks = 1.88e-4 * (1.0 + 0.05 * member)                     # ensemble members differ in Ks (weak scaling replicas)
+    row = (ks, ks, ks, 1.0e-5, 0.55, 1.46, 0.15, 0.03125)
+    synthetic.make_project(d, nrow, ncol, nstr, ic=("wt", 1.0), ISIMGR=1, DELTAT=1.0, DTMIN=1e-2, DTMAX=100.0,
+                           TMAX=7200.0, TIMPRT=[7200.0], NODVP=[1], soil_rows=[row] * nstr, hspatm=0,
+                           atmbc=[(0.0, np.zeros((nrow + 1) * (ncol + 1))), (60.0, np.full((nrow + 1) * (ncol + 1), 2.0e-5)),
+                                  (3600.0, np.full((nrow + 1) * (ncol + 1), 2.0e-5)),
+                                  (3660.0, np.zeros((nrow + 1) * (ncol + 1))), (1.0e9, np.zeros((nrow + 1) * (ncol + 1)))])
+    prj = load_project(d)
+    shutil.rmtree(d, ignore_errors=True)
+    return prj
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.idx, self.samples, self.reasons, self.stop_flag, self.maxmhz = gpu_index, [], set(), False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.maxmhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.maxmhz,
+                "reasons": sorted(self.reasons)}
+
+
+def run_ours(args, size):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    from pycathy_wrapper_b200.capi import Simulation, load_library
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+    lib = load_library()
+    prj = make_workload(size, member=rank)
+    nnod = prj.nnod
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def rank_max(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def rank_sum(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---------------- device-resident measurement ("value") ----------------
+    sim = Simulation(lib, prj, device=local)
+    n = sim.n
+    for _ in range(args.warmup):
+        sim.step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    gpu_ms = pcg_ms = 0.0
+    pcg_iters = pcg_solves = launches = nl_its = 0
+    for _ in range(args.steps):
+        rep = sim.step()
+        gpu_ms += rep.gpu_ms
+        pcg_ms += rep.pcg_ms
+        pcg_iters += rep.pcg_iters
+        pcg_solves += rep.pcg_solves
+        launches += rep.launches
+        nl_its += rep.iter
+        if rep.finished:
+            raise SystemExit("bench.py: workload finished before K steps; lower --steps")
+    barrier()
+    wall = time.perf_counter() - t0
+    sampler.stop_flag = True
+    # device time of the timed region = sum of per-step CUDA-event times on the simulation's stream
+    dev_s = rank_max(gpu_ms / 1e3)
+    wall_s = rank_max(wall)
+    value = world * n * args.steps / wall_s
+    # SpMV roofline sample on the last assembled system
+    x = np.random.default_rng(0).standard_normal(n)
+    _, spmv_ms = sim.debug_spmv(x, reps=50)
+    sim.close()
+
+    # ---------------- end-to-end through the C ABI with host buffers ("e2e") ----------------
+    sim = Simulation(lib, prj, device=local)
+    forcing = np.ascontiguousarray(prj.atm_values[1])          # pinned by torch below
+    pin = torch.from_numpy(forcing.copy()).pin_memory()
+    forcing = pin.numpy()
+    for _ in range(args.warmup):
+        sim.upload_atm_record(1, forcing)
+        sim.step()
+        sim.state()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sim.upload_atm_record(1, forcing)                       # H2D: this step's forcing record
+        sim.step()
+        st = sim.state()                                        # D2H: psi, sw, ckrw, ... (what DETOUT prints)
+    barrier()
+    e2e_s = rank_max(time.perf_counter() - t0)
+    d2h = sum(v.nbytes for v in st.values())
+    h2d = forcing.nbytes
+    sim.close()
+    e2e_value = world * n * args.steps / e2e_s
+
+    peak, peak_src = measured_peaks()
+    pcg_bytes = (pcg_iters * PCG_BYTES_PER_ROW_ITER + pcg_solves * PCG_BYTES_PER_ROW_SETUP) * n
+    achieved = pcg_bytes / (pcg_ms / 1e3) / 1e9 if pcg_ms > 0 else None
+    out = {
+        "metric": "node-timesteps/s", "value": value, "unit": "node-timesteps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall_s / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic %dx%d DEM x %d layers (%d nodes, %d tets), van Genuchten, Picard+PCG, infiltration pulse on a hillslope with a water table 2 m deep (INDP=3), "
+                               "ISIMGR=1, first %d accepted steps after %d warm-up" % (size[1], size[0], size[2], n, sim.nt, args.steps, args.warmup),
+                   "parallelism": "1 ensemble member per GPU" if world > 1 else "single forward run",
+                   "l2": "per-iteration working set (~%.0f MB) vs 126 MB L2: inputs are not larger than L2; no flush between PCG iterations (they are consecutive launches of one solve)" % (n * 21 * 8 / 1e6),
+                   "nonlinear_its": nl_its, "pcg_iters": pcg_iters, "pcg_solves": pcg_solves},
+        "device_ms_per_step": 1e3 * dev_s / args.steps,
+        "e2e": {"value": e2e_value, "unit": "node-timesteps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "hbm", "kernel": "k_pcg (persistent PCG: SpMV + fused vector ops)", "achieved": achieved,
+                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                     "traffic": None, "share_of_step": pcg_ms / gpu_ms if gpu_ms else None,
+                     "spmv_only": {"achieved": SPMV_BYTES_PER_ROW * n / (spmv_ms / 1e3) / 1e9, "ms": spmv_ms,
+                                   "frac": SPMV_BYTES_PER_ROW * n / (spmv_ms / 1e3) / 1e9 / peak,
+                                   "csr_equivalent_gbs": (12.0 * sim.nnz + 20.0 * n) / (spmv_ms / 1e3) / 1e9}},
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(size, budget_s=args.cpu_budget)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(size, budget_s: float = 25.0, max_steps: int = 1000):
+    """The CPU oracle (a C port of the reference's algorithm; the reference ELFs cannot hold this mesh)
+    timed on a bounded sample of the same workload: the first accepted step(s), single thread."""
+    from oracle import oracle
+    prj = make_workload(size)
+    sim = oracle.simulation(prj)
+    t0 = time.perf_counter()
+    k = 0
+    while True:
+        rep = sim.step()
+        k += 1
+        if time.perf_counter() - t0 > budget_s or rep.finished or k >= max_steps:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": sim.n * k / dt, "unit": "node-timesteps/s", "cores": 1, "kind": "port",
+            "sample": "first %d accepted time step(s) of the same workload (%.1f s of CPU work, sequential IC(0)-PCG as in the reference)" % (k, dt)}
+
+
+def run_reference(args, size):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import __graft_entry__ as g
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], check=True)
+    from oracle import oracle
+    prj = make_workload(size)
+    sim = oracle.simulation(prj)
+    n = sim.n
+    budget = 150.0
+    t_w = time.perf_counter()
+    nw = 0
+    for _ in range(args.warmup):
+        if time.perf_counter() - t_w > 30.0:
+            break
+        sim.step()
+        nw += 1
+    t0 = time.perf_counter()
+    k = 0
+    for _ in range(args.steps):
+        sim.step()
+        k += 1
+        if time.perf_counter() - t0 > budget:
+            break
+    dt = time.perf_counter() - t0
+    v = n * k / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "node-timesteps/s", "value": v, "unit": "node-timesteps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": k, "warmup": nw, "ms_per_step": 1e3 * dt / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic %dx%d DEM x %d layers (%d nodes), same project files as the GPU arm; CPU restatement of the reference "
+                               "(oracle port: no Fortran compiler here and the shipped ELFs are dimensioned for <= 82,416 nodes)" % (size[1], size[0], size[2], n)},
+        "cpu_baseline": {"value": v, "unit": "node-timesteps/s", "cores": 1, "kind": "port",
+                         "sample": "%d accepted step(s) after %d warm-up, time-boxed to %.0f s; the reference has no intra-run threading" % (k, nw, budget)},
+        "e2e": {"value": v, "unit": "node-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+    del g
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", default="200x200x20")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-budget", type=float, default=25.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    size = tuple(int(v) for v in args.size.lower().split("x"))
+    if args.impl == "reference":
+        run_reference(args, size)
+    else:
+        run_ours(args, size)
+
+
+if __name__ == "__main__":
+    main()

@@ -116,6 +116,9 @@ typedef struct CathyStepReport {
     double q_outlet_1, q_outlet_2; /* Q_OUT_KKP1_SN_1/2 at the outlet cell (SRC/detoutq.f) */
     double gpu_ms; /* device time of this step (CUDA events), 0 for the CPU oracle */
     int64_t launches; /* kernels launched during this step                         */
+    double pcg_ms;      /* device time inside the PCG kernel over all solves of this step (incl. back-stepped attempts) */
+    int64_t pcg_iters;  /* PCG iterations over all those solves */
+    int64_t pcg_solves; /* number of linear solves (nonlinear iterations incl. back-stepped attempts) */
     CathyIterRecord it[CATHY_MAXIT];
 } CathyStepReport;
 
@@ -151,6 +154,10 @@ int32_t cathy_get_state(CathySim *sim, double *psi, double *sw, double *ckrw, do
 /* Overwrite the pressure-head state (DA restart; stands for pyCATHY update_ic(INDP=1) +
  * relaunch, pyCATHY/cathy_tools.py:1863-1875).  Only valid before the first step. */
 int32_t cathy_set_psi(CathySim *sim, const double *psi);
+/* Overwrite record `rec` (0-based) of the atmospheric forcing table with new rates (stands for the
+ * reference reading the next (TIME, ATMINP) record of input/atmbc as the run proceeds, SRC/atmnxt.f:34-45).
+ * vals: [NNOD] when HSPATM = 0, [1] otherwise.  Host -> device copy on the handle's stream. */
+int32_t cathy_upload_atm_record(CathySim *sim, int32_t rec, const double *vals);
 
 /* ---- kernel-level entry points used by parity tests and bench.py -------------------- */
 /* Assemble the Picard system at the current state for time step `deltat` without solving

@@ -82,6 +82,7 @@ class CathyStepReport(C.Structure):
         ("next_deltat", C.c_double), ("next_time", C.c_double),
         ("ak_max", C.c_double), ("q_outlet_1", C.c_double), ("q_outlet_2", C.c_double), ("gpu_ms", C.c_double),
         ("launches", C.c_int64),
+        ("pcg_ms", C.c_double), ("pcg_iters", C.c_int64), ("pcg_solves", C.c_int64),
         ("it", CathyIterRecord * MAXIT),
     ]
 
@@ -171,7 +172,7 @@ class CathyLib:
     """Binds one shared library exporting the cathy_b200.h entry points under ``prefix``."""
 
     SYMBOLS = ["sizeof_problem", "sizeof_report", "last_error", "create", "destroy", "get_dims", "get_mesh",
-               "initial_storage", "step", "get_state", "set_psi", "debug_assemble", "debug_spmv", "debug_solve"]
+               "initial_storage", "step", "get_state", "set_psi", "upload_atm_record", "debug_assemble", "debug_spmv", "debug_solve"]
 
     def __init__(self, path: str, prefix: str):
         if not os.path.exists(path):
@@ -201,6 +202,7 @@ class CathyLib:
         f["step"].argtypes = [C.c_void_p, C.POINTER(CathyStepReport)]
         f["get_state"].argtypes = [C.c_void_p, _D, _D, _D, _D, _D, _D, _D, _D, _I]
         f["set_psi"].argtypes = [C.c_void_p, _D]
+        f["upload_atm_record"].argtypes = [C.c_void_p, C.c_int32, _D]
         f["debug_assemble"].argtypes = [C.c_void_p, C.c_double, _I, _I, _D, _D]
         f["debug_spmv"].argtypes = [C.c_void_p, _D, _D, C.c_int32, _D]
         f["debug_solve"].argtypes = [C.c_void_p, _D, _I, _D, _D]
@@ -274,6 +276,12 @@ class Simulation:
         rc = self.lib.f["set_psi"](self.h, _dp(psi))
         if rc != 0:
             raise CathyLibraryError(f"set_psi failed ({rc}): {self.lib.error()}")
+
+    def upload_atm_record(self, rec: int, vals: np.ndarray):
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        rc = self.lib.f["upload_atm_record"](self.h, rec, _dp(vals))
+        if rc != 0:
+            raise CathyLibraryError(f"upload_atm_record failed ({rc}): {self.lib.error()}")
 
     def debug_assemble(self, deltat: float):
         topol = np.empty(self.n + 1, dtype=np.int32)

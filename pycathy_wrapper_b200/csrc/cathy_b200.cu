@@ -939,7 +939,9 @@ struct CathySim {
     int nrow, ncol, nc1, nstr, nnod, n, ntri, nt, ncell;
     bool surf;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr;
+    double pcg_ms = 0;
+    int64_t pcg_iters = 0, pcg_solves = 0;
     int sms = 148, grid_n = 0, grid_pcg = 0;
     int64_t launches = 0;
     // host mesh kept for export
@@ -1365,7 +1367,9 @@ static int solve_system(CathySim *S)
     a.x = S->pdiff.p; a.r = S->wr.p; a.z = S->wz.p; a.p0 = S->wp0.p; a.p1 = S->wp1.p; a.bv = S->wbv.p;
     a.ifatm = S->ifatm.p; a.contp_flag = nullptr; a.partial = S->partial.p; a.out = S->d_iter.p;
     void *args[] = {&a};
+    CK(cudaEventRecord(S->evp0, S->st));
     CK(cudaLaunchCooperativeKernel((void *)k_pcg, dim3(S->grid_pcg), dim3(RED_BLOCK), args, 0, S->st));
+    CK(cudaEventRecord(S->evp1, S->st));
     S->launches++;
     return 0;
 }
@@ -1401,6 +1405,11 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
     if (switch_always && S->surf) CK(cudaMemcpyAsync(&S->h_iter->ponding, S->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, S->st));
     CK(cudaStreamSynchronize(S->st));
     const IterOut &o = *S->h_iter;
+    {   // per-launch device time of the PCG kernel (events sit on the launching stream)
+        float pm = 0.f;
+        if (cudaEventElapsedTime(&pm, S->evp0, S->evp1) == cudaSuccess) S->pcg_ms += pm;
+        S->pcg_iters += o.pcg_niter; S->pcg_solves++;
+    }
     rec->niter = o.pcg_niter; rec->ikmax = o.ikmax + 1; rec->pl2 = o.pl2; rec->pinf = o.pinf; rec->pnew_ik = o.pnew_ik;
     rec->pold_ik = o.pold_ik; rec->fl2 = o.fl2; rec->finf = o.finf;
     if (!switch_always) {
@@ -1534,6 +1543,8 @@ void cathy_destroy(CathySim *S)
     if (S->h_step) cudaFreeHost(S->h_step);
     if (S->ev0) cudaEventDestroy(S->ev0);
     if (S->ev1) cudaEventDestroy(S->ev1);
+    if (S->evp0) cudaEventDestroy(S->evp0);
+    if (S->evp1) cudaEventDestroy(S->evp1);
     if (S->st) cudaStreamDestroy(S->st);
     delete[] S->p.atm_time;
     delete S;
@@ -1562,7 +1573,7 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
     S->sms = prop.multiProcessorCount;
     if (!prop.cooperativeLaunch) FAIL(-102, "device does not support cooperative launches");
     CK(cudaStreamCreateWithFlags(&S->st, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&S->ev0)); CK(cudaEventCreate(&S->ev1));
+    CK(cudaEventCreate(&S->ev0)); CK(cudaEventCreate(&S->ev1)); CK(cudaEventCreate(&S->evp0)); CK(cudaEventCreate(&S->evp1));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pcg, RED_BLOCK, 0));
     if (occ < 1) FAIL(-102, "PCG kernel does not fit on an SM");
@@ -1742,6 +1753,15 @@ int32_t cathy_set_psi(CathySim *S, const double *psi)
     return init_atm_and_storage(S);
 }
 
+int32_t cathy_upload_atm_record(CathySim *S, int32_t rec, const double *vals)
+{
+    if (rec < 0 || rec >= S->p.natm) FAIL(-1, "atm record %d out of range", rec);
+    CK(cudaSetDevice(S->p.device));
+    size_t w = S->p.hspatm ? 1 : (size_t)S->nnod;
+    CK(cudaMemcpyAsync(S->atmtab.p + (size_t)rec * w, vals, w * sizeof(double), cudaMemcpyHostToDevice, S->st));
+    return 0;
+}
+
 // time loop body, SRC/cathy_main.f:2882-3829
 int32_t cathy_step(CathySim *S, CathyStepReport *rep)
 {
@@ -1749,7 +1769,8 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
     if (S->finished) FAIL(-1, "simulation already finished");
     CK(cudaSetDevice(p.device));
     memset(rep, 0, sizeof *rep);
-    int64_t l0 = S->launches;
+    int64_t l0 = S->launches, pi0 = S->pcg_iters, ps0 = S->pcg_solves;
+    double pm0 = S->pcg_ms;
     const int NN = S->nnod, N = S->n;
     size_t bn = (size_t)N * sizeof(double), bs = (size_t)NN * sizeof(double);
     CK(cudaEventRecord(S->ev0, S->st));
@@ -1790,7 +1811,6 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
         CK(cudaMemcpyAsync(&S->d_step.p->ak_max, S->d_akmax.p, sizeof(double), cudaMemcpyDeviceToDevice, S->st));
     }
     // end-of-step copies (SRC/cathy_main.f:3762-3790) are queued before the single synchronisation of the step
-    int rc = 0;
     LAUNCH(S, k_step_final, 1, RED_BLOCK, NN, S->nstr, p.pmin, p.pondh_min, S->grid_n, S->store_part.p, S->ifatm.p, S->atmpot.p, S->atmact.p,
            S->pnew.p, S->d_step.p);
     CK(cudaMemcpyAsync(S->h_step, S->d_step.p, sizeof(StepOut), cudaMemcpyDeviceToHost, S->st));
@@ -1811,7 +1831,6 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
     CK(cudaEventRecord(S->ev1, S->st));
     CK(cudaStreamSynchronize(S->st));
     if (h_err) FAIL(-5, "ETRAN: ZROOT reaches the bottom layer (decrease ZROOT)");
-    (void)rc;
     float ms = 0.f;
     cudaEventElapsedTime(&ms, S->ev0, S->ev1);
     const StepOut &so = *S->h_step;
@@ -1842,6 +1861,7 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
     }
     rep->finished = S->finished; rep->next_deltat = S->deltat; rep->next_time = S->time;
     rep->gpu_ms = ms; rep->launches = S->launches - l0;
+    rep->pcg_ms = S->pcg_ms - pm0; rep->pcg_iters = S->pcg_iters - pi0; rep->pcg_solves = S->pcg_solves - ps0;
     return 0;
 }
 

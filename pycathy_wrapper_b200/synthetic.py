@@ -200,4 +200,8 @@ def make_project(path: str, nrow: int, ncol: int, nstr: int, dx: float = 0.5, dy
         open(os.path.join(path, "input", nm), "a").close()
     with open(os.path.join(path, "input", "nudging"), "w") as fh:
         fh.write("0 0 0\tNUDN,NUDT,NUDFLAG\n")
+    # the reference opens every input unit of cathy.fnames (SRC/openio.f), also those it never reads
+    for nm in FNAMES:
+        if not nm.startswith("output/") and not os.path.exists(os.path.join(path, nm)):
+            open(os.path.join(path, nm), "a").close()
     return path
