@@ -184,48 +184,47 @@ __global__ void k_tet_avg(int nt, const int4 *__restrict__ tet, const double *__
 // Every matrix slot owns a static list of (tet, coefficient) pairs sorted by tet, i.e. the
 // reference's TETJA scatter turned into a gather; the sum runs in the reference's element order.
 // ------------------------------------------------------------------------------------------
-__global__ void k_assemble(long long nslots, const int *__restrict__ ptr, const int *__restrict__ ctet,
-                           const double *__restrict__ coef, const double *__restrict__ krt, double *__restrict__ out)
-{
-    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += (long long)gridDim.x * blockDim.x) {
-        int b = ptr[s], e = ptr[s + 1];
-        double acc = 0.0;
-        for (int c = b; c < e; ++c) acc += krt[ctet[c]] * coef[c];
-        out[s] = acc;
-    }
-}
-__global__ void k_assemble_nodes(int n, const int *__restrict__ ptr, const int *__restrict__ ctet,
-                                 const double *__restrict__ gcoef, const double *__restrict__ mcoef,
-                                 const double *__restrict__ krt, const double *__restrict__ e1t,
-                                 double *__restrict__ grav, double *__restrict__ m2)
+// The lists are stored ELL-style, transposed: entry c of row k of diagonal d sits at [c][k], so that
+// consecutive threads (rows) read consecutive addresses; rows with fewer entries are padded with coef 0.
+struct EllFamily { const int *tet; const double *coef; const double *coef2; int w; int pad; };
+struct EllPlan { EllFamily diag[NDIAG]; EllFamily node; long long ld; };
+__global__ void __launch_bounds__(RED_BLOCK) k_assemble(int n, EllPlan P, const double *__restrict__ krt, const double *__restrict__ e1t,
+                                                        Diag A, double *__restrict__ grav, double *__restrict__ m2)
 {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        int b = ptr[k], e = ptr[k + 1];
+#pragma unroll
+        for (int d = 0; d < NDIAG; ++d) {
+            const EllFamily f = P.diag[d];
+            double acc = 0.0;
+            for (int c = 0; c < f.w; ++c) {
+                size_t q = (size_t)c * P.ld + k;
+                acc += krt[f.tet[q]] * f.coef[q];
+            }
+            A.d[d][k] = acc;
+        }
+        const EllFamily f = P.node;
         double g = 0.0, m = 0.0;
-        for (int c = b; c < e; ++c) {
-            int t = ctet[c];
-            g += krt[t] * gcoef[c];
-            m += e1t[t] * mcoef[c];
+        for (int c = 0; c < f.w; ++c) {
+            size_t q = (size_t)c * P.ld + k;
+            int t = f.tet[q];
+            g += krt[t] * f.coef[q];
+            m += e1t[t] * f.coef2[q];
         }
         grav[k] = g;
         m2[k] = m;
     }
 }
 
-// symmetric DIA row product: (A x)_k from the 8 upper diagonals
+// symmetric DIA row product: (A x)_k from the 8 upper diagonals.  Branch free: every gathered vector
+// carries NNOD zero-filled halo elements on both sides and structurally absent entries are stored as 0.
 __device__ __forceinline__ double dia_row(const Diag &A, const double *__restrict__ diag0, const double *__restrict__ x, int k, int n)
 {
+    (void)n;
     double acc = diag0[k] * x[k];
 #pragma unroll
-    for (int d = 1; d < NDIAG; ++d) {
-        int j = k + A.off[d];
-        if (j < n) acc += A.d[d][k] * x[j];
-    }
+    for (int d = 1; d < NDIAG; ++d) acc += A.d[d][k] * x[k + A.off[d]];
 #pragma unroll
-    for (int d = 1; d < NDIAG; ++d) {
-        int j = k - A.off[d];
-        if (j >= 0) acc += A.d[d][j] * x[j];
-    }
+    for (int d = 1; d < NDIAG; ++d) acc += A.d[d][k - A.off[d]] * x[k - A.off[d]];
     return acc;
 }
 
@@ -295,78 +294,110 @@ struct PcgArgs {
     const int *ifatm;
     const unsigned char *contp_flag;
     double *partial;         // [3][gridDim.x]
+    unsigned int *counter;   // grid barrier counter (monotonic)
+    unsigned int epoch0;     // its value at launch
     IterOut *out;
 };
 
-__device__ __forceinline__ void grid_reduce3(cg::grid_group &grid, double a, double b, double c, double *partial, double *sh, double &ra, double &rb, double &rc)
+// Grid-wide barrier for the persistent kernel: one arrival per block on a monotonically increasing counter
+// (release), then a spin on an acquire load.  All blocks are co-resident (cooperative launch).
+__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int &epoch)
 {
-    int nb = gridDim.x;
-    double ta = block_sum<RED_BLOCK>(a, sh);
-    double tb = block_sum<RED_BLOCK>(b, sh);
-    double tc = block_sum<RED_BLOCK>(c, sh);
-    if (threadIdx.x == 0) { partial[blockIdx.x] = ta; partial[nb + blockIdx.x] = tb; partial[2 * nb + blockIdx.x] = tc; }
-    grid.sync();
-    // every block sums all partials in the same order (warp 0..2 take one quantity each)
-    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (w < 3) {
-        double s = 0.0;
-        for (int i = lane; i < nb; i += 32) s += partial[w * nb + i];
-        s = warp_sum(s);
-        if (lane == 0) sh[w] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        epoch += gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned int v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while ((int)(v - epoch) < 0);
     }
     __syncthreads();
-    ra = sh[0]; rb = sh[1]; rc = sh[2];
+}
+// three sums at once: block partials (one shared-memory round), one grid barrier, then every block adds the
+// partials in the same fixed order -> bit-reproducible and identical in all blocks
+template <int BLOCK, bool CUSTOM>
+__device__ __forceinline__ void grid_reduce3(cg::grid_group &grid, unsigned int *counter, unsigned int &epoch, double a, double b, double c,
+                                             double *partial, double (*sh)[3], double &ra, double &rb, double &rc)
+{
+    const int nb = gridDim.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    if (lane == 0) { sh[w][0] = a; sh[w][1] = b; sh[w][2] = c; }
+    __syncthreads();
+    if (w == 0) {
+        double t0 = lane < BLOCK / 32 ? sh[lane][0] : 0.0, t1 = lane < BLOCK / 32 ? sh[lane][1] : 0.0, t2 = lane < BLOCK / 32 ? sh[lane][2] : 0.0;
+        t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_sum(t2);
+        if (lane == 0) { partial[blockIdx.x] = t0; partial[nb + blockIdx.x] = t1; partial[2 * nb + blockIdx.x] = t2; }
+    }
+    if (CUSTOM) grid_barrier(counter, epoch); else grid.sync();
+    if (w < 3) {
+        double s0 = 0.0, s1 = 0.0;
+        const volatile double *pp = partial + w * nb;
+        int i = lane;
+        for (; i + 32 < nb; i += 64) { s0 += pp[i]; s1 += pp[i + 32]; }
+        if (i < nb) s0 += pp[i];
+        double t = warp_sum(s0 + s1);
+        if (lane == 0) sh[0][w] = t;
+    }
+    __syncthreads();
+    ra = sh[0][0]; rb = sh[0][1]; rc = sh[0][2];
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(RED_BLOCK) k_pcg(PcgArgs a)
+template <int BLOCK, bool CUSTOM>
+__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_pcg(PcgArgs a)
 {
     cg::grid_group grid = cg::this_grid();
-    __shared__ double sh[32];
+    __shared__ double sh[BLOCK / 32][3];
+    unsigned int epoch = a.epoch0;
     const int n = a.n, stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const double *__restrict__ dg = a.diag;
     // x0 = M^-1 b ; xlung = ||b_free||^2   (PRODDP call at :4686, XLUNG at :1286-1297)
     double xl = 0.0;
     for (int k = t0; k < n; k += stride) {
         double b = a.rhs[k];
-        a.x[k] = b / a.diag[k];
+        a.x[k] = b / dg[k];
         if (!is_dirichlet(k, a.nnod, a.ifatm, a.contp_flag)) xl += b * b;
     }
     double xlung, d1, d2;
-    grid_reduce3(grid, xl, 0.0, 0.0, a.partial, sh, xlung, d1, d2);
+    grid_reduce3<BLOCK, CUSTOM>(grid, a.counter, epoch, xl, 0.0, 0.0, a.partial, sh, xlung, d1, d2);
     // r = b - A x0 ; z = M^-1 r ; p_old = 0 so that p = z in the first phase A
     for (int k = t0; k < n; k += stride) {
-        double r = a.rhs[k] - dia_row(a.A, a.diag, a.x, k, n);
+        double r = a.rhs[k] - dia_row(a.A, dg, a.x, k, n);
         a.r[k] = r;
-        a.z[k] = r / a.diag[k];
+        a.z[k] = r / dg[k];
         a.p0[k] = 0.0;
     }
-    grid.sync();
+    if (CUSTOM) grid_barrier(a.counter, epoch); else grid.sync();
     double beta = 0.0, err = 0.0;
     double *pold = a.p0, *pnew = a.p1;
     int niter = 1;
     for (;;) {
         // ---- phase A
         double s_pr = 0.0, s_pb = 0.0;
-        for (int k = t0; k < n; k += stride) {
-            double pk = a.z[k] + beta * pold[k];
-            double acc = a.diag[k] * pk;
+        {
+            const double *z = a.z;      // NOT __restrict__/read-only: rewritten every iteration by other SMs
+            const double *po = pold;
+            for (int k = t0; k < n; k += stride) {
+                double pk = z[k] + beta * po[k];
+                double acc = dg[k] * pk;
 #pragma unroll
-            for (int d = 1; d < NDIAG; ++d) {
-                int j = k + a.A.off[d];
-                if (j < n) acc += a.A.d[d][k] * (a.z[j] + beta * pold[j]);
-            }
+                for (int d = 1; d < NDIAG; ++d) {
+                    const int o = a.A.off[d];
+                    acc += a.A.d[d][k] * (z[k + o] + beta * po[k + o]);
+                }
 #pragma unroll
-            for (int d = 1; d < NDIAG; ++d) {
-                int j = k - a.A.off[d];
-                if (j >= 0) acc += a.A.d[d][j] * (a.z[j] + beta * pold[j]);
+                for (int d = 1; d < NDIAG; ++d) {
+                    const int o = a.A.off[d];
+                    acc += a.A.d[d][k - o] * (z[k - o] + beta * po[k - o]);
+                }
+                pnew[k] = pk;
+                a.bv[k] = acc;
+                s_pr += pk * a.r[k];
+                s_pb += pk * acc;
             }
-            pnew[k] = pk;
-            a.bv[k] = acc;
-            s_pr += pk * a.r[k];
-            s_pb += pk * acc;
         }
         double pr, pb;
-        grid_reduce3(grid, s_pr, s_pb, 0.0, a.partial, sh, pr, pb, d1);
+        grid_reduce3<BLOCK, CUSTOM>(grid, a.counter, epoch, s_pr, s_pb, 0.0, a.partial, sh, pr, pb, d1);
         double alfa = pr / pb;
         // ---- phase B
         double s_bz = 0.0, s_rr = 0.0;
@@ -375,20 +406,20 @@ __global__ void __launch_bounds__(RED_BLOCK) k_pcg(PcgArgs a)
             double r = a.r[k] - alfa * bk;
             a.r[k] = r;
             a.x[k] = a.x[k] + alfa * pnew[k];
-            double z = r / a.diag[k];
-            a.z[k] = z;
-            s_bz += bk * z;
+            double zz = r / dg[k];
+            a.z[k] = zz;
+            s_bz += bk * zz;
             if (!is_dirichlet(k, a.nnod, a.ifatm, a.contp_flag)) s_rr += r * r;
         }
         double bz, rr;
-        grid_reduce3(grid, s_bz, s_rr, 0.0, a.partial, sh, bz, rr, d1);
+        grid_reduce3<BLOCK, CUSTOM>(grid, a.counter, epoch, s_bz, s_rr, 0.0, a.partial, sh, bz, rr, d1);
         beta = -bz / pb;
         err = xlung > 0.0 ? sqrt(rr / xlung) : sqrt(rr / n);
         double *t = pold; pold = pnew; pnew = t;
         if (err > a.tol && niter < a.itmax) { ++niter; continue; }
         break;
     }
-    if (t0 == 0) { a.out->pcg_niter = niter; a.out->pcg_err = err; }
+    if (t0 == 0) { a.out->pcg_niter = niter; a.out->pcg_err = err; a.out->pad = (int)epoch; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -421,18 +452,20 @@ __global__ void k_bkflux(int n, int nnod, Diag A, const double *__restrict__ dia
     }
 }
 
-// norms (NORMS, SRC/norms.f:18-38) + storage change (STORMB, SRC/stormb.f) block partials
-struct NormPartial { double pl2, fl2, dstore, pinf, finf; int ik; int pad; };
-__global__ void k_norms(int n, const double *__restrict__ pnew, const double *__restrict__ pold,
+// norms (NORMS, SRC/norms.f:18-38) + storage change (STORMB, SRC/stormb.f) + boundary flux sums
+// (FLUXMB, SRC/fluxmb.f:29-88): block partials in fixed order
+struct NormPartial { double pl2, fl2, dstore, pinf, finf, adin, adout, anin, anout; int ik; int pad; };
+__global__ void k_norms(int n, int nnod, const double *__restrict__ pnew, const double *__restrict__ pold,
                         const double *__restrict__ rhs, const double *__restrict__ ptimep,
                         const double *__restrict__ swnew, const double *__restrict__ swtimep,
                         const double *__restrict__ volnod, const double *__restrict__ snodi,
-                        const double *__restrict__ pnodi, NormPartial *__restrict__ part)
+                        const double *__restrict__ pnodi, const int *__restrict__ ifatm, const double *__restrict__ atmact,
+                        NormPartial *__restrict__ part)
 {
     __shared__ double sh[32];
     __shared__ double shv[RED_BLOCK / 32];
     __shared__ int shi[RED_BLOCK / 32];
-    double pl2 = 0, fl2 = 0, ds = 0, pinf = 0, finf = 0;
+    double pl2 = 0, fl2 = 0, ds = 0, pinf = 0, finf = 0, adin = 0, adout = 0, anin = 0, anout = 0;
     int ik = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         double d = pnew[k] - pold[k], da = fabs(d), f = rhs[k];
@@ -441,8 +474,17 @@ __global__ void k_norms(int n, const double *__restrict__ pnew, const double *__
         if (da > pinf || (da == pinf && k >= ik)) { pinf = da; ik = k; }
         finf = fmax(finf, fabs(f));
         ds += volnod[k] * (snodi[k] * (swnew[k] + swtimep[k]) * 0.5 * (pnew[k] - ptimep[k]) + pnodi[k] * (swnew[k] - swtimep[k]));
+        if (k < nnod) {
+            int fa = ifatm[k];
+            if (fa != -1) {
+                double a = atmact[k];
+                if (fa == 1 || fa == 2) { if (a > 0.0) adin += a; else adout += a; }
+                else { if (a > 0.0) anin += a; else anout += a; }
+            }
+        }
     }
     double t1 = block_sum<RED_BLOCK>(pl2, sh), t2 = block_sum<RED_BLOCK>(fl2, sh), t3 = block_sum<RED_BLOCK>(ds, sh);
+    double t4 = block_sum<RED_BLOCK>(adin, sh), t5 = block_sum<RED_BLOCK>(adout, sh), t6 = block_sum<RED_BLOCK>(anin, sh), t7 = block_sum<RED_BLOCK>(anout, sh);
     // max reductions (ties -> larger index, i.e. the LAST node like the sequential >= test)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -463,32 +505,24 @@ __global__ void k_norms(int n, const double *__restrict__ pnew, const double *__
         }
         NormPartial p;
         p.pl2 = t1; p.fl2 = t2; p.dstore = t3; p.pinf = pinf; p.finf = finf; p.ik = ik; p.pad = 0;
+        p.adin = t4; p.adout = t5; p.anin = t6; p.anout = t7;
         part[blockIdx.x] = p;
     }
 }
-// final fixed-order reduction + boundary flux sums (FLUXMB, SRC/fluxmb.f:29-88), one block
-__global__ void k_norms_final(int nb, const NormPartial *__restrict__ part, int nnod, const int *__restrict__ ifatm,
-                              const double *__restrict__ atmact, const double *__restrict__ pnew,
+// final fixed-order reduction of the block partials, one block
+__global__ void k_norms_final(int nb, const NormPartial *__restrict__ part, const double *__restrict__ pnew,
                               const double *__restrict__ pold, IterOut *__restrict__ out)
 {
     __shared__ double sh[32];
     __shared__ double shv[RED_BLOCK / 32];
     __shared__ int shi[RED_BLOCK / 32];
-    double pl2 = 0, fl2 = 0, ds = 0, pinf = 0, finf = 0;
+    double pl2 = 0, fl2 = 0, ds = 0, pinf = 0, finf = 0, adin = 0, adout = 0, anin = 0, anout = 0;
     int ik = 0;
     for (int b = threadIdx.x; b < nb; b += blockDim.x) {
         NormPartial p = part[b];
-        pl2 += p.pl2; fl2 += p.fl2; ds += p.dstore;
+        pl2 += p.pl2; fl2 += p.fl2; ds += p.dstore; adin += p.adin; adout += p.adout; anin += p.anin; anout += p.anout;
         if (p.pinf > pinf || (p.pinf == pinf && p.ik > ik)) { pinf = p.pinf; ik = p.ik; }
         finf = fmax(finf, p.finf);
-    }
-    double adin = 0, adout = 0, anin = 0, anout = 0;
-    for (int k = threadIdx.x; k < nnod; k += blockDim.x) {
-        int f = ifatm[k];
-        if (f == -1) continue;
-        double a = atmact[k];
-        if (f == 1 || f == 2) { if (a > 0.0) adin += a; else adout += a; }
-        else { if (a > 0.0) anin += a; else anout += a; }
     }
     double t1 = block_sum<RED_BLOCK>(pl2, sh), t2 = block_sum<RED_BLOCK>(fl2, sh), t3 = block_sum<RED_BLOCK>(ds, sh);
     double t4 = block_sum<RED_BLOCK>(adin, sh), t5 = block_sum<RED_BLOCK>(adout, sh), t6 = block_sum<RED_BLOCK>(anin, sh), t7 = block_sum<RED_BLOCK>(anout, sh);
@@ -818,20 +852,19 @@ __global__ void k_pond_zero(int nnod, const double *__restrict__ pnew, double *_
         if (pnew[i] <= 0.0) pondnod[i] = 0.0;
 }
 
-// HGRAPH + SAT_FRAC (SRC/hgraph.f, SRC/sat_frac.f) + final STORE1 sum, one block, fixed order
-__global__ void k_step_final(int nnod, int nstr, double pmin, double ph, int nbpart, const double *__restrict__ store_part,
-                             const int *__restrict__ ifatm, const double *__restrict__ atmpot,
-                             const double *__restrict__ atmact, const double *__restrict__ pnew, StepOut *__restrict__ out)
+// HGRAPH + SAT_FRAC (SRC/hgraph.f, SRC/sat_frac.f): block partials over the surface nodes ...
+struct StepPartial { double apot, aact, refl, ovf; int c[13]; int pad; };
+__global__ void k_step_partial(int nnod, int nstr, double pmin, double ph, const int *__restrict__ ifatm,
+                               const double *__restrict__ atmpot, const double *__restrict__ atmact,
+                               const double *__restrict__ pnew, StepPartial *__restrict__ part)
 {
     __shared__ double sh[32];
     __shared__ int shi[13];
     if (threadIdx.x < 13) shi[threadIdx.x] = 0;
     __syncthreads();
-    double st = 0.0;
-    for (int b = threadIdx.x; b < nbpart; b += blockDim.x) st += store_part[b];
     double apot = 0, aact = 0, refl = 0, ovf = 0;
     int hg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, nh = 0, nd = 0, np = 0, ns = 0;
-    for (int k = threadIdx.x; k < nnod; k += blockDim.x) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nnod; k += gridDim.x * blockDim.x) {
         double pot = atmpot[k], act = atmact[k], pn = pnew[k];
         int f = ifatm[k];
         apot += pot; aact += act;
@@ -862,13 +895,40 @@ __global__ void k_step_final(int nnod, int nstr, double pmin, double ph, int nbp
             if (hd) nh++; else nd++;
         }
     }
-    double t0 = block_sum<RED_BLOCK>(st, sh), t1 = block_sum<RED_BLOCK>(apot, sh), t2 = block_sum<RED_BLOCK>(aact, sh);
+    double t1 = block_sum<RED_BLOCK>(apot, sh), t2 = block_sum<RED_BLOCK>(aact, sh);
     double t3 = block_sum<RED_BLOCK>(refl, sh), t4 = block_sum<RED_BLOCK>(ovf, sh);
     for (int q = 0; q < 9; ++q) if (hg[q]) atomicAdd(&shi[q], hg[q]);
     if (nh) atomicAdd(&shi[9], nh);
     if (nd) atomicAdd(&shi[10], nd);
     if (np) atomicAdd(&shi[11], np);
     if (ns) atomicAdd(&shi[12], ns);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        StepPartial p;
+        p.apot = t1; p.aact = t2; p.refl = t3; p.ovf = t4; p.pad = 0;
+        for (int q = 0; q < 13; ++q) p.c[q] = shi[q];
+        part[blockIdx.x] = p;
+    }
+}
+// ... and their fixed-order reduction together with STORE1 (SRC/storcal.f), one block
+__global__ void k_step_final(int nbs, const StepPartial *__restrict__ spart, int nbpart, const double *__restrict__ store_part,
+                             StepOut *__restrict__ out)
+{
+    __shared__ double sh[32];
+    __shared__ int shi[13];
+    if (threadIdx.x < 13) shi[threadIdx.x] = 0;
+    __syncthreads();
+    double st = 0.0, apot = 0, aact = 0, refl = 0, ovf = 0;
+    int c[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = threadIdx.x; b < nbpart; b += blockDim.x) st += store_part[b];
+    for (int b = threadIdx.x; b < nbs; b += blockDim.x) {
+        StepPartial p = spart[b];
+        apot += p.apot; aact += p.aact; refl += p.refl; ovf += p.ovf;
+        for (int q = 0; q < 13; ++q) c[q] += p.c[q];
+    }
+    double t0 = block_sum<RED_BLOCK>(st, sh), t1 = block_sum<RED_BLOCK>(apot, sh), t2 = block_sum<RED_BLOCK>(aact, sh);
+    double t3 = block_sum<RED_BLOCK>(refl, sh), t4 = block_sum<RED_BLOCK>(ovf, sh);
+    for (int q = 0; q < 13; ++q) if (c[q]) atomicAdd(&shi[q], c[q]);
     __syncthreads();
     if (threadIdx.x == 0) {
         out->store1 = t0; out->apot = t1; out->aact = t2; out->reflow = t3; out->ovflow = t4;
@@ -917,21 +977,25 @@ __global__ void k_mbinit(int nnod, const int *__restrict__ ifatmp, const double 
 // ==========================================================================================
 template <class T>
 struct DBuf {
-    T *p = nullptr;
-    size_t n = 0;
-    int alloc(size_t cnt)
+    T *p = nullptr;      // logical element 0
+    T *base = nullptr;   // allocation start (p - pad)
+    size_t n = 0, pad = 0;
+    // `halo` zero-filled elements are kept on both sides so stencil kernels can gather without bounds checks
+    int alloc(size_t cnt, size_t halo = 0)
     {
-        n = cnt;
-        if (cudaMalloc((void **)&p, std::max<size_t>(cnt, 1) * sizeof(T)) != cudaSuccess) return -1;
-        return cudaMemset(p, 0, std::max<size_t>(cnt, 1) * sizeof(T)) == cudaSuccess ? 0 : -1;
+        n = cnt; pad = halo;
+        size_t tot = std::max<size_t>(cnt + 2 * halo, 1);
+        if (cudaMalloc((void **)&base, tot * sizeof(T)) != cudaSuccess) return -1;
+        p = base + halo;
+        return cudaMemset(base, 0, tot * sizeof(T)) == cudaSuccess ? 0 : -1;
     }
-    int upload(const std::vector<T> &h)
+    int upload(const std::vector<T> &h, size_t halo = 0)
     {
-        if (alloc(h.size())) return -1;
+        if (alloc(h.size(), halo)) return -1;
         if (h.empty()) return 0;
         return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -1;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; }
+    void release() { if (base) cudaFree(base); base = p = nullptr; }
 };
 
 struct CathySim {
@@ -942,7 +1006,9 @@ struct CathySim {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr;
     double pcg_ms = 0;
     int64_t pcg_iters = 0, pcg_solves = 0;
-    int sms = 148, grid_n = 0, grid_pcg = 0;
+    int sms = 148, grid_n = 0, grid_pcg = 0, pcg_block = 1024, pcg_custom = 1;
+    unsigned int barrier_epoch = 0;
+    DBuf<unsigned int> d_counter;
     int64_t launches = 0;
     // host mesh kept for export
     std::vector<double> hx, hy, hz, harenod;
@@ -954,8 +1020,11 @@ struct CathySim {
     DBuf<double> vgn, vgm, vgpsat, vgpnot, rr, snodi, pnodi, vgn1, vgnr, vgpsn, vgmr, volnod, arenod, z, m4, vegpar;
     DBuf<int> veg;
     DBuf<int4> tet;
-    DBuf<int> s_ptr, s_tet, n_ptr, n_tet;
-    DBuf<double> s_coef, n_g, n_m;
+    DBuf<int> ell_tet;           // ELL-transposed gather lists (see k_assemble)
+    DBuf<double> ell_coef, ell_coef2;
+    EllPlan plan;
+    size_t ld = 0, halo = 0;     // leading dimension of the diagonals / halo of gathered vectors
+    DBuf<StepPartial> spart;
     // matrices / vectors
     DBuf<double> A;              // 8 diagonals, [NDIAG][n]
     DBuf<double> diag_true, diag_bc, grav, m2, krt, e1t;
@@ -1004,7 +1073,7 @@ static inline int nblk(long long n, int cap) { long long b = (n + RED_BLOCK - 1)
 static Diag make_diag(CathySim *S, double *base)
 {
     Diag D;
-    for (int d = 0; d < NDIAG; ++d) { D.d[d] = base + (size_t)d * S->n; D.off[d] = S->off[d]; }
+    for (int d = 0; d < NDIAG; ++d) { D.d[d] = base + (size_t)d * S->ld; D.off[d] = S->off[d]; }
     return D;
 }
 static Soil make_soil(CathySim *S)
@@ -1141,12 +1210,19 @@ static int build_static(CathySim *S)
         if (tp[k] == 0) FAIL(-3, "node %d is not connected to any element", k + 1);
         pnodi[k] /= tp[k]; snodi[k] /= tp[k]; vgn[k] /= tp[k]; vgpsat[k] /= tp[k]; vgrmc[k] /= tp[k];
     }
-    for (size_t s = 0; s < nslots; ++s) s_cnt[s + 1] += s_cnt[s];
-    for (int k = 0; k < n; ++k) n_cnt[k + 1] += n_cnt[k];
-    if ((long long)s_cnt[nslots] != (long long)10 * (long long)nt) FAIL(-3, "contribution count mismatch");
-    std::vector<int> s_fill(s_cnt.begin(), s_cnt.end() - 1), n_fill(n_cnt.begin(), n_cnt.end() - 1);
-    std::vector<int> s_tet((size_t)10 * nt), n_tet((size_t)4 * nt);
-    std::vector<double> s_coef((size_t)10 * nt), n_g((size_t)4 * nt), n_m((size_t)4 * nt), m4(n, 0.0);
+    // ELL widths per diagonal / for the node family, then transposed fill (entry c of row k at [c][k])
+    int wd[NDIAG], wnode = 0;
+    for (int d = 0; d < NDIAG; ++d) { wd[d] = 0; for (int k = 0; k < n; ++k) wd[d] = std::max(wd[d], s_cnt[(size_t)d * n + k + 1]); }
+    for (int k = 0; k < n; ++k) wnode = std::max(wnode, n_cnt[k + 1]);
+    const size_t ld = S->ld;
+    size_t wtot = wnode;
+    for (int d = 0; d < NDIAG; ++d) wtot += wd[d];
+    std::vector<int> e_tet(wtot * ld, 0);
+    std::vector<double> e_coef(wtot * ld, 0.0), e_coef2((size_t)wnode * ld, 0.0), m4(n, 0.0);
+    size_t fam_off[NDIAG + 1];
+    fam_off[0] = 0;
+    for (int d = 0; d < NDIAG; ++d) fam_off[d + 1] = fam_off[d] + (size_t)wd[d] * ld;   // node family starts at fam_off[NDIAG]
+    std::vector<int> s_fill(nslots, 0), n_fill(n, 0);
     for (size_t e = 0; e < nt; ++e) {
         int T[4] = {tet[e].x, tet[e].y, tet[e].z, tet[e].w};
         double b[4], c[4], d[4], vol;
@@ -1161,23 +1237,23 @@ static int build_static(CathySim *S)
         double pel = (((pnodi[T[0]] + pnodi[T[1]]) + pnodi[T[2]]) + pnodi[T[3]]) * 0.25;   // PICUNS' NODELT(PNODI,PEL)
         for (int q = 0; q < 4; ++q) {
             volnod[T[q]] += V * 0.25;
-            int pos = n_fill[T[q]]++;
-            n_tet[pos] = (int)e;
-            n_g[pos] = p.permz[idx] * d[q] * ivol;
-            n_m[pos] = V * 0.25;
+            size_t pos = fam_off[NDIAG] + (size_t)(n_fill[T[q]]++) * ld + T[q];
+            e_tet[pos] = (int)e;
+            e_coef[pos] = p.permz[idx] * d[q] * ivol;
+            e_coef2[pos - fam_off[NDIAG]] = V * 0.25;
             m4[T[q]] += (V * pel) * 0.25;
         }
         for (int k = 0; k < 4; ++k)
             for (int l = k; l < 4; ++l) {
                 int dg = diag_of(T[l] - T[k]);
-                int pos = s_fill[(size_t)dg * n + T[k]]++;
-                s_tet[pos] = (int)e;
-                s_coef[pos] = (kx * b[k]) * b[l] + (ky * c[k]) * c[l] + (kz * d[k]) * d[l];
+                size_t pos = fam_off[dg] + (size_t)(s_fill[(size_t)dg * n + T[k]]++) * ld + T[k];
+                e_tet[pos] = (int)e;
+                e_coef[pos] = (kx * b[k]) * b[l] + (ky * c[k]) * c[l] + (kz * d[k]) * d[l];
             }
     }
     S->hexist.assign(nslots, 0);
     S->nterm = 0;
-    for (size_t s = 0; s < nslots; ++s) if (s_cnt[s + 1] > s_cnt[s]) { S->hexist[s] = 1; S->nterm++; }
+    for (size_t s = 0; s < nslots; ++s) if (s_cnt[s + 1] > 0) { S->hexist[s] = 1; S->nterm++; }
     // --- derived VG constants (SRC/chparm.f:22-35)
     std::vector<double> vgm(n), vgn1(n), vgnr(n), vgpsn(n), vgmr(n), vgpnot(n), rr(n);
     for (int k = 0; k < n; ++k) {
@@ -1211,8 +1287,10 @@ static int build_static(CathySim *S)
     rc |= S->vgnr.upload(vgnr); rc |= S->vgpsn.upload(vgpsn); rc |= S->vgmr.upload(vgmr); rc |= S->volnod.upload(volnod);
     rc |= S->arenod.upload(S->harenod); rc |= S->z.upload(S->hz); rc |= S->m4.upload(m4); rc |= S->veg.upload(veg);
     rc |= S->vegpar.upload(vegpar); rc |= S->tet.upload(tet);
-    rc |= S->s_ptr.upload(s_cnt); rc |= S->s_tet.upload(s_tet); rc |= S->s_coef.upload(s_coef);
-    rc |= S->n_ptr.upload(n_cnt); rc |= S->n_tet.upload(n_tet); rc |= S->n_g.upload(n_g); rc |= S->n_m.upload(n_m);
+    rc |= S->ell_tet.upload(e_tet); rc |= S->ell_coef.upload(e_coef); rc |= S->ell_coef2.upload(e_coef2);
+    for (int d = 0; d < NDIAG; ++d) { S->plan.diag[d].tet = S->ell_tet.p + fam_off[d]; S->plan.diag[d].coef = S->ell_coef.p + fam_off[d]; S->plan.diag[d].coef2 = nullptr; S->plan.diag[d].w = wd[d]; S->plan.diag[d].pad = 0; }
+    S->plan.node.tet = S->ell_tet.p + fam_off[NDIAG]; S->plan.node.coef = S->ell_coef.p + fam_off[NDIAG]; S->plan.node.coef2 = S->ell_coef2.p; S->plan.node.w = wnode; S->plan.node.pad = 0;
+    S->plan.ld = (long long)ld;
     if (rc) FAIL(-101, "device allocation/upload of static tables failed: %s", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
@@ -1335,8 +1413,9 @@ static void chvelo_launch(CathySim *S, const double *psi)
 }
 static int step_final_sync(CathySim *S)
 {
-    LAUNCH(S, k_step_final, 1, RED_BLOCK, S->nnod, S->nstr, S->p.pmin, S->p.pondh_min, S->grid_n, S->store_part.p, S->ifatm.p, S->atmpot.p,
-           S->atmact.p, S->pnew.p, S->d_step.p);
+    int nbs = nblk(S->nnod, S->grid_n);
+    LAUNCH(S, k_step_partial, nbs, RED_BLOCK, S->nnod, S->nstr, S->p.pmin, S->p.pondh_min, S->ifatm.p, S->atmpot.p, S->atmact.p, S->pnew.p, S->spart.p);
+    LAUNCH(S, k_step_final, 1, RED_BLOCK, nbs, S->spart.p, S->grid_n, S->store_part.p, S->d_step.p);
     CK(cudaMemcpyAsync(S->h_step, S->d_step.p, sizeof(StepOut), cudaMemcpyDeviceToHost, S->st));
     CK(cudaStreamSynchronize(S->st));
     return 0;
@@ -1350,13 +1429,12 @@ static int assemble_system(CathySim *S, double deltat)
     LAUNCH(S, k_curves, nblk(n, S->grid_n), RED_BLOCK, n, make_soil(S), S->ptnew.p, S->pnew.p, S->ptimep.p, S->timep_dirty, S->sw.p, S->ckrw.p, S->et1.p, S->et2.p, S->swnew.p, S->swtimep.p);
     S->timep_dirty = 0;
     LAUNCH(S, k_tet_avg, nblk(S->nt, 4 * S->grid_n), RED_BLOCK, S->nt, S->tet.p, S->ckrw.p, S->et1.p, S->krt.p, S->e1t.p);
-    LAUNCH(S, k_assemble, nblk((long long)NDIAG * n, 8 * S->grid_n), RED_BLOCK, (long long)NDIAG * n, S->s_ptr.p, S->s_tet.p, S->s_coef.p, S->krt.p, S->A.p);
-    LAUNCH(S, k_assemble_nodes, nblk(n, S->grid_n), RED_BLOCK, n, S->n_ptr.p, S->n_tet.p, S->n_g.p, S->n_m.p, S->krt.p, S->e1t.p, S->grav.p, S->m2.p);
+    LAUNCH(S, k_assemble, nblk(n, 4 * S->grid_n), RED_BLOCK, n, S->plan, S->krt.p, S->e1t.p, A, S->grav.p, S->m2.p);
     LAUNCH(S, k_rhs_lhs, nblk(n, S->grid_n), RED_BLOCK, n, S->nnod, A, S->tetaf, 1.0 / deltat, S->ptnew.p, S->pnew.p, S->ptimep.p, S->swnew.p,
            S->swtimep.p, S->m2.p, S->m4.p, S->et2.p, S->grav.p, S->ifatm.p, (const unsigned char *)nullptr, (const double *)nullptr,
            S->atmact.p, S->atmold.p, S->qtranie.p, S->rhs.p, S->xt5.p, S->diag_true.p, S->diag_bc.p);
     if (S->tetaf != 1.0)   // off-diagonals of the LHS are TETAF * stiffness (SRC/cfmatp.f:24-26)
-        LAUNCH(S, k_scale, nblk((long long)(NDIAG - 1) * n, 8 * S->grid_n), RED_BLOCK, (long long)(NDIAG - 1) * n, S->tetaf, S->A.p + n);
+        LAUNCH(S, k_scale, nblk((long long)(NDIAG - 1) * S->ld, 8 * S->grid_n), RED_BLOCK, (long long)(NDIAG - 1) * S->ld, S->tetaf, S->A.p + S->ld);
     return 0;
 }
 static int solve_system(CathySim *S)
@@ -1366,9 +1444,17 @@ static int solve_system(CathySim *S)
     a.A = make_diag(S, S->A.p); a.diag = S->diag_bc.p; a.rhs = S->rhs.p;
     a.x = S->pdiff.p; a.r = S->wr.p; a.z = S->wz.p; a.p0 = S->wp0.p; a.p1 = S->wp1.p; a.bv = S->wbv.p;
     a.ifatm = S->ifatm.p; a.contp_flag = nullptr; a.partial = S->partial.p; a.out = S->d_iter.p;
+    a.counter = S->d_counter.p; a.epoch0 = S->barrier_epoch;
     void *args[] = {&a};
     CK(cudaEventRecord(S->evp0, S->st));
-    CK(cudaLaunchCooperativeKernel((void *)k_pcg, dim3(S->grid_pcg), dim3(RED_BLOCK), args, 0, S->st));
+    void *fn = nullptr;
+    const bool cu = S->pcg_custom != 0;
+    switch (S->pcg_block) {
+    case 256: fn = cu ? (void *)k_pcg<256, true> : (void *)k_pcg<256, false>; break;
+    case 512: fn = cu ? (void *)k_pcg<512, true> : (void *)k_pcg<512, false>; break;
+    default: fn = cu ? (void *)k_pcg<1024, true> : (void *)k_pcg<1024, false>; break;
+    }
+    CK(cudaLaunchCooperativeKernel(fn, dim3(S->grid_pcg), dim3(S->pcg_block), args, 0, S->st));
     CK(cudaEventRecord(S->evp1, S->st));
     S->launches++;
     return 0;
@@ -1385,9 +1471,9 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
            (const double *)nullptr, S->pnew.p);
     LAUNCH(S, k_bkflux, nblk(S->nnod, S->grid_n), RED_BLOCK, n, S->nnod, A, S->diag_true.p, S->pdiff.p, S->xt5.p, S->ifatm.p, S->tetaf,
            S->atmold.p, S->atmact.p);
-    LAUNCH(S, k_norms, S->grid_n, RED_BLOCK, n, S->pnew.p, S->pold.p, S->rhs.p, S->ptimep.p, S->swnew.p, S->swtimep.p, S->volnod.p,
-           S->snodi.p, S->pnodi.p, S->npart.p);
-    LAUNCH(S, k_norms_final, 1, RED_BLOCK, S->grid_n, S->npart.p, S->nnod, S->ifatm.p, S->atmact.p, S->pnew.p, S->pold.p, S->d_iter.p);
+    LAUNCH(S, k_norms, S->grid_n, RED_BLOCK, n, S->nnod, S->pnew.p, S->pold.p, S->rhs.p, S->ptimep.p, S->swnew.p, S->swtimep.p, S->volnod.p,
+           S->snodi.p, S->pnodi.p, S->ifatm.p, S->atmact.p, S->npart.p);
+    LAUNCH(S, k_norms_final, 1, RED_BLOCK, S->grid_n, S->npart.p, S->pnew.p, S->pold.p, S->d_iter.p);
     // atmospheric switching is evaluated every iteration when TOLSWI is large (SRC/conver.f:58-71); when it is
     // conditional the host decides after the read-back below.
     bool switch_always = S->p.tolswi >= 1.0e29;
@@ -1405,6 +1491,7 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
     if (switch_always && S->surf) CK(cudaMemcpyAsync(&S->h_iter->ponding, S->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, S->st));
     CK(cudaStreamSynchronize(S->st));
     const IterOut &o = *S->h_iter;
+    S->barrier_epoch = (unsigned int)o.pad;
     {   // per-launch device time of the PCG kernel (events sit on the launching stream)
         float pm = 0.f;
         if (cudaEventElapsedTime(&pm, S->evp0, S->evp1) == cudaSuccess) S->pcg_ms += pm;
@@ -1526,7 +1613,7 @@ void cathy_destroy(CathySim *S)
     if (S->st) cudaStreamSynchronize(S->st);
     // DBuf members are plain pointers: release them explicitly
     DBuf<double> *dd[] = {&S->vgn, &S->vgm, &S->vgpsat, &S->vgpnot, &S->rr, &S->snodi, &S->pnodi, &S->vgn1, &S->vgnr, &S->vgpsn, &S->vgmr,
-                          &S->volnod, &S->arenod, &S->z, &S->m4, &S->vegpar, &S->s_coef, &S->n_g, &S->n_m, &S->A, &S->diag_true, &S->diag_bc,
+                          &S->volnod, &S->arenod, &S->z, &S->m4, &S->vegpar, &S->ell_coef, &S->ell_coef2, &S->A, &S->diag_true, &S->diag_bc,
                           &S->grav, &S->m2, &S->krt, &S->e1t, &S->pnew, &S->pold, &S->ptimep, &S->ptnew, &S->pdiff, &S->sw, &S->ckrw, &S->ckrwp,
                           &S->et1, &S->et2, &S->swnew, &S->swtimep, &S->rhs, &S->xt5, &S->qtranie, &S->wr, &S->wz, &S->wp0, &S->wp1, &S->wbv,
                           &S->partial, &S->store_part, &S->atmpot, &S->atmact, &S->atmold, &S->atmtab, &S->pondnod, &S->ovflnod, &S->ovflp,
@@ -1535,10 +1622,10 @@ void cathy_destroy(CathySim *S)
                           &S->q_out_kkp1_2, &S->volume_kk, &S->volume_kkp1, &S->h_water, &S->q_in_kk_sav, &S->q_out_kk_1_sav, &S->q_out_kk_2_sav,
                           &S->volume_kk_sav, &S->q_in_kk_p, &S->q_out_kk_1_p, &S->q_out_kk_2_p, &S->volume_kk_p, &S->d_akmax};
     for (auto *b : dd) b->release();
-    DBuf<int> *di[] = {&S->veg, &S->s_ptr, &S->s_tet, &S->n_ptr, &S->n_tet, &S->ifatm, &S->ifatmp, &S->d_flags, &S->lv_ptr, &S->lv_cell,
+    DBuf<int> *di[] = {&S->veg, &S->ell_tet, &S->ifatm, &S->ifatmp, &S->d_flags, &S->lv_ptr, &S->lv_cell,
                        &S->seqpos, &S->don_ptr, &S->don_cell, &S->d_nsurf};
     for (auto *b : di) b->release();
-    S->tet.release(); S->don_dir.release(); S->npart.release(); S->d_iter.release(); S->d_step.release();
+    S->d_counter.release(); S->tet.release(); S->don_dir.release(); S->npart.release(); S->spart.release(); S->d_iter.release(); S->d_step.release();
     if (S->h_iter) cudaFreeHost(S->h_iter);
     if (S->h_step) cudaFreeHost(S->h_step);
     if (S->ev0) cudaEventDestroy(S->ev0);
@@ -1574,25 +1661,28 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
     if (!prop.cooperativeLaunch) FAIL(-102, "device does not support cooperative launches");
     CK(cudaStreamCreateWithFlags(&S->st, cudaStreamNonBlocking));
     CK(cudaEventCreate(&S->ev0)); CK(cudaEventCreate(&S->ev1)); CK(cudaEventCreate(&S->evp0)); CK(cudaEventCreate(&S->evp1));
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pcg, RED_BLOCK, 0));
-    if (occ < 1) FAIL(-102, "PCG kernel does not fit on an SM");
-    S->grid_pcg = S->sms * std::min(occ, 8);
+    if (const char *e = getenv("CATHY_PCG_BLOCK")) S->pcg_block = atoi(e);
+    if (const char *e = getenv("CATHY_PCG_CUSTOM_BARRIER")) S->pcg_custom = atoi(e);
+    if (S->pcg_block != 256 && S->pcg_block != 512 && S->pcg_block != 1024) FAIL(-2, "CATHY_PCG_BLOCK must be 256, 512 or 1024");
+    S->grid_pcg = S->sms * (1024 / S->pcg_block);   // one full SM worth of threads per SM, persistent
+    if (S->d_counter.alloc(1)) FAIL(-101, "barrier counter allocation failed");
     S->grid_n = S->sms * 8;                      // grid-stride kernels: a multiple of the SM count
     // the device PCG is diagonally preconditioned: it needs more (cheaper) iterations than IC(0), so the
     // failure threshold ITMXCG is scaled; LSFAIL keeps its meaning "did not reach TOLCG"
     S->itmax_dev = p.itmxcg * 20;
     S->tol_dev = p.tolcg * (p.tolcg_scale > 0.0 ? p.tolcg_scale : 1.0);
+    S->ld = ((size_t)S->n + 31) / 32 * 32;
+    S->halo = ((size_t)S->nnod + 1 + 31) / 32 * 32;
     int rc = build_static(S);
     if (rc) return rc;
     const int N = S->n, NN = S->nnod;
     int a = 0;
-    a |= S->A.alloc((size_t)NDIAG * N);
+    a |= S->A.alloc((size_t)NDIAG * S->ld, S->halo);
     DBuf<double> *vn[] = {&S->diag_true, &S->diag_bc, &S->grav, &S->m2, &S->pnew, &S->pold, &S->ptimep, &S->ptnew, &S->pdiff, &S->sw, &S->ckrw,
                           &S->ckrwp, &S->et1, &S->et2, &S->swnew, &S->swtimep, &S->rhs, &S->xt5, &S->qtranie, &S->wr, &S->wz, &S->wp0, &S->wp1, &S->wbv};
-    for (auto *b : vn) a |= b->alloc(N);
+    for (auto *b : vn) a |= b->alloc(N, S->halo);   // halo: stencil gathers need no bounds checks
     a |= S->krt.alloc(S->nt); a |= S->e1t.alloc(S->nt);
-    a |= S->partial.alloc(3 * (size_t)S->grid_pcg); a |= S->store_part.alloc(S->grid_n); a |= S->npart.alloc(S->grid_n);
+    a |= S->partial.alloc(3 * (size_t)std::max(S->grid_pcg, 1)); a |= S->store_part.alloc(S->grid_n); a |= S->npart.alloc(S->grid_n); a |= S->spart.alloc(S->grid_n);
     a |= S->d_iter.alloc(1); a |= S->d_step.alloc(1); a |= S->ifatm.alloc(NN); a |= S->ifatmp.alloc(NN); a |= S->d_flags.alloc(4);
     DBuf<double> *vs[] = {&S->atmpot, &S->atmact, &S->atmold, &S->pondnod, &S->ovflnod, &S->ovflp};
     for (auto *b : vs) a |= b->alloc(NN);
@@ -1811,8 +1901,11 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
         CK(cudaMemcpyAsync(&S->d_step.p->ak_max, S->d_akmax.p, sizeof(double), cudaMemcpyDeviceToDevice, S->st));
     }
     // end-of-step copies (SRC/cathy_main.f:3762-3790) are queued before the single synchronisation of the step
-    LAUNCH(S, k_step_final, 1, RED_BLOCK, NN, S->nstr, p.pmin, p.pondh_min, S->grid_n, S->store_part.p, S->ifatm.p, S->atmpot.p, S->atmact.p,
-           S->pnew.p, S->d_step.p);
+    {
+        int nbs = nblk(NN, S->grid_n);
+        LAUNCH(S, k_step_partial, nbs, RED_BLOCK, NN, S->nstr, p.pmin, p.pondh_min, S->ifatm.p, S->atmpot.p, S->atmact.p, S->pnew.p, S->spart.p);
+        LAUNCH(S, k_step_final, 1, RED_BLOCK, nbs, S->spart.p, S->grid_n, S->store_part.p, S->d_step.p);
+    }
     CK(cudaMemcpyAsync(S->h_step, S->d_step.p, sizeof(StepOut), cudaMemcpyDeviceToHost, S->st));
     CK(cudaMemcpyAsync(S->ifatmp.p, S->ifatm.p, (size_t)NN * sizeof(int), cudaMemcpyDeviceToDevice, S->st));
     CK(cudaMemcpyAsync(S->atmold.p, S->atmact.p, bs, cudaMemcpyDeviceToDevice, S->st));
@@ -1876,7 +1969,7 @@ int32_t cathy_debug_assemble(CathySim *S, double deltat, int32_t *topol, int32_t
     const int n = S->n;
     std::vector<double> hA, hd;
     if (coef1) {
-        hA.resize((size_t)NDIAG * n); hd.resize(n);
+        hA.resize((size_t)NDIAG * S->ld); hd.resize(n);
         CK(cudaMemcpy(hA.data(), S->A.p, hA.size() * sizeof(double), cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(hd.data(), S->diag_bc.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
     }
@@ -1886,7 +1979,7 @@ int32_t cathy_debug_assemble(CathySim *S, double deltat, int32_t *topol, int32_t
         for (int d = 0; d < NDIAG; ++d) {
             if (d > 0 && !S->hexist[(size_t)d * n + k]) continue;
             if (ja) ja[m] = k + S->off[d] + 1;
-            if (coef1) coef1[m] = d == 0 ? hd[k] : hA[(size_t)d * n + k];
+            if (coef1) coef1[m] = d == 0 ? hd[k] : hA[(size_t)d * S->ld + k];
             ++m;
         }
     }
@@ -1924,6 +2017,7 @@ int32_t cathy_debug_solve(CathySim *S, double *sol, int32_t *niter, double *err,
     float t = 0.f;
     cudaEventElapsedTime(&t, S->ev0, S->ev1);
     if (ms) *ms = t;
+    S->barrier_epoch = (unsigned int)S->h_iter->pad;
     if (niter) *niter = S->h_iter->pcg_niter;
     if (err) *err = S->h_iter->pcg_err;
     if (sol) CK(cudaMemcpy(sol, S->pdiff.p, (size_t)S->n * sizeof(double), cudaMemcpyDeviceToHost));
