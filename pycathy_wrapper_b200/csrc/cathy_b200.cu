@@ -451,6 +451,44 @@ __global__ void k_bkflux(int n, int nnod, Diag A, const double *__restrict__ dia
         }
     }
 }
+// same for the prescribed-head nodes: QPNEW (SRC/bkpic.f:38-41), indexed by list position like the reference
+__global__ void k_bkflux_list(int n, int m, const int *__restrict__ list, Diag A, const double *__restrict__ diag_true,
+                              const double *__restrict__ pdiff, const double *__restrict__ xt5, double tetaf,
+                              const double *__restrict__ qpold, double *__restrict__ qpnew)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        int k = list[i];
+        double scr = dia_row(A, diag_true, pdiff, k, n) - xt5[k];
+        qpnew[i] = (scr - (1.0 - tetaf) * qpold[i]) * (1.0 / tetaf);
+    }
+}
+// surface nodes carrying a non-atmospheric BC leave the atmospheric state machine (SRC/atmone.f label 400, SRC/atmnxt.f label 800)
+__global__ void k_mark_nonatm(int nnod, const unsigned char *__restrict__ contp_flag, const unsigned char *__restrict__ contq_flag,
+                              int *__restrict__ ifatm, int *__restrict__ ifatmp)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnod; i += gridDim.x * blockDim.x)
+        if ((contp_flag && contp_flag[i]) || (contq_flag && contq_flag[i])) { ifatm[i] = -1; if (ifatmp) ifatmp[i] = -1; }
+}
+// signed sums of a flux list (NDIN/NDOUT, NNIN/NNOUT of SRC/fluxmb.f:29-48), one block, fixed order
+__global__ void k_flux_sums(int m, const double *__restrict__ q, double *__restrict__ out2)
+{
+    __shared__ double sh[32];
+    double a = 0.0, b = 0.0;
+    for (int k = threadIdx.x; k < m; k += blockDim.x) { double v = q[k]; if (v > 0.0) a += v; else b += v; }
+    double t0 = block_sum<RED_BLOCK>(a, sh), t1 = block_sum<RED_BLOCK>(b, sh);
+    if (threadIdx.x == 0) { out2[0] = t0; out2[1] = t1; }
+}
+// free drainage writes into the list-ordered Q array as well as the dense one
+__global__ void k_free_drain_list(int nnod, int nstr, const double *__restrict__ arenod, const double *__restrict__ ckrw,
+                                  const double *__restrict__ kznod, double *__restrict__ qlist, double *__restrict__ qdense)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnod; i += gridDim.x * blockDim.x) {
+        size_t nn = (size_t)nstr * nnod + i;
+        double q = -1.0 * arenod[i] * ckrw[nn] * kznod[nn];
+        qlist[i] = q;
+        qdense[nn] = q;
+    }
+}
 
 // norms (NORMS, SRC/norms.f:18-38) + storage change (STORMB, SRC/stormb.f) + boundary flux sums
 // (FLUXMB, SRC/fluxmb.f:29-88): block partials in fixed order
@@ -998,8 +1036,25 @@ struct DBuf {
     void release() { if (base) cudaFree(base); base = p = nullptr; }
 };
 
+// host bookkeeping of one nansfdirbc / nansfneubc record stream: the three-slot window of BCONE/BCNXT/BCBAK
+struct HostBc {
+    int nrec = 0;
+    std::vector<double> time, val;
+    std::vector<int> ptr, node, n2d;
+    int slot[3] = {-1, -1, -1};
+    double tim[3] = {0, 0, 0};
+    int next = 0, hti = 0, active = -2;   // active: record currently loaded on the device (-1 none, -2 never)
+    int anbc() const { return active >= 0 ? ptr[active + 1] - ptr[active] : 0; }
+};
+
 struct CathySim {
     CathyProblem p;
+    HostBc dir, neu;
+    bool have_dir = false, have_neu = false, free_drain = false, bc_any = false;
+    DBuf<unsigned char> contp_flag, contq_flag;
+    DBuf<double> contp_val, qneu, qlist, qpnew, qpold, kznod, bcsum;
+    DBuf<int> contp_list;
+    double ndin = 0, ndout = 0, nnin = 0, nnout = 0, vndin = 0, vndout = 0, vnnin = 0, vnnout = 0;
     int nrow, ncol, nc1, nstr, nnod, n, ntri, nt, ncell;
     bool surf;
     cudaStream_t st = nullptr;
@@ -1154,7 +1209,7 @@ static int build_static(CathySim *S)
     auto diag_of = [&](int dlt) -> int { for (int d = 0; d < NDIAG; ++d) if (offs[d] == dlt) return d; return -1; };
     // --- per-tet geometry, nodal soil averages, contribution lists
     std::vector<int4> tet(nt);
-    std::vector<double> volnod(n, 0.0), pnodi(n, 0.0), snodi(n, 0.0), vgn(n, 0.0), vgrmc(n, 0.0), vgpsat(n, 0.0);
+    std::vector<double> volnod(n, 0.0), pnodi(n, 0.0), snodi(n, 0.0), vgn(n, 0.0), vgrmc(n, 0.0), vgpsat(n, 0.0), kznod(n, 0.0);
     std::vector<int> tp(n, 0);
     const size_t nslots = (size_t)NDIAG * n;
     std::vector<int> s_cnt(nslots + 1, 0), n_cnt(n + 1, 0);
@@ -1196,6 +1251,7 @@ static int build_static(CathySim *S)
         for (int q = 0; q < 4; ++q) {
             int nd = T[q];
             pnodi[nd] += p.poros[idx]; snodi[nd] += p.elstor[idx]; vgn[nd] += p.vgn[idx]; vgrmc[nd] += p.vgrmc[idx]; vgpsat[nd] += p.vgpsat[idx];
+            kznod[nd] += p.permz[idx];
             tp[nd]++;
             n_cnt[nd + 1]++;
         }
@@ -1208,7 +1264,7 @@ static int build_static(CathySim *S)
     }
     for (int k = 0; k < n; ++k) {
         if (tp[k] == 0) FAIL(-3, "node %d is not connected to any element", k + 1);
-        pnodi[k] /= tp[k]; snodi[k] /= tp[k]; vgn[k] /= tp[k]; vgpsat[k] /= tp[k]; vgrmc[k] /= tp[k];
+        pnodi[k] /= tp[k]; snodi[k] /= tp[k]; vgn[k] /= tp[k]; vgpsat[k] /= tp[k]; vgrmc[k] /= tp[k]; kznod[k] /= tp[k];
     }
     // ELL widths per diagonal / for the node family, then transposed fill (entry c of row k at [c][k])
     int wd[NDIAG], wnode = 0;
@@ -1287,6 +1343,7 @@ static int build_static(CathySim *S)
     rc |= S->vgnr.upload(vgnr); rc |= S->vgpsn.upload(vgpsn); rc |= S->vgmr.upload(vgmr); rc |= S->volnod.upload(volnod);
     rc |= S->arenod.upload(S->harenod); rc |= S->z.upload(S->hz); rc |= S->m4.upload(m4); rc |= S->veg.upload(veg);
     rc |= S->vegpar.upload(vegpar); rc |= S->tet.upload(tet);
+    if (S->bc_any) rc |= S->kznod.upload(kznod);
     rc |= S->ell_tet.upload(e_tet); rc |= S->ell_coef.upload(e_coef); rc |= S->ell_coef2.upload(e_coef2);
     for (int d = 0; d < NDIAG; ++d) { S->plan.diag[d].tet = S->ell_tet.p + fam_off[d]; S->plan.diag[d].coef = S->ell_coef.p + fam_off[d]; S->plan.diag[d].coef2 = nullptr; S->plan.diag[d].w = wd[d]; S->plan.diag[d].pad = 0; }
     S->plan.node.tet = S->ell_tet.p + fam_off[NDIAG]; S->plan.node.coef = S->ell_coef.p + fam_off[NDIAG]; S->plan.node.coef2 = S->ell_coef2.p; S->plan.node.w = wnode; S->plan.node.pad = 0;
@@ -1385,12 +1442,94 @@ static void atm_interp_launch(CathySim *S, int slot_a, int slot_b, double time, 
            S->atmrec[slot_b], !up, S->atmtim[slot_a], S->atmtim[slot_b], time, S->p.ieto, S->p.scf, S->arenod.p, S->ifatm.p, set_act,
            S->atmpot.p, S->atmact.p);
 }
+// ---- non-atmospheric BC record streams (SRC/bcone.f, bcnxt.f, bcbak.f, rdndbc.f, neumann.f) ----------------
+static void bc_advance(HostBc &b, double time, int &want)
+{   // label 200..300: shift the window while TIME > BCTIM(3); piecewise-constant values
+    while (!(time <= b.tim[2])) {
+        b.tim[0] = b.tim[1]; b.tim[1] = b.tim[2];
+        b.slot[0] = b.slot[1]; b.slot[1] = b.slot[2];
+        if (b.next >= b.nrec) { b.hti = 1; break; }
+        b.tim[2] = b.time[b.next]; b.slot[2] = b.next; b.next++;
+    }
+    want = b.tim[2] > b.tim[1] ? b.slot[1] : b.slot[2];
+}
+static void bc_one(HostBc &b, double time, int &want)
+{
+    b.hti = 0; b.tim[0] = b.tim[1] = b.tim[2] = 0.0; b.slot[0] = b.slot[1] = b.slot[2] = -1; b.next = 0;
+    if (b.nrec > 0) { b.tim[2] = b.time[0]; b.slot[2] = 0; b.next = 1; }
+    bc_advance(b, time, want);
+}
+// make record `want` of both streams the active one on the device (dense flag/value arrays + lists)
+static int bc_upload(CathySim *S, int want_dir, int want_neu)
+{
+    const int n = S->n;
+    if (want_dir != S->dir.active) {
+        S->dir.active = want_dir;
+        int m = S->dir.anbc();
+        S->have_dir = m > 0;
+        std::vector<unsigned char> flag(n, 0);
+        std::vector<double> val(n, 0.0), lv(std::max(m, 1), 0.0);
+        std::vector<int> list(std::max(m, 1), 0);
+        for (int q = 0; q < m; ++q) {
+            int nd = S->dir.node[S->dir.ptr[want_dir] + q] - 1;
+            if (nd < 0 || nd >= n) FAIL(-4, "nansfdirbc node %d out of range", nd + 1);
+            flag[nd] = 1; val[nd] = S->dir.val[S->dir.ptr[want_dir] + q]; list[q] = nd;
+        }
+        CK(cudaMemcpyAsync(S->contp_flag.p, flag.data(), n, cudaMemcpyHostToDevice, S->st));
+        CK(cudaMemcpyAsync(S->contp_val.p, val.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, S->st));
+        CK(cudaMemcpyAsync(S->contp_list.p, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, S->st));
+        CK(cudaStreamSynchronize(S->st));   // the staging vectors go out of scope
+    }
+    if (want_neu != S->neu.active) {
+        S->neu.active = want_neu;
+        int m = S->neu.anbc();
+        S->have_neu = m > 0;
+        std::vector<unsigned char> flag(n, 0);
+        std::vector<double> q(n, 0.0), ql(std::max(m, 1), 0.0);
+        for (int i = 0; i < m; ++i) {
+            int nd = S->neu.node[S->neu.ptr[want_neu] + i] - 1;
+            if (nd < 0 || nd >= n) FAIL(-4, "nansfneubc node %d out of range", nd + 1);
+            flag[nd] = 1; q[nd] += S->neu.val[S->neu.ptr[want_neu] + i]; ql[i] = S->neu.val[S->neu.ptr[want_neu] + i];
+        }
+        CK(cudaMemcpyAsync(S->contq_flag.p, flag.data(), n, cudaMemcpyHostToDevice, S->st));
+        CK(cudaMemcpyAsync(S->qneu.p, q.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, S->st));
+        CK(cudaMemcpyAsync(S->qlist.p, ql.data(), ql.size() * sizeof(double), cudaMemcpyHostToDevice, S->st));
+        CK(cudaStreamSynchronize(S->st));
+    }
+    return 0;
+}
+// NEUMANN (SRC/neumann.f): acts only when the slot-2 record is a free-drainage one (NODIN2 < 0)
+static void neumann_device(CathySim *S, const double *ckrw)
+{
+    int r = S->neu.slot[1];
+    if (r < 0 || S->neu.n2d[r] >= 0 || S->neu.active != r) return;
+    LAUNCH(S, k_free_drain_list, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, S->nstr, S->arenod.p, ckrw, S->kznod.p, S->qlist.p, S->qneu.p);
+}
+static int bc_next_both(CathySim *S, bool back)
+{
+    if (!S->bc_any) return 0;
+    int wd = S->dir.active, wn = S->neu.active;
+    if (!back) {
+        if (S->dir.hti == 0) bc_advance(S->dir, S->time, wd);
+        if (S->neu.hti == 0) bc_advance(S->neu, S->time, wn);
+    } else {   // BKSTEP: BCNXT if TIME > BCTIM(2) else BCBAK (slot 1 when the window holds an older record)
+        if (S->time > S->dir.tim[1]) { if (S->dir.hti == 0) bc_advance(S->dir, S->time, wd); }
+        else if (S->dir.tim[0] < S->dir.tim[1]) wd = S->dir.slot[0];
+        if (S->time > S->neu.tim[1]) { if (S->neu.hti == 0) bc_advance(S->neu, S->time, wn); }
+        else if (S->neu.tim[0] < S->neu.tim[1]) wn = S->neu.slot[0];
+    }
+    return bc_upload(S, wd, wn);
+}
+
 static void atmnxt(CathySim *S)
 {
     if (S->htiatm == 0) {
         atm_shift_read(S, S->time);
         atm_interp_launch(S, 1, 2, S->time, 1);
     }
+    if (S->have_dir || S->have_neu)
+        LAUNCH(S, k_mark_nonatm, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, S->have_dir ? S->contp_flag.p : nullptr,
+               S->have_neu ? S->contq_flag.p : nullptr, S->ifatm.p, (int *)nullptr);
 }
 static void atmbak(CathySim *S)
 {
@@ -1431,8 +1570,8 @@ static int assemble_system(CathySim *S, double deltat)
     LAUNCH(S, k_tet_avg, nblk(S->nt, 4 * S->grid_n), RED_BLOCK, S->nt, S->tet.p, S->ckrw.p, S->et1.p, S->krt.p, S->e1t.p);
     LAUNCH(S, k_assemble, nblk(n, 4 * S->grid_n), RED_BLOCK, n, S->plan, S->krt.p, S->e1t.p, A, S->grav.p, S->m2.p);
     LAUNCH(S, k_rhs_lhs, nblk(n, S->grid_n), RED_BLOCK, n, S->nnod, A, S->tetaf, 1.0 / deltat, S->ptnew.p, S->pnew.p, S->ptimep.p, S->swnew.p,
-           S->swtimep.p, S->m2.p, S->m4.p, S->et2.p, S->grav.p, S->ifatm.p, (const unsigned char *)nullptr, (const double *)nullptr,
-           S->atmact.p, S->atmold.p, S->qtranie.p, S->rhs.p, S->xt5.p, S->diag_true.p, S->diag_bc.p);
+           S->swtimep.p, S->m2.p, S->m4.p, S->et2.p, S->grav.p, S->ifatm.p, S->have_dir ? S->contp_flag.p : (const unsigned char *)nullptr,
+           S->have_neu ? S->qneu.p : (const double *)nullptr, S->atmact.p, S->atmold.p, S->qtranie.p, S->rhs.p, S->xt5.p, S->diag_true.p, S->diag_bc.p);
     if (S->tetaf != 1.0)   // off-diagonals of the LHS are TETAF * stiffness (SRC/cfmatp.f:24-26)
         LAUNCH(S, k_scale, nblk((long long)(NDIAG - 1) * S->ld, 8 * S->grid_n), RED_BLOCK, (long long)(NDIAG - 1) * S->ld, S->tetaf, S->A.p + S->ld);
     return 0;
@@ -1443,7 +1582,7 @@ static int solve_system(CathySim *S)
     a.n = S->n; a.nnod = S->nnod; a.itmax = S->itmax_dev; a.tol = S->tol_dev;
     a.A = make_diag(S, S->A.p); a.diag = S->diag_bc.p; a.rhs = S->rhs.p;
     a.x = S->pdiff.p; a.r = S->wr.p; a.z = S->wz.p; a.p0 = S->wp0.p; a.p1 = S->wp1.p; a.bv = S->wbv.p;
-    a.ifatm = S->ifatm.p; a.contp_flag = nullptr; a.partial = S->partial.p; a.out = S->d_iter.p;
+    a.ifatm = S->ifatm.p; a.contp_flag = S->have_dir ? S->contp_flag.p : nullptr; a.partial = S->partial.p; a.out = S->d_iter.p;
     a.counter = S->d_counter.p; a.epoch0 = S->barrier_epoch;
     void *args[] = {&a};
     CK(cudaEventRecord(S->evp0, S->st));
@@ -1467,10 +1606,16 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
     rc = solve_system(S);
     if (rc) return rc;
     Diag A = make_diag(S, S->A.p);
-    LAUNCH(S, k_update, nblk(n, S->grid_n), RED_BLOCK, n, S->nnod, S->pdiff.p, S->pold.p, S->ifatm.p, (const unsigned char *)nullptr,
-           (const double *)nullptr, S->pnew.p);
+    LAUNCH(S, k_update, nblk(n, S->grid_n), RED_BLOCK, n, S->nnod, S->pdiff.p, S->pold.p, S->ifatm.p, S->have_dir ? S->contp_flag.p : (const unsigned char *)nullptr,
+           S->have_dir ? S->contp_val.p : (const double *)nullptr, S->pnew.p);
     LAUNCH(S, k_bkflux, nblk(S->nnod, S->grid_n), RED_BLOCK, n, S->nnod, A, S->diag_true.p, S->pdiff.p, S->xt5.p, S->ifatm.p, S->tetaf,
            S->atmold.p, S->atmact.p);
+    if (S->have_dir) {
+        int m = S->dir.anbc();
+        LAUNCH(S, k_bkflux_list, nblk(m, S->grid_n), RED_BLOCK, n, m, S->contp_list.p, A, S->diag_true.p, S->pdiff.p, S->xt5.p, S->tetaf, S->qpold.p, S->qpnew.p);
+        LAUNCH(S, k_flux_sums, 1, RED_BLOCK, m, S->qpnew.p, S->bcsum.p);
+    }
+    if (S->have_neu) LAUNCH(S, k_flux_sums, 1, RED_BLOCK, S->neu.anbc(), S->qlist.p, S->bcsum.p + 2);
     LAUNCH(S, k_norms, S->grid_n, RED_BLOCK, n, S->nnod, S->pnew.p, S->pold.p, S->rhs.p, S->ptimep.p, S->swnew.p, S->swtimep.p, S->volnod.p,
            S->snodi.p, S->pnodi.p, S->ifatm.p, S->atmact.p, S->npart.p);
     LAUNCH(S, k_norms_final, 1, RED_BLOCK, S->grid_n, S->npart.p, S->pnew.p, S->pold.p, S->d_iter.p);
@@ -1489,6 +1634,8 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
     CK(cudaMemcpyAsync(S->h_iter, S->d_iter.p, sizeof(IterOut), cudaMemcpyDeviceToHost, S->st));
     int h_pond = 0;
     if (switch_always && S->surf) CK(cudaMemcpyAsync(&S->h_iter->ponding, S->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, S->st));
+    double h_bc[4] = {0, 0, 0, 0};
+    if (S->have_dir || S->have_neu) CK(cudaMemcpyAsync(h_bc, S->bcsum.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, S->st));
     CK(cudaStreamSynchronize(S->st));
     const IterOut &o = *S->h_iter;
     S->barrier_epoch = (unsigned int)o.pad;
@@ -1510,8 +1657,12 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
     S->adin = o.adin; S->adout = o.adout; S->anin = o.anin; S->anout = o.anout; S->dstore = o.dstore;
     double dm = 0.5 * S->deltat;
     double vadin = (S->adin + S->adinp) * dm, vadout = (S->adout + S->adoutp) * dm, vanin = (S->anin + S->aninp) * dm, vanout = (S->anout + S->anoutp) * dm;
-    S->vin = vadin + 0.0 + vanin + 0.0 + 0.0;
-    S->vout = vadout + 0.0 + vanout + 0.0 + 0.0 + 0.0;
+    S->ndin = S->have_dir ? h_bc[0] : 0.0; S->ndout = S->have_dir ? h_bc[1] : 0.0;
+    S->nnin = S->have_neu ? h_bc[2] : 0.0; S->nnout = S->have_neu ? h_bc[3] : 0.0;
+    S->vndin = (S->ndin + S->ndinp) * dm; S->vndout = (S->ndout + S->ndoutp) * dm;
+    S->vnnin = (S->nnin + S->nninp) * dm; S->vnnout = (S->nnout + S->nnoutp) * dm;
+    S->vin = vadin + S->vndin + vanin + S->vnnin + 0.0;
+    S->vout = vadout + S->vndout + vanout + S->vnnout + 0.0 + 0.0;
     S->erras = S->vin + S->vout - S->dstore;
     S->errel = (S->vin + S->vout) != 0.0 ? 100.0 * S->erras / (S->vin + S->vout) : 0.0;
     S->itlin += o.pcg_niter; S->nitert += o.pcg_niter;
@@ -1583,6 +1734,8 @@ static void bkstep(CathySim *S)
     if (S->deltat <= S->dtmin) { S->deltat = S->dtmin; S->dtgmin = 0; } else S->dtgmin = 1;
     S->time = S->time + S->deltat;
     S->kbackt++; S->kback++; S->iter = 1; S->nitert = 0;
+    if (S->have_dir) cudaMemcpyAsync(S->qpnew.p, S->qpold.p, (size_t)S->dir.anbc() * sizeof(double), cudaMemcpyDeviceToDevice, S->st);
+    bc_next_both(S, true);
     if (S->time > S->atmtim[1]) atmnxt(S); else atmbak(S);
     if (!S->surf) LAUNCH(S, k_switch_old, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, p.pmin, S->atmpot.p, S->ifatm.p, S->atmact.p, S->pnew.p);
     else LAUNCH(S, k_adrstn, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, p.pmin, S->atmpot.p, S->ifatm.p, S->atmact.p, S->pnew.p);
@@ -1625,6 +1778,8 @@ void cathy_destroy(CathySim *S)
     DBuf<int> *di[] = {&S->veg, &S->ell_tet, &S->ifatm, &S->ifatmp, &S->d_flags, &S->lv_ptr, &S->lv_cell,
                        &S->seqpos, &S->don_ptr, &S->don_cell, &S->d_nsurf};
     for (auto *b : di) b->release();
+    S->contp_flag.release(); S->contq_flag.release(); S->contp_val.release(); S->qneu.release(); S->qlist.release(); S->qpnew.release();
+    S->qpold.release(); S->kznod.release(); S->bcsum.release(); S->contp_list.release();
     S->d_counter.release(); S->tet.release(); S->don_dir.release(); S->npart.release(); S->spart.release(); S->d_iter.release(); S->d_step.release();
     if (S->h_iter) cudaFreeHost(S->h_iter);
     if (S->h_step) cudaFreeHost(S->h_step);
@@ -1671,6 +1826,19 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
     // failure threshold ITMXCG is scaled; LSFAIL keeps its meaning "did not reach TOLCG"
     S->itmax_dev = p.itmxcg * 20;
     S->tol_dev = p.tolcg * (p.tolcg_scale > 0.0 ? p.tolcg_scale : 1.0);
+    {   // own copies of the BC record tables (the caller's arrays are not kept)
+        auto fill = [](HostBc &b, int nrec, const double *t, const int32_t *ptr, const int32_t *node, const double *val, const int32_t *n2d) {
+            b.nrec = nrec;
+            if (nrec <= 0) return;
+            b.time.assign(t, t + nrec); b.ptr.assign(ptr, ptr + nrec + 1);
+            b.node.assign(node, node + ptr[nrec]); b.val.assign(val, val + ptr[nrec]);
+            if (n2d) b.n2d.assign(n2d, n2d + nrec); else b.n2d.assign(nrec, 0);
+        };
+        fill(S->dir, prob->ndir_rec, prob->dir_time, prob->dir_ptr, prob->dir_node, prob->dir_val, nullptr);
+        fill(S->neu, prob->nneu_rec, prob->neu_time, prob->neu_ptr, prob->neu_node, prob->neu_val, prob->neu_n2d);
+        S->bc_any = (S->dir.nrec > 0 && S->dir.ptr[S->dir.nrec] > 0) || (S->neu.nrec > 0 && S->neu.ptr[S->neu.nrec] > 0);
+        for (int r = 0; r < S->neu.nrec; ++r) if (S->neu.n2d[r] < 0) S->free_drain = true;
+    }
     S->ld = ((size_t)S->n + 31) / 32 * 32;
     S->halo = ((size_t)S->nnod + 1 + 31) / 32 * 32;
     int rc = build_static(S);
@@ -1687,6 +1855,10 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
     DBuf<double> *vs[] = {&S->atmpot, &S->atmact, &S->atmold, &S->pondnod, &S->ovflnod, &S->ovflp};
     for (auto *b : vs) a |= b->alloc(NN);
     a |= S->scal3.alloc(4);
+    if (S->bc_any) {
+        a |= S->contp_flag.alloc(N); a |= S->contq_flag.alloc(N); a |= S->contp_val.alloc(N); a |= S->qneu.alloc(N);
+        a |= S->qlist.alloc(N); a |= S->qpnew.alloc(N); a |= S->qpold.alloc(N); a |= S->contp_list.alloc(N); a |= S->bcsum.alloc(4);
+    }
     if (a) FAIL(-101, "device allocation failed (N=%d): %s", N, cudaGetErrorString(cudaGetLastError()));
     CK(cudaMallocHost((void **)&S->h_iter, sizeof(IterOut)));
     CK(cudaMallocHost((void **)&S->h_step, sizeof(StepOut)));
@@ -1696,10 +1868,6 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
         if (S->atmtab.upload(tab)) FAIL(-101, "atmbc table upload failed");
     }
     if (S->surf) { rc = build_surface(S); if (rc) return rc; }
-    if (p.ndir_rec > 0 && p.dir_ptr[p.ndir_rec] > 0) FAIL(-2, "non-atmospheric Dirichlet nodes (nansfdirbc) are not implemented on the device yet");
-    if (p.nneu_rec > 0 && p.neu_ptr[p.nneu_rec] > 0) FAIL(-2, "non-atmospheric Neumann nodes (nansfneubc) are not implemented on the device yet");
-    for (int r = 0; r < p.nneu_rec; ++r) if (p.neu_n2d[r] < 0) FAIL(-2, "free-drainage bottom (NODIN2<0) is not implemented on the device yet");
-
     // ---- initial conditions (SRC/datin.f:380-403, SRC/icvhe.f, icvhwt.f, icvdwt.f) on the host, then upload
     std::vector<double> pt(N, 0.0), pond(NN, 0.0);
     if (p.indp == 0 || p.indp == 1) for (int k = 0; k < N; ++k) pt[k] = prob->ic_psi[k];
@@ -1731,6 +1899,15 @@ static int init_atm_and_storage(CathySim *S)
     const CathyProblem &p = S->p;
     const int NN = S->nnod, N = S->n;
     S->htiatm = 0; S->atmtim[0] = S->atmtim[1] = S->atmtim[2] = 0.0; S->atmrec[0] = S->atmrec[1] = S->atmrec[2] = -1; S->atm_next = 0;
+    if (S->bc_any) {   // BCONE x2 (SRC/inital.f: NATM,NSF DIRICHLET / NEUMANN)
+        int wd = -1, wn = -1;
+        bc_one(S->dir, S->time, wd); bc_one(S->neu, S->time, wn);
+        S->dir.active = S->neu.active = -2;
+        int rcb = bc_upload(S, wd, wn);
+        if (rcb) return rcb;
+        CK(cudaMemsetAsync(S->qpold.p, 0, (size_t)N * sizeof(double), S->st));
+        CK(cudaMemsetAsync(S->qpnew.p, 0, (size_t)N * sizeof(double), S->st));
+    }
     CK(cudaMemsetAsync(S->atmpot.p, 0, (size_t)NN * sizeof(double), S->st));
     CK(cudaMemsetAsync(S->atmact.p, 0, (size_t)NN * sizeof(double), S->st));
     CK(cudaMemsetAsync(S->atmold.p, 0, (size_t)NN * sizeof(double), S->st));
@@ -1752,6 +1929,9 @@ static int init_atm_and_storage(CathySim *S)
             atm_shift_read(S, S->time);
             atm_interp_launch(S, 1, 2, S->time, 0);
         }
+        if (S->have_dir || S->have_neu)
+            LAUNCH(S, k_mark_nonatm, nblk(NN, S->grid_n), RED_BLOCK, NN, S->have_dir ? S->contp_flag.p : nullptr,
+                   S->have_neu ? S->contq_flag.p : nullptr, S->ifatm.p, S->ifatmp.p);
         LAUNCH(S, k_atmone, nblk(NN, S->grid_n), RED_BLOCK, NN, p.pmin, p.pondh_min, p.scf, S->atmpot.p, S->atmold.p, S->atmact.p, S->pnew.p,
                S->ptimep.p, S->ifatm.p, S->ifatmp.p);
     }
@@ -1764,6 +1944,14 @@ static int init_atm_and_storage(CathySim *S)
     if (rc) return rc;
     S->aactp = h3[0]; S->aninp = h3[1]; S->anoutp = h3[2];
     S->adinp = S->adoutp = S->ndinp = S->ndoutp = S->nninp = S->nnoutp = 0.0;
+    if (S->have_neu) {   // MBINIT's NNINP/NNOUTP, after the initial NEUMANN call for free drainage (SRC/cathy_main.f:2691-2708)
+        if (S->free_drain) { CK(cudaMemcpyAsync(S->ckrwp.p, S->ckrw.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, S->st)); neumann_device(S, S->ckrw.p); }
+        LAUNCH(S, k_flux_sums, 1, RED_BLOCK, S->neu.anbc(), S->qlist.p, S->bcsum.p + 2);
+        double hb[2];
+        CK(cudaMemcpyAsync(hb, S->bcsum.p + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+        CK(cudaStreamSynchronize(S->st));
+        S->nninp = hb[0]; S->nnoutp = hb[1];
+    }
     S->store0 = S->store1 = S->store2 = S->h_step->store1;
     S->timep_dirty = 1;
     (void)N;
@@ -1864,6 +2052,11 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
     const int NN = S->nnod, N = S->n;
     size_t bn = (size_t)N * sizeof(double), bs = (size_t)NN * sizeof(double);
     CK(cudaEventRecord(S->ev0, S->st));
+    {
+        int rcb = bc_next_both(S, false);
+        if (rcb) return rcb;
+        if (S->have_neu) neumann_device(S, S->ckrw.p);
+    }
     atmnxt(S);
     CK(cudaMemsetAsync(S->d_flags.p + 1, 0, sizeof(int), S->st));
     LAUNCH(S, k_etran, nblk(NN, S->grid_n), RED_BLOCK, NN, S->nstr, S->z.p, S->pnew.p, S->atmpot.p, S->veg.p, S->vegpar.p, p.scf, S->qtranie.p, S->d_flags.p + 1);
@@ -1892,6 +2085,7 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
             zero_cells(S, S->q_in_kkp1); zero_cells(S, S->q_out_kkp1_1); zero_cells(S, S->q_out_kkp1_2); zero_cells(S, S->volume_kkp1);
         }
         bkstep(S);
+        if (S->have_neu) neumann_device(S, S->ckrwp.p);
     }
     if (S->surf) LAUNCH(S, k_pond_zero, nblk(NN, S->grid_n), RED_BLOCK, NN, S->pnew.p, S->pondnod.p);
     chvelo_launch(S, S->pnew.p);
@@ -1910,6 +2104,8 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
     CK(cudaMemcpyAsync(S->ifatmp.p, S->ifatm.p, (size_t)NN * sizeof(int), cudaMemcpyDeviceToDevice, S->st));
     CK(cudaMemcpyAsync(S->atmold.p, S->atmact.p, bs, cudaMemcpyDeviceToDevice, S->st));
     CK(cudaMemcpyAsync(S->ptimep.p, S->pnew.p, bn, cudaMemcpyDeviceToDevice, S->st));
+    if (S->have_dir) CK(cudaMemcpyAsync(S->qpold.p, S->qpnew.p, (size_t)S->dir.anbc() * sizeof(double), cudaMemcpyDeviceToDevice, S->st));
+    if (S->free_drain) CK(cudaMemcpyAsync(S->ckrwp.p, S->ckrw.p, bn, cudaMemcpyDeviceToDevice, S->st));
     S->timep_dirty = 1;
     if (S->surf) {
         S->pondp = S->ponding;
@@ -1933,6 +2129,8 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
     rep->kbackt = S->kbackt; rep->nsurf = nsurf; rep->nsurft = S->nsurft; rep->noback = status == 2; rep->ponding = S->ponding;
     rep->store1 = S->store1; rep->store2 = S->store2; rep->dstore = S->dstore; rep->vin = S->vin; rep->vout = S->vout;
     rep->erras = S->erras; rep->errel = S->errel; rep->adin = S->adin; rep->adout = S->adout; rep->anin = S->anin; rep->anout = S->anout;
+    rep->ndin = S->ndin; rep->ndout = S->ndout; rep->nnin = S->nnin; rep->nnout = S->nnout;
+    rep->vndin = S->vndin; rep->vndout = S->vndout; rep->vnnin = S->vnnin; rep->vnnout = S->vnnout;
     rep->apot = so.apot; rep->aact = so.aact; rep->ovflow = so.ovflow; rep->reflow = so.reflow;
     rep->fhort = (double)so.nhort / NN; rep->fdunn = (double)so.ndunn / NN; rep->fpond = (double)so.npond / NN; rep->fsat = (double)so.nsat / NN;
     rep->n_iter_rec = std::min(S->iter, CATHY_MAXIT);
@@ -1940,6 +2138,7 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
     rep->klsfai_total = S->klsfai; rep->kback_total = S->kback;
     if (S->surf) { rep->q_outlet_1 = so.q_out1; rep->q_outlet_2 = so.q_out2; rep->ak_max = so.ak_max; }
     S->adinp = S->adin; S->adoutp = S->adout; S->aninp = S->anin; S->anoutp = S->anout;
+    S->ndinp = S->ndin; S->ndoutp = S->ndout; S->nninp = S->nnin; S->nnoutp = S->nnout;
     if (status == 2) S->finished = 1;
     else if (std::fabs(S->time - S->tmax) <= 0.001 * S->deltat) S->finished = 1;
     else {   // TIMUPD + TIMNXT (SRC/timupd.f, SRC/timnxt.f)

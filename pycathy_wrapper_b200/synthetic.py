@@ -139,7 +139,7 @@ def write_hapin(path: str, nrow: int, ncol: int, dx: float, dy: float) -> None:
 
 def make_project(path: str, nrow: int, ncol: int, nstr: int, dx: float = 0.5, dy: float = 0.5, base: float = 3.0,
                  zratio=None, dem=None, soil_rows=None, ic=("uniform", -1.0), atmbc=None, hspatm: int = 1, ieto: int = 0,
-                 pmin: float = -5.0, **parm) -> str:
+                 pmin: float = -5.0, dirbc_text: str | None = None, neubc_text: str | None = None, **parm) -> str:
     """Write a full project directory.  `ic` = ("uniform", psi) | ("hydrostatic",) | ("wt", position);
     `atmbc` = list of (time, rate) pairs (homogeneous) -- rate in m/s, +ve = rain."""
     for sub in ("input", "prepro", "output", "vtk"):
@@ -188,9 +188,9 @@ def make_project(path: str, nrow: int, ncol: int, nstr: int, dx: float = 0.5, dy
                 fh.write("%r\tATMINP\n" % float(v))
             else:
                 fh.write(" ".join("%.9E" % x for x in np.ravel(v)) + "\n")
-    for nm in ("nansfdirbc", "nansfneubc"):
+    for nm, txt in (("nansfdirbc", dirbc_text), ("nansfneubc", neubc_text)):
         with open(os.path.join(path, "input", nm), "w") as fh:
-            fh.write("0.0\tTIME\n0 0\n1.0e9\tTIME\n0 0\n")
+            fh.write(txt if txt is not None else "0.0\tTIME\n0 0\n1.0e9\tTIME\n0 0\n")
     with open(os.path.join(path, "input", "sfbc"), "w") as fh:
         fh.write("0\n0\n1.0e9\n0\n")
     with open(os.path.join(path, "input", "posizione_serb"), "w") as fh:

@@ -136,6 +136,40 @@ def test_infiltration_subsurface_only(gpu_lib, oracle_mod, tmp_path):
     assert ok, dmax
 
 
+def _bc_project(tmp_path, name, neubc_text, with_dir=True, ic=("wt", 1.0)):
+    from pycathy_wrapper_b200 import synthetic
+    from pycathy_wrapper_b200.project import load_project
+    nrow, ncol, nstr = 10, 12, 6
+    nnod = (nrow + 1) * (ncol + 1)
+    # prescribed heads on the bottom nodes of the last surface row (explicit 3-D list), changing at t = 150 s
+    nodes = [nstr * nnod + nrow * (ncol + 1) + j + 1 for j in range(ncol + 1)]
+    dirbc = ("0.0 TIME\n0 %d\n%s\n%s\n150.0 TIME\n0 %d\n%s\n%s\n1e9 TIME\n0 0\n"
+             % (len(nodes), " ".join(map(str, nodes)), " ".join(["1.2"] * len(nodes)),
+                len(nodes), " ".join(map(str, nodes)), " ".join(["0.8"] * len(nodes))))
+    p = synthetic.make_project(str(tmp_path / name), nrow, ncol, nstr, ic=ic, TMAX=400.0, TIMPRT=[400.0],
+                               atmbc=[(0.0, 1.0e-5), (1e9, 1.0e-5)], dirbc_text=dirbc if with_dir else None, neubc_text=neubc_text)
+    return load_project(p)
+
+
+def test_dirichlet_and_neumann_nodes(gpu_lib, oracle_mod, tmp_path):
+    """nansfdirbc / nansfneubc on the device: prescribed heads (two records), three injection nodes."""
+    prj = _bc_project(tmp_path, "bc1", "0.0 TIME\n0 3\n200 310 420\n2.0e-6 -1.0e-6 3.0e-6\n1e9 TIME\n0 0\n")
+    g, c, rg, rc = _run_both(gpu_lib, oracle_mod, prj)
+    ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
+    assert ok, dmax
+    assert abs(rg.ndin + rg.ndout - rc.ndin - rc.ndout) <= 1e-6 * max(abs(rc.ndin + rc.ndout), 1e-12)
+    assert abs(rg.nnin - rc.nnin) <= 1e-12 and rc.nnin > 0
+
+
+def test_free_drainage_bottom(gpu_lib, oracle_mod, tmp_path):
+    """NODIN2 < 0: unit-gradient drainage at every bottom node (NEUMANN, SRC/neumann.f)."""
+    prj = _bc_project(tmp_path, "bc2", "0.0 TIME\n-1 0\n1e9 TIME\n-1 0\n", with_dir=False, ic=("uniform", -0.5))
+    g, c, rg, rc = _run_both(gpu_lib, oracle_mod, prj)
+    ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
+    assert ok, dmax
+    assert rc.nnout < 0 and abs(rg.nnout - rc.nnout) <= 1e-6 * abs(rc.nnout)
+
+
 def test_run_processor_writes_reference_format(gpu_lib, tmp_path):
     """Through the plugin-level call: output files parse like the reference's and match the golden ones."""
     from pycathy_wrapper_b200.processor import run_processor
