@@ -173,6 +173,70 @@ int32_t cathy_debug_spmv(CathySim *sim, const double *x, double *y, int32_t reps
  * sol [N]; niter, err = relative residual as GRADDP defines it. */
 int32_t cathy_debug_solve(CathySim *sim, double *sol, int32_t *niter, double *err, double *ms);
 
+/* ---- ensemble data assimilation: dense analysis update (fp64 tensor cores) ------------------
+ * Reference arithmetic: pyCATHY/DA/enkf.py:16-224 (enkf_analysis), :225-342
+ * (enkf_analysis_localized_with_inflation); pyCATHY/DA/pf.py:3-110,197-211 (particle filter
+ * weights + systematic resampling).  Ensemble matrices are row-major [n_state][n_ens], the
+ * orientation the reference uses (ensemble.shape = (N_state, N_ens)).
+ *
+ * Notation: X [n][ne] augmented state (states, then parameters), HX [m][ne] predicted
+ * observations, y [m] (or [m][ne] when y_is_matrix), R [m][m] observation error covariance,
+ * L [n_loc][m] localisation (Schur) factors applied to the first n_loc rows of the cross
+ * covariance (NULL: none), inflate: multiplicative inflation about the analysis mean applied to the
+ * first n_infl rows (1.0: none). */
+const char *cathy_enkf_last_error(void);
+/* Whole analysis with HOST buffers (what DA.run_analysis calls, pyCATHY/DA/cathy_DA.py:86-260):
+ * Xa = X + [(X - mean)(HX - mean)^T/(ne-1) o L] B,  B = C^-1 (y - HX) or (y - HX)/diag(R) (sakov).
+ * Outputs (any may be NULL): Xa [n][ne], B [m][ne] (inv_data_pert), P [n][m] (ensemble_pert). */
+int32_t cathy_enkf_analysis_host(const double *X, int64_t n, int32_t ne, const double *HX, const double *y,
+                                 int32_t y_is_matrix, const double *R, int32_t m, int32_t sakov,
+                                 const double *L, int64_t n_loc, double inflate, int64_t n_infl,
+                                 double inflate2 /* rows n_infl..n, e.g. parameters */,
+                                 double *Xa, double *B, double *P, int32_t device, double *device_ms);
+/* Stage 1 (tiny, host buffers): S = HX - mean (obs_pert) and B (inv_data_pert); enkf.py:139-171. */
+int32_t cathy_enkf_gain(const double *hx, const double *y, int32_t y_is_matrix, const double *R, int32_t m,
+                        int32_t ne, int32_t sakov, double *S_out, double *B_out);
+/* Stages on DEVICE pointers (member-sharded ensembles; the caller all-reduces rowsum and P between
+ * stages).  `stream` is a cudaStream_t passed as an integer (0 = legacy default stream). */
+int32_t cathy_enkf_rowsum(const double *dX, int64_t n, int32_t ne, double *d_rowsum, uint64_t stream);
+/* d_mean = rowsum / ne_total is formed by the caller after the reduction (or by cathy_enkf_scale). */
+int32_t cathy_enkf_scale(double *d_v, int64_t n, double a, uint64_t stream);
+/* partial cross covariance of the local members: P = (X - mean) S_local^T / (ne_total - 1); enkf.py:182 */
+int32_t cathy_enkf_crosscov(const double *dX, const double *d_mean, const double *dS_local, int64_t n,
+                            int32_t ne_local, int32_t m, int32_t ne_total, double *dP, uint64_t stream);
+/* Xa = X + (P o L) B_local, then inflation about mean_a = mean + (P o L) bbar; enkf.py:197, :317-324.
+ * inflate applies to rows [0,n_infl), inflate2 to rows [n_infl,n). dXa may alias dX. */
+int32_t cathy_enkf_update(const double *dX, const double *dP, const double *dL, int64_t n_loc,
+                          const double *dB_local, const double *d_mean, const double *d_bbar, double inflate,
+                          int64_t n_infl, double inflate2, int64_t n, int32_t ne_local, int32_t m, double *dXa,
+                          uint64_t stream);
+/* Particle filter (pf.py:60-110): normalised weights [ne] and n_eff from HX [m][ne], y [m], obs_std [m];
+ * host buffers. */
+int32_t cathy_pf_weights(const double *hx, const double *y, const double *obs_std, int32_t m, int32_t ne,
+                         double *weights, double *n_eff);
+/* Systematic resampling (pf.py:197-211) with the caller's uniform draw u in [0,1): indices [ne] (0-based). */
+int32_t cathy_pf_systematic_resample(const double *weights, int32_t ne, double u, int32_t *indices);
+/* Xout[:, j] = X[:, idx[j]] on the device (ensemble[:, indices], pf.py:104-106); dXout must not alias dX. */
+int32_t cathy_pf_gather_members(const double *dX, int64_t n, int32_t ne, const int32_t *d_idx, double *dXout,
+                                uint64_t stream);
+/* Move one member's pressure heads between its simulation handle and column `col` of a device-resident
+ * ensemble matrix [n][ld] (stands for DA._read_state_ensemble / update_ENS_files' text round trip,
+ * pyCATHY/DA/cathy_DA.py:2684, :1863-1875).  which: 0 = psi, 1 = sw. */
+int32_t cathy_pack_state(CathySim *sim, int32_t which, double *dX, int64_t ld, int64_t col);
+int32_t cathy_unpack_psi(CathySim *sim, const double *dX, int64_t ld, int64_t col);
+/* Begin a new run at time 0 from the CURRENT pressure heads with a new TMAX / first DELTAT (<= 0: keep):
+ * the relaunch of the processor between assimilation windows (pyCATHY/cathy_tools.py:593-740 after
+ * update_ic + update_parm, pyCATHY/DA/cathy_DA.py:1863-1875). */
+int32_t cathy_restart(CathySim *sim, double tmax, double deltat);
+/* Replace the soil tables ([nstr][nzone] each; SRC/datin.f:510-514; pyCATHY/cathy_tools.py update_soil):
+ * the parameter part of the analysis.  Host buffers. */
+int32_t cathy_set_soil(CathySim *sim, const double *permx, const double *permy, const double *permz,
+                       const double *elstor, const double *poros, const double *vgn, const double *vgrmc,
+                       const double *vgpsat);
+/* Replace the atmospheric forcing table (input/atmbc rewrite per window; SRC/atmone.f).  Host buffers:
+ * times [natm], vals [natm * (HSPATM ? 1 : NNOD)].  Effective at the next cathy_restart. */
+int32_t cathy_set_atm_table(CathySim *sim, int32_t natm, const double *times, const double *vals);
+
 #ifdef __cplusplus
 }
 #endif

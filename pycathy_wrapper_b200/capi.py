@@ -174,6 +174,9 @@ class CathyLib:
     SYMBOLS = ["sizeof_problem", "sizeof_report", "last_error", "create", "destroy", "get_dims", "get_mesh",
                "initial_storage", "step", "get_state", "set_psi", "upload_atm_record", "debug_assemble", "debug_spmv", "debug_solve"]
 
+    # entry points only the product library has (in-process ensemble support); bound when present
+    PRODUCT_ONLY = ["pack_state", "unpack_psi", "restart", "set_soil", "set_atm_table"]
+
     def __init__(self, path: str, prefix: str):
         if not os.path.exists(path):
             raise CathyLibraryError(f"{path} not found -- run `python -c 'import __graft_entry__ as g; g.build()'`")
@@ -188,7 +191,19 @@ class CathyLib:
                 f[name] = getattr(self.lib, prefix + name)
             except AttributeError as e:
                 raise CathyLibraryError(f"{path} does not export {prefix}{name}") from e
+        for name in self.PRODUCT_ONLY:
+            if prefix == "cathy_":
+                try:
+                    f[name] = getattr(self.lib, prefix + name)
+                except AttributeError as e:
+                    raise CathyLibraryError(f"{path} does not export {prefix}{name}") from e
         self.f = f
+        if "pack_state" in f:
+            f["pack_state"].argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64]
+            f["unpack_psi"].argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+            f["restart"].argtypes = [C.c_void_p, C.c_double, C.c_double]
+            f["set_soil"].argtypes = [C.c_void_p] + [_D] * 8
+            f["set_atm_table"].argtypes = [C.c_void_p, C.c_int32, _D, _D]
         f["sizeof_problem"].restype = C.c_int64
         f["sizeof_report"].restype = C.c_int64
         f["last_error"].restype = C.c_char_p
@@ -282,6 +297,31 @@ class Simulation:
         rc = self.lib.f["upload_atm_record"](self.h, rec, _dp(vals))
         if rc != 0:
             raise CathyLibraryError(f"upload_atm_record failed ({rc}): {self.lib.error()}")
+
+    def _ck(self, rc: int, what: str):
+        if rc != 0:
+            raise CathyLibraryError(f"{what} failed ({rc}): {self.lib.error()}")
+
+    # ---- in-process ensemble support (product library only) ----
+    def pack_state(self, which: int, dptr: int, ld: int, col: int):
+        """Copy psi (which=0) or sw (1) into column `col` of a device matrix [n][ld] at address `dptr`."""
+        self._ck(self.lib.f["pack_state"](self.h, which, C.c_void_p(dptr), ld, col), "pack_state")
+
+    def unpack_psi(self, dptr: int, ld: int, col: int):
+        self._ck(self.lib.f["unpack_psi"](self.h, C.c_void_p(dptr), ld, col), "unpack_psi")
+
+    def restart(self, tmax: float = 0.0, deltat: float = 0.0):
+        self._ck(self.lib.f["restart"](self.h, tmax, deltat), "restart")
+
+    def set_soil(self, table: np.ndarray):
+        """table: [nstr][nzone][8] = PERMX PERMY PERMZ ELSTOR POROS VGN VGRMC VGPSAT (the rows of input/soil)."""
+        cols = [np.ascontiguousarray(table[:, :, k], dtype=np.float64) for k in range(8)]
+        self._ck(self.lib.f["set_soil"](self.h, *[_dp(c) for c in cols]), "set_soil")
+
+    def set_atm_table(self, times: np.ndarray, vals: np.ndarray):
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        self._ck(self.lib.f["set_atm_table"](self.h, len(times), _dp(times), _dp(vals)), "set_atm_table")
 
     def debug_assemble(self, deltat: float):
         topol = np.empty(self.n + 1, dtype=np.int32)

@@ -1010,6 +1010,16 @@ __global__ void k_mbinit(int nnod, const int *__restrict__ ifatmp, const double 
     if (threadIdx.x == 0) { out3[0] = t0; out3[1] = t1; out3[2] = t2; }
 }
 
+// one member's state <-> column `col` of a row-major ensemble matrix [n][ld]
+__global__ void k_pack_col(int n, const double *__restrict__ v, double *__restrict__ X, long long ld, long long col)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) X[(long long)k * ld + col] = v[k];
+}
+__global__ void k_unpack_col(int n, const double *__restrict__ X, long long ld, long long col, double *__restrict__ a, double *__restrict__ b)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) { double v = X[(long long)k * ld + col]; a[k] = v; b[k] = v; }
+}
+
 // ==========================================================================================
 // host side
 // ==========================================================================================
@@ -1029,6 +1039,11 @@ struct DBuf {
     }
     int upload(const std::vector<T> &h, size_t halo = 0)
     {
+        if (base && n == h.size() && pad == halo) {   // refresh of an existing table (cathy_set_soil)
+            if (h.empty()) return 0;
+            return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -1;
+        }
+        release();
         if (alloc(h.size(), halo)) return -1;
         if (h.empty()) return 0;
         return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -1;
@@ -1067,6 +1082,8 @@ struct CathySim {
     int64_t launches = 0;
     // host mesh kept for export
     std::vector<double> hx, hy, hz, harenod;
+    std::vector<double> h_dem, h_root, h_zratio, h_veg;   // owned copies of the caller's mesh inputs (cathy_set_soil rebuilds from them)
+    std::vector<int32_t> h_zone;
     std::vector<int> htri;       // [ntri*4] sorted nodes + zone
     std::vector<unsigned char> hexist; // [NDIAG*n] structural mask of the upper diagonals
     int64_t nterm = 0;
@@ -1807,6 +1824,14 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
         for (int i = 0; i < prob->natm; ++i) t[i] = prob->atm_time[i];
         p.atm_time = t;
     }
+    {
+        size_t nc = (size_t)p.nrow * p.ncol;
+        S->h_dem.assign(prob->dem, prob->dem + nc); S->h_zone.assign(prob->zone, prob->zone + nc);
+        S->h_root.assign(prob->root_map, prob->root_map + nc); S->h_zratio.assign(prob->zratio, prob->zratio + p.nstr);
+        const double *vp[6] = {prob->pcana, prob->pcref, prob->pcwlt, prob->zroot, prob->pz, prob->omgc};
+        S->h_veg.resize((size_t)6 * p.nveg);
+        for (int q = 0; q < 6; ++q) for (int v = 0; v < p.nveg; ++v) S->h_veg[(size_t)q * p.nveg + v] = vp[q][v];
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) FAIL(-102, "no CUDA device available: the CATHY B200 path has no CPU fallback");
     CK(cudaSetDevice(p.device));
@@ -2154,6 +2179,89 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
     rep->finished = S->finished; rep->next_deltat = S->deltat; rep->next_time = S->time;
     rep->gpu_ms = ms; rep->launches = S->launches - l0;
     rep->pcg_ms = S->pcg_ms - pm0; rep->pcg_iters = S->pcg_iters - pi0; rep->pcg_solves = S->pcg_solves - ps0;
+    return 0;
+}
+
+
+// ---- in-process ensemble support (data assimilation restarts) ----------------------------------
+int32_t cathy_pack_state(CathySim *S, int32_t which, double *dX, int64_t ld, int64_t col)
+{
+    if (which != 0 && which != 1) FAIL(-1, "cathy_pack_state: which must be 0 (psi) or 1 (sw)");
+    CK(cudaSetDevice(S->p.device));
+    LAUNCH(S, k_pack_col, nblk(S->n, S->grid_n), RED_BLOCK, S->n, which == 0 ? S->pnew.p : S->sw.p, dX, (long long)ld, (long long)col);
+    CK(cudaStreamSynchronize(S->st));   // the matrix is consumed on the caller's stream
+    return 0;
+}
+int32_t cathy_unpack_psi(CathySim *S, const double *dX, int64_t ld, int64_t col)
+{
+    CK(cudaSetDevice(S->p.device));
+    LAUNCH(S, k_unpack_col, nblk(S->n, S->grid_n), RED_BLOCK, S->n, dX, (long long)ld, (long long)col, S->pnew.p, S->ptimep.p);
+    CK(cudaStreamSynchronize(S->st));
+    return 0;
+}
+// Start a new run from the CURRENT pressure heads (device resident) at time 0 with a new TMAX: what pyCATHY does
+// between assimilation windows by rewriting input/ic + input/parm and relaunching the processor
+// (pyCATHY/DA/cathy_DA.py:1863-1875 update_ENS_files, pyCATHY/cathy_tools.py:593-740 run_processor).
+int32_t cathy_restart(CathySim *S, double tmax, double deltat)
+{
+    CK(cudaSetDevice(S->p.device));
+    const CathyProblem &p = S->p;
+    if (tmax > 0.0) S->p.tmax = tmax;
+    if (deltat > 0.0) S->p.deltat = deltat;
+    CK(cudaMemcpyAsync(S->ptimep.p, S->pnew.p, (size_t)S->n * sizeof(double), cudaMemcpyDeviceToDevice, S->st));
+    // SRC/init1.f
+    S->deltat = p.deltat; S->dtmin = p.dtmin; S->dtmax = p.dtmax; S->tmax = p.tmax; S->tetaf = p.tetaf;
+    if (S->deltat > S->dtmax) S->deltat = S->dtmax;
+    if (S->deltat <= S->dtmin) { S->deltat = S->dtmin; S->dtgmin = 0; } else S->dtgmin = 1;
+    S->timep = 0.0; S->time = S->deltat;
+    S->nstep = 1; S->iter = 1; S->nitert = 0; S->itlin = 0; S->itrtot = 0; S->kbackt = 0; S->kback = 0; S->klsfai = 0; S->nsurft = 0;
+    S->finished = 0; S->lsfail = 0;
+    S->ponding = p.ipond != 0; S->pondp = S->ponding;
+    for (int q = 0; q < 9; ++q) S->hgflag[q] = 0;
+    CK(cudaMemsetAsync(S->pondnod.p, 0, (size_t)S->nnod * sizeof(double), S->st));
+    CK(cudaMemsetAsync(S->ovflnod.p, 0, (size_t)S->nnod * sizeof(double), S->st));
+    CK(cudaMemsetAsync(S->ovflp.p, 0, (size_t)S->nnod * sizeof(double), S->st));
+    CK(cudaMemsetAsync(S->qtranie.p, 0, (size_t)S->n * sizeof(double), S->st));
+    if (S->surf) {
+        DBuf<double> *bufs[] = {&S->sw_sn, &S->q_in_kk, &S->q_in_kkp1, &S->q_out_kk_1, &S->q_out_kk_2, &S->q_out_kkp1_1, &S->q_out_kkp1_2,
+                                &S->volume_kk, &S->volume_kkp1, &S->h_water, &S->q_in_kk_sav, &S->q_out_kk_1_sav, &S->q_out_kk_2_sav,
+                                &S->volume_kk_sav, &S->q_in_kk_p, &S->q_out_kk_1_p, &S->q_out_kk_2_p, &S->volume_kk_p};
+        for (auto *b : bufs) zero_cells(S, *b);
+        CK(cudaMemsetAsync(S->d_akmax.p, 0, 3 * sizeof(double), S->st));
+    }
+    return init_atm_and_storage(S);
+}
+// Replace the soil tables ([nstr][nzone] each, SRC/datin.f:510-514) -- the parameter update of the DA analysis
+// (pyCATHY/cathy_tools.py:3043-3130 update_soil).  Nodal constants and the assembly coefficients are rebuilt.
+int32_t cathy_set_soil(CathySim *S, const double *permx, const double *permy, const double *permz, const double *elstor,
+                       const double *poros, const double *vgn, const double *vgrmc, const double *vgpsat)
+{
+    CK(cudaSetDevice(S->p.device));
+    CK(cudaStreamSynchronize(S->st));
+    CathyProblem keep = S->p;
+    S->p.permx = permx; S->p.permy = permy; S->p.permz = permz; S->p.elstor = elstor; S->p.poros = poros;
+    S->p.vgn = vgn; S->p.vgrmc = vgrmc; S->p.vgpsat = vgpsat;
+    S->p.dem = S->h_dem.data(); S->p.zone = S->h_zone.data(); S->p.root_map = S->h_root.data(); S->p.zratio = S->h_zratio.data();
+    S->p.pcana = S->h_veg.data(); S->p.pcref = S->h_veg.data() + keep.nveg; S->p.pcwlt = S->h_veg.data() + 2 * keep.nveg;
+    S->p.zroot = S->h_veg.data() + 3 * keep.nveg; S->p.pz = S->h_veg.data() + 4 * keep.nveg; S->p.omgc = S->h_veg.data() + 5 * keep.nveg;
+    int rc = build_static(S);
+    S->timep_dirty = 1;
+    return rc;
+}
+// Replace the atmospheric forcing table (times and rates) -- the per-window input/atmbc rewrite of the DA loop
+// (pyCATHY/DA/cathy_DA.py update_ENS_files -> update_atmbc).  Takes effect at the next cathy_restart.
+int32_t cathy_set_atm_table(CathySim *S, int32_t natm, const double *times, const double *vals)
+{
+    if (natm < 0) FAIL(-1, "cathy_set_atm_table: natm < 0");
+    CK(cudaSetDevice(S->p.device));
+    CK(cudaStreamSynchronize(S->st));
+    delete[] S->p.atm_time;
+    double *t = new double[std::max(natm, 1)];
+    for (int i = 0; i < natm; ++i) t[i] = times[i];
+    S->p.atm_time = t; S->p.natm = natm;
+    size_t cnt = (size_t)natm * (S->p.hspatm ? 1 : S->nnod);
+    std::vector<double> tab(vals, vals + cnt);
+    if (S->atmtab.upload(tab)) FAIL(-101, "atmbc table upload failed");
     return 0;
 }
 
