@@ -77,8 +77,36 @@ def main():
     oracle.run_prepro(tmp)
     oracle.run_reference(tmp, tmp + "_ref", "20x20x15")
     stash(tmp, os.path.join(tmp + "_ref", "output"), os.path.join(HERE, "storm20"))
+    newton()
     print("golden fixtures written")
 
 
+def newton():
+    """Newton scheme (IOPT=2, ISOLV=0: ILU(0)+BiCGSTAB) fixtures from the reference ELF built with Newton storage
+    (examples/SSHydro/weil_exemple_outputs_plot/cathy): an infiltration pulse (newton20) and the coupled storm with
+    surface routing (storm20n).  The ELF prints NaN in mbeconv's storage columns on this path (its STORMB reads SWNEW,
+    which only the Picard routines set); the step-sequence columns and psi/sw/vp are the pins."""
+    tmp = "/tmp/golden_newton20"
+    shutil.rmtree(tmp, ignore_errors=True)
+    synthetic.make_project(tmp, 20, 20, 15, ic=("wt", 1.0), ISIMGR=1, IOPT=2, ISOLV=0, TMAX=400.0, TIMPRT=[200.0, 400.0], DELTAT=1.0,
+                           DTMIN=1e-4, DTMAX=100.0, NODVP=[5],
+                           atmbc=[(0.0, 0.0), (60.0, 2.0e-5), (1800.0, 2.0e-5), (1860.0, 0.0), (1.0e9, 0.0)])
+    shutil.rmtree(tmp + "_ref", ignore_errors=True)
+    oracle.run_reference(tmp, tmp + "_ref", "20x20x15_newton")
+    stash(tmp, os.path.join(tmp + "_ref", "output"), os.path.join(HERE, "newton20"))
+    tmp = "/tmp/golden_storm20n"
+    shutil.rmtree(tmp, ignore_errors=True)
+    synthetic.make_project(tmp, 20, 20, 15, ic=("hydrostatic",), ISIMGR=2, IOPT=2, ISOLV=0, TMAX=700.0, TIMPRT=[350.0, 700.0], DELTAT=1.0,
+                           DTMIN=1e-4, NODVP=[441], atmbc=[(0.0, 0.0), (60.0, 1.0e-4), (600.0, 1.0e-4), (660.0, 0.0), (1.0e9, 0.0)],
+                           zratio=[0.002, 0.004, 0.006, 0.008, 0.01, 0.01, 0.02, 0.02, 0.05, 0.05, 0.1, 0.1, 0.2, 0.2, 0.22])
+    oracle.run_prepro(tmp)
+    shutil.rmtree(tmp + "_ref", ignore_errors=True)
+    oracle.run_reference(tmp, tmp + "_ref", "20x20x15_newton")
+    stash(tmp, os.path.join(tmp + "_ref", "output"), os.path.join(HERE, "storm20n"))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "newton":
+        newton()
+    else:
+        main()
