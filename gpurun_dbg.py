@@ -1,19 +1,26 @@
-import os, sys
+import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from oracle import oracle
+import __graft_entry__ as g
+g.build()
 from pycathy_wrapper_b200.capi import Simulation, load_library
 from pycathy_wrapper_b200.project import load_project
-prj = load_project('tests/golden/storm20')
-tol = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
-g, c = Simulation(load_library(), prj, tolcg_scale=tol), oracle.simulation(prj)
-for k in range(1, 8):
-    rg, rc = g.step(), c.step()
-    print('step', k, 'gpu', (rg.nstep, rg.iter, rg.kbackt, rg.nsurf, rg.deltat), 'cpu', (rc.nstep, rc.iter, rc.kbackt, rc.nsurf, rc.deltat))
-    for i in range(max(rg.n_iter_rec, rc.n_iter_rec)):
-        a = rg.it[i] if i < rg.n_iter_rec else None
-        b = rc.it[i] if i < rc.n_iter_rec else None
-        print('   it', i+1, 'gpu', None if a is None else (a.niter, '%.6e'%a.pinf, a.ikmax, '%.6e'%a.fl2), 'cpu', None if b is None else (b.niter, '%.6e'%b.pinf, b.ikmax, '%.6e'%b.fl2))
-    sg, sc = g.state(), c.state()
-    print('   psi maxdiff %.3e  ifatm diff %d  atmact maxdiff %.3e pond maxdiff %.3e' % (np.abs(sg['psi']-sc['psi']).max(), int((sg['ifatm']!=sc['ifatm']).sum()), np.abs(sg['atmact']-sc['atmact']).max(), np.abs(sg['pond']-sc['pond']).max()))
-    if (rg.iter != rc.iter): break
+from oracle import oracle
+prj = load_project("tests/golden/storm20n")
+c = oracle.simulation(prj)
+crec, cpsi150 = [], None
+while True:
+    r = c.step(); crec.append((r.nstep, r.iter, r.kbackt, r.nsurf, r.deltat))
+    if r.nstep == 150: cpsi150 = c.state()["psi"].copy()
+    if r.finished: break
+cpsi = c.state()["psi"]
+for scale in (1e-2, 1e-3, 1e-4):
+    s = Simulation(load_library(), prj, tolcg_scale=scale)
+    k, first, d150, lin = 0, None, None, 0
+    t0 = time.time()
+    while True:
+        r = s.step(); k += 1; lin += r.pcg_iters
+        if first is None and (k > len(crec) or (r.nstep, r.iter, r.kbackt, r.nsurf) != crec[k - 1][:4]): first = k
+        if r.nstep == 150: d150 = np.abs(s.state()["psi"] - cpsi150).max()
+        if r.finished: break
+    print("scale", scale, "steps", k, "oracle steps", len(crec), "first divergence", first, "dmax@150", d150, "dmax end", np.abs(s.state()["psi"] - cpsi).max(), "lin its", lin, "wall", time.time() - t0)

@@ -98,7 +98,7 @@ def _ip(a):
 class ProblemHolder:
     """Owns the numpy buffers a CathyProblem points to (they must outlive the create call)."""
 
-    def __init__(self, prj: CathyProject, precond: int = 0, device: int = 0, tolcg_scale: float = 1.0,
+    def __init__(self, prj: CathyProject, precond: int = 0, device: int = 0, tolcg_scale: float = 0.0,
                  **overrides):
         p = dict(prj.parm)
         p.update({k.upper(): v for k, v in overrides.items()})
@@ -324,9 +324,11 @@ class Simulation:
         self._ck(self.lib.f["set_atm_table"](self.h, len(times), _dp(times), _dp(vals)), "set_atm_table")
 
     def debug_assemble(self, deltat: float):
+        # Picard: symmetric upper CSR (NTERM entries); Newton: the Jacobian in full CSR (nnz entries)
+        nent = self.nnz if int(self.parm.get("IOPT", 1)) == 2 else self.nterm
         topol = np.empty(self.n + 1, dtype=np.int32)
-        ja = np.empty(self.nterm, dtype=np.int32)
-        coef = np.empty(self.nterm)
+        ja = np.empty(nent, dtype=np.int32)
+        coef = np.empty(nent)
         rhs = np.empty(self.n)
         rc = self.lib.f["debug_assemble"](self.h, deltat, _ip(topol), _ip(ja), _dp(coef), _dp(rhs))
         if rc != 0:

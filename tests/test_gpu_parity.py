@@ -82,7 +82,7 @@ def test_pcg_solution_matches_oracle(gpu_lib, oracle_mod, weill, dt):
     assert np.max(np.abs(xg - xc)) <= 1e-7 * max(np.abs(xc).max(), 1e-12), (np.abs(xg - xc).max(), np.abs(xc).max(), ng, nc)
 
 
-def _run_both(gpu_lib, oracle_mod, prj, nsteps=None):
+def _run_both(gpu_lib, oracle_mod, prj, nsteps=None, store_rtol=1e-9):
     from pycathy_wrapper_b200.capi import Simulation
     g, c = Simulation(gpu_lib, prj), oracle_mod.simulation(prj)
     k = 0
@@ -92,7 +92,7 @@ def _run_both(gpu_lib, oracle_mod, prj, nsteps=None):
         assert (rg.nstep, rg.iter, rg.kbackt, rg.nsurf) == (rc.nstep, rc.iter, rc.kbackt, rc.nsurf), \
             f"step {k}: gpu (nstep,iter,back,nsurf)={(rg.nstep, rg.iter, rg.kbackt, rg.nsurf)} oracle={(rc.nstep, rc.iter, rc.kbackt, rc.nsurf)}"
         assert abs(rg.deltat - rc.deltat) <= 1e-12 * rc.deltat and abs(rg.time - rc.time) <= 1e-12 * rc.time
-        assert abs(rg.store1 - rc.store1) <= 1e-9 * abs(rc.store1)
+        assert abs(rg.store1 - rc.store1) <= store_rtol * abs(rc.store1)
         assert abs(rg.erras) <= max(2.0 * abs(rc.erras), 1e-9 * abs(rc.store1)), (rg.erras, rc.erras)
         assert rg.finished == rc.finished
         if rg.finished or (nsteps and k >= nsteps):
@@ -193,3 +193,95 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(capi, "library_path", lambda: "/nonexistent/libcathy_b200.so")
     with pytest.raises(capi.CathyLibraryError):
         capi.load_library()
+
+
+# ---------------------------------------------------------------------------------------------
+# Newton scheme (IOPT = 2): SRC/newton.f on the device against the oracle (itself byte-identical to the reference's Newton ELF)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def newton20():
+    from pycathy_wrapper_b200.project import load_project
+    return load_project(os.path.join(GOLDEN, "newton20"))
+
+
+@pytest.mark.parametrize("dt", [0.5, 20.0])
+def test_newton_jacobian_matches_oracle(gpu_lib, oracle_mod, newton20, dt):
+    """NEWUNS+ASSNEW+RHSNEW+CFMATN+RHSGRV+BCNEW: same full-row CSR pattern (bit exact), Jacobian and RHS to 1e-10 relative.
+    Three warm-up steps first so that psi differs from the previous time level and every derivative term is active."""
+    import scipy.sparse as sp
+    from pycathy_wrapper_b200.capi import Simulation
+    g, c = Simulation(gpu_lib, newton20), oracle_mod.simulation(newton20)
+    for _ in range(3):
+        g.step(); c.step()
+    tg, jg, ag, bg = g.debug_assemble(dt)
+    tc, jc, ac, bc = c.debug_assemble(dt)
+    assert np.array_equal(tg, tc) and np.array_equal(jg, jc)
+    big = ac > 1e80
+    assert np.array_equal(big, ag > 1e80)
+    assert np.max(np.abs(ag[~big] - ac[~big])) <= 1e-10 * np.abs(ac[~big]).max()
+    assert np.max(np.abs(bg - bc)) <= 1e-9 * max(np.abs(bc).max(), 1e-30)
+    n = g.n
+    J = sp.csr_matrix((ac, jc - 1, tc - 1), shape=(n, n))
+    assert abs(J - J.T).max() > 0            # the derivative terms make it nonsymmetric
+    xg, ng, eg, _ = g.debug_solve()
+    xc, nc, ec, _ = c.debug_solve()
+    assert eg <= 1e-10
+    assert np.max(np.abs(xg - xc)) <= 1e-7 * max(np.abs(xc).max(), 1e-12), (np.abs(xg - xc).max(), np.abs(xc).max(), ng, nc)
+
+
+def test_newton_illconditioned_saturated_solve(gpu_lib, oracle_mod):
+    """Hydrostatic, fully saturated start of the storm: the Newton increment is ~5e4 x the RHS (ill-conditioned); the device
+    BiCGSTAB must still land on the oracle's ILU(0)-BiCGSTAB solution."""
+    from pycathy_wrapper_b200.capi import Simulation
+    from pycathy_wrapper_b200.project import load_project
+    prj = load_project(os.path.join(GOLDEN, "storm20n"))
+    g, c = Simulation(gpu_lib, prj), oracle_mod.simulation(prj)
+    tg, jg, ag, bg = g.debug_assemble(1.0)
+    tc, jc, ac, bc = c.debug_assemble(1.0)
+    assert np.array_equal(jg, jc)
+    big = ac > 1e80
+    assert np.max(np.abs(ag[~big] - ac[~big])) <= 1e-10 * np.abs(ac[~big]).max()
+    assert np.max(np.abs(bg - bc)) <= 1e-9 * np.abs(bc).max()
+    xg, ng, eg, _ = g.debug_solve()
+    xc, nc, ec, _ = c.debug_solve()
+    assert np.abs(xc).max() > 0.1
+    assert np.max(np.abs(xg - xc)) <= 1e-6 * np.abs(xc).max(), (np.abs(xg - xc).max(), np.abs(xc).max(), ng, eg)
+
+
+def test_newton_full_run_same_steps_and_heads(gpu_lib, oracle_mod):
+    """Infiltration pulse under Newton: all 130 accepted steps, nonlinear iteration counts and heads as the reference ELF."""
+    from pycathy_wrapper_b200.project import load_project
+    prj = load_project(os.path.join(GOLDEN, "newton20"))
+    g, c, rg, rc = _run_both(gpu_lib, oracle_mod, prj)
+    assert rg.nstep == 130
+    sg, sc = g.state(), c.state()
+    ok, dmax = psi_close(sg["psi"], sc["psi"])
+    assert ok, dmax
+    assert np.array_equal(sg["ifatm"], sc["ifatm"])
+    gold = np.load(os.path.join(GOLDEN, "newton20", "golden", "psi.npz"))
+    ok, dmax = psi_close(sg["psi"], gold["values"][-1], rtol=2e-6, atol=1e-7)   # the ELF's file carries 7 significant digits
+    assert ok, dmax
+
+
+def test_newton_coupled_storm(gpu_lib, oracle_mod):
+    """Newton + surface routing (BASELINE config 3 in small): the first step back-steps 9 times in the reference because its
+    third linear solve fails -- the device must fail there too -- and the following accepted steps (ponding, routing
+    sub-steps, atmospheric switching every iteration) must match exactly with heads inside the 1e-6 / 1e-8 m band: checked
+    for the first 150 of the 556 steps.  Further on the reference's own nonlinear convergence is non-monotone with
+    switching at every iteration (e.g. PINF 3.6e-4, 4.0e-4, 9.3e-5 at step 154, accepted at TOLUNS = 1e-4), so the two
+    linear solvers' different roundoff shows up at the 1e-4 m level in single iterates and eventually in one iteration
+    count (measured: step 388 of 556); from there only the end state is compared: same end time, storage to 1e-6
+    relative, heads to 1e-3 m (measured 1.5e-5 m)."""
+    from pycathy_wrapper_b200.project import load_project
+    prj = load_project(os.path.join(GOLDEN, "storm20n"))
+    g, c, rg, rc = _run_both(gpu_lib, oracle_mod, prj, nsteps=150, store_rtol=1e-8)
+    assert rg.nstep == 150 and g.state()["ifatm"].tolist() == c.state()["ifatm"].tolist()
+    ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
+    assert ok, dmax
+    while not rg.finished:
+        rg = g.step()
+    while not rc.finished:
+        rc = c.step()
+    assert abs(rg.time - rc.time) <= 1e-9 * rc.time
+    assert abs(rg.store1 - rc.store1) <= 1e-6 * rc.store1
+    assert np.max(np.abs(g.state()["psi"] - c.state()["psi"])) <= 1e-3
