@@ -218,6 +218,123 @@ def run_ours(args, size):
         dist.destroy_process_group()
 
 
+def run_enkf(args, size):
+    """BASELINE config 4: EnKF data assimilation, `--members` members (default 256) on a 100x100x15 catchment, members sharded
+    over the ranks, SWC observations at 64 surface nodes, one forecast window + one analysis per "step".
+    Metric: ensemble member-steps/s (accepted time steps summed over members / seconds), analysis included."""
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    from pycathy_wrapper_b200 import da
+    from pycathy_wrapper_b200.capi import load_library
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("CATHY_NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+    lib = load_library()
+    nrow, ncol, nstr = size
+    ne = args.members
+    mine = [k for k in range(ne) if k % world == rank]
+    rng = np.random.default_rng(1234)
+    lnk = 0.5 * rng.standard_normal(ne)                      # log-normal Ks, sigma = 0.5
+    dwt = 0.25 * rng.standard_normal(ne)                     # IC: water-table depth perturbation, sigma = 0.25 m
+    window = 1800.0
+    prjs = []
+    for k in mine:
+        d = tempfile.mkdtemp(prefix="cathy_enkf_")
+        ks = 1.88e-4 * float(np.exp(lnk[k]))
+        row = (ks, ks, ks, 1.0e-5, 0.55, 1.46, 0.15, 0.03125)
+        synthetic.make_project(d, nrow, ncol, nstr, ic=("wt", 1.0 + float(dwt[k])), ISIMGR=1, DELTAT=10.0, DTMIN=1e-2, DTMAX=300.0,
+                               TMAX=window, TIMPRT=[window], NODVP=[1], soil_rows=[row] * nstr,
+                               atmbc=[(0.0, 5.0e-6), (1.0e9, 5.0e-6)])
+        prjs.append(load_project(d))
+        shutil.rmtree(d, ignore_errors=True)
+    t_build = time.perf_counter()
+    ens = da.Ensemble(lib, prjs, device=local)
+    t_build = time.perf_counter() - t_build
+    n, nnod = ens.n, prjs[0].nnod
+    m = 64
+    obs_nodes = (np.linspace(0, nnod - 1, m).astype(np.int64))          # 64 surface-layer nodes
+    R = np.diag(np.full(m, 0.02 ** 2))
+    noise = 0.02 * np.random.default_rng(4321).standard_normal(m)        # synthetic truth = ensemble-mean SWC + observation noise
+    failed_total = [0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def rsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return float(t.item())
+
+    def rmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def cycle():
+        steps = ens.forecast()
+        failed_total[0] += len(ens.failed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        HX = ens.predict_obs(obs_nodes, 0.55)
+        ybar = HX.sum(dim=1)
+        if world > 1:
+            dist.all_reduce(ybar)
+        y = (ybar / ne).cpu().numpy() + noise
+        ens.analysis(obs_nodes, 0.55, y, R, sakov=False, inflate=1.02, HX=HX)
+        e1.record()
+        ens.restart(window, 10.0)
+        torch.cuda.synchronize()
+        return steps, e0.elapsed_time(e1)
+
+    for _ in range(max(args.warmup, 1)):
+        cycle()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    steps = 0
+    ana_ms = 0.0
+    for _ in range(args.steps):
+        s_, a_ = cycle()
+        steps += s_
+        ana_ms += a_
+    barrier()
+    wall = rmax(time.perf_counter() - t0)
+    sampler.stop_flag = True
+    steps_all = rsum(float(steps))
+    out = {"metric": "ensemble member-steps/s", "value": steps_all / wall, "unit": "member-steps/s", "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "EnKF DA, %d members on a %dx%d DEM x %d layers (%d nodes), %d SWC observations, window %.0f s; a step = "
+                                  "one forecast window of every member + one analysis (NCCL all-gather / all-reduce when sharded)" % (ne, ncol, nrow, nstr, n, m, window),
+                      "parallelism": "members round-robin over %d GPU(s)" % world, "member_steps_per_cycle": steps_all / args.steps},
+           "node_member_steps_per_s": steps_all * n / wall, "analysis_ms_per_cycle": rmax(ana_ms / args.steps),
+           "setup_s_per_rank": t_build, "failed_member_windows": rsum(float(failed_total[0])), "clocks": sampler.summary()}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    ens.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def cpu_baseline(size, budget_s: float = 25.0, max_steps: int = 1000):
     """The CPU oracle (a C port of the reference's algorithm; the reference ELFs cannot hold this mesh)
     timed on a bounded sample of the same workload: the first accepted step(s), single thread."""
@@ -282,12 +399,18 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", default="200x200x20")
+    ap.add_argument("--size", default=None)
+    ap.add_argument("--workload", default="picard", choices=["picard", "enkf"], help="picard: BASELINE config 2 (headline); enkf: config 4")
+    ap.add_argument("--members", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.size is None:
+        args.size = "200x200x20" if args.workload == "picard" else "100x100x15"
     size = tuple(int(v) for v in args.size.lower().split("x"))
+    if args.workload == "enkf" and args.impl == "ours":
+        return run_enkf(args, size)
     if args.impl == "reference":
         run_reference(args, size)
     else:

@@ -361,13 +361,18 @@ class Ensemble:
         self.steps = 0
 
     def forecast(self) -> int:
-        """Advance every local member to the end of its current window (TMAX); returns accepted steps summed over members."""
+        """Advance every local member to the end of its current window (TMAX); returns accepted steps summed over members.
+        Members whose run stopped before TMAX (no convergence at DTMIN) are listed in ``self.failed`` -- pyCATHY's
+        ``rejected_ens`` (pyCATHY/DA/cathy_DA.py:1450-1491 detects them from a short mbeconv)."""
         steps = 0
-        for s in self.sims:
+        self.failed = []
+        for j, s in enumerate(self.sims):
             while True:
                 rep = s.step()
                 steps += 1
                 if rep.finished:
+                    if rep.noback:
+                        self.failed.append(j)
                     break
         self.steps += steps
         return steps
@@ -378,13 +383,18 @@ class Ensemble:
             s.pack_state(1, self.SW.data_ptr(), self.ne_local, j)
         return self.X, self.SW
 
-    def analysis(self, obs_nodes, porosity, y, R, sakov=False, L=None, inflate=1.0):
-        """Assimilate soil-water-content observations at 0-based ``obs_nodes`` (theta = Sw * porosity, the 'swc' mapping of
-        pyCATHY/DA/mapper.py) into the pressure-head ensemble, in place."""
+    def predict_obs(self, obs_nodes, porosity):
+        """Predicted soil-water-content observations of the local members, [m][ne_local] on the device."""
         t = self.torch
         self.gather_states()
         idx = t.as_tensor(np.asarray(obs_nodes, dtype=np.int64), device=self.X.device)
-        HX = self.SW.index_select(0, idx) * float(porosity)
+        return self.SW.index_select(0, idx) * float(porosity)
+
+    def analysis(self, obs_nodes, porosity, y, R, sakov=False, L=None, inflate=1.0, HX=None):
+        """Assimilate soil-water-content observations at 0-based ``obs_nodes`` (theta = Sw * porosity, the 'swc' mapping of
+        pyCATHY/DA/mapper.py) into the pressure-head ensemble, in place."""
+        if HX is None:
+            HX = self.predict_obs(obs_nodes, porosity)
         _, info = sharded_enkf_update(self.X, HX, y, R, sakov=sakov, L=L, inflate=inflate, n_infl=self.n, group=self.group)
         info["HX_local"] = HX
         return info
