@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CATHY_ABI_VERSION 1
+#define CATHY_ABI_VERSION 2
 #define CATHY_MAXIT 64 /* upper bound on ITUNS kept in a step report (CATHY.H MAXIT=30) */
 
 /* Everything DATIN / INITAL read from the project files (SRC/datin.f:80-514,
@@ -89,6 +89,11 @@ typedef struct CathyProblem {
     int32_t precond;    /* 0: default; see DESIGN.md                                */
     int32_t device;     /* CUDA device ordinal                                      */
     double tolcg_scale; /* multiplies TOLCG for the device PCG (<=0: 1)            */
+    /* --- row-block partition of ONE mesh over several GPUs (dd_world > 1): this handle owns the global
+     * node rows [dd_row0, dd_row1) of the (nrow+1) DEM node rows (row 0 = north); all arrays above stay
+     * GLOBAL.  The handle builds its window (owned rows + 2 ghost node rows per interior side), and the
+     * ranks exchange halo rows and reduction scalars through peer memory (cathy_dd_export/connect). */
+    int32_t dd_world, dd_rank, dd_row0, dd_row1;
 } CathyProblem;
 
 /* One nonlinear iteration line of output/iter (SRC/conver.f:44 FORMAT 1070). */
@@ -158,6 +163,20 @@ int32_t cathy_set_psi(CathySim *sim, const double *psi);
  * reference reading the next (TIME, ATMINP) record of input/atmbc as the run proceeds, SRC/atmnxt.f:34-45).
  * vals: [NNOD] when HSPATM = 0, [1] otherwise.  Host -> device copy on the handle's stream. */
 int32_t cathy_upload_atm_record(CathySim *sim, int32_t rec, const double *vals);
+
+/* ---- row-block partition (BASELINE config 5): one process per GPU, one handle per process --------
+ * After every rank has created its handle: each exports an opaque 64-byte CUDA IPC handle of its
+ * communication box, the caller gathers them (torch.distributed all_gather) and every rank connects.
+ * From then on cathy_step must be called by ALL ranks for every step (the kernels rendezvous). */
+int32_t cathy_dd_export(CathySim *sim, void *handle64);
+int32_t cathy_dd_connect(CathySim *sim, const void *handles /* [dd_world][64] */);
+/* Same-process variant (one host thread per handle): wire the ranks by direct pointers, then let every thread call
+ * cathy_dd_start concurrently (the collective part of the set-up). */
+int32_t cathy_dd_connect_local(CathySim *sim, CathySim *const *all /* [dd_world] */);
+int32_t cathy_dd_start(CathySim *sim);
+/* info[0..7] = window start (global node row), window rows, owned global rows [a,b), local NNOD, local N,
+ * global NNOD, global N. */
+int32_t cathy_dd_info(const CathySim *sim, int64_t info[8]);
 
 /* ---- kernel-level entry points used by parity tests and bench.py -------------------- */
 /* Assemble the Picard system at the current state for time step `deltat` without solving

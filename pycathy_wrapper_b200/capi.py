@@ -12,7 +12,7 @@ import numpy as np
 
 from .project import CathyProject
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAXIT = 64
 _D = C.POINTER(C.c_double)
 _I = C.POINTER(C.c_int32)
@@ -58,6 +58,7 @@ class CathyProblem(C.Structure):
         ("dtm_b1_sf", _D), ("dtm_y1_sf", _D), ("dtm_nrc", _D),
         ("precond", C.c_int32), ("device", C.c_int32),
         ("tolcg_scale", C.c_double),
+        ("dd_world", C.c_int32), ("dd_rank", C.c_int32), ("dd_row0", C.c_int32), ("dd_row1", C.c_int32),
     ]
 
 
@@ -99,7 +100,7 @@ class ProblemHolder:
     """Owns the numpy buffers a CathyProblem points to (they must outlive the create call)."""
 
     def __init__(self, prj: CathyProject, precond: int = 0, device: int = 0, tolcg_scale: float = 0.0,
-                 **overrides):
+                 dd: tuple | None = None, **overrides):
         p = dict(prj.parm)
         p.update({k.upper(): v for k, v in overrides.items()})
         self.parm = p
@@ -165,6 +166,10 @@ class ProblemHolder:
         elif int(p["ISIMGR"]) == 2:
             raise ValueError("ISIMGR=2 needs the prepro rasters")
         s.precond, s.device, s.tolcg_scale = precond, device, tolcg_scale
+        if dd is not None:      # (world, rank, row0, row1): row-block partition, see partition_rows()
+            s.dd_world, s.dd_rank, s.dd_row0, s.dd_row1 = (int(v) for v in dd)
+        else:
+            s.dd_world, s.dd_rank, s.dd_row0, s.dd_row1 = 1, 0, 0, prj.nrow + 1
         self.struct = s
 
 
@@ -175,7 +180,7 @@ class CathyLib:
                "initial_storage", "step", "get_state", "set_psi", "upload_atm_record", "debug_assemble", "debug_spmv", "debug_solve"]
 
     # entry points only the product library has (in-process ensemble support); bound when present
-    PRODUCT_ONLY = ["pack_state", "unpack_psi", "restart", "set_soil", "set_atm_table"]
+    PRODUCT_ONLY = ["pack_state", "unpack_psi", "restart", "set_soil", "set_atm_table", "dd_export", "dd_connect", "dd_connect_local", "dd_start", "dd_info"]
 
     def __init__(self, path: str, prefix: str):
         if not os.path.exists(path):
@@ -204,6 +209,11 @@ class CathyLib:
             f["restart"].argtypes = [C.c_void_p, C.c_double, C.c_double]
             f["set_soil"].argtypes = [C.c_void_p] + [_D] * 8
             f["set_atm_table"].argtypes = [C.c_void_p, C.c_int32, _D, _D]
+            f["dd_export"].argtypes = [C.c_void_p, C.c_void_p]
+            f["dd_connect"].argtypes = [C.c_void_p, C.c_void_p]
+            f["dd_info"].argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+            f["dd_connect_local"].argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+            f["dd_start"].argtypes = [C.c_void_p]
         f["sizeof_problem"].restype = C.c_int64
         f["sizeof_report"].restype = C.c_int64
         f["last_error"].restype = C.c_char_p
@@ -323,6 +333,21 @@ class Simulation:
         vals = np.ascontiguousarray(vals, dtype=np.float64)
         self._ck(self.lib.f["set_atm_table"](self.h, len(times), _dp(times), _dp(vals)), "set_atm_table")
 
+    # ---- row-block partition ----
+    def dd_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.f["dd_export"](self.h, buf), "dd_export")
+        return buf.raw
+
+    def dd_connect(self, handles: bytes):
+        self._ck(self.lib.f["dd_connect"](self.h, C.c_char_p(handles)), "dd_connect")
+
+    def dd_info(self) -> dict:
+        v = (C.c_int64 * 8)()
+        self._ck(self.lib.f["dd_info"](self.h, v), "dd_info")
+        keys = ["win_row0", "win_rows", "own_row0", "own_row1", "nnod_local", "n_local", "nnod_global", "n_global"]
+        return dict(zip(keys, (int(x) for x in v)))
+
     def debug_assemble(self, deltat: float):
         # Picard: symmetric upper CSR (NTERM entries); Newton: the Jacobian in full CSR (nnz entries)
         nent = self.nnz if int(self.parm.get("IOPT", 1)) == 2 else self.nterm
@@ -366,3 +391,16 @@ def load_library() -> CathyLib:
     if _LIB is None:
         _LIB = CathyLib(library_path(), "cathy_")
     return _LIB
+
+
+def partition_rows(nrow: int, world: int) -> list[tuple[int, int]]:
+    """Owned global node-row ranges [a, b) of the (nrow + 1) DEM node rows for `world` ranks: contiguous strips of DEM rows
+    (SURVEY.md section 8e), as even as possible."""
+    rows = nrow + 1
+    base, rem = divmod(rows, world)
+    out, a = [], 0
+    for r in range(world):
+        b = a + base + (1 if r < rem else 0)
+        out.append((a, b))
+        a = b
+    return out

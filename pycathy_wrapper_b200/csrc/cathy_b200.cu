@@ -150,7 +150,7 @@ __global__ void k_curves(int n, Soil s, const double *__restrict__ ptnew, const 
 }
 // CHVELO (SRC/chvelo.f, IVGHU=0) fused with STORCAL's sum term (SRC/storcal.f)
 __global__ void k_chvelo(int n, Soil s, const double *__restrict__ psiv, const double *__restrict__ volnod,
-                         double *__restrict__ sw, double *__restrict__ ckrw, double *__restrict__ partial)
+                         double *__restrict__ sw, double *__restrict__ ckrw, double *__restrict__ partial, const unsigned char *__restrict__ own)
 {
     __shared__ double sh[32];
     double acc = 0.0;
@@ -160,7 +160,7 @@ __global__ void k_chvelo(int n, Soil s, const double *__restrict__ psiv, const d
         double w = s.vgpnot[i] * se + s.rr[i];
         sw[i] = w;
         ckrw[i] = fvgkr(psi, se, m, s.vgmr[i]);
-        acc += w * volnod[i] * s.pnodi[i];
+        if (!own || (own[i] & 1)) acc += w * volnod[i] * s.pnodi[i];
     }
     double t = block_sum<RED_BLOCK>(acc, sh);
     if (threadIdx.x == 0) partial[blockIdx.x] = t;
@@ -275,6 +275,176 @@ __global__ void k_spmv(int n, Diag A, const double *__restrict__ diag0, const do
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) y[k] = dia_row(A, diag0, x, k, n);
 }
 
+
+// ==========================================================================================
+// Row-block partition of ONE mesh over several GPUs (BASELINE config 5).  Each rank holds a window of DEM rows (its owned
+// node rows + DD_W ghost node rows per interior side) with the same layer-major numbering and the same 15-point DIA stencil.
+// Ranks exchange data through peer memory over NVLink (CUDA IPC mapped "boxes"): halo rows are STORED straight into the
+// neighbour's inbox by the kernel that produces them, all-reduces are slot writes + system-scope release/acquire flags,
+// summed in rank order on every rank (bit-identical results on all ranks, hence identical control flow).
+// ==========================================================================================
+#define DD_W 2
+#define DD_MAXW 8
+#define DD_NRED 24
+#define DD_TIMEOUT_CYCLES 12000000000LL   // ~6 s: a lost peer turns into an error, not a hang
+struct DDBox {                               // lives in each rank's device memory, mapped by all peers
+    unsigned int ar_flag[DD_MAXW];           // sequence number of the last all-reduce contribution of rank r
+    unsigned int halo_flag[2];               // [0]: from the north neighbour, [1]: from the south neighbour
+    unsigned int pad[6];
+    double ar_slot[2][DD_MAXW][DD_NRED];     // [parity][rank][value]
+};
+struct DDCtx {
+    int world, rank, north, south;           // neighbour ranks (-1: none)
+    DDBox *me;
+    DDBox *peer[DD_MAXW];                    // peer[rank] == me
+    double *inbox_me;                        // [2 parities][2 sides][hcap]
+    double *inbox_peer[DD_MAXW];
+    long long hcap;
+    int nc1, nlay, nnod, own_a, own_b;
+    unsigned int *seq;                       // [0] all-reduce sequence, [1] halo sequence (device resident, advanced by the kernels)
+    int *err;
+};
+__device__ __forceinline__ void dd_wait(const unsigned int *flag, unsigned int target, int *err, int site = 1)
+{
+    if (*(volatile int *)err) return;
+    long long t0 = clock64();
+    for (;;) {
+        unsigned int v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - target) >= 0) return;
+        if (clock64() - t0 > DD_TIMEOUT_CYCLES) { *(volatile int *)err = site + 10 * (int)(target & 0xffffffu); return; }
+    }
+}
+__device__ __forceinline__ void dd_release(unsigned int *flag, unsigned int v)
+{
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+}
+// All-reduce (sum, rank order) of NV block-uniform values; called by every thread of every block of a kernel whose blocks
+// all hold the same v[] (after a grid-wide local reduction).  sh: NV doubles of shared memory.
+template <int NV>
+__device__ __forceinline__ void dd_allreduce(const DDCtx &c, unsigned int &seq, double (&v)[NV], double *sh)
+{
+    ++seq;
+    const int par = seq & 1u;
+    if (blockIdx.x == 0 && (int)threadIdx.x < c.world) {
+        DDBox *dst = c.peer[threadIdx.x];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) dst->ar_slot[par][c.rank][q] = v[q];
+        dd_release(&dst->ar_flag[c.rank], seq);
+    }
+    if ((int)threadIdx.x < c.world) dd_wait(&c.me->ar_flag[threadIdx.x], seq, c.err, 1);
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double acc = 0.0;
+        for (int r = 0; r < c.world; ++r) acc += *(volatile double *)&c.me->ar_slot[par][r][threadIdx.x];
+        sh[threadIdx.x] = acc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NV; ++q) v[q] = sh[q];
+    __syncthreads();
+}
+// element e of a halo message <-> (layer, row offset, column)
+__device__ __forceinline__ long long dd_index(const DDCtx &c, long long e, int row0)
+{
+    int j = (int)(e % c.nc1);
+    long long t = e / c.nc1;
+    int w = (int)(t % DD_W), l = (int)(t / DD_W);
+    return (long long)l * c.nnod + (long long)(row0 + w) * c.nc1 + j;
+}
+__device__ __forceinline__ void dd_send_rows(const DDCtx &c, unsigned int next_seq, const double *vec, long long tid, long long nthreads)
+{   // my first / last DD_W owned rows -> the neighbours' south / north inboxes
+    const long long E = (long long)DD_W * c.nlay * c.nc1;
+    const int par = next_seq & 1u;
+    bool any = false;
+    if (c.north >= 0) { double *dst = c.inbox_peer[c.north] + ((size_t)par * 2 + 1) * c.hcap; for (long long e = tid; e < E; e += nthreads) { dst[e] = vec[dd_index(c, e, c.own_a)]; any = true; } }
+    if (c.south >= 0) { double *dst = c.inbox_peer[c.south] + ((size_t)par * 2 + 0) * c.hcap; for (long long e = tid; e < E; e += nthreads) { dst[e] = vec[dd_index(c, e, c.own_b - DD_W)]; any = true; } }
+    if (any) __threadfence_system();
+}
+// after a grid-wide barrier that follows the sends: publish, wait for the neighbours' rows, copy them into the ghost rows
+__device__ __forceinline__ void dd_recv_rows(const DDCtx &c, unsigned int &seq, double *vec, long long tid, long long nthreads)
+{
+    ++seq;
+    const int par = seq & 1u;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && c.north >= 0) dd_release(&c.peer[c.north]->halo_flag[1], seq);
+    if (blockIdx.x == 0 && threadIdx.x == 1 && c.south >= 0) dd_release(&c.peer[c.south]->halo_flag[0], seq);
+    if (threadIdx.x == 0 && c.north >= 0) dd_wait(&c.me->halo_flag[0], seq, c.err, 2);
+    if (threadIdx.x == 1 && c.south >= 0) dd_wait(&c.me->halo_flag[1], seq, c.err, 3);
+    __syncthreads();
+    const long long E = (long long)DD_W * c.nlay * c.nc1;
+    if (c.north >= 0) { const double *src = c.inbox_me + ((size_t)par * 2 + 0) * c.hcap; for (long long e = tid; e < E; e += nthreads) vec[dd_index(c, e, c.own_a - DD_W)] = *(volatile const double *)&src[e]; }
+    if (c.south >= 0) { const double *src = c.inbox_me + ((size_t)par * 2 + 1) * c.hcap; for (long long e = tid; e < E; e += nthreads) vec[dd_index(c, e, c.own_b)] = *(volatile const double *)&src[e]; }
+}
+// stand-alone halo exchange of one N-vector between kernels of the nonlinear loop (two launches: the kernel boundary is the
+// grid-wide barrier between "all rows stored" and "flag published")
+__global__ void k_dd_send(DDCtx c, const double *__restrict__ vec)
+{
+    dd_send_rows(c, c.seq[1] + 1u, vec, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+__global__ void k_dd_recv(DDCtx c, double *__restrict__ vec, unsigned int *counter)
+{   // counter: arrival count so that the LAST block to finish advances the sequence number
+    unsigned int seq = c.seq[1];
+    dd_recv_rows(c, seq, vec, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(counter, 1u) == gridDim.x - 1) { c.seq[1] = seq; *counter = 0u; }
+    }
+}
+// cross-rank combination of the per-iteration scalars (sums in rank order; max-norm with the reference's "last node wins" tie
+// rule on GLOBAL node numbers) and of the per-step scalars; one block
+__global__ void k_dd_combine_iter(DDCtx c, IterOut *__restrict__ io, int gnnod, int lo_shift)
+{
+    __shared__ double sh[DD_NRED];
+    unsigned int seq = c.seq[0];
+    // the two norms arrive squared-rooted from k_norms_final: square them back for the sum
+    double v[7] = {io->pl2 * io->pl2, io->fl2 * io->fl2, io->dstore, io->adin, io->adout, io->anin, io->anout};
+    dd_allreduce<7>(c, seq, v, sh);
+    // max part: every rank publishes (pinf, global ik, pnew_ik, pold_ik, finf) in its slot, all pick the same winner
+    int ikl = io->ikmax, lay = ikl / c.nnod;
+    double gik = (double)((long long)lay * gnnod + (ikl - lay * c.nnod) + lo_shift);
+    ++seq;
+    const int par = seq & 1u;
+    if ((int)threadIdx.x < c.world) {
+        DDBox *dst = c.peer[threadIdx.x];
+        double *sl = dst->ar_slot[par][c.rank];
+        sl[0] = io->pinf; sl[1] = gik; sl[2] = io->pnew_ik; sl[3] = io->pold_ik; sl[4] = io->finf;
+        dd_release(&dst->ar_flag[c.rank], seq);
+    }
+    if ((int)threadIdx.x < c.world) dd_wait(&c.me->ar_flag[threadIdx.x], seq, c.err, 4);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double pinf = -1.0, ik = -1.0, pn = 0.0, po = 0.0, finf = 0.0;
+        for (int r = 0; r < c.world; ++r) {
+            const volatile double *sl = c.me->ar_slot[par][r];
+            if (sl[0] > pinf || (sl[0] == pinf && sl[1] > ik)) { pinf = sl[0]; ik = sl[1]; pn = sl[2]; po = sl[3]; }
+            finf = fmax(finf, sl[4]);
+        }
+        io->pl2 = sqrt(v[0]); io->fl2 = sqrt(v[1]); io->dstore = v[2]; io->adin = v[3]; io->adout = v[4]; io->anin = v[5]; io->anout = v[6];
+        io->pinf = pinf; io->ikmax = (int)ik; io->pnew_ik = pn; io->pold_ik = po; io->finf = finf;
+        c.seq[0] = seq;
+    }
+}
+__global__ void k_dd_combine_step(DDCtx c, StepOut *__restrict__ so, double *__restrict__ extra3)
+{
+    __shared__ double sh[DD_NRED];
+    unsigned int seq = c.seq[0];
+    double v[21];
+    v[0] = so->store1; v[1] = so->apot; v[2] = so->aact; v[3] = so->ovflow; v[4] = so->reflow;
+    v[5] = so->nhort; v[6] = so->ndunn; v[7] = so->npond; v[8] = so->nsat;
+    for (int q = 0; q < 9; ++q) v[9 + q] = so->hgflag[q];
+    for (int q = 0; q < 3; ++q) v[18 + q] = extra3 ? extra3[q] : 0.0;
+    dd_allreduce<21>(c, seq, v, sh);
+    if (threadIdx.x == 0) {
+        so->store1 = v[0]; so->apot = v[1]; so->aact = v[2]; so->ovflow = v[3]; so->reflow = v[4];
+        so->nhort = (int)v[5]; so->ndunn = (int)v[6]; so->npond = (int)v[7]; so->nsat = (int)v[8];
+        for (int q = 0; q < 9; ++q) so->hgflag[q] = (int)v[9 + q];
+        if (extra3) for (int q = 0; q < 3; ++q) extra3[q] = v[18 + q];
+        c.seq[0] = seq;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // K5-K7: the whole SYMSLV (SRC/solscal-extended.f:4669-4699) as ONE persistent cooperative
 // kernel: preconditioner set-up, x0 = M^-1 b, and the GRADDP recurrence (:1260-1380) with two
@@ -297,6 +467,8 @@ struct PcgArgs {
     unsigned int *counter;   // grid barrier counter (monotonic)
     unsigned int epoch0;     // its value at launch
     IterOut *out;
+    const unsigned char *own;   // row-block partition: bit0 = owned row, bit1 / bit2 = row is sent to the north / south neighbour
+    DDCtx dd;
 };
 
 // Grid-wide barrier for the persistent kernel: one arrival per block on a monotonically increasing counter
@@ -343,23 +515,36 @@ __device__ __forceinline__ void grid_reduce3(cg::grid_group &grid, unsigned int 
     __syncthreads();
 }
 
-template <int BLOCK, bool CUSTOM>
+template <int BLOCK, bool CUSTOM, bool DD>
 __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_pcg(PcgArgs a)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[BLOCK / 32][3];
+    __shared__ double shdd[4];
     unsigned int epoch = a.epoch0;
+    unsigned int seq_ar = 0, seq_h = 0;
+    if (DD) { seq_ar = a.dd.seq[0]; seq_h = a.dd.seq[1]; }
     const int n = a.n, stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
     const double *__restrict__ dg = a.diag;
+    const unsigned char *__restrict__ own = a.own;
     // x0 = M^-1 b ; xlung = ||b_free||^2   (PRODDP call at :4686, XLUNG at :1286-1297)
     double xl = 0.0;
     for (int k = t0; k < n; k += stride) {
         double b = a.rhs[k];
         a.x[k] = b / dg[k];
-        if (!is_dirichlet(k, a.nnod, a.ifatm, a.contp_flag)) xl += b * b;
+        if ((!DD || (own[k] & 1)) && !is_dirichlet(k, a.nnod, a.ifatm, a.contp_flag)) xl += b * b;
     }
     double xlung, d1, d2;
     grid_reduce3<BLOCK, CUSTOM>(grid, a.counter, epoch, xl, 0.0, 0.0, a.partial, sh, xlung, d1, d2);
+    if (DD) {   // global ||b||^2, and x0 on the ghost rows from their owners
+        double v[1] = {xlung};
+        dd_allreduce<1>(a.dd, seq_ar, v, shdd);
+        xlung = v[0];
+        dd_send_rows(a.dd, seq_h + 1u, a.x, t0, stride);
+        grid_barrier(a.counter, epoch);
+        dd_recv_rows(a.dd, seq_h, a.x, t0, stride);
+        grid_barrier(a.counter, epoch);
+    }
     // r = b - A x0 ; z = M^-1 r ; p_old = 0 so that p = z in the first phase A
     for (int k = t0; k < n; k += stride) {
         double r = a.rhs[k] - dia_row(a.A, dg, a.x, k, n);
@@ -368,6 +553,12 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_pcg(PcgArgs a)
         a.p0[k] = 0.0;
     }
     if (CUSTOM) grid_barrier(a.counter, epoch); else grid.sync();
+    if (DD) {
+        dd_send_rows(a.dd, seq_h + 1u, a.z, t0, stride);
+        grid_barrier(a.counter, epoch);
+        dd_recv_rows(a.dd, seq_h, a.z, t0, stride);
+        grid_barrier(a.counter, epoch);
+    }
     double beta = 0.0, err = 0.0;
     double *pold = a.p0, *pnew = a.p1;
     int niter = 1;
@@ -392,15 +583,17 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_pcg(PcgArgs a)
                 }
                 pnew[k] = pk;
                 a.bv[k] = acc;
-                s_pr += pk * a.r[k];
-                s_pb += pk * acc;
+                if (!DD || (own[k] & 1)) { s_pr += pk * a.r[k]; s_pb += pk * acc; }
             }
         }
         double pr, pb;
         grid_reduce3<BLOCK, CUSTOM>(grid, a.counter, epoch, s_pr, s_pb, 0.0, a.partial, sh, pr, pb, d1);
+        if (DD) { double v[2] = {pr, pb}; dd_allreduce<2>(a.dd, seq_ar, v, shdd); pr = v[0]; pb = v[1]; }
         double alfa = pr / pb;
-        // ---- phase B
+        // ---- phase B (row-block partition: the new z of my boundary rows goes straight into the neighbours' inboxes)
         double s_bz = 0.0, s_rr = 0.0;
+        const int hpar = (seq_h + 1u) & 1u;
+        bool sent = false;
         for (int k = t0; k < n; k += stride) {
             double bk = a.bv[k];
             double r = a.r[k] - alfa * bk;
@@ -408,18 +601,38 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_pcg(PcgArgs a)
             a.x[k] = a.x[k] + alfa * pnew[k];
             double zz = r / dg[k];
             a.z[k] = zz;
-            s_bz += bk * zz;
-            if (!is_dirichlet(k, a.nnod, a.ifatm, a.contp_flag)) s_rr += r * r;
+            if (!DD || (own[k] & 1)) {
+                s_bz += bk * zz;
+                if (!is_dirichlet(k, a.nnod, a.ifatm, a.contp_flag)) s_rr += r * r;
+            }
+            if (DD && (own[k] & 6)) {
+                const DDCtx &c = a.dd;
+                int l = k / c.nnod, sidx = k - l * c.nnod, row = sidx / c.nc1, j = sidx - row * c.nc1;
+                if ((own[k] & 2) && c.north >= 0) c.inbox_peer[c.north][((size_t)hpar * 2 + 1) * c.hcap + ((size_t)l * DD_W + (row - c.own_a)) * c.nc1 + j] = zz;
+                if ((own[k] & 4) && c.south >= 0) c.inbox_peer[c.south][((size_t)hpar * 2 + 0) * c.hcap + ((size_t)l * DD_W + (row - (c.own_b - DD_W))) * c.nc1 + j] = zz;
+                sent = true;
+            }
         }
+        if (DD && sent) __threadfence_system();
         double bz, rr;
         grid_reduce3<BLOCK, CUSTOM>(grid, a.counter, epoch, s_bz, s_rr, 0.0, a.partial, sh, bz, rr, d1);
+        if (DD) {
+            double v[2] = {bz, rr};
+            dd_allreduce<2>(a.dd, seq_ar, v, shdd);
+            bz = v[0]; rr = v[1];
+            dd_recv_rows(a.dd, seq_h, a.z, t0, stride);     // publish my rows (stored in phase B), fetch the neighbours'
+            grid_barrier(a.counter, epoch);
+        }
         beta = -bz / pb;
         err = xlung > 0.0 ? sqrt(rr / xlung) : sqrt(rr / n);
         double *t = pold; pold = pnew; pnew = t;
-        if (err > a.tol && niter < a.itmax) { ++niter; continue; }
+        if (err > a.tol && niter < a.itmax && !(DD && *(volatile int *)a.dd.err)) { ++niter; continue; }
         break;
     }
-    if (t0 == 0) { a.out->pcg_niter = niter; a.out->pcg_err = err; a.out->pad = (int)epoch; }
+    if (t0 == 0) {
+        a.out->pcg_niter = niter; a.out->pcg_err = err; a.out->pad = (int)epoch;
+        if (DD) { a.dd.seq[0] = seq_ar; a.dd.seq[1] = seq_h; }
+    }
 }
 
 
@@ -816,7 +1029,7 @@ __global__ void k_norms(int n, int nnod, const double *__restrict__ pnew, const 
                         const double *__restrict__ swnew, const double *__restrict__ swtimep,
                         const double *__restrict__ volnod, const double *__restrict__ snodi,
                         const double *__restrict__ pnodi, const int *__restrict__ ifatm, const double *__restrict__ atmact,
-                        NormPartial *__restrict__ part)
+                        NormPartial *__restrict__ part, const unsigned char *__restrict__ own)
 {
     __shared__ double sh[32];
     __shared__ double shv[RED_BLOCK / 32];
@@ -824,6 +1037,7 @@ __global__ void k_norms(int n, int nnod, const double *__restrict__ pnew, const 
     double pl2 = 0, fl2 = 0, ds = 0, pinf = 0, finf = 0, adin = 0, adout = 0, anin = 0, anout = 0;
     int ik = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        if (own && !(own[k] & 1)) continue;      // row-block partition: ghost rows belong to another rank
         double d = pnew[k] - pold[k], da = fabs(d), f = rhs[k];
         pl2 += d * d;
         fl2 += f * f;
@@ -1212,7 +1426,7 @@ __global__ void k_pond_zero(int nnod, const double *__restrict__ pnew, double *_
 struct StepPartial { double apot, aact, refl, ovf; int c[13]; int pad; };
 __global__ void k_step_partial(int nnod, int nstr, double pmin, double ph, const int *__restrict__ ifatm,
                                const double *__restrict__ atmpot, const double *__restrict__ atmact,
-                               const double *__restrict__ pnew, StepPartial *__restrict__ part)
+                               const double *__restrict__ pnew, StepPartial *__restrict__ part, const unsigned char *__restrict__ own)
 {
     __shared__ double sh[32];
     __shared__ int shi[13];
@@ -1221,6 +1435,7 @@ __global__ void k_step_partial(int nnod, int nstr, double pmin, double ph, const
     double apot = 0, aact = 0, refl = 0, ovf = 0;
     int hg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, nh = 0, nd = 0, np = 0, ns = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nnod; k += gridDim.x * blockDim.x) {
+        if (own && !(own[k] & 1)) continue;
         double pot = atmpot[k], act = atmact[k], pn = pnew[k];
         int f = ifatm[k];
         apot += pot; aact += act;
@@ -1318,12 +1533,13 @@ __global__ void k_atmone(int nnod, double pmin, double ph, double scf, const dou
         if (fp == 1 || fp == 2) atmold[i] = 0.0;
     }
 }
-__global__ void k_mbinit(int nnod, const int *__restrict__ ifatmp, const double *__restrict__ atmold, double *__restrict__ out3)
+__global__ void k_mbinit(int nnod, const int *__restrict__ ifatmp, const double *__restrict__ atmold, double *__restrict__ out3,
+                         const unsigned char *__restrict__ own)
 {   // MBINIT sums (SRC/mbinit.f): AACTP, ANINP, ANOUTP -- one block
     __shared__ double sh[32];
     double a = 0, b = 0, c = 0;
     for (int k = threadIdx.x; k < nnod; k += blockDim.x)
-        if (ifatmp[k] == 0) { a += atmold[k]; if (atmold[k] > 0.0) b += atmold[k]; else c += atmold[k]; }
+        if (ifatmp[k] == 0 && (!own || (own[k] & 1))) { a += atmold[k]; if (atmold[k] > 0.0) b += atmold[k]; else c += atmold[k]; }
     double t0 = block_sum<RED_BLOCK>(a, sh), t1 = block_sum<RED_BLOCK>(b, sh), t2 = block_sum<RED_BLOCK>(c, sh);
     if (threadIdx.x == 0) { out3[0] = t0; out3[1] = t1; out3[2] = t2; }
 }
@@ -1380,6 +1596,19 @@ struct HostBc {
     int anbc() const { return active >= 0 ? ptr[active + 1] - ptr[active] : 0; }
 };
 
+struct DDComm {
+    void *base = nullptr;            // [DDBox][inbox 2 x 2 x hcap doubles]
+    size_t bytes = 0;
+    void *peer_base[DD_MAXW] = {nullptr};
+    bool opened[DD_MAXW] = {false};
+    bool connected = false;
+    DDCtx ctx;
+    unsigned int *seq = nullptr;     // device [2]
+    int *err = nullptr;              // device [1]
+    unsigned int *recv_counter = nullptr;
+    cudaIpcMemHandle_t handle;
+};
+
 struct CathySim {
     CathyProblem p;
     HostBc dir, neu;
@@ -1425,6 +1654,16 @@ struct CathySim {
     DBuf<double> wr, wz, wp0, wp1, wbv, partial, store_part;
     DBuf<double> Ju, Jl, dinv, dckrw, detai, ts, s1, ws, wsh, wt;   // Newton: Jacobian diagonals, Jacobi scaling, derivative curves, element factors, BiCGSTAB vectors
     bool newton = false;
+    // ---- row-block partition of one large mesh over several GPUs (BASELINE config 5) ----
+    bool dd = false, pcg_shared_gpu = false;
+    int dd_world = 1, dd_rank = 0;
+    int gnrow = 0;            // global number of DEM rows
+    int grow0 = 0;            // global node row of local node row 0 (window start)
+    int own_a = 0, own_b = 0; // owned LOCAL node rows [own_a, own_b)
+    int gnnod = 0;            // global surface node count
+    std::vector<double> ovr_z; std::vector<int> ovr_veg; double ovr_zmin = 0.0;
+    DBuf<unsigned char> own;  // [n] 1 = row owned by this rank (reductions count owned rows only)
+    struct DDComm *comm = nullptr;
     DBuf<NormPartial> npart;
     DBuf<IterOut> d_iter;
     DBuf<StepOut> d_step;
@@ -1502,7 +1741,11 @@ static int build_static(CathySim *S)
     S->htri.resize(4 * (size_t)ntri);
     std::vector<int> cnt(nnod, 0);
     for (int i = 0; i <= nrow; ++i)
-        for (int j = 0; j <= ncol; ++j) { int k = i * nc1 + j; S->hx[k] = p.west + j * p.dx; S->hy[k] = p.south + (nrow - i) * p.dy; }
+        for (int j = 0; j <= ncol; ++j) {
+            int k = i * nc1 + j;
+            S->hx[k] = p.west + j * p.dx;
+            S->hy[k] = S->dd ? p.south + (S->gnrow - (i + S->grow0)) * p.dy : p.south + (nrow - i) * p.dy;   // row-block window: global row index
+        }
     for (int i = 0, it = 0; i < nrow; ++i)
         for (int j = 0; j < ncol; ++j) {
             int n00 = i * nc1 + j, n10 = n00 + nc1, n11 = n10 + 1, n01 = n00 + 1, zn = p.zone[i * ncol + j];
@@ -1514,6 +1757,7 @@ static int build_static(CathySim *S)
             int *b = &S->htri[4 * (size_t)it++]; b[0] = n00; b[1] = n01; b[2] = n11; b[3] = zn;
         }
     for (int k = 0; k < nnod; ++k) S->hz[k] /= cnt[k];
+    if (S->dd) for (int k = 0; k < nnod; ++k) S->hz[k] = S->ovr_z[k];   // node elevations from the GLOBAL DEM (window edges lack cells)
     for (int t = 0; t < ntri; ++t) {
         const int *T = &S->htri[4 * (size_t)t];
         double a3 = 0, a2 = 0;
@@ -1527,6 +1771,7 @@ static int build_static(CathySim *S)
     // --- vertical discretisation (SRC/gen3d.f:52-77)
     double zmin = RMAX_;
     for (int i = 0; i < nnod; ++i) zmin = std::min(zmin, S->hz[i]);
+    if (S->dd) zmin = S->ovr_zmin;
     for (int i = 0; i < nnod; ++i) {
         double zthick = (S->hz[i] - zmin) + p.base, zrsum = 0.0;
         for (int j = 1; j <= nstr; ++j) {
@@ -1688,6 +1933,7 @@ static int build_static(CathySim *S)
                 for (int q = 0; q < 3; ++q) { acc[t1[q]] += e; c2[t1[q]]++; acc[t2[q]] += e; c2[t2[q]]++; }
             }
         for (int k = 0; k < nnod; ++k) { int v = (int)(acc[k] / c2[k]); veg[k] = std::min(std::max(v, 1), p.nveg) - 1; }
+        if (S->dd) veg = S->ovr_veg;
     }
     std::vector<double> vegpar((size_t)6 * p.nveg);
     for (int v = 0; v < p.nveg; ++v) {
@@ -1909,18 +2155,26 @@ static void weight_and_copy(CathySim *S)
 // chvelo + storage sum -> returns STORE1 through h_step later; here just launches
 static void chvelo_launch(CathySim *S, const double *psi)
 {
-    LAUNCH(S, k_chvelo, S->grid_n, RED_BLOCK, S->n, make_soil(S), psi, S->volnod.p, S->sw.p, S->ckrw.p, S->store_part.p);
+    LAUNCH(S, k_chvelo, S->grid_n, RED_BLOCK, S->n, make_soil(S), psi, S->volnod.p, S->sw.p, S->ckrw.p, S->store_part.p, S->dd ? S->own.p : (const unsigned char *)nullptr);
 }
-static int step_final_sync(CathySim *S)
+static int step_final_sync(CathySim *S, double *extra3 = nullptr)
 {
     int nbs = nblk(S->nnod, S->grid_n);
-    LAUNCH(S, k_step_partial, nbs, RED_BLOCK, S->nnod, S->nstr, S->p.pmin, S->p.pondh_min, S->ifatm.p, S->atmpot.p, S->atmact.p, S->pnew.p, S->spart.p);
+    LAUNCH(S, k_step_partial, nbs, RED_BLOCK, S->nnod, S->nstr, S->p.pmin, S->p.pondh_min, S->ifatm.p, S->atmpot.p, S->atmact.p, S->pnew.p, S->spart.p, S->dd ? S->own.p : (const unsigned char *)nullptr);
     LAUNCH(S, k_step_final, 1, RED_BLOCK, nbs, S->spart.p, S->grid_n, S->store_part.p, S->d_step.p);
+    if (S->dd) LAUNCH(S, k_dd_combine_step, 1, 32, S->comm->ctx, S->d_step.p, extra3);
     CK(cudaMemcpyAsync(S->h_step, S->d_step.p, sizeof(StepOut), cudaMemcpyDeviceToHost, S->st));
     CK(cudaStreamSynchronize(S->st));
     return 0;
 }
 
+static void dd_exchange(CathySim *S, double *vec)
+{
+    const long long E = (long long)DD_W * (S->nstr + 1) * S->nc1;
+    int blocks = (int)std::max<long long>(1, std::min<long long>((E + RED_BLOCK - 1) / RED_BLOCK, S->sms));
+    LAUNCH(S, k_dd_send, blocks, RED_BLOCK, S->comm->ctx, vec);
+    LAUNCH(S, k_dd_recv, blocks, RED_BLOCK, S->comm->ctx, vec, S->comm->recv_counter);
+}
 // ---- one Picard iteration on the device: SRC/picard.f:74-198 + MASBAL + NORMS ------------
 static int assemble_system(CathySim *S, double deltat)
 {
@@ -1950,10 +2204,18 @@ static int solve_system(CathySim *S)
     void *fn = nullptr;
     const bool cu = S->pcg_custom != 0;
     switch (S->pcg_block) {
-    case 256: fn = cu ? (void *)k_pcg<256, true> : (void *)k_pcg<256, false>; break;
-    case 512: fn = cu ? (void *)k_pcg<512, true> : (void *)k_pcg<512, false>; break;
-    default: fn = cu ? (void *)k_pcg<1024, true> : (void *)k_pcg<1024, false>; break;
+    case 256: fn = cu ? (void *)k_pcg<256, true, false> : (void *)k_pcg<256, false, false>; break;
+    case 512: fn = cu ? (void *)k_pcg<512, true, false> : (void *)k_pcg<512, false, false>; break;
+    default: fn = cu ? (void *)k_pcg<1024, true, false> : (void *)k_pcg<1024, false, false>; break;
     }
+    a.own = nullptr;
+    if (S->dd) { fn = (void *)k_pcg<1024, true, true>; a.own = S->own.p; a.dd = S->comm->ctx; }
+    if (S->dd && S->pcg_shared_gpu) {
+        // several ranks share this GPU (tests): the driver runs cooperative launches one at a time, which would deadlock ranks that
+        // wait for each other inside the kernel.  The custom grid barrier only needs co-residency, which CATHY_PCG_GRID guarantees.
+        k_pcg<1024, true, true><<<S->grid_pcg, 1024, 0, S->st>>>(a);
+        CK(cudaGetLastError());
+    } else
     CK(cudaLaunchCooperativeKernel(fn, dim3(S->grid_pcg), dim3(S->pcg_block), args, 0, S->st));
     CK(cudaEventRecord(S->evp1, S->st));
     S->launches++;
@@ -2020,8 +2282,9 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
     }
     if (S->have_neu) LAUNCH(S, k_flux_sums, 1, RED_BLOCK, S->neu.anbc(), S->qlist.p, S->bcsum.p + 2);
     LAUNCH(S, k_norms, S->grid_n, RED_BLOCK, n, S->nnod, S->pnew.p, S->pold.p, S->rhs.p, S->ptimep.p, S->swnew.p, S->swtimep.p, S->volnod.p,
-           S->snodi.p, S->pnodi.p, S->ifatm.p, S->atmact.p, S->npart.p);
+           S->snodi.p, S->pnodi.p, S->ifatm.p, S->atmact.p, S->npart.p, S->dd ? S->own.p : (const unsigned char *)nullptr);
     LAUNCH(S, k_norms_final, 1, RED_BLOCK, S->grid_n, S->npart.p, S->pnew.p, S->pold.p, S->d_iter.p);
+    if (S->dd) LAUNCH(S, k_dd_combine_iter, 1, 32, S->comm->ctx, S->d_iter.p, S->gnnod, S->grow0 * S->nc1);
     // atmospheric switching is evaluated every iteration when TOLSWI is large (SRC/conver.f:58-71); when it is
     // conditional the host decides after the read-back below.
     bool switch_always = S->p.tolswi >= 1.0e29;
@@ -2056,6 +2319,14 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
             if (S->surf) { CK(cudaMemcpyAsync(&h_pond, S->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, S->st)); CK(cudaStreamSynchronize(S->st)); S->ponding = h_pond; }
         }
     } else if (S->surf) S->ponding = o.ponding;
+    if (S->dd) {   // the new heads (after SHLPIC and the atmospheric switch) go to the neighbours' ghost rows
+        dd_exchange(S, S->pnew.p);
+        int h_err = 0;
+        CK(cudaMemcpyAsync(&h_err, S->comm->err, sizeof(int), cudaMemcpyDeviceToHost, S->st));
+        CK(cudaStreamSynchronize(S->st));
+        if (h_err) FAIL(-6, "row-block partition: a peer did not answer within the time-out (rank %d of %d, wait site %d, sequence %d, PCG iterations %d)",
+                        S->dd_rank, S->dd_world, h_err % 10, h_err / 10, S->h_iter->pcg_niter);
+    }
     // MASBAL scalars (SRC/masbal.f:69-109); fluxes were summed BEFORE the switch, as in the reference
     S->adin = o.adin; S->adout = o.adout; S->anin = o.anin; S->anout = o.anout; S->dstore = o.dstore;
     double dm = 0.5 * S->deltat;
@@ -2188,6 +2459,15 @@ void cathy_destroy(CathySim *S)
     S->contp_flag.release(); S->contq_flag.release(); S->contp_val.release(); S->qneu.release(); S->qlist.release(); S->qpnew.release();
     S->qpold.release(); S->kznod.release(); S->bcsum.release(); S->contp_list.release();
     S->d_counter.release(); S->tet.release(); S->don_dir.release(); S->npart.release(); S->spart.release(); S->d_iter.release(); S->d_step.release();
+    if (S->comm) {
+        for (int r = 0; r < DD_MAXW; ++r) if (S->comm->opened[r]) cudaIpcCloseMemHandle(S->comm->peer_base[r]);
+        if (S->comm->base) cudaFree(S->comm->base);
+        if (S->comm->seq) cudaFree(S->comm->seq);
+        if (S->comm->err) cudaFree(S->comm->err);
+        if (S->comm->recv_counter) cudaFree(S->comm->recv_counter);
+        delete S->comm;
+    }
+    S->own.release();
     if (S->h_iter) cudaFreeHost(S->h_iter);
     if (S->h_step) cudaFreeHost(S->h_step);
     if (S->ev0) cudaEventDestroy(S->ev0);
@@ -2199,11 +2479,93 @@ void cathy_destroy(CathySim *S)
     delete S;
 }
 
+
+// CUDA loads kernels lazily at their first launch, and a load may wait for running kernels to drain -- fatal when a running
+// kernel is itself waiting for a peer whose next kernel still has to be loaded (partitioned runs).  Touch every kernel once.
+static int preload_kernels()
+{
+    static bool done = false;
+    if (done) return 0;
+    cudaFuncAttributes at;
+    const void *fns[] = {(const void *)k_curves, (const void *)k_chvelo, (const void *)k_tet_avg, (const void *)k_assemble, (const void *)k_rhs_lhs,
+                         (const void *)k_scale, (const void *)k_spmv, (const void *)k_dd_send, (const void *)k_dd_recv, (const void *)k_dd_combine_iter,
+                         (const void *)k_dd_combine_step, (const void *)k_pcg<1024, true, true>, (const void *)k_pcg<1024, true, false>,
+                         (const void *)k_pcg<1024, false, false>, (const void *)k_pcg<512, true, false>, (const void *)k_pcg<512, false, false>,
+                         (const void *)k_pcg<256, true, false>, (const void *)k_pcg<256, false, false>, (const void *)k_curves_newton,
+                         (const void *)k_sw_pair, (const void *)k_tet_newton, (const void *)k_assemble_newton, (const void *)k_rhs_lhs_newton,
+                         (const void *)k_bkflux_n, (const void *)k_bkflux_list_n, (const void *)k_bicgstab<1024>, (const void *)k_update,
+                         (const void *)k_bkflux, (const void *)k_bkflux_list, (const void *)k_mark_nonatm, (const void *)k_flux_sums,
+                         (const void *)k_free_drain_list, (const void *)k_norms, (const void *)k_norms_final, (const void *)k_switch,
+                         (const void *)k_switch_old, (const void *)k_adrstn, (const void *)k_pondupd, (const void *)k_atm_interp, (const void *)k_etran,
+                         (const void *)k_div_area, (const void *)k_nod_cell, (const void *)k_cell_nod, (const void *)k_route, (const void *)k_pond_zero,
+                         (const void *)k_step_partial, (const void *)k_step_final, (const void *)k_weight, (const void *)k_atmone, (const void *)k_mbinit,
+                         (const void *)k_pack_col, (const void *)k_unpack_col};
+    for (const void *f : fns) CK(cudaFuncGetAttributes(&at, f));
+    done = true;
+    return 0;
+}
+
 static int create_impl(const CathyProblem *prob, CathySim *S)
 {
     S->p = *prob;
     S->p.atm_time = nullptr;   // re-pointed below at an owned copy (cathy_destroy frees it)
     CathyProblem &p = S->p;
+    std::vector<double> w_dem, w_root, w_ic, w_atm;   // window copies (row-block partition)
+    std::vector<int32_t> w_zone;
+    if (prob->dd_world > 1) {
+        // ---- row-block partition: cut this rank's window out of the GLOBAL rasters ----
+        const int gnrow = prob->nrow, ncol = prob->ncol, nc1 = ncol + 1, W = DD_W;
+        if (prob->dd_world > DD_MAXW) FAIL(-2, "dd_world = %d > %d", prob->dd_world, DD_MAXW);
+        if (prob->dd_rank < 0 || prob->dd_rank >= prob->dd_world || prob->dd_row0 < 0 || prob->dd_row1 > gnrow + 1 || prob->dd_row1 - prob->dd_row0 < W)
+            FAIL(-2, "bad row-block partition: rank %d of %d owns node rows [%d,%d) of %d (each rank needs >= %d rows)", prob->dd_rank, prob->dd_world,
+                 prob->dd_row0, prob->dd_row1, gnrow + 1, W);
+        if (prob->isimgr != 1) FAIL(-2, "row-block partition: surface routing (ISIMGR=2) is not partitioned yet");
+        if (prob->iopt != 1) FAIL(-2, "row-block partition: Picard scheme only");
+        if ((prob->ndir_rec > 0 && prob->dir_ptr[prob->ndir_rec] > 0) || (prob->nneu_rec > 0 && prob->neu_ptr[prob->nneu_rec] > 0))
+            FAIL(-2, "row-block partition: nansfdirbc / nansfneubc records are not partitioned yet");
+        const int lo = std::max(0, prob->dd_row0 - W), hi = std::min(gnrow + 1, prob->dd_row1 + W);   // node rows [lo, hi)
+        const int lrow = hi - lo - 1;                                                                    // local cell rows [lo, hi-1)
+        S->dd = true; S->dd_world = prob->dd_world; S->dd_rank = prob->dd_rank; S->gnrow = gnrow; S->grow0 = lo;
+        S->own_a = prob->dd_row0 - lo; S->own_b = prob->dd_row1 - lo; S->gnnod = (gnrow + 1) * nc1;
+        // global surface elevations / vegetation classes exactly as the unpartitioned build forms them (same summation order)
+        std::vector<double> gz((size_t)S->gnnod, 0.0), gv((size_t)S->gnnod, 0.0);
+        std::vector<int> gc((size_t)S->gnnod, 0);
+        for (int i = 0; i < gnrow; ++i)
+            for (int j = 0; j < ncol; ++j) {
+                int n00 = i * nc1 + j, n10 = n00 + nc1, n11 = n10 + 1, n01 = n00 + 1;
+                double e = prob->dem[(size_t)i * ncol + j] * prob->factor, r = prob->root_map[(size_t)i * ncol + j] * prob->factor;
+                int t1[3] = {n00, n10, n11}, t2[3] = {n00, n11, n01};
+                for (int q = 0; q < 3; ++q) { gz[t1[q]] += e; gv[t1[q]] += r; gc[t1[q]]++; }
+                for (int q = 0; q < 3; ++q) { gz[t2[q]] += e; gv[t2[q]] += r; gc[t2[q]]++; }
+            }
+        double zmin = RMAX_;
+        for (int k = 0; k < S->gnnod; ++k) { gz[k] /= gc[k]; zmin = std::min(zmin, gz[k]); }
+        S->ovr_zmin = zmin;
+        const int lnnod = (lrow + 1) * nc1;
+        S->ovr_z.assign(gz.begin() + (size_t)lo * nc1, gz.begin() + (size_t)lo * nc1 + lnnod);
+        S->ovr_veg.resize(lnnod);
+        for (int k = 0; k < lnnod; ++k) { int v = (int)(gv[(size_t)lo * nc1 + k] / gc[(size_t)lo * nc1 + k]); S->ovr_veg[k] = std::min(std::max(v, 1), prob->nveg) - 1; }
+        w_dem.assign(prob->dem + (size_t)lo * ncol, prob->dem + (size_t)(lo + lrow) * ncol);
+        w_zone.assign(prob->zone + (size_t)lo * ncol, prob->zone + (size_t)(lo + lrow) * ncol);
+        w_root.assign(prob->root_map + (size_t)lo * ncol, prob->root_map + (size_t)(lo + lrow) * ncol);
+        p.dem = w_dem.data(); p.zone = w_zone.data(); p.root_map = w_root.data();
+        const long long gN = (long long)S->gnnod * (prob->nstr + 1);
+        (void)gN;
+        if ((prob->indp == 0 || prob->indp == 1) && prob->ic_psi) {
+            w_ic.resize((size_t)lnnod * (prob->nstr + 1));
+            for (int l = 0; l <= prob->nstr; ++l)
+                for (int k = 0; k < lnnod; ++k) w_ic[(size_t)l * lnnod + k] = prob->ic_psi[(size_t)l * S->gnnod + (size_t)lo * nc1 + k];
+            p.ic_psi = w_ic.data();
+        }
+        if (prob->ipond != 0) FAIL(-2, "row-block partition: IPOND != 0 is not partitioned yet");
+        if (prob->hspatm == 0 && prob->natm > 0) {
+            w_atm.resize((size_t)prob->natm * lnnod);
+            for (int r = 0; r < prob->natm; ++r)
+                for (int k = 0; k < lnnod; ++k) w_atm[(size_t)r * lnnod + k] = prob->atm_val[(size_t)r * S->gnnod + (size_t)lo * nc1 + k];
+            p.atm_val = w_atm.data();
+        }
+        p.nrow = lrow;
+    }
     S->nrow = p.nrow; S->ncol = p.ncol; S->nc1 = p.ncol + 1; S->nstr = p.nstr;
     long long nnod = (long long)(p.nrow + 1) * (p.ncol + 1), n = nnod * (p.nstr + 1), nt = 6LL * p.nrow * p.ncol * p.nstr;
     if (n > 2000000000LL || nt * 10 > 2147000000LL) FAIL(-2, "mesh too large for 32-bit indexing in this build (N=%lld, NT=%lld)", n, nt);
@@ -2217,8 +2579,8 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
     }
     {
         size_t nc = (size_t)p.nrow * p.ncol;
-        S->h_dem.assign(prob->dem, prob->dem + nc); S->h_zone.assign(prob->zone, prob->zone + nc);
-        S->h_root.assign(prob->root_map, prob->root_map + nc); S->h_zratio.assign(prob->zratio, prob->zratio + p.nstr);
+        S->h_dem.assign(p.dem, p.dem + nc); S->h_zone.assign(p.zone, p.zone + nc);      // p.*: the window when partitioned
+        S->h_root.assign(p.root_map, p.root_map + nc); S->h_zratio.assign(prob->zratio, prob->zratio + p.nstr);
         const double *vp[6] = {prob->pcana, prob->pcref, prob->pcwlt, prob->zroot, prob->pz, prob->omgc};
         S->h_veg.resize((size_t)6 * p.nveg);
         for (int q = 0; q < 6; ++q) for (int v = 0; v < p.nveg; ++v) S->h_veg[(size_t)q * p.nveg + v] = vp[q][v];
@@ -2230,12 +2592,14 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
     CK(cudaGetDeviceProperties(&prop, p.device));
     S->sms = prop.multiProcessorCount;
     if (!prop.cooperativeLaunch) FAIL(-102, "device does not support cooperative launches");
+    { int rcp = preload_kernels(); if (rcp) return rcp; }
     CK(cudaStreamCreateWithFlags(&S->st, cudaStreamNonBlocking));
     CK(cudaEventCreate(&S->ev0)); CK(cudaEventCreate(&S->ev1)); CK(cudaEventCreate(&S->evp0)); CK(cudaEventCreate(&S->evp1));
     if (const char *e = getenv("CATHY_PCG_BLOCK")) S->pcg_block = atoi(e);
     if (const char *e = getenv("CATHY_PCG_CUSTOM_BARRIER")) S->pcg_custom = atoi(e);
     if (S->pcg_block != 256 && S->pcg_block != 512 && S->pcg_block != 1024) FAIL(-2, "CATHY_PCG_BLOCK must be 256, 512 or 1024");
     S->grid_pcg = S->sms * (1024 / S->pcg_block);   // one full SM worth of threads per SM, persistent
+    if (const char *e = getenv("CATHY_PCG_GRID")) { int g = atoi(e); if (g >= 1 && g <= S->grid_pcg) { S->grid_pcg = g; S->pcg_shared_gpu = true; } }   // several handles sharing one GPU
     if (S->d_counter.alloc(1)) FAIL(-101, "barrier counter allocation failed");
     S->grid_n = S->sms * 8;                      // grid-stride kernels: a multiple of the SM count
     // the device PCG is diagonally preconditioned: it needs more (cheaper) iterations than IC(0), so the
@@ -2286,17 +2650,48 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
         a |= S->qlist.alloc(N); a |= S->qpnew.alloc(N); a |= S->qpold.alloc(N); a |= S->contp_list.alloc(N); a |= S->bcsum.alloc(4);
     }
     if (a) FAIL(-101, "device allocation failed (N=%d): %s", N, cudaGetErrorString(cudaGetLastError()));
+    if (S->dd) {
+        std::vector<unsigned char> own((size_t)N, 0);
+        for (int l = 0; l <= S->nstr; ++l)
+            for (int r = S->own_a; r < S->own_b; ++r)
+                for (int j = 0; j < S->nc1; ++j) {
+                    unsigned char f = 1;
+                    if (r < S->own_a + DD_W) f |= 2;
+                    if (r >= S->own_b - DD_W) f |= 4;
+                    own[(size_t)l * NN + (size_t)r * S->nc1 + j] = f;
+                }
+        if (S->own.upload(own)) FAIL(-101, "owned-row mask upload failed");
+        DDComm *c = new DDComm();
+        S->comm = c;
+        const long long hcap = (long long)DD_W * (S->nstr + 1) * S->nc1;
+        c->bytes = sizeof(DDBox) + (size_t)4 * hcap * sizeof(double);
+        CK(cudaMalloc(&c->base, c->bytes));
+        CK(cudaMemset(c->base, 0, c->bytes));
+        CK(cudaMalloc((void **)&c->seq, 2 * sizeof(unsigned int))); CK(cudaMemset(c->seq, 0, 2 * sizeof(unsigned int)));
+        CK(cudaMalloc((void **)&c->err, sizeof(int))); CK(cudaMemset(c->err, 0, sizeof(int)));
+        CK(cudaMalloc((void **)&c->recv_counter, sizeof(unsigned int))); CK(cudaMemset(c->recv_counter, 0, sizeof(unsigned int)));
+        CK(cudaIpcGetMemHandle(&c->handle, c->base));
+        DDCtx &x = c->ctx;
+        x.world = S->dd_world; x.rank = S->dd_rank;
+        x.north = S->dd_rank > 0 ? S->dd_rank - 1 : -1; x.south = S->dd_rank + 1 < S->dd_world ? S->dd_rank + 1 : -1;
+        x.me = (DDBox *)c->base; x.inbox_me = (double *)((char *)c->base + sizeof(DDBox));
+        for (int r = 0; r < DD_MAXW; ++r) { x.peer[r] = nullptr; x.inbox_peer[r] = nullptr; }
+        x.peer[x.rank] = x.me; x.inbox_peer[x.rank] = x.inbox_me;
+        x.hcap = hcap; x.nc1 = S->nc1; x.nlay = S->nstr + 1; x.nnod = NN; x.own_a = S->own_a; x.own_b = S->own_b;
+        x.seq = c->seq; x.err = c->err;
+        CK(cudaDeviceSynchronize());
+    }
     CK(cudaMallocHost((void **)&S->h_iter, sizeof(IterOut)));
     CK(cudaMallocHost((void **)&S->h_step, sizeof(StepOut)));
     {
         size_t cnt = (size_t)p.natm * (p.hspatm ? 1 : NN);
-        std::vector<double> tab(prob->atm_val, prob->atm_val + cnt);
+        std::vector<double> tab(p.atm_val, p.atm_val + cnt);
         if (S->atmtab.upload(tab)) FAIL(-101, "atmbc table upload failed");
     }
     if (S->surf) { rc = build_surface(S); if (rc) return rc; }
     // ---- initial conditions (SRC/datin.f:380-403, SRC/icvhe.f, icvhwt.f, icvdwt.f) on the host, then upload
     std::vector<double> pt(N, 0.0), pond(NN, 0.0);
-    if (p.indp == 0 || p.indp == 1) for (int k = 0; k < N; ++k) pt[k] = prob->ic_psi[k];
+    if (p.indp == 0 || p.indp == 1) for (int k = 0; k < N; ++k) pt[k] = p.ic_psi[k];
     if (p.ipond != 0 && prob->ic_pond) for (int k = 0; k < NN; ++k) { pond[k] = prob->ic_pond[k]; if (pond[k] > 0.0) pt[k] = pond[k]; }
     const double *Z = S->hz.data();
     double mult = p.ipond == 0 ? 0.0 : 1.0;
@@ -2362,12 +2757,13 @@ static int init_atm_and_storage(CathySim *S)
                S->ptimep.p, S->ifatm.p, S->ifatmp.p);
     }
     weight_and_copy(S);
-    LAUNCH(S, k_mbinit, 1, RED_BLOCK, NN, S->ifatmp.p, S->atmold.p, S->scal3.p);
+    LAUNCH(S, k_mbinit, 1, RED_BLOCK, NN, S->ifatmp.p, S->atmold.p, S->scal3.p, S->dd ? S->own.p : (const unsigned char *)nullptr);
     double h3[3];
-    CK(cudaMemcpyAsync(h3, S->scal3.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, S->st));
     chvelo_launch(S, S->ptimep.p);
-    int rc = step_final_sync(S);
+    int rc = step_final_sync(S, S->scal3.p);      // partitioned: the three MBINIT sums are combined across ranks with the step scalars
     if (rc) return rc;
+    CK(cudaMemcpyAsync(h3, S->scal3.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
     S->aactp = h3[0]; S->aninp = h3[1]; S->anoutp = h3[2];
     S->adinp = S->adoutp = S->ndinp = S->ndoutp = S->nninp = S->nnoutp = 0.0;
     if (S->have_neu) {   // MBINIT's NNINP/NNOUTP, after the initial NEUMANN call for free drainage (SRC/cathy_main.f:2691-2708)
@@ -2400,7 +2796,7 @@ int32_t cathy_create(const CathyProblem *prob, CathySim **out)
     if (prob->ituns > CATHY_MAXIT) FAIL(-2, "ITUNS larger than %d", CATHY_MAXIT);
     CathySim *S = new CathySim();
     int rc = create_impl(prob, S);
-    if (rc == 0) rc = init_atm_and_storage(S);
+    if (rc == 0 && !S->dd) rc = init_atm_and_storage(S);   // partitioned handles finish their set-up in cathy_dd_connect (needs the peers)
     if (rc) { std::string keep = g_err; cathy_destroy(S); snprintf(g_err, sizeof g_err, "%s", keep.c_str()); return rc; }
     // the caller's arrays are not referenced after this point, except the copied atm_time
     *out = S;
@@ -2472,6 +2868,7 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
 {
     const CathyProblem &p = S->p;
     if (S->finished) FAIL(-1, "simulation already finished");
+    if (S->dd && !S->comm->connected) FAIL(-1, "row-block partition: call cathy_dd_connect on every rank before stepping");
     CK(cudaSetDevice(p.device));
     memset(rep, 0, sizeof *rep);
     int64_t l0 = S->launches, pi0 = S->pcg_iters, ps0 = S->pcg_solves;
@@ -2524,8 +2921,9 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
     // end-of-step copies (SRC/cathy_main.f:3762-3790) are queued before the single synchronisation of the step
     {
         int nbs = nblk(NN, S->grid_n);
-        LAUNCH(S, k_step_partial, nbs, RED_BLOCK, NN, S->nstr, p.pmin, p.pondh_min, S->ifatm.p, S->atmpot.p, S->atmact.p, S->pnew.p, S->spart.p);
+        LAUNCH(S, k_step_partial, nbs, RED_BLOCK, NN, S->nstr, p.pmin, p.pondh_min, S->ifatm.p, S->atmpot.p, S->atmact.p, S->pnew.p, S->spart.p, S->dd ? S->own.p : (const unsigned char *)nullptr);
         LAUNCH(S, k_step_final, 1, RED_BLOCK, nbs, S->spart.p, S->grid_n, S->store_part.p, S->d_step.p);
+        if (S->dd) LAUNCH(S, k_dd_combine_step, 1, 32, S->comm->ctx, S->d_step.p, (double *)nullptr);
     }
     CK(cudaMemcpyAsync(S->h_step, S->d_step.p, sizeof(StepOut), cudaMemcpyDeviceToHost, S->st));
     CK(cudaMemcpyAsync(S->ifatmp.p, S->ifatm.p, (size_t)NN * sizeof(int), cudaMemcpyDeviceToDevice, S->st));
@@ -2559,7 +2957,8 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
     rep->ndin = S->ndin; rep->ndout = S->ndout; rep->nnin = S->nnin; rep->nnout = S->nnout;
     rep->vndin = S->vndin; rep->vndout = S->vndout; rep->vnnin = S->vnnin; rep->vnnout = S->vnnout;
     rep->apot = so.apot; rep->aact = so.aact; rep->ovflow = so.ovflow; rep->reflow = so.reflow;
-    rep->fhort = (double)so.nhort / NN; rep->fdunn = (double)so.ndunn / NN; rep->fpond = (double)so.npond / NN; rep->fsat = (double)so.nsat / NN;
+    const double NNg = S->dd ? (double)S->gnnod : (double)NN;
+    rep->fhort = (double)so.nhort / NNg; rep->fdunn = (double)so.ndunn / NNg; rep->fpond = (double)so.npond / NNg; rep->fsat = (double)so.nsat / NNg;
     rep->n_iter_rec = std::min(S->iter, CATHY_MAXIT);
     memcpy(rep->it, S->itrec, sizeof(CathyIterRecord) * rep->n_iter_rec);
     rep->klsfai_total = S->klsfai; rep->kback_total = S->kback;
@@ -2664,6 +3063,69 @@ int32_t cathy_set_atm_table(CathySim *S, int32_t natm, const double *times, cons
     size_t cnt = (size_t)natm * (S->p.hspatm ? 1 : S->nnod);
     std::vector<double> tab(vals, vals + cnt);
     if (S->atmtab.upload(tab)) FAIL(-101, "atmbc table upload failed");
+    return 0;
+}
+
+// ---- row-block partition: peer-memory wiring -------------------------------------------------
+int32_t cathy_dd_export(CathySim *S, void *handle64)
+{
+    if (!S->dd) FAIL(-1, "cathy_dd_export: the handle is not partitioned (dd_world = 1)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    memcpy(handle64, &S->comm->handle, 64);
+    return 0;
+}
+int32_t cathy_dd_connect(CathySim *S, const void *handles)
+{
+    if (!S->dd) FAIL(-1, "cathy_dd_connect: the handle is not partitioned (dd_world = 1)");
+    CK(cudaSetDevice(S->p.device));
+    DDComm *c = S->comm;
+    for (int r = 0; r < S->dd_world; ++r) {
+        if (r == S->dd_rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + (size_t)64 * r, 64);
+        void *ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_base[r] = ptr; c->opened[r] = true;
+        c->ctx.peer[r] = (DDBox *)ptr;
+        c->ctx.inbox_peer[r] = (double *)((char *)ptr + sizeof(DDBox));
+    }
+    c->connected = true;
+    return init_atm_and_storage(S);      // collective: ATMONE / MBINIT / initial storage sums are combined across the ranks
+}
+// Same-process variant (all ranks are handles of ONE process, e.g. one host thread per GPU): direct pointers, no IPC.
+int32_t cathy_dd_connect_local(CathySim *S, CathySim *const *all)
+{
+    if (!S->dd) FAIL(-1, "cathy_dd_connect_local: the handle is not partitioned (dd_world = 1)");
+    CK(cudaSetDevice(S->p.device));
+    DDComm *c = S->comm;
+    for (int r = 0; r < S->dd_world; ++r) {
+        if (r == S->dd_rank) continue;
+        CathySim *o = all[r];
+        if (!o || !o->dd || o->dd_rank != r || o->dd_world != S->dd_world) FAIL(-1, "cathy_dd_connect_local: handle %d is not rank %d of this partition", r, r);
+        if (o->p.device != S->p.device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->p.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) FAIL(-100, "peer access %d -> %d: %s", S->p.device, o->p.device, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        c->ctx.peer[r] = (DDBox *)o->comm->base;
+        c->ctx.inbox_peer[r] = (double *)((char *)o->comm->base + sizeof(DDBox));
+    }
+    c->connected = true;
+    return 0;
+}
+// second half of the local connection: the collective part of the set-up, to be called concurrently (one thread per handle)
+int32_t cathy_dd_start(CathySim *S)
+{
+    if (!S->dd || !S->comm->connected) FAIL(-1, "cathy_dd_start: connect first");
+    CK(cudaSetDevice(S->p.device));
+    return init_atm_and_storage(S);
+}
+int32_t cathy_dd_info(const CathySim *S, int64_t info[8])
+{
+    info[0] = S->grow0; info[1] = S->nrow + 1; info[2] = S->grow0 + S->own_a; info[3] = S->grow0 + S->own_b;
+    info[4] = S->nnod; info[5] = S->n;
+    info[6] = S->dd ? S->gnnod : S->nnod; info[7] = S->dd ? (int64_t)S->gnnod * (S->nstr + 1) : S->n;
+    if (!S->dd) { info[2] = 0; info[3] = S->nrow + 1; }
     return 0;
 }
 
