@@ -335,6 +335,89 @@ def run_enkf(args, size):
         dist.destroy_process_group()
 
 
+def run_partitioned(args, size):
+    """BASELINE config 5: ONE mesh, row-block partitioned over the ranks (strips of DEM rows), Picard + PCG with halo rows and
+    reduction scalars exchanged through peer memory over NVLink inside the solver kernel.  Strong scaling: the mesh is fixed."""
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    from pycathy_wrapper_b200.capi import Simulation, load_library
+    from pycathy_wrapper_b200.partition import PartitionedSimulation
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("CATHY_NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+    lib = load_library()
+    nrow, ncol, nstr = size
+    d = tempfile.mkdtemp(prefix="cathy_part_")
+    synthetic.make_project(d, nrow, ncol, nstr, ic=("wt", 1.0), ISIMGR=1, DELTAT=1.0, DTMIN=1e-2, DTMAX=100.0, TMAX=600.0, TIMPRT=[600.0],
+                           NODVP=[1], atmbc=[(0.0, 0.0), (60.0, 2.0e-5), (1.0e9, 2.0e-5)])
+    prj = load_project(d)
+    shutil.rmtree(d, ignore_errors=True)
+    t_build = time.perf_counter()
+    sim = PartitionedSimulation(lib, prj, device=local) if world > 1 else Simulation(lib, prj, device=local)
+    t_build = time.perf_counter() - t_build
+    n_global = sim.n_global if world > 1 else sim.n
+    n_local = sim.sim.n if world > 1 else sim.n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def rmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        sim.step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    gpu_ms = pcg_ms = 0.0
+    pcg_iters = pcg_solves = launches = nl = 0
+    for _ in range(args.steps):
+        rep = sim.step()
+        gpu_ms += rep.gpu_ms; pcg_ms += rep.pcg_ms; pcg_iters += rep.pcg_iters; pcg_solves += rep.pcg_solves; launches += rep.launches; nl += rep.iter
+    barrier()
+    wall = rmax(time.perf_counter() - t0)
+    sampler.stop_flag = True
+    peak, peak_src = measured_peaks()
+    pcg_bytes = (pcg_iters * PCG_BYTES_PER_ROW_ITER + pcg_solves * PCG_BYTES_PER_ROW_SETUP) * n_local
+    achieved = pcg_bytes / (pcg_ms / 1e3) / 1e9 if pcg_ms > 0 else None
+    halo = 2 * 2 * (nstr + 1) * (ncol + 1) * 8 if world > 1 else 0          # bytes stored into the neighbours per PCG iteration (interior rank)
+    out = {"metric": "node-timesteps/s", "value": n_global * args.steps / wall, "unit": "node-timesteps/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "ONE synthetic %dx%d DEM x %d layers mesh (%d nodes), Picard+PCG, infiltration pulse; row-block partitioned into %d strip(s) of DEM rows, "
+                                  "halo exchange + all-reduce through peer memory inside the PCG kernel" % (ncol, nrow, nstr, n_global, world),
+                      "parallelism": "row-block x%d" % world, "nodes_per_rank": n_local, "nonlinear_its": nl, "pcg_iters": pcg_iters, "pcg_solves": pcg_solves,
+                      "halo_bytes_per_pcg_iteration": halo},
+           "device_ms_per_step": 1e3 * rmax(gpu_ms / 1e3) / args.steps, "pcg_us_per_iteration": 1e3 * pcg_ms / max(pcg_iters, 1),
+           "gpu_launches": launches, "setup_s_per_rank": t_build, "clocks": sampler.summary(),
+           "roofline": {"bound": "hbm", "kernel": "k_pcg (persistent PCG, per rank)", "achieved": achieved, "peak": peak, "peak_source": peak_src,
+                        "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None}}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def cpu_baseline(size, budget_s: float = 25.0, max_steps: int = 1000):
     """The CPU oracle (a C port of the reference's algorithm; the reference ELFs cannot hold this mesh)
     timed on a bounded sample of the same workload: the first accepted step(s), single thread."""
@@ -400,17 +483,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", default=None)
-    ap.add_argument("--workload", default="picard", choices=["picard", "enkf"], help="picard: BASELINE config 2 (headline); enkf: config 4")
+    ap.add_argument("--workload", default="picard", choices=["picard", "enkf", "partitioned"], help="picard: BASELINE config 2 (headline); enkf: config 4; partitioned: config 5")
     ap.add_argument("--members", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.size is None:
-        args.size = "200x200x20" if args.workload == "picard" else "100x100x15"
+        args.size = {"picard": "200x200x20", "enkf": "100x100x15", "partitioned": "1000x1000x30"}[args.workload]
     size = tuple(int(v) for v in args.size.lower().split("x"))
     if args.workload == "enkf" and args.impl == "ours":
         return run_enkf(args, size)
+    if args.workload == "partitioned" and args.impl == "ours":
+        return run_partitioned(args, size)
     if args.impl == "reference":
         run_reference(args, size)
     else:
