@@ -260,7 +260,7 @@ def run_enkf(args, size):
         prjs.append(load_project(d))
         shutil.rmtree(d, ignore_errors=True)
     t_build = time.perf_counter()
-    ens = da.Ensemble(lib, prjs, device=local)
+    ens = da.Ensemble(lib, prjs, device=local, concurrent=args.concurrent)
     t_build = time.perf_counter() - t_build
     n, nnod = ens.n, prjs[0].nnod
     m = 64
@@ -325,7 +325,7 @@ def run_enkf(args, size):
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": "EnKF DA, %d members on a %dx%d DEM x %d layers (%d nodes), %d SWC observations, window %.0f s; a step = "
                                   "one forecast window of every member + one analysis (NCCL all-gather / all-reduce when sharded)" % (ne, ncol, nrow, nstr, n, m, window),
-                      "parallelism": "members round-robin over %d GPU(s)" % world, "member_steps_per_cycle": steps_all / args.steps},
+                      "parallelism": "members round-robin over %d GPU(s), %d concurrent per GPU" % (world, args.concurrent), "member_steps_per_cycle": steps_all / args.steps},
            "node_member_steps_per_s": steps_all * n / wall, "analysis_ms_per_cycle": rmax(ana_ms / args.steps),
            "setup_s_per_rank": t_build, "failed_member_windows": rsum(float(failed_total[0])), "clocks": sampler.summary()}
     if rank == 0:
@@ -485,6 +485,7 @@ def main():
     ap.add_argument("--size", default=None)
     ap.add_argument("--workload", default="picard", choices=["picard", "enkf", "partitioned"], help="picard: BASELINE config 2 (headline); enkf: config 4; partitioned: config 5")
     ap.add_argument("--members", type=int, default=256)
+    ap.add_argument("--concurrent", type=int, default=4, help="enkf workload: ensemble members advancing concurrently per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     args = ap.parse_args()

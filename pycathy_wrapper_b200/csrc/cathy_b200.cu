@@ -467,6 +467,7 @@ struct PcgArgs {
     unsigned int *counter;   // grid barrier counter (monotonic)
     unsigned int epoch0;     // its value at launch
     IterOut *out;
+    int prefetch;               // 1: software prefetch of the next grid-stride row into L2
     const unsigned char *own;   // row-block partition: bit0 = owned row, bit1 / bit2 = row is sent to the north / south neighbour
     DDCtx dd;
 };
@@ -515,9 +516,11 @@ __device__ __forceinline__ void grid_reduce3(cg::grid_group &grid, unsigned int 
     __syncthreads();
 }
 
-template <int BLOCK, bool CUSTOM, bool DD>
-__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_pcg(PcgArgs a)
+__device__ __forceinline__ void l2_prefetch(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <int BLOCK, bool CUSTOM, bool DD, int MINB = 1024 / BLOCK>
+__global__ void __launch_bounds__(BLOCK, MINB) k_pcg(PcgArgs a)
 {
+    const bool PF = a.prefetch != 0;
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[BLOCK / 32][3];
     __shared__ double shdd[4];
@@ -569,6 +572,12 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_pcg(PcgArgs a)
             const double *z = a.z;      // NOT __restrict__/read-only: rewritten every iteration by other SMs
             const double *po = pold;
             for (int k = t0; k < n; k += stride) {
+                if (PF && k + stride < n) {   // pull the next row's DRAM-bound streams into L2 while this row's FMA chain runs
+                    const int kn = k + stride;
+#pragma unroll
+                    for (int d = 1; d < NDIAG; ++d) l2_prefetch(&a.A.d[d][kn]);
+                    l2_prefetch(&dg[kn]); l2_prefetch(&z[kn]); l2_prefetch(&po[kn]); l2_prefetch(&a.r[kn]);
+                }
                 double pk = z[k] + beta * po[k];
                 double acc = dg[k] * pk;
 #pragma unroll
@@ -595,6 +604,10 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_pcg(PcgArgs a)
         const int hpar = (seq_h + 1u) & 1u;
         bool sent = false;
         for (int k = t0; k < n; k += stride) {
+            if (PF && k + stride < n) {
+                const int kn = k + stride;
+                l2_prefetch(&a.bv[kn]); l2_prefetch(&a.r[kn]); l2_prefetch(&a.x[kn]); l2_prefetch(&pnew[kn]); l2_prefetch(&dg[kn]);
+            }
             double bk = a.bv[k];
             double r = a.r[k] - alfa * bk;
             a.r[k] = r;
@@ -1623,7 +1636,7 @@ struct CathySim {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr;
     double pcg_ms = 0;
     int64_t pcg_iters = 0, pcg_solves = 0;
-    int sms = 148, grid_n = 0, grid_pcg = 0, pcg_block = 1024, pcg_custom = 1;
+    int sms = 148, grid_n = 0, grid_pcg = 0, pcg_block = 1024, pcg_custom = 1, pcg_minb = 0, pcg_prefetch = 1;
     unsigned int barrier_epoch = 0;
     DBuf<unsigned int> d_counter;
     int64_t launches = 0;
@@ -2208,12 +2221,18 @@ static int solve_system(CathySim *S)
     case 512: fn = cu ? (void *)k_pcg<512, true, false> : (void *)k_pcg<512, false, false>; break;
     default: fn = cu ? (void *)k_pcg<1024, true, false> : (void *)k_pcg<1024, false, false>; break;
     }
+    if (S->pcg_minb == 1 && S->pcg_block == 512) fn = (void *)k_pcg<512, true, false, 1>;      // 128 registers/thread: all stencil loads in flight
+    if (S->pcg_minb == 1 && S->pcg_block == 768) fn = (void *)k_pcg<768, true, false, 1>;
+    if (S->pcg_minb == 1 && S->pcg_block == 256) fn = (void *)k_pcg<256, true, false, 1>;
     a.own = nullptr;
+    a.prefetch = S->pcg_prefetch;
     if (S->dd) { fn = (void *)k_pcg<1024, true, true>; a.own = S->own.p; a.dd = S->comm->ctx; }
-    if (S->dd && S->pcg_shared_gpu) {
-        // several ranks share this GPU (tests): the driver runs cooperative launches one at a time, which would deadlock ranks that
-        // wait for each other inside the kernel.  The custom grid barrier only needs co-residency, which CATHY_PCG_GRID guarantees.
-        k_pcg<1024, true, true><<<S->grid_pcg, 1024, 0, S->st>>>(a);
+    if (S->pcg_shared_gpu) {
+        // Several handles share this GPU (partition ranks in tests, concurrent ensemble members): the driver runs cooperative
+        // launches one at a time, which would serialise members and deadlock ranks that wait for each other inside the kernel.
+        // The custom grid barrier only needs co-residency: the caller keeps (handles in flight) x CATHY_PCG_GRID <= #SMs.
+        if (S->dd) k_pcg<1024, true, true><<<S->grid_pcg, 1024, 0, S->st>>>(a);
+        else k_pcg<1024, true, false><<<S->grid_pcg, 1024, 0, S->st>>>(a);
         CK(cudaGetLastError());
     } else
     CK(cudaLaunchCooperativeKernel(fn, dim3(S->grid_pcg), dim3(S->pcg_block), args, 0, S->st));
@@ -2246,7 +2265,8 @@ static int solve_system_newton(CathySim *S)
     a.partial = S->partial.p; a.out = S->d_iter.p; a.counter = S->d_counter.p; a.epoch0 = S->barrier_epoch;
     void *args[] = {&a};
     CK(cudaEventRecord(S->evp0, S->st));
-    CK(cudaLaunchCooperativeKernel((void *)k_bicgstab<1024>, dim3(S->sms), dim3(1024), args, 0, S->st));
+    if (S->pcg_shared_gpu) { k_bicgstab<1024><<<S->grid_pcg, 1024, 0, S->st>>>(a); CK(cudaGetLastError()); }
+    else CK(cudaLaunchCooperativeKernel((void *)k_bicgstab<1024>, dim3(S->sms), dim3(1024), args, 0, S->st));
     CK(cudaEventRecord(S->evp1, S->st));
     S->launches++;
     return 0;
@@ -2597,9 +2617,16 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
     CK(cudaEventCreate(&S->ev0)); CK(cudaEventCreate(&S->ev1)); CK(cudaEventCreate(&S->evp0)); CK(cudaEventCreate(&S->evp1));
     if (const char *e = getenv("CATHY_PCG_BLOCK")) S->pcg_block = atoi(e);
     if (const char *e = getenv("CATHY_PCG_CUSTOM_BARRIER")) S->pcg_custom = atoi(e);
-    if (S->pcg_block != 256 && S->pcg_block != 512 && S->pcg_block != 1024) FAIL(-2, "CATHY_PCG_BLOCK must be 256, 512 or 1024");
+    if (const char *e = getenv("CATHY_PCG_MINB")) S->pcg_minb = atoi(e);
+    if (const char *e = getenv("CATHY_PCG_PREFETCH")) S->pcg_prefetch = atoi(e);
+    if (S->pcg_block != 256 && S->pcg_block != 512 && S->pcg_block != 1024 && !(S->pcg_block == 768 && S->pcg_minb == 1)) FAIL(-2, "CATHY_PCG_BLOCK must be 256, 512 or 1024");
     S->grid_pcg = S->sms * (1024 / S->pcg_block);   // one full SM worth of threads per SM, persistent
-    if (const char *e = getenv("CATHY_PCG_GRID")) { int g = atoi(e); if (g >= 1 && g <= S->grid_pcg) { S->grid_pcg = g; S->pcg_shared_gpu = true; } }   // several handles sharing one GPU
+    if (S->pcg_minb == 1) S->grid_pcg = S->sms;
+    if (S->dd) { S->pcg_block = 1024; S->pcg_minb = 0; S->grid_pcg = S->sms; }
+    if (const char *e = getenv("CATHY_PCG_GRID")) {   // several handles sharing one GPU
+        int g = atoi(e);
+        if (g >= 1 && g <= S->grid_pcg) { S->grid_pcg = g; S->pcg_shared_gpu = true; S->pcg_block = 1024; S->pcg_custom = 1; S->pcg_minb = 0; }
+    }
     if (S->d_counter.alloc(1)) FAIL(-101, "barrier counter allocation failed");
     S->grid_n = S->sms * 8;                      // grid-stride kernels: a multiple of the SM count
     // the device PCG is diagonally preconditioned: it needs more (cheaper) iterations than IC(0), so the

@@ -347,12 +347,27 @@ class Ensemble:
     """``members``: list of (CathyProject, soil_table) for THIS rank.  Each member is one simulation handle on ``device``;
     states stay in HBM between assimilation windows (the reference writes input/ic and re-reads output/psi as text)."""
 
-    def __init__(self, lib, projects, device: int = 0, group=None):
+    def __init__(self, lib, projects, device: int = 0, group=None, concurrent: int = 1):
+        """``concurrent`` > 1: that many members advance at the same time (one host thread each); their persistent solver
+        kernels then use #SMs // concurrent CTAs each so that all of them stay co-resident (CATHY_PCG_GRID)."""
+        import os
         import torch
         from .capi import Simulation
         self.torch = torch
         self.device, self.group = device, group
-        self.sims = [Simulation(lib, prj, device=device) for prj in projects]
+        self.concurrent = max(1, int(concurrent))
+        if self.concurrent > 1:
+            sms = torch.cuda.get_device_properties(device).multi_processor_count
+            old = os.environ.get("CATHY_PCG_GRID")
+            os.environ["CATHY_PCG_GRID"] = str(max(1, sms // self.concurrent))
+        try:
+            self.sims = [Simulation(lib, prj, device=device) for prj in projects]
+        finally:
+            if self.concurrent > 1:
+                if old is None:
+                    os.environ.pop("CATHY_PCG_GRID", None)
+                else:
+                    os.environ["CATHY_PCG_GRID"] = old
         self.n = self.sims[0].n if self.sims else 0
         self.ne_local = len(self.sims)
         dev = torch.device("cuda", device)
@@ -364,16 +379,24 @@ class Ensemble:
         """Advance every local member to the end of its current window (TMAX); returns accepted steps summed over members.
         Members whose run stopped before TMAX (no convergence at DTMIN) are listed in ``self.failed`` -- pyCATHY's
         ``rejected_ens`` (pyCATHY/DA/cathy_DA.py:1450-1491 detects them from a short mbeconv)."""
-        steps = 0
         self.failed = []
-        for j, s in enumerate(self.sims):
+
+        def run(j):
+            s, k = self.sims[j], 0
             while True:
                 rep = s.step()
-                steps += 1
+                k += 1
                 if rep.finished:
-                    if rep.noback:
-                        self.failed.append(j)
-                    break
+                    return k, bool(rep.noback)
+
+        if self.concurrent > 1 and len(self.sims) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=self.concurrent) as ex:      # ctypes releases the GIL inside cathy_step
+                res = list(ex.map(run, range(len(self.sims))))
+        else:
+            res = [run(j) for j in range(len(self.sims))]
+        steps = sum(r[0] for r in res)
+        self.failed = [j for j, r in enumerate(res) if r[1]]
         self.steps += steps
         return steps
 

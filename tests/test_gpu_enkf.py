@@ -95,14 +95,15 @@ def _member_projects(nmem):
     return prjs
 
 
-def test_ensemble_forecast_analysis_restart_matches_oracle(gpu_lib, oracle_mod):
+@pytest.mark.parametrize("concurrent", [1, 2])
+def test_ensemble_forecast_analysis_restart_matches_oracle(gpu_lib, oracle_mod, concurrent):
     """Two assimilation windows of a 4-member ensemble, device resident, against the same cycle built from the CPU oracle
     (fresh oracle runs restarted from the analysed heads with INDP=1, which is what pyCATHY does through input/ic)."""
     from oracle import enkf_oracle as o
     from pycathy_wrapper_b200 import da
     nmem = 4
     prjs = _member_projects(nmem)
-    ens = da.Ensemble(gpu_lib, prjs, device=0)
+    ens = da.Ensemble(gpu_lib, prjs, device=0, concurrent=concurrent)     # 2: two members advance at the same time on one GPU
     n = ens.n
     obs_nodes = np.array([3, 17, 40, 58 + 56])          # 0-based; three surface nodes and one in the second layer
     poro = 0.55
