@@ -649,6 +649,136 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_pcg(PcgArgs a)
 }
 
 
+
+// ------------------------------------------------------------------------------------------
+// SYMSLV, second formulation (opt-in, CATHY_PCG_ALGO=2; measured slower than k_pcg on B200 except on tiny meshes, see
+// profiles/r1_pcg_experiments.md): the system is scaled symmetrically, As = D^-1/2 A D^-1/2 (unit
+// diagonal, y = D^1/2 x), so that the Jacobi-preconditioned CG of k_pcg becomes plain CG without the z vector and without the
+// diagonal; and the recurrence is the single-reduction form of CG (Chronopoulos & Gear): with w = As r,
+//     gamma = (r,r), delta = (w,r);  beta = gamma/gamma_old;  alpha = gamma / (delta - beta*gamma/alpha_old)
+//     p = r + beta p;  s = w + beta s;  y += alpha p;  r -= alpha s;  w = As r
+// The new w needs the new r of the 14 neighbours, which every thread recomputes on the fly from the OLD r, w, s
+// (r_j - alpha (w_j + beta s_j)); r, w, s are double-buffered.  ONE grid-wide barrier per iteration (inside the reduction)
+// instead of two, 144 instead of 168 bytes per row and iteration.  Same iterates as SYMSLV/GRADDP in exact arithmetic (same
+// x0 = M^-1 b, same stopping test on the unscaled residual, Dirichlet rows excluded).
+// ------------------------------------------------------------------------------------------
+__global__ void k_sym_scale(int n, Diag A, const double *__restrict__ diag_bc, double *__restrict__ dis)
+{   // pass 1: dis = 1/sqrt(diag)
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) dis[k] = 1.0 / sqrt(diag_bc[k]);
+}
+__global__ void k_sym_scale2(int n, Diag A, const double *__restrict__ dis)
+{   // pass 2: off-diagonals in place (dis carries a halo; the entries that reach into it are structurally zero)
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const double dk = dis[k];
+#pragma unroll
+        for (int d = 1; d < NDIAG; ++d) A.d[d][k] = (A.d[d][k] * dk) * dis[k + A.off[d]];
+    }
+}
+struct Pcg2Args {
+    int n, nnod, itmax, prefetch;
+    double tol;
+    Diag A;                  // scaled off-diagonals in d[1..7]
+    const double *dis;       // 1/sqrt(diagonal with the Dirichlet penalty)
+    const double *rhs;
+    double *y, *p, *r0, *r1, *w0, *w1, *s0, *s1;
+    const int *ifatm;
+    const unsigned char *contp_flag;
+    double *partial;
+    unsigned int *counter;
+    unsigned int epoch0;
+    IterOut *out;
+};
+__device__ __forceinline__ double dia_offrow(const Diag &A, const double *x, int k)
+{   // sum over the 14 off-diagonal entries of row k (unit diagonal not included)
+    double acc = 0.0;
+#pragma unroll
+    for (int d = 1; d < NDIAG; ++d) acc += A.d[d][k] * x[k + A.off[d]];
+#pragma unroll
+    for (int d = 1; d < NDIAG; ++d) acc += A.d[d][k - A.off[d]] * x[k - A.off[d]];
+    return acc;
+}
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_pcg2(Pcg2Args a)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[BLOCK / 32][3];
+    unsigned int epoch = a.epoch0;
+    const int n = a.n, stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const double *__restrict__ dis = a.dis;
+    const bool PF = a.prefetch != 0;
+    // y0 = D^1/2 x0 = b/sqrt(d) (x0 = M^-1 b, :4686);  xlung = ||b_free||^2 (:1286-1297)
+    double xl = 0.0;
+    for (int k = t0; k < n; k += stride) {
+        double b = a.rhs[k];
+        a.y[k] = b * dis[k];
+        a.p[k] = 0.0; a.s0[k] = 0.0;
+        if (!is_dirichlet(k, a.nnod, a.ifatm, a.contp_flag)) xl += b * b;
+    }
+    double xlung, g0, d0;
+    grid_reduce3<BLOCK, true>(grid, a.counter, epoch, xl, 0.0, 0.0, a.partial, sh, xlung, g0, d0);
+    // r = b~ - As y0
+    for (int k = t0; k < n; k += stride) a.r0[k] = a.rhs[k] * dis[k] - (a.y[k] + dia_offrow(a.A, a.y, k));
+    grid_barrier(a.counter, epoch);
+    // w = As r ; gamma = (r,r) ; delta = (w,r)
+    double sg = 0.0, sd = 0.0;
+    for (int k = t0; k < n; k += stride) {
+        double r = a.r0[k], w = r + dia_offrow(a.A, a.r0, k);
+        a.w0[k] = w;
+        sg += r * r; sd += w * r;
+    }
+    double gamma, delta, rr;
+    grid_reduce3<BLOCK, true>(grid, a.counter, epoch, sg, sd, 0.0, a.partial, sh, gamma, delta, rr);
+    double alpha = gamma / delta, beta = 0.0, err = 0.0;
+    double *rc = a.r0, *rn = a.r1, *wc = a.w0, *wn = a.w1, *sc = a.s0, *sn = a.s1;
+    int niter = 1;
+    for (;;) {
+        const double ab = alpha * beta;
+        double s_g = 0.0, s_d = 0.0, s_rr = 0.0;
+        for (int k = t0; k < n; k += stride) {
+            if (PF && k + stride < n) {
+                const int kn = k + stride;
+#pragma unroll
+                for (int d = 1; d < NDIAG; ++d) l2_prefetch(&a.A.d[d][kn]);
+                l2_prefetch(&rc[kn]); l2_prefetch(&wc[kn]); l2_prefetch(&sc[kn]); l2_prefetch(&a.p[kn]); l2_prefetch(&a.y[kn]); l2_prefetch(&dis[kn]);
+            }
+            const double r = rc[k], w = wc[k], so = sc[k];
+            const double s = w + beta * so;
+            const double p = r + beta * a.p[k];
+            const double r2 = (r - alpha * w) - ab * so;      // = r - alpha s, in the very form the neighbours use below
+            double acc = r2;                                 // unit diagonal
+#pragma unroll
+            for (int d = 1; d < NDIAG; ++d) {
+                const int j = k + a.A.off[d];
+                acc += a.A.d[d][k] * ((rc[j] - alpha * wc[j]) - ab * sc[j]);
+            }
+#pragma unroll
+            for (int d = 1; d < NDIAG; ++d) {
+                const int j = k - a.A.off[d];
+                acc += a.A.d[d][j] * ((rc[j] - alpha * wc[j]) - ab * sc[j]);
+            }
+            sn[k] = s; a.p[k] = p; a.y[k] = a.y[k] + alpha * p; rn[k] = r2; wn[k] = acc;
+            s_g += r2 * r2; s_d += acc * r2;
+            if (!is_dirichlet(k, a.nnod, a.ifatm, a.contp_flag)) { double di = dis[k]; s_rr += (r2 * r2) / (di * di); }   // unscaled residual
+        }
+        double g1, d1;
+        grid_reduce3<BLOCK, true>(grid, a.counter, epoch, s_g, s_d, s_rr, a.partial, sh, g1, d1, rr);
+        err = xlung > 0.0 ? sqrt(rr / xlung) : sqrt(rr / n);
+        double *t;
+        t = rc; rc = rn; rn = t; t = wc; wc = wn; wn = t; t = sc; sc = sn; sn = t;
+        if (err > a.tol && niter < a.itmax) {
+            beta = g1 / gamma;
+            alpha = g1 / (d1 - beta * g1 / alpha);
+            gamma = g1;
+            ++niter;
+            continue;
+        }
+        break;
+    }
+    // x = D^-1/2 y
+    for (int k = t0; k < n; k += stride) a.y[k] = a.y[k] * dis[k];
+    if (t0 == 0) { a.out->pcg_niter = niter; a.out->pcg_err = err; a.out->pad = (int)epoch; }
+}
+
 // ==========================================================================================
 // Newton scheme (IOPT = 2): SRC/newton.f.  The Jacobian J = TETAF*A + M/dt + C3 is nonsymmetric with the same
 // 15-point stencil: upper part (incl. diagonal) in 8 diagonals Ju[d][k] = J(k, k+off_d), lower part in 7 diagonals
@@ -983,14 +1113,26 @@ __global__ void k_update(int n, int nnod, const double *__restrict__ pdiff, cons
 
 // back-calculated fluxes at atmospheric Dirichlet nodes (BKPIC, SRC/bkpic.f:27-53): only the rows
 // that are read afterwards are formed, i.e. one 15-point row product per Dirichlet node.
+// row product with the ORIGINAL matrix when its off-diagonals are stored symmetrically scaled (dis != nullptr, see k_pcg2)
+__device__ __forceinline__ double dia_row_orig(const Diag &A, const double *__restrict__ diag0, const double *__restrict__ dis,
+                                               const double *__restrict__ x, int k, int n)
+{
+    if (!dis) return dia_row(A, diag0, x, k, n);
+    double acc = 0.0;
+#pragma unroll
+    for (int d = 1; d < NDIAG; ++d) { int j = k + A.off[d]; double dj = dis[j]; if (dj != 0.0) acc += A.d[d][k] * (x[j] / dj); }
+#pragma unroll
+    for (int d = 1; d < NDIAG; ++d) { int j = k - A.off[d]; double dj = dis[j]; if (dj != 0.0) acc += A.d[d][j] * (x[j] / dj); }
+    return diag0[k] * x[k] + acc / dis[k];
+}
 __global__ void k_bkflux(int n, int nnod, Diag A, const double *__restrict__ diag_true, const double *__restrict__ pdiff,
                          const double *__restrict__ xt5, const int *__restrict__ ifatm, double tetaf,
-                         const double *__restrict__ atmold, double *__restrict__ atmact)
+                         const double *__restrict__ atmold, double *__restrict__ atmact, const double *__restrict__ dis)
 {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nnod; k += gridDim.x * blockDim.x) {
         int f = ifatm[k];
         if (f == 1 || f == 2) {
-            double scr = dia_row(A, diag_true, pdiff, k, n) - xt5[k];
+            double scr = dia_row_orig(A, diag_true, dis, pdiff, k, n) - xt5[k];
             atmact[k] = (scr - (1.0 - tetaf) * atmold[k]) * (1.0 / tetaf);
         }
     }
@@ -998,11 +1140,11 @@ __global__ void k_bkflux(int n, int nnod, Diag A, const double *__restrict__ dia
 // same for the prescribed-head nodes: QPNEW (SRC/bkpic.f:38-41), indexed by list position like the reference
 __global__ void k_bkflux_list(int n, int m, const int *__restrict__ list, Diag A, const double *__restrict__ diag_true,
                               const double *__restrict__ pdiff, const double *__restrict__ xt5, double tetaf,
-                              const double *__restrict__ qpold, double *__restrict__ qpnew)
+                              const double *__restrict__ qpold, double *__restrict__ qpnew, const double *__restrict__ dis)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
         int k = list[i];
-        double scr = dia_row(A, diag_true, pdiff, k, n) - xt5[k];
+        double scr = dia_row_orig(A, diag_true, dis, pdiff, k, n) - xt5[k];
         qpnew[i] = (scr - (1.0 - tetaf) * qpold[i]) * (1.0 / tetaf);
     }
 }
@@ -1665,6 +1807,9 @@ struct CathySim {
     DBuf<double> diag_true, diag_bc, grav, m2, krt, e1t;
     DBuf<double> pnew, pold, ptimep, ptnew, pdiff, sw, ckrw, ckrwp, et1, et2, swnew, swtimep, rhs, xt5, qtranie;
     DBuf<double> wr, wz, wp0, wp1, wbv, partial, store_part;
+    DBuf<double> dis, wq0, wq1;      // k_pcg2: 1/sqrt(diag), two more work vectors
+    bool scaled = false;             // off-diagonals of A currently hold the symmetrically scaled matrix
+    int pcg_algo = 1;                // 1: k_pcg (two reductions / iteration, default), 2: k_pcg2 (scaled, single reduction; CATHY_PCG_ALGO=2)
     DBuf<double> Ju, Jl, dinv, dckrw, detai, ts, s1, ws, wsh, wt;   // Newton: Jacobian diagonals, Jacobi scaling, derivative curves, element factors, BiCGSTAB vectors
     bool newton = false;
     // ---- row-block partition of one large mesh over several GPUs (BASELINE config 5) ----
@@ -2192,6 +2337,7 @@ static void dd_exchange(CathySim *S, double *vec)
 static int assemble_system(CathySim *S, double deltat)
 {
     const int n = S->n;
+    S->scaled = false;
     Diag A = make_diag(S, S->A.p);
     LAUNCH(S, k_curves, nblk(n, S->grid_n), RED_BLOCK, n, make_soil(S), S->ptnew.p, S->pnew.p, S->ptimep.p, S->timep_dirty, S->sw.p, S->ckrw.p, S->et1.p, S->et2.p, S->swnew.p, S->swtimep.p);
     S->timep_dirty = 0;
@@ -2204,8 +2350,32 @@ static int assemble_system(CathySim *S, double deltat)
         LAUNCH(S, k_scale, nblk((long long)(NDIAG - 1) * S->ld, 8 * S->grid_n), RED_BLOCK, (long long)(NDIAG - 1) * S->ld, S->tetaf, S->A.p + S->ld);
     return 0;
 }
+static int solve_system2(CathySim *S)
+{
+    const int n = S->n;
+    Diag A = make_diag(S, S->A.p);
+    if (!S->scaled) {
+        LAUNCH(S, k_sym_scale, nblk(n, S->grid_n), RED_BLOCK, n, A, S->diag_bc.p, S->dis.p);
+        LAUNCH(S, k_sym_scale2, nblk(n, S->grid_n), RED_BLOCK, n, A, S->dis.p);
+        S->scaled = true;
+    }
+    Pcg2Args a;
+    a.n = n; a.nnod = S->nnod; a.itmax = S->itmax_dev; a.prefetch = S->pcg_prefetch; a.tol = S->tol_dev;
+    a.A = A; a.dis = S->dis.p; a.rhs = S->rhs.p;
+    a.y = S->pdiff.p; a.p = S->wbv.p; a.r0 = S->wr.p; a.r1 = S->wz.p; a.w0 = S->wp0.p; a.w1 = S->wp1.p; a.s0 = S->wq0.p; a.s1 = S->wq1.p;
+    a.ifatm = S->ifatm.p; a.contp_flag = S->have_dir ? S->contp_flag.p : nullptr; a.partial = S->partial.p; a.out = S->d_iter.p;
+    a.counter = S->d_counter.p; a.epoch0 = S->barrier_epoch;
+    void *args[] = {&a};
+    CK(cudaEventRecord(S->evp0, S->st));
+    if (S->pcg_shared_gpu) { k_pcg2<1024><<<S->grid_pcg, 1024, 0, S->st>>>(a); CK(cudaGetLastError()); }
+    else CK(cudaLaunchCooperativeKernel((void *)k_pcg2<1024>, dim3(S->sms), dim3(1024), args, 0, S->st));
+    CK(cudaEventRecord(S->evp1, S->st));
+    S->launches += 1;
+    return 0;
+}
 static int solve_system(CathySim *S)
 {
+    if (!S->dd && S->pcg_algo == 2) return solve_system2(S);
     PcgArgs a;
     a.n = S->n; a.nnod = S->nnod; a.itmax = S->itmax_dev; a.tol = S->tol_dev;
     a.A = make_diag(S, S->A.p); a.diag = S->diag_bc.p; a.rhs = S->rhs.p;
@@ -2292,11 +2462,12 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
         LAUNCH(S, k_sw_pair, nblk(n, S->grid_n), RED_BLOCK, n, make_soil(S), S->pnew.p, S->ptimep.p, S->timep_dirty, S->swnew.p, S->swtimep.p);
         S->timep_dirty = 0;
     } else {
+    const double *dis = S->scaled ? S->dis.p : (const double *)nullptr;
     LAUNCH(S, k_bkflux, nblk(S->nnod, S->grid_n), RED_BLOCK, n, S->nnod, A, S->diag_true.p, S->pdiff.p, S->xt5.p, S->ifatm.p, S->tetaf,
-           S->atmold.p, S->atmact.p);
+           S->atmold.p, S->atmact.p, dis);
     if (S->have_dir) {
         int m = S->dir.anbc();
-        LAUNCH(S, k_bkflux_list, nblk(m, S->grid_n), RED_BLOCK, n, m, S->contp_list.p, A, S->diag_true.p, S->pdiff.p, S->xt5.p, S->tetaf, S->qpold.p, S->qpnew.p);
+        LAUNCH(S, k_bkflux_list, nblk(m, S->grid_n), RED_BLOCK, n, m, S->contp_list.p, A, S->diag_true.p, S->pdiff.p, S->xt5.p, S->tetaf, S->qpold.p, S->qpnew.p, dis);
         LAUNCH(S, k_flux_sums, 1, RED_BLOCK, m, S->qpnew.p, S->bcsum.p);
     }
     }
@@ -2476,6 +2647,7 @@ void cathy_destroy(CathySim *S)
     for (auto *b : di) b->release();
     { DBuf<double> *nn[] = {&S->Ju, &S->Jl, &S->dinv, &S->dckrw, &S->detai, &S->ts, &S->s1, &S->ws, &S->wsh, &S->wt, &S->tet_k0, &S->tet_gz, &S->tet_vol, &S->vgm52, &S->vgmm1};
       for (auto *b : nn) b->release(); S->ell_loc.release(); }
+    S->dis.release(); S->wq0.release(); S->wq1.release();
     S->contp_flag.release(); S->contq_flag.release(); S->contp_val.release(); S->qneu.release(); S->qlist.release(); S->qpnew.release();
     S->qpold.release(); S->kznod.release(); S->bcsum.release(); S->contp_list.release();
     S->d_counter.release(); S->tet.release(); S->don_dir.release(); S->npart.release(); S->spart.release(); S->d_iter.release(); S->d_step.release();
@@ -2509,7 +2681,7 @@ static int preload_kernels()
     cudaFuncAttributes at;
     const void *fns[] = {(const void *)k_curves, (const void *)k_chvelo, (const void *)k_tet_avg, (const void *)k_assemble, (const void *)k_rhs_lhs,
                          (const void *)k_scale, (const void *)k_spmv, (const void *)k_dd_send, (const void *)k_dd_recv, (const void *)k_dd_combine_iter,
-                         (const void *)k_dd_combine_step, (const void *)k_pcg<1024, true, true>, (const void *)k_pcg<1024, true, false>,
+                         (const void *)k_dd_combine_step, (const void *)k_pcg<1024, true, true>, (const void *)k_pcg<1024, true, false>, (const void *)k_pcg2<1024>, (const void *)k_sym_scale, (const void *)k_sym_scale2,
                          (const void *)k_pcg<1024, false, false>, (const void *)k_pcg<512, true, false>, (const void *)k_pcg<512, false, false>,
                          (const void *)k_pcg<256, true, false>, (const void *)k_pcg<256, false, false>, (const void *)k_curves_newton,
                          (const void *)k_sw_pair, (const void *)k_tet_newton, (const void *)k_assemble_newton, (const void *)k_rhs_lhs_newton,
@@ -2619,6 +2791,7 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
     if (const char *e = getenv("CATHY_PCG_CUSTOM_BARRIER")) S->pcg_custom = atoi(e);
     if (const char *e = getenv("CATHY_PCG_MINB")) S->pcg_minb = atoi(e);
     if (const char *e = getenv("CATHY_PCG_PREFETCH")) S->pcg_prefetch = atoi(e);
+    if (const char *e = getenv("CATHY_PCG_ALGO")) S->pcg_algo = atoi(e);
     if (S->pcg_block != 256 && S->pcg_block != 512 && S->pcg_block != 1024 && !(S->pcg_block == 768 && S->pcg_minb == 1)) FAIL(-2, "CATHY_PCG_BLOCK must be 256, 512 or 1024");
     S->grid_pcg = S->sms * (1024 / S->pcg_block);   // one full SM worth of threads per SM, persistent
     if (S->pcg_minb == 1) S->grid_pcg = S->sms;
@@ -2660,6 +2833,7 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
     DBuf<double> *vn[] = {&S->diag_true, &S->diag_bc, &S->grav, &S->m2, &S->pnew, &S->pold, &S->ptimep, &S->ptnew, &S->pdiff, &S->sw, &S->ckrw,
                           &S->ckrwp, &S->et1, &S->et2, &S->swnew, &S->swtimep, &S->rhs, &S->xt5, &S->qtranie, &S->wr, &S->wz, &S->wp0, &S->wp1, &S->wbv};
     for (auto *b : vn) a |= b->alloc(N, S->halo);   // halo: stencil gathers need no bounds checks
+    a |= S->dis.alloc(N, S->halo); a |= S->wq0.alloc(N, S->halo); a |= S->wq1.alloc(N, S->halo);
     a |= S->krt.alloc(S->nt); a |= S->e1t.alloc(S->nt);
     a |= S->partial.alloc(10 * (size_t)std::max(S->grid_pcg, 1));
     if (S->newton) {
