@@ -38,6 +38,14 @@ PCG_BYTES_PER_ROW_SETUP = 152.0    # x0, residual and first preconditioner appli
 SPMV_BYTES_PER_ROW = 80.0          # 8 diagonals + x + y
 
 
+def _quiet_nccl():
+    """stdout must carry the ONE JSON line only: NCCL prints its version banner there at NCCL_DEBUG=WARN/VERSION/INFO."""
+    if "CATHY_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["CATHY_NCCL_DEBUG"]
+    else:
+        os.environ.pop("NCCL_DEBUG", None)
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -103,7 +111,7 @@ def run_ours(args, size):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("CATHY_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        _quiet_nccl()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0:
         g.build()
@@ -235,7 +243,7 @@ def run_enkf(args, size):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("CATHY_NCCL_DEBUG", "WARN")
+        _quiet_nccl()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0:
         g.build()
@@ -351,7 +359,7 @@ def run_partitioned(args, size):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("CATHY_NCCL_DEBUG", "WARN")
+        _quiet_nccl()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0:
         g.build()
