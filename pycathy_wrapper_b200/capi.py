@@ -283,11 +283,27 @@ class Simulation:
             raise CathyLibraryError(f"{self.lib.prefix}step failed ({rc}): {self.lib.error()}")
         return rep
 
-    def state(self) -> dict:
+    def state_buffers(self, pinned: bool = False) -> dict:
+        """Host arrays for ``state(out=...)``; pinned (page-locked, via torch) buffers make the device-to-host copies DMA at
+        full PCIe speed and are reusable from step to step."""
         n, nn = self.n, self.nnod
+        if pinned:
+            import torch
+
+            def mk(m, dt):
+                return torch.empty(m, dtype=dt).pin_memory().numpy()
+            out = {k: mk(n, torch.float64) for k in ("psi", "sw", "ckrw", "qtranie")}
+            out.update({k: mk(nn, torch.float64) for k in ("pond", "atmact", "atmpot", "ovfl")})
+            out["ifatm"] = mk(nn, torch.int32)
+            return out
         out = {k: np.empty(n) for k in ("psi", "sw", "ckrw", "qtranie")}
         out.update({k: np.empty(nn) for k in ("pond", "atmact", "atmpot", "ovfl")})
         out["ifatm"] = np.empty(nn, dtype=np.int32)
+        return out
+
+    def state(self, out: dict | None = None) -> dict:
+        if out is None:
+            out = self.state_buffers()
         rc = self.lib.f["get_state"](self.h, _dp(out["psi"]), _dp(out["sw"]), _dp(out["ckrw"]), _dp(out["qtranie"]),
                                      _dp(out["pond"]), _dp(out["atmact"]), _dp(out["atmpot"]), _dp(out["ovfl"]),
                                      _ip(out["ifatm"]))
