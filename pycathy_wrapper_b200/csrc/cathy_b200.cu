@@ -3035,15 +3035,17 @@ int32_t cathy_get_state(CathySim *S, double *psi, double *sw, double *ckrw, doub
     CK(cudaSetDevice(S->p.device));
     CK(cudaStreamSynchronize(S->st));
     size_t bn = (size_t)S->n * sizeof(double), bs = (size_t)S->nnod * sizeof(double);
-    if (psi) CK(cudaMemcpy(psi, S->pnew.p, bn, cudaMemcpyDeviceToHost));
-    if (sw) CK(cudaMemcpy(sw, S->sw.p, bn, cudaMemcpyDeviceToHost));
-    if (ckrw) CK(cudaMemcpy(ckrw, S->ckrw.p, bn, cudaMemcpyDeviceToHost));
-    if (qtranie) CK(cudaMemcpy(qtranie, S->qtranie.p, bn, cudaMemcpyDeviceToHost));
-    if (pond) CK(cudaMemcpy(pond, S->pondnod.p, bs, cudaMemcpyDeviceToHost));
-    if (atmact) CK(cudaMemcpy(atmact, S->atmact.p, bs, cudaMemcpyDeviceToHost));
-    if (atmpot) CK(cudaMemcpy(atmpot, S->atmpot.p, bs, cudaMemcpyDeviceToHost));
-    if (ovfl) CK(cudaMemcpy(ovfl, S->ovflnod.p, bs, cudaMemcpyDeviceToHost));
-    if (ifatm) CK(cudaMemcpy(ifatm, S->ifatm.p, (size_t)S->nnod * sizeof(int), cudaMemcpyDeviceToHost));
+    // queued on the handle's stream and awaited once: with page-locked destination buffers the copies run back to back at PCIe speed
+    if (psi) CK(cudaMemcpyAsync(psi, S->pnew.p, bn, cudaMemcpyDeviceToHost, S->st));
+    if (sw) CK(cudaMemcpyAsync(sw, S->sw.p, bn, cudaMemcpyDeviceToHost, S->st));
+    if (ckrw) CK(cudaMemcpyAsync(ckrw, S->ckrw.p, bn, cudaMemcpyDeviceToHost, S->st));
+    if (qtranie) CK(cudaMemcpyAsync(qtranie, S->qtranie.p, bn, cudaMemcpyDeviceToHost, S->st));
+    if (pond) CK(cudaMemcpyAsync(pond, S->pondnod.p, bs, cudaMemcpyDeviceToHost, S->st));
+    if (atmact) CK(cudaMemcpyAsync(atmact, S->atmact.p, bs, cudaMemcpyDeviceToHost, S->st));
+    if (atmpot) CK(cudaMemcpyAsync(atmpot, S->atmpot.p, bs, cudaMemcpyDeviceToHost, S->st));
+    if (ovfl) CK(cudaMemcpyAsync(ovfl, S->ovflnod.p, bs, cudaMemcpyDeviceToHost, S->st));
+    if (ifatm) CK(cudaMemcpyAsync(ifatm, S->ifatm.p, (size_t)S->nnod * sizeof(int), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
     return 0;
 }
 int32_t cathy_set_psi(CathySim *S, const double *psi)
