@@ -156,6 +156,10 @@ int32_t cathy_step(CathySim *sim, CathyStepReport *rep);
  * Any pointer may be NULL.  psi,sw,ckrw,qtranie: [N]; pond,atmact,atmpot,ovfl: [NNOD]; ifatm [NNOD]. */
 int32_t cathy_get_state(CathySim *sim, double *psi, double *sw, double *ckrw, double *qtranie,
                         double *pond, double *atmact, double *atmpot, double *ovfl, int32_t *ifatm);
+/* Darcy velocities at the current state: VEL3D (SRC/vel3d.f) per element [NT] in the processor's element order (nodes of an
+ * element sorted ascending under Picard, SRC/grdsys.f:63) and VNOD3D (SRC/vnod3d.f) per node [N] -- what DETOUT prints to
+ * velelt / velnod and VTKRIS3D to vtk/1NN.vtk (SRC/detout.f:35, SRC/vtkris3d.f).  Any pointer may be NULL. */
+int32_t cathy_get_velocity(CathySim *sim, double *uu, double *vv, double *ww, double *unod, double *vnod, double *wnod);
 /* Overwrite the pressure-head state (DA restart; stands for pyCATHY update_ic(INDP=1) +
  * relaunch, pyCATHY/cathy_tools.py:1863-1875).  Only valid before the first step. */
 int32_t cathy_set_psi(CathySim *sim, const double *psi);

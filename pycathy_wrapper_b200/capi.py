@@ -177,7 +177,7 @@ class CathyLib:
     """Binds one shared library exporting the cathy_b200.h entry points under ``prefix``."""
 
     SYMBOLS = ["sizeof_problem", "sizeof_report", "last_error", "create", "destroy", "get_dims", "get_mesh",
-               "initial_storage", "step", "get_state", "set_psi", "upload_atm_record", "debug_assemble", "debug_spmv", "debug_solve"]
+               "initial_storage", "step", "get_state", "get_velocity", "set_psi", "upload_atm_record", "debug_assemble", "debug_spmv", "debug_solve"]
 
     # entry points only the product library has (in-process ensemble support); bound when present
     PRODUCT_ONLY = ["pack_state", "unpack_psi", "restart", "set_soil", "set_atm_table", "dd_export", "dd_connect", "dd_connect_local", "dd_start", "dd_info"]
@@ -226,6 +226,7 @@ class CathyLib:
         f["initial_storage"].restype = C.c_double
         f["step"].argtypes = [C.c_void_p, C.POINTER(CathyStepReport)]
         f["get_state"].argtypes = [C.c_void_p, _D, _D, _D, _D, _D, _D, _D, _D, _I]
+        f["get_velocity"].argtypes = [C.c_void_p, _D, _D, _D, _D, _D, _D]
         f["set_psi"].argtypes = [C.c_void_p, _D]
         f["upload_atm_record"].argtypes = [C.c_void_p, C.c_int32, _D]
         f["debug_assemble"].argtypes = [C.c_void_p, C.c_double, _I, _I, _D, _D]
@@ -309,6 +310,17 @@ class Simulation:
                                      _ip(out["ifatm"]))
         if rc != 0:
             raise CathyLibraryError(f"get_state failed ({rc}): {self.lib.error()}")
+        return out
+
+    def velocity(self, nodal: bool = True) -> dict:
+        """Darcy velocities at the current state: per element (VEL3D) and, optionally, per node (VNOD3D)."""
+        out = {k: np.empty(self.nt) for k in ("uu", "vv", "ww")}
+        if nodal:
+            out.update({k: np.empty(self.n) for k in ("unod", "vnod", "wnod")})
+        null = C.cast(None, _D)
+        self._ck(self.lib.f["get_velocity"](self.h, _dp(out["uu"]), _dp(out["vv"]), _dp(out["ww"]),
+                                            _dp(out["unod"]) if nodal else null, _dp(out["vnod"]) if nodal else null,
+                                            _dp(out["wnod"]) if nodal else null), "get_velocity")
         return out
 
     def set_psi(self, psi: np.ndarray):

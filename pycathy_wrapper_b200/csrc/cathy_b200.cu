@@ -1699,6 +1699,68 @@ __global__ void k_mbinit(int nnod, const int *__restrict__ ifatmp, const double 
     if (threadIdx.x == 0) { out3[0] = t0; out3[1] = t1; out3[2] = t2; }
 }
 
+
+// VEL3D (SRC/vel3d.f): Darcy velocity per element from the nodal heads, basis-function coefficients recomputed from the node
+// coordinates (SRC/basis6.f / volbas.f formulas, same operation order as build_static) instead of being stored per element
+__global__ void k_vel3d(int nt, int ntri, int nzone, const int4 *__restrict__ tet, const int *__restrict__ trizone,
+                        const double *__restrict__ permx, const double *__restrict__ permy, const double *__restrict__ permz,
+                        const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ Z,
+                        const double *__restrict__ psi, const double *__restrict__ ckrw, double *__restrict__ uu, double *__restrict__ vv,
+                        double *__restrict__ ww)
+{
+    const double amen[5] = {-1.0, 1.0, -1.0, 1.0, -1.0};
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nt; e += gridDim.x * blockDim.x) {
+        int4 t4 = tet[e];
+        const int T[4] = {t4.x, t4.y, t4.z, t4.w};
+        double x[4], y[4], z[4], p[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { x[q] = X[T[q]]; y[q] = Y[T[q]]; z[q] = Z[T[q]]; p[q] = psi[T[q]]; }
+        double vol = 0.0, bb = 0.0, cc = 0.0, dd = 0.0;
+#pragma unroll
+        for (int nn = 0; nn < 4; ++nn) {
+            const int o3[3] = {(nn + 1) & 3, (nn + 2) & 3, (nn + 3) & 3};
+            double a2 = 0.0, a3 = 0.0;
+#pragma unroll
+            for (int ii = 0; ii < 3; ++ii) { int I = o3[ii], J = o3[(ii + 1) % 3], M = o3[(ii + 2) % 3]; a3 = y[I] * z[J] + a3; a2 = y[I] * z[M] + a2; }
+            double b = amen[nn] * (a3 - a2) / 6.0;
+            vol = vol + x[nn] * amen[nn] * (a3 - a2) / 6.0;
+            a2 = a3 = 0.0;
+#pragma unroll
+            for (int ii = 0; ii < 3; ++ii) { int I = o3[ii], J = o3[(ii + 1) % 3], M = o3[(ii + 2) % 3]; a3 = x[I] * z[J] + a3; a2 = x[I] * z[M] + a2; }
+            double c = amen[nn + 1] * (a3 - a2) / 6.0;
+            a2 = a3 = 0.0;
+#pragma unroll
+            for (int ii = 0; ii < 3; ++ii) { int I = o3[ii], J = o3[(ii + 1) % 3], M = o3[(ii + 2) % 3]; a3 = x[I] * y[J] + a3; a2 = x[I] * y[M] + a2; }
+            double d = amen[nn] * (a3 - a2) / 6.0;
+            bb = bb + p[nn] * b; cc = cc + p[nn] * c; dd = dd + p[nn] * d;
+        }
+        const int ivol = vol < 0.0 ? -1 : 1;
+        const double volur = 1.0 / fabs(vol);
+        const double kre = (((ckrw[T[0]] + ckrw[T[1]]) + ckrw[T[2]]) + ckrw[T[3]]) * 0.25;
+        const int lay = e / (3 * ntri), tri = (e - lay * 3 * ntri) / 3, idx = lay * nzone + trizone[tri];
+        const double xyz = -kre * volur * ivol;
+        uu[e] = bb * xyz * permx[idx];
+        vv[e] = cc * xyz * permy[idx];
+        ww[e] = (dd * xyz - kre) * permz[idx];
+    }
+}
+// VNOD3D (SRC/vnod3d.f): nodal velocity = mean over the elements of the node, summed in element order (the node family of the
+// assembly plan lists them in that order; padding entries carry coef2 = 0)
+__global__ void k_vnod3d(int n, EllPlan P, const double *__restrict__ uu, const double *__restrict__ vv, const double *__restrict__ ww,
+                         double *__restrict__ unod, double *__restrict__ vnod, double *__restrict__ wnod)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const EllFamily f = P.node;
+        double a = 0.0, b = 0.0, c = 0.0;
+        int cnt = 0;
+        for (int q = 0; q < f.w; ++q) {
+            size_t i = (size_t)q * P.ld + k;
+            if (f.coef2[i] != 0.0) { int t = f.tet[i]; a = a + uu[t]; b = b + vv[t]; c = c + ww[t]; ++cnt; }
+        }
+        unod[k] = a / cnt; vnod[k] = b / cnt; wnod[k] = c / cnt;
+    }
+}
+
 // one member's state <-> column `col` of a row-major ensemble matrix [n][ld]
 __global__ void k_pack_col(int n, const double *__restrict__ v, double *__restrict__ X, long long ld, long long col)
 {
@@ -1786,6 +1848,7 @@ struct CathySim {
     std::vector<double> hx, hy, hz, harenod;
     std::vector<double> h_dem, h_root, h_zratio, h_veg;   // owned copies of the caller's mesh inputs (cathy_set_soil rebuilds from them)
     std::vector<int32_t> h_zone;
+    std::vector<double> h_perm;     // permx | permy | permz tables as last built ([nstr][nzone] each)
     std::vector<int> htri;       // [ntri*4] sorted nodes + zone
     std::vector<unsigned char> hexist; // [NDIAG*n] structural mask of the upper diagonals
     int64_t nterm = 0;
@@ -2066,6 +2129,11 @@ static int build_static(CathySim *S)
             for (int q = 0; q < 4; ++q) tet_gz[(size_t)q * nt + e] = p.permz[idx] * ivol * d[q];
             tet_vol[e] = V;
         }
+    }
+    {
+        const size_t nsz = (size_t)nstr * p.nzone;
+        S->h_perm.resize(3 * nsz);
+        for (size_t q = 0; q < nsz; ++q) { S->h_perm[q] = p.permx[q]; S->h_perm[nsz + q] = p.permy[q]; S->h_perm[2 * nsz + q] = p.permz[q]; }
     }
     S->hexist.assign(nslots, 0);
     S->nterm = 0;
@@ -2691,7 +2759,7 @@ static int preload_kernels()
                          (const void *)k_switch_old, (const void *)k_adrstn, (const void *)k_pondupd, (const void *)k_atm_interp, (const void *)k_etran,
                          (const void *)k_div_area, (const void *)k_nod_cell, (const void *)k_cell_nod, (const void *)k_route, (const void *)k_pond_zero,
                          (const void *)k_step_partial, (const void *)k_step_final, (const void *)k_weight, (const void *)k_atmone, (const void *)k_mbinit,
-                         (const void *)k_pack_col, (const void *)k_unpack_col};
+                         (const void *)k_pack_col, (const void *)k_unpack_col, (const void *)k_vel3d, (const void *)k_vnod3d};
     for (const void *f : fns) CK(cudaFuncGetAttributes(&at, f));
     done = true;
     return 0;
@@ -3046,6 +3114,39 @@ int32_t cathy_get_state(CathySim *S, double *psi, double *sw, double *ckrw, doub
     if (ovfl) CK(cudaMemcpyAsync(ovfl, S->ovflnod.p, bs, cudaMemcpyDeviceToHost, S->st));
     if (ifatm) CK(cudaMemcpyAsync(ifatm, S->ifatm.p, (size_t)S->nnod * sizeof(int), cudaMemcpyDeviceToHost, S->st));
     CK(cudaStreamSynchronize(S->st));
+    return 0;
+}
+
+int32_t cathy_get_velocity(CathySim *S, double *uu, double *vv, double *ww, double *unod, double *vnod, double *wnod)
+{
+    CK(cudaSetDevice(S->p.device));
+    const int n = S->n, nt = S->nt;
+    DBuf<double> dx, dy, px, py, pz, du, dv, dw, dun, dvn, dwn;
+    DBuf<int> tz;
+    std::vector<double> hx(S->hx.begin(), S->hx.end()), hy(S->hy.begin(), S->hy.end());
+    std::vector<int> trizone(S->ntri);
+    for (int t = 0; t < S->ntri; ++t) trizone[t] = S->htri[4 * (size_t)t + 3] - 1;
+    const size_t nsz = (size_t)S->nstr * S->p.nzone;
+    if (S->h_perm.size() != 3 * nsz) FAIL(-1, "cathy_get_velocity: conductivity tables are not available");
+    std::vector<double> kx(S->h_perm.begin(), S->h_perm.begin() + nsz), ky(S->h_perm.begin() + nsz, S->h_perm.begin() + 2 * nsz),
+        kz(S->h_perm.begin() + 2 * nsz, S->h_perm.end());
+    int rc = 0;
+    rc |= dx.upload(hx); rc |= dy.upload(hy); rc |= tz.upload(trizone); rc |= px.upload(kx); rc |= py.upload(ky); rc |= pz.upload(kz);
+    rc |= du.alloc(nt); rc |= dv.alloc(nt); rc |= dw.alloc(nt); rc |= dun.alloc(n); rc |= dvn.alloc(n); rc |= dwn.alloc(n);
+    if (rc) FAIL(-101, "cathy_get_velocity: device allocation failed");
+    LAUNCH(S, k_vel3d, nblk(nt, 4 * S->grid_n), RED_BLOCK, nt, S->ntri, S->p.nzone, S->tet.p, tz.p, px.p, py.p, pz.p, dx.p, dy.p, S->z.p, S->pnew.p, S->ckrw.p,
+           du.p, dv.p, dw.p);
+    LAUNCH(S, k_vnod3d, nblk(n, S->grid_n), RED_BLOCK, n, S->plan, du.p, dv.p, dw.p, dun.p, dvn.p, dwn.p);
+    CK(cudaStreamSynchronize(S->st));
+    if (uu) CK(cudaMemcpy(uu, du.p, (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost));
+    if (vv) CK(cudaMemcpy(vv, dv.p, (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost));
+    if (ww) CK(cudaMemcpy(ww, dw.p, (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost));
+    if (unod) CK(cudaMemcpy(unod, dun.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (vnod) CK(cudaMemcpy(vnod, dvn.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (wnod) CK(cudaMemcpy(wnod, dwn.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    DBuf<double> *all[] = {&dx, &dy, &px, &py, &pz, &du, &dv, &dw, &dun, &dvn, &dwn};
+    for (auto *b : all) b->release();
+    tz.release();
     return 0;
 }
 int32_t cathy_set_psi(CathySim *S, const double *psi)

@@ -128,3 +128,79 @@ def write_xyz(path, nnod, n, x, y, z) -> None:
         idx = np.arange(1, n + 1)
         for i, a, b, c in zip(idx, x, y, z):
             fh.write("%7d%15.6E%15.6E%15.6E\n" % (i, a, b, c))
+
+
+# ---------------------------------------------------------------------------------------------
+# vtk/1NN.vtk (SRC/vtkris3d.f): legacy ASCII unstructured grid with pressure, saturation (VTKF >= 2), element
+# conductivity (VTKF >= 3) and element Darcy velocity (VTKF >= 4).  Header lines use FORMATs 78/77/79/80/81/82-85, the value
+# lists are LIST-DIRECTED writes, reproduced here with gfortran's rules for REAL(8) / INTEGER(4).
+# ---------------------------------------------------------------------------------------------
+def ld_real(x: float) -> str:
+    """gfortran list-directed REAL(8): 17 significant digits; F editing in a 21-column field + 5 blanks when
+    0.1 <= |x| < 1e17 (after rounding), ES26.17E3 otherwise; zero prints as 0.0000000000000000."""
+    x = float(x)
+    if x != x or x in (float("inf"), float("-inf")):
+        return ("NaN" if x != x else ("Infinity" if x > 0 else "-Infinity")).rjust(26)
+    if x == 0.0:
+        return "  -0.0000000000000000     " if np.signbit(x) else "   0.0000000000000000     "
+    mant, ex = ("%.16E" % x).split("E")
+    k = int(ex) + 1                                   # 10**(k-1) <= |x| < 10**k after rounding to 17 digits
+    if 0 <= k <= 17:
+        return ("%.*f" % (17 - k, x)).rjust(21) + "     "
+    return ("%sE%+04d" % (mant, int(ex))).rjust(26)
+
+
+def _ld_reals(v: np.ndarray) -> np.ndarray:
+    """Vectorised ld_real for an array (one 26-character token per value)."""
+    v = np.asarray(v, dtype=np.float64).ravel()
+    out = np.empty(v.shape, dtype="U26")
+    fin = np.isfinite(v) & (v != 0.0)
+    ex = np.zeros(v.shape, dtype=np.int64)
+    es = np.char.mod("%.16E", v[fin])
+    ex[fin] = np.array([int(t[-4:]) if t[-4] in "+-" else int(t.split("E")[1]) for t in es], dtype=np.int64) if es.size else ex[fin]
+    k = ex + 1
+    use_f = fin & (k >= 0) & (k <= 17)
+    for kk in np.unique(k[use_f]):
+        m = use_f & (k == kk)
+        out[m] = np.char.add(np.char.rjust(np.char.mod("%%.%df" % (17 - int(kk)), v[m]), 21), "     ")
+    m = fin & ~use_f
+    if np.any(m):
+        out[m] = [ld_real(t) for t in v[m]]
+    m = ~fin
+    if np.any(m):
+        out[m] = [ld_real(t) for t in v[m]]
+    return out
+
+
+def write_vtk(path: str, time: float, x, y, z, tetra0: np.ndarray, psi, sw, ks=None, vel=None, vtkf: int = 1) -> None:
+    """tetra0: [NT][4] 0-based node ids in the processor's stored order (sorted ascending under Picard)."""
+    n, nt = len(x), len(tetra0)
+    with open(path, "w") as fh:
+        fh.write("# vtk DataFile Version 2.0\n3D Unstructured Grid of Linear Triangles\nASCII\n")
+        fh.write("DATASET UNSTRUCTURED_GRID\nFIELD FieldData  1\nTIME 1 1 double\n%18.5f\n" % time)
+        fh.write("POINTS %8d float\n" % n)
+        pts = np.char.add(np.char.add(np.char.mod("%16.8E", x), np.char.mod("%16.8E", y)), np.char.mod("%16.8E", z))
+        fh.write("\n".join(np.char.add("    ", pts)))
+        fh.write("\nCELLS %8d %8d\n" % (nt, nt * 5))
+        t = np.asarray(tetra0)
+        cells = np.char.add("4", np.char.add(np.char.add(np.char.mod("   %8d", t[:, 0]), np.char.mod("   %8d", t[:, 1])),
+                                              np.char.add(np.char.mod("   %8d", t[:, 2]), np.char.mod("   %8d", t[:, 3]))))
+        fh.write("\n".join(cells))
+        fh.write("\nCELL_TYPES%8d\n" % nt)
+        fh.write(("          10\n") * nt)
+        fh.write("POINT_DATA %8d\nSCALARS pressure float\nLOOKUP_TABLE default\n" % n)
+        fh.write("\n".join(_ld_reals(psi)))
+        fh.write("\n")
+        if vtkf >= 2:
+            fh.write("SCALARS saturation float\nLOOKUP_TABLE default\n")
+            fh.write("\n".join(_ld_reals(sw)))
+            fh.write("\n")
+        if vtkf >= 3:
+            fh.write("CELL_DATA %8d\nSCALARS permeability float\nLOOKUP_TABLE default\n" % nt)
+            fh.write("\n".join(_ld_reals(ks)))
+            fh.write("\n")
+        if vtkf >= 4:
+            fh.write("VECTORS velocity float\n")
+            a, b, c = (_ld_reals(v) for v in vel)
+            fh.write("\n".join(np.char.add(np.char.add(a, b), c)))
+            fh.write("\n")

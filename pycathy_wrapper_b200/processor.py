@@ -16,6 +16,8 @@ import os
 import sys
 import time
 
+import numpy as np
+
 from . import outputs as O
 from .capi import CathyLib, Simulation, load_library
 from .project import CathyProject, load_project
@@ -85,10 +87,37 @@ def run_processor(project_dir: str, lib: CathyLib | None = None, write_files: bo
         if parm["ISIMGR"] == 2:
             fh["hgraph"].write("#          TIME %s\n" % "".join(O.fi(v, 16) for v in [int(prj.surf["qoi"][-1])] + parm["ID_QOUT"]))
 
-    def detout(nstep, tim):
+    vtk_state = {"tet0": None, "ks": None}
+
+    def vtkout(unit, tim, st):
+        """VTKRIS3D (SRC/vtkris3d.f), called with unit 100 at time 0 and 100+KPRT at the detailed outputs when IPRT >= 2 and
+        VTKF > 0 (SRC/cathy_main.f:2833-2837, 3727-3729, 3860-3862); files land in ./vtk like the reference's."""
+        vtkf = int(parm.get("VTKF", 0))
+        if parm["IPRT"] < 2 or vtkf <= 0:
+            return
+        if vtk_state["tet0"] is None:
+            _, _, _, tet = sim.mesh()
+            t0 = tet[:, :4].astype(np.int64) - 1
+            if int(parm["IOPT"]) == 1:
+                t0 = np.sort(t0, axis=1)                  # element nodes are kept sorted under Picard (SRC/grdsys.f:63)
+            vtk_state["tet0"] = t0
+            ntri3 = 3 * 2 * prj.nrow * prj.ncol
+            lay = np.arange(sim.nt) // ntri3
+            vtk_state["ks"] = prj.soil["TABLE"][lay, tet[:, 4] - 1, 0]   # KS(J) = PERMX(layer, zone), SRC/cathy_main.f:2688-2691
+        vel = None
+        if vtkf >= 4:
+            v = sim.velocity(nodal=False)
+            vel = (v["uu"], v["vv"], v["ww"])
+        vdir = os.path.join(os.path.dirname(os.path.dirname(_out(prj, "IOUT11"))), "vtk")
+        os.makedirs(vdir, exist_ok=True)
+        O.write_vtk(os.path.join(vdir, "%3d.vtk" % unit), tim, x, y, z, vtk_state["tet0"], st["psi"], st["sw"], vtk_state["ks"], vel, vtkf)
+
+    def detout(nstep, tim, vtk_unit=None):
         if not write_files:
             return
         st = sim.state()
+        if vtk_unit is not None:
+            vtkout(vtk_unit, tim, st)
         if parm["IPRT"] >= 1:
             O.write_block(fh["psi"], nstep, tim, st["psi"])
             O.write_block(fh["pondhead"], nstep, tim, st["pond"])
@@ -98,7 +127,7 @@ def run_processor(project_dir: str, lib: CathyLib | None = None, write_files: bo
             O.write_vp(fh["vp"], nstep, tim, parm["NODVP"], nnod, nstr, x, y, z, st["psi"], st["sw"], st["ckrw"],
                        st["qtranie"])
 
-    detout(0, 0.0)
+    detout(0, 0.0, vtk_unit=100)
     res.wall_setup = time.perf_counter() - t_start
 
     cum = dict(VSFTOT=0.0, VNDTOT=0.0, VNNTOT=0.0, VNUDTOT=0.0, VTOT=0.0, CVIN=0.0, CVOUT=0.0, CDSTOR=0.0,
@@ -148,7 +177,7 @@ def run_processor(project_dir: str, lib: CathyLib | None = None, write_files: bo
             print(" TIME STEP: %6d  DELTAT: %12.4E  TIME: %12.4E  NL its %2d  lin its %4d  back-steps %d"
                   % (rep.nstep, rep.deltat, rep.time, rep.iter, rep.nitert, rep.kbackt), flush=True)
         if nprt > 0 and kprt <= nprt and rep.time >= timprt[kprt - 1]:
-            detout(rep.nstep, rep.time)
+            detout(rep.nstep, rep.time, vtk_unit=100 + kprt)
             kprt += 1
         res.wall_io += time.perf_counter() - t1
         if rep.finished or (max_steps is not None and rep.nstep >= max_steps):
@@ -157,7 +186,7 @@ def run_processor(project_dir: str, lib: CathyLib | None = None, write_files: bo
     res.finished_ok = not bool(last.noback)
     t1 = time.perf_counter()
     if max_steps is None:
-        detout(last.nstep, parm["TMAX"])            # label 300: final DETOUT always carries TIME=TMAX
+        detout(last.nstep, parm["TMAX"], vtk_unit=100 + kprt)   # label 300: final DETOUT always carries TIME=TMAX
     res.final_state = sim.state()
     for f in fh.values():
         f.close()

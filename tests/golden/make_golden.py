@@ -105,8 +105,27 @@ def newton():
     stash(tmp, os.path.join(tmp + "_ref", "output"), os.path.join(HERE, "storm20n"))
 
 
+def vtk():
+    """vtk/1NN.vtk of the reference ELF (VTKF=4: pressure, saturation, element conductivity, element Darcy velocity printed
+    list-directed with 17 significant digits) on a small 6x5x3 mesh; stored gzipped."""
+    import gzip
+    tmp = "/tmp/golden_vtk6"
+    shutil.rmtree(tmp, ignore_errors=True)
+    synthetic.make_project(tmp, 6, 5, 3, ic=("wt", 0.6), ISIMGR=1, TMAX=120.0, TIMPRT=[60.0, 120.0], DELTAT=1.0, DTMIN=1e-4, DTMAX=50.0,
+                           VTKF=4, IPRT=4, NODVP=[3], atmbc=[(0.0, 0.0), (30.0, 3.0e-5), (1.0e9, 3.0e-5)])
+    shutil.rmtree(tmp + "_ref", ignore_errors=True)
+    oracle.run_reference(tmp, tmp + "_ref", "20x20x15")
+    dst = os.path.join(HERE, "vtk6")
+    stash(tmp, os.path.join(tmp + "_ref", "output"), dst)
+    for f in sorted(os.listdir(os.path.join(tmp + "_ref", "vtk"))):
+        with open(os.path.join(tmp + "_ref", "vtk", f), "rb") as fi, gzip.GzipFile(os.path.join(dst, "golden", f + ".gz"), "wb", mtime=0) as fo:
+            fo.write(fi.read())
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "newton":
         newton()
+    elif len(sys.argv) > 1 and sys.argv[1] == "vtk":
+        vtk()
     else:
         main()

@@ -285,3 +285,39 @@ def test_newton_coupled_storm(gpu_lib, oracle_mod):
     assert abs(rg.time - rc.time) <= 1e-9 * rc.time
     assert abs(rg.store1 - rc.store1) <= 1e-6 * rc.store1
     assert np.max(np.abs(g.state()["psi"] - c.state()["psi"])) <= 1e-3
+
+
+def test_vtk_and_velocities_against_reference(gpu_lib, oracle_mod, tmp_path):
+    """Row (f)1 of SURVEY 8: vtk/1NN.vtk written by the device path.  Structure lines (header, points, cells) identical to the
+    reference ELF's files; pressure / saturation within the head tolerance; VEL3D element velocities and VNOD3D nodal
+    velocities within 1e-6 of the largest velocity (the device recomputes the basis coefficients with fused multiply-adds)."""
+    import gzip
+    from pycathy_wrapper_b200.capi import Simulation
+    from pycathy_wrapper_b200.processor import run_processor
+    from pycathy_wrapper_b200.project import load_project
+    dst = str(tmp_path / "vtk6")
+    shutil.copytree(os.path.join(GOLDEN, "vtk6"), dst)
+    res = run_processor(dst, lib=gpu_lib)
+    assert res.finished_ok
+    for f in ("100.vtk", "101.vtk", "102.vtk", "103.vtk"):
+        with gzip.open(os.path.join(GOLDEN, "vtk6", "golden", f + ".gz"), "rt") as fh:
+            gold = fh.read().split("\n")
+        ours = open(os.path.join(dst, "vtk", f)).read().split("\n")
+        assert len(ours) == len(gold)
+        ipd = gold.index([ln for ln in gold if ln.startswith("POINT_DATA")][0])
+        assert ours[:ipd + 3] == gold[:ipd + 3]                     # header, TIME, POINTS, CELLS, CELL_TYPES: character for character
+        num = lambda L: np.array([[float(v) for v in ln.split()] for ln in L if ln and (ln[0] == " " or ln[0] == "-")])
+        n = int(gold[ipd].split()[1])
+        pg, po = num(gold[ipd + 3:ipd + 3 + n]).ravel(), num(ours[ipd + 3:ipd + 3 + n]).ravel()
+        assert np.all(np.abs(po - pg) <= np.maximum(1e-6 * np.abs(pg), 1e-8))
+        iv = gold.index("VECTORS velocity float")
+        vg, vo = num(gold[iv + 1:]), num(ours[iv + 1:])
+        assert vg.shape == vo.shape and vg.shape[1] == 3
+        assert np.max(np.abs(vo - vg)) <= 1e-6 * np.abs(vg).max()
+    prj = load_project(dst)
+    g, c = Simulation(gpu_lib, prj), oracle_mod.simulation(prj)
+    for _ in range(5):
+        g.step(); c.step()
+    vg, vc = g.velocity(), c.velocity()
+    for k in ("uu", "vv", "ww", "unod", "vnod", "wnod"):
+        assert np.max(np.abs(vg[k] - vc[k])) <= 1e-6 * max(np.abs(vc[k]).max(), 1e-30), k
