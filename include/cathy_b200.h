@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CATHY_ABI_VERSION 2
+#define CATHY_ABI_VERSION 3
 #define CATHY_MAXIT 64 /* upper bound on ITUNS kept in a step report (CATHY.H MAXIT=30) */
 
 /* Everything DATIN / INITAL read from the project files (SRC/datin.f:80-514,
@@ -124,6 +124,10 @@ typedef struct CathyStepReport {
     double pcg_ms;      /* device time inside the PCG kernel over all solves of this step (incl. back-stepped attempts) */
     int64_t pcg_iters;  /* PCG iterations over all those solves */
     int64_t pcg_solves; /* number of linear solves (nonlinear iterations incl. back-stepped attempts) */
+    double aact_prev;   /* AACTP: actual atmospheric flux of the previous time level (dtcoupling's AACTAV, SRC/cathy_main.f:3685) */
+    double areatot;     /* AREATOT: total catchment surface area (SRC/inital.f:131-134) */
+    int32_t itrtot;     /* ITRTOT: nonlinear iterations so far incl. back-stepped attempts (dtcoupling footer, SRC/cathy_main.f:3876) */
+    int32_t hgflag[9];  /* HGFLAG totals so far (output/hgflag, SRC/hgraph.f) */
     CathyIterRecord it[CATHY_MAXIT];
 } CathyStepReport;
 
@@ -160,6 +164,11 @@ int32_t cathy_get_state(CathySim *sim, double *psi, double *sw, double *ckrw, do
  * element sorted ascending under Picard, SRC/grdsys.f:63) and VNOD3D (SRC/vnod3d.f) per node [N] -- what DETOUT prints to
  * velelt / velnod and VTKRIS3D to vtk/1NN.vtk (SRC/detout.f:35, SRC/vtkris3d.f).  Any pointer may be NULL. */
 int32_t cathy_get_velocity(CathySim *sim, double *uu, double *vv, double *ww, double *unod, double *vnod, double *wnod);
+/* RECHARGE (SRC/recharge.f): recharge flux to the water table per surface node [NNOD] (any pointer may be NULL) and its sum
+ * RECFLOW, from the nodal vertical Darcy velocity (VEL3D + VNOD3D) at the current state -- hgatmsf's REC. FLUX column and
+ * output/recharge.  WTDEPTH (SRC/wtdepth.f): water-table elevation under the surface nodes nodvp[numvp] (1-based). */
+int32_t cathy_get_recharge(CathySim *sim, double *recnod, double *recflow);
+int32_t cathy_get_wtdepth(CathySim *sim, const int32_t *nodvp, int32_t numvp, double *wt);
 /* Overwrite the pressure-head state (DA restart; stands for pyCATHY update_ic(INDP=1) +
  * relaunch, pyCATHY/cathy_tools.py:1863-1875).  Only valid before the first step. */
 int32_t cathy_set_psi(CathySim *sim, const double *psi);

@@ -12,7 +12,7 @@ import numpy as np
 
 from .project import CathyProject
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAXIT = 64
 _D = C.POINTER(C.c_double)
 _I = C.POINTER(C.c_int32)
@@ -84,6 +84,8 @@ class CathyStepReport(C.Structure):
         ("ak_max", C.c_double), ("q_outlet_1", C.c_double), ("q_outlet_2", C.c_double), ("gpu_ms", C.c_double),
         ("launches", C.c_int64),
         ("pcg_ms", C.c_double), ("pcg_iters", C.c_int64), ("pcg_solves", C.c_int64),
+        ("aact_prev", C.c_double), ("areatot", C.c_double),
+        ("itrtot", C.c_int32), ("hgflag", C.c_int32 * 9),
         ("it", CathyIterRecord * MAXIT),
     ]
 
@@ -177,7 +179,7 @@ class CathyLib:
     """Binds one shared library exporting the cathy_b200.h entry points under ``prefix``."""
 
     SYMBOLS = ["sizeof_problem", "sizeof_report", "last_error", "create", "destroy", "get_dims", "get_mesh",
-               "initial_storage", "step", "get_state", "get_velocity", "set_psi", "upload_atm_record", "debug_assemble", "debug_spmv", "debug_solve"]
+               "initial_storage", "step", "get_state", "get_velocity", "get_recharge", "get_wtdepth", "set_psi", "upload_atm_record", "debug_assemble", "debug_spmv", "debug_solve"]
 
     # entry points only the product library has (in-process ensemble support); bound when present
     PRODUCT_ONLY = ["pack_state", "unpack_psi", "restart", "set_soil", "set_atm_table", "dd_export", "dd_connect", "dd_connect_local", "dd_start", "dd_info"]
@@ -227,6 +229,8 @@ class CathyLib:
         f["step"].argtypes = [C.c_void_p, C.POINTER(CathyStepReport)]
         f["get_state"].argtypes = [C.c_void_p, _D, _D, _D, _D, _D, _D, _D, _D, _I]
         f["get_velocity"].argtypes = [C.c_void_p, _D, _D, _D, _D, _D, _D]
+        f["get_recharge"].argtypes = [C.c_void_p, _D, _D]
+        f["get_wtdepth"].argtypes = [C.c_void_p, _I, C.c_int32, _D]
         f["set_psi"].argtypes = [C.c_void_p, _D]
         f["upload_atm_record"].argtypes = [C.c_void_p, C.c_int32, _D]
         f["debug_assemble"].argtypes = [C.c_void_p, C.c_double, _I, _I, _D, _D]
@@ -322,6 +326,19 @@ class Simulation:
                                             _dp(out["unod"]) if nodal else null, _dp(out["vnod"]) if nodal else null,
                                             _dp(out["wnod"]) if nodal else null), "get_velocity")
         return out
+
+    def recharge(self):
+        """(RECNOD[NNOD], RECFLOW) of SRC/recharge.f at the current state."""
+        rec = np.empty(self.nnod)
+        flow = C.c_double()
+        self._ck(self.lib.f["get_recharge"](self.h, _dp(rec), C.cast(C.byref(flow), _D)), "get_recharge")
+        return rec, flow.value
+
+    def wtdepth(self, nodvp) -> np.ndarray:
+        nd = np.ascontiguousarray(nodvp, dtype=np.int32)
+        wt = np.empty(len(nd))
+        self._ck(self.lib.f["get_wtdepth"](self.h, _ip(nd), len(nd), _dp(wt)), "get_wtdepth")
+        return wt
 
     def set_psi(self, psi: np.ndarray):
         psi = np.ascontiguousarray(psi, dtype=np.float64)

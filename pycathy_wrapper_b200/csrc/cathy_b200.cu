@@ -1761,6 +1761,43 @@ __global__ void k_vnod3d(int n, EllPlan P, const double *__restrict__ uu, const 
     }
 }
 
+
+// RECHARGE (SRC/recharge.f): per surface column, the vertical nodal velocity at the node just above the water table
+__global__ void k_recharge(int nnod, int nstr, const double *__restrict__ psi, const double *__restrict__ wnod, const double *__restrict__ arenod,
+                           double *__restrict__ recnod)
+{
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nnod; s += gridDim.x * blockDim.x) {
+        const size_t i = (size_t)nnod * nstr + s;
+        double r = 0.0;
+        bool done = false;
+        for (int j = 1; j <= nstr && !done; ++j)
+            if (psi[i - (size_t)(j - 1) * nnod] > 0.0 && psi[i - (size_t)j * nnod] <= 0.0 && wnod[i - (size_t)j * nnod] <= 0.0) {
+                r = -1.0 * wnod[i - (size_t)j * nnod] * arenod[s];
+                done = true;
+            }
+        if (!done && psi[s] >= 0.0 && wnod[s] <= 0.0) r = -1.0 * wnod[s] * arenod[s];
+        recnod[s] = r;
+    }
+}
+// WTDEPTH (SRC/wtdepth.f), one thread per requested surface node
+__global__ void k_wtdepth(int numvp, const int *__restrict__ nodvp, int nnod, int nstr, const double *__restrict__ Z, const double *__restrict__ P,
+                          double *__restrict__ wt)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numvp) return;
+    const int nd = nodvp[i] - 1;
+    int flag = 0;
+    double v = Z[nd];
+    for (int j = nstr; j >= 1; --j) {
+        const size_t i1 = nd + (size_t)j * nnod, i2 = nd + (size_t)(j - 1) * nnod;
+        if (P[i1] >= 0.0 && P[i2] < 0.0 && flag == 0) { double rc = (Z[i1] - Z[i2]) / (P[i1] - P[i2]); v = Z[i1] - rc * P[i1]; flag = 1; }
+        else if (P[i1] >= 0.0 && P[i2] < 0.0 && flag == 1) flag = 2;
+        else if (j == 1 && P[i2] >= 0.0 && flag == 0) { flag = 3; v = Z[nd] + P[i2]; }
+        else if (j == 1 && flag == 0) { flag = 4; v = Z[nd + (size_t)nstr * nnod]; }
+    }
+    wt[i] = v;
+}
+
 // one member's state <-> column `col` of a row-major ensemble matrix [n][ld]
 __global__ void k_pack_col(int n, const double *__restrict__ v, double *__restrict__ X, long long ld, long long col)
 {
@@ -1848,6 +1885,7 @@ struct CathySim {
     std::vector<double> hx, hy, hz, harenod;
     std::vector<double> h_dem, h_root, h_zratio, h_veg;   // owned copies of the caller's mesh inputs (cathy_set_soil rebuilds from them)
     std::vector<int32_t> h_zone;
+    double areatot = 0.0;           // AREATOT (SRC/inital.f:131-134), sequential sum over the (global) surface nodes
     std::vector<double> h_perm;     // permx | permy | permz tables as last built ([nstr][nzone] each)
     std::vector<int> htri;       // [ntri*4] sorted nodes + zone
     std::vector<unsigned char> hexist; // [NDIAG*n] structural mask of the upper diagonals
@@ -1989,6 +2027,8 @@ static int build_static(CathySim *S)
         double are3 = std::fabs(0.5 * (a3 - a2)) * (1.0 / 3.0);
         S->harenod[T[0]] += are3; S->harenod[T[1]] += are3; S->harenod[T[2]] += are3;
     }
+    S->areatot = 0.0;
+    for (int k = 0; k < nnod; ++k) S->areatot = S->areatot + S->harenod[k];
     // --- vertical discretisation (SRC/gen3d.f:52-77)
     double zmin = RMAX_;
     for (int i = 0; i < nnod; ++i) zmin = std::min(zmin, S->hz[i]);
@@ -2759,7 +2799,7 @@ static int preload_kernels()
                          (const void *)k_switch_old, (const void *)k_adrstn, (const void *)k_pondupd, (const void *)k_atm_interp, (const void *)k_etran,
                          (const void *)k_div_area, (const void *)k_nod_cell, (const void *)k_cell_nod, (const void *)k_route, (const void *)k_pond_zero,
                          (const void *)k_step_partial, (const void *)k_step_final, (const void *)k_weight, (const void *)k_atmone, (const void *)k_mbinit,
-                         (const void *)k_pack_col, (const void *)k_unpack_col, (const void *)k_vel3d, (const void *)k_vnod3d};
+                         (const void *)k_pack_col, (const void *)k_unpack_col, (const void *)k_vel3d, (const void *)k_vnod3d, (const void *)k_recharge, (const void *)k_wtdepth};
     for (const void *f : fns) CK(cudaFuncGetAttributes(&at, f));
     done = true;
     return 0;
@@ -3149,6 +3189,40 @@ int32_t cathy_get_velocity(CathySim *S, double *uu, double *vv, double *ww, doub
     tz.release();
     return 0;
 }
+
+int32_t cathy_get_recharge(CathySim *S, double *recnod, double *recflow)
+{
+    CK(cudaSetDevice(S->p.device));
+    const int n = S->n, nn = S->nnod;
+    std::vector<double> w(n), rec(nn);
+    int rc = cathy_get_velocity(S, nullptr, nullptr, nullptr, nullptr, nullptr, w.data());
+    if (rc) return rc;
+    DBuf<double> dw, dr;
+    if (dw.upload(w) || dr.alloc(nn)) FAIL(-101, "cathy_get_recharge: device allocation failed");
+    LAUNCH(S, k_recharge, nblk(nn, S->grid_n), RED_BLOCK, nn, S->nstr, S->pnew.p, dw.p, S->arenod.p, dr.p);
+    CK(cudaStreamSynchronize(S->st));
+    CK(cudaMemcpy(rec.data(), dr.p, (size_t)nn * sizeof(double), cudaMemcpyDeviceToHost));
+    dw.release(); dr.release();
+    double flow = 0.0;
+    for (int s = 0; s < nn; ++s) flow = flow + rec[s];      // RECFLOW: the reference's sequential sum over the surface nodes
+    if (recnod) memcpy(recnod, rec.data(), (size_t)nn * sizeof(double));
+    if (recflow) *recflow = flow;
+    return 0;
+}
+int32_t cathy_get_wtdepth(CathySim *S, const int32_t *nodvp, int32_t numvp, double *wt)
+{
+    CK(cudaSetDevice(S->p.device));
+    if (numvp <= 0) return 0;
+    for (int i = 0; i < numvp; ++i) if (nodvp[i] < 1 || nodvp[i] > S->nnod) FAIL(-1, "cathy_get_wtdepth: NODVP(%d) = %d is not a surface node", i + 1, nodvp[i]);
+    DBuf<int> dn; DBuf<double> dwt;
+    std::vector<int> hn(nodvp, nodvp + numvp);
+    if (dn.upload(hn) || dwt.alloc(numvp)) FAIL(-101, "cathy_get_wtdepth: device allocation failed");
+    LAUNCH(S, k_wtdepth, (numvp + 127) / 128, 128, numvp, dn.p, S->nnod, S->nstr, S->z.p, S->pnew.p, dwt.p);
+    CK(cudaStreamSynchronize(S->st));
+    CK(cudaMemcpy(wt, dwt.p, (size_t)numvp * sizeof(double), cudaMemcpyDeviceToHost));
+    dn.release(); dwt.release();
+    return 0;
+}
 int32_t cathy_set_psi(CathySim *S, const double *psi)
 {
     if (S->nstep != 1 || S->kbackt != 0 || S->itrtot != 0) FAIL(-1, "cathy_set_psi is only valid before the first step");
@@ -3261,6 +3335,8 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
     rep->ndin = S->ndin; rep->ndout = S->ndout; rep->nnin = S->nnin; rep->nnout = S->nnout;
     rep->vndin = S->vndin; rep->vndout = S->vndout; rep->vnnin = S->vnnin; rep->vnnout = S->vnnout;
     rep->apot = so.apot; rep->aact = so.aact; rep->ovflow = so.ovflow; rep->reflow = so.reflow;
+    rep->aact_prev = S->aactp; S->aactp = so.aact;      // AACTP = AACT, SRC/cathy_main.f:3695
+    rep->areatot = S->areatot;
     const double NNg = S->dd ? (double)S->gnnod : (double)NN;
     rep->fhort = (double)so.nhort / NNg; rep->fdunn = (double)so.ndunn / NNg; rep->fpond = (double)so.npond / NNg; rep->fsat = (double)so.nsat / NNg;
     rep->n_iter_rec = std::min(S->iter, CATHY_MAXIT);
@@ -3282,6 +3358,8 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
         if (!(S->time <= S->tmax)) S->finished = 1;
     }
     rep->finished = S->finished; rep->next_deltat = S->deltat; rep->next_time = S->time;
+    rep->itrtot = S->itrtot;
+    for (int q = 0; q < 9; ++q) rep->hgflag[q] = S->hgflag[q];
     rep->gpu_ms = ms; rep->launches = S->launches - l0;
     rep->pcg_ms = S->pcg_ms - pm0; rep->pcg_iters = S->pcg_iters - pi0; rep->pcg_solves = S->pcg_solves - ps0;
     return 0;

@@ -204,3 +204,130 @@ def write_vtk(path: str, time: float, x, y, z, tetra0: np.ndarray, psi, sw, ks=N
             a, b, c = (_ld_reals(v) for v in vel)
             fh.write("\n".join(np.char.add(np.char.add(a, b), c)))
             fh.write("\n")
+
+
+# ---------------------------------------------------------------------------------------------
+# Auxiliary per-step and per-DETOUT outputs pyCATHY plots or maps (read_hgatmsf, read_dtcoupling, read_hgsfdet, read_wtdepth,
+# read_recharge, read_fort777 in pyCATHY/importers/cathy_outputs.py).  FORMAT numbers refer to SRC/cathy_main.f unless noted.
+# ---------------------------------------------------------------------------------------------
+HGATMSF_HEADER = ("#NSTP            DELTAT         TIME    POT. FLUX    ACT. FLUX    OVL. FLUX    RET. FLUX    SEEP FLUX"
+                  "    REC. FLUX     REC.VOL.\n")                                                     # SRC/mbinit.f FORMAT 1000
+HGNANSF_HEADER = "#NSTEP     DELTAT       TIME   NET NATM,NSF DIR FLUX   NET NATM,NSF NEU FLUX\n"     # mbinit.f 1010
+HGSFDET_HEADER = "# NSTEP            DELTAT              TIME  NET SEEPFACE VOL  NET SEEPFACE FLX\n"  # mbinit.f 1020
+HGNANSFDIR_HEADER = "# NSTEP            DELTAT              TIME NET NANSF DIR VOL NET NANSF DIR FLX\n"
+HGNANSFNEU_HEADER = "# NSTEP            DELTAT              TIME NET NANSF NEU VOL NET NANSF NEU FLX\n"
+WTDEPTH_HEADER = "#TIME      <--- WTDEPTH(NODVP(I)), I=1,2,...,NUMVP --->\n"                          # FORMAT 1232
+_DTC = [("Step      (1)", "Time step"), ("Deltat    (2)", "Time step size"), ("Time      (3)", "See parm input file for units"),
+        ("Back      (4)", "# of back-stepping occurrences"),
+        ("NL-l      (5)", "# of nonlinear iterations for the successful (last) time step"),
+        ("NL-a      (6)", "# of nonlinear iterations for the successful time step and any back-steps (= NL-last + ITUNS*Back)"),
+        ("Sdt-l     (7)", "# of time steps in the surface routing module for the successful (last) subsurface module time step"),
+        ("Sdt-a     (8)", "# of time steps in the surface routing module for the successful subsurface module time step and any back-steps"),
+        ("Atmpot-vf (9)", "Potential atmospheric forcing (rain +ve / evap -ve) as a volumetric flux [L^3/T]"),
+        ("Atmpot-v (10)", "Potential atmospheric forcing volume [L^3] (See parm input file for units)"),
+        ("Atmpot-r (11)", "Potential atmospheric forcing rate [L/T]"), ("Atmpot-d (12)", "Potential atmospheric forcing depth [L]"),
+        ("Atmact-vf(13)", "Actual infiltration (+ve) or exfiltration (-ve) at atmospheric BC nodes as a volumetric flux [L^3/T]"),
+        ("Atmact-v (14)", "Actual infiltration (+ve) or exfiltration (-ve) volume [L^3]"),
+        ("Atmact-r (15)", "Actual infiltration (+ve) or exfiltration (-ve) rate [L/T]"),
+        ("Atmact-d (16)", "Actual infiltration (+ve) or exfiltration (-ve) depth [L]"),
+        ("Horton   (17)", "Fraction of the surface nodes that are saturated or ponded due to Horton infiltration excess (Note: based on PNEW and not on IFATM)"),
+        ("Dunne    (18)", "Fraction of the surface nodes that are saturated or ponded due to Dunne saturation excess (see previous note)"),
+        ("Ponded   (19)", "Fraction of the surface nodes that are ponded (PNEW > PONDH_MIN)"),
+        ("Satur    (20)", "Fraction of the surface nodes that are saturated or ponded (PNEW > 0)"),
+        ("CPU-sub  (21)", "CPU seconds for the subsurface flow module"), ("CPU-surf (22)", "CPU seconds for the surface routing module")]
+
+
+def dtcoupling_header(surf: bool, nnod: int, ncell: int, areatot: float) -> str:
+    """SRC/inital.f FORMAT 1100 (coupled runs only) + 1110."""
+    s = ""
+    if surf:
+        s += "#" + " " * 17 + " ***** Surface vs subsurface diagnostics ***** \n"
+        s += "#NNOD    (# of surface nodes)            = %s\n#NCELL   (# of DEM cells)                = %s\n" % (fi(nnod, 6), fi(ncell, 6))
+        s += "#AREATOT (total catchment surface area)  = %s\n" % fe(areatot, 15, 5)
+    s += "".join("#%s : %s\n" % kv for kv in _DTC)
+    s += ("#   (1)       (2)       (3)   (4)   (5)   (6)   (7)   (8)        (9)       (10)       (11)       (12)       (13)"
+          "       (14)       (15)       (16)   (17)   (18)   (19)   (20)       (21)       (22)\n"
+          "#  Step    Deltat      Time  Back  NL-l  NL-a Sdt-l Sdt-a  Atmpot-vf   Atmpot-v   Atmpot-r   Atmpot-d  Atmact-vf"
+          "   Atmact-v   Atmact-r   Atmact-d Horton  Dunne Ponded  Satur   CPU-sub  CPU-surf\n")
+    return s
+
+
+def dtcoupling_line(rep, ituns: int, cpusub: float, cpusurf: float) -> str:
+    """FORMAT 1170: I7,2(1PE10.3),5(I6),8(1PE11.3),4(0PF7.3),2(1PE11.3)"""
+    at = rep.areatot
+    aav = 0.5 * (rep.aact + rep.aact_prev)
+    vals = [rep.apot, rep.apot * rep.deltat, rep.apot / at, (rep.apot * rep.deltat) / at, aav, aav * rep.deltat, aav / at, (aav * rep.deltat) / at]
+    return (fi(rep.nstep, 7) + fe(rep.deltat, 10, 3) + fe(rep.time, 10, 3)
+            + "".join(fi(v, 6) for v in (rep.kbackt, rep.iter, rep.iter + ituns * rep.kbackt, rep.nsurf, rep.nsurft))
+            + "".join(fe(v, 11, 3) for v in vals) + "".join("%7.3f" % v for v in (rep.fhort, rep.fdunn, rep.fpond, rep.fsat))
+            + fe(cpusub, 11, 3) + fe(cpusurf, 11, 3) + "\n")
+
+
+def dtcoupling_footer(kback, itrtot, ituns, nsurft_t, nsurft_tb, vapot_t, vaact_t, areatot, cpusub_t, cpusurf_t) -> str:
+    """FORMAT 1175"""
+    return ("#" + "=" * 192 + "\n#Total:" + " " * 20 + "".join(fi(v, 6) for v in (kback, itrtot, itrtot + ituns * kback, nsurft_t, nsurft_tb))
+            + "".join(" " * 11 + fe(v, 11, 3) for v in (vapot_t, vapot_t / areatot, vaact_t, vaact_t / areatot)) + " " * 28
+            + fe(cpusub_t, 11, 3) + fe(cpusurf_t, 11, 3) + "\n")
+
+
+def hgatmsf_line(rep, recflow: float, recvol: float) -> str:
+    """FORMAT 1190: I10,2(1PE13.5),7(1PE13.5)"""
+    return fi(rep.nstep, 10) + "".join(fe(v, 13, 5) for v in (rep.deltat, rep.time, rep.apot, rep.aact, rep.ovflow, rep.reflow, rep.sfflw,
+                                                               recflow, recvol / rep.areatot)) + "\n"
+
+
+def hgnansf_line(rep) -> str:
+    """FORMAT 1195: I6,2(1PE11.3),2(11X,1PE13.5)"""
+    return fi(rep.nstep, 6) + fe(rep.deltat, 11, 3) + fe(rep.time, 11, 3) + " " * 11 + fe(rep.ndin + rep.ndout, 13, 5) + " " * 11 + \
+        fe(rep.nnin + rep.nnout, 13, 5) + "\n"
+
+
+def det_line(rep, vol: float) -> str:
+    """FORMAT 1197: I7,4(4X,1PE17.9) -- hgsfdet, hgnansfdirdet, hgnansfneudet"""
+    return fi(rep.nstep, 7) + "".join("    " + fe(v, 17, 9) for v in (rep.deltat, rep.time, vol, vol / rep.deltat)) + "\n"
+
+
+def wtdepth_line(time: float, wt) -> str:
+    """SRC/wtdepth.f FORMAT 1020: 70(1PE15.6)"""
+    vals = [time] + [float(v) for v in wt]
+    return "\n".join("".join(fe(v, 15, 6) for v in vals[i:i + 70]) for i in range(0, len(vals), 70)) + "\n"
+
+
+def hgflag_text(hg) -> str:
+    """FORMAT 1260"""
+    return "\n HGFLAG:    (1)    (2)    (3)    (4)    (5)    (6)    (7)    (8)    (9)\n" + " " * 8 + " ".join(fi(v, 6) for v in hg) + "\n"
+
+
+def write_surface_table(fh, nstep: int, time: float, title: str, x, y, values, integer: bool = False) -> None:
+    """psisurf / satsurf / swsurf / recharge / fort.777 block of DETOUT (SRC/detout.f FORMATs 1000, 2000-2042, 2060/2080)."""
+    fh.write("%s%s     NSTEP   TIME\n" % (fi(nstep, 7), fe(time, 16, 8)))
+    fh.write(" SURFACE NODE              X              Y%s\n" % title.rjust(15))
+    n = len(values)
+    idx = np.char.mod("%6d", np.arange(1, n + 1))
+    xs, ys = np.char.mod("%15.6E", x[:n]), np.char.mod("%15.6E", y[:n])
+    vs = np.char.mod("%15d", np.asarray(values, dtype=np.int64)) if integer else np.char.mod("%15.6E", values)
+    rows = np.char.add(np.char.add(np.char.add(np.char.add("       ", idx), xs), ys), vs)
+    fh.write("\n".join(rows))
+    fh.write("\n")
+
+
+def write_velnod(fh, nstep: int, time: float, u, v, w) -> None:
+    """SRC/detout.f:34-35, FORMAT 1000 + 1040 (3 values per line = one node per line)."""
+    fh.write("%s%s     NSTEP   TIME\n" % (fi(nstep, 7), fe(time, 16, 8)))
+    rows = np.char.add(np.char.add(np.char.mod("%15.6E", u), np.char.mod("%15.6E", v)), np.char.mod("%15.6E", w))
+    fh.write("\n".join(rows))
+    fh.write("\n")
+
+
+def write_velelt(fh, time: float, uu, vv, ww) -> None:
+    """SRC/detout.f:40-43, FORMAT 1010 + three 1020 lists."""
+    fh.write("%s       TIME\n" % fe(time, 16, 8))
+    for arr in (uu, vv, ww):
+        txt = np.char.mod("%15.6E", arr)
+        n = len(txt)
+        full = (n // 5) * 5
+        if full:
+            fh.write("\n".join("".join(r) for r in txt[:full].reshape(-1, 5)))
+            fh.write("\n")
+        if n > full:
+            fh.write("".join(txt[full:]) + "\n")

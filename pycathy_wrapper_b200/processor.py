@@ -78,7 +78,20 @@ def run_processor(project_dir: str, lib: CathyLib | None = None, write_files: bo
         for key, unit in (("psi", "IOUT11"), ("sw", "IOUT13"), ("vp", "IOUT6"), ("mbeconv", "IOUT5"),
                           ("cumflowvol", "IOUT36"), ("iter", "IOUT4"), ("hgraph", "IOUT41"), ("pondhead", "IOUT42")):
             fh[key] = open(_out(prj, unit), "w")
+        aux = (("hgatmsf", "IOUT7"), ("hgnansf", "IOUT8"), ("hgflag", "IOUT9"), ("velnod", "IOUT12"), ("velelt", "IOUT15"), ("psisurf", "IOUT16"),
+               ("satsurf", "IOUT17"), ("swsurf", "IOUT18"), ("hgsfdet", "IOUT30"), ("hgnansfdirdet", "IOUT31"), ("hgnansfneudet", "IOUT32"),
+               ("dtcoupling", "IOUT43"), ("recharge", "IOUT44"), ("wtdepth", "IOUT57"))
+        for key, unit in aux:
+            if unit in prj.fnames:
+                fh[key] = open(_out(prj, unit), "w")
+        fh["fort777"] = open(os.path.join(os.path.dirname(os.path.dirname(_out(prj, "IOUT11"))), "fort.777"), "w")   # unit 777: unnamed, lands in the cwd
+        for key, head in (("hgatmsf", O.HGATMSF_HEADER), ("hgnansf", O.HGNANSF_HEADER), ("hgsfdet", O.HGSFDET_HEADER),
+                          ("hgnansfdirdet", O.HGNANSFDIR_HEADER), ("hgnansfneudet", O.HGNANSFNEU_HEADER), ("wtdepth", O.WTDEPTH_HEADER)):
+            if key in fh:
+                fh[key].write(head)
         if parm["IPRT"] >= 4:
+            if "velelt" in fh:
+                fh["velelt"].write("  0   HSPVEL\n")
             fh["sw"].write("  0   HSPSW\n")
         fh["iter"].write(O.iter_header(parm))
         fh["mbeconv"].write(O.MBECONV_HEADER % O.fe(sim.initial_storage(), 13, 5))
@@ -88,6 +101,21 @@ def run_processor(project_dir: str, lib: CathyLib | None = None, write_files: bo
             fh["hgraph"].write("#          TIME %s\n" % "".join(O.fi(v, 16) for v in [int(prj.surf["qoi"][-1])] + parm["ID_QOUT"]))
 
     vtk_state = {"tet0": None, "ks": None}
+    area_cache = {}
+
+    def arenod():
+        """Nodal surface areas (SRC/area2d.f): a third of the area of every adjacent triangle, summed in triangle order."""
+        if "a" not in area_cache:
+            nc1 = prj.ncol + 1
+            a = np.zeros(nnod)
+            are3 = abs(0.5 * prj.dx * prj.dy) * (1.0 / 3.0)
+            for i in range(prj.nrow):
+                for j in range(prj.ncol):
+                    n00 = i * nc1 + j
+                    for nd in (n00, n00 + nc1, n00 + nc1 + 1, n00, n00 + 1, n00 + nc1 + 1):
+                        a[nd] += are3
+            area_cache["a"] = a
+        return area_cache["a"]
 
     def vtkout(unit, tim, st):
         """VTKRIS3D (SRC/vtkris3d.f), called with unit 100 at time 0 and 100+KPRT at the detailed outputs when IPRT >= 2 and
@@ -126,6 +154,27 @@ def run_processor(project_dir: str, lib: CathyLib | None = None, write_files: bo
         if parm["NUMVP"] > 0:
             O.write_vp(fh["vp"], nstep, tim, parm["NODVP"], nnod, nstr, x, y, z, st["psi"], st["sw"], st["ckrw"],
                        st["qtranie"])
+        # SRC/detout.f:34-43 velocities, :99-122 surface tables (psisurf, satsurf, swsurf, recharge, fort.777)
+        vel = None
+        if parm["IPRT"] >= 2 and ("velnod" in fh or "velelt" in fh):
+            vel = sim.velocity(nodal=True)
+            if "velnod" in fh and parm["IPRT"] >= 1:
+                O.write_velnod(fh["velnod"], nstep, tim, vel["unod"], vel["vnod"], vel["wnod"])
+            if "velelt" in fh and parm["IPRT"] >= 4:
+                O.write_velelt(fh["velelt"], tim, vel["uu"], vel["vv"], vel["ww"])
+        psi2 = st["psi"].reshape(nstr + 1, nnod)
+        satsur = np.where(psi2[0] >= 0.0, np.where(np.any(psi2[1:] < 0.0, axis=0), 2, 3), 1)
+        eta = st["qtranie"].reshape(nstr + 1, nnod)
+        etasum = np.zeros(nnod)
+        for k in range(nstr + 1):
+            etasum = etasum + eta[k]
+        rec = sim.recharge()[0] if parm["IPRT"] >= 2 else np.zeros(nnod)
+        area = arenod()
+        for key, title, vals, integer in (("psisurf", "PRESSURE HEAD", psi2[0], False), ("satsurf", "SATSUR", satsur, True),
+                                          ("swsurf", "SW", st["sw"][:nnod], False), ("recharge", "REC. FLUX", rec / area, False),
+                                          ("fort777", "ACT. ETRA", etasum / area, False)):
+            if key in fh:
+                O.write_surface_table(fh[key], nstep, tim, title, x, y, vals, integer)
 
     detout(0, 0.0, vtk_unit=100)
     res.wall_setup = time.perf_counter() - t_start
@@ -133,6 +182,7 @@ def run_processor(project_dir: str, lib: CathyLib | None = None, write_files: bo
     cum = dict(VSFTOT=0.0, VNDTOT=0.0, VNNTOT=0.0, VNUDTOT=0.0, VTOT=0.0, CVIN=0.0, CVOUT=0.0, CDSTOR=0.0,
                CERRAS=0.0, CAERAS=0.0)
     kprt = 1
+    tot = dict(recvol=0.0, dtc_head=False, cpusub=0.0, vapot=0.0, vaact=0.0, nsurf=0, nsurft=0)
     nprt, timprt = parm["NPRT"], parm["TIMPRT"]
     last = None
     while True:
@@ -173,6 +223,29 @@ def run_processor(project_dir: str, lib: CathyLib | None = None, write_files: bo
                                                      cum["VNNTOT"], cum["VNUDTOT"], cum["VTOT"]))
             if parm["ISIMGR"] == 2:
                 fh["hgraph"].write("".join(O.fe(v, 16, 8) for v in (rep.time, rep.q_outlet_1, rep.q_outlet_2, 0.0, 0.0)) + "\n")
+            # SRC/cathy_main.f:3628, 3658-3695: water-table depth, recharge, detailed hydrograph files, coupling diagnostics
+            if parm["NUMVP"] > 0 and "wtdepth" in fh:
+                fh["wtdepth"].write(O.wtdepth_line(rep.time, sim.wtdepth(parm["NODVP"])))
+            recflow = sim.recharge()[1] if (parm["IPRT"] >= 2 and "hgatmsf" in fh) else 0.0
+            tot["recvol"] += recflow * rep.deltat
+            if "hgatmsf" in fh:
+                fh["hgatmsf"].write(O.hgatmsf_line(rep, recflow, tot["recvol"]))
+            if "hgnansf" in fh:
+                fh["hgnansf"].write(O.hgnansf_line(rep))
+            for key, vol in (("hgsfdet", rep.vsfflw), ("hgnansfdirdet", rep.vndin + rep.vndout), ("hgnansfneudet", rep.vnnin + rep.vnnout)):
+                if key in fh:
+                    fh[key].write(O.det_line(rep, vol))
+            if "dtcoupling" in fh:
+                if not tot["dtc_head"]:
+                    fh["dtcoupling"].write(O.dtcoupling_header(parm["ISIMGR"] == 2, nnod, prj.nrow * prj.ncol, rep.areatot))
+                    tot["dtc_head"] = True
+                cpusub = time.perf_counter() - t0
+                fh["dtcoupling"].write(O.dtcoupling_line(rep, parm["ITUNS"], cpusub, 0.0))
+                tot["cpusub"] += cpusub
+                tot["vapot"] += rep.apot * rep.deltat
+                tot["vaact"] += 0.5 * (rep.aact + rep.aact_prev) * rep.deltat
+                tot["nsurf"] += rep.nsurf
+                tot["nsurft"] += rep.nsurft
         if verbose:
             print(" TIME STEP: %6d  DELTAT: %12.4E  TIME: %12.4E  NL its %2d  lin its %4d  back-steps %d"
                   % (rep.nstep, rep.deltat, rep.time, rep.iter, rep.nitert, rep.kbackt), flush=True)
@@ -188,6 +261,12 @@ def run_processor(project_dir: str, lib: CathyLib | None = None, write_files: bo
     if max_steps is None:
         detout(last.nstep, parm["TMAX"], vtk_unit=100 + kprt)   # label 300: final DETOUT always carries TIME=TMAX
     res.final_state = sim.state()
+    if write_files and last is not None:
+        if "dtcoupling" in fh and tot["dtc_head"]:
+            fh["dtcoupling"].write(O.dtcoupling_footer(last.kback_total, last.itrtot, parm["ITUNS"], tot["nsurf"], tot["nsurft"], tot["vapot"],
+                                                       tot["vaact"], last.areatot, tot["cpusub"], 0.0))
+        if "hgflag" in fh:
+            fh["hgflag"].write(O.hgflag_text(list(last.hgflag)))
     for f in fh.values():
         f.close()
     res.wall_io += time.perf_counter() - t1

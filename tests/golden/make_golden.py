@@ -25,6 +25,8 @@ KEEP_PREPRO = ["dem", "zone", "lakes_map", "qoi_a", "dtm_w_1", "dtm_w_2", "dtm_p
                "dtm_local_slope_1", "dtm_local_slope_2", "dtm_epl_1", "dtm_epl_2", "dtm_kSs1_sf_1", "dtm_kSs1_sf_2",
                "dtm_Ws1_sf_1", "dtm_Ws1_sf_2", "dtm_b1_sf", "dtm_y1_sf", "dtm_nrc", "hap.in"]
 VERBATIM = ["mbeconv", "cumflowvol", "hgraph", "vp"]
+AUX = ["hgatmsf", "hgnansf", "hgsfdet", "hgnansfdirdet", "hgnansfneudet", "wtdepth", "recharge", "fort.777", "psisurf", "satsurf", "swsurf",
+       "velnod", "velelt", "hgflag", "dtcoupling"]
 
 
 def read_blocks(path):
@@ -117,6 +119,10 @@ def vtk():
     oracle.run_reference(tmp, tmp + "_ref", "20x20x15")
     dst = os.path.join(HERE, "vtk6")
     stash(tmp, os.path.join(tmp + "_ref", "output"), dst)
+    for f in AUX:            # auxiliary outputs of the same run (SRC/detout.f, SRC/cathy_main.f:3628-3695)
+        src = os.path.join(tmp + "_ref", f if f == "fort.777" else os.path.join("output", f))
+        with open(src, "rb") as fi, gzip.GzipFile(os.path.join(dst, "golden", f + ".gz"), "wb", mtime=0) as fo:
+            fo.write(fi.read())
     for f in sorted(os.listdir(os.path.join(tmp + "_ref", "vtk"))):
         with open(os.path.join(tmp + "_ref", "vtk", f), "rb") as fi, gzip.GzipFile(os.path.join(dst, "golden", f + ".gz"), "wb", mtime=0) as fo:
             fo.write(fi.read())
