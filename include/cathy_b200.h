@@ -242,6 +242,10 @@ int32_t cathy_enkf_update(const double *dX, const double *dP, const double *dL, 
                           const double *dB_local, const double *d_mean, const double *d_bbar, double inflate,
                           int64_t n_infl, double inflate2, int64_t n, int32_t ne_local, int32_t m, double *dXa,
                           uint64_t stream);
+/* Gaspari-Cohn localisation matrix (pyCATHY/DA/localisation.py:136-188 gaspari_cohn, build_localization_matrix):
+ * L[i][k] = gc(|grid_i - obs_k| / radius) with 2-D positions; DEVICE pointers grid_xy [n][2], obs_xy [m][2], L [n][m]. */
+int32_t cathy_enkf_localization(const double *d_grid_xy, int64_t n, const double *d_obs_xy, int32_t m, double radius,
+                                double *dL, uint64_t stream);
 /* Particle filter (pf.py:60-110): normalised weights [ne] and n_eff from HX [m][ne], y [m], obs_std [m];
  * host buffers. */
 int32_t cathy_pf_weights(const double *hx, const double *y, const double *obs_std, int32_t m, int32_t ne,

@@ -5,6 +5,7 @@ Plain-numpy restatement of the arithmetic in
   * /root/reference/pyCATHY/DA/enkf.py:225-342  ``enkf_analysis_localized_with_inflation``
   * /root/reference/pyCATHY/DA/pf.py:3-110      ``particle_filter_analysis`` (weights, n_eff, resampling; no jitter)
   * /root/reference/pyCATHY/DA/pf.py:197-211    ``systematic_resample``
+  * /root/reference/pyCATHY/DA/localisation.py:136-188  ``gaspari_cohn``, ``build_localization_matrix``
 Parity is PINNED: tests/golden/enkf_golden.npz holds outputs of the reference's own functions (module loaded from
 /root/reference with matplotlib stubbed, see tests/golden/make_golden_enkf.py) and tests/test_enkf_oracle.py checks
 this file against them.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module;
@@ -121,3 +122,26 @@ def particle_filter_analysis(data, data_cov, param, ensemble, observation, resam
         weights_out = weights
     return {"Analysis": ensemble, "Analysisparam": param, "weights": weights_out, "raw_weights": weights, "n_eff": n_eff,
             "resampled": resampled, "observation": observation, "indices": indices}
+
+
+def gaspari_cohn(r, L):
+    """/root/reference/pyCATHY/DA/localisation.py:136-152 (verbatim arithmetic)."""
+    r = np.abs(r) / L
+    w = np.zeros_like(r)
+    mask1 = r <= 1
+    mask2 = (r > 1) & (r <= 2)
+    w[mask1] = (((-0.25 * r[mask1] + 0.5) * r[mask1] + 0.625) * r[mask1] - 5 / 3) * r[mask1] ** 2 + 1
+    w[mask2] = ((((r[mask2] / 12 - 0.5) * r[mask2] + 0.625) * r[mask2] + 5 / 3) * r[mask2] - 5) * r[mask2] + 4 - 2 / (3 * r[mask2])
+    w[r > 2] = 0
+    return w
+
+
+def build_localization_matrix(obs_pos, grid_pos, L):
+    """/root/reference/pyCATHY/DA/localisation.py:155-188."""
+    n_grid, n_obs = grid_pos.shape[0], obs_pos.shape[0]
+    loc = np.zeros((n_grid, n_obs))
+    for i in range(n_grid):
+        dx = obs_pos[:, 0] - grid_pos[i, 0]
+        dy = obs_pos[:, 1] - grid_pos[i, 1]
+        loc[i, :] = gaspari_cohn(np.sqrt(dx ** 2 + dy ** 2), L)
+    return loc

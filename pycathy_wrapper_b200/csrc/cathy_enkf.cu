@@ -294,6 +294,25 @@ __global__ void k_pf_gather(long long n, int ne, const double *__restrict__ X, c
     }
 }
 
+// Gaspari-Cohn localisation matrix (pyCATHY/DA/localisation.py:136-188): L[i][k] = gc(|grid_i - obs_k| / radius), 2-D distances
+__device__ __forceinline__ double gaspari_cohn(double d, double radius)
+{
+    double r = fabs(d) / radius;
+    if (r <= 1.0) return (((-0.25 * r + 0.5) * r + 0.625) * r - 5.0 / 3.0) * (r * r) + 1.0;
+    if (r <= 2.0) return ((((r / 12.0 - 0.5) * r + 0.625) * r + 5.0 / 3.0) * r - 5.0) * r + 4.0 - 2.0 / (3.0 * r);
+    return 0.0;
+}
+__global__ void k_enkf_localization(long long n, int m, const double *__restrict__ gxy, const double *__restrict__ oxy, double radius,
+                                    double *__restrict__ L)
+{
+    long long tot = n * m;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+        long long i = e / m; int k = (int)(e - i * m);
+        double dx = oxy[2 * k] - gxy[2 * i], dy = oxy[2 * k + 1] - gxy[2 * i + 1];
+        L[e] = gaspari_cohn(sqrt(dx * dx + dy * dy), radius);
+    }
+}
+
 extern "C" {
 
 // S, D=B on output.  hx [m][ne], y [m] (y_ld = 0) or [m][ne] (y_ld = ne), R [m][m]; host pointers.
@@ -449,6 +468,17 @@ int32_t cathy_pf_gather_members(const double *dX, int64_t n, int32_t ne, const i
     if (dX == dXout) EFAIL(-1, "cathy_pf_gather_members: output must not alias the input");
     int blocks = (int)std::min<int64_t>((n * ne + 255) / 256, 148 * 16);
     k_pf_gather<<<std::max(blocks, 1), 256, 0, (cudaStream_t)stream>>>(n, ne, dX, d_idx, dXout);
+    ECK(cudaGetLastError());
+    return 0;
+}
+
+
+// DEVICE pointers: grid_xy [n][2], obs_xy [m][2] -> L [n][m]
+int32_t cathy_enkf_localization(const double *d_grid_xy, int64_t n, const double *d_obs_xy, int32_t m, double radius, double *dL, uint64_t stream)
+{
+    if (!(radius > 0.0)) EFAIL(-1, "cathy_enkf_localization: the localisation radius must be positive");
+    int blocks = (int)std::min<int64_t>((n * m + 255) / 256, 148 * 16);
+    k_enkf_localization<<<std::max(blocks, 1), 256, 0, (cudaStream_t)stream>>>(n, m, d_grid_xy, d_obs_xy, radius, dL);
     ECK(cudaGetLastError());
     return 0;
 }

@@ -33,7 +33,7 @@ def _dp(a):
 
 class EnkfLib:
     SYMBOLS = ["enkf_last_error", "enkf_analysis_host", "enkf_gain", "enkf_rowsum", "enkf_scale", "enkf_crosscov",
-               "enkf_update", "pf_weights", "pf_systematic_resample", "pf_gather_members"]
+               "enkf_update", "enkf_localization", "pf_weights", "pf_systematic_resample", "pf_gather_members"]
 
     def __init__(self, path: str):
         import os
@@ -57,6 +57,7 @@ class EnkfLib:
         f["enkf_scale"].argtypes = [V, I64, DBL, U64]
         f["enkf_crosscov"].argtypes = [V, V, V, I64, I32, I32, I32, V, U64]
         f["enkf_update"].argtypes = [V, V, V, I64, V, V, V, DBL, I64, DBL, I64, I32, I32, V, U64]
+        f["enkf_localization"].argtypes = [V, I64, V, I32, DBL, V, U64]
         f["pf_weights"].argtypes = [_D, _D, _D, I32, I32, _D, _D]
         f["pf_systematic_resample"].argtypes = [_D, I32, DBL, _I]
         f["pf_gather_members"].argtypes = [V, I64, I32, V, V, U64]
@@ -222,6 +223,25 @@ def particle_filter_analysis(data, data_cov, param, ensemble, observation, **kwa
                 param += np.random.randn(*param.shape) * jitter_std_param
     return {"Analysis": ensemble, "Analysisparam": param, "weights": weights, "n_eff": n_eff, "resampled": resampled,
             "observation": observation}
+
+
+def build_localization_matrix(obs_pos, grid_pos, L, device: int = 0, as_tensor: bool = False):
+    """Mirror of pyCATHY/DA/localisation.py:163-188 (Gaspari-Cohn weights between grid and observation positions, 2-D):
+    returns the (n_grid, n_obs) matrix -- a numpy array, or the device tensor when ``as_tensor`` (to feed
+    ``sharded_enkf_update(..., L=...)`` without a host round trip)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise CathyLibraryError("build_localization_matrix: no CUDA device (there is no CPU path)")
+    lib = load_enkf_library()
+    dev = torch.device("cuda", device)
+    g = torch.from_numpy(_f64(np.asarray(grid_pos)[:, :2])).to(dev)
+    o = torch.from_numpy(_f64(np.asarray(obs_pos)[:, :2])).to(dev)
+    out = torch.empty((g.shape[0], o.shape[0]), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        lib.check(lib.f["enkf_localization"](g.data_ptr(), g.shape[0], o.data_ptr(), o.shape[0], float(L), out.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream), "cathy_enkf_localization")
+        torch.cuda.current_stream().synchronize()
+    return out if as_tensor else out.cpu().numpy()
 
 
 def run_analysis(DA_type, data, data_cov, param, list_update_parm, ensembleX, prediction, default_state="psi", **kwargs):

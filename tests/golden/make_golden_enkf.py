@@ -68,6 +68,19 @@ def main():
         r = pf.particle_filter_analysis(y.copy(), Rpf2, theta.copy(), X.copy(), HX.copy(), jitter_std_param=0.0, jitter_std_state=0.0)
         out["pf2_R"] = Rpf2
         out["pf2_weights"], out["pf2_neff"], out["pf2_resampled"] = r["weights"], np.array(r["n_eff"]), np.array(r["resampled"])
+    # Gaspari-Cohn localisation (localisation.py imports the pyCATHY package at module level, which cannot be imported here:
+    # its two pure-numpy functions are extracted from the source text and executed as they are)
+    src = open("/root/reference/pyCATHY/DA/localisation.py").read()
+    ns = {"np": np}
+    for name in ("gaspari_cohn", "build_localization_matrix"):
+        i = src.index("def %s(" % name)
+        j = src.index("\ndef ", i + 1) if "\ndef " in src[i + 1:] else len(src)
+        exec(src[i:j], ns)
+    grid = np.column_stack([rng.uniform(0, 10, 200), rng.uniform(0, 10, 200)])
+    obs = np.column_stack([rng.uniform(0, 10, 9), rng.uniform(0, 10, 9)])
+    obs[0] = grid[0]
+    out["gc_grid"], out["gc_obs"], out["gc_radius"] = grid, obs, np.array(1.7)
+    out["gc_matrix"] = ns["build_localization_matrix"](obs, grid, 1.7)
     np.savez_compressed(os.path.join(HERE, "enkf_golden.npz"), **out)
     print("enkf golden written:", {k: v.shape for k, v in out.items()})
 

@@ -59,3 +59,9 @@ def test_enkf_library_exports_declared_symbols():
     assert len(names) >= 10
     for nm in names:
         assert hasattr(lib.lib, nm), nm
+
+
+def test_gaspari_cohn_localisation(g):
+    from oracle import enkf_oracle as o
+    L = o.build_localization_matrix(g["gc_obs"], g["gc_grid"], float(g["gc_radius"]))
+    assert np.array_equal(L, g["gc_matrix"]) and L[0, 0] == 1.0 and L.min() == 0.0

@@ -162,3 +162,12 @@ def test_set_soil_equals_fresh_handle(gpu_lib):
     ta, ja, ca, ra = a.debug_assemble(2.0)
     tb, jb, cb, rb = b.debug_assemble(2.0)
     assert np.array_equal(ja, jb) and np.array_equal(ca, cb) and np.array_equal(ra, rb)
+
+
+def test_gaspari_cohn_localisation_matches_reference_golden(gpu_lib, g):
+    from pycathy_wrapper_b200 import da
+    L = da.build_localization_matrix(g["gc_obs"], g["gc_grid"], float(g["gc_radius"]))
+    assert L.shape == g["gc_matrix"].shape
+    assert np.max(np.abs(L - g["gc_matrix"])) <= 1e-14
+    Lt = da.build_localization_matrix(g["gc_obs"], g["gc_grid"], float(g["gc_radius"]), as_tensor=True)
+    assert Lt.is_cuda and np.array_equal(Lt.cpu().numpy(), L)
