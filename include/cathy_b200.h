@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CATHY_ABI_VERSION 3
+#define CATHY_ABI_VERSION 4
 #define CATHY_MAXIT 64 /* upper bound on ITUNS kept in a step report (CATHY.H MAXIT=30) */
 
 /* Everything DATIN / INITAL read from the project files (SRC/datin.f:80-514,
@@ -94,6 +94,9 @@ typedef struct CathyProblem {
      * GLOBAL.  The handle builds its window (owned rows + 2 ghost node rows per interior side), and the
      * ranks exchange halo rows and reduction scalars through peer memory (cathy_dd_export/connect). */
     int32_t dd_world, dd_rank, dd_row0, dd_row1;
+    /* --- moisture-curve parameters of the Huyakorn (IVGHU = 2, 3) and Brooks-Corey (IVGHU = 4) models, read from the header
+     * of input/soil (SRC/datin.f:440-458; constants derived in SRC/chparm.f:79-106) */
+    double hualfa, hubeta, hugama, hupsia, huswr, hun, hua, hub, bcbeta, bcrmc, bcpsat;
 } CathyProblem;
 
 /* One nonlinear iteration line of output/iter (SRC/conver.f:44 FORMAT 1070). */

@@ -12,7 +12,7 @@ import numpy as np
 
 from .project import CathyProject
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAXIT = 64
 _D = C.POINTER(C.c_double)
 _I = C.POINTER(C.c_int32)
@@ -59,6 +59,8 @@ class CathyProblem(C.Structure):
         ("precond", C.c_int32), ("device", C.c_int32),
         ("tolcg_scale", C.c_double),
         ("dd_world", C.c_int32), ("dd_rank", C.c_int32), ("dd_row0", C.c_int32), ("dd_row1", C.c_int32),
+        ("hualfa", C.c_double), ("hubeta", C.c_double), ("hugama", C.c_double), ("hupsia", C.c_double), ("huswr", C.c_double),
+        ("hun", C.c_double), ("hua", C.c_double), ("hub", C.c_double), ("bcbeta", C.c_double), ("bcrmc", C.c_double), ("bcpsat", C.c_double),
     ]
 
 
@@ -172,6 +174,10 @@ class ProblemHolder:
             s.dd_world, s.dd_rank, s.dd_row0, s.dd_row1 = (int(v) for v in dd)
         else:
             s.dd_world, s.dd_rank, s.dd_row0, s.dd_row1 = 1, 0, 0, prj.nrow + 1
+        hu, huab, bc = prj.soil.get("HU", [0.0] * 5), prj.soil.get("HUAB", [0.0, 0.0]), prj.soil.get("BC", [0.0] * 3)
+        s.hualfa, s.hubeta, s.hugama, s.hupsia, s.huswr = (float(v) for v in hu)
+        s.hun, s.hua, s.hub = float(prj.soil.get("HUN", 0.0)), float(huab[0]), float(huab[1])
+        s.bcbeta, s.bcrmc, s.bcpsat = (float(v) for v in bc)
         self.struct = s
 
 

@@ -124,6 +124,67 @@ __device__ __forceinline__ double fvgdse(double psi, double psat, double n, doub
     return 0.0;
 }
 
+// Huyakorn (IVGHU = 2, 3) and Brooks-Corey (IVGHU = 4) models: global parameters, constants of SRC/chparm.f:79-106
+struct CurveModel {
+    int ivghu;
+    double hupsia, hubeta, hugama, huswr, huswr1, hualb, hugam1, hugb, hun, hua, hub2a, huab;
+    double bcpsat, bcbeta, bcrmc, bcb1, bcbps, bc23b;
+};
+// SRC/fhuse.f, fhudse.f, fhukr2.f, fhukr3.f, fbcse.f, fbcdse.f, fbckr.f: saturation sw, kr and d(sw)/d(psi) of one node
+__device__ __forceinline__ void curve_alt(const CurveModel &c, double psi, double pnodi, double &sw, double &kr, double &dsw, bool need_d)
+{
+    if (c.ivghu == 4) {
+        const double porm = (pnodi - c.bcrmc) / pnodi;
+        if (psi < c.bcpsat) {
+            const double q = fabs(c.bcpsat / psi);
+            sw = porm * pow(q, c.bcbeta) + c.bcrmc / pnodi;
+            kr = pow(q, c.bc23b);
+            dsw = need_d ? porm * (c.bcbps * pow(q, c.bcb1)) : 0.0;
+        } else { sw = porm * 1.0 + c.bcrmc / pnodi; kr = 1.0; dsw = need_d ? porm * 0.0 : 0.0; }
+        return;
+    }
+    if (psi < c.hupsia) {
+        const double pap = c.hupsia - psi, lambda = c.hualb * pow(pap, c.hubeta), lamr = 1.0 / (1.0 + lambda);
+        const double se = pow(lamr, c.hugama);
+        sw = c.huswr1 * se + c.huswr;
+        kr = c.ivghu == 2 ? pow(se, c.hun) : pow(10.0, c.hua * se * se + c.hub2a * se + c.huab);
+        dsw = need_d ? c.huswr1 * ((c.hugb * lambda / pap) * pow(lamr, c.hugam1)) : 0.0;
+    } else { sw = c.huswr1 * 1.0 + c.huswr; kr = 1.0; dsw = need_d ? c.huswr1 * 0.0 : 0.0; }
+}
+// CHPIC0 for IVGHU = 2, 3, 4 (SRC/chpic0.f:51-99)
+__global__ void k_curves_alt(int n, CurveModel c, const double *__restrict__ snodi, const double *__restrict__ pnodi, const double *__restrict__ ptnew,
+                             const double *__restrict__ pnew, const double *__restrict__ ptimep, int do_timep, double *__restrict__ sw,
+                             double *__restrict__ ckrw, double *__restrict__ et1, double *__restrict__ et2, double *__restrict__ swnew,
+                             double *__restrict__ swtimep)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double po = pnodi[i], sn = snodi[i], psi = ptnew[i];
+        double w, kr, dsw, dum1, dum2;
+        curve_alt(c, psi, po, w, kr, dsw, true);
+        const double etai = w * sn + po * dsw;
+        sw[i] = w; ckrw[i] = kr;
+        et1[i] = w * sn;
+        et2[i] = (etai - w * sn) / po;
+        const double pn = pnew[i];
+        if (pn == psi) swnew[i] = w; else { curve_alt(c, pn, po, w, dum1, dum2, false); swnew[i] = w; }
+        if (do_timep) { curve_alt(c, ptimep[i], po, w, dum1, dum2, false); swtimep[i] = w; }
+    }
+}
+__global__ void k_chvelo_alt(int n, CurveModel c, const double *__restrict__ pnodi, const double *__restrict__ psiv, const double *__restrict__ volnod,
+                             double *__restrict__ sw, double *__restrict__ ckrw, double *__restrict__ partial, const unsigned char *__restrict__ own)
+{
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double w, kr, d;
+        curve_alt(c, psiv[i], pnodi[i], w, kr, d, false);
+        sw[i] = w; ckrw[i] = kr;
+        if (!own || (own[i] & 1)) acc += w * volnod[i] * pnodi[i];
+    }
+    double t = block_sum<RED_BLOCK>(acc, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
 // ------------------------------------------------------------------------------------------
 // K1: moisture curves per node (PICUNS -> CHPIC0, SRC/picuns.f:22-48, SRC/chpic0.f:23-36)
 // ------------------------------------------------------------------------------------------
@@ -1885,6 +1946,7 @@ struct CathySim {
     std::vector<double> hx, hy, hz, harenod;
     std::vector<double> h_dem, h_root, h_zratio, h_veg;   // owned copies of the caller's mesh inputs (cathy_set_soil rebuilds from them)
     std::vector<int32_t> h_zone;
+    CurveModel cm;                  // Huyakorn / Brooks-Corey constants (ivghu = 0: unused)
     double areatot = 0.0;           // AREATOT (SRC/inital.f:131-134), sequential sum over the (global) surface nodes
     std::vector<double> h_perm;     // permx | permy | permz tables as last built ([nstr][nzone] each)
     std::vector<int> htri;       // [ntri*4] sorted nodes + zone
@@ -2421,6 +2483,9 @@ static void weight_and_copy(CathySim *S)
 // chvelo + storage sum -> returns STORE1 through h_step later; here just launches
 static void chvelo_launch(CathySim *S, const double *psi)
 {
+    if (S->cm.ivghu != 0)
+        LAUNCH(S, k_chvelo_alt, S->grid_n, RED_BLOCK, S->n, S->cm, S->pnodi.p, psi, S->volnod.p, S->sw.p, S->ckrw.p, S->store_part.p, S->dd ? S->own.p : (const unsigned char *)nullptr);
+    else
     LAUNCH(S, k_chvelo, S->grid_n, RED_BLOCK, S->n, make_soil(S), psi, S->volnod.p, S->sw.p, S->ckrw.p, S->store_part.p, S->dd ? S->own.p : (const unsigned char *)nullptr);
 }
 static int step_final_sync(CathySim *S, double *extra3 = nullptr)
@@ -2447,6 +2512,10 @@ static int assemble_system(CathySim *S, double deltat)
     const int n = S->n;
     S->scaled = false;
     Diag A = make_diag(S, S->A.p);
+    if (S->cm.ivghu != 0)
+        LAUNCH(S, k_curves_alt, nblk(n, S->grid_n), RED_BLOCK, n, S->cm, S->snodi.p, S->pnodi.p, S->ptnew.p, S->pnew.p, S->ptimep.p, S->timep_dirty, S->sw.p, S->ckrw.p,
+               S->et1.p, S->et2.p, S->swnew.p, S->swtimep.p);
+    else
     LAUNCH(S, k_curves, nblk(n, S->grid_n), RED_BLOCK, n, make_soil(S), S->ptnew.p, S->pnew.p, S->ptimep.p, S->timep_dirty, S->sw.p, S->ckrw.p, S->et1.p, S->et2.p, S->swnew.p, S->swtimep.p);
     S->timep_dirty = 0;
     LAUNCH(S, k_tet_avg, nblk(S->nt, 4 * S->grid_n), RED_BLOCK, S->nt, S->tet.p, S->ckrw.p, S->et1.p, S->krt.p, S->e1t.p);
@@ -2799,7 +2868,7 @@ static int preload_kernels()
                          (const void *)k_switch_old, (const void *)k_adrstn, (const void *)k_pondupd, (const void *)k_atm_interp, (const void *)k_etran,
                          (const void *)k_div_area, (const void *)k_nod_cell, (const void *)k_cell_nod, (const void *)k_route, (const void *)k_pond_zero,
                          (const void *)k_step_partial, (const void *)k_step_final, (const void *)k_weight, (const void *)k_atmone, (const void *)k_mbinit,
-                         (const void *)k_pack_col, (const void *)k_unpack_col, (const void *)k_vel3d, (const void *)k_vnod3d, (const void *)k_recharge, (const void *)k_wtdepth};
+                         (const void *)k_pack_col, (const void *)k_unpack_col, (const void *)k_vel3d, (const void *)k_vnod3d, (const void *)k_recharge, (const void *)k_wtdepth, (const void *)k_curves_alt, (const void *)k_chvelo_alt};
     for (const void *f : fns) CK(cudaFuncGetAttributes(&at, f));
     done = true;
     return 0;
@@ -2872,6 +2941,13 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
     S->nnod = (int)nnod; S->n = (int)n; S->ntri = 2 * p.nrow * p.ncol; S->nt = (int)nt; S->ncell = p.nrow * p.ncol;
     S->surf = p.isimgr == 2;
     S->newton = p.iopt == 2;
+    {   // SRC/chparm.f:79-106
+        CurveModel &c = S->cm;
+        c.ivghu = p.ivghu; c.hupsia = p.hupsia; c.hubeta = p.hubeta; c.hugama = p.hugama; c.huswr = p.huswr; c.huswr1 = 1.0 - p.huswr;
+        c.hualb = std::pow(p.hualfa, (double)(int)p.hubeta); c.hugam1 = p.hugama + 1.0; c.hugb = p.hugama * p.hubeta; c.hun = p.hun; c.hua = p.hua;
+        c.hub2a = p.hub - 2.0 * p.hua; c.huab = p.hua - p.hub;
+        c.bcpsat = p.bcpsat; c.bcbeta = p.bcbeta; c.bcrmc = p.bcrmc; c.bcb1 = p.bcbeta + 1.0; c.bcbps = p.bcbeta / std::fabs(p.bcpsat); c.bc23b = 2.0 + (3.0 * p.bcbeta);
+    }
     {
         double *t = new double[std::max(prob->natm, 1)];
         for (int i = 0; i < prob->natm; ++i) t[i] = prob->atm_time[i];
@@ -3097,7 +3173,9 @@ int32_t cathy_create(const CathyProblem *prob, CathySim **out)
     if (prob->iopt != 1 && prob->iopt != 2) FAIL(-2, "IOPT=%d: must be 1 (Picard) or 2 (Newton)", prob->iopt);
     if (prob->iopt == 2 && prob->tetaf != 1.0 && prob->tetaf <= 0.0) FAIL(-2, "TETAF must be positive");
     if (prob->kslope != 0) FAIL(-2, "KSLOPE=%d: only analytical moisture-curve derivatives (0) are implemented", prob->kslope);
-    if (prob->ivghu != 0) FAIL(-2, "IVGHU=%d: only van Genuchten curves (0) are implemented", prob->ivghu);
+    if (!(prob->ivghu == 0 || (prob->ivghu >= 2 && prob->ivghu <= 4)))
+        FAIL(-2, "IVGHU=%d: van Genuchten (0), Huyakorn (2, 3) and Brooks-Corey (4) curves are implemented; extended van Genuchten (1) and look-up tables (-1) are not", prob->ivghu);
+    if (prob->ivghu != 0 && prob->iopt != 1) FAIL(-2, "IVGHU=%d with the Newton scheme is not implemented (Picard only)", prob->ivghu);
     if (prob->lump == 0) FAIL(-2, "LUMP=0 (consistent mass matrix) is not implemented on the device");
     if (prob->nlrelx != 0) FAIL(-2, "NLRELX != 0 (nonlinear relaxation) is not implemented on the device");
     if (prob->isimgr != 1 && prob->isimgr != 2) FAIL(-2, "ISIMGR=%d not supported", prob->isimgr);

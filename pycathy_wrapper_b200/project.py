@@ -425,8 +425,8 @@ def load_project(prj: str) -> CathyProject:
     P.soil = soil
     if soil["IPEAT"] != 0:
         raise CathyInputError("IPEAT=1 (peat deformation) is outside the hot-path scope")
-    if soil["IVGHU"] != 0:
-        raise CathyInputError(f"IVGHU={soil['IVGHU']}: only van Genuchten (0) is implemented")
+    if soil["IVGHU"] not in (0, 2, 3, 4):
+        raise CathyInputError(f"IVGHU={soil['IVGHU']}: van Genuchten (0), Huyakorn (2, 3) and Brooks-Corey (4) are implemented")
 
     # ---- atmbc (SRC/atmone.f, SRC/atmnxt.f)
     rd = ListDirectedReader(fn["IIN6"])

@@ -139,7 +139,8 @@ def write_hapin(path: str, nrow: int, ncol: int, dx: float, dy: float) -> None:
 
 def make_project(path: str, nrow: int, ncol: int, nstr: int, dx: float = 0.5, dy: float = 0.5, base: float = 3.0,
                  zratio=None, dem=None, soil_rows=None, ic=("uniform", -1.0), atmbc=None, hspatm: int = 1, ieto: int = 0,
-                 pmin: float = -5.0, dirbc_text: str | None = None, neubc_text: str | None = None, **parm) -> str:
+                 pmin: float = -5.0, dirbc_text: str | None = None, neubc_text: str | None = None, ivghu: int = 0,
+                 hu=(0.02, 2, 2, 0, 0.333), hun=1, huab=(-5, 1), bc=(1.2, 0, -0.345), **parm) -> str:
     """Write a full project directory.  `ic` = ("uniform", psi) | ("hydrostatic",) | ("wt", position);
     `atmbc` = list of (time, rate) pairs (homogeneous) -- rate in m/s, +ve = rain."""
     for sub in ("input", "prepro", "output", "vtk"):
@@ -166,8 +167,9 @@ def make_project(path: str, nrow: int, ncol: int, nstr: int, dx: float = 0.5, dy
     rows = soil_rows if soil_rows is not None else [DEFAULT_SOIL_ROW] * nstr
     with open(os.path.join(path, "input", "soil"), "w") as fh:
         fh.write("%r\tPMIN\n0 1.0\tIPEAT SCF\n0.4 0.225\tCBETA0,CANG\n" % pmin)
-        fh.write("0.0 -4.0 -150.0 1.0 1.0 1.0\tPCANA,PCREF,PCWLT,ZROOT,PZ,OMGC\n0\tIVGHU\n")
-        fh.write("0.02 2 2 0 0.333\tHUALFA,HUBETA,HUGAMA,HUPSIA,HUSWR\n1\tHUN\n-5 1\tHUA,HUB\n1.2 0 -0.345\tBCBETA,BCRMC,BCPSAT\n")
+        fh.write("0.0 -4.0 -150.0 1.0 1.0 1.0\tPCANA,PCREF,PCWLT,ZROOT,PZ,OMGC\n%d\tIVGHU\n" % ivghu)
+        fh.write("%r %r %r %r %r\tHUALFA,HUBETA,HUGAMA,HUPSIA,HUSWR\n%r\tHUN\n%r %r\tHUA,HUB\n%r %r %r\tBCBETA,BCRMC,BCPSAT\n"
+                 % (*hu, hun, *huab, *bc))
         for r in rows:
             fh.write(" ".join("%.6E" % v for v in r) + "\n")
     with open(os.path.join(path, "input", "ic"), "w") as fh:
