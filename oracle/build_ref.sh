@@ -24,6 +24,7 @@ if [ -d "$REF" ]; then
   cp -f "$REF/examples/SSHydro/weill_exemple/cathy"                         "$OUT/bin/cathy_20x20x15"
   cp -f "$REF/examples/SSHydro/weil_exemple_outputs_plot/cathy"             "$OUT/bin/cathy_20x20x15_newton"
   cp -f "$REF/examplesTmp/SSHydro/ERA5_ETp_spatially_from_weill/cathy"      "$OUT/bin/cathy_100x50x15"
+  cp -f "$REF/examples/SSHydro/soil_withzones/cathy"                        "$OUT/bin/cathy_20x20x15_zones"   # MAXZON=4
   cp -f "$REF/examples/SSHydro/weill_exemple/prepro/pycppp"                 "$OUT/bin/pycppp"
   chmod +x "$OUT/bin/"*
 fi

@@ -38,7 +38,8 @@ def simulation(prj, **kw) -> Simulation:
     return Simulation(load(), prj, **kw)
 
 
-REF_BIN = {"20x20x15": "cathy_20x20x15", "20x20x15_newton": "cathy_20x20x15_newton", "100x50x15": "cathy_100x50x15"}
+REF_BIN = {"20x20x15": "cathy_20x20x15", "20x20x15_newton": "cathy_20x20x15_newton", "100x50x15": "cathy_100x50x15",
+           "20x20x15_zones": "cathy_20x20x15_zones"}
 
 
 def ref_available(which: str = "20x20x15") -> bool:

@@ -1245,7 +1245,7 @@ __global__ void k_norms(int n, int nnod, const double *__restrict__ pnew, const 
                         const double *__restrict__ swnew, const double *__restrict__ swtimep,
                         const double *__restrict__ volnod, const double *__restrict__ snodi,
                         const double *__restrict__ pnodi, const int *__restrict__ ifatm, const double *__restrict__ atmact,
-                        NormPartial *__restrict__ part, const unsigned char *__restrict__ own)
+                        NormPartial *__restrict__ part, const unsigned char *__restrict__ own, double omega)
 {
     __shared__ double sh[32];
     __shared__ double shv[RED_BLOCK / 32];
@@ -1254,7 +1254,9 @@ __global__ void k_norms(int n, int nnod, const double *__restrict__ pnew, const 
     int ik = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         if (own && !(own[k] & 1)) continue;      // row-block partition: ghost rows belong to another rank
-        double d = pnew[k] - pold[k], da = fabs(d), f = rhs[k];
+        // NLRELX = 1: the norms see the relaxed heads (SRC/relax.f runs between MASBAL and NORMS), the storage change below does not
+        const double pr = omega == 1.0 ? pnew[k] : (1.0 - omega) * pold[k] + omega * pnew[k];
+        double d = pr - pold[k], da = fabs(d), f = rhs[k];
         pl2 += d * d;
         fl2 += f * f;
         if (da > pinf || (da == pinf && k >= ik)) { pinf = da; ik = k; }
@@ -1722,6 +1724,12 @@ __global__ void k_step_final(int nbs, const StepPartial *__restrict__ spart, int
         for (int q = 0; q < 9; ++q) out->hgflag[q] = shi[q];
         out->nhort = shi[9]; out->ndunn = shi[10]; out->npond = shi[11]; out->nsat = shi[12];
     }
+}
+// RELAX with a constant factor (SRC/relax.f, NLRELX = 1): PNEW = (1 - OMEGA) POLD + OMEGA PNEW, after the mass balance and
+// before the convergence norms (SRC/flow3d.f:165-190)
+__global__ void k_relax(int n, double omega, const double *__restrict__ pold, double *__restrict__ pnew)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) pnew[k] = (1.0 - omega) * pold[k] + omega * pnew[k];
 }
 __global__ void k_weight(int n, double tetaf, const double *__restrict__ pnew, const double *__restrict__ ptimep, double *__restrict__ ptnew)
 {
@@ -2650,7 +2658,9 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
     }
     if (S->have_neu) LAUNCH(S, k_flux_sums, 1, RED_BLOCK, S->neu.anbc(), S->qlist.p, S->bcsum.p + 2);
     LAUNCH(S, k_norms, S->grid_n, RED_BLOCK, n, S->nnod, S->pnew.p, S->pold.p, S->rhs.p, S->ptimep.p, S->swnew.p, S->swtimep.p, S->volnod.p,
-           S->snodi.p, S->pnodi.p, S->ifatm.p, S->atmact.p, S->npart.p, S->dd ? S->own.p : (const unsigned char *)nullptr);
+           S->snodi.p, S->pnodi.p, S->ifatm.p, S->atmact.p, S->npart.p, S->dd ? S->own.p : (const unsigned char *)nullptr,
+           S->p.nlrelx == 1 ? S->p.omega : 1.0);
+    if (S->p.nlrelx == 1) LAUNCH(S, k_relax, nblk(n, S->grid_n), RED_BLOCK, n, S->p.omega, S->pold.p, S->pnew.p);
     LAUNCH(S, k_norms_final, 1, RED_BLOCK, S->grid_n, S->npart.p, S->pnew.p, S->pold.p, S->d_iter.p);
     if (S->dd) LAUNCH(S, k_dd_combine_iter, 1, 32, S->comm->ctx, S->d_iter.p, S->gnnod, S->grow0 * S->nc1);
     // atmospheric switching is evaluated every iteration when TOLSWI is large (SRC/conver.f:58-71); when it is
@@ -2868,7 +2878,7 @@ static int preload_kernels()
                          (const void *)k_switch_old, (const void *)k_adrstn, (const void *)k_pondupd, (const void *)k_atm_interp, (const void *)k_etran,
                          (const void *)k_div_area, (const void *)k_nod_cell, (const void *)k_cell_nod, (const void *)k_route, (const void *)k_pond_zero,
                          (const void *)k_step_partial, (const void *)k_step_final, (const void *)k_weight, (const void *)k_atmone, (const void *)k_mbinit,
-                         (const void *)k_pack_col, (const void *)k_unpack_col, (const void *)k_vel3d, (const void *)k_vnod3d, (const void *)k_recharge, (const void *)k_wtdepth, (const void *)k_curves_alt, (const void *)k_chvelo_alt};
+                         (const void *)k_pack_col, (const void *)k_unpack_col, (const void *)k_vel3d, (const void *)k_vnod3d, (const void *)k_recharge, (const void *)k_wtdepth, (const void *)k_curves_alt, (const void *)k_chvelo_alt, (const void *)k_relax};
     for (const void *f : fns) CK(cudaFuncGetAttributes(&at, f));
     done = true;
     return 0;
@@ -3177,7 +3187,7 @@ int32_t cathy_create(const CathyProblem *prob, CathySim **out)
         FAIL(-2, "IVGHU=%d: van Genuchten (0), Huyakorn (2, 3) and Brooks-Corey (4) curves are implemented; extended van Genuchten (1) and look-up tables (-1) are not", prob->ivghu);
     if (prob->ivghu != 0 && prob->iopt != 1) FAIL(-2, "IVGHU=%d with the Newton scheme is not implemented (Picard only)", prob->ivghu);
     if (prob->lump == 0) FAIL(-2, "LUMP=0 (consistent mass matrix) is not implemented on the device");
-    if (prob->nlrelx != 0) FAIL(-2, "NLRELX != 0 (nonlinear relaxation) is not implemented on the device");
+    if (prob->nlrelx != 0 && prob->nlrelx != 1) FAIL(-2, "NLRELX=%d: only no relaxation (0) and constant OMEGA (1) are implemented", prob->nlrelx);
     if (prob->isimgr != 1 && prob->isimgr != 2) FAIL(-2, "ISIMGR=%d not supported", prob->isimgr);
     if (prob->deltat >= 1.0e15) FAIL(-2, "steady-state runs (DELTAT>=1e15) are not implemented");
     if (prob->ituns > CATHY_MAXIT) FAIL(-2, "ITUNS larger than %d", CATHY_MAXIT);

@@ -183,6 +183,9 @@ def run_processor(project_dir: str, lib: CathyLib | None = None, write_files: bo
                CERRAS=0.0, CAERAS=0.0)
     kprt = 1
     tot = dict(recvol=0.0, dtc_head=False, cpusub=0.0, vapot=0.0, vaact=0.0, nsurf=0, nsurft=0)
+    if write_files and parm["IPRT"] >= 2 and "hgatmsf" in fh:
+        # recharge at the initial conditions already counts into RECVOL with the first DELTAT (SRC/cathy_main.f:2814, SRC/recharge.f:45)
+        tot["recvol"] = sim.recharge()[1] * float(parm["DELTAT"])
     nprt, timprt = parm["NPRT"], parm["TIMPRT"]
     last = None
     while True:

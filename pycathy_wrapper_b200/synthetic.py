@@ -140,7 +140,7 @@ def write_hapin(path: str, nrow: int, ncol: int, dx: float, dy: float) -> None:
 def make_project(path: str, nrow: int, ncol: int, nstr: int, dx: float = 0.5, dy: float = 0.5, base: float = 3.0,
                  zratio=None, dem=None, soil_rows=None, ic=("uniform", -1.0), atmbc=None, hspatm: int = 1, ieto: int = 0,
                  pmin: float = -5.0, dirbc_text: str | None = None, neubc_text: str | None = None, ivghu: int = 0,
-                 hu=(0.02, 2, 2, 0, 0.333), hun=1, huab=(-5, 1), bc=(1.2, 0, -0.345), **parm) -> str:
+                 hu=(0.02, 2, 2, 0, 0.333), hun=1, huab=(-5, 1), bc=(1.2, 0, -0.345), zone=None, ivert: int = 0, **parm) -> str:
     """Write a full project directory.  `ic` = ("uniform", psi) | ("hydrostatic",) | ("wt", position);
     `atmbc` = list of (time, rate) pairs (homogeneous) -- rate in m/s, +ve = rain."""
     for sub in ("input", "prepro", "output", "vtk"):
@@ -157,14 +157,16 @@ def make_project(path: str, nrow: int, ncol: int, nstr: int, dx: float = 0.5, dy
     zr = geometric_zratio(nstr) if zratio is None else np.asarray(zratio, dtype=np.float64)
     _raster(os.path.join(path, "prepro", "dem"), dem, "%.12E")
     np.savetxt(os.path.join(path, "prepro", "dtm_13.val"), dem, fmt="%.9f", delimiter="\t")
-    _raster(os.path.join(path, "prepro", "zone"), np.ones((nrow, ncol), dtype=int), "%d")
+    zone = np.ones((nrow, ncol), dtype=int) if zone is None else np.asarray(zone, dtype=int)
+    nzone = int(zone.max())
+    _raster(os.path.join(path, "prepro", "zone"), zone, "%d")
     _raster(os.path.join(path, "prepro", "lakes_map"), np.zeros((nrow, ncol), dtype=int), "%d")
     _raster(os.path.join(path, "input", "root_map"), np.ones((nrow, ncol), dtype=int), "%d")
     write_hapin(os.path.join(path, "prepro", "hap.in"), nrow, ncol, dx, dy)
     with open(os.path.join(path, "input", "dem_parameters"), "w") as fh:
-        fh.write("%r\n%r\n1.0\n1\n1\t%d\t25\n0\t1\t%r\n%s\n" % (dx, dy, nstr, base, "\t".join(repr(float(v)) for v in zr)))
+        fh.write("%r\n%r\n1.0\n1\n%d\t%d\t25\n%d\t1\t%r\n%s\n" % (dx, dy, nzone, nstr, ivert, base, "\t".join(repr(float(v)) for v in zr)))
         fh.write("delta_x\ndelta_y\nfactor\ndostep\nnzone\tnstr\tn1\nivert\tisp\tbase\nzratio(i),i=1,nstr\n")
-    rows = soil_rows if soil_rows is not None else [DEFAULT_SOIL_ROW] * nstr
+    rows = soil_rows if soil_rows is not None else [DEFAULT_SOIL_ROW] * (nstr * nzone)     # layer-major: all zones of layer 1, then layer 2, ...
     with open(os.path.join(path, "input", "soil"), "w") as fh:
         fh.write("%r\tPMIN\n0 1.0\tIPEAT SCF\n0.4 0.225\tCBETA0,CANG\n" % pmin)
         fh.write("0.0 -4.0 -150.0 1.0 1.0 1.0\tPCANA,PCREF,PCWLT,ZROOT,PZ,OMGC\n%d\tIVGHU\n" % ivghu)

@@ -387,3 +387,30 @@ def test_huyakorn_and_brooks_corey_curves(gpu_lib, oracle_mod, tmp_path, ivghu):
     ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
     assert ok, dmax
     assert np.max(np.abs(g.state()["sw"] - c.state()["sw"])) < 1e-6
+
+
+@pytest.mark.parametrize("ivert", [0, 1, 2])
+def test_soil_zones_and_ivert(gpu_lib, oracle_mod, tmp_path, ivert):
+    """NZONE = 3 soil zones with per-(layer, zone) soils and IVERT = 0, 1, 2 (SRC/gen3d.f, SRC/tpnodi.f): same accepted steps and
+    heads as the oracle, which is byte-identical to the reference's MAXZON=4 ELF on these very projects
+    (tests/test_oracle_golden.py::test_oracle_soil_zones_and_ivert_against_reference_elf_when_available)."""
+    from pycathy_wrapper_b200.project import load_project
+    from test_oracle_golden import _zoned_project
+    prj = load_project(_zoned_project(str(tmp_path / "p"), ivert))
+    g, c, rg, rc = _run_both(gpu_lib, oracle_mod, prj)
+    assert rg.nstep == 44
+    ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
+    assert ok, dmax
+    assert np.max(np.abs(g.state()["sw"] - c.state()["sw"])) < 1e-6
+
+
+def test_constant_relaxation(gpu_lib, oracle_mod, tmp_path):
+    """NLRELX = 1 (SRC/relax.f): the relaxed heads enter the convergence norms and the next iterate; 276 accepted steps as the ELF."""
+    from pycathy_wrapper_b200 import synthetic
+    from pycathy_wrapper_b200.project import load_project
+    d = synthetic.make_project(str(tmp_path / "p"), 8, 9, 5, ic=("wt", 0.8), ISIMGR=1, TMAX=600.0, TIMPRT=[300.0, 600.0], DELTAT=1.0, DTMIN=1e-4,
+                               DTMAX=50.0, NODVP=[4], NLRELX=1, OMEGA=0.7, atmbc=[(0.0, 0.0), (60.0, 2.0e-5), (1.0e9, 2.0e-5)])
+    g, c, rg, rc = _run_both(gpu_lib, oracle_mod, load_project(d))
+    assert rg.nstep == 276
+    ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
+    assert ok, dmax
