@@ -33,8 +33,11 @@ if ROOT not in sys.path:
 from pycathy_wrapper_b200 import synthetic  # noqa: E402
 from pycathy_wrapper_b200.project import load_project  # noqa: E402
 
-PCG_BYTES_PER_ROW_ITER = 168.0     # phase A 104 B + phase B 64 B per row and iteration (fp64, DIA layout)
+PCG_BYTES_PER_ROW_ITER = 168.0     # the CG recurrence in the DIA layout, every operand touched once per phase:
+                                   # phase A 104 B + phase B 64 B per row and iteration (fp64) -- the ALGORITHMIC bytes
 PCG_BYTES_PER_ROW_SETUP = 152.0    # x0, residual and first preconditioner application
+# k_pcg_res keeps r, p, B (and x) of a CTA's rows in shared memory: what it still moves through L2/HBM per row and iteration
+PCG_RES_BYTES_PER_ROW_ITER = 88.0  # 8 diagonals + z read (phase A); main diagonal + z write (phase B); +16 when x is not resident
 SPMV_BYTES_PER_ROW = 80.0          # 8 diagonals + x + y
 
 
@@ -46,6 +49,17 @@ def _quiet_nccl():
         os.environ.pop("NCCL_DEBUG", None)
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes (read + write) of ONE captured launch of `kernel` from the committed `ncu --set full` summary
+    (profiles/ncu_traffic.json, written from the .ncu-rep of the same bench command); None when no capture is committed."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        rec = json.load(fh).get(kernel)
+    return rec
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -54,13 +68,13 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
-def make_workload(size, member: int = 0):
+def make_workload(size, member: int = 0, iopt: int = 1):
     nrow, ncol, nstr = size
     d = tempfile.mkdtemp(prefix="cathy_bench_")
     ks = 1.88e-4 * (1.0 + 0.05 * member)                     # ensemble members differ in Ks (weak scaling replicas)
     row = (ks, ks, ks, 1.0e-5, 0.55, 1.46, 0.15, 0.03125)
     synthetic.make_project(d, nrow, ncol, nstr, ic=("wt", 1.0), ISIMGR=1, DELTAT=1.0, DTMIN=1e-2, DTMAX=100.0,
-                           TMAX=7200.0, TIMPRT=[7200.0], NODVP=[1], soil_rows=[row] * nstr, hspatm=0,
+                           TMAX=7200.0, TIMPRT=[7200.0], NODVP=[1], soil_rows=[row] * nstr, hspatm=0, IOPT=iopt,
                            atmbc=[(0.0, np.zeros((nrow + 1) * (ncol + 1))), (60.0, np.full((nrow + 1) * (ncol + 1), 2.0e-5)),
                                   (3600.0, np.full((nrow + 1) * (ncol + 1), 2.0e-5)),
                                   (3660.0, np.zeros((nrow + 1) * (ncol + 1))), (1.0e9, np.zeros((nrow + 1) * (ncol + 1)))])
@@ -118,7 +132,8 @@ def run_ours(args, size):
     if world > 1:
         dist.barrier()
     lib = load_library()
-    prj = make_workload(size, member=rank)
+    newton = args.workload == "newton"
+    prj = make_workload(size, member=rank, iopt=2 if newton else 1)
     nnod = prj.nnod
 
     def barrier():
@@ -171,6 +186,7 @@ def run_ours(args, size):
     # SpMV roofline sample on the last assembled system
     x = np.random.default_rng(0).standard_normal(n)
     _, spmv_ms = sim.debug_spmv(x, reps=50)
+    solver = sim.solver_info()
     sim.close()
 
     # ---------------- end-to-end through the C ABI with host buffers ("e2e") ----------------
@@ -199,29 +215,55 @@ def run_ours(args, size):
     peak, peak_src = measured_peaks()
     pcg_bytes = (pcg_iters * PCG_BYTES_PER_ROW_ITER + pcg_solves * PCG_BYTES_PER_ROW_SETUP) * n
     achieved = pcg_bytes / (pcg_ms / 1e3) / 1e9 if pcg_ms > 0 else None
+    resident = solver["kernel"] == 3
+    if newton:      # k_bicgstab: 2 x (15 diagonals + dinv + x) + 10 vector passes per iteration
+        pcg_bytes = pcg_iters * 350.0 * n
+        achieved = pcg_bytes / (pcg_ms / 1e3) / 1e9 if pcg_ms > 0 else None
+    if newton:
+        kname = "k_bicgstab (persistent right-preconditioned BiCGSTAB on the 15-diagonal Jacobian)"
+    elif resident:
+        kname = "k_pcg_res (persistent PCG, CG vectors resident in shared memory: SpMV on z + fused vector ops)"
+    else:
+        kname = "k_pcg (persistent PCG: SpMV + fused vector ops)"
+    kernel_bytes = None
+    if resident and pcg_ms > 0:
+        per_it = PCG_RES_BYTES_PER_ROW_ITER + (0.0 if solver["x_resident"] else 16.0)
+        moved = (pcg_iters * per_it + pcg_solves * PCG_BYTES_PER_ROW_SETUP) * n / (pcg_ms / 1e3) / 1e9
+        kernel_bytes = {"per_row_iter": per_it, "achieved": moved, "frac": moved / peak,
+                        "note": "global-memory bytes the resident kernel itself moves (the rest of the 168 algorithmic bytes never leaves the SM); "
+                                "at this size the 54 MB of diagonals are L2-resident as well, so `achieved` above can exceed the HBM peak"}
+    # `traffic`: measured DRAM bytes of one captured launch, next to the algorithmic bytes of an average launch
+    trec = ncu_traffic("k_pcg_res" if resident else "k_pcg") if (size == (200, 200, 20)) else None
+    traffic = None
+    if trec:
+        traffic = {"dram_bytes_per_launch": trec["dram_bytes_per_launch"], "pcg_iters_in_launch": trec.get("pcg_iters_in_launch"),
+                   "algorithmic_bytes_per_launch": pcg_bytes / max(pcg_solves, 1), "source": trec.get("source")}
     out = {
         "metric": "node-timesteps/s", "value": value, "unit": "node-timesteps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall_s / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic %dx%d DEM x %d layers (%d nodes, %d tets), van Genuchten, Picard+PCG, infiltration pulse on a hillslope with a water table 2 m deep (INDP=3), "
-                               "ISIMGR=1, first %d accepted steps after %d warm-up" % (size[1], size[0], size[2], n, sim.nt, args.steps, args.warmup),
+        "config": {"workload": "synthetic %dx%d DEM x %d layers (%d nodes, %d tets), van Genuchten, %s, infiltration pulse on a hillslope with a water table 2 m deep (INDP=3), "
+                               "ISIMGR=1, first %d accepted steps after %d warm-up" % (size[1], size[0], size[2], n, sim.nt, "Newton+BiCGSTAB (BASELINE config 3 without the surface-routing coupling)" if newton else "Picard+PCG", args.steps, args.warmup),
                    "parallelism": "1 ensemble member per GPU" if world > 1 else "single forward run",
-                   "l2": "per-iteration working set (~%.0f MB) vs 126 MB L2: inputs are not larger than L2; no flush between PCG iterations (they are consecutive launches of one solve)" % (n * 21 * 8 / 1e6),
+                   "l2": "inputs larger than L2: every nonlinear iteration streams the %.2f GB gather plan and the nodal soil constants through the 126 MB L2 "
+                         "between two linear solves; inside ONE solve (one persistent launch) the diagonals (%.0f MB) are re-read every PCG iteration, no flush there" % (1.27e3 * n / 1e9, n * 64 / 1e6),
                    "nonlinear_its": nl_its, "pcg_iters": pcg_iters, "pcg_solves": pcg_solves},
         "device_ms_per_step": 1e3 * dev_s / args.steps,
         "e2e": {"value": e2e_value, "unit": "node-timesteps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
-        "roofline": {"bound": "hbm", "kernel": "k_pcg (persistent PCG: SpMV + fused vector ops)", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                     "traffic": None, "share_of_step": pcg_ms / gpu_ms if gpu_ms else None,
+                     "traffic": traffic, "share_of_step": pcg_ms / gpu_ms if gpu_ms else None,
+                     "algorithmic_bytes_per_row_iter": PCG_BYTES_PER_ROW_ITER, "kernel_bytes": kernel_bytes,
+                     "us_per_pcg_iter": 1e3 * pcg_ms / max(pcg_iters, 1),
                      "spmv_only": {"achieved": SPMV_BYTES_PER_ROW * n / (spmv_ms / 1e3) / 1e9, "ms": spmv_ms,
                                    "frac": SPMV_BYTES_PER_ROW * n / (spmv_ms / 1e3) / 1e9 / peak,
                                    "csr_equivalent_gbs": (12.0 * sim.nnz + 20.0 * n) / (spmv_ms / 1e3) / 1e9}},
     }
     if rank == 0:
         if world == 1 and not args.no_cpu:
-            out["cpu_baseline"] = cpu_baseline(size, budget_s=args.cpu_budget)
+            out["cpu_baseline"] = cpu_baseline(size, budget_s=args.cpu_budget, iopt=2 if newton else 1)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -427,11 +469,11 @@ def run_partitioned(args, size):
         dist.destroy_process_group()
 
 
-def cpu_baseline(size, budget_s: float = 25.0, max_steps: int = 1000):
+def cpu_baseline(size, budget_s: float = 25.0, max_steps: int = 1000, iopt: int = 1):
     """The CPU oracle (a C port of the reference's algorithm; the reference ELFs cannot hold this mesh)
     timed on a bounded sample of the same workload: the first accepted step(s), single thread."""
     from oracle import oracle
-    prj = make_workload(size)
+    prj = make_workload(size, iopt=iopt)
     sim = oracle.simulation(prj)
     t0 = time.perf_counter()
     k = 0
@@ -452,7 +494,7 @@ def run_reference(args, size):
     import __graft_entry__ as g
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], check=True)
     from oracle import oracle
-    prj = make_workload(size)
+    prj = make_workload(size, iopt=2 if args.workload == "newton" else 1)
     sim = oracle.simulation(prj)
     n = sim.n
     budget = 150.0
@@ -492,7 +534,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", default=None)
-    ap.add_argument("--workload", default="picard", choices=["picard", "enkf", "partitioned"], help="picard: BASELINE config 2 (headline); enkf: config 4; partitioned: config 5")
+    ap.add_argument("--workload", default="picard", choices=["picard", "newton", "enkf", "partitioned"], help="picard: BASELINE config 2 (headline); newton: config 3's linearisation on the same mesh; enkf: config 4; partitioned: config 5")
     ap.add_argument("--members", type=int, default=256)
     ap.add_argument("--concurrent", type=int, default=4, help="enkf workload: ensemble members advancing concurrently per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -500,7 +542,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.size is None:
-        args.size = {"picard": "200x200x20", "enkf": "100x100x15", "partitioned": "1000x1000x30"}[args.workload]
+        args.size = {"picard": "200x200x20", "newton": "200x200x20", "enkf": "100x100x15", "partitioned": "1000x1000x30"}[args.workload]
     size = tuple(int(v) for v in args.size.lower().split("x"))
     if args.workload == "enkf" and args.impl == "ours":
         return run_enkf(args, size)

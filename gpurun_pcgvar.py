@@ -4,11 +4,15 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import bench
 from pycathy_wrapper_b200.capi import Simulation, load_library
 lib = load_library()
-for size in [(20, 20, 15), (100, 100, 15), (200, 200, 20), (400, 400, 20)]:
+variants = [("algo1", {"CATHY_PCG_ALGO": "1"}), ("res", {"CATHY_PCG_ALGO": "3"}), ("res_xglobal", {"CATHY_PCG_ALGO": "3", "CATHY_PCG_RES_X": "0"}),
+            ("res_pf1", {"CATHY_PCG_ALGO": "3", "CATHY_PCG_RES_PREFETCH": "1"}), ("res_pf0", {"CATHY_PCG_ALGO": "3", "CATHY_PCG_RES_PREFETCH": "0"})]
+for size in [(20, 20, 15), (100, 100, 15), (200, 200, 20), (250, 250, 20)]:
     prj = bench.make_workload(size)
     sols = {}
-    for fs in (0, 1):
-        os.environ['CATHY_PCG_FASTSYNC'] = str(fs)
+    for name, env in variants:
+        for k in ("CATHY_PCG_ALGO", "CATHY_PCG_RES_X", "CATHY_PCG_RES_PREFETCH"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
         sim = Simulation(lib, prj, tolcg_scale=1e-30, ITMXCG=10)      # 200 iterations, never converges: pure per-iteration cost
         sim.debug_assemble(10.0)
         sim.debug_solve()
@@ -20,7 +24,7 @@ for size in [(20, 20, 15), (100, 100, 15), (200, 200, 20), (400, 400, 20)]:
         sim2 = Simulation(lib, prj)
         sim2.debug_assemble(10.0)
         xs, nit2, err2, ms2 = sim2.debug_solve()
-        sols[fs] = xs
-        print(f"size {size} fastsync {fs}: {nit} its {best:.3f} ms -> {1e3*best/nit:.2f} us/iter = {168.0*n/(best/nit*1e-3)/1e9:.0f} GB/s ; converged: {nit2} its err {err2:.2e} {ms2:.3f} ms", flush=True)
+        sols[name] = xs
+        print(f"size {size} n {n} {name}: {nit} its {best:.3f} ms -> {1e3*best/nit:.2f} us/iter = {168.0*n/(best/nit*1e-3)/1e9:.0f} GB/s (168 B/row) ; converged: {nit2} its err {err2:.2e} {ms2:.3f} ms", flush=True)
         sim.close(); sim2.close()
-    print("   max |x0-x1| / max|x| =", np.abs(sols[0] - sols[1]).max() / np.abs(sols[0]).max(), flush=True)
+    print("   max |x_algo1 - x_res| / max|x| =", np.abs(sols["algo1"] - sols["res"]).max() / np.abs(sols["algo1"]).max(), flush=True)

@@ -194,6 +194,11 @@ int32_t cathy_dd_start(CathySim *sim);
  * global NNOD, global N. */
 int32_t cathy_dd_info(const CathySim *sim, int64_t info[8]);
 
+/* Which linear-solver kernel this handle launches (for bench.py's roofline bookkeeping; no reference counterpart):
+ * info[0] = 1 k_pcg (CG vectors streamed), 2 k_pcg2, 3 k_pcg_res (CG vectors resident in shared memory), 10 k_bicgstab (Newton);
+ * info[1] = rows per CTA (k_pcg_res), info[2] = 1 if the solution vector is resident too, info[3] = CTAs of the solver grid. */
+int32_t cathy_solver_info(const CathySim *sim, int64_t info[4]);
+
 /* ---- kernel-level entry points used by parity tests and bench.py -------------------- */
 /* Assemble the Picard system at the current state for time step `deltat` without solving
  * (PICUNS+ASSPIC+RHSPIC+CFMATP+RHSGRV+BCPIC, SRC/picard.f:74-154) and export it as

@@ -188,7 +188,7 @@ class CathyLib:
                "initial_storage", "step", "get_state", "get_velocity", "get_recharge", "get_wtdepth", "set_psi", "upload_atm_record", "debug_assemble", "debug_spmv", "debug_solve"]
 
     # entry points only the product library has (in-process ensemble support); bound when present
-    PRODUCT_ONLY = ["pack_state", "unpack_psi", "restart", "set_soil", "set_atm_table", "dd_export", "dd_connect", "dd_connect_local", "dd_start", "dd_info"]
+    PRODUCT_ONLY = ["pack_state", "unpack_psi", "restart", "set_soil", "set_atm_table", "dd_export", "dd_connect", "dd_connect_local", "dd_start", "dd_info", "solver_info"]
 
     def __init__(self, path: str, prefix: str):
         if not os.path.exists(path):
@@ -220,6 +220,7 @@ class CathyLib:
             f["dd_export"].argtypes = [C.c_void_p, C.c_void_p]
             f["dd_connect"].argtypes = [C.c_void_p, C.c_void_p]
             f["dd_info"].argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+            f["solver_info"].argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
             f["dd_connect_local"].argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
             f["dd_start"].argtypes = [C.c_void_p]
         f["sizeof_problem"].restype = C.c_int64
@@ -398,6 +399,12 @@ class Simulation:
         self._ck(self.lib.f["dd_info"](self.h, v), "dd_info")
         keys = ["win_row0", "win_rows", "own_row0", "own_row1", "nnod_local", "n_local", "nnod_global", "n_global"]
         return dict(zip(keys, (int(x) for x in v)))
+
+    def solver_info(self) -> dict:
+        """Linear-solver kernel of this handle: kernel id (1 k_pcg, 2 k_pcg2, 3 k_pcg_res, 10 k_bicgstab), rows per CTA, x resident, grid."""
+        v = (C.c_int64 * 4)()
+        self._ck(self.lib.f["solver_info"](self.h, v), "solver_info")
+        return dict(zip(["kernel", "rows_per_cta", "x_resident", "grid"], (int(x) for x in v)))
 
     def debug_assemble(self, deltat: float):
         # Picard: symmetric upper CSR (NTERM entries); Newton: the Jacobian in full CSR (nnz entries)

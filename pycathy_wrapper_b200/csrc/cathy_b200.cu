@@ -531,6 +531,8 @@ struct PcgArgs {
     int prefetch;               // 1: software prefetch of the next grid-stride row into L2
     const unsigned char *own;   // row-block partition: bit0 = owned row, bit1 / bit2 = row is sent to the north / south neighbour
     DDCtx dd;
+    int rows_cta;               // k_pcg_res: rows owned by one CTA (multiple of 32)
+    int xres;                   // k_pcg_res: 1 = the solution vector lives in shared memory too
 };
 
 // Grid-wide barrier for the persistent kernel: one arrival per block on a monotonically increasing counter
@@ -710,6 +712,102 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_pcg(PcgArgs a)
 }
 
 
+
+// ------------------------------------------------------------------------------------------
+// SYMSLV with the CG vectors RESIDENT IN SHARED MEMORY (default whenever they fit: n <= #CTAs x ~9.6k rows, i.e. up to
+// ~1.4 M nodes on one B200).  Every CTA owns a contiguous block of rows_cta rows for the whole solve and keeps r, p and
+// B = A p (and x when there is room) of its rows in its 227 KB of shared memory; only z = M^-1 r, which the neighbours'
+// stencils need, goes through global memory (L2).  The search direction is never gathered: by linearity
+//     p = z + beta p_old   =>   B = A p = A z + beta B_old,
+// so phase A is ONE stencil product on z (15 gathered operands per row instead of 29) and two shared-memory recurrences.
+// Same recurrence otherwise (GRADDP, SRC/solscal-extended.f:1260-1380): x0 = M^-1 b, alfa = (p.r)/(p.B),
+// beta = -(B.z)/(p.B), residual test on the non-Dirichlet rows; two grid barriers per iteration, fixed-order reductions.
+// Per row and iteration the kernel moves 8 diagonals + z (read, write) + the diagonal again in phase B = 88 B
+// (+16 B for x when it is not resident) instead of 168 B.
+// ------------------------------------------------------------------------------------------
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1) k_pcg_res(PcgArgs a)
+{
+    extern __shared__ __align__(16) double smv[];
+    __shared__ double sh[BLOCK / 32][3];
+    cg::grid_group grid = cg::this_grid();
+    unsigned int epoch = a.epoch0;
+    const bool PF = a.prefetch != 0;
+    const int R = a.rows_cta, row0 = blockIdx.x * R, cnt = max(0, min(R, a.n - row0)), tid = threadIdx.x;
+    double *rs = smv, *ps = smv + R, *bs = smv + 2 * (size_t)R, *xs = a.xres ? smv + 3 * (size_t)R : a.x + row0;
+    const double *__restrict__ dg = a.diag;
+    // x0 = M^-1 b ; xlung = ||b_free||^2 ; Dirichlet rows of this thread as a bit mask (row j*BLOCK + tid -> bit j)
+    unsigned int dmask = 0;
+    double xl = 0.0;
+    for (int i = tid, j = 0; i < cnt; i += BLOCK, ++j) {
+        const int k = row0 + i;
+        double b = a.rhs[k];
+        a.x[k] = b / dg[k];
+        if (is_dirichlet(k, a.nnod, a.ifatm, a.contp_flag)) dmask |= 1u << j; else xl += b * b;
+    }
+    double xlung, d1, d2;
+    grid_reduce3<BLOCK, true>(grid, a.counter, epoch, xl, 0.0, 0.0, a.partial, sh, xlung, d1, d2);
+    // r = b - A x0 ; z = M^-1 r ; p = B = 0
+    for (int i = tid; i < cnt; i += BLOCK) {
+        const int k = row0 + i;
+        double r = a.rhs[k] - dia_row(a.A, dg, a.x, k, a.n);
+        rs[i] = r;
+        a.z[k] = r / dg[k];
+        ps[i] = 0.0;
+        bs[i] = 0.0;
+        if (a.xres) xs[i] = a.x[k];
+    }
+    grid_barrier(a.counter, epoch);
+    double beta = 0.0, err = 0.0;
+    int niter = 1;
+    const double *z = a.z;      // NOT __restrict__/read-only: rewritten every iteration by other SMs
+    for (;;) {
+        // ---- phase A: B = A z + beta B, p = z + beta p, (p.r), (p.B)
+        double s_pr = 0.0, s_pb = 0.0;
+        for (int i = tid; i < cnt; i += BLOCK) {
+            const int k = row0 + i;
+            if (PF && i + BLOCK < cnt) {
+#pragma unroll
+                for (int d = 1; d < NDIAG; ++d) l2_prefetch(&a.A.d[d][k + BLOCK]);
+                l2_prefetch(&dg[k + BLOCK]);
+            }
+            const double zk = z[k];
+            double acc = dg[k] * zk;
+#pragma unroll
+            for (int d = 1; d < NDIAG; ++d) acc += a.A.d[d][k] * z[k + a.A.off[d]];
+#pragma unroll
+            for (int d = 1; d < NDIAG; ++d) acc += a.A.d[d][k - a.A.off[d]] * z[k - a.A.off[d]];
+            const double pk = zk + beta * ps[i], bk = acc + beta * bs[i];
+            ps[i] = pk;
+            bs[i] = bk;
+            s_pr += pk * rs[i];
+            s_pb += pk * bk;
+        }
+        double pr, pb;
+        grid_reduce3<BLOCK, true>(grid, a.counter, epoch, s_pr, s_pb, 0.0, a.partial, sh, pr, pb, d1);
+        const double alfa = pr / pb;
+        // ---- phase B: r -= alfa B, x += alfa p, z = M^-1 r, (B.z), ||r_free||^2
+        double s_bz = 0.0, s_rr = 0.0;
+        for (int i = tid, j = 0; i < cnt; i += BLOCK, ++j) {
+            const int k = row0 + i;
+            const double bk = bs[i], r = rs[i] - alfa * bk;
+            rs[i] = r;
+            xs[i] += alfa * ps[i];
+            const double zz = r / dg[k];
+            a.z[k] = zz;
+            s_bz += bk * zz;
+            if (!((dmask >> j) & 1u)) s_rr += r * r;
+        }
+        double bz, rr;
+        grid_reduce3<BLOCK, true>(grid, a.counter, epoch, s_bz, s_rr, 0.0, a.partial, sh, bz, rr, d1);
+        beta = -bz / pb;
+        err = xlung > 0.0 ? sqrt(rr / xlung) : sqrt(rr / a.n);
+        if (err > a.tol && niter < a.itmax) { ++niter; continue; }
+        break;
+    }
+    if (a.xres) for (int i = tid; i < cnt; i += BLOCK) a.x[row0 + i] = xs[i];
+    if (blockIdx.x == 0 && tid == 0) { a.out->pcg_niter = niter; a.out->pcg_err = err; a.out->pad = (int)epoch; }
+}
 
 // ------------------------------------------------------------------------------------------
 // SYMSLV, second formulation (opt-in, CATHY_PCG_ALGO=2; measured slower than k_pcg on B200 except on tiny meshes, see
@@ -1980,7 +2078,9 @@ struct CathySim {
     DBuf<double> wr, wz, wp0, wp1, wbv, partial, store_part;
     DBuf<double> dis, wq0, wq1;      // k_pcg2: 1/sqrt(diag), two more work vectors
     bool scaled = false;             // off-diagonals of A currently hold the symmetrically scaled matrix
-    int pcg_algo = 1;                // 1: k_pcg (two reductions / iteration, default), 2: k_pcg2 (scaled, single reduction; CATHY_PCG_ALGO=2)
+    int pcg_algo = 3;                // 3: k_pcg_res (CG vectors resident in shared memory; default, falls back to 1 when they do not fit),
+                                     // 1: k_pcg (vectors streamed from HBM/L2), 2: k_pcg2 (scaled, single reduction); CATHY_PCG_ALGO
+    int res_rows = 0, res_x = 0, res_prefetch = 0;   // k_pcg_res: rows per CTA (0 = does not fit), x resident too, L2 prefetch of the diagonals
     DBuf<double> Ju, Jl, dinv, dckrw, detai, ts, s1, ws, wsh, wt;   // Newton: Jacobian diagonals, Jacobi scaling, derivative curves, element factors, BiCGSTAB vectors
     bool newton = false;
     // ---- row-block partition of one large mesh over several GPUs (BASELINE config 5) ----
@@ -2562,6 +2662,7 @@ static int solve_system(CathySim *S)
 {
     if (!S->dd && S->pcg_algo == 2) return solve_system2(S);
     PcgArgs a;
+    a.rows_cta = 0; a.xres = 0;
     a.n = S->n; a.nnod = S->nnod; a.itmax = S->itmax_dev; a.tol = S->tol_dev;
     a.A = make_diag(S, S->A.p); a.diag = S->diag_bc.p; a.rhs = S->rhs.p;
     a.x = S->pdiff.p; a.r = S->wr.p; a.z = S->wz.p; a.p0 = S->wp0.p; a.p1 = S->wp1.p; a.bv = S->wbv.p;
@@ -2582,6 +2683,16 @@ static int solve_system(CathySim *S)
     a.own = nullptr;
     a.prefetch = S->pcg_prefetch;
     if (S->dd) { fn = (void *)k_pcg<1024, true, true>; a.own = S->own.p; a.dd = S->comm->ctx; }
+    if (!S->dd && S->pcg_algo == 3 && S->res_rows > 0) {
+        // CG vectors resident in shared memory (k_pcg_res): one 1024-thread CTA per SM owns res_rows consecutive rows
+        a.rows_cta = S->res_rows; a.xres = S->res_x; a.prefetch = S->res_prefetch;
+        const size_t smem = (size_t)(3 + S->res_x) * S->res_rows * sizeof(double);
+        if (S->pcg_shared_gpu) { k_pcg_res<1024><<<S->grid_pcg, 1024, smem, S->st>>>(a); CK(cudaGetLastError()); }
+        else CK(cudaLaunchCooperativeKernel((void *)k_pcg_res<1024>, dim3(S->grid_pcg), dim3(1024), args, smem, S->st));
+        CK(cudaEventRecord(S->evp1, S->st));
+        S->launches++;
+        return 0;
+    }
     if (S->pcg_shared_gpu) {
         // Several handles share this GPU (partition ranks in tests, concurrent ensemble members): the driver runs cooperative
         // launches one at a time, which would serialise members and deadlock ranks that wait for each other inside the kernel.
@@ -2878,7 +2989,7 @@ static int preload_kernels()
                          (const void *)k_switch_old, (const void *)k_adrstn, (const void *)k_pondupd, (const void *)k_atm_interp, (const void *)k_etran,
                          (const void *)k_div_area, (const void *)k_nod_cell, (const void *)k_cell_nod, (const void *)k_route, (const void *)k_pond_zero,
                          (const void *)k_step_partial, (const void *)k_step_final, (const void *)k_weight, (const void *)k_atmone, (const void *)k_mbinit,
-                         (const void *)k_pack_col, (const void *)k_unpack_col, (const void *)k_vel3d, (const void *)k_vnod3d, (const void *)k_recharge, (const void *)k_wtdepth, (const void *)k_curves_alt, (const void *)k_chvelo_alt, (const void *)k_relax};
+                         (const void *)k_pack_col, (const void *)k_unpack_col, (const void *)k_vel3d, (const void *)k_vnod3d, (const void *)k_recharge, (const void *)k_wtdepth, (const void *)k_curves_alt, (const void *)k_chvelo_alt, (const void *)k_relax, (const void *)k_pcg_res<1024>};
     for (const void *f : fns) CK(cudaFuncGetAttributes(&at, f));
     done = true;
     return 0;
@@ -3018,6 +3129,25 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
         for (int r = 0; r < S->neu.nrec; ++r) if (S->neu.n2d[r] < 0) S->free_drain = true;
     }
     S->ld = ((size_t)S->n + 31) / 32 * 32;
+    if (!S->dd && S->pcg_algo == 3) {
+        // k_pcg_res: r, p, B (and x if there is room) of a CTA's rows stay in its shared memory for the whole solve
+        cudaFuncAttributes at;
+        CK(cudaFuncGetAttributes(&at, (const void *)k_pcg_res<1024>));
+        int optin = 0;
+        CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, p.device));
+        const size_t avail = (size_t)optin > at.sharedSizeBytes ? (size_t)optin - at.sharedSizeBytes : 0;
+        const int rows = (int)((((size_t)S->n + S->grid_pcg - 1) / S->grid_pcg + 31) / 32 * 32);
+        if ((size_t)3 * rows * sizeof(double) <= avail && rows <= 32 * 1024) {
+            S->res_rows = rows;
+            S->res_x = (size_t)4 * rows * sizeof(double) <= avail ? 1 : 0;
+            if (const char *e = getenv("CATHY_PCG_RES_X")) S->res_x = S->res_x && atoi(e);
+            // the diagonals (64 B/row) stay in the 126 MB L2 up to ~1 M rows (measured: prefetch costs 4 % at 848 k rows); beyond that they
+            // stream from HBM and the prefetch pays (+13 % at 1.32 M rows)
+            S->res_prefetch = S->pcg_prefetch && (size_t)S->n * 64 > ((size_t)64 << 20);
+            if (const char *e = getenv("CATHY_PCG_RES_PREFETCH")) S->res_prefetch = atoi(e);
+            CK(cudaFuncSetAttribute((const void *)k_pcg_res<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
+        }
+    }
     S->halo = ((size_t)S->nnod + 1 + 31) / 32 * 32;
     int rc = build_static(S);
     if (rc) return rc;
@@ -3589,6 +3719,13 @@ int32_t cathy_dd_start(CathySim *S)
     if (!S->dd || !S->comm->connected) FAIL(-1, "cathy_dd_start: connect first");
     CK(cudaSetDevice(S->p.device));
     return init_atm_and_storage(S);
+}
+int32_t cathy_solver_info(const CathySim *S, int64_t info[4])
+{
+    const bool res = !S->dd && S->pcg_algo == 3 && S->res_rows > 0;
+    info[0] = S->newton ? 10 : res ? 3 : (!S->dd && S->pcg_algo == 2) ? 2 : 1;
+    info[1] = res ? S->res_rows : 0; info[2] = res ? S->res_x : 0; info[3] = S->grid_pcg;
+    return 0;
 }
 int32_t cathy_dd_info(const CathySim *S, int64_t info[8])
 {

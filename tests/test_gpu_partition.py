@@ -29,7 +29,11 @@ def test_partitioned_run_equals_single_domain(gpu_lib, world):
     prj = _project()
     os.environ["CATHY_PCG_GRID"] = str(148 // (world + 1))      # world partitioned kernels + nothing else must be co-resident
     try:
-        ref = Simulation(gpu_lib, prj)
+        os.environ["CATHY_PCG_ALGO"] = "1"      # the streamed-vector k_pcg: the recurrence the partitioned kernel shares, so that PCG
+        try:                                    # iteration counts are comparable one to one (the default k_pcg_res forms B = A z + beta B)
+            ref = Simulation(gpu_lib, prj)
+        finally:
+            os.environ.pop("CATHY_PCG_ALGO", None)
         part = LocalPartition(gpu_lib, prj, [0] * world)
         assert sum(i["own_row1"] - i["own_row0"] for i in part.infos) == prj.nrow + 1
         k = 0
