@@ -215,14 +215,14 @@ def run_ours(args, size):
     peak, peak_src = measured_peaks()
     pcg_bytes = (pcg_iters * PCG_BYTES_PER_ROW_ITER + pcg_solves * PCG_BYTES_PER_ROW_SETUP) * n
     achieved = pcg_bytes / (pcg_ms / 1e3) / 1e9 if pcg_ms > 0 else None
-    resident = solver["kernel"] == 3
+    resident = solver["kernel"] in (3, 4)
     if newton:      # k_bicgstab: 2 x (15 diagonals + dinv + x) + 10 vector passes per iteration
         pcg_bytes = pcg_iters * 350.0 * n
         achieved = pcg_bytes / (pcg_ms / 1e3) / 1e9 if pcg_ms > 0 else None
     if newton:
         kname = "k_bicgstab (persistent right-preconditioned BiCGSTAB on the 15-diagonal Jacobian)"
     elif resident:
-        kname = "k_pcg_res (persistent PCG, CG vectors resident in shared memory: SpMV on z + fused vector ops)"
+        kname = "%s (persistent PCG, CG vectors resident in shared memory: SpMV on z + fused vector ops)" % ("k_pcg_res2" if solver["kernel"] == 4 else "k_pcg_res")
     else:
         kname = "k_pcg (persistent PCG: SpMV + fused vector ops)"
     kernel_bytes = None

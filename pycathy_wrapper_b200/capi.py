@@ -401,7 +401,7 @@ class Simulation:
         return dict(zip(keys, (int(x) for x in v)))
 
     def solver_info(self) -> dict:
-        """Linear-solver kernel of this handle: kernel id (1 k_pcg, 2 k_pcg2, 3 k_pcg_res, 10 k_bicgstab), rows per CTA, x resident, grid."""
+        """Linear-solver kernel of this handle: kernel id (1 k_pcg, 2 k_pcg2, 3 k_pcg_res, 4 k_pcg_res2, 10 k_bicgstab), rows per CTA, x resident, grid."""
         v = (C.c_int64 * 4)()
         self._ck(self.lib.f["solver_info"](self.h, v), "solver_info")
         return dict(zip(["kernel", "rows_per_cta", "x_resident", "grid"], (int(x) for x in v)))

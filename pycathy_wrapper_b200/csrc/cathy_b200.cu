@@ -579,6 +579,59 @@ __device__ __forceinline__ void grid_reduce3(cg::grid_group &grid, unsigned int 
     __syncthreads();
 }
 
+// two sums at once, second generation (k_pcg_res, k_pcg_res2): half-warp butterflies, double-buffered partials, see k_pcg_res2
+#define FULLMASK 0xffffffffu
+template <int BLOCK>
+__device__ __forceinline__ void grid_reduce2(unsigned int *counter, unsigned int &epoch, unsigned int &par, double a, double b, double *partial,
+                                             double (*sh)[2], double (*res)[2], double &ra, double &rb)
+{
+    static_assert(BLOCK == 1024, "32 warps: the second level is one half-warp butterfly");
+    const int nb = gridDim.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool hi = lane >= 16;
+    double keep = hi ? b : a, send = hi ? a : b;
+    keep += __shfl_xor_sync(FULLMASK, send, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(FULLMASK, keep, o);
+    if ((lane & 15) == 0) sh[w][hi] = keep;
+    __syncthreads();
+    double *pp = partial + (size_t)par * 2 * nb;   // [2][nb], buffer of this reduction
+    if (w == 0) {
+        double v = hi ? sh[lane - 16][1] + sh[lane][1] : sh[lane][0] + sh[lane + 16][0];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+        if ((lane & 15) == 0) pp[(hi ? nb : 0) + blockIdx.x] = v;
+        __syncwarp();
+        epoch += nb;
+        // only thread 0 spins and nobody of its warp waits at a __syncwarp meanwhile: a lane spinning next to parked lanes of
+        // the same warp costs +1.5 us per reduction on B200 (tools/bench_barrier4.cu)
+        if (lane == 0) {
+            __threadfence();
+            atomicAdd(counter, 1u);
+            unsigned int c;
+            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(counter) : "memory"); } while ((int)(c - epoch) < 0);
+        }
+    } else
+        epoch += nb;
+    __syncthreads();
+    if (w < 2) {      // warp 0 sums the first quantity, warp 1 the second: independent loads, fixed order
+        constexpr int MAXJ = 5;    // up to 160 CTAs (B200: 148)
+        double v[MAXJ];
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+            const int i = lane + 32 * j;
+            v[j] = 0.0;
+            if (i < nb) asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v[j]) : "l"(pp + w * nb + i) : "memory");
+        }
+        double t = (((v[0] + v[1]) + v[2]) + v[3]) + v[4];
+        for (int i = lane + 32 * MAXJ; i < nb; i += 32) t += ((volatile double *)pp)[w * nb + i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULLMASK, t, o);
+        if (lane == 0) res[par][w] = t;
+    }
+    __syncthreads();
+    ra = res[par][0]; rb = res[par][1];
+    par ^= 1u;
+}
 __device__ __forceinline__ void l2_prefetch(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <int BLOCK, bool CUSTOM, bool DD, int MINB = 1024 / BLOCK>
 __global__ void __launch_bounds__(BLOCK, MINB) k_pcg(PcgArgs a)
@@ -729,9 +782,9 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 1) k_pcg_res(PcgArgs a)
 {
     extern __shared__ __align__(16) double smv[];
-    __shared__ double sh[BLOCK / 32][3];
-    cg::grid_group grid = cg::this_grid();
-    unsigned int epoch = a.epoch0;
+    __shared__ double sh[BLOCK / 32][2];
+    __shared__ double res[2][2];
+    unsigned int epoch = a.epoch0, par = 0;
     const bool PF = a.prefetch != 0;
     const int R = a.rows_cta, row0 = blockIdx.x * R, cnt = max(0, min(R, a.n - row0)), tid = threadIdx.x;
     double *rs = smv, *ps = smv + R, *bs = smv + 2 * (size_t)R, *xs = a.xres ? smv + 3 * (size_t)R : a.x + row0;
@@ -745,8 +798,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pcg_res(PcgArgs a)
         a.x[k] = b / dg[k];
         if (is_dirichlet(k, a.nnod, a.ifatm, a.contp_flag)) dmask |= 1u << j; else xl += b * b;
     }
-    double xlung, d1, d2;
-    grid_reduce3<BLOCK, true>(grid, a.counter, epoch, xl, 0.0, 0.0, a.partial, sh, xlung, d1, d2);
+    double xlung, d1;
+    grid_reduce2<BLOCK>(a.counter, epoch, par, xl, 0.0, a.partial, sh, res, xlung, d1);
     // r = b - A x0 ; z = M^-1 r ; p = B = 0
     for (int i = tid; i < cnt; i += BLOCK) {
         const int k = row0 + i;
@@ -784,7 +837,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pcg_res(PcgArgs a)
             s_pb += pk * bk;
         }
         double pr, pb;
-        grid_reduce3<BLOCK, true>(grid, a.counter, epoch, s_pr, s_pb, 0.0, a.partial, sh, pr, pb, d1);
+        grid_reduce2<BLOCK>(a.counter, epoch, par, s_pr, s_pb, a.partial, sh, res, pr, pb);
         const double alfa = pr / pb;
         // ---- phase B: r -= alfa B, x += alfa p, z = M^-1 r, (B.z), ||r_free||^2
         double s_bz = 0.0, s_rr = 0.0;
@@ -799,7 +852,184 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pcg_res(PcgArgs a)
             if (!((dmask >> j) & 1u)) s_rr += r * r;
         }
         double bz, rr;
-        grid_reduce3<BLOCK, true>(grid, a.counter, epoch, s_bz, s_rr, 0.0, a.partial, sh, bz, rr, d1);
+        grid_reduce2<BLOCK>(a.counter, epoch, par, s_bz, s_rr, a.partial, sh, res, bz, rr);
+        beta = -bz / pb;
+        err = xlung > 0.0 ? sqrt(rr / xlung) : sqrt(rr / a.n);
+        if (err > a.tol && niter < a.itmax) { ++niter; continue; }
+        break;
+    }
+    if (a.xres) for (int i = tid; i < cnt; i += BLOCK) a.x[row0 + i] = xs[i];
+    if (blockIdx.x == 0 && tid == 0) { a.out->pcg_niter = niter; a.out->pcg_err = err; a.out->pad = (int)epoch; }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_pcg_res2 (default, CATHY_PCG_ALGO=4): the resident-vector PCG above, re-cut after ncu showed k_pcg_res bound by the L1/LSU
+// data pipe (l1tex__data_pipe_lsu_wavefronts 55 % of peak over the whole launch, ~90 % inside the phases) and by the grid
+// reduction (tools/bench_barrier*.cu: 2.9 us each = 1400 cycles of fp64 shuffles + 870 fence + 1480 arrive/poll + 1000 re-read):
+//  * every thread owns TWO consecutive rows (k0 even, k0+1) and loads 16-byte aligned pairs; the element that a misaligned
+//    window lacks comes from the neighbouring lane by shuffle (edge lanes fetch it themselves).  The stencil offsets come in
+//    pairs (o, o+1) -- {-1,0,1}, {NC1,NC1+1}, {NNOD-NC1-1,NNOD-NC1}, {NNOD-1,NNOD} -- so one 3-element z window serves two
+//    diagonals of both rows: ~60 instead of 81 LSU wavefronts per 32 rows;
+//  * M^-1 is applied as a multiplication with the reciprocal diagonal computed once per solve (no fp64 division per row);
+//  * the grid reduction sums two quantities in ONE half-warp butterfly (a in lanes 0-15, b in lanes 16-31), the partials are
+//    double-buffered (a fast CTA can no longer overwrite what a slow one still reads) and fetched with independent loads.
+// Same recurrence and stopping test as k_pcg_res; inside a row the products are summed pair of diagonals by pair of diagonals.
+// ------------------------------------------------------------------------------------------
+// paired-row loads: this thread needs p[0..1] (pair) or p[0..2] (win3); lanes own consecutive pairs of rows, so lane+1 needs
+// p[2..], lane-1 p[-2..].  ODD (compile time, uniform): p is 8 but not 16 bytes aligned.  The 16-byte aligned pair is loaded, the
+// missing element comes from the neighbouring lane by shuffle; edge_lo / edge_hi: the lane below / above does not hold the
+// continuation (lane 0 / lane 31 or the last active pair) and the element is fetched directly.  Loads (`*_ld`) and shuffles
+// (`*_fin`) are separate calls so that all loads of a group are in flight before the first shuffle waits for one of them.
+struct PairLd { double2 q; double e; };
+template <bool ODD> __device__ __forceinline__ PairLd pair_ld(const double *p, bool edge_hi)
+{
+    PairLd r; r.e = 0.0;
+    if (!ODD) r.q = *reinterpret_cast<const double2 *>(p);
+    else { r.q = *reinterpret_cast<const double2 *>(p - 1); if (edge_hi) r.e = p[1]; }
+    return r;
+}
+template <bool ODD> __device__ __forceinline__ void pair_fin(const PairLd &r, bool edge_hi, double &v0, double &v1)
+{
+    if (!ODD) { v0 = r.q.x; v1 = r.q.y; }
+    else { v0 = r.q.y; const double t = __shfl_down_sync(FULLMASK, r.q.x, 1); v1 = edge_hi ? r.e : t; }
+}
+template <bool ODD> __device__ __forceinline__ PairLd win3_ld(const double *p, bool edge_lo, bool edge_hi)
+{
+    PairLd r; r.e = 0.0;
+    if (!ODD) { r.q = *reinterpret_cast<const double2 *>(p); if (edge_hi) r.e = p[2]; }
+    else { r.q = *reinterpret_cast<const double2 *>(p + 1); if (edge_lo) r.e = p[0]; }
+    return r;
+}
+template <bool ODD> __device__ __forceinline__ void win3_fin(const PairLd &r, bool edge_lo, bool edge_hi, double &v0, double &v1, double &v2)
+{
+    if (!ODD) { v0 = r.q.x; v1 = r.q.y; const double t = __shfl_down_sync(FULLMASK, r.q.x, 1); v2 = edge_hi ? r.e : t; }
+    else { v1 = r.q.x; v2 = r.q.y; const double t = __shfl_up_sync(FULLMASK, r.q.y, 1); v0 = edge_lo ? r.e : t; }
+}
+// one pair of diagonals (o, o+1) = (da, da+1): upper and lower products of rows k, k+1
+template <bool ODD>
+__device__ __forceinline__ void pair_group(const Diag &A, const double *z, int da, int o, int k, bool elo, bool ehi, double &a0, double &a1)
+{
+    const double2 ua = *reinterpret_cast<const double2 *>(A.d[da] + k), ub = *reinterpret_cast<const double2 *>(A.d[da + 1] + k);
+    const PairLd rw = win3_ld<ODD>(z + k + o, elo, ehi), rm = win3_ld<!ODD>(z + k - o - 1, elo, ehi);
+    const PairLd ra = pair_ld<ODD>(A.d[da] + k - o, ehi), rb = pair_ld<!ODD>(A.d[da + 1] + k - o - 1, ehi);   // L_d = (A_d[k - off_d], A_d[k + 1 - off_d])
+    double w0, w1, w2, m0, m1, m2, la0, la1, lb0, lb1;
+    win3_fin<ODD>(rw, elo, ehi, w0, w1, w2);
+    win3_fin<!ODD>(rm, elo, ehi, m0, m1, m2);
+    pair_fin<ODD>(ra, ehi, la0, la1);
+    pair_fin<!ODD>(rb, ehi, lb0, lb1);
+    a0 += ua.x * w0;  a1 += ua.y * w1;
+    a0 += ub.x * w1;  a1 += ub.y * w2;
+    a0 += la0 * m1;   a1 += la1 * m2;
+    a0 += lb0 * m0;   a1 += lb1 * m1;
+}
+template <int BLOCK, int PAR>     // PAR: parities of the offsets off[2], off[4], off[6] (bits 0, 1, 2)
+__global__ void __launch_bounds__(BLOCK, 1) k_pcg_res2(PcgArgs a)
+{
+    extern __shared__ __align__(16) double smv[];
+    __shared__ double sh[BLOCK / 32][2];
+    __shared__ double res[2][2];
+    unsigned int epoch = a.epoch0, par = 0;
+    const int R = a.rows_cta, row0 = blockIdx.x * R, cnt = max(0, min(R, a.n - row0)), tid = threadIdx.x, lane = tid & 31;
+    double *rs = smv, *ps = smv + R, *bs = smv + 2 * (size_t)R, *xs = a.xres ? smv + 3 * (size_t)R : a.x + row0;
+    const double *__restrict__ dg = a.diag;
+    double *dinv = a.p0;          // k_pcg's search-direction buffer is free here: reciprocal diagonal
+    // x0 = M^-1 b ; xlung = ||b_free||^2 ; Dirichlet rows of this thread as a bit mask (pass j: rows 2 tid + 2 BLOCK j + {0,1} -> bits 2j, 2j+1)
+    unsigned int dmask = 0;
+    double xl = 0.0;
+    for (int i = 2 * tid, j = 0; i < cnt; i += 2 * BLOCK, ++j)
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            if (i + q < cnt) {
+                const int k = row0 + i + q;
+                const double b = a.rhs[k], dv = 1.0 / dg[k];
+                dinv[k] = dv;
+                a.x[k] = b * dv;
+                if (is_dirichlet(k, a.nnod, a.ifatm, a.contp_flag)) dmask |= 1u << (2 * j + q); else xl += b * b;
+            }
+    double xlung, d1;
+    grid_reduce2<BLOCK>(a.counter, epoch, par, xl, 0.0, a.partial, sh, res, xlung, d1);
+    // r = b - A x0 ; z = M^-1 r ; p = B = 0
+    for (int i = tid; i < cnt; i += BLOCK) {
+        const int k = row0 + i;
+        const double r = a.rhs[k] - dia_row(a.A, dg, a.x, k, a.n);
+        rs[i] = r;
+        a.z[k] = r * dinv[k];
+        ps[i] = 0.0;
+        bs[i] = 0.0;
+        if (a.xres) xs[i] = a.x[k];
+    }
+    grid_barrier(a.counter, epoch);
+    double beta = 0.0, err = 0.0;
+    int niter = 1;
+    const double *z = a.z;      // NOT __restrict__/read-only: rewritten every iteration by other SMs
+    const int o2 = a.A.off[2], o4 = a.A.off[4], o6 = a.A.off[6];      // off[1] = 1, off[3] = o2 + 1, off[5] = o4 + 1, off[7] = o6 + 1 (checked by the host)
+    const int last = (cnt - 1) & ~1;                                   // first row of the last pair
+    const int iwarp_end = cnt;                                         // a warp runs a pass while its first pair exists
+    for (;;) {
+        // ---- phase A: B = A z + beta B, p = z + beta p, (p.r), (p.B)
+        double s_pr = 0.0, s_pb = 0.0;
+        for (int iw = 2 * (tid - lane); iw < iwarp_end; iw += 2 * BLOCK) {
+            const int i_own = iw + 2 * lane;
+            const bool act = i_own < cnt, ok1 = i_own + 1 < cnt;
+            const int i = act ? i_own : last;                          // idle lanes of the last warp shadow the last pair (their shuffles feed nobody)
+            const bool ehi = lane == 31 || i_own + 2 >= cnt, elo = lane == 0;
+            const int k = row0 + i;
+            // centre window z[k-1..k+2]: (z[k], z[k+1]) is the aligned pair
+            const double2 zc = *reinterpret_cast<const double2 *>(z + k);
+            double zm = __shfl_up_sync(FULLMASK, zc.y, 1), zp = __shfl_down_sync(FULLMASK, zc.x, 1);
+            if (elo) zm = z[k - 1];
+            if (ehi) zp = z[k + 2];
+            const double2 dd = *reinterpret_cast<const double2 *>(dg + k);
+            const double2 u1 = *reinterpret_cast<const double2 *>(a.A.d[1] + k);
+            // lower part of diagonal 1: A1[k-1] (from the lane below), A1[k] = u1.x
+            double l1 = __shfl_up_sync(FULLMASK, u1.y, 1);
+            if (elo) l1 = a.A.d[1][k - 1];
+            double a0 = dd.x * zc.x, a1 = dd.y * zc.y;
+            a0 += u1.x * zc.y;  a1 += u1.y * zp;
+            a0 += l1 * zm;      a1 += u1.x * zc.x;
+            // the three offset pairs (o, o+1), one after the other (keeps the live registers under the 64 a 1024-thread CTA gets)
+            pair_group<(PAR & 1) != 0>(a.A, z, 2, o2, k, elo, ehi, a0, a1);
+            pair_group<(PAR & 2) != 0>(a.A, z, 4, o4, k, elo, ehi, a0, a1);
+            pair_group<(PAR & 4) != 0>(a.A, z, 6, o6, k, elo, ehi, a0, a1);
+            if (act) {
+                double2 pv = *reinterpret_cast<double2 *>(ps + i), bv = *reinterpret_cast<double2 *>(bs + i);
+                const double2 rv = *reinterpret_cast<const double2 *>(rs + i);
+                pv.x = zc.x + beta * pv.x; pv.y = zc.y + beta * pv.y;
+                bv.x = a0 + beta * bv.x;   bv.y = a1 + beta * bv.y;
+                s_pr += pv.x * rv.x; s_pb += pv.x * bv.x;
+                if (ok1) {
+                    s_pr += pv.y * rv.y; s_pb += pv.y * bv.y;
+                    *reinterpret_cast<double2 *>(ps + i) = pv; *reinterpret_cast<double2 *>(bs + i) = bv;
+                } else { ps[i] = pv.x; bs[i] = bv.x; }
+            }
+        }
+        double pr, pb;
+        grid_reduce2<BLOCK>(a.counter, epoch, par, s_pr, s_pb, a.partial, sh, res, pr, pb);
+        const double alfa = pr / pb;
+        // ---- phase B: r -= alfa B, x += alfa p, z = M^-1 r, (B.z), ||r_free||^2
+        double s_bz = 0.0, s_rr = 0.0;
+        for (int i = 2 * tid, j = 0; i < cnt; i += 2 * BLOCK, ++j) {
+            const int k = row0 + i;
+            const bool ok1 = i + 1 < cnt;
+            const double2 bv = *reinterpret_cast<const double2 *>(bs + i), pv = *reinterpret_cast<const double2 *>(ps + i);
+            double2 rv = *reinterpret_cast<double2 *>(rs + i);
+            const double2 dv = *reinterpret_cast<const double2 *>(dinv + k);
+            rv.x -= alfa * bv.x; rv.y -= alfa * bv.y;
+            double2 zz; zz.x = rv.x * dv.x; zz.y = rv.y * dv.y;
+            s_bz += bv.x * zz.x;
+            if (!((dmask >> (2 * j)) & 1u)) s_rr += rv.x * rv.x;
+            if (ok1) {
+                double2 xv = *reinterpret_cast<double2 *>(xs + i);
+                xv.x += alfa * pv.x; xv.y += alfa * pv.y;
+                *reinterpret_cast<double2 *>(xs + i) = xv;
+                *reinterpret_cast<double2 *>(rs + i) = rv;
+                *reinterpret_cast<double2 *>(a.z + k) = zz;
+                s_bz += bv.y * zz.y;
+                if (!((dmask >> (2 * j + 1)) & 1u)) s_rr += rv.y * rv.y;
+            } else { xs[i] += alfa * pv.x; rs[i] = rv.x; a.z[k] = zz.x; }
+        }
+        double bz, rr;
+        grid_reduce2<BLOCK>(a.counter, epoch, par, s_bz, s_rr, a.partial, sh, res, bz, rr);
         beta = -bz / pb;
         err = xlung > 0.0 ? sqrt(rr / xlung) : sqrt(rr / a.n);
         if (err > a.tol && niter < a.itmax) { ++niter; continue; }
@@ -2078,7 +2308,8 @@ struct CathySim {
     DBuf<double> wr, wz, wp0, wp1, wbv, partial, store_part;
     DBuf<double> dis, wq0, wq1;      // k_pcg2: 1/sqrt(diag), two more work vectors
     bool scaled = false;             // off-diagonals of A currently hold the symmetrically scaled matrix
-    int pcg_algo = 3;                // 3: k_pcg_res (CG vectors resident in shared memory; default, falls back to 1 when they do not fit),
+    int pcg_algo = 4;                // 4: k_pcg_res2 (CG vectors resident in shared memory, paired rows; default, falls back to 1 when they do not fit),
+                                     // 3: k_pcg_res (first resident version, one row per thread),
                                      // 1: k_pcg (vectors streamed from HBM/L2), 2: k_pcg2 (scaled, single reduction); CATHY_PCG_ALGO
     int res_rows = 0, res_x = 0, res_prefetch = 0;   // k_pcg_res: rows per CTA (0 = does not fit), x resident too, L2 prefetch of the diagonals
     DBuf<double> Ju, Jl, dinv, dckrw, detai, ts, s1, ws, wsh, wt;   // Newton: Jacobian diagonals, Jacobi scaling, derivative curves, element factors, BiCGSTAB vectors
@@ -2658,6 +2889,13 @@ static int solve_system2(CathySim *S)
     S->launches += 1;
     return 0;
 }
+static const void *pcg_res2_fn(const CathySim *S)
+{
+    static const void *const fn[8] = {(const void *)k_pcg_res2<1024, 0>, (const void *)k_pcg_res2<1024, 1>, (const void *)k_pcg_res2<1024, 2>, (const void *)k_pcg_res2<1024, 3>,
+                                      (const void *)k_pcg_res2<1024, 4>, (const void *)k_pcg_res2<1024, 5>, (const void *)k_pcg_res2<1024, 6>, (const void *)k_pcg_res2<1024, 7>};
+    const int nc1 = S->ncol + 1, o2 = nc1, o4 = S->nnod - nc1 - 1, o6 = S->nnod - 1;    // = off[2], off[4], off[6] (set later, by the mesh builder)
+    return fn[(o2 & 1) | ((o4 & 1) << 1) | ((o6 & 1) << 2)];
+}
 static int solve_system(CathySim *S)
 {
     if (!S->dd && S->pcg_algo == 2) return solve_system2(S);
@@ -2683,12 +2921,13 @@ static int solve_system(CathySim *S)
     a.own = nullptr;
     a.prefetch = S->pcg_prefetch;
     if (S->dd) { fn = (void *)k_pcg<1024, true, true>; a.own = S->own.p; a.dd = S->comm->ctx; }
-    if (!S->dd && S->pcg_algo == 3 && S->res_rows > 0) {
-        // CG vectors resident in shared memory (k_pcg_res): one 1024-thread CTA per SM owns res_rows consecutive rows
+    if (!S->dd && (S->pcg_algo == 3 || S->pcg_algo == 4) && S->res_rows > 0) {
+        // CG vectors resident in shared memory (k_pcg_res2 / k_pcg_res): one 1024-thread CTA per SM owns res_rows consecutive rows
         a.rows_cta = S->res_rows; a.xres = S->res_x; a.prefetch = S->res_prefetch;
         const size_t smem = (size_t)(3 + S->res_x) * S->res_rows * sizeof(double);
-        if (S->pcg_shared_gpu) { k_pcg_res<1024><<<S->grid_pcg, 1024, smem, S->st>>>(a); CK(cudaGetLastError()); }
-        else CK(cudaLaunchCooperativeKernel((void *)k_pcg_res<1024>, dim3(S->grid_pcg), dim3(1024), args, smem, S->st));
+        const void *fres = S->pcg_algo == 4 ? pcg_res2_fn(S) : (const void *)k_pcg_res<1024>;
+        if (S->pcg_shared_gpu) CK(cudaLaunchKernel(fres, dim3(S->grid_pcg), dim3(1024), args, smem, S->st));
+        else CK(cudaLaunchCooperativeKernel(fres, dim3(S->grid_pcg), dim3(1024), args, smem, S->st));
         CK(cudaEventRecord(S->evp1, S->st));
         S->launches++;
         return 0;
@@ -3129,10 +3368,16 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
         for (int r = 0; r < S->neu.nrec; ++r) if (S->neu.n2d[r] < 0) S->free_drain = true;
     }
     S->ld = ((size_t)S->n + 31) / 32 * 32;
-    if (!S->dd && S->pcg_algo == 3) {
-        // k_pcg_res: r, p, B (and x if there is room) of a CTA's rows stay in its shared memory for the whole solve
+    if (!S->dd && S->pcg_algo == 4) {
+        // k_pcg_res2 pairs the stencil offsets (o, o+1); the prism-split DEM mesh always yields {1 | NC1, NC1+1 | NNOD-NC1-1, NNOD-NC1 | NNOD-1, NNOD}
+        const int nc1 = S->ncol + 1, o[NDIAG] = {0, 1, nc1, nc1 + 1, S->nnod - nc1 - 1, S->nnod - nc1, S->nnod - 1, S->nnod};
+        if (!(o[3] == o[2] + 1 && o[5] == o[4] + 1 && o[7] == o[6] + 1 && S->grid_pcg <= 160)) S->pcg_algo = 3;
+    }
+    if (!S->dd && (S->pcg_algo == 3 || S->pcg_algo == 4)) {
+        // k_pcg_res*: r, p, B (and x if there is room) of a CTA's rows stay in its shared memory for the whole solve
+        const void *fres = S->pcg_algo == 4 ? pcg_res2_fn(S) : (const void *)k_pcg_res<1024>;
         cudaFuncAttributes at;
-        CK(cudaFuncGetAttributes(&at, (const void *)k_pcg_res<1024>));
+        CK(cudaFuncGetAttributes(&at, fres));
         int optin = 0;
         CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, p.device));
         const size_t avail = (size_t)optin > at.sharedSizeBytes ? (size_t)optin - at.sharedSizeBytes : 0;
@@ -3145,7 +3390,7 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
             // stream from HBM and the prefetch pays (+13 % at 1.32 M rows)
             S->res_prefetch = S->pcg_prefetch && (size_t)S->n * 64 > ((size_t)64 << 20);
             if (const char *e = getenv("CATHY_PCG_RES_PREFETCH")) S->res_prefetch = atoi(e);
-            CK(cudaFuncSetAttribute((const void *)k_pcg_res<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
+            CK(cudaFuncSetAttribute(fres, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
         }
     }
     S->halo = ((size_t)S->nnod + 1 + 31) / 32 * 32;
@@ -3722,8 +3967,8 @@ int32_t cathy_dd_start(CathySim *S)
 }
 int32_t cathy_solver_info(const CathySim *S, int64_t info[4])
 {
-    const bool res = !S->dd && S->pcg_algo == 3 && S->res_rows > 0;
-    info[0] = S->newton ? 10 : res ? 3 : (!S->dd && S->pcg_algo == 2) ? 2 : 1;
+    const bool res = !S->dd && (S->pcg_algo == 3 || S->pcg_algo == 4) && S->res_rows > 0;
+    info[0] = S->newton ? 10 : res ? S->pcg_algo : (!S->dd && S->pcg_algo == 2) ? 2 : 1;
     info[1] = res ? S->res_rows : 0; info[2] = res ? S->res_x : 0; info[3] = S->grid_pcg;
     return 0;
 }
