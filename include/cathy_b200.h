@@ -163,6 +163,12 @@ int32_t cathy_step(CathySim *sim, CathyStepReport *rep);
  * Any pointer may be NULL.  psi,sw,ckrw,qtranie: [N]; pond,atmact,atmpot,ovfl: [NNOD]; ifatm [NNOD]. */
 int32_t cathy_get_state(CathySim *sim, double *psi, double *sw, double *ckrw, double *qtranie,
                         double *pond, double *atmact, double *atmpot, double *ovfl, int32_t *ifatm);
+/* The same read-back, pipelined: returns at once; the copies land in the caller's buffers (page-locked memory for full overlap)
+ * while later cathy_step calls compute.  cathy_state_wait blocks until the last requested read-back is complete; a second
+ * cathy_get_state_async waits (on the device) for the first to drain, so two sets of host buffers suffice to overlap every step. */
+int32_t cathy_get_state_async(CathySim *sim, double *psi, double *sw, double *ckrw, double *qtranie,
+                              double *pond, double *atmact, double *atmpot, double *ovfl, int32_t *ifatm);
+int32_t cathy_state_wait(CathySim *sim);
 /* Darcy velocities at the current state: VEL3D (SRC/vel3d.f) per element [NT] in the processor's element order (nodes of an
  * element sorted ascending under Picard, SRC/grdsys.f:63) and VNOD3D (SRC/vnod3d.f) per node [N] -- what DETOUT prints to
  * velelt / velnod and VTKRIS3D to vtk/1NN.vtk (SRC/detout.f:35, SRC/vtkris3d.f).  Any pointer may be NULL. */

@@ -188,7 +188,7 @@ class CathyLib:
                "initial_storage", "step", "get_state", "get_velocity", "get_recharge", "get_wtdepth", "set_psi", "upload_atm_record", "debug_assemble", "debug_spmv", "debug_solve"]
 
     # entry points only the product library has (in-process ensemble support); bound when present
-    PRODUCT_ONLY = ["pack_state", "unpack_psi", "restart", "set_soil", "set_atm_table", "dd_export", "dd_connect", "dd_connect_local", "dd_start", "dd_info", "solver_info"]
+    PRODUCT_ONLY = ["pack_state", "unpack_psi", "restart", "set_soil", "set_atm_table", "dd_export", "dd_connect", "dd_connect_local", "dd_start", "dd_info", "solver_info", "get_state_async", "state_wait"]
 
     def __init__(self, path: str, prefix: str):
         if not os.path.exists(path):
@@ -223,6 +223,8 @@ class CathyLib:
             f["solver_info"].argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
             f["dd_connect_local"].argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
             f["dd_start"].argtypes = [C.c_void_p]
+            f["get_state_async"].argtypes = [C.c_void_p, _D, _D, _D, _D, _D, _D, _D, _D, _I]
+            f["state_wait"].argtypes = [C.c_void_p]
         f["sizeof_problem"].restype = C.c_int64
         f["sizeof_report"].restype = C.c_int64
         f["last_error"].restype = C.c_char_p
@@ -322,6 +324,17 @@ class Simulation:
         if rc != 0:
             raise CathyLibraryError(f"get_state failed ({rc}): {self.lib.error()}")
         return out
+
+    def state_async(self, out: dict) -> dict:
+        """Pipelined ``state``: returns at once, ``out`` (page-locked buffers from ``state_buffers(pinned=True)``) is valid after
+        ``state_wait()``; later ``step()`` calls overlap with the copies.  Alternate between two buffer sets."""
+        self._ck(self.lib.f["get_state_async"](self.h, _dp(out["psi"]), _dp(out["sw"]), _dp(out["ckrw"]), _dp(out["qtranie"]),
+                                               _dp(out["pond"]), _dp(out["atmact"]), _dp(out["atmpot"]), _dp(out["ovfl"]),
+                                               _ip(out["ifatm"])), "get_state_async")
+        return out
+
+    def state_wait(self) -> None:
+        self._ck(self.lib.f["state_wait"](self.h), "state_wait")
 
     def velocity(self, nodal: bool = True) -> dict:
         """Darcy velocities at the current state: per element (VEL3D) and, optionally, per node (VNOD3D)."""

@@ -247,29 +247,47 @@ __global__ void k_tet_avg(int nt, const int4 *__restrict__ tet, const double *__
 // ------------------------------------------------------------------------------------------
 // The lists are stored ELL-style, transposed: entry c of row k of diagonal d sits at [c][k], so that
 // consecutive threads (rows) read consecutive addresses; rows with fewer entries are padded with coef 0.
-struct EllFamily { const int *tet; const double *coef; const double *coef2; int w; int pad; };
+struct EllFamily { const int *tet; const double *coef; const double *coef2; int w; int pad; };   // node.pad = 1: node.tet == diag[0].tet entry for entry
 struct EllPlan { EllFamily diag[NDIAG]; EllFamily node; long long ld; };
 __global__ void __launch_bounds__(RED_BLOCK) k_assemble(int n, EllPlan P, const double *__restrict__ krt, const double *__restrict__ e1t,
                                                         Diag A, double *__restrict__ grav, double *__restrict__ m2)
 {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const EllFamily f = P.node;
+        double g = 0.0, m = 0.0;
+        if (P.node.pad) {
+            // the node family lists the tets around node k in the same order as the main-diagonal family (both are filled
+            // tet by tet): one index stream and one gather of kr serve both
+            const EllFamily f0 = P.diag[0];
+            double acc = 0.0;
+            for (int c = 0; c < f0.w; ++c) {
+                size_t q = (size_t)c * P.ld + k;
+                const int t = f0.tet[q];
+                const double kr = krt[t];
+                acc += kr * f0.coef[q];
+                g += kr * f.coef[q];
+                m += e1t[t] * f.coef2[q];
+            }
+            A.d[0][k] = acc;
+        }
 #pragma unroll
         for (int d = 0; d < NDIAG; ++d) {
-            const EllFamily f = P.diag[d];
+            if (d == 0 && P.node.pad) continue;
+            const EllFamily fd = P.diag[d];
             double acc = 0.0;
-            for (int c = 0; c < f.w; ++c) {
+            for (int c = 0; c < fd.w; ++c) {
                 size_t q = (size_t)c * P.ld + k;
-                acc += krt[f.tet[q]] * f.coef[q];
+                acc += krt[fd.tet[q]] * fd.coef[q];
             }
             A.d[d][k] = acc;
         }
-        const EllFamily f = P.node;
-        double g = 0.0, m = 0.0;
-        for (int c = 0; c < f.w; ++c) {
-            size_t q = (size_t)c * P.ld + k;
-            int t = f.tet[q];
-            g += krt[t] * f.coef[q];
-            m += e1t[t] * f.coef2[q];
+        if (!P.node.pad) {
+            for (int c = 0; c < f.w; ++c) {
+                size_t q = (size_t)c * P.ld + k;
+                int t = f.tet[q];
+                g += krt[t] * f.coef[q];
+                m += e1t[t] * f.coef2[q];
+            }
         }
         grav[k] = g;
         m2[k] = m;
@@ -2276,6 +2294,10 @@ struct CathySim {
     int64_t pcg_iters = 0, pcg_solves = 0;
     int sms = 148, grid_n = 0, grid_pcg = 0, pcg_block = 1024, pcg_custom = 1, pcg_minb = 0, pcg_prefetch = 1;
     unsigned int barrier_epoch = 0;
+    cudaStream_t st_copy = nullptr;          // cathy_get_state_async: drain stream, snapshot buffers
+    cudaEvent_t ev_snap = nullptr, ev_drained = nullptr;
+    DBuf<double> snap;
+    DBuf<int> snap_i;
     DBuf<unsigned int> d_counter;
     int64_t launches = 0;
     // host mesh kept for export
@@ -2620,7 +2642,8 @@ static int build_static(CathySim *S)
     if (newton) { rc |= S->ell_loc.upload(e_loc); rc |= S->tet_k0.upload(tet_k0); rc |= S->tet_gz.upload(tet_gz); rc |= S->tet_vol.upload(tet_vol); }
     for (int d = 0; d < NDIAG; ++d) S->fam_off[d] = fam_off[d];
     for (int d = 0; d < NDIAG; ++d) { S->plan.diag[d].tet = S->ell_tet.p + fam_off[d]; S->plan.diag[d].coef = S->ell_coef.p + fam_off[d]; S->plan.diag[d].coef2 = nullptr; S->plan.diag[d].w = wd[d]; S->plan.diag[d].pad = 0; }
-    S->plan.node.tet = S->ell_tet.p + fam_off[NDIAG]; S->plan.node.coef = S->ell_coef.p + fam_off[NDIAG]; S->plan.node.coef2 = S->ell_coef2.p; S->plan.node.w = wnode; S->plan.node.pad = 0;
+    S->plan.node.tet = S->ell_tet.p + fam_off[NDIAG]; S->plan.node.coef = S->ell_coef.p + fam_off[NDIAG]; S->plan.node.coef2 = S->ell_coef2.p; S->plan.node.w = wnode;
+    S->plan.node.pad = wnode == wd[0] && std::memcmp(e_tet.data() + fam_off[0], e_tet.data() + fam_off[NDIAG], (size_t)wnode * ld * sizeof(int)) == 0;
     S->plan.ld = (long long)ld;
     if (rc) FAIL(-101, "device allocation/upload of static tables failed: %s", cudaGetErrorString(cudaGetLastError()));
     return 0;
@@ -3203,6 +3226,7 @@ void cathy_destroy(CathySim *S)
     if (S->ev1) cudaEventDestroy(S->ev1);
     if (S->evp0) cudaEventDestroy(S->evp0);
     if (S->evp1) cudaEventDestroy(S->evp1);
+    if (S->st_copy) { cudaStreamSynchronize(S->st_copy); cudaStreamDestroy(S->st_copy); cudaEventDestroy(S->ev_snap); cudaEventDestroy(S->ev_drained); }
     if (S->st) cudaStreamDestroy(S->st);
     delete[] S->p.atm_time;
     delete S;
@@ -3617,6 +3641,48 @@ int32_t cathy_get_state(CathySim *S, double *psi, double *sw, double *ckrw, doub
     if (ovfl) CK(cudaMemcpyAsync(ovfl, S->ovflnod.p, bs, cudaMemcpyDeviceToHost, S->st));
     if (ifatm) CK(cudaMemcpyAsync(ifatm, S->ifatm.p, (size_t)S->nnod * sizeof(int), cudaMemcpyDeviceToHost, S->st));
     CK(cudaStreamSynchronize(S->st));
+    return 0;
+}
+
+// Pipelined read-back: the state is snapshotted device-to-device on the compute stream (tens of microseconds), then a second
+// stream drains the snapshot to the caller's (page-locked) buffers while the next cathy_step computes.
+int32_t cathy_get_state_async(CathySim *S, double *psi, double *sw, double *ckrw, double *qtranie, double *pond, double *atmact, double *atmpot,
+                              double *ovfl, int32_t *ifatm)
+{
+    CK(cudaSetDevice(S->p.device));
+    const size_t n = (size_t)S->n, nn = (size_t)S->nnod;
+    if (!S->st_copy) {
+        CK(cudaStreamCreateWithFlags(&S->st_copy, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&S->ev_snap, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&S->ev_drained, cudaEventDisableTiming));
+        if (S->snap.alloc(4 * n + 4 * nn) || S->snap_i.alloc(nn)) FAIL(-101, "cathy_get_state_async: snapshot allocation failed");
+    } else
+        CK(cudaStreamWaitEvent(S->st, S->ev_drained, 0));       // the previous snapshot must have left the staging buffers
+    struct Item { double *host; const double *dev; size_t cnt; };
+    const Item items[8] = {{psi, S->pnew.p, n}, {sw, S->sw.p, n}, {ckrw, S->ckrw.p, n}, {qtranie, S->qtranie.p, n},
+                           {pond, S->pondnod.p, nn}, {atmact, S->atmact.p, nn}, {atmpot, S->atmpot.p, nn}, {ovfl, S->ovflnod.p, nn}};
+    size_t off = 0;
+    for (const Item &it : items) {
+        if (it.host) CK(cudaMemcpyAsync(S->snap.p + off, it.dev, it.cnt * sizeof(double), cudaMemcpyDeviceToDevice, S->st));
+        off += it.cnt;
+    }
+    if (ifatm) CK(cudaMemcpyAsync(S->snap_i.p, S->ifatm.p, nn * sizeof(int), cudaMemcpyDeviceToDevice, S->st));
+    CK(cudaEventRecord(S->ev_snap, S->st));
+    CK(cudaStreamWaitEvent(S->st_copy, S->ev_snap, 0));
+    off = 0;
+    for (const Item &it : items) {
+        if (it.host) CK(cudaMemcpyAsync(it.host, S->snap.p + off, it.cnt * sizeof(double), cudaMemcpyDeviceToHost, S->st_copy));
+        off += it.cnt;
+    }
+    if (ifatm) CK(cudaMemcpyAsync(ifatm, S->snap_i.p, nn * sizeof(int), cudaMemcpyDeviceToHost, S->st_copy));
+    CK(cudaEventRecord(S->ev_drained, S->st_copy));
+    return 0;
+}
+int32_t cathy_state_wait(CathySim *S)
+{
+    if (!S->st_copy) return 0;
+    CK(cudaSetDevice(S->p.device));
+    CK(cudaStreamSynchronize(S->st_copy));
     return 0;
 }
 

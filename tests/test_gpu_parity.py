@@ -82,6 +82,53 @@ def test_pcg_solution_matches_oracle(gpu_lib, oracle_mod, weill, dt):
     assert np.max(np.abs(xg - xc)) <= 1e-7 * max(np.abs(xc).max(), 1e-12), (np.abs(xg - xc).max(), np.abs(xc).max(), ng, nc)
 
 
+@pytest.mark.parametrize("size", [(6, 7, 4), (7, 6, 5), (7, 7, 3), (6, 6, 4), (60, 50, 8), (120, 120, 20)])
+def test_pcg_kernel_variants_agree(gpu_lib, tmp_path, monkeypatch, size):
+    """k_pcg (streaming), k_pcg_res (resident, one row per thread) and k_pcg_res2 (resident, paired rows: aligned 16-byte loads +
+    lane shuffles) run the same recurrence: same iteration count, solutions equal to rounding.  The sizes cover the three possible
+    parity combinations of the stencil offsets NC1, NNOD-NC1-1, NNOD-1 (template variants 6, 5, 3 of k_pcg_res2), odd and even row
+    counts, CTAs without rows, and (last size) more than one pass of 2048 rows per CTA."""
+    from pycathy_wrapper_b200 import synthetic
+    from pycathy_wrapper_b200.capi import Simulation
+    from pycathy_wrapper_b200.project import load_project
+    nrow, ncol, nstr = size
+    d = str(tmp_path / "prj")
+    synthetic.make_project(d, nrow, ncol, nstr, ic=("wt", 0.6), ISIMGR=1, TMAX=100.0, TIMPRT=[100.0], NODVP=[1])
+    prj = load_project(d)
+    sols = {}
+    for algo in (1, 3, 4):
+        monkeypatch.setenv("CATHY_PCG_ALGO", str(algo))
+        sim = Simulation(gpu_lib, prj)
+        assert sim.solver_info()["kernel"] == algo
+        sim.debug_assemble(7.0)
+        sols[algo] = sim.debug_solve()[:3]
+        sim.close()
+    x1, n1, e1 = sols[1]
+    for algo in (3, 4):
+        x, nit, err = sols[algo]
+        assert abs(nit - n1) <= 1 and err <= 1e-10
+        assert np.max(np.abs(x - x1)) <= 1e-10 * max(np.abs(x1).max(), 1e-300), (algo, np.abs(x - x1).max(), np.abs(x1).max())
+
+
+def test_state_async_equals_state(gpu_lib, weill):
+    """cathy_get_state_async + cathy_state_wait (snapshot drained by a second stream while the next step computes) returns
+    exactly what the blocking cathy_get_state returns for the same step."""
+    from pycathy_wrapper_b200.capi import Simulation
+    g = Simulation(gpu_lib, weill)
+    bufs = [g.state_buffers(pinned=True) for _ in range(2)]
+    want = []
+    for i in range(4):
+        g.step()
+        want.append({k: v.copy() for k, v in g.state().items()})
+        g.state_async(bufs[i & 1])
+        if i >= 1:      # the previous read-back completes while this step was computed; check it after the wait
+            g.state_wait()
+            for k, v in want[i].items():
+                assert np.array_equal(bufs[i & 1][k], v), k
+    g.state_wait()
+    g.close()
+
+
 def _run_both(gpu_lib, oracle_mod, prj, nsteps=None, store_rtol=1e-9):
     from pycathy_wrapper_b200.capi import Simulation
     g, c = Simulation(gpu_lib, prj), oracle_mod.simulation(prj)
