@@ -68,11 +68,27 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
-def make_workload(size, member: int = 0, iopt: int = 1):
+ROUTE200 = os.path.join(ROOT, "tests", "golden", "route200_prepro.tar.xz")
+
+
+def make_workload(size, member: int = 0, iopt: int = 1, routing: bool = False):
     nrow, ncol, nstr = size
     d = tempfile.mkdtemp(prefix="cathy_bench_")
     ks = 1.88e-4 * (1.0 + 0.05 * member)                     # ensemble members differ in Ks (weak scaling replicas)
     row = (ks, ks, ks, 1.0e-5, 0.55, 1.46, 0.15, 0.03125)
+    if routing:
+        # BASELINE config 3: Newton + coupled surface routing.  A storm (1e-4 m/s for 10 min) on a hillslope whose water table
+        # sits 0.3 m below the surface: the lower slope saturates, ponds and runs off through SURF_FLOWTRA.  The routing rasters
+        # of the 200 x 200 DEM come from the reference's own pre-processor (tests/golden/make_route200.py).
+        if (nrow, ncol) != (200, 200):
+            raise SystemExit("bench.py: the coupled workload ships routing rasters for the 200x200 DEM only")
+        rain = [(0.0, 0.0), (60.0, 1.0e-4), (600.0, 1.0e-4), (660.0, 0.0), (1.0e9, 0.0)]
+        synthetic.make_project(d, nrow, ncol, nstr, ic=("wt", 0.3), ISIMGR=2, DELTAT=1.0, DTMIN=1e-4, DTMAX=100.0, TMAX=7200.0, TIMPRT=[7200.0],
+                               NODVP=[1], soil_rows=[row] * nstr, IOPT=iopt, ISOLV=0 if iopt == 2 else 2, atmbc=rain)
+        subprocess.run(["tar", "-xJf", ROUTE200, "-C", os.path.join(d, "prepro")], check=True)
+        prj = load_project(d)
+        shutil.rmtree(d, ignore_errors=True)
+        return prj
     synthetic.make_project(d, nrow, ncol, nstr, ic=("wt", 1.0), ISIMGR=1, DELTAT=1.0, DTMIN=1e-2, DTMAX=100.0,
                            TMAX=7200.0, TIMPRT=[7200.0], NODVP=[1], soil_rows=[row] * nstr, hspatm=0, IOPT=iopt, ISOLV=0 if iopt == 2 else 2,
                            atmbc=[(0.0, np.zeros((nrow + 1) * (ncol + 1))), (60.0, np.full((nrow + 1) * (ncol + 1), 2.0e-5)),
@@ -132,8 +148,9 @@ def run_ours(args, size):
     if world > 1:
         dist.barrier()
     lib = load_library()
-    newton = args.workload == "newton"
-    prj = make_workload(size, member=rank, iopt=2 if newton else 1)
+    newton = args.workload in ("newton", "coupled")
+    coupled = args.workload == "coupled"
+    prj = make_workload(size, member=rank, iopt=2 if newton else 1, routing=coupled)
     nnod = prj.nnod
 
     def barrier():
@@ -246,8 +263,8 @@ def run_ours(args, size):
         "metric": "node-timesteps/s", "value": value, "unit": "node-timesteps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall_s / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic %dx%d DEM x %d layers (%d nodes, %d tets), van Genuchten, %s, infiltration pulse on a hillslope with a water table 2 m deep (INDP=3), "
-                               "ISIMGR=1, first %d accepted steps after %d warm-up" % (size[1], size[0], size[2], n, sim.nt, "Newton+BiCGSTAB (BASELINE config 3 without the surface-routing coupling)" if newton else "Picard+PCG", args.steps, args.warmup),
+        "config": {"workload": "synthetic %dx%d DEM x %d layers (%d nodes, %d tets), van Genuchten, %s, %s"
+                               ", first %d accepted steps after %d warm-up" % (size[1], size[0], size[2], n, sim.nt, ("Newton+BiCGSTAB, coupled surface routing (BASELINE config 3)" if coupled else "Newton+BiCGSTAB (BASELINE config 3 without the surface-routing coupling)") if newton else "Picard+PCG", "storm of 1e-4 m/s on a hillslope with a shallow water table (INDP=3, WTPOSITION 0.3), ISIMGR=2: SURF_FLOWTRA routing every step" if coupled else "infiltration pulse on a hillslope with a water table 2 m deep (INDP=3), ISIMGR=1", args.steps, args.warmup),
                    "parallelism": "1 ensemble member per GPU" if world > 1 else "single forward run",
                    "l2": "inputs larger than L2: every nonlinear iteration streams the %.2f GB gather plan and the nodal soil constants through the 126 MB L2 "
                          "between two linear solves; inside ONE solve (one persistent launch) the diagonals (%.0f MB) are re-read every PCG iteration, no flush there" % (1.27e3 * n / 1e9, n * 64 / 1e6),
@@ -267,7 +284,7 @@ def run_ours(args, size):
     }
     if rank == 0:
         if world == 1 and not args.no_cpu:
-            out["cpu_baseline"] = cpu_baseline(size, budget_s=args.cpu_budget, iopt=2 if newton else 1)
+            out["cpu_baseline"] = cpu_baseline(size, budget_s=args.cpu_budget, iopt=2 if newton else 1, routing=coupled)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -473,11 +490,11 @@ def run_partitioned(args, size):
         dist.destroy_process_group()
 
 
-def cpu_baseline(size, budget_s: float = 25.0, max_steps: int = 1000, iopt: int = 1):
+def cpu_baseline(size, budget_s: float = 25.0, max_steps: int = 1000, iopt: int = 1, routing: bool = False):
     """The CPU oracle (a C port of the reference's algorithm; the reference ELFs cannot hold this mesh)
     timed on a bounded sample of the same workload: the first accepted step(s), single thread."""
     from oracle import oracle
-    prj = make_workload(size, iopt=iopt)
+    prj = make_workload(size, iopt=iopt, routing=routing)
     sim = oracle.simulation(prj)
     t0 = time.perf_counter()
     k = 0
@@ -488,7 +505,7 @@ def cpu_baseline(size, budget_s: float = 25.0, max_steps: int = 1000, iopt: int 
             break
     dt = time.perf_counter() - t0
     return {"value": sim.n * k / dt, "unit": "node-timesteps/s", "cores": 1, "kind": "port",
-            "sample": "first %d accepted time step(s) of the same workload (%.1f s of CPU work, sequential IC(0)-PCG as in the reference)" % (k, dt)}
+            "sample": "first %d accepted time step(s) of the same workload (%.1f s of CPU work, sequential %s as in the reference)" % (k, dt, "ILU(0)-BiCGSTAB" if iopt == 2 else "IC(0)-PCG")}
 
 
 def run_reference(args, size):
@@ -498,7 +515,7 @@ def run_reference(args, size):
     import __graft_entry__ as g
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], check=True)
     from oracle import oracle
-    prj = make_workload(size, iopt=2 if args.workload == "newton" else 1)
+    prj = make_workload(size, iopt=2 if args.workload in ("newton", "coupled") else 1, routing=args.workload == "coupled")
     sim = oracle.simulation(prj)
     n = sim.n
     budget = 150.0
@@ -538,7 +555,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", default=None)
-    ap.add_argument("--workload", default="picard", choices=["picard", "newton", "enkf", "partitioned"], help="picard: BASELINE config 2 (headline); newton: config 3's linearisation on the same mesh; enkf: config 4; partitioned: config 5")
+    ap.add_argument("--workload", default="picard", choices=["picard", "newton", "coupled", "enkf", "partitioned"], help="picard: BASELINE config 2 (headline); newton: config 3's linearisation on the same mesh; coupled: config 3 (Newton + surface routing); enkf: config 4; partitioned: config 5")
     ap.add_argument("--members", type=int, default=256)
     ap.add_argument("--concurrent", type=int, default=4, help="enkf workload: ensemble members advancing concurrently per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -546,7 +563,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.size is None:
-        args.size = {"picard": "200x200x20", "newton": "200x200x20", "enkf": "100x100x15", "partitioned": "1000x1000x30"}[args.workload]
+        args.size = {"picard": "200x200x20", "newton": "200x200x20", "coupled": "200x200x20", "enkf": "100x100x15", "partitioned": "1000x1000x30"}[args.workload]
     size = tuple(int(v) for v in args.size.lower().split("x"))
     if args.workload == "enkf" and args.impl == "ours":
         return run_enkf(args, size)
