@@ -77,13 +77,13 @@ def make_workload(size, member: int = 0, iopt: int = 1, routing: bool = False):
     ks = 1.88e-4 * (1.0 + 0.05 * member)                     # ensemble members differ in Ks (weak scaling replicas)
     row = (ks, ks, ks, 1.0e-5, 0.55, 1.46, 0.15, 0.03125)
     if routing:
-        # BASELINE config 3: Newton + coupled surface routing.  A storm (1e-4 m/s for 10 min) on a hillslope whose water table
-        # sits 0.3 m below the surface: the lower slope saturates, ponds and runs off through SURF_FLOWTRA.  The routing rasters
-        # of the 200 x 200 DEM come from the reference's own pre-processor (tests/golden/make_route200.py).
+        # BASELINE config 3: Newton + coupled surface routing.  A storm (1e-4 m/s for 10 min) on a saturated hillslope (water table
+        # at the surface) that starts with 5 mm of ponded water, so that SURF_FLOWTRA routes runoff from the first step on.  The
+        # routing rasters of the 200 x 200 DEM come from the reference's own pre-processor (tests/golden/make_route200.py).
         if (nrow, ncol) != (200, 200):
             raise SystemExit("bench.py: the coupled workload ships routing rasters for the 200x200 DEM only")
         rain = [(0.0, 0.0), (60.0, 1.0e-4), (600.0, 1.0e-4), (660.0, 0.0), (1.0e9, 0.0)]
-        synthetic.make_project(d, nrow, ncol, nstr, ic=("wt", 0.3), ISIMGR=2, DELTAT=1.0, DTMIN=1e-4, DTMAX=100.0, TMAX=7200.0, TIMPRT=[7200.0],
+        synthetic.make_project(d, nrow, ncol, nstr, ic=("hydrostatic",), pond=0.005, ISIMGR=2, DELTAT=1.0, DTMIN=1e-4, DTMAX=100.0, TMAX=7200.0, TIMPRT=[7200.0],
                                NODVP=[1], soil_rows=[row] * nstr, IOPT=iopt, ISOLV=0 if iopt == 2 else 2, atmbc=rain)
         subprocess.run(["tar", "-xJf", ROUTE200, "-C", os.path.join(d, "prepro")], check=True)
         prj = load_project(d)
@@ -264,7 +264,7 @@ def run_ours(args, size):
         "warmup": args.warmup, "ms_per_step": 1e3 * wall_s / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "synthetic %dx%d DEM x %d layers (%d nodes, %d tets), van Genuchten, %s, %s"
-                               ", first %d accepted steps after %d warm-up" % (size[1], size[0], size[2], n, sim.nt, ("Newton+BiCGSTAB, coupled surface routing (BASELINE config 3)" if coupled else "Newton+BiCGSTAB (BASELINE config 3 without the surface-routing coupling)") if newton else "Picard+PCG", "storm of 1e-4 m/s on a hillslope with a shallow water table (INDP=3, WTPOSITION 0.3), ISIMGR=2: SURF_FLOWTRA routing every step" if coupled else "infiltration pulse on a hillslope with a water table 2 m deep (INDP=3), ISIMGR=1", args.steps, args.warmup),
+                               ", first %d accepted steps after %d warm-up" % (size[1], size[0], size[2], n, sim.nt, ("Newton+BiCGSTAB, coupled surface routing (BASELINE config 3)" if coupled else "Newton+BiCGSTAB (BASELINE config 3 without the surface-routing coupling)") if newton else "Picard+PCG", "storm of 1e-4 m/s on a saturated hillslope (INDP=2) with 5 mm of initial ponding (IPOND=1), ISIMGR=2: SURF_FLOWTRA routing every step" if coupled else "infiltration pulse on a hillslope with a water table 2 m deep (INDP=3), ISIMGR=1", args.steps, args.warmup),
                    "parallelism": "1 ensemble member per GPU" if world > 1 else "single forward run",
                    "l2": "inputs larger than L2: every nonlinear iteration streams the %.2f GB gather plan and the nodal soil constants through the 126 MB L2 "
                          "between two linear solves; inside ONE solve (one persistent launch) the diagonals (%.0f MB) are re-read every PCG iteration, no flush there" % (1.27e3 * n / 1e9, n * 64 / 1e6),

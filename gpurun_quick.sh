@@ -1,8 +1,4 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/t_res.log; cat gpurun_out/t_res.log
-timeout 900 python gpurun_pcgvar.py > gpurun_out/pcgvar7.log 2>&1; cat gpurun_out/pcgvar7.log
-python bench.py --steps 20 --warmup 3 --no-cpu 2>gpurun_out/bench4.err | tail -1 > gpurun_out/bench4.json
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench4.json'))
-print('value %.4g e2e %.4g ms/step %.3f dev_ms/step %.3f pcg_frac %.3f pcg_share %.3f spmv_frac %.3f iters %d solves %d launches %d' % (d['value'], d['e2e']['value'], d['ms_per_step'], d['device_ms_per_step'], d['roofline']['frac'], d['roofline']['share_of_step'], d['roofline']['spmv_only']['frac'], d['config']['pcg_iters'], d['config']['pcg_solves'], d['gpu_launches']))
-PY
+for pf in 0 1; do CATHY_PCG_PREFETCH=$pf python bench.py --workload coupled --steps 20 --warmup 3 --no-cpu 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('prefetch $pf: ms/step %.3f value %.4g us/it %.2f frac %.3f share %.3f its %d' % (d['ms_per_step'], d['value'], d['roofline']['us_per_pcg_iter'], d['roofline']['frac'], d['roofline']['share_of_step'], d['config']['pcg_iters']))"; done

@@ -1388,6 +1388,7 @@ struct BicgArgs {
     unsigned int *counter;
     unsigned int epoch0;
     IterOut *out;
+    int prefetch;
 };
 template <int BLOCK, int NS>
 __device__ __forceinline__ void grid_reduce_n(unsigned int *counter, unsigned int &epoch, unsigned int &flip, const double (&in)[NS],
@@ -1426,9 +1427,19 @@ __device__ __forceinline__ void grid_reduce_n(unsigned int *counter, unsigned in
     for (int q = 0; q < NS; ++q) out[q] = sh[0][q];
     __syncthreads();
 }
+// the 15 matrix streams of the next grid-stride row, pulled into L2 while this row's FMA chain runs (as in k_pcg: the Jacobian
+// of a large mesh streams from HBM twice per iteration)
+__device__ __forceinline__ void bicg_prefetch_row(const Diag &U, const Diag &L, int kn)
+{
+#pragma unroll
+    for (int d = 0; d < NDIAG; ++d) l2_prefetch(&U.d[d][kn]);
+#pragma unroll
+    for (int d = 1; d < NDIAG; ++d) l2_prefetch(&L.d[d][kn - U.off[d]]);
+}
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab(BicgArgs a)
 {
+    const bool PF = a.prefetch != 0;
     __shared__ double sh[BLOCK / 32][5];
     unsigned int epoch = a.epoch0, flip = 0;
     const int n = a.n, stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1459,6 +1470,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab(BicgArgs a)
         // ---- v = J ph, sigma = (rt, v)
         in[0] = in[1] = in[2] = in[3] = in[4] = 0.0;
         for (int k = t0; k < n; k += stride) {
+            if (PF && k + stride < n) bicg_prefetch_row(a.U, a.L, k + stride);
             double v = di[k] != 0.0 ? dia_row_n(a.U, a.L, a.ph, k) : 0.0;
             a.v[k] = v;
             in[0] += a.rt[k] * v;
@@ -1474,6 +1486,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab(BicgArgs a)
         // ---- t = J sh; (t,s), (t,t), (rt,s), (rt,t)
         in[0] = in[1] = in[2] = in[3] = in[4] = 0.0;
         for (int k = t0; k < n; k += stride) {
+            if (PF && k + stride < n) bicg_prefetch_row(a.U, a.L, k + stride);
             double t = di[k] != 0.0 ? dia_row_n(a.U, a.L, a.sh, k) : 0.0, s = a.s[k], rt = a.rt[k];
             a.t[k] = t;
             in[0] += t * s; in[1] += t * t; in[2] += rt * s; in[3] += rt * t;
@@ -2991,6 +3004,7 @@ static int solve_system_newton(CathySim *S)
     a.U = make_diag(S, S->Ju.p); a.L = make_diag(S, S->Jl.p); a.dinv = S->dinv.p; a.rhs = S->rhs.p;
     a.x = S->pdiff.p; a.r = S->wr.p; a.rt = S->wz.p; a.p = S->wp0.p; a.ph = S->wp1.p; a.v = S->wbv.p; a.s = S->ws.p; a.sh = S->wsh.p; a.t = S->wt.p;
     a.partial = S->partial.p; a.out = S->d_iter.p; a.counter = S->d_counter.p; a.epoch0 = S->barrier_epoch;
+    a.prefetch = S->pcg_prefetch && (size_t)S->n * 240 > ((size_t)64 << 20);     // the Jacobian (2 x 15 diagonals) does not stay in L2
     void *args[] = {&a};
     CK(cudaEventRecord(S->evp0, S->st));
     if (S->pcg_shared_gpu) { k_bicgstab<1024><<<S->grid_pcg, 1024, 0, S->st>>>(a); CK(cudaGetLastError()); }

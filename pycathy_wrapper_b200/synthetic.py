@@ -140,7 +140,7 @@ def write_hapin(path: str, nrow: int, ncol: int, dx: float, dy: float) -> None:
 def make_project(path: str, nrow: int, ncol: int, nstr: int, dx: float = 0.5, dy: float = 0.5, base: float = 3.0,
                  zratio=None, dem=None, soil_rows=None, ic=("uniform", -1.0), atmbc=None, hspatm: int = 1, ieto: int = 0,
                  pmin: float = -5.0, dirbc_text: str | None = None, neubc_text: str | None = None, ivghu: int = 0,
-                 hu=(0.02, 2, 2, 0, 0.333), hun=1, huab=(-5, 1), bc=(1.2, 0, -0.345), zone=None, ivert: int = 0, **parm) -> str:
+                 hu=(0.02, 2, 2, 0, 0.333), hun=1, huab=(-5, 1), bc=(1.2, 0, -0.345), zone=None, ivert: int = 0, pond: float | None = None, **parm) -> str:
     """Write a full project directory.  `ic` = ("uniform", psi) | ("hydrostatic",) | ("wt", position);
     `atmbc` = list of (time, rate) pairs (homogeneous) -- rate in m/s, +ve = rain."""
     for sub in ("input", "prepro", "output", "vtk"):
@@ -175,14 +175,17 @@ def make_project(path: str, nrow: int, ncol: int, nstr: int, dx: float = 0.5, dy
         for r in rows:
             fh.write(" ".join("%.6E" % v for v in r) + "\n")
     with open(os.path.join(path, "input", "ic"), "w") as fh:
+        ipond = 1 if pond is not None else 0          # IPOND = 1: uniform initial ponding head (SRC/datin.f:380-403)
         if ic[0] == "uniform":
-            fh.write("0 0\tINDP IPOND\n%r\n" % float(ic[1]))
+            fh.write("0 %d\tINDP IPOND\n%r\n" % (ipond, float(ic[1])))
         elif ic[0] == "hydrostatic":
-            fh.write("2 0\tINDP IPOND\n0\tWTPOSITION\n")
+            fh.write("2 %d\tINDP IPOND\n0\tWTPOSITION\n" % ipond)
         elif ic[0] == "wt":
-            fh.write("3 0\tINDP IPOND\n%r\tWTPOSITION\n" % float(ic[1]))
+            fh.write("3 %d\tINDP IPOND\n%r\tWTPOSITION\n" % (ipond, float(ic[1])))
         else:
             raise ValueError(ic)
+        if ipond:
+            fh.write("%r\tPONDING HEAD\n" % float(pond))
     atmbc = atmbc if atmbc is not None else [(0.0, 0.0), (1.0e9, 0.0)]
     with open(os.path.join(path, "input", "atmbc"), "w") as fh:
         fh.write("%d %d\tHSPATM IETO\n" % (hspatm, ieto))

@@ -171,6 +171,24 @@ def test_storm_full_run(gpu_lib, oracle_mod):
     assert rg.q_outlet_1 > 0
 
 
+def test_initial_ponding_with_routing(gpu_lib, oracle_mod, tmp_path):
+    """IPOND = 1: 5 mm of water ponded on a saturated hillslope, routed from the first step on (the small version of bench.py's
+    `coupled` workload; the oracle is pinned byte-for-byte against the ELF on this case in tests/test_oracle_golden.py).
+    Routing rasters: the reference pre-processor's output for this 20 x 20 DEM, committed with the storm20 fixture."""
+    from pycathy_wrapper_b200.project import load_project
+    from test_oracle_golden import _ponded_project
+    d = _ponded_project(str(tmp_path / "p"))
+    src = os.path.join(GOLDEN, "storm20", "prepro")
+    for f in os.listdir(src):
+        if f.startswith("dtm_") or f == "qoi_a":
+            shutil.copy(os.path.join(src, f), os.path.join(d, "prepro", f))
+    prj = load_project(d)
+    g, c, rg, rc = _run_both(gpu_lib, oracle_mod, prj)
+    ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
+    assert ok, dmax
+    assert rg.nsurf > 0 and rg.q_outlet_1 > 0
+
+
 def test_infiltration_subsurface_only(gpu_lib, oracle_mod, tmp_path):
     """ISIMGR=1 (SWITCH_OLD path), unsaturated start, rain pulse, geometric layers."""
     from pycathy_wrapper_b200 import synthetic
