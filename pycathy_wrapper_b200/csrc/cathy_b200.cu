@@ -1389,6 +1389,9 @@ struct BicgArgs {
     unsigned int epoch0;
     IterOut *out;
     int prefetch;
+    int line;                // 1: vertical-line (one tridiagonal system per DEM column) preconditioner, 0: point Jacobi
+    int nnod, nl;            // surface nodes (= columns) and node layers (rows of a column: s, s + nnod, ...)
+    double *idn, *cp;        // Thomas factors of the column systems: 1 / pivot and the eliminated super-diagonal
 };
 template <int BLOCK, int NS>
 __device__ __forceinline__ void grid_reduce_n(unsigned int *counter, unsigned int &epoch, unsigned int &flip, const double (&in)[NS],
@@ -1436,10 +1439,57 @@ __device__ __forceinline__ void bicg_prefetch_row(const Diag &U, const Diag &L, 
 #pragma unroll
     for (int d = 1; d < NDIAG; ++d) l2_prefetch(&L.d[d][kn - U.off[d]]);
 }
+// Vertical-line preconditioner.  The layers of the DEM mesh are thin against the cell size (config 3: 0.15 m against 0.5 m), so on
+// saturated (elliptic) systems the coupling between the nodes of one DEM column dominates: M = the block diagonal of J with one
+// nonsymmetric tridiagonal block per column (sub-/super-diagonal = the +-NNOD diagonals).  Opt-in (CATHY_BICG_LINE=1): measured on
+// B200 at config 3 it saves 36 % of the BiCGSTAB iterations of the saturated storm (103 -> 66 per solve) but each iteration costs
+// 46 % more (two latency-bound column sweeps of 21 us), and it saves nothing on unsaturated systems.
+// One thread per column: Thomas factorisation once per solve, two dependent sweeps over the nl layers per application; adjacent
+// threads own adjacent columns, so every access is coalesced.  Dirichlet rows (dinv = 0) are identity rows with a zero right-hand
+// side: their factor entries are 0, which also removes them from the neighbouring rows' recurrences.
+__device__ __forceinline__ void line_factor(const BicgArgs &a, int t0, int stride)
+{
+    const double *lo = a.L.d[NDIAG - 1], *up = a.U.d[NDIAG - 1], *dg = a.U.d[0];
+    for (int sidx = t0; sidx < a.nnod; sidx += stride) {
+        double cprev = 0.0;
+        for (int l = 0, k = sidx; l < a.nl; ++l, k += a.nnod) {
+            double idn = 0.0, c = 0.0;
+            if (a.dinv[k] != 0.0) {
+                const double piv = dg[k] - (l ? lo[k - a.nnod] * cprev : 0.0);
+                idn = 1.0 / piv;
+                c = l + 1 < a.nl ? up[k] * idn : 0.0;
+            }
+            a.idn[k] = idn; a.cp[k] = c;
+            cprev = c;
+        }
+    }
+}
+__device__ __forceinline__ void line_solve(const BicgArgs &a, const double *in, double *out, int t0, int stride)
+{
+    const double *lo = a.L.d[NDIAG - 1];
+    const int nnod = a.nnod, nl = a.nl;
+    for (int sidx = t0; sidx < nnod; sidx += stride) {
+        double y = in[sidx] * a.idn[sidx];
+        out[sidx] = y;
+#pragma unroll 4
+        for (int l = 1; l < nl; ++l) {
+            const int k = sidx + l * nnod;
+            y = (in[k] - lo[k - nnod] * y) * a.idn[k];
+            out[k] = y;
+        }
+#pragma unroll 4
+        for (int l = nl - 2; l >= 0; --l) {
+            const int k = sidx + l * nnod;
+            y = out[k] - a.cp[k] * y;
+            out[k] = y;
+        }
+    }
+}
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab(BicgArgs a)
 {
     const bool PF = a.prefetch != 0;
+    const bool LINE = a.line != 0;
     __shared__ double sh[BLOCK / 32][5];
     unsigned int epoch = a.epoch0, flip = 0;
     const int n = a.n, stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1451,6 +1501,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab(BicgArgs a)
         a.x[k] = b * d;
         if (d != 0.0) in[0] += b * b;
     }
+    if (LINE) line_factor(a, t0, stride);
     grid_reduce_n<BLOCK, 5>(a.counter, epoch, flip, in, a.partial, sh, out);
     const double xlung = out[0];
     // r0 = b - J x0 (zero on Dirichlet rows), rt = r0, p = r0, ph = M^-1 p; rho = (rt, r0)
@@ -1465,6 +1516,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab(BicgArgs a)
     double rho = out[0], err = xlung > 0.0 ? sqrt(out[0] / xlung) : sqrt(out[0] / n);
     int niter = 0;
     if (rho == 0.0 || err <= a.tol) { if (t0 == 0) { a.out->pcg_niter = 1; a.out->pcg_err = err; a.out->pad = (int)epoch; } return; }
+    if (LINE) { line_solve(a, a.p, a.ph, t0, stride); grid_barrier(a.counter, epoch); }
     for (;;) {
         ++niter;
         // ---- v = J ph, sigma = (rt, v)
@@ -1480,9 +1532,11 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab(BicgArgs a)
         // ---- s = r - alpha v, sh = M^-1 s
         for (int k = t0; k < n; k += stride) {
             double s = a.r[k] - alpha * a.v[k];
-            a.s[k] = s; a.sh[k] = s * di[k];
+            a.s[k] = s;
+            if (!LINE) a.sh[k] = s * di[k];
         }
         grid_barrier(a.counter, epoch);
+        if (LINE) { line_solve(a, a.s, a.sh, t0, stride); grid_barrier(a.counter, epoch); }
         // ---- t = J sh; (t,s), (t,t), (rt,s), (rt,t)
         in[0] = in[1] = in[2] = in[3] = in[4] = 0.0;
         for (int k = t0; k < n; k += stride) {
@@ -1505,11 +1559,13 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab(BicgArgs a)
             a.r[k] = r;
             in[0] += r * r;
             double p = r + beta * (a.p[k] - omega * a.v[k]);
-            a.p[k] = p; a.ph[k] = p * di[k];
+            a.p[k] = p;
+            if (!LINE) a.ph[k] = p * di[k];
         }
         grid_reduce_n<BLOCK, 5>(a.counter, epoch, flip, in, a.partial, sh, out);
         err = xlung > 0.0 ? sqrt(out[0] / xlung) : sqrt(out[0] / n);
         if (!(err > a.tol) || niter >= a.itmax || breakdown) break;
+        if (LINE) { line_solve(a, a.p, a.ph, t0, stride); grid_barrier(a.counter, epoch); }
         rho = rho_new;
     }
     // a breakdown (NaN / zero inner products) without convergence is reported as "ITMXCG reached" so that FLOW3D back-steps
@@ -2347,6 +2403,9 @@ struct CathySim {
                                      // 3: k_pcg_res (first resident version, one row per thread),
                                      // 1: k_pcg (vectors streamed from HBM/L2), 2: k_pcg2 (scaled, single reduction); CATHY_PCG_ALGO
     int res_rows = 0, res_x = 0, res_prefetch = 0;   // k_pcg_res: rows per CTA (0 = does not fit), x resident too, L2 prefetch of the diagonals
+    int bicg_line = 0;               // Newton: 0 = point Jacobi (default), 1 = vertical-line preconditioner (opt-in, CATHY_BICG_LINE=1: -36 % iterations but
+                                     // +46 % per iteration on the config-3 storm, no gain on unsaturated systems; profiles/r1_precond_experiment.md)
+    DBuf<double> widn, wcp;          // its Thomas factors
     DBuf<double> Ju, Jl, dinv, dckrw, detai, ts, s1, ws, wsh, wt;   // Newton: Jacobian diagonals, Jacobi scaling, derivative curves, element factors, BiCGSTAB vectors
     bool newton = false;
     // ---- row-block partition of one large mesh over several GPUs (BASELINE config 5) ----
@@ -3005,6 +3064,7 @@ static int solve_system_newton(CathySim *S)
     a.x = S->pdiff.p; a.r = S->wr.p; a.rt = S->wz.p; a.p = S->wp0.p; a.ph = S->wp1.p; a.v = S->wbv.p; a.s = S->ws.p; a.sh = S->wsh.p; a.t = S->wt.p;
     a.partial = S->partial.p; a.out = S->d_iter.p; a.counter = S->d_counter.p; a.epoch0 = S->barrier_epoch;
     a.prefetch = S->pcg_prefetch && (size_t)S->n * 240 > ((size_t)64 << 20);     // the Jacobian (2 x 15 diagonals) does not stay in L2
+    a.line = S->bicg_line; a.nnod = S->nnod; a.nl = S->nstr + 1; a.idn = S->widn.p; a.cp = S->wcp.p;
     void *args[] = {&a};
     CK(cudaEventRecord(S->evp0, S->st));
     if (S->pcg_shared_gpu) { k_bicgstab<1024><<<S->grid_pcg, 1024, 0, S->st>>>(a); CK(cudaGetLastError()); }
@@ -3219,7 +3279,7 @@ void cathy_destroy(CathySim *S)
     DBuf<int> *di[] = {&S->veg, &S->ell_tet, &S->ifatm, &S->ifatmp, &S->d_flags, &S->lv_ptr, &S->lv_cell,
                        &S->seqpos, &S->don_ptr, &S->don_cell, &S->d_nsurf};
     for (auto *b : di) b->release();
-    { DBuf<double> *nn[] = {&S->Ju, &S->Jl, &S->dinv, &S->dckrw, &S->detai, &S->ts, &S->s1, &S->ws, &S->wsh, &S->wt, &S->tet_k0, &S->tet_gz, &S->tet_vol, &S->vgm52, &S->vgmm1};
+    { DBuf<double> *nn[] = {&S->widn, &S->wcp, &S->Ju, &S->Jl, &S->dinv, &S->dckrw, &S->detai, &S->ts, &S->s1, &S->ws, &S->wsh, &S->wt, &S->tet_k0, &S->tet_gz, &S->tet_vol, &S->vgm52, &S->vgmm1};
       for (auto *b : nn) b->release(); S->ell_loc.release(); }
     S->dis.release(); S->wq0.release(); S->wq1.release();
     S->contp_flag.release(); S->contq_flag.release(); S->contp_val.release(); S->qneu.release(); S->qlist.release(); S->qpnew.release();
@@ -3374,6 +3434,7 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
     if (const char *e = getenv("CATHY_PCG_MINB")) S->pcg_minb = atoi(e);
     if (const char *e = getenv("CATHY_PCG_PREFETCH")) S->pcg_prefetch = atoi(e);
     if (const char *e = getenv("CATHY_PCG_ALGO")) S->pcg_algo = atoi(e);
+    if (const char *e = getenv("CATHY_BICG_LINE")) S->bicg_line = atoi(e);
     if (S->pcg_block != 256 && S->pcg_block != 512 && S->pcg_block != 1024 && !(S->pcg_block == 768 && S->pcg_minb == 1)) FAIL(-2, "CATHY_PCG_BLOCK must be 256, 512 or 1024");
     S->grid_pcg = S->sms * (1024 / S->pcg_block);   // one full SM worth of threads per SM, persistent
     if (S->pcg_minb == 1) S->grid_pcg = S->sms;
@@ -3445,7 +3506,7 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
     a |= S->partial.alloc(10 * (size_t)std::max(S->grid_pcg, 1));
     if (S->newton) {
         a |= S->Ju.alloc((size_t)NDIAG * S->ld, S->halo); a |= S->Jl.alloc((size_t)NDIAG * S->ld, S->halo);
-        DBuf<double> *vv[] = {&S->dinv, &S->dckrw, &S->detai, &S->ws, &S->wsh, &S->wt};
+        DBuf<double> *vv[] = {&S->dinv, &S->dckrw, &S->detai, &S->ws, &S->wsh, &S->wt, &S->widn, &S->wcp};
         for (auto *b : vv) a |= b->alloc(N, S->halo);
         a |= S->ts.alloc(4 * (size_t)S->nt); a |= S->s1.alloc(4 * (size_t)S->nt);
     } a |= S->store_part.alloc(S->grid_n); a |= S->npart.alloc(S->grid_n); a |= S->spart.alloc(S->grid_n);
