@@ -110,6 +110,57 @@ def test_pcg_kernel_variants_agree(gpu_lib, tmp_path, monkeypatch, size):
         assert np.max(np.abs(x - x1)) <= 1e-10 * max(np.abs(x1).max(), 1e-300), (algo, np.abs(x - x1).max(), np.abs(x1).max())
 
 
+def test_config2_full_size_properties(gpu_lib, monkeypatch):
+    """BASELINE config 2 at its full size (200 x 200 DEM x 20 layers, 848,421 nodes: too large for the oracle to finish in
+    seconds), checked through size-independent properties: the assembled operator is symmetric and linear, the PCG solution
+    satisfies the exported system (true residual recomputed on the host from the CSR the handle exports), the streaming and the
+    resident PCG kernels drive the run through the same accepted steps to the same heads, saturation stays inside its bounds and the
+    mass-balance error of every step stays below 1e-6 of the storage."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from pycathy_wrapper_b200.capi import Simulation
+    prj = bench.make_workload((200, 200, 20))
+    sim = Simulation(gpu_lib, prj)
+    assert (sim.n, sim.nt, sim.nterm, sim.nnz) == (848421, 4800000, 6592841, 12337261)      # closed forms of SURVEY.md section 8
+    assert sim.solver_info()["kernel"] == 4
+    topol, ja, coef, rhs = sim.debug_assemble(1.0)
+    n = sim.n
+    rows = np.repeat(np.arange(n), np.diff(topol))
+    import scipy.sparse as sp
+    U = sp.csr_matrix((coef, (rows, ja - 1)), shape=(n, n))
+    A = (U + sp.triu(U, 1).T).tocsr()
+    rng = np.random.default_rng(7)
+    x, y = rng.standard_normal(n), rng.standard_normal(n)
+    ax, _ = sim.debug_spmv(x)
+    ay, _ = sim.debug_spmv(y)
+    axy, _ = sim.debug_spmv(2.0 * x - 3.0 * y)
+    scale = np.abs(ax).max()
+    assert np.abs(ax - A @ x).max() <= 1e-12 * scale                       # the DIA operator is the exported CSR
+    assert np.abs(axy - (2.0 * ax - 3.0 * ay)).max() <= 1e-12 * scale      # linearity
+    assert abs(y @ ax - x @ ay) <= 1e-11 * abs(y @ ax)                     # symmetry
+    sol, nit, err, _ = sim.debug_solve()
+    assert err <= 1e-10 and 1 < nit < 500
+    assert np.linalg.norm(rhs - A @ sol) <= 2e-10 * np.linalg.norm(rhs)    # true residual of the resident PCG's answer
+    sim.close()
+    runs = {}
+    for algo in (1, 4):
+        monkeypatch.setenv("CATHY_PCG_ALGO", str(algo))
+        g = Simulation(gpu_lib, prj)
+        seq = []
+        for _ in range(6):
+            r = g.step()
+            seq.append((r.nstep, r.iter, r.kbackt, round(r.deltat, 12)))
+            assert abs(r.erras) <= 1e-6 * abs(r.store1), (r.erras, r.store1)      # set by the nonlinear tolerance TOLUNS, observed 2e-7
+        st = g.state()
+        assert st["sw"].max() <= 1.0 + 1e-12 and st["sw"].min() >= 0.15 / 0.55 - 1e-12
+        runs[algo] = (seq, st["psi"].copy())
+        g.close()
+    assert runs[1][0] == runs[4][0]
+    ok, dmax = psi_close(runs[4][1], runs[1][1], rtol=1e-8, atol=1e-10)
+    assert ok, dmax
+
+
 def test_state_async_equals_state(gpu_lib, weill):
     """cathy_get_state_async + cathy_state_wait (snapshot drained by a second stream while the next step computes) returns
     exactly what the blocking cathy_get_state returns for the same step."""
