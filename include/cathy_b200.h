@@ -201,9 +201,13 @@ int32_t cathy_dd_start(CathySim *sim);
 int32_t cathy_dd_info(const CathySim *sim, int64_t info[8]);
 
 /* Which linear-solver kernel this handle launches (for bench.py's roofline bookkeeping; no reference counterpart):
- * info[0] = 1 k_pcg (CG vectors streamed), 2 k_pcg2, 3 k_pcg_res (CG vectors resident in shared memory), 10 k_bicgstab (Newton);
+ * info[0] = 1 k_pcg (CG vectors streamed), 2 k_pcg2, 3 k_pcg_res / 4 k_pcg_res2 (CG vectors resident in shared memory), 10 k_bicgstab (Newton);
  * info[1] = rows per CTA (k_pcg_res), info[2] = 1 if the solution vector is resident too, info[3] = CTAs of the solver grid. */
 int32_t cathy_solver_info(const CathySim *sim, int64_t info[4]);
+/* How the assembly (ASSPIC, SRC/asspic.f:26-51) finds the elements of a matrix entry: info[0] = 1 when the tet indices of the gather
+ * plan are derived from the mesh structure (verified against the stored lists at cathy_create), 0 when they are read from memory;
+ * info[1] = width of the per-class offset tables. */
+int32_t cathy_plan_info(const CathySim *sim, int64_t info[2]);
 
 /* ---- kernel-level entry points used by parity tests and bench.py -------------------- */
 /* Assemble the Picard system at the current state for time step `deltat` without solving

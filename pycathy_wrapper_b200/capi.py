@@ -188,7 +188,7 @@ class CathyLib:
                "initial_storage", "step", "get_state", "get_velocity", "get_recharge", "get_wtdepth", "set_psi", "upload_atm_record", "debug_assemble", "debug_spmv", "debug_solve"]
 
     # entry points only the product library has (in-process ensemble support); bound when present
-    PRODUCT_ONLY = ["pack_state", "unpack_psi", "restart", "set_soil", "set_atm_table", "dd_export", "dd_connect", "dd_connect_local", "dd_start", "dd_info", "solver_info", "get_state_async", "state_wait"]
+    PRODUCT_ONLY = ["pack_state", "unpack_psi", "restart", "set_soil", "set_atm_table", "dd_export", "dd_connect", "dd_connect_local", "dd_start", "dd_info", "solver_info", "plan_info", "get_state_async", "state_wait"]
 
     def __init__(self, path: str, prefix: str):
         if not os.path.exists(path):
@@ -221,6 +221,7 @@ class CathyLib:
             f["dd_connect"].argtypes = [C.c_void_p, C.c_void_p]
             f["dd_info"].argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
             f["solver_info"].argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+            f["plan_info"].argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
             f["dd_connect_local"].argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
             f["dd_start"].argtypes = [C.c_void_p]
             f["get_state_async"].argtypes = [C.c_void_p, _D, _D, _D, _D, _D, _D, _D, _D, _I]
@@ -418,6 +419,12 @@ class Simulation:
         v = (C.c_int64 * 4)()
         self._ck(self.lib.f["solver_info"](self.h, v), "solver_info")
         return dict(zip(["kernel", "rows_per_cta", "x_resident", "grid"], (int(x) for x in v)))
+
+    def plan_info(self) -> dict:
+        """Assembly plan of this handle: analytic = tet indices derived from the mesh structure instead of stored."""
+        v = (C.c_int64 * 2)()
+        self._ck(self.lib.f["plan_info"](self.h, v), "plan_info")
+        return {"analytic": bool(v[0]), "table_width": int(v[1])}
 
     def debug_assemble(self, deltat: float):
         # Picard: symmetric upper CSR (NTERM entries); Newton: the Jacobian in full CSR (nnz entries)

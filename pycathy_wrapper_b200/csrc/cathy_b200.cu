@@ -294,6 +294,49 @@ __global__ void __launch_bounds__(RED_BLOCK) k_assemble(int n, EllPlan P, const 
     }
 }
 
+// The same gather with the tet indices DERIVED instead of stored.  On the prism-split DEM mesh the tets around node (layer l, row i,
+// column j) are base(k) + a fixed offset, base(k) = 3 NTRI l + 6 (i NCOL + j); the list of offsets depends only on which of the
+// 27 boundary classes (top / inner / bottom layer x north / inner / south row x west / inner / east column) the node is in.  The
+// host builds the 27 offset tables from the stored lists and checks EVERY entry of every row against them (any mismatch keeps
+// the stored indices), so this kernel reads 8 instead of 12 bytes per contribution: -20 % of the DRAM traffic that bounds it.
+struct PlanGeom { const int *rel; int wrel, nnod, nc1, ncol, nrow, nstr, ntri3, nt; };
+__global__ void __launch_bounds__(RED_BLOCK) k_assemble_a(int n, EllPlan P, PlanGeom G, const double *__restrict__ krt, const double *__restrict__ e1t,
+                                                          Diag A, double *__restrict__ grav, double *__restrict__ m2)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int l = k / G.nnod, sidx = k - l * G.nnod, i = sidx / G.nc1, j = sidx - i * G.nc1;
+        const int cls = ((l == 0 ? 0 : l == G.nstr ? 2 : 1) * 3 + (i == 0 ? 0 : i == G.nrow ? 2 : 1)) * 3 + (j == 0 ? 0 : j == G.ncol ? 2 : 1);
+        const int base = G.ntri3 * l + 6 * (i * G.ncol + j);
+        const int *__restrict__ rl = G.rel + (size_t)cls * NDIAG * G.wrel;
+        {
+            const EllFamily f0 = P.diag[0], f = P.node;
+            double acc = 0.0, g = 0.0, m = 0.0;
+            for (int c = 0; c < f0.w; ++c) {
+                const size_t q = (size_t)c * P.ld + k;
+                const int t = min(max(base + __ldg(rl + c), 0), G.nt - 1);
+                const double kr = krt[t];
+                acc += kr * f0.coef[q];
+                g += kr * f.coef[q];
+                m += e1t[t] * f.coef2[q];
+            }
+            A.d[0][k] = acc;
+            grav[k] = g;
+            m2[k] = m;
+        }
+#pragma unroll
+        for (int d = 1; d < NDIAG; ++d) {
+            const EllFamily fd = P.diag[d];
+            double acc = 0.0;
+            for (int c = 0; c < fd.w; ++c) {
+                const size_t q = (size_t)c * P.ld + k;
+                const int t = min(max(base + __ldg(rl + d * G.wrel + c), 0), G.nt - 1);
+                acc += krt[t] * fd.coef[q];
+            }
+            A.d[d][k] = acc;
+        }
+    }
+}
+
 // symmetric DIA row product: (A x)_k from the 8 upper diagonals.  Branch free: every gathered vector
 // carries NNOD zero-filled halo elements on both sides and structurally absent entries are stored as 0.
 __device__ __forceinline__ double dia_row(const Diag &A, const double *__restrict__ diag0, const double *__restrict__ x, int k, int n)
@@ -2388,6 +2431,8 @@ struct CathySim {
     DBuf<double> tet_k0, tet_gz, tet_vol;   // Newton: per-tet unit-kr stiffness [10][nt], Kz*IVOL*d_k [4][nt], volume [nt]
     size_t fam_off[NDIAG] = {0};
     DBuf<int> ell_tet;           // ELL-transposed gather lists (see k_assemble)
+    DBuf<int> plan_rel;          // k_assemble_a: 27 classes x NDIAG x wrel tet offsets
+    PlanGeom geom{};             // rel == nullptr: stored indices (k_assemble)
     DBuf<double> ell_coef, ell_coef2;
     EllPlan plan;
     size_t ld = 0, halo = 0;     // leading dimension of the diagonals / halo of gathered vectors
@@ -2716,6 +2761,33 @@ static int build_static(CathySim *S)
     for (int d = 0; d < NDIAG; ++d) { S->plan.diag[d].tet = S->ell_tet.p + fam_off[d]; S->plan.diag[d].coef = S->ell_coef.p + fam_off[d]; S->plan.diag[d].coef2 = nullptr; S->plan.diag[d].w = wd[d]; S->plan.diag[d].pad = 0; }
     S->plan.node.tet = S->ell_tet.p + fam_off[NDIAG]; S->plan.node.coef = S->ell_coef.p + fam_off[NDIAG]; S->plan.node.coef2 = S->ell_coef2.p; S->plan.node.w = wnode;
     S->plan.node.pad = wnode == wd[0] && std::memcmp(e_tet.data() + fam_off[0], e_tet.data() + fam_off[NDIAG], (size_t)wnode * ld * sizeof(int)) == 0;
+    // --- tet indices as base(k) + per-class offset (k_assemble_a): build the 27 tables and verify every stored entry against them
+    S->geom = PlanGeom{};
+    if (!newton && S->plan.node.pad && !getenv("CATHY_PLAN_STORED") && (long long)nt < (1LL << 30)) {
+        int wrel = 0;
+        for (int d = 0; d < NDIAG; ++d) wrel = std::max(wrel, wd[d]);
+        const int UNSET = INT32_MIN;
+        std::vector<int> rel((size_t)27 * NDIAG * wrel, UNSET);
+        bool ok = true;
+        for (int k = 0; k < n && ok; ++k) {
+            const int l = k / nnod, sidx = k - l * nnod, i = sidx / nc1, j = sidx - i * nc1;
+            const int cls = ((l == 0 ? 0 : l == nstr ? 2 : 1) * 3 + (i == 0 ? 0 : i == nrow ? 2 : 1)) * 3 + (j == 0 ? 0 : j == ncol ? 2 : 1);
+            const long long base = 3LL * ntri * l + 6LL * ((long long)i * ncol + j);
+            for (int d = 0; d < NDIAG && ok; ++d) {
+                const int cnt = s_fill[(size_t)d * n + k];
+                for (int c = 0; c < cnt; ++c) {
+                    const long long r = (long long)e_tet[fam_off[d] + (size_t)c * ld + k] - base;
+                    int &slot = rel[((size_t)cls * NDIAG + d) * wrel + c];
+                    if (slot == UNSET) slot = (int)r; else if (slot != r) { ok = false; break; }
+                }
+            }
+        }
+        if (ok) {
+            for (int &v : rel) if (v == UNSET) v = 0;     // padding positions (coefficient 0): any valid tet, the kernel clamps
+            if (S->plan_rel.upload(rel)) FAIL(-101, "device allocation of the tet offset tables failed");
+            S->geom = PlanGeom{S->plan_rel.p, wrel, nnod, nc1, ncol, nrow, nstr, 3 * ntri, (int)nt};
+        }
+    }
     S->plan.ld = (long long)ld;
     if (rc) FAIL(-101, "device allocation/upload of static tables failed: %s", cudaGetErrorString(cudaGetLastError()));
     return 0;
@@ -2953,7 +3025,8 @@ static int assemble_system(CathySim *S, double deltat)
     LAUNCH(S, k_curves, nblk(n, S->grid_n), RED_BLOCK, n, make_soil(S), S->ptnew.p, S->pnew.p, S->ptimep.p, S->timep_dirty, S->sw.p, S->ckrw.p, S->et1.p, S->et2.p, S->swnew.p, S->swtimep.p);
     S->timep_dirty = 0;
     LAUNCH(S, k_tet_avg, nblk(S->nt, 4 * S->grid_n), RED_BLOCK, S->nt, S->tet.p, S->ckrw.p, S->et1.p, S->krt.p, S->e1t.p);
-    LAUNCH(S, k_assemble, nblk(n, 4 * S->grid_n), RED_BLOCK, n, S->plan, S->krt.p, S->e1t.p, A, S->grav.p, S->m2.p);
+    if (S->geom.rel) LAUNCH(S, k_assemble_a, nblk(n, 4 * S->grid_n), RED_BLOCK, n, S->plan, S->geom, S->krt.p, S->e1t.p, A, S->grav.p, S->m2.p);
+    else LAUNCH(S, k_assemble, nblk(n, 4 * S->grid_n), RED_BLOCK, n, S->plan, S->krt.p, S->e1t.p, A, S->grav.p, S->m2.p);
     LAUNCH(S, k_rhs_lhs, nblk(n, S->grid_n), RED_BLOCK, n, S->nnod, A, S->tetaf, 1.0 / deltat, S->ptnew.p, S->pnew.p, S->ptimep.p, S->swnew.p,
            S->swtimep.p, S->m2.p, S->m4.p, S->et2.p, S->grav.p, S->ifatm.p, S->have_dir ? S->contp_flag.p : (const unsigned char *)nullptr,
            S->have_neu ? S->qneu.p : (const double *)nullptr, S->atmact.p, S->atmold.p, S->qtranie.p, S->rhs.p, S->xt5.p, S->diag_true.p, S->diag_bc.p);
@@ -3314,7 +3387,7 @@ static int preload_kernels()
     static bool done = false;
     if (done) return 0;
     cudaFuncAttributes at;
-    const void *fns[] = {(const void *)k_curves, (const void *)k_chvelo, (const void *)k_tet_avg, (const void *)k_assemble, (const void *)k_rhs_lhs,
+    const void *fns[] = {(const void *)k_curves, (const void *)k_chvelo, (const void *)k_tet_avg, (const void *)k_assemble, (const void *)k_assemble_a, (const void *)k_rhs_lhs,
                          (const void *)k_scale, (const void *)k_spmv, (const void *)k_dd_send, (const void *)k_dd_recv, (const void *)k_dd_combine_iter,
                          (const void *)k_dd_combine_step, (const void *)k_pcg<1024, true, true>, (const void *)k_pcg<1024, true, false>, (const void *)k_pcg2<1024>, (const void *)k_sym_scale, (const void *)k_sym_scale2,
                          (const void *)k_pcg<1024, false, false>, (const void *)k_pcg<512, true, false>, (const void *)k_pcg<512, false, false>,
@@ -4111,6 +4184,12 @@ int32_t cathy_solver_info(const CathySim *S, int64_t info[4])
     const bool res = !S->dd && (S->pcg_algo == 3 || S->pcg_algo == 4) && S->res_rows > 0;
     info[0] = S->newton ? 10 : res ? S->pcg_algo : (!S->dd && S->pcg_algo == 2) ? 2 : 1;
     info[1] = res ? S->res_rows : 0; info[2] = res ? S->res_x : 0; info[3] = S->grid_pcg;
+    return 0;
+}
+int32_t cathy_plan_info(const CathySim *S, int64_t info[2])
+{
+    info[0] = S->geom.rel ? 1 : 0;      // 1: assembly derives the tet indices (k_assemble_a), 0: stored index lists (k_assemble)
+    info[1] = S->geom.rel ? S->geom.wrel : 0;
     return 0;
 }
 int32_t cathy_dd_info(const CathySim *S, int64_t info[8])
