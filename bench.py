@@ -204,6 +204,7 @@ def run_ours(args, size):
     x = np.random.default_rng(0).standard_normal(n)
     _, spmv_ms = sim.debug_spmv(x, reps=50)
     solver = sim.solver_info()
+    sim_nnz = sim.nnz
     sim.close()
 
     # ---------------- end-to-end through the C ABI with host buffers ("e2e") ----------------
@@ -237,8 +238,8 @@ def run_ours(args, size):
     pcg_bytes = (pcg_iters * PCG_BYTES_PER_ROW_ITER + pcg_solves * PCG_BYTES_PER_ROW_SETUP) * n
     achieved = pcg_bytes / (pcg_ms / 1e3) / 1e9 if pcg_ms > 0 else None
     resident = solver["kernel"] in (3, 4)
-    if newton:      # k_bicgstab: 2 x (15 diagonals + dinv + x) + 10 vector passes per iteration
-        pcg_bytes = pcg_iters * 350.0 * n
+    if newton:      # k_bicgstab: two SpMVs per iteration at SURVEY section 8d's CSR figure (12 nnz + 20 N bytes each) + 10 vector passes
+        pcg_bytes = pcg_iters * (2.0 * (12.0 * sim_nnz + 20.0 * n) + 80.0 * n)
         achieved = pcg_bytes / (pcg_ms / 1e3) / 1e9 if pcg_ms > 0 else None
     if newton:
         kname = "k_bicgstab (persistent right-preconditioned BiCGSTAB on the 15-diagonal Jacobian)"
@@ -276,7 +277,7 @@ def run_ours(args, size):
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "share_of_step": pcg_ms / gpu_ms if gpu_ms else None,
-                     "algorithmic_bytes_per_row_iter": PCG_BYTES_PER_ROW_ITER, "kernel_bytes": kernel_bytes,
+                     "algorithmic_bytes_per_row_iter": (2.0 * (12.0 * sim_nnz + 20.0 * n) + 80.0 * n) / n if newton else PCG_BYTES_PER_ROW_ITER, "kernel_bytes": kernel_bytes,
                      "us_per_pcg_iter": 1e3 * pcg_ms / max(pcg_iters, 1),
                      "spmv_only": {"achieved": SPMV_BYTES_PER_ROW * n / (spmv_ms / 1e3) / 1e9, "ms": spmv_ms,
                                    "frac": SPMV_BYTES_PER_ROW * n / (spmv_ms / 1e3) / 1e9 / peak,

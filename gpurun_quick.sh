@@ -1,5 +1,4 @@
-timeout 800 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-for st in 1 0; do if [ $st = 1 ]; then export CATHY_PLAN_STORED=1; else unset CATHY_PLAN_STORED; fi; python bench.py --steps 20 --warmup 3 --no-cpu 2>/dev/null | python -c "
+for g in 0 148; do if [ $g = 0 ]; then unset CATHY_PCG_GRID; else export CATHY_PCG_GRID=$g; fi; python bench.py --steps 20 --warmup 3 --no-cpu 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('stored=$st: ms/step %.3f value %.4g e2e %.4g share_pcg %.3f' % (d['ms_per_step'], d['value'], d['e2e']['value'], d['roofline']['share_of_step']))"; done
+print('grid env=$g: ms/step %.3f dev %.3f value %.4g e2e %.4g share_pcg %.3f us/it %.2f' % (d['ms_per_step'], d['device_ms_per_step'], d['value'], d['e2e']['value'], d['roofline']['share_of_step'], d['roofline']['us_per_pcg_iter']))"; done
