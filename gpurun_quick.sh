@@ -1,4 +1,5 @@
-for g in 0 148; do if [ $g = 0 ]; then unset CATHY_PCG_GRID; else export CATHY_PCG_GRID=$g; fi; python bench.py --steps 20 --warmup 3 --no-cpu 2>/dev/null | python -c "
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "newton or ponding" 2>&1 | tail -5
+for wl in newton coupled; do python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('grid env=$g: ms/step %.3f dev %.3f value %.4g e2e %.4g share_pcg %.3f us/it %.2f' % (d['ms_per_step'], d['device_ms_per_step'], d['value'], d['e2e']['value'], d['roofline']['share_of_step'], d['roofline']['us_per_pcg_iter']))"; done
+print('$wl: ms/step %.3f value %.4g us/it %.2f frac %.3f share %.3f its %d nl %d' % (d['ms_per_step'], d['value'], d['roofline']['us_per_pcg_iter'], d['roofline']['frac'], d['roofline']['share_of_step'], d['config']['pcg_iters'], d['config']['nonlinear_its']))"; done
