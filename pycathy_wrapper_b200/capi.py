@@ -329,9 +329,13 @@ class Simulation:
     def state_async(self, out: dict) -> dict:
         """Pipelined ``state``: returns at once, ``out`` (page-locked buffers from ``state_buffers(pinned=True)``) is valid after
         ``state_wait()``; later ``step()`` calls overlap with the copies.  Alternate between two buffer sets."""
-        self._ck(self.lib.f["get_state_async"](self.h, _dp(out["psi"]), _dp(out["sw"]), _dp(out["ckrw"]), _dp(out["qtranie"]),
-                                               _dp(out["pond"]), _dp(out["atmact"]), _dp(out["atmpot"]), _dp(out["ovfl"]),
-                                               _ip(out["ifatm"])), "get_state_async")
+        cache = self.__dict__.setdefault("_async_ptrs", {})
+        ptrs = cache.get(id(out))
+        if ptrs is None or ptrs[0] is not out:      # the ctypes pointers of a buffer set are built once (this call sits between two steps)
+            ptrs = (out, (_dp(out["psi"]), _dp(out["sw"]), _dp(out["ckrw"]), _dp(out["qtranie"]), _dp(out["pond"]), _dp(out["atmact"]),
+                          _dp(out["atmpot"]), _dp(out["ovfl"]), _ip(out["ifatm"])))
+            cache[id(out)] = ptrs
+        self._ck(self.lib.f["get_state_async"](self.h, *ptrs[1]), "get_state_async")
         return out
 
     def state_wait(self) -> None:
