@@ -71,6 +71,14 @@ def run_processor(project_dir: str, lib: CathyLib | None = None, write_files: bo
         sim.close()
         return res
 
+    if getattr(prj, "transport_skipped", False):
+        note = (" TRAFLAG=1: cathy-b200 runs the FLOW problem of this project only; the solute-transport add-on (one-way coupled, "
+                "SRC/cathy_main.f:3304-3607) is not simulated and no concentration output is written\n")
+        print(note, end="")
+        if write_files:
+            with open(_out(prj, "IOUT2"), "a") as fh_r:
+                fh_r.write(note)
+
     x = y = z = None
     fh = {}
     if write_files:

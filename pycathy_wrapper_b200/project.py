@@ -221,6 +221,7 @@ class CathyProject:
     path: str
     fnames: dict
     parm: dict
+    transport_skipped: bool = False      # parm says TRAFLAG=1 and the caller opted in to run the flow problem only
     # mesh description
     nrow: int = 0
     ncol: int = 0
@@ -334,7 +335,11 @@ def read_parm(path: str) -> dict:
     return p
 
 
-def load_project(prj: str) -> CathyProject:
+def load_project(prj: str, skip_transport: bool | None = None) -> CathyProject:
+    """Read a CATHY project directory like DATIN does.  ``skip_transport`` (default: the environment variable
+    CATHY_B200_SKIP_TRANSPORT=1): accept a project whose parm says TRAFLAG=1 and run its FLOW problem only.  In the reference the
+    solute transport is a one-way add-on after each flow step (SRC/cathy_main.f:3304-3607: it reads the flow's velocities, the flow
+    never reads a concentration), so psi, sw, vp, mbeconv, cumflowvol ... are unaffected; the concentration outputs are not written."""
     prj = os.path.abspath(prj)
     fn = read_fnames(prj)
     parm = read_parm(fn["IIN1"])
@@ -342,8 +347,14 @@ def load_project(prj: str) -> CathyProject:
     isim = parm["ISIMGR"]
     if isim not in (1, 2):
         raise CathyInputError(f"ISIMGR={isim}: only DEM based runs (1: subsurface, 2: coupled) are implemented")
+    if skip_transport is None:
+        skip_transport = os.environ.get("CATHY_B200_SKIP_TRANSPORT", "0") == "1"
+    P.transport_skipped = False
     if parm["TRAFLAG"] != 0:
-        raise CathyInputError("TRAFLAG=1 (solute transport) is outside the hot-path scope")
+        if not skip_transport:
+            raise CathyInputError("TRAFLAG=1 (solute transport) is outside the hot-path scope; set CATHY_B200_SKIP_TRANSPORT=1 "
+                                  "(or load_project(..., skip_transport=True)) to run the flow problem of this project without its transport add-on")
+        P.transport_skipped = True
 
     P.dem, hdr = read_raster(fn["IIN10"])
     P.nrow, P.ncol = P.dem.shape

@@ -23,8 +23,12 @@ def test_reader_rejects_out_of_scope_features(tmp_path):
     from pycathy_wrapper_b200 import synthetic
     from pycathy_wrapper_b200.project import CathyInputError, load_project
     d = synthetic.make_project(str(tmp_path / "a"), 4, 5, 3, TRAFLAG=1)
-    with pytest.raises(CathyInputError):
+    with pytest.raises(CathyInputError, match="CATHY_B200_SKIP_TRANSPORT"):
         load_project(d)
+    # explicit opt-in: the flow problem of a TRAFLAG=1 project (pyCATHY's template project carries TRAFLAG=1) is the TRAFLAG=0 problem
+    p1, p0 = load_project(d, skip_transport=True), load_project(synthetic.make_project(str(tmp_path / "a0"), 4, 5, 3))
+    assert p1.transport_skipped and not p0.transport_skipped
+    assert p1.n == p0.n and np.array_equal(p1.dem, p0.dem) and np.array_equal(p1.ic_psi, p0.ic_psi)
     d = synthetic.make_project(str(tmp_path / "b"), 4, 5, 3)
     dem = os.path.join(d, "prepro", "dem")
     txt = open(dem).read().splitlines()
