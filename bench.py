@@ -213,16 +213,19 @@ def run_ours(args, size):
     pin = torch.from_numpy(forcing.copy()).pin_memory()
     forcing = pin.numpy()
     hostbufs = [sim.state_buffers(pinned=True) for _ in range(2)]   # the caller's (pinned) host buffers for the per-step read-back
+    sim.upload_atm_record(1, forcing)
     for i in range(args.warmup):
-        sim.upload_atm_record(1, forcing)
         sim.step()
+        sim.upload_atm_record(1, forcing)
         sim.state_async(hostbufs[i & 1])
     sim.state_wait()
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        sim.upload_atm_record(1, forcing)                       # H2D: this step's forcing record
         sim.step()
+        # H2D: the NEXT step's forcing record, enqueued before this step's read-back starts to drain: both copies would
+        # otherwise meet on the copy engines and the upload (on the compute stream) would wait for the 28 MB drain.  K steps = K uploads.
+        sim.upload_atm_record(1, forcing)
         # D2H: psi, sw, ckrw, ... (what DETOUT prints) of THIS step, snapshotted on the device and drained by a second stream
         # while the next step computes; two host buffer sets alternate, the last read-back is awaited inside the timed region
         st = sim.state_async(hostbufs[i & 1])

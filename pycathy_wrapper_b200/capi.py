@@ -305,11 +305,13 @@ class Simulation:
         if pinned:
             import torch
 
-            def mk(m, dt):
-                return torch.empty(m, dtype=dt).pin_memory().numpy()
-            out = {k: mk(n, torch.float64) for k in ("psi", "sw", "ckrw", "qtranie")}
-            out.update({k: mk(nn, torch.float64) for k in ("pond", "atmact", "atmpot", "ovfl")})
-            out["ifatm"] = mk(nn, torch.int32)
+            # one page-locked block, carved in the order cathy_get_state_async stages the arrays: the read-back is a single copy
+            block = torch.empty(4 * n + 4 * nn, dtype=torch.float64).pin_memory().numpy()
+            out, off = {}, 0
+            for k, m in (("psi", n), ("sw", n), ("ckrw", n), ("qtranie", n), ("pond", nn), ("atmact", nn), ("atmpot", nn), ("ovfl", nn)):
+                out[k] = block[off:off + m]
+                off += m
+            out["ifatm"] = torch.empty(nn, dtype=torch.int32).pin_memory().numpy()
             return out
         out = {k: np.empty(n) for k in ("psi", "sw", "ckrw", "qtranie")}
         out.update({k: np.empty(nn) for k in ("pond", "atmact", "atmpot", "ovfl")})

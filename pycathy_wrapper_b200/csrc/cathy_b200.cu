@@ -1635,6 +1635,21 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab(BicgArgs a)
 // ------------------------------------------------------------------------------------------
 // after the solve: PNEW += PDIFF and SHLPIC's Dirichlet reset (SRC/picard.f:185-198, SRC/shlpic.f:30-56)
 // ------------------------------------------------------------------------------------------
+// one launch instead of nine device-to-device copies: the state arrays that cathy_get_state returns, packed into the staging buffer
+struct SnapArgs { const double *src[8]; double *dst[8]; const int *isrc; int *idst; int n, nn; };
+__global__ void k_snapshot(SnapArgs a)
+{
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int k = t0; k < a.n; k += stride) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (a.dst[q]) a.dst[q][k] = a.src[q][k];
+    }
+    for (int k = t0; k < a.nn; k += stride) {
+#pragma unroll
+        for (int q = 4; q < 8; ++q) if (a.dst[q]) a.dst[q][k] = a.src[q][k];
+        if (a.idst) a.idst[k] = a.isrc[k];
+    }
+}
 __global__ void k_update(int n, int nnod, const double *__restrict__ pdiff, const double *__restrict__ pold,
                          const int *__restrict__ ifatm, const unsigned char *__restrict__ contp_flag,
                          const double *__restrict__ contp_val, double *__restrict__ pnew)
@@ -3404,7 +3419,7 @@ static int preload_kernels()
     static bool done = false;
     if (done) return 0;
     cudaFuncAttributes at;
-    const void *fns[] = {(const void *)k_curves, (const void *)k_chvelo, (const void *)k_tet_avg, (const void *)k_assemble, (const void *)k_assemble_a, (const void *)k_rhs_lhs,
+    const void *fns[] = {(const void *)k_curves, (const void *)k_chvelo, (const void *)k_tet_avg, (const void *)k_assemble, (const void *)k_assemble_a, (const void *)k_snapshot, (const void *)k_rhs_lhs,
                          (const void *)k_scale, (const void *)k_spmv, (const void *)k_dd_send, (const void *)k_dd_recv, (const void *)k_dd_combine_iter,
                          (const void *)k_dd_combine_step, (const void *)k_pcg<1024, true, true>, (const void *)k_pcg<1024, true, false>, (const void *)k_pcg2<1024>, (const void *)k_sym_scale, (const void *)k_sym_scale2,
                          (const void *)k_pcg<1024, false, false>, (const void *)k_pcg<512, true, false>, (const void *)k_pcg<512, false, false>,
@@ -3827,17 +3842,25 @@ int32_t cathy_get_state_async(CathySim *S, double *psi, double *sw, double *ckrw
     const Item items[8] = {{psi, S->pnew.p, n}, {sw, S->sw.p, n}, {ckrw, S->ckrw.p, n}, {qtranie, S->qtranie.p, n},
                            {pond, S->pondnod.p, nn}, {atmact, S->atmact.p, nn}, {atmpot, S->atmpot.p, nn}, {ovfl, S->ovflnod.p, nn}};
     size_t off = 0;
-    for (const Item &it : items) {
-        if (it.host) CK(cudaMemcpyAsync(S->snap.p + off, it.dev, it.cnt * sizeof(double), cudaMemcpyDeviceToDevice, S->st));
-        off += it.cnt;
+    SnapArgs sa;
+    for (int q = 0; q < 8; ++q) {
+        sa.src[q] = items[q].dev; sa.dst[q] = items[q].host ? S->snap.p + off : nullptr;
+        off += items[q].cnt;
     }
-    if (ifatm) CK(cudaMemcpyAsync(S->snap_i.p, S->ifatm.p, nn * sizeof(int), cudaMemcpyDeviceToDevice, S->st));
+    sa.isrc = S->ifatm.p; sa.idst = ifatm ? S->snap_i.p : nullptr; sa.n = S->n; sa.nn = S->nnod;
+    LAUNCH(S, k_snapshot, nblk(S->n, S->grid_n), RED_BLOCK, sa);
     CK(cudaEventRecord(S->ev_snap, S->st));
     CK(cudaStreamWaitEvent(S->st_copy, S->ev_snap, 0));
-    off = 0;
-    for (const Item &it : items) {
-        if (it.host) CK(cudaMemcpyAsync(it.host, S->snap.p + off, it.cnt * sizeof(double), cudaMemcpyDeviceToHost, S->st_copy));
-        off += it.cnt;
+    // host buffers carved out of ONE block in the staging order (capi.state_buffers(pinned=True) does that): one copy instead of eight
+    bool contiguous = true;
+    for (int q = 0; q + 1 < 8 && contiguous; ++q) contiguous = items[q].host && items[q + 1].host && items[q].host + items[q].cnt == items[q + 1].host;
+    if (contiguous) CK(cudaMemcpyAsync(items[0].host, S->snap.p, (4 * n + 4 * nn) * sizeof(double), cudaMemcpyDeviceToHost, S->st_copy));
+    else {
+        off = 0;
+        for (const Item &it : items) {
+            if (it.host) CK(cudaMemcpyAsync(it.host, S->snap.p + off, it.cnt * sizeof(double), cudaMemcpyDeviceToHost, S->st_copy));
+            off += it.cnt;
+        }
     }
     if (ifatm) CK(cudaMemcpyAsync(ifatm, S->snap_i.p, nn * sizeof(int), cudaMemcpyDeviceToHost, S->st_copy));
     CK(cudaEventRecord(S->ev_drained, S->st_copy));
