@@ -1730,12 +1730,15 @@ __global__ void k_free_drain_list(int nnod, int nstr, const double *__restrict__
 // norms (NORMS, SRC/norms.f:18-38) + storage change (STORMB, SRC/stormb.f) + boundary flux sums
 // (FLUXMB, SRC/fluxmb.f:29-88): block partials in fixed order
 struct NormPartial { double pl2, fl2, dstore, pinf, finf, adin, adout, anin, anout; int ik; int pad; };
-__global__ void k_norms(int n, int nnod, const double *__restrict__ pnew, const double *__restrict__ pold,
+// pdiff != nullptr: SHLPIC's update PNEW += PDIFF (k_update) is done here, in the same pass (Picard; Newton needs the new heads in
+// k_sw_pair first and keeps the separate launch)
+__global__ void k_norms(int n, int nnod, double *pnew, const double *__restrict__ pold,
                         const double *__restrict__ rhs, const double *__restrict__ ptimep,
                         const double *__restrict__ swnew, const double *__restrict__ swtimep,
                         const double *__restrict__ volnod, const double *__restrict__ snodi,
                         const double *__restrict__ pnodi, const int *__restrict__ ifatm, const double *__restrict__ atmact,
-                        NormPartial *__restrict__ part, const unsigned char *__restrict__ own, double omega)
+                        NormPartial *__restrict__ part, const unsigned char *__restrict__ own, double omega,
+                        const double *__restrict__ pdiff, const unsigned char *__restrict__ contp_flag, const double *__restrict__ contp_val)
 {
     __shared__ double sh[32];
     __shared__ double shv[RED_BLOCK / 32];
@@ -1743,15 +1746,23 @@ __global__ void k_norms(int n, int nnod, const double *__restrict__ pnew, const 
     double pl2 = 0, fl2 = 0, ds = 0, pinf = 0, finf = 0, adin = 0, adout = 0, anin = 0, anout = 0;
     int ik = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        double pn;
+        if (pdiff) {
+            pn = pnew[k] + pdiff[k];
+            if (contp_flag && contp_flag[k]) pn = contp_val[k];
+            if (k < nnod) { int f = ifatm[k]; if (f == 1 || f == 2) pn = pold[k]; }
+            pnew[k] = pn;
+        } else
+            pn = pnew[k];
         if (own && !(own[k] & 1)) continue;      // row-block partition: ghost rows belong to another rank
         // NLRELX = 1: the norms see the relaxed heads (SRC/relax.f runs between MASBAL and NORMS), the storage change below does not
-        const double pr = omega == 1.0 ? pnew[k] : (1.0 - omega) * pold[k] + omega * pnew[k];
+        const double pr = omega == 1.0 ? pn : (1.0 - omega) * pold[k] + omega * pn;
         double d = pr - pold[k], da = fabs(d), f = rhs[k];
         pl2 += d * d;
         fl2 += f * f;
         if (da > pinf || (da == pinf && k >= ik)) { pinf = da; ik = k; }
         finf = fmax(finf, fabs(f));
-        ds += volnod[k] * (snodi[k] * (swnew[k] + swtimep[k]) * 0.5 * (pnew[k] - ptimep[k]) + pnodi[k] * (swnew[k] - swtimep[k]));
+        ds += volnod[k] * (snodi[k] * (swnew[k] + swtimep[k]) * 0.5 * (pn - ptimep[k]) + pnodi[k] * (swnew[k] - swtimep[k]));
         if (k < nnod) {
             int fa = ifatm[k];
             if (fa != -1) {
@@ -3186,6 +3197,8 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
     rc = S->newton ? solve_system_newton(S) : solve_system(S);
     if (rc) return rc;
     Diag A = make_diag(S, S->A.p);
+    const bool fuse_update = !S->newton;     // Picard: PNEW += PDIFF happens inside k_norms
+    if (!fuse_update)
     LAUNCH(S, k_update, nblk(n, S->grid_n), RED_BLOCK, n, S->nnod, S->pdiff.p, S->pold.p, S->ifatm.p, S->have_dir ? S->contp_flag.p : (const unsigned char *)nullptr,
            S->have_dir ? S->contp_val.p : (const double *)nullptr, S->pnew.p);
     if (S->newton) {
@@ -3211,7 +3224,8 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
     if (S->have_neu) LAUNCH(S, k_flux_sums, 1, RED_BLOCK, S->neu.anbc(), S->qlist.p, S->bcsum.p + 2);
     LAUNCH(S, k_norms, S->grid_n, RED_BLOCK, n, S->nnod, S->pnew.p, S->pold.p, S->rhs.p, S->ptimep.p, S->swnew.p, S->swtimep.p, S->volnod.p,
            S->snodi.p, S->pnodi.p, S->ifatm.p, S->atmact.p, S->npart.p, S->dd ? S->own.p : (const unsigned char *)nullptr,
-           S->p.nlrelx == 1 ? S->p.omega : 1.0);
+           S->p.nlrelx == 1 ? S->p.omega : 1.0, fuse_update ? S->pdiff.p : (const double *)nullptr,
+           S->have_dir ? S->contp_flag.p : (const unsigned char *)nullptr, S->have_dir ? S->contp_val.p : (const double *)nullptr);
     if (S->p.nlrelx == 1) LAUNCH(S, k_relax, nblk(n, S->grid_n), RED_BLOCK, n, S->p.omega, S->pold.p, S->pnew.p);
     LAUNCH(S, k_norms_final, 1, RED_BLOCK, S->grid_n, S->npart.p, S->pnew.p, S->pold.p, S->d_iter.p);
     if (S->dd) LAUNCH(S, k_dd_combine_iter, 1, 32, S->comm->ctx, S->d_iter.p, S->gnnod, S->grow0 * S->nc1);
