@@ -1,5 +1,5 @@
 set -x
-TAG=${TAG:-r1g}
+TAG=${TAG:-r1h}
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/t_$TAG.log; cat gpurun_out/t_$TAG.log
 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
