@@ -1,4 +1,4 @@
-timeout 800 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "curves or zones or infiltration" 2>&1 | tail -6
 python bench.py --steps 20 --warmup 3 --no-cpu 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])

@@ -201,6 +201,61 @@ __global__ void k_chvelo_alt(int n, CurveModel c, const double *__restrict__ pno
     if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }
 
+// Extended van Genuchten (IVGHU = 1): SRC/fxvmc.f, fxvkr.f, fxvdmc.f.  Above the head PNOT (where the slope of the van Genuchten
+// curve has fallen to the specific storage) the moisture content continues linearly with slope SS.  With IVGHU = 1 Soil::vgpnot
+// holds PNOT (bisection of SRC/chparm.f:36-78, done once on the host) and Soil::rr the residual moisture content VGRMC itself.
+__device__ __forceinline__ void xvg_node(const Soil &s, int i, double psi, bool need_kr, bool need_d, double &sw, double &kr, double &dmc)
+{
+    const double n = s.vgn[i], m = s.vgm[i], psat = s.vgpsat[i], pnot = s.vgpnot[i], rmc = s.rr[i], ss = s.snodi[i], por = s.pnodi[i];
+    const double tsr = por - rmc;
+    kr = 1.0; dmc = ss;
+    if (psi < pnot) {
+        const double beta = pow(fabs(psi / psat), n), b1 = beta + 1.0, b1r = 1.0 / b1;
+        sw = (rmc + (tsr / pow(b1, m))) / por;
+        if (need_d) dmc = s.vgn1[i] * tsr * (pow(fabs(psi), s.vgn1[i]) / s.vgpsn[i]) * pow(b1, s.vgnr[i]) * b1r * b1r;
+        if (need_kr) { const double v1 = pow(b1, m) - pow(beta, m); kr = pow(b1r, s.vgm52[i]) * v1 * v1; }
+    } else {
+        const double b01 = pow(fabs(pnot / psat), n) + 1.0;
+        sw = (rmc + tsr * pow(b01, -m) + ss * (psi - pnot)) / por;
+        if (need_kr && psi < -1.0e-14) {
+            const double beta = pow(fabs(psi / psat), n), b1 = beta + 1.0, v1 = pow(b1, m) - pow(beta, m);
+            kr = pow(1.0 / b1, s.vgm52[i]) * v1 * v1;
+        }
+    }
+}
+// CHPIC0 for IVGHU = 1 (SRC/chpic0.f:37-50)
+__global__ void k_curves_xvg(int n, Soil s, const double *__restrict__ ptnew, const double *__restrict__ pnew, const double *__restrict__ ptimep,
+                             int do_timep, double *__restrict__ sw, double *__restrict__ ckrw, double *__restrict__ et1, double *__restrict__ et2,
+                             double *__restrict__ swnew, double *__restrict__ swtimep)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double psi = ptnew[i], sn = s.snodi[i], po = s.pnodi[i];
+        double w, kr, etai, dum1, dum2;
+        xvg_node(s, i, psi, true, true, w, kr, etai);
+        sw[i] = w; ckrw[i] = kr;
+        et1[i] = w * sn;
+        et2[i] = (etai - w * sn) / po;
+        const double pn = pnew[i];
+        if (pn == psi) swnew[i] = w; else { xvg_node(s, i, pn, false, false, w, dum1, dum2); swnew[i] = w; }
+        if (do_timep) { xvg_node(s, i, ptimep[i], false, false, w, dum1, dum2); swtimep[i] = w; }
+    }
+}
+// CHVELO for IVGHU = 1 (SRC/chvelo.f:34-39) fused with STORCAL's sum term
+__global__ void k_chvelo_xvg(int n, Soil s, const double *__restrict__ psiv, const double *__restrict__ volnod, double *__restrict__ sw,
+                             double *__restrict__ ckrw, double *__restrict__ partial, const unsigned char *__restrict__ own)
+{
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double w, kr, d;
+        xvg_node(s, i, psiv[i], true, false, w, kr, d);
+        sw[i] = w; ckrw[i] = kr;
+        if (!own || (own[i] & 1)) acc += w * volnod[i] * s.pnodi[i];
+    }
+    double t = block_sum<RED_BLOCK>(acc, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
 // ------------------------------------------------------------------------------------------
 // K1: moisture curves per node (PICUNS -> CHPIC0, SRC/picuns.f:22-48, SRC/chpic0.f:23-36)
 // ------------------------------------------------------------------------------------------
@@ -2769,6 +2824,28 @@ static int build_static(CathySim *S)
         vgpnot[k] = (pnodi[k] - vgrmc[k]) / pnodi[k]; rr[k] = vgrmc[k] / pnodi[k];
         vgmm1[k] = vgm[k] - 1.0; vgm52[k] = 2.5 * vgm[k];
     }
+    if (p.ivghu == 1) {
+        // extended van Genuchten (SRC/chparm.f:36-78): vgpnot <- PNOT, the head between the curve's inflexion point and 0 at which
+        // d(theta)/d(psi) = SS (interval halving with the reference's stopping rule: half-width < 1e-14 or an exact root); rr <- VGRMC
+        for (int k = 0; k < n; ++k) {
+            const double m1 = vgm[k] + 1.0, ss = snodi[k], tsr = pnodi[k] - vgrmc[k], target = ss * vgpsn[k] / (vgn1[k] * tsr);
+            const double dmcmax = -vgm[k] * vgn[k] * tsr * std::pow(vgm[k], vgm[k]) / (vgpsat[k] * std::pow(m1, m1));
+            if (ss >= dmcmax) FAIL(-2, "IVGHU=1: SNODI = %g at node %d must be smaller than DMCMAX = %g (SRC/chparm.f:48-52)", ss, k + 1, dmcmax);
+            auto g = [&](double h) { return std::pow(std::fabs(h), vgn1[k]) / std::pow(1.0 + std::pow(h / vgpsat[k], vgn[k]), m1) - target; };
+            double lo = vgpsat[k] * std::pow(vgm[k], 1.0 / vgn[k]), hi = 0.0, mid = 0.0;
+            bool found = false;
+            for (int it = 0; it < 500 && !found; ++it) {
+                const double half = (hi - lo) / 2.0;
+                mid = lo + half;
+                const double gm = g(mid);
+                if (gm == 0.0 || half < 1.0e-14) found = true;
+                else if (g(lo) * gm > 0.0) lo = mid;
+                else hi = mid;
+            }
+            if (!found) FAIL(-2, "IVGHU=1: the bisection for PNOT did not converge at node %d (SRC/chparm.f:71-73)", k + 1);
+            vgpnot[k] = mid; rr[k] = vgrmc[k];
+        }
+    }
     // --- vegetation type per surface node (SRC/datin.f:236-246)
     std::vector<int> veg(nnod);
     {
@@ -3032,7 +3109,9 @@ static void weight_and_copy(CathySim *S)
 // chvelo + storage sum -> returns STORE1 through h_step later; here just launches
 static void chvelo_launch(CathySim *S, const double *psi)
 {
-    if (S->cm.ivghu != 0)
+    if (S->cm.ivghu == 1)
+        LAUNCH(S, k_chvelo_xvg, S->grid_n, RED_BLOCK, S->n, make_soil(S), psi, S->volnod.p, S->sw.p, S->ckrw.p, S->store_part.p, S->dd ? S->own.p : (const unsigned char *)nullptr);
+    else if (S->cm.ivghu != 0)
         LAUNCH(S, k_chvelo_alt, S->grid_n, RED_BLOCK, S->n, S->cm, S->pnodi.p, psi, S->volnod.p, S->sw.p, S->ckrw.p, S->store_part.p, S->dd ? S->own.p : (const unsigned char *)nullptr);
     else
     LAUNCH(S, k_chvelo, S->grid_n, RED_BLOCK, S->n, make_soil(S), psi, S->volnod.p, S->sw.p, S->ckrw.p, S->store_part.p, S->dd ? S->own.p : (const unsigned char *)nullptr);
@@ -3061,7 +3140,10 @@ static int assemble_system(CathySim *S, double deltat)
     const int n = S->n;
     S->scaled = false;
     Diag A = make_diag(S, S->A.p);
-    if (S->cm.ivghu != 0)
+    if (S->cm.ivghu == 1)
+        LAUNCH(S, k_curves_xvg, nblk(n, S->grid_n), RED_BLOCK, n, make_soil(S), S->ptnew.p, S->pnew.p, S->ptimep.p, S->timep_dirty, S->sw.p, S->ckrw.p, S->et1.p, S->et2.p,
+               S->swnew.p, S->swtimep.p);
+    else if (S->cm.ivghu != 0)
         LAUNCH(S, k_curves_alt, nblk(n, S->grid_n), RED_BLOCK, n, S->cm, S->snodi.p, S->pnodi.p, S->ptnew.p, S->pnew.p, S->ptimep.p, S->timep_dirty, S->sw.p, S->ckrw.p,
                S->et1.p, S->et2.p, S->swnew.p, S->swtimep.p);
     else
@@ -3776,8 +3858,8 @@ int32_t cathy_create(const CathyProblem *prob, CathySim **out)
     if (prob->iopt != 1 && prob->iopt != 2) FAIL(-2, "IOPT=%d: must be 1 (Picard) or 2 (Newton)", prob->iopt);
     if (prob->iopt == 2 && prob->tetaf != 1.0 && prob->tetaf <= 0.0) FAIL(-2, "TETAF must be positive");
     if (prob->kslope != 0) FAIL(-2, "KSLOPE=%d: only analytical moisture-curve derivatives (0) are implemented", prob->kslope);
-    if (!(prob->ivghu == 0 || (prob->ivghu >= 2 && prob->ivghu <= 4)))
-        FAIL(-2, "IVGHU=%d: van Genuchten (0), Huyakorn (2, 3) and Brooks-Corey (4) curves are implemented; extended van Genuchten (1) and look-up tables (-1) are not", prob->ivghu);
+    if (!(prob->ivghu >= 0 && prob->ivghu <= 4))
+        FAIL(-2, "IVGHU=%d: van Genuchten (0), extended van Genuchten (1), Huyakorn (2, 3) and Brooks-Corey (4) curves are implemented; look-up tables (-1) are not", prob->ivghu);
     if (prob->ivghu != 0 && prob->iopt != 1) FAIL(-2, "IVGHU=%d with the Newton scheme is not implemented (Picard only)", prob->ivghu);
     if (prob->lump == 0) FAIL(-2, "LUMP=0 (consistent mass matrix) is not implemented on the device");
     if (prob->nlrelx != 0 && prob->nlrelx != 1) FAIL(-2, "NLRELX=%d: only no relaxation (0) and constant OMEGA (1) are implemented", prob->nlrelx);

@@ -9,7 +9,7 @@ grammar in Python and returns plain numpy arrays; nothing here touches the GPU.
 
 Scope of round 1: DEM based projects (ISIMGR = 1 or 2) whose DEM
 rectangle is fully inside the catchment (no zero cells), no lakes/reservoirs, no
-seepage faces, DOSTEP = 1, IVGHU = 0 (van Genuchten).  Anything else raises
+seepage faces, DOSTEP = 1, IVGHU = 0..4 (no look-up tables).  Anything else raises
 ``CathyInputError`` -- loudly, never silently ignored.
 """
 from __future__ import annotations
@@ -436,8 +436,8 @@ def load_project(prj: str, skip_transport: bool | None = None) -> CathyProject:
     P.soil = soil
     if soil["IPEAT"] != 0:
         raise CathyInputError("IPEAT=1 (peat deformation) is outside the hot-path scope")
-    if soil["IVGHU"] not in (0, 2, 3, 4):
-        raise CathyInputError(f"IVGHU={soil['IVGHU']}: van Genuchten (0), Huyakorn (2, 3) and Brooks-Corey (4) are implemented")
+    if soil["IVGHU"] not in (0, 1, 2, 3, 4):
+        raise CathyInputError(f"IVGHU={soil['IVGHU']}: van Genuchten (0), extended van Genuchten (1), Huyakorn (2, 3) and Brooks-Corey (4) are implemented")
 
     # ---- atmbc (SRC/atmone.f, SRC/atmnxt.f)
     rd = ListDirectedReader(fn["IIN6"])

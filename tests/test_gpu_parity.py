@@ -515,19 +515,18 @@ def test_auxiliary_outputs_against_reference(gpu_lib, tmp_path):
             assert np.max(np.abs(o - g)) <= 1e-5 * max(np.abs(g).max(), 1e-30), (f, np.abs(o - g).max(), np.abs(g).max())
 
 
-@pytest.mark.parametrize("ivghu", [2, 3, 4])
-def test_huyakorn_and_brooks_corey_curves(gpu_lib, oracle_mod, tmp_path, ivghu):
-    """IVGHU = 2, 3 (Huyakorn) and 4 (Brooks-Corey) moisture curves (SRC/chpic0.f:51-99, SRC/chvelo.f, fhu*.f, fbc*.f): same
-    accepted steps and heads as the oracle, which is byte-identical to the reference ELF on these cases
+@pytest.mark.parametrize("ivghu,xvg_case", [(1, 0), (1, 1), (2, None), (3, None), (4, None)])
+def test_huyakorn_and_brooks_corey_curves(gpu_lib, oracle_mod, tmp_path, ivghu, xvg_case):
+    """IVGHU = 1 (extended van Genuchten: SRC/fxvmc.f, fxvkr.f, fxvdmc.f, PNOT of SRC/chparm.f:36-78), 2, 3 (Huyakorn) and 4
+    (Brooks-Corey) moisture curves (SRC/chpic0.f:37-99, SRC/chvelo.f, fhu*.f, fbc*.f): same accepted steps and heads as the oracle,
+    which is byte-identical to the reference ELF on these cases
     (tests/test_oracle_golden.py::test_oracle_other_moisture_curves_against_reference_elf_when_available)."""
-    from pycathy_wrapper_b200 import synthetic
     from pycathy_wrapper_b200.project import load_project
-    d = synthetic.make_project(str(tmp_path / "p"), 8, 9, 5, ic=("wt", 0.8), ISIMGR=1, TMAX=600.0, TIMPRT=[300.0, 600.0], DELTAT=1.0, DTMIN=1e-4,
-                               DTMAX=50.0, NODVP=[4], ivghu=ivghu, hu=(2.0, 2, 2, 0, 0.333), hun=2.5, huab=(-5, 6), bc=(1.2, 0.05, -0.345),
-                               atmbc=[(0.0, 0.0), (60.0, 2.0e-5), (1.0e9, 2.0e-5)])
+    from test_oracle_golden import _curve_project
+    d, nstep = _curve_project(str(tmp_path / "p"), ivghu, xvg_case)
     prj = load_project(d)
     g, c, rg, rc = _run_both(gpu_lib, oracle_mod, prj)
-    assert rg.nstep == 44
+    assert rg.nstep == nstep
     ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
     assert ok, dmax
     assert np.max(np.abs(g.state()["sw"] - c.state()["sw"])) < 1e-6
