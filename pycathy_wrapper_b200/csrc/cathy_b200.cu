@@ -1346,6 +1346,60 @@ __global__ void k_curves_newton(int n, Soil s, const double *__restrict__ ptnew,
         dckrw[i] = fvgdkr(psi, psat, n_, m, n1, s.vgm52[i], s.vgmm1[i]);
     }
 }
+// CHNEW0 for IVGHU = 1..4 (SRC/chnew0.f:39-89): the curve of the node plus the derivatives the Jacobian needs, d(kr)/d(psi) and
+// d(eta)/d(psi) -- SRC/fxvddm.f, fxvdkr.f (extended van Genuchten), fhudds.f, fhudk2.f, fhudk3.f (Huyakorn), fbcdds.f, fbcdkr.f (Brooks-Corey)
+__global__ void k_curves_newton_alt(int n, CurveModel c, Soil s, const double *__restrict__ ptnew, double *__restrict__ sw, double *__restrict__ ckrw,
+                                    double *__restrict__ etai, double *__restrict__ dckrw, double *__restrict__ detai)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double psi = ptnew[i], sn = s.snodi[i], po = s.pnodi[i];
+        double w, kr, eta, dkr = 0.0, deta = 0.0;
+        if (c.ivghu == 1) {
+            xvg_node(s, i, psi, true, true, w, kr, eta);
+            const double nn = s.vgn[i], m = s.vgm[i], psat = s.vgpsat[i], n1 = s.vgn1[i];
+            if (psi < -1.0e-14) {
+                const double beta = pow(fabs(psi / psat), nn), b1 = beta + 1.0, b1r = 1.0 / b1;
+                const double v1 = pow(b1, m) - pow(beta, m), v2 = psat / psi;
+                const double v3 = n1 * beta * v2 * pow(b1r, s.vgm52[i]) / psat;
+                const double v4 = v2 * ((2.5 / b1) * beta - 2.0) - 0.5 * pow(b1, s.vgmm1[i]);
+                dkr = v3 * v1 * v4;
+                if (psi < s.vgpnot[i]) deta = n1 * (po - s.rr[i]) * (beta / psi) * (1.0 / psi) * ((1.0 + nn * (beta - 1.0)) / pow(b1, m)) * b1r * b1r;
+            }
+        } else {
+            double dsw;
+            curve_alt(c, psi, po, w, kr, dsw, true);
+            eta = w * sn + po * dsw;
+            double d2 = 0.0;     // d2(sw)/d(psi)2
+            if (c.ivghu == 4) {
+                if (psi < c.bcpsat) {
+                    const double porm = (po - c.bcrmc) / po, q = c.bcpsat / psi;
+                    d2 = porm * ((c.bcbeta * c.bcb1 / (c.bcpsat * c.bcpsat)) * pow(q, c.bcbeta + 2.0));
+                    dkr = (c.bc23b / fabs(c.bcpsat)) * pow(q, 3.0 + (3.0 * c.bcbeta));
+                }
+            } else if (psi < c.hupsia) {
+                const double pap = c.hupsia - psi, papr = 1.0 / pap, lambda = c.hualb * pow(pap, c.hubeta), lamr = 1.0 / (1.0 + lambda);
+                const double se = pow(lamr, c.hugama), dsedp = (c.hugb * lambda / pap) * pow(lamr, c.hugam1);
+                d2 = c.huswr1 * (c.hugb * lambda * papr * papr * ((1.0 - c.hubeta) + (1.0 + c.hugb) * lambda) * pow(lamr, c.hugama + 2.0));
+                dkr = c.ivghu == 2 ? c.hun * pow(se, c.hun - 1.0) * dsedp : ((2.0 * c.hua) * se + c.hub2a) * dsedp * kr * log(10.0);
+            }
+            deta = dsw * sn + po * d2;
+        }
+        sw[i] = w; ckrw[i] = kr; etai[i] = eta; dckrw[i] = dkr; detai[i] = deta;
+    }
+}
+__global__ void k_sw_pair_alt(int n, CurveModel c, Soil s, const double *__restrict__ pnew, const double *__restrict__ ptimep, int do_timep,
+                              double *__restrict__ swnew, double *__restrict__ swtimep)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double w, d1, d2;
+        if (c.ivghu == 1) xvg_node(s, i, pnew[i], false, false, w, d1, d2); else curve_alt(c, pnew[i], s.pnodi[i], w, d1, d2, false);
+        swnew[i] = w;
+        if (do_timep) {
+            if (c.ivghu == 1) xvg_node(s, i, ptimep[i], false, false, w, d1, d2); else curve_alt(c, ptimep[i], s.pnodi[i], w, d1, d2, false);
+            swtimep[i] = w;
+        }
+    }
+}
 // SWNEW = Sw(PNEW), SWTIMEP = Sw(PTIMEP) for the storage change of the mass balance (the reference's Newton path leaves
 // them unset -- its mbeconv prints NaN there)
 __global__ void k_sw_pair(int n, Soil s, const double *__restrict__ pnew, const double *__restrict__ ptimep, int do_timep,
@@ -3244,6 +3298,9 @@ static int assemble_system_newton(CathySim *S, double deltat)
 {
     const int n = S->n;
     Diag A = make_diag(S, S->A.p), Ju = make_diag(S, S->Ju.p), Jl = make_diag(S, S->Jl.p);
+    if (S->cm.ivghu != 0)
+        LAUNCH(S, k_curves_newton_alt, nblk(n, S->grid_n), RED_BLOCK, n, S->cm, make_soil(S), S->ptnew.p, S->sw.p, S->ckrw.p, S->et1.p, S->dckrw.p, S->detai.p);
+    else
     LAUNCH(S, k_curves_newton, nblk(n, S->grid_n), RED_BLOCK, n, make_soil(S), S->ptnew.p, S->sw.p, S->ckrw.p, S->et1.p, S->dckrw.p, S->detai.p);
     LAUNCH(S, k_tet_newton, nblk(S->nt, 4 * S->grid_n), RED_BLOCK, S->nt, S->tet.p, S->ckrw.p, S->et1.p, S->ptnew.p, S->pnew.p, S->ptimep.p,
            S->tet_k0.p, S->tet_gz.p, S->tet_vol.p, S->tetaf, 1.0 / deltat, S->krt.p, S->e1t.p, S->ts.p, S->s1.p);
@@ -3291,6 +3348,9 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
             LAUNCH(S, k_bkflux_list_n, nblk(m, S->grid_n), RED_BLOCK, m, S->contp_list.p, Ju, Jl, S->pdiff.p, S->xt5.p, S->tetaf, S->qpold.p, S->qpnew.p);
             LAUNCH(S, k_flux_sums, 1, RED_BLOCK, m, S->qpnew.p, S->bcsum.p);
         }
+        if (S->cm.ivghu != 0)
+            LAUNCH(S, k_sw_pair_alt, nblk(n, S->grid_n), RED_BLOCK, n, S->cm, make_soil(S), S->pnew.p, S->ptimep.p, S->timep_dirty, S->swnew.p, S->swtimep.p);
+        else
         LAUNCH(S, k_sw_pair, nblk(n, S->grid_n), RED_BLOCK, n, make_soil(S), S->pnew.p, S->ptimep.p, S->timep_dirty, S->swnew.p, S->swtimep.p);
         S->timep_dirty = 0;
     } else {
@@ -3527,7 +3587,8 @@ static int preload_kernels()
                          (const void *)k_switch_old, (const void *)k_adrstn, (const void *)k_pondupd, (const void *)k_atm_interp, (const void *)k_etran,
                          (const void *)k_div_area, (const void *)k_nod_cell, (const void *)k_cell_nod, (const void *)k_route, (const void *)k_pond_zero,
                          (const void *)k_step_partial, (const void *)k_step_final, (const void *)k_weight, (const void *)k_atmone, (const void *)k_mbinit,
-                         (const void *)k_pack_col, (const void *)k_unpack_col, (const void *)k_vel3d, (const void *)k_vnod3d, (const void *)k_recharge, (const void *)k_wtdepth, (const void *)k_curves_alt, (const void *)k_chvelo_alt, (const void *)k_relax, (const void *)k_pcg_res<1024>};
+                         (const void *)k_pack_col, (const void *)k_unpack_col, (const void *)k_vel3d, (const void *)k_vnod3d, (const void *)k_recharge, (const void *)k_wtdepth, (const void *)k_curves_alt, (const void *)k_chvelo_alt, (const void *)k_curves_xvg, (const void *)k_chvelo_xvg,
+                         (const void *)k_curves_newton_alt, (const void *)k_sw_pair_alt, (const void *)k_relax, (const void *)k_pcg_res<1024>};
     for (const void *f : fns) CK(cudaFuncGetAttributes(&at, f));
     done = true;
     return 0;
@@ -3860,7 +3921,6 @@ int32_t cathy_create(const CathyProblem *prob, CathySim **out)
     if (prob->kslope != 0) FAIL(-2, "KSLOPE=%d: only analytical moisture-curve derivatives (0) are implemented", prob->kslope);
     if (!(prob->ivghu >= 0 && prob->ivghu <= 4))
         FAIL(-2, "IVGHU=%d: van Genuchten (0), extended van Genuchten (1), Huyakorn (2, 3) and Brooks-Corey (4) curves are implemented; look-up tables (-1) are not", prob->ivghu);
-    if (prob->ivghu != 0 && prob->iopt != 1) FAIL(-2, "IVGHU=%d with the Newton scheme is not implemented (Picard only)", prob->ivghu);
     if (prob->lump == 0) FAIL(-2, "LUMP=0 (consistent mass matrix) is not implemented on the device");
     if (prob->nlrelx != 0 && prob->nlrelx != 1) FAIL(-2, "NLRELX=%d: only no relaxation (0) and constant OMEGA (1) are implemented", prob->nlrelx);
     if (prob->isimgr != 1 && prob->isimgr != 2) FAIL(-2, "ISIMGR=%d not supported", prob->isimgr);

@@ -532,6 +532,33 @@ def test_huyakorn_and_brooks_corey_curves(gpu_lib, oracle_mod, tmp_path, ivghu, 
     assert np.max(np.abs(g.state()["sw"] - c.state()["sw"])) < 1e-6
 
 
+@pytest.mark.parametrize("ivghu,xvg_case", [(1, 0), (1, 1), (2, None), (3, None), (4, None)])
+def test_other_moisture_curves_under_newton(gpu_lib, oracle_mod, tmp_path, ivghu, xvg_case):
+    """CHNEW0's IVGHU = 1..4 branches (SRC/chnew0.f:39-89) in `k_curves_newton_alt`: Jacobian and RHS of a system with active
+    derivative terms to 1e-10 / 1e-9, then the whole run with the accepted steps of the reference's Newton ELF (the oracle is byte-identical
+    to it on these projects: test_oracle_other_moisture_curves_newton_against_reference_elf_when_available) and the oracle's heads."""
+    from pycathy_wrapper_b200.capi import Simulation
+    from pycathy_wrapper_b200.project import load_project
+    from test_oracle_golden import _curve_project
+    d, nstep = _curve_project(str(tmp_path / "p"), ivghu, xvg_case, newton=True)
+    prj = load_project(d)
+    g, c = Simulation(gpu_lib, prj), oracle_mod.simulation(prj)
+    for _ in range(12):
+        g.step(); c.step()
+    tg, jg, ag, bg = g.debug_assemble(5.0)
+    tc, jc, ac, bc = c.debug_assemble(5.0)
+    assert np.array_equal(tg, tc) and np.array_equal(jg, jc)
+    big = ac > 1e80
+    assert np.array_equal(big, ag > 1e80)
+    assert np.max(np.abs(ag[~big] - ac[~big])) <= 1e-10 * np.abs(ac[~big]).max()
+    assert np.max(np.abs(bg - bc)) <= 1e-9 * max(np.abs(bc).max(), 1e-30)
+    g, c, rg, rc = _run_both(gpu_lib, oracle_mod, prj)
+    assert rg.nstep == nstep
+    ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
+    assert ok, dmax
+    assert np.max(np.abs(g.state()["sw"] - c.state()["sw"])) < 1e-6
+
+
 @pytest.mark.parametrize("ivert", [0, 1, 2])
 def test_soil_zones_and_ivert(gpu_lib, oracle_mod, tmp_path, ivert):
     """NZONE = 3 soil zones with per-(layer, zone) soils and IVERT = 0, 1, 2 (SRC/gen3d.f, SRC/tpnodi.f): same accepted steps and
