@@ -1,4 +1,4 @@
-timeout 700 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "curves or zones or newton" 2>&1 | tail -25
+timeout 700 python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short -k "curves or zones or newton" 2>&1 | tail -60
 python bench.py --steps 20 --warmup 3 --no-cpu 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])

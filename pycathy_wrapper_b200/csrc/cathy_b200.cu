@@ -2925,7 +2925,7 @@ static int build_static(CathySim *S)
     rc |= S->vgn.upload(vgn); rc |= S->vgm.upload(vgm); rc |= S->vgpsat.upload(vgpsat); rc |= S->vgpnot.upload(vgpnot);
     rc |= S->rr.upload(rr); rc |= S->snodi.upload(snodi); rc |= S->pnodi.upload(pnodi); rc |= S->vgn1.upload(vgn1);
     rc |= S->vgnr.upload(vgnr); rc |= S->vgpsn.upload(vgpsn); rc |= S->vgmr.upload(vgmr); rc |= S->volnod.upload(volnod);
-    if (newton) { rc |= S->vgm52.upload(vgm52); rc |= S->vgmm1.upload(vgmm1); }
+    if (newton || p.ivghu == 1) { rc |= S->vgm52.upload(vgm52); rc |= S->vgmm1.upload(vgmm1); }   // FXVKR needs VGM52 under Picard too
     rc |= S->arenod.upload(S->harenod); rc |= S->z.upload(S->hz); rc |= S->m4.upload(m4); rc |= S->veg.upload(veg);
     rc |= S->vegpar.upload(vegpar); rc |= S->tet.upload(tet);
     if (S->bc_any) rc |= S->kznod.upload(kznod);
