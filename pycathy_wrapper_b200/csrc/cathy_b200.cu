@@ -1443,13 +1443,24 @@ __global__ void k_tet_newton(int nt, const int4 *__restrict__ tet, const double 
     }
 }
 // Gather pass of ASSNEW: stiffness A (symmetric, 8 upper diagonals) and the derivative part C3 of the Jacobian, upper and lower.
-__global__ void __launch_bounds__(RED_BLOCK) k_assemble_newton(int n, int nt, EllPlan P, const unsigned char *__restrict__ loc,
+// DERIVED: tet indices as base(k) + per-class offset (tables of k_assemble_a, verified against every stored entry at cathy_create)
+// instead of the stored lists: 4 bytes less per contribution, same contributions in the same order.
+template <bool DERIVED>
+__global__ void __launch_bounds__(RED_BLOCK) k_assemble_newton(int n, int nt, EllPlan P, PlanGeom G, const unsigned char *__restrict__ loc,
                                                                const double *__restrict__ krt, const double *__restrict__ etat,
                                                                const double *__restrict__ ts, const double *__restrict__ s1,
                                                                const double *__restrict__ dckrw, const double *__restrict__ detai, Diag A,
                                                                Diag C3u, Diag C3l, double *__restrict__ grav, double *__restrict__ m2)
 {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        int base = 0;
+        const int *__restrict__ rl = nullptr;
+        if (DERIVED) {
+            const int l = k / G.nnod, sidx = k - l * G.nnod, i = sidx / G.nc1, j = sidx - i * G.nc1;
+            const int cls = ((l == 0 ? 0 : l == G.nstr ? 2 : 1) * 3 + (i == 0 ? 0 : i == G.nrow ? 2 : 1)) * 3 + (j == 0 ? 0 : j == G.ncol ? 2 : 1);
+            base = G.ntri3 * l + 6 * (i * G.ncol + j);
+            rl = G.rel + (size_t)cls * NDIAG * G.wrel;
+        }
 #pragma unroll
         for (int d = 0; d < NDIAG; ++d) {
             const EllFamily f = P.diag[d];
@@ -1457,7 +1468,7 @@ __global__ void __launch_bounds__(RED_BLOCK) k_assemble_newton(int n, int nt, El
             double acc = 0.0, gu = 0.0, hu = 0.0, gl = 0.0, hl = 0.0;
             for (int c = 0; c < f.w; ++c) {
                 size_t q = (size_t)c * P.ld + k;
-                int t = f.tet[q];
+                int t = DERIVED ? min(max(base + __ldg(rl + d * G.wrel + c), 0), G.nt - 1) : f.tet[q];
                 unsigned l = lc[q];
                 acc += krt[t] * f.coef[q];
                 if (l & 16u) {
@@ -1475,7 +1486,7 @@ __global__ void __launch_bounds__(RED_BLOCK) k_assemble_newton(int n, int nt, El
         double g = 0.0, m = 0.0;
         for (int c = 0; c < f.w; ++c) {
             size_t q = (size_t)c * P.ld + k;
-            int t = f.tet[q];
+            int t = DERIVED ? min(max(base + __ldg(rl + c), 0), G.nt - 1) : f.tet[q];     // DERIVED implies node.pad: the node family lists the tets of diag[0]
             g += krt[t] * f.coef[q];
             m += etat[t] * f.coef2[q];
         }
@@ -2937,7 +2948,7 @@ static int build_static(CathySim *S)
     S->plan.node.pad = wnode == wd[0] && std::memcmp(e_tet.data() + fam_off[0], e_tet.data() + fam_off[NDIAG], (size_t)wnode * ld * sizeof(int)) == 0;
     // --- tet indices as base(k) + per-class offset (k_assemble_a): build the 27 tables and verify every stored entry against them
     S->geom = PlanGeom{};
-    if (!newton && S->plan.node.pad && !getenv("CATHY_PLAN_STORED") && (long long)nt < (1LL << 30)) {
+    if (S->plan.node.pad && !getenv("CATHY_PLAN_STORED") && (long long)nt < (1LL << 30)) {
         int wrel = 0;
         for (int d = 0; d < NDIAG; ++d) wrel = std::max(wrel, wd[d]);
         const int UNSET = INT32_MIN;
@@ -3304,7 +3315,9 @@ static int assemble_system_newton(CathySim *S, double deltat)
     LAUNCH(S, k_curves_newton, nblk(n, S->grid_n), RED_BLOCK, n, make_soil(S), S->ptnew.p, S->sw.p, S->ckrw.p, S->et1.p, S->dckrw.p, S->detai.p);
     LAUNCH(S, k_tet_newton, nblk(S->nt, 4 * S->grid_n), RED_BLOCK, S->nt, S->tet.p, S->ckrw.p, S->et1.p, S->ptnew.p, S->pnew.p, S->ptimep.p,
            S->tet_k0.p, S->tet_gz.p, S->tet_vol.p, S->tetaf, 1.0 / deltat, S->krt.p, S->e1t.p, S->ts.p, S->s1.p);
-    LAUNCH(S, k_assemble_newton, nblk(n, 4 * S->grid_n), RED_BLOCK, n, S->nt, S->plan, S->ell_loc.p, S->krt.p, S->e1t.p, S->ts.p, S->s1.p,
+    if (S->geom.rel) LAUNCH(S, k_assemble_newton<true>, nblk(n, 4 * S->grid_n), RED_BLOCK, n, S->nt, S->plan, S->geom, S->ell_loc.p, S->krt.p, S->e1t.p, S->ts.p, S->s1.p,
+           S->dckrw.p, S->detai.p, A, Ju, Jl, S->grav.p, S->m2.p);
+    else LAUNCH(S, k_assemble_newton<false>, nblk(n, 4 * S->grid_n), RED_BLOCK, n, S->nt, S->plan, S->geom, S->ell_loc.p, S->krt.p, S->e1t.p, S->ts.p, S->s1.p,
            S->dckrw.p, S->detai.p, A, Ju, Jl, S->grav.p, S->m2.p);
     LAUNCH(S, k_rhs_lhs_newton, nblk(n, S->grid_n), RED_BLOCK, n, S->nnod, A, Ju, Jl, S->tetaf, 1.0 / deltat, S->ptnew.p, S->pnew.p, S->ptimep.p,
            S->m2.p, S->grav.p, S->ifatm.p, S->have_dir ? S->contp_flag.p : (const unsigned char *)nullptr,
@@ -3580,7 +3593,7 @@ static int preload_kernels()
                          (const void *)k_dd_combine_step, (const void *)k_pcg<1024, true, true>, (const void *)k_pcg<1024, true, false>, (const void *)k_pcg2<1024>, (const void *)k_sym_scale, (const void *)k_sym_scale2,
                          (const void *)k_pcg<1024, false, false>, (const void *)k_pcg<512, true, false>, (const void *)k_pcg<512, false, false>,
                          (const void *)k_pcg<256, true, false>, (const void *)k_pcg<256, false, false>, (const void *)k_curves_newton,
-                         (const void *)k_sw_pair, (const void *)k_tet_newton, (const void *)k_assemble_newton, (const void *)k_rhs_lhs_newton,
+                         (const void *)k_sw_pair, (const void *)k_tet_newton, (const void *)k_assemble_newton<true>, (const void *)k_assemble_newton<false>, (const void *)k_rhs_lhs_newton,
                          (const void *)k_bkflux_n, (const void *)k_bkflux_list_n, (const void *)k_bicgstab<1024>, (const void *)k_update,
                          (const void *)k_bkflux, (const void *)k_bkflux_list, (const void *)k_mark_nonatm, (const void *)k_flux_sums,
                          (const void *)k_free_drain_list, (const void *)k_norms, (const void *)k_norms_final, (const void *)k_switch,

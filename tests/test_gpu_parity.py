@@ -189,6 +189,24 @@ def test_assembly_with_derived_tet_indices_equals_stored_lists(gpu_lib, weill, t
         assert np.array_equal(a, b)
 
 
+def test_newton_assembly_with_derived_tet_indices_equals_stored_lists(gpu_lib, newton20, monkeypatch):
+    """k_assemble_newton<true> (derived tet indices, the tables of k_assemble_a) against k_assemble_newton<false> (stored lists):
+    Jacobian (stiffness + derivative terms, upper and lower) and right-hand side bit-identical, with active derivative terms."""
+    from pycathy_wrapper_b200.capi import Simulation
+    out = {}
+    for stored in (0, 1):
+        if stored:
+            monkeypatch.setenv("CATHY_PLAN_STORED", "1")
+        sim = Simulation(gpu_lib, newton20)
+        assert sim.plan_info()["analytic"] == (not stored)
+        for _ in range(3):
+            sim.step()
+        out[stored] = sim.debug_assemble(2.0)
+        sim.close()
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+
+
 def test_state_async_equals_state(gpu_lib, weill):
     """cathy_get_state_async + cathy_state_wait (snapshot drained by a second stream while the next step computes) returns
     exactly what the blocking cathy_get_state returns for the same step."""
