@@ -279,7 +279,7 @@ def run_ours(args, size):
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                     "traffic": traffic, "share_of_step": pcg_ms / gpu_ms if gpu_ms else None,
+                     "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "traffic_detail": traffic, "share_of_step": pcg_ms / gpu_ms if gpu_ms else None,
                      "algorithmic_bytes_per_row_iter": (2.0 * (12.0 * sim_nnz + 20.0 * n) + 80.0 * n) / n if newton else PCG_BYTES_PER_ROW_ITER, "kernel_bytes": kernel_bytes,
                      "us_per_pcg_iter": 1e3 * pcg_ms / max(pcg_iters, 1),
                      "spmv_only": {"achieved": SPMV_BYTES_PER_ROW * n / (spmv_ms / 1e3) / 1e9, "ms": spmv_ms,
