@@ -2,7 +2,7 @@
 import os, sys, time
 import numpy as np
 import torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from pycathy_wrapper_b200.capi import Simulation, load_library
 lib = load_library()
