@@ -2150,24 +2150,43 @@ struct RouteArgs {
     double *ak_max;           // in/out
     int *nsurf_out;
     double deltat, cellarea;
+    double *ckf1, *ckf2, *dhd1, *dhd2;   // static factors of MC per cell and direction (k_route_static)
 };
-// Muskingum-Cunge for one cell and direction (MC, SRC/mc.f)
-__device__ __forceinline__ double mc_cell(double slope, double epl, double ks, double w, double b1, double y1, double dt,
+// Muskingum-Cunge for one cell and direction (MC, SRC/mc.f).  Of the kinematic celerity
+//   CK = 5/(3 G) KS^(3/5) W^(-2/5) sin(BETA)^(3/10) QC^(1 - 3G/5)   and   DH = QC^(1 - B1) / (2 G W tan(BETA))
+// only the powers of QC change during a run: the leading product `ckf` and the denominator `dhd` are evaluated once per cell and
+// direction by k_route_static with the same operations in the same order (products associate left to right), so hoisting them
+// leaves every result bit-identical and takes 3 of the 5 pow() calls, atan, sin and tan out of each cell's dependent chain --
+// the routing runs level by level on ONE SM, where this chain is the critical path.
+__device__ __forceinline__ void mc_static(double slope, double ks, double w, double b1, double y1, double &ckf, double &dhd)
+{
+    double beta = atan(slope);
+    double g = (1.0 - y1 + 2.0 / 3.0 * b1);
+    ckf = 5.0 / (3.0 * g) * pow(ks, 3.0 / 5.0) * pow(w, -2.0 / 5.0) * pow(sin(beta), 3.0 / 1.0e1);
+    dhd = 2 * g * w * tan(beta);
+}
+__device__ __forceinline__ double mc_cell(double ckf, double dhd, double epl, double b1, double y1, double dt,
                                           double q_in_kk, double q_in_kkp1, double q_out_kk, double q_over, double &cu, double &ak)
 {
     double qc = 1.0 / 3.0 * (q_in_kk + q_in_kkp1 + q_out_kk);
     if (qc <= 1.0e-05) qc = 1.0e-05;
-    double beta = atan(slope);
     double g = (1.0 - y1 + 2.0 / 3.0 * b1);
-    double ck = 5.0 / (3.0 * g) * pow(ks, 3.0 / 5.0) * pow(w, -2.0 / 5.0) * pow(sin(beta), 3.0 / 1.0e1) * pow(qc, 1.0 - 3.0 * g / 5.0);
+    double ck = ckf * pow(qc, 1.0 - 3.0 * g / 5.0);
     ak = ck / epl;
     cu = ck * dt / epl;
-    double dh = pow(qc, 1.0 - b1) / (2 * g * w * tan(beta));
+    double dh = pow(qc, 1.0 - b1) / dhd;
     if (dh < (1.0 - cu)) dh = 1.0 - cu;
     double xx = 0.50 - dh / (ck * epl);
     double den = 2.0 * (1.0 - xx) + cu;
     double c1 = (cu - 2.0 * xx) / den, c2 = (cu + 2.0 * xx) / den, c3 = (2.0 * (1.0 - xx) - cu) / den, c4 = (2.0 * ck * dt) / den;
     return c1 * q_in_kkp1 + c2 * q_in_kk + c3 * q_out_kk + c4 * q_over;
+}
+__global__ void k_route_static(RouteArgs a)
+{
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.ncell; c += gridDim.x * blockDim.x) {
+        mc_static(a.sl1[c], a.ks1[c], a.ws1[c], a.b1[c], a.y1[c], a.ckf1[c], a.dhd1[c]);
+        mc_static(a.sl2[c], a.ks2[c], a.ws2[c], a.b1[c], a.y1[c], a.ckf2[c], a.dhd2[c]);
+    }
 }
 // All NSURF sub-steps of ROUTE + ALTEZZE (SRC/route.f:47-253, SRC/altezze.f) in ONE launch of one CTA:
 // cells are processed level by level down the drainage tree (a cell's inflow is the ordered sum of its
@@ -2209,7 +2228,7 @@ __global__ void __launch_bounds__(1024) k_route(RouteArgs a)
                     double q_over = swv * w * (1.0 / epl);
                     double q_in_kk = a.q_in_kk[ib] * w / nrc, q_out_kk = (dir ? a.q_out_kk_2[ib] : a.q_out_kk_1[ib]) / nrc;
                     double q_in_kkp1 = qin * w / nrc, cu, ak;
-                    double qo = mc_cell(dir ? a.sl2[ib] : a.sl1[ib], epl, dir ? a.ks2[ib] : a.ks1[ib], dir ? a.ws2[ib] : a.ws1[ib],
+                    double qo = mc_cell(dir ? a.ckf2[ib] : a.ckf1[ib], dir ? a.dhd2[ib] : a.dhd1[ib], epl,
                                         a.b1[ib], a.y1[ib], dt, q_in_kk, q_in_kkp1, q_out_kk, q_over, cu, ak);
                     if (qo < 0.0) qo = 0.0;
                     qo_kkp1[ib] = qo * nrc;
@@ -2640,7 +2659,8 @@ struct CathySim {
     // surface routing
     DBuf<int> lv_ptr, lv_cell, seqpos, don_ptr, don_cell;
     DBuf<unsigned char> don_dir;
-    DBuf<double> r_w1, r_w2, r_sl1, r_sl2, r_epl1, r_epl2, r_ks1, r_ks2, r_ws1, r_ws2, r_b1, r_y1, r_nrc;
+    DBuf<double> r_w1, r_w2, r_sl1, r_sl2, r_epl1, r_epl2, r_ks1, r_ks2, r_ws1, r_ws2, r_b1, r_y1, r_nrc, r_ckf1, r_ckf2, r_dhd1, r_dhd2;
+    bool route_static_done = false;
     DBuf<double> sw_sn, q_in_kk, q_in_kkp1, q_out_kk_1, q_out_kk_2, q_out_kkp1_1, q_out_kkp1_2, volume_kk, volume_kkp1, h_water;
     DBuf<double> q_in_kk_sav, q_out_kk_1_sav, q_out_kk_2_sav, volume_kk_sav, q_in_kk_p, q_out_kk_1_p, q_out_kk_2_p, volume_kk_p;
     DBuf<double> d_akmax;   // [3]: ak_max, ak_max_p, ak_max_sav
@@ -3045,6 +3065,8 @@ static int build_surface(CathySim *S)
                             &S->volume_kk, &S->volume_kkp1, &S->h_water, &S->q_in_kk_sav, &S->q_out_kk_1_sav, &S->q_out_kk_2_sav,
                             &S->volume_kk_sav, &S->q_in_kk_p, &S->q_out_kk_1_p, &S->q_out_kk_2_p, &S->volume_kk_p};
     for (auto *b : bufs) rc |= b->alloc(nc);
+    rc |= S->r_ckf1.alloc(nc); rc |= S->r_ckf2.alloc(nc); rc |= S->r_dhd1.alloc(nc); rc |= S->r_dhd2.alloc(nc);
+    S->route_static_done = false;
     rc |= S->d_akmax.alloc(3); rc |= S->d_nsurf.alloc(1);
     if (rc) FAIL(-101, "device allocation of surface routing tables failed");
     return 0;
@@ -3481,6 +3503,8 @@ static int surf_flowtra(CathySim *S)
     a.sw_sn = S->sw_sn.p; a.q_in_kk = S->q_in_kk.p; a.q_in_kkp1 = S->q_in_kkp1.p; a.q_out_kk_1 = S->q_out_kk_1.p; a.q_out_kk_2 = S->q_out_kk_2.p;
     a.q_out_kkp1_1 = S->q_out_kkp1_1.p; a.q_out_kkp1_2 = S->q_out_kkp1_2.p; a.volume_kk = S->volume_kk.p; a.volume_kkp1 = S->volume_kkp1.p;
     a.h_water = S->h_water.p; a.ak_max = S->d_akmax.p; a.nsurf_out = S->d_nsurf.p; a.deltat = S->deltat; a.cellarea = S->p.dx * S->p.dy;
+    a.ckf1 = S->r_ckf1.p; a.ckf2 = S->r_ckf2.p; a.dhd1 = S->r_dhd1.p; a.dhd2 = S->r_dhd2.p;
+    if (!S->route_static_done) { LAUNCH(S, k_route_static, nblk(S->ncell, S->grid_n), RED_BLOCK, a); S->route_static_done = true; }
     LAUNCH(S, k_route, 1, 1024, a);
     LAUNCH(S, k_cell_nod, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nrow, S->ncol, S->h_water.p, S->pondnod.p);
     cudaMemsetAsync(S->d_flags.p, 0, sizeof(int), S->st);
@@ -3546,7 +3570,7 @@ void cathy_destroy(CathySim *S)
                           &S->et1, &S->et2, &S->swnew, &S->swtimep, &S->rhs, &S->xt5, &S->qtranie, &S->wr, &S->wz, &S->wp0, &S->wp1, &S->wbv,
                           &S->partial, &S->store_part, &S->atmpot, &S->atmact, &S->atmold, &S->atmtab, &S->pondnod, &S->ovflnod, &S->ovflp,
                           &S->scal3, &S->r_w1, &S->r_w2, &S->r_sl1, &S->r_sl2, &S->r_epl1, &S->r_epl2, &S->r_ks1, &S->r_ks2, &S->r_ws1, &S->r_ws2,
-                          &S->r_b1, &S->r_y1, &S->r_nrc, &S->sw_sn, &S->q_in_kk, &S->q_in_kkp1, &S->q_out_kk_1, &S->q_out_kk_2, &S->q_out_kkp1_1,
+                          &S->r_b1, &S->r_y1, &S->r_nrc, &S->r_ckf1, &S->r_ckf2, &S->r_dhd1, &S->r_dhd2, &S->sw_sn, &S->q_in_kk, &S->q_in_kkp1, &S->q_out_kk_1, &S->q_out_kk_2, &S->q_out_kkp1_1,
                           &S->q_out_kkp1_2, &S->volume_kk, &S->volume_kkp1, &S->h_water, &S->q_in_kk_sav, &S->q_out_kk_1_sav, &S->q_out_kk_2_sav,
                           &S->volume_kk_sav, &S->q_in_kk_p, &S->q_out_kk_1_p, &S->q_out_kk_2_p, &S->volume_kk_p, &S->d_akmax};
     for (auto *b : dd) b->release();
@@ -3598,7 +3622,7 @@ static int preload_kernels()
                          (const void *)k_bkflux, (const void *)k_bkflux_list, (const void *)k_mark_nonatm, (const void *)k_flux_sums,
                          (const void *)k_free_drain_list, (const void *)k_norms, (const void *)k_norms_final, (const void *)k_switch,
                          (const void *)k_switch_old, (const void *)k_adrstn, (const void *)k_pondupd, (const void *)k_atm_interp, (const void *)k_etran,
-                         (const void *)k_div_area, (const void *)k_nod_cell, (const void *)k_cell_nod, (const void *)k_route, (const void *)k_pond_zero,
+                         (const void *)k_div_area, (const void *)k_nod_cell, (const void *)k_cell_nod, (const void *)k_route, (const void *)k_route_static, (const void *)k_pond_zero,
                          (const void *)k_step_partial, (const void *)k_step_final, (const void *)k_weight, (const void *)k_atmone, (const void *)k_mbinit,
                          (const void *)k_pack_col, (const void *)k_unpack_col, (const void *)k_vel3d, (const void *)k_vnod3d, (const void *)k_recharge, (const void *)k_wtdepth, (const void *)k_curves_alt, (const void *)k_chvelo_alt, (const void *)k_curves_xvg, (const void *)k_chvelo_xvg,
                          (const void *)k_curves_newton_alt, (const void *)k_sw_pair_alt, (const void *)k_relax, (const void *)k_pcg_res<1024>};
