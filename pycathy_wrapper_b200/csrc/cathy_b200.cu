@@ -2191,7 +2191,56 @@ __global__ void k_route_static(RouteArgs a)
 // All NSURF sub-steps of ROUTE + ALTEZZE (SRC/route.f:47-253, SRC/altezze.f) in ONE launch of one CTA:
 // cells are processed level by level down the drainage tree (a cell's inflow is the ordered sum of its
 // donors' outflows, so the result equals the reference's sequential descending-elevation sweep).
-__global__ void __launch_bounds__(1024) k_route(RouteArgs a)
+// The levels are short (a few hundred cells) and strictly dependent, so the time per level is the latency of one thread's chain
+// level_cell -> don_ptr -> don_cell -> donor outflow -> MC.  Everything in that chain that does not depend on the previous level
+// (indices, donor lists, the cell's parameters and old-time-level values) is loaded one level AHEAD, while the current level
+// computes: after the barrier only the donors' outflows remain to be fetched.
+constexpr int ROUTE_BLOCK = 512, ROUTE_RD = 4;
+struct RouteCell {
+    int ib, d0, nd, seq;
+    int dc[ROUTE_RD];        // the first ROUTE_RD donors: routing index * 2 + direction
+    double w[2], epl[2], ckf[2], dhd[2], qok[2], nrc, b1, y1, sw, qik;
+};
+__device__ __forceinline__ void route_load(const RouteArgs &a, int q, RouteCell &c)
+{
+    const int ib = a.level_cell[q];
+    c.ib = ib; c.seq = a.seq[ib];
+    c.d0 = a.don_ptr[ib]; c.nd = a.don_ptr[ib + 1] - c.d0;
+#pragma unroll
+    for (int j = 0; j < ROUTE_RD; ++j) c.dc[j] = j < c.nd ? a.don_cell[c.d0 + j] * 2 + a.don_dir[c.d0 + j] : 0;
+    c.w[0] = a.w1[ib]; c.w[1] = a.w2[ib]; c.epl[0] = a.epl1[ib]; c.epl[1] = a.epl2[ib];
+    c.ckf[0] = a.ckf1[ib]; c.ckf[1] = a.ckf2[ib]; c.dhd[0] = a.dhd1[ib]; c.dhd[1] = a.dhd2[ib];
+    c.qok[0] = a.q_out_kk_1[ib]; c.qok[1] = a.q_out_kk_2[ib];
+    c.nrc = a.nrc[ib]; c.b1 = a.b1[ib]; c.y1 = a.y1[ib]; c.sw = a.sw_sn[ib]; c.qik = a.q_in_kk[ib];
+}
+__device__ __forceinline__ void route_cell(const RouteArgs &a, const RouteCell &c, double dt, double &best_cu, double &best_ak, int &best_seq)
+{
+    const int ib = c.ib;
+    double qin = 0.0;
+#pragma unroll
+    for (int j = 0; j < ROUTE_RD; ++j)
+        if (j < c.nd) qin = qin + ((c.dc[j] & 1) ? a.q_out_kkp1_2[c.dc[j] >> 1] : a.q_out_kkp1_1[c.dc[j] >> 1]);
+    for (int dn = c.d0 + ROUTE_RD; dn < c.d0 + c.nd; ++dn)
+        qin = qin + (a.don_dir[dn] ? a.q_out_kkp1_2[a.don_cell[dn]] : a.q_out_kkp1_1[a.don_cell[dn]]);
+    a.q_in_kkp1[ib] = qin;
+    const double nrc = c.nrc, swv = c.sw / nrc;
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+        const double w = c.w[dir];
+        double *qo_kkp1 = dir ? a.q_out_kkp1_2 : a.q_out_kkp1_1;
+        if (w == 0.0) continue;
+        const double epl = c.epl[dir];
+        double q_over = swv * w * (1.0 / epl);
+        double q_in_kk = c.qik * w / nrc, q_out_kk = c.qok[dir] / nrc;
+        double q_in_kkp1 = qin * w / nrc, cu, ak;
+        double qo = mc_cell(c.ckf[dir], c.dhd[dir], epl, c.b1, c.y1, dt, q_in_kk, q_in_kkp1, q_out_kk, q_over, cu, ak);
+        if (qo < 0.0) qo = 0.0;
+        qo_kkp1[ib] = qo * nrc;
+        int sq = 2 * c.seq + dir;
+        if (cu > best_cu || (cu == best_cu && sq > best_seq)) { best_cu = cu; best_ak = ak; best_seq = sq; }
+    }
+}
+__global__ void __launch_bounds__(ROUTE_BLOCK) k_route(RouteArgs a)
 {
     __shared__ double s_cu[32], s_ak[32];
     __shared__ int s_seq[32];
@@ -2208,33 +2257,28 @@ __global__ void __launch_bounds__(1024) k_route(RouteArgs a)
     __syncthreads();
     const int nsurf = s_nsurf;
     const double dt = s_dt;
+    const int *__restrict__ lp = a.level_ptr;
     for (int sub = 1; sub <= nsurf; ++sub) {
         double best_cu = -1.0, best_ak = 0.0;
         int best_seq = -1;
+        RouteCell nxt;
+        bool have = (int)threadIdx.x < lp[1] - lp[0];
+        if (have) route_load(a, lp[0] + threadIdx.x, nxt);
         for (int lv = 0; lv < a.nlevel; ++lv) {
-            for (int q = a.level_ptr[lv] + threadIdx.x; q < a.level_ptr[lv + 1]; q += blockDim.x) {
-                int ib = a.level_cell[q];
-                double qin = 0.0;
-                for (int dn = a.don_ptr[ib]; dn < a.don_ptr[ib + 1]; ++dn)
-                    qin = qin + (a.don_dir[dn] ? a.q_out_kkp1_2[a.don_cell[dn]] : a.q_out_kkp1_1[a.don_cell[dn]]);
-                a.q_in_kkp1[ib] = qin;
-                double nrc = a.nrc[ib], swv = a.sw_sn[ib] / nrc;
-#pragma unroll
-                for (int dir = 0; dir < 2; ++dir) {
-                    double w = dir ? a.w2[ib] : a.w1[ib];
-                    double *qo_kkp1 = dir ? a.q_out_kkp1_2 : a.q_out_kkp1_1;
-                    if (w == 0.0) continue;
-                    double epl = dir ? a.epl2[ib] : a.epl1[ib];
-                    double q_over = swv * w * (1.0 / epl);
-                    double q_in_kk = a.q_in_kk[ib] * w / nrc, q_out_kk = (dir ? a.q_out_kk_2[ib] : a.q_out_kk_1[ib]) / nrc;
-                    double q_in_kkp1 = qin * w / nrc, cu, ak;
-                    double qo = mc_cell(dir ? a.ckf2[ib] : a.ckf1[ib], dir ? a.dhd2[ib] : a.dhd1[ib], epl,
-                                        a.b1[ib], a.y1[ib], dt, q_in_kk, q_in_kkp1, q_out_kk, q_over, cu, ak);
-                    if (qo < 0.0) qo = 0.0;
-                    qo_kkp1[ib] = qo * nrc;
-                    int sq = 2 * a.seq[ib] + dir;
-                    if (cu > best_cu || (cu == best_cu && sq > best_seq)) { best_cu = cu; best_ak = ak; best_seq = sq; }
-                }
+            const int beg = lp[lv], end = lp[lv + 1];
+            const RouteCell cur = nxt;
+            const bool hc = have;
+            have = false;
+            if (lv + 1 < a.nlevel) {       // the next level's first cell of this thread: nothing here depends on this level's results
+                const int q = end + threadIdx.x;
+                have = q < lp[lv + 2];
+                if (have) route_load(a, q, nxt);
+            }
+            if (hc) route_cell(a, cur, dt, best_cu, best_ak, best_seq);
+            for (int q = beg + threadIdx.x + blockDim.x; q < end; q += blockDim.x) {
+                RouteCell t;
+                route_load(a, q, t);
+                route_cell(a, t, dt, best_cu, best_ak, best_seq);
             }
             __syncthreads();
         }
@@ -3505,7 +3549,7 @@ static int surf_flowtra(CathySim *S)
     a.h_water = S->h_water.p; a.ak_max = S->d_akmax.p; a.nsurf_out = S->d_nsurf.p; a.deltat = S->deltat; a.cellarea = S->p.dx * S->p.dy;
     a.ckf1 = S->r_ckf1.p; a.ckf2 = S->r_ckf2.p; a.dhd1 = S->r_dhd1.p; a.dhd2 = S->r_dhd2.p;
     if (!S->route_static_done) { LAUNCH(S, k_route_static, nblk(S->ncell, S->grid_n), RED_BLOCK, a); S->route_static_done = true; }
-    LAUNCH(S, k_route, 1, 1024, a);
+    LAUNCH(S, k_route, 1, ROUTE_BLOCK, a);
     LAUNCH(S, k_cell_nod, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nrow, S->ncol, S->h_water.p, S->pondnod.p);
     cudaMemsetAsync(S->d_flags.p, 0, sizeof(int), S->st);
     LAUNCH(S, k_pondupd, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, S->p.pondh_min, 1.0 / S->deltat, S->pondnod.p, S->arenod.p, S->atmpot.p,
