@@ -1569,6 +1569,7 @@ struct BicgArgs {
     unsigned int epoch0;
     IterOut *out;
     int prefetch;
+    int zigzag;              // 1: boustrophedon sweeps (Jacobian larger than the L2), see k_bicgstab
     int line;                // 1: vertical-line (one tridiagonal system per DEM column) preconditioner, 0: point Jacobi
     int nnod, nl;            // surface nodes (= columns) and node layers (rows of a column: s, s + nnod, ...)
     double *idn, *cp;        // Thomas factors of the column systems: 1 / pivot and the eliminated super-diagonal
@@ -1670,9 +1671,11 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab(BicgArgs a)
 {
     const bool PF = a.prefetch != 0;
     const bool LINE = a.line != 0;
+    const bool ZZ = a.zigzag != 0;
     __shared__ double sh[BLOCK / 32][5];
     unsigned int epoch = a.epoch0, flip = 0;
     const int n = a.n, stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int klast = t0 < n ? t0 + ((n - 1 - t0) / stride) * stride : -1;     // this thread's last row
     const double *__restrict__ di = a.dinv;
     double in[5] = {0, 0, 0, 0, 0}, out[5];
     // x0 = M^-1 b, xlung = ||b_free||^2
@@ -1710,6 +1713,15 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab(BicgArgs a)
         grid_reduce_n<BLOCK, 5>(a.counter, epoch, flip, in, a.partial, sh, out);
         const double alpha = rho / out[0];
         // ---- s = r - alpha v, sh = M^-1 s
+        // Boustrophedon sweeps (a.zigzag): the Jacobian of a large mesh (config 3: 197 MB) does not fit the 126 MB L2, so two
+        // product sweeps in the same direction re-read ALL of it from HBM.  This pass and the second product run from the last row
+        // back to the first: they start on the rows the first product touched last, which are still in the L2.
+        if (ZZ) for (int k = klast; k >= 0; k -= stride) {
+            double s = a.r[k] - alpha * a.v[k];
+            a.s[k] = s;
+            if (!LINE) a.sh[k] = s * di[k];
+        }
+        else
         for (int k = t0; k < n; k += stride) {
             double s = a.r[k] - alpha * a.v[k];
             a.s[k] = s;
@@ -1719,6 +1731,13 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab(BicgArgs a)
         if (LINE) { line_solve(a, a.s, a.sh, t0, stride); grid_barrier(a.counter, epoch); }
         // ---- t = J sh; (t,s), (t,t), (rt,s), (rt,t)
         in[0] = in[1] = in[2] = in[3] = in[4] = 0.0;
+        if (ZZ) for (int k = klast; k >= 0; k -= stride) {
+            if (PF && k - stride >= 0) bicg_prefetch_row(a.U, a.L, k - stride);
+            double t = di[k] != 0.0 ? dia_row_n(a.U, a.L, a.sh, k) : 0.0, s = a.s[k], rt = a.rt[k];
+            a.t[k] = t;
+            in[0] += t * s; in[1] += t * t; in[2] += rt * s; in[3] += rt * t;
+        }
+        else
         for (int k = t0; k < n; k += stride) {
             if (PF && k + stride < n) bicg_prefetch_row(a.U, a.L, k + stride);
             double t = di[k] != 0.0 ? dia_row_n(a.U, a.L, a.sh, k) : 0.0, s = a.s[k], rt = a.rt[k];
@@ -2677,6 +2696,8 @@ struct CathySim {
     int bicg_line = 0;               // Newton: 0 = point Jacobi (default), 1 = vertical-line preconditioner (opt-in, CATHY_BICG_LINE=1: -36 % iterations but
                                      // +46 % per iteration on the config-3 storm, no gain on unsaturated systems; profiles/r1_precond_experiment.md)
     DBuf<double> widn, wcp;          // its Thomas factors
+    bool l2_reset = true;
+    size_t l2_window = 0, l2_persist = 0;   // bytes of the Jacobian covered by the access-policy window / L2 set-aside for persisting lines
     DBuf<double> Ju, Jl, dinv, dckrw, detai, ts, s1, ws, wsh, wt;   // Newton: Jacobian diagonals, Jacobi scaling, derivative curves, element factors, BiCGSTAB vectors
     bool newton = false;
     // ---- row-block partition of one large mesh over several GPUs (BASELINE config 5) ----
@@ -3375,6 +3396,9 @@ static int assemble_system_newton(CathySim *S, double deltat)
 {
     const int n = S->n;
     Diag A = make_diag(S, S->A.p), Ju = make_diag(S, S->Ju.p), Jl = make_diag(S, S->Jl.p);
+    // the previous solve's persisting L2 lines go back to normal, so that the gathers below have the whole cache (the device is idle
+    // here: the host has just read the previous iteration's scalars)
+    if (S->l2_window && S->l2_reset) cudaCtxResetPersistingL2Cache();
     if (S->cm.ivghu != 0)
         LAUNCH(S, k_curves_newton_alt, nblk(n, S->grid_n), RED_BLOCK, n, S->cm, make_soil(S), S->ptnew.p, S->sw.p, S->ckrw.p, S->et1.p, S->dckrw.p, S->detai.p);
     else
@@ -3398,11 +3422,31 @@ static int solve_system_newton(CathySim *S)
     a.x = S->pdiff.p; a.r = S->wr.p; a.rt = S->wz.p; a.p = S->wp0.p; a.ph = S->wp1.p; a.v = S->wbv.p; a.s = S->ws.p; a.sh = S->wsh.p; a.t = S->wt.p;
     a.partial = S->partial.p; a.out = S->d_iter.p; a.counter = S->d_counter.p; a.epoch0 = S->barrier_epoch;
     a.prefetch = S->pcg_prefetch && (size_t)S->n * 240 > ((size_t)64 << 20);     // the Jacobian (2 x 15 diagonals) does not stay in L2
+    {   // CATHY_BICG_ZIGZAG=0/1 overrides; default: on when the Jacobian does not fit the L2
+        const char *e = getenv("CATHY_BICG_ZIGZAG");
+        a.zigzag = e ? atoi(e) != 0 : (size_t)S->n * 240 > ((size_t)100 << 20);
+    }
     a.line = S->bicg_line; a.nnod = S->nnod; a.nl = S->nstr + 1; a.idn = S->widn.p; a.cp = S->wcp.p;
     void *args[] = {&a};
+    // The Jacobian (15 diagonals, config 3: 102 MB) is read twice per iteration and would fit the 126 MB L2, but the nine work
+    // vectors streaming past it evict it every time.  An access-policy window marks its lines PERSISTING for this launch (as many
+    // as the device's set-aside holds: hitRatio = set-aside / window) so that the vectors stream through the rest of the cache.
+    cudaStreamAttrValue av = {};
+    if (S->l2_window) {
+        av.accessPolicyWindow.base_ptr = S->Ju.base;
+        av.accessPolicyWindow.num_bytes = S->l2_window;
+        av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)S->l2_persist / (double)S->l2_window);
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        CK(cudaStreamSetAttribute(S->st, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
     CK(cudaEventRecord(S->evp0, S->st));
     if (S->pcg_shared_gpu) { k_bicgstab<1024><<<S->grid_pcg, 1024, 0, S->st>>>(a); CK(cudaGetLastError()); }
     else CK(cudaLaunchCooperativeKernel((void *)k_bicgstab<1024>, dim3(S->sms), dim3(1024), args, 0, S->st));
+    if (S->l2_window) {
+        av.accessPolicyWindow.num_bytes = 0;
+        CK(cudaStreamSetAttribute(S->st, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
     CK(cudaEventRecord(S->evp1, S->st));
     S->launches++;
     return 0;
@@ -3848,7 +3892,31 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
     a |= S->krt.alloc(S->nt); a |= S->e1t.alloc(S->nt);
     a |= S->partial.alloc(10 * (size_t)std::max(S->grid_pcg, 1));
     if (S->newton) {
-        a |= S->Ju.alloc((size_t)NDIAG * S->ld, S->halo); a |= S->Jl.alloc((size_t)NDIAG * S->ld, S->halo);
+        // Ju and Jl share ONE allocation ([halo | 8 upper diagonals | halo][halo | 8 lower | halo]) so that one L2 access-policy
+        // window covers the whole Jacobian (see solve_system_newton); Jl is a non-owning view
+        a |= S->Ju.alloc((size_t)2 * NDIAG * S->ld + 2 * S->halo, S->halo);
+        S->Jl.release();
+        if (!a) { S->Jl.p = S->Ju.p + (size_t)NDIAG * S->ld + 2 * S->halo; S->Jl.n = (size_t)NDIAG * S->ld; S->Jl.pad = S->halo; }
+        {   // L2 persistence for the Jacobian during the BiCGSTAB solve: OPT-IN (CATHY_L2_PERSIST=1: the device's maximum set-aside,
+            // >1: that many MB).  Measured on B200 at config 3 (profiles/micro/r1i_l2_persist.log): the time per BiCGSTAB iteration does
+            // not move (91.7 -> 91.6 us with the maximum, 89.4 us with 64 MB), i.e. the solve is not bound by re-reading the Jacobian
+            // from HBM, while the set-aside slows every other kernel of the step (Newton workload 10.08 -> 11.85 ms/step).
+            S->l2_window = S->l2_persist = 0;
+            { const char *r = getenv("CATHY_L2_RESET"); S->l2_reset = !(r && atoi(r) == 0); }
+            const char *e = getenv("CATHY_L2_PERSIST");
+            const size_t jbytes = ((size_t)2 * NDIAG * S->ld + 4 * S->halo) * sizeof(double);
+            int dev = 0, maxp = 0, maxw = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
+            cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+            if (e && atoi(e) >= 1 && maxp > 0 && maxw > 0) {
+                const size_t want = e && atoi(e) > 1 ? (size_t)atoi(e) << 20 : (size_t)maxp;
+                const size_t persist = std::min(std::min((size_t)maxp, want), jbytes);
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess) {
+                    S->l2_window = std::min(jbytes, (size_t)maxw); S->l2_persist = persist;
+                } else cudaGetLastError();
+            }
+        }
         DBuf<double> *vv[] = {&S->dinv, &S->dckrw, &S->detai, &S->ws, &S->wsh, &S->wt, &S->widn, &S->wcp};
         for (auto *b : vv) a |= b->alloc(N, S->halo);
         a |= S->ts.alloc(4 * (size_t)S->nt); a |= S->s1.alloc(4 * (size_t)S->nt);

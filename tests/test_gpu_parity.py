@@ -425,6 +425,24 @@ def test_newton_full_run_same_steps_and_heads(gpu_lib, oracle_mod):
     assert ok, dmax
 
 
+def test_newton_boustrophedon_sweeps(gpu_lib, oracle_mod, monkeypatch):
+    """k_bicgstab with CATHY_BICG_ZIGZAG=1 (the second product and the s-update sweep from the last row to the first: default only
+    when the Jacobian is larger than the L2, i.e. never at test sizes): the inner products are summed in another order, the
+    runs must still follow the reference -- all 130 steps of the infiltration pulse and the first 150 of the coupled storm."""
+    from pycathy_wrapper_b200.project import load_project
+    monkeypatch.setenv("CATHY_BICG_ZIGZAG", "1")
+    prj = load_project(os.path.join(GOLDEN, "newton20"))
+    g, c, rg, rc = _run_both(gpu_lib, oracle_mod, prj)
+    assert rg.nstep == 130
+    ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
+    assert ok, dmax
+    prj = load_project(os.path.join(GOLDEN, "storm20n"))
+    g, c, rg, rc = _run_both(gpu_lib, oracle_mod, prj, nsteps=150, store_rtol=1e-8)
+    assert rg.nstep == 150 and g.state()["ifatm"].tolist() == c.state()["ifatm"].tolist()
+    ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
+    assert ok, dmax
+
+
 def test_newton_coupled_storm(gpu_lib, oracle_mod):
     """Newton + surface routing (BASELINE config 3 in small): the first step back-steps 9 times in the reference because its
     third linear solve fails -- the device must fail there too -- and the following accepted steps (ponding, routing
