@@ -595,6 +595,17 @@ def test_other_moisture_curves_under_newton(gpu_lib, oracle_mod, tmp_path, ivghu
     assert np.max(np.abs(g.state()["sw"] - c.state()["sw"])) < 1e-6
 
 
+def test_extended_van_genuchten_input_check(gpu_lib, tmp_path):
+    """IVGHU = 1 with a specific storage above the curve's steepest slope (here: positive VGPSAT): cathy_create fails with the
+    reference's CHPARM message instead of running on NaNs (SRC/chparm.f:48-52)."""
+    from pycathy_wrapper_b200.capi import CathyLibraryError, Simulation
+    from pycathy_wrapper_b200.project import load_project
+    from test_oracle_golden import _xvg_bad_project
+    prj = load_project(_xvg_bad_project(str(tmp_path / "p")))
+    with pytest.raises(CathyLibraryError, match="DMCMAX"):
+        Simulation(gpu_lib, prj)
+
+
 @pytest.mark.parametrize("ivert", [0, 1, 2])
 def test_soil_zones_and_ivert(gpu_lib, oracle_mod, tmp_path, ivert):
     """NZONE = 3 soil zones with per-(layer, zone) soils and IVERT = 0, 1, 2 (SRC/gen3d.f, SRC/tpnodi.f): same accepted steps and
