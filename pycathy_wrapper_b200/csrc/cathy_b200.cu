@@ -2163,6 +2163,7 @@ struct RouteArgs {
     const int *don_ptr;       // [ncell+1] donors of each cell in QOI order
     const int *don_cell;      // donor routing index
     const unsigned char *don_dir; // 0: donor's direction-1 outflow, 1: direction-2
+    const int *don_code;      // per donor entry: (index << 3) | (direction << 2) | kind, see k_route
     const double *w1, *w2, *sl1, *sl2, *epl1, *epl2, *ks1, *ks2, *ws1, *ws2, *b1, *y1, *nrc;
     double *sw_sn, *q_in_kk, *q_in_kkp1, *q_out_kk_1, *q_out_kk_2, *q_out_kkp1_1, *q_out_kkp1_2;
     double *volume_kk, *volume_kkp1, *h_water;
@@ -2214,10 +2215,15 @@ __global__ void k_route_static(RouteArgs a)
 // level_cell -> don_ptr -> don_cell -> donor outflow -> MC.  Everything in that chain that does not depend on the previous level
 // (indices, donor lists, the cell's parameters and old-time-level values) is loaded one level AHEAD, while the current level
 // computes: after the barrier only the donors' outflows remain to be fetched.
-constexpr int ROUTE_BLOCK = 512, ROUTE_RD = 4;
+// Donor kinds (don_code & 3): 0 = the donor sits at least two levels up: its outflow is final when the loads of the next level are
+// issued, so it is fetched ahead with everything else; 1 = the donor was computed in the level just finished by the thread whose
+// slot is the index: its outflow is read from the CTA's shared stash (a few cycles instead of an L2 round trip on the critical
+// path); 2 = previous level but beyond the stash (levels wider than the CTA): read from global memory after the barrier.
+constexpr int ROUTE_BLOCK = 384, ROUTE_RD = 4;
 struct RouteCell {
     int ib, d0, nd, seq;
-    int dc[ROUTE_RD];        // the first ROUTE_RD donors: routing index * 2 + direction
+    int dc[ROUTE_RD];        // don_code of the first ROUTE_RD donors
+    double dq[ROUTE_RD];     // outflows of the kind-0 donors among them
     double w[2], epl[2], ckf[2], dhd[2], qok[2], nrc, b1, y1, sw, qik;
 };
 __device__ __forceinline__ void route_load(const RouteArgs &a, int q, RouteCell &c)
@@ -2226,19 +2232,29 @@ __device__ __forceinline__ void route_load(const RouteArgs &a, int q, RouteCell 
     c.ib = ib; c.seq = a.seq[ib];
     c.d0 = a.don_ptr[ib]; c.nd = a.don_ptr[ib + 1] - c.d0;
 #pragma unroll
-    for (int j = 0; j < ROUTE_RD; ++j) c.dc[j] = j < c.nd ? a.don_cell[c.d0 + j] * 2 + a.don_dir[c.d0 + j] : 0;
+    for (int j = 0; j < ROUTE_RD; ++j) {
+        const int code = j < c.nd ? a.don_code[c.d0 + j] : 1;
+        c.dc[j] = code;
+        c.dq[j] = (code & 3) == 0 ? ((code & 4) ? a.q_out_kkp1_2[code >> 3] : a.q_out_kkp1_1[code >> 3]) : 0.0;
+    }
     c.w[0] = a.w1[ib]; c.w[1] = a.w2[ib]; c.epl[0] = a.epl1[ib]; c.epl[1] = a.epl2[ib];
     c.ckf[0] = a.ckf1[ib]; c.ckf[1] = a.ckf2[ib]; c.dhd[0] = a.dhd1[ib]; c.dhd[1] = a.dhd2[ib];
     c.qok[0] = a.q_out_kk_1[ib]; c.qok[1] = a.q_out_kk_2[ib];
     c.nrc = a.nrc[ib]; c.b1 = a.b1[ib]; c.y1 = a.y1[ib]; c.sw = a.sw_sn[ib]; c.qik = a.q_in_kk[ib];
 }
-__device__ __forceinline__ void route_cell(const RouteArgs &a, const RouteCell &c, double dt, double &best_cu, double &best_ak, int &best_seq)
+// prev: stash written by the previous level, mine: this level's stash, slot: this thread's stash slot or -1
+__device__ __forceinline__ void route_cell(const RouteArgs &a, const RouteCell &c, double dt, const double (*prev)[ROUTE_BLOCK],
+                                           double (*mine)[ROUTE_BLOCK], int slot, double &best_cu, double &best_ak, int &best_seq)
 {
     const int ib = c.ib;
     double qin = 0.0;
 #pragma unroll
     for (int j = 0; j < ROUTE_RD; ++j)
-        if (j < c.nd) qin = qin + ((c.dc[j] & 1) ? a.q_out_kkp1_2[c.dc[j] >> 1] : a.q_out_kkp1_1[c.dc[j] >> 1]);
+        if (j < c.nd) {
+            const int code = c.dc[j], kind = code & 3, idx = code >> 3, dr = (code >> 2) & 1;
+            const double v = kind == 0 ? c.dq[j] : kind == 1 ? prev[dr][idx] : (dr ? a.q_out_kkp1_2[idx] : a.q_out_kkp1_1[idx]);
+            qin = qin + v;
+        }
     for (int dn = c.d0 + ROUTE_RD; dn < c.d0 + c.nd; ++dn)
         qin = qin + (a.don_dir[dn] ? a.q_out_kkp1_2[a.don_cell[dn]] : a.q_out_kkp1_1[a.don_cell[dn]]);
     a.q_in_kkp1[ib] = qin;
@@ -2255,6 +2271,7 @@ __device__ __forceinline__ void route_cell(const RouteArgs &a, const RouteCell &
         double qo = mc_cell(c.ckf[dir], c.dhd[dir], epl, c.b1, c.y1, dt, q_in_kk, q_in_kkp1, q_out_kk, q_over, cu, ak);
         if (qo < 0.0) qo = 0.0;
         qo_kkp1[ib] = qo * nrc;
+        if (slot >= 0) mine[dir][slot] = qo * nrc;
         int sq = 2 * c.seq + dir;
         if (cu > best_cu || (cu == best_cu && sq > best_seq)) { best_cu = cu; best_ak = ak; best_seq = sq; }
     }
@@ -2266,6 +2283,7 @@ __global__ void __launch_bounds__(ROUTE_BLOCK) k_route(RouteArgs a)
     __shared__ double s_akmax;
     __shared__ int s_nsurf;
     __shared__ double s_dt;
+    __shared__ double s_q[2][2][ROUTE_BLOCK];      // [level parity][direction][slot]: outflows of the level's first ROUTE_BLOCK cells
     if (threadIdx.x == 0) {
         double akm = *a.ak_max, cu_max = akm * a.deltat, dts;
         int ns;
@@ -2293,11 +2311,11 @@ __global__ void __launch_bounds__(ROUTE_BLOCK) k_route(RouteArgs a)
                 have = q < lp[lv + 2];
                 if (have) route_load(a, q, nxt);
             }
-            if (hc) route_cell(a, cur, dt, best_cu, best_ak, best_seq);
+            if (hc) route_cell(a, cur, dt, s_q[(lv + 1) & 1], s_q[lv & 1], (int)threadIdx.x, best_cu, best_ak, best_seq);
             for (int q = beg + threadIdx.x + blockDim.x; q < end; q += blockDim.x) {
                 RouteCell t;
                 route_load(a, q, t);
-                route_cell(a, t, dt, best_cu, best_ak, best_seq);
+                route_cell(a, t, dt, s_q[(lv + 1) & 1], s_q[lv & 1], -1, best_cu, best_ak, best_seq);
             }
             __syncthreads();
         }
@@ -2722,7 +2740,7 @@ struct CathySim {
     int atmrec[3] = {-1, -1, -1};
     int atm_next = 0, htiatm = 0;
     // surface routing
-    DBuf<int> lv_ptr, lv_cell, seqpos, don_ptr, don_cell;
+    DBuf<int> lv_ptr, lv_cell, seqpos, don_ptr, don_cell, don_code;
     DBuf<unsigned char> don_dir;
     DBuf<double> r_w1, r_w2, r_sl1, r_sl2, r_epl1, r_epl2, r_ks1, r_ks2, r_ws1, r_ws2, r_b1, r_y1, r_nrc, r_ckf1, r_ckf2, r_dhd1, r_dhd2;
     bool route_static_done = false;
@@ -3116,8 +3134,22 @@ static int build_surface(CathySim *S)
         dptr[c + 1] = dptr[c] + (int)don[c].size();
         for (auto &pr : don[c]) { dcell.push_back(pr.first); ddir.push_back((unsigned char)pr.second); }
     }
+    std::vector<int> dcode(dcell.size());
+    {
+        std::vector<int> slot(nc);
+        for (int l = 0; l < nlev; ++l) for (int q = lptr[l]; q < lptr[l + 1]; ++q) slot[lcell[q]] = q - lptr[l];
+        if ((long long)nc >= (1LL << 28)) FAIL(-2, "surface routing: more than 2^28 cells");
+        for (int c = 0; c < nc; ++c)
+            for (int dn = dptr[c]; dn < dptr[c + 1]; ++dn) {
+                const int dc = dcell[dn], dr = ddir[dn];
+                if (level[dc] < level[c] - 1) dcode[dn] = (dc << 3) | (dr << 2) | 0;
+                else if (slot[dc] < ROUTE_BLOCK) dcode[dn] = (slot[dc] << 3) | (dr << 2) | 1;
+                else dcode[dn] = (dc << 3) | (dr << 2) | 2;
+            }
+    }
     S->nlevel = nlev; S->outlet_cell = qoi[nc - 1];
     int rc = 0;
+    rc |= S->don_code.upload(dcode);
     rc |= S->lv_ptr.upload(lptr); rc |= S->lv_cell.upload(lcell); rc |= S->seqpos.upload(seq); rc |= S->don_ptr.upload(dptr);
     rc |= S->don_cell.upload(dcell); rc |= S->don_dir.upload(ddir);
     rc |= S->r_w1.upload(w1); rc |= S->r_w2.upload(w2);
@@ -3585,7 +3617,7 @@ static int surf_flowtra(CathySim *S)
     LAUNCH(S, k_nod_cell, nblk(S->ncell, S->grid_n), RED_BLOCK, S->nrow, S->ncol, S->p.dx, S->p.dy, S->ovflnod.p, S->sw_sn.p);
     RouteArgs a;
     a.ncell = S->ncell; a.nlevel = S->nlevel; a.level_ptr = S->lv_ptr.p; a.level_cell = S->lv_cell.p; a.seq = S->seqpos.p;
-    a.don_ptr = S->don_ptr.p; a.don_cell = S->don_cell.p; a.don_dir = S->don_dir.p;
+    a.don_ptr = S->don_ptr.p; a.don_cell = S->don_cell.p; a.don_dir = S->don_dir.p; a.don_code = S->don_code.p;
     a.w1 = S->r_w1.p; a.w2 = S->r_w2.p; a.sl1 = S->r_sl1.p; a.sl2 = S->r_sl2.p; a.epl1 = S->r_epl1.p; a.epl2 = S->r_epl2.p;
     a.ks1 = S->r_ks1.p; a.ks2 = S->r_ks2.p; a.ws1 = S->r_ws1.p; a.ws2 = S->r_ws2.p; a.b1 = S->r_b1.p; a.y1 = S->r_y1.p; a.nrc = S->r_nrc.p;
     a.sw_sn = S->sw_sn.p; a.q_in_kk = S->q_in_kk.p; a.q_in_kkp1 = S->q_in_kkp1.p; a.q_out_kk_1 = S->q_out_kk_1.p; a.q_out_kk_2 = S->q_out_kk_2.p;
@@ -3663,7 +3695,7 @@ void cathy_destroy(CathySim *S)
                           &S->volume_kk_sav, &S->q_in_kk_p, &S->q_out_kk_1_p, &S->q_out_kk_2_p, &S->volume_kk_p, &S->d_akmax};
     for (auto *b : dd) b->release();
     DBuf<int> *di[] = {&S->veg, &S->ell_tet, &S->ifatm, &S->ifatmp, &S->d_flags, &S->lv_ptr, &S->lv_cell,
-                       &S->seqpos, &S->don_ptr, &S->don_cell, &S->d_nsurf};
+                       &S->seqpos, &S->don_ptr, &S->don_cell, &S->don_code, &S->d_nsurf};
     for (auto *b : di) b->release();
     { DBuf<double> *nn[] = {&S->widn, &S->wcp, &S->Ju, &S->Jl, &S->dinv, &S->dckrw, &S->detai, &S->ts, &S->s1, &S->ws, &S->wsh, &S->wt, &S->tet_k0, &S->tet_gz, &S->tet_vol, &S->vgm52, &S->vgmm1};
       for (auto *b : nn) b->release(); S->ell_loc.release(); }
