@@ -128,9 +128,38 @@ def vtk():
             fo.write(fi.read())
 
 
+def mid82k_project(path):
+    """100 x 50 DEM x 15 layers = 82,416 nodes, 450,000 tets: the largest mesh a shipped reference ELF holds
+    (examplesTmp/SSHydro/ERA5_ETp_spatially_from_weill/cathy).  Infiltration pulse on the synthetic
+    hillslope with a water table 1 m deep -- the bench workload of BASELINE config 2 at a tenth of its size."""
+    return synthetic.make_project(path, 100, 50, 15, ic=("wt", 1.0), ISIMGR=1, TMAX=300.0, TIMPRT=[150.0, 300.0], DELTAT=1.0, DTMIN=1e-2,
+                                  DTMAX=100.0, NODVP=[5], atmbc=[(0.0, 0.0), (60.0, 2.0e-5), (1.0e9, 2.0e-5)])
+
+
+def mid82k():
+    """Outputs of the reference ELF on the 82,416-node project (about 90 s of CPU): mbeconv, vp verbatim, psi/sw as .npz.
+    The inputs are NOT stored: tests regenerate them with mid82k_project (deterministic generator)."""
+    tmp = "/tmp/golden_mid82k"
+    shutil.rmtree(tmp, ignore_errors=True)
+    shutil.rmtree(tmp + "_ref", ignore_errors=True)
+    mid82k_project(tmp)
+    oracle.run_reference(tmp, tmp + "_ref", "100x50x15", timeout=3600)
+    dst = os.path.join(HERE, "mid82k", "golden")
+    os.makedirs(dst, exist_ok=True)
+    out = os.path.join(tmp + "_ref", "output")
+    for f in ("mbeconv", "vp"):
+        shutil.copy(os.path.join(out, f), os.path.join(dst, f))
+        os.chmod(os.path.join(dst, f), 0o644)
+    for f in ("psi", "sw"):
+        s, t, b = read_blocks(os.path.join(out, f))
+        np.savez_compressed(os.path.join(dst, f + ".npz"), nstep=s, time=t, values=b)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "newton":
         newton()
+    elif len(sys.argv) > 1 and sys.argv[1] == "mid82k":
+        mid82k()
     elif len(sys.argv) > 1 and sys.argv[1] == "vtk":
         vtk()
     else:

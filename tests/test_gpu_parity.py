@@ -161,6 +161,63 @@ def test_config2_full_size_properties(gpu_lib, monkeypatch):
     assert ok, dmax
 
 
+def _bench_module():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    return bench
+
+
+def test_config2_full_size_first_steps_match_oracle(gpu_lib, oracle_mod):
+    """BASELINE config 2 at the size the headline number is quoted on (200 x 200 DEM x 20 layers, 848,421 nodes; bench.py's own
+    workload): the first 6 accepted steps of the device against the CPU oracle (about 3 s of CPU per step) -- same
+    (nstep, Picard iterations, back-steps, dt) sequence, storage, and heads inside the 1e-6 relative / 1e-8 m band.
+    Here every one of the 148 persistent CTAs of k_pcg_res2 owns ~5.7 k rows."""
+    prj = _bench_module().make_workload((200, 200, 20))
+    g, c, rg, rc = _run_both(gpu_lib, oracle_mod, prj, nsteps=6)
+    assert g.solver_info()["kernel"] == 4 and rg.nstep == 6
+    sg, sc = g.state(), c.state()
+    ok, dmax = psi_close(sg["psi"], sc["psi"])
+    assert ok, dmax
+    assert np.max(np.abs(sg["sw"] - sc["sw"])) < 1e-6
+    assert np.array_equal(sg["ifatm"], sc["ifatm"])
+
+
+def test_config3_full_size_first_steps_match_oracle(gpu_lib, oracle_mod):
+    """BASELINE config 3 at full size (same mesh, Newton + BiCGSTAB, surface routing from the first step; bench.py's `coupled`
+    workload): first 3 accepted steps against the oracle's ILU(0)-BiCGSTAB (about 20 s of CPU per step) -- same step sequence,
+    Newton iteration counts, routing sub-steps, heads inside the band, outlet discharge to 1e-6."""
+    prj = _bench_module().make_workload((200, 200, 20), iopt=2, routing=True)
+    g, c, rg, rc = _run_both(gpu_lib, oracle_mod, prj, nsteps=3, store_rtol=1e-8)
+    assert rg.nsurf > 0
+    sg, sc = g.state(), c.state()
+    ok, dmax = psi_close(sg["psi"], sc["psi"])
+    assert ok, dmax
+    assert np.array_equal(sg["ifatm"], sc["ifatm"])
+    assert abs(rg.q_outlet_1 - rc.q_outlet_1) <= 1e-6 * max(abs(rc.q_outlet_1), 1e-12)
+
+
+def test_mid_size_82k_full_run_matches_oracle_and_reference_elf(gpu_lib, oracle_mod, tmp_path):
+    """The largest mesh a shipped reference ELF holds (100 x 50 DEM x 15 layers, 82,416 nodes): whole run on the device against
+    the oracle step by step, and the final heads against the ELF's own psi output (tests/golden/mid82k, produced by
+    make_golden.py mid82k; the oracle is byte-identical to it: test_oracle_golden.py::test_oracle_82k_mesh_reproduces_reference_elf)."""
+    import importlib.util
+    from pycathy_wrapper_b200.project import load_project
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    prj = load_project(mg.mid82k_project(str(tmp_path / "p")))
+    g, c, rg, rc = _run_both(gpu_lib, oracle_mod, prj)
+    gold = np.loadtxt(os.path.join(GOLDEN, "mid82k", "golden", "mbeconv"), skiprows=3, usecols=range(4))
+    assert rg.nstep == int(gold[-1, 0]) and g.n == 82416
+    sg, sc = g.state(), c.state()
+    ok, dmax = psi_close(sg["psi"], sc["psi"])
+    assert ok, dmax
+    psi_ref = np.load(os.path.join(GOLDEN, "mid82k", "golden", "psi.npz"))["values"][-1]
+    ok, dmax = psi_close(sg["psi"], psi_ref, rtol=2e-6, atol=1e-7)        # the ELF's file carries 7 significant digits
+    assert ok, dmax
+
+
 @pytest.mark.parametrize("case", ["weill", (6, 7, 4), (7, 6, 5), (2, 2, 1), (3, 9, 2), "zones"])
 def test_assembly_with_derived_tet_indices_equals_stored_lists(gpu_lib, weill, tmp_path, monkeypatch, case):
     """k_assemble_a (tet indices = base(k) + per-class offset, the tables verified entry by entry at cathy_create) sums the same
