@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CATHY_ABI_VERSION 4
+#define CATHY_ABI_VERSION 5
 #define CATHY_MAXIT 64 /* upper bound on ITUNS kept in a step report (CATHY.H MAXIT=30) */
 
 /* Everything DATIN / INITAL read from the project files (SRC/datin.f:80-514,
@@ -97,6 +97,11 @@ typedef struct CathyProblem {
     /* --- moisture-curve parameters of the Huyakorn (IVGHU = 2, 3) and Brooks-Corey (IVGHU = 4) models, read from the header
      * of input/soil (SRC/datin.f:440-458; constants derived in SRC/chparm.f:79-106) */
     double hualfa, hubeta, hugama, hupsia, huswr, hun, hua, hub, bcbeta, bcrmc, bcpsat;
+    /* --- stopping rule of the device linear solvers (SYMSLV / NSYSLV, SRC/solscal-extended.f:4669-4699, :3063-3240): the
+     * solvers run at most ITMXCG x itmxcg_scale iterations to a relative residual of TOLCG x tolcg_scale (above).
+     * <= 0 selects the documented default: itmxcg_scale 20; tolcg_scale 1 (Picard) / 1e-3 (Newton).  The effective
+     * values are returned by cathy_solver_limits and printed in the header of output/iter. */
+    double itmxcg_scale;
 } CathyProblem;
 
 /* One nonlinear iteration line of output/iter (SRC/conver.f:44 FORMAT 1070). */
@@ -204,6 +209,11 @@ int32_t cathy_dd_info(const CathySim *sim, int64_t info[8]);
  * info[0] = 1 k_pcg (CG vectors streamed), 2 k_pcg2, 3 k_pcg_res / 4 k_pcg_res2 (CG vectors resident in shared memory), 10 k_bicgstab (Newton);
  * info[1] = rows per CTA (k_pcg_res), info[2] = 1 if the solution vector is resident too, info[3] = CTAs of the solver grid. */
 int32_t cathy_solver_info(const CathySim *sim, int64_t info[4]);
+/* Effective stopping rule of this handle's linear solver: lim[0] = iteration limit (ITMXCG x itmxcg_scale), lim[1] = relative
+ * residual tolerance (TOLCG x tolcg_scale), lim[2] = itmxcg_scale, lim[3] = tolcg_scale as applied, lim[4] = preconditioner
+ * (1 diagonal, 2 vertical line).  The reference's ISOLV preconditioners IC(0) / ILU(0) (SRC/solscal-extended.f:2142-2267) are sequential
+ * sweeps; the device uses parallel ones and therefore other iteration counts -- LSFAIL keeps its meaning. */
+int32_t cathy_solver_limits(const CathySim *sim, double lim[5]);
 /* How the assembly (ASSPIC, SRC/asspic.f:26-51) finds the elements of a matrix entry: info[0] = 1 when the tet indices of the gather
  * plan are derived from the mesh structure (verified against the stored lists at cathy_create), 0 when they are read from memory;
  * info[1] = width of the per-class offset tables. */

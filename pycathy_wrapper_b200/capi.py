@@ -12,7 +12,7 @@ import numpy as np
 
 from .project import CathyProject
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAXIT = 64
 _D = C.POINTER(C.c_double)
 _I = C.POINTER(C.c_int32)
@@ -61,6 +61,7 @@ class CathyProblem(C.Structure):
         ("dd_world", C.c_int32), ("dd_rank", C.c_int32), ("dd_row0", C.c_int32), ("dd_row1", C.c_int32),
         ("hualfa", C.c_double), ("hubeta", C.c_double), ("hugama", C.c_double), ("hupsia", C.c_double), ("huswr", C.c_double),
         ("hun", C.c_double), ("hua", C.c_double), ("hub", C.c_double), ("bcbeta", C.c_double), ("bcrmc", C.c_double), ("bcpsat", C.c_double),
+        ("itmxcg_scale", C.c_double),
     ]
 
 
@@ -104,7 +105,7 @@ class ProblemHolder:
     """Owns the numpy buffers a CathyProblem points to (they must outlive the create call)."""
 
     def __init__(self, prj: CathyProject, precond: int = 0, device: int = 0, tolcg_scale: float = 0.0,
-                 dd: tuple | None = None, **overrides):
+                 dd: tuple | None = None, itmxcg_scale: float = 0.0, **overrides):
         p = dict(prj.parm)
         p.update({k.upper(): v for k, v in overrides.items()})
         self.parm = p
@@ -169,7 +170,7 @@ class ProblemHolder:
                 setattr(s, cname, fd(S[key]))
         elif int(p["ISIMGR"]) == 2:
             raise ValueError("ISIMGR=2 needs the prepro rasters")
-        s.precond, s.device, s.tolcg_scale = precond, device, tolcg_scale
+        s.precond, s.device, s.tolcg_scale, s.itmxcg_scale = precond, device, tolcg_scale, itmxcg_scale
         if dd is not None:      # (world, rank, row0, row1): row-block partition, see partition_rows()
             s.dd_world, s.dd_rank, s.dd_row0, s.dd_row1 = (int(v) for v in dd)
         else:
@@ -188,7 +189,7 @@ class CathyLib:
                "initial_storage", "step", "get_state", "get_velocity", "get_recharge", "get_wtdepth", "set_psi", "upload_atm_record", "debug_assemble", "debug_spmv", "debug_solve"]
 
     # entry points only the product library has (in-process ensemble support); bound when present
-    PRODUCT_ONLY = ["pack_state", "unpack_psi", "restart", "set_soil", "set_atm_table", "dd_export", "dd_connect", "dd_connect_local", "dd_start", "dd_info", "solver_info", "plan_info", "get_state_async", "state_wait"]
+    PRODUCT_ONLY = ["pack_state", "unpack_psi", "restart", "set_soil", "set_atm_table", "dd_export", "dd_connect", "dd_connect_local", "dd_start", "dd_info", "solver_info", "solver_limits", "plan_info", "get_state_async", "state_wait"]
 
     def __init__(self, path: str, prefix: str):
         if not os.path.exists(path):
@@ -222,6 +223,7 @@ class CathyLib:
             f["dd_info"].argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
             f["solver_info"].argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
             f["plan_info"].argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+            f["solver_limits"].argtypes = [C.c_void_p, _D]
             f["dd_connect_local"].argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
             f["dd_start"].argtypes = [C.c_void_p]
             f["get_state_async"].argtypes = [C.c_void_p, _D, _D, _D, _D, _D, _D, _D, _D, _I]
@@ -425,6 +427,16 @@ class Simulation:
         v = (C.c_int64 * 4)()
         self._ck(self.lib.f["solver_info"](self.h, v), "solver_info")
         return dict(zip(["kernel", "rows_per_cta", "x_resident", "grid"], (int(x) for x in v)))
+
+    def solver_limits(self) -> dict | None:
+        """Effective stopping rule of the linear solver: ITMXCG x itmxcg_scale iterations, TOLCG x tolcg_scale relative residual
+        (None for the CPU oracle, which runs the reference's own rule)."""
+        if "solver_limits" not in self.lib.f:
+            return None
+        v = (C.c_double * 5)()
+        self._ck(self.lib.f["solver_limits"](self.h, v), "solver_limits")
+        return {"itmax": int(v[0]), "tol": float(v[1]), "itmxcg_scale": float(v[2]), "tolcg_scale": float(v[3]),
+                "preconditioner": {1: "diagonal", 2: "vertical line"}.get(int(v[4]), "?")}
 
     def plan_info(self) -> dict:
         """Assembly plan of this handle: analytic = tet indices derived from the mesh structure instead of stored."""

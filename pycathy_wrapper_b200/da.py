@@ -306,8 +306,8 @@ class GpuOps:
 
     def update(self, X, P, L, B_local, mean, bbar, inflate, n_infl, inflate2):
         t = self.torch
-        dB = t.from_numpy(_f64(B_local)).to(X.device)
-        dbb = t.from_numpy(_f64(bbar)).to(X.device)
+        dB = B_local if isinstance(B_local, t.Tensor) else t.from_numpy(_f64(B_local)).to(X.device)
+        dbb = bbar if isinstance(bbar, t.Tensor) else t.from_numpy(_f64(bbar)).to(X.device)
         n_loc = L.shape[0] if L is not None else 0
         self.lib.check(self.lib.f["enkf_update"](X.data_ptr(), P.data_ptr(), L.data_ptr() if L is not None else None, n_loc, dB.data_ptr(),
                                                  mean.data_ptr(), dbb.data_ptr(), float(inflate), n_infl, float(inflate2), X.shape[0],
@@ -349,15 +349,37 @@ def sharded_enkf_update(X_local, HX_local, y, R, sakov=False, L=None, inflate=1.
     c0 = sum(counts[:rank])
     S_all, B_all = ops.gain(HX_all.cpu().numpy(), y, R, sakov)
     bbar = B_all.mean(axis=1)
+    # CUDA events around the two dense kernels and the collectives (torch's current stream is the one they are launched on)
+    cuda = X_local.is_cuda
+
+    class _NoEvent:
+        def record(self):
+            pass
+
+    ev = [torch.cuda.Event(enable_timing=True) if cuda else _NoEvent() for _ in range(6)]
+    ev[0].record()
     rs = ops.rowsum(X_local)
     if multi:
         dist.all_reduce(rs, group=group)
     mean = rs * (1.0 / ne_total)
+    ev[1].record()
     P = ops.crosscov(X_local, mean, S_all[:, c0:c0 + ne_local], ne_total)
+    ev[2].record()
     if multi:
         dist.all_reduce(P, group=group)
-    ops.update(X_local, P, L, B_all[:, c0:c0 + ne_local], mean, bbar, inflate, n_infl, inflate2)
-    return X_local, {"ne_total": ne_total, "col0": c0, "B": B_all, "S": S_all, "P": P, "mean": mean}
+    ev[3].record()
+    B_loc, bb = B_all[:, c0:c0 + ne_local], bbar
+    if cuda:      # staged before the timed kernel
+        B_loc, bb = torch.from_numpy(_f64(B_loc)).to(X_local.device), torch.from_numpy(_f64(bbar)).to(X_local.device)
+    ev[4].record()
+    ops.update(X_local, P, L, B_loc, mean, bb, inflate, n_infl, inflate2)
+    ev[5].record()
+    timing = {}
+    if cuda:
+        torch.cuda.current_stream().synchronize()
+        timing = {"rowsum_mean_ms": ev[0].elapsed_time(ev[1]), "crosscov_ms": ev[1].elapsed_time(ev[2]), "collective_ms": ev[2].elapsed_time(ev[3]),
+                  "update_ms": ev[4].elapsed_time(ev[5])}
+    return X_local, {"ne_total": ne_total, "col0": c0, "B": B_all, "S": S_all, "P": P, "mean": mean, "timing_ms": timing}
 
 
 # ------------------------------------------------------------------------------------------------

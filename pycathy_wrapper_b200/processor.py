@@ -35,6 +35,7 @@ class RunResult:
         self.n = 0
         self.finished_ok = True
         self.final_state = None
+        self.solver_limits = None  # effective (itmax, tol) of the device linear solver, also written to output/risul
 
 
 def _out(prj: CathyProject, unit: str) -> str:
@@ -54,7 +55,7 @@ def run_processor(project_dir: str, lib: CathyLib | None = None, write_files: bo
         lib = load_library()                       # raises if the CUDA library is missing: no CPU path
     if prj is None:
         prj = load_project(project_dir)
-    sim_kw = {k: overrides.pop(k) for k in ("precond", "device", "tolcg_scale") if k in overrides}
+    sim_kw = {k: overrides.pop(k) for k in ("precond", "device", "tolcg_scale", "itmxcg_scale") if k in overrides}
     sim = Simulation(lib, prj, **sim_kw, **overrides)
     parm = sim.parm
     res = RunResult()
@@ -70,6 +71,15 @@ def run_processor(project_dir: str, lib: CathyLib | None = None, write_files: bo
                 fh.write("\n\n IPRT1=3: Program terminating after output of X, Y, Z coordinate values\n")
         sim.close()
         return res
+
+    lim = sim.solver_limits()
+    if write_files and lim is not None:
+        # the stopping rule the device solver really applies (ITMXCG x itmxcg_scale, TOLCG x tolcg_scale; include/cathy_b200.h) goes on
+        # record in the run log, next to the parm values the user wrote
+        with open(_out(prj, "IOUT2"), "w") as fh_r:
+            fh_r.write(" cathy-b200 linear solver: %s preconditioner, ITMXCG = %d (parm %d x %g), TOLCG = %.3E (parm %.3E x %g)\n"
+                       % (lim["preconditioner"], lim["itmax"], parm["ITMXCG"], lim["itmxcg_scale"], lim["tol"], parm["TOLCG"], lim["tolcg_scale"]))
+    res.solver_limits = lim
 
     if getattr(prj, "transport_skipped", False):
         note = (" TRAFLAG=1: cathy-b200 runs the FLOW problem of this project only; the solute-transport add-on (one-way coupled, "
