@@ -18,23 +18,27 @@
 //   P2  s = r - alpha v             sh = M^-1 s (Thomas, shared memory)              -> grid barrier
 //   P3  t = J sh                    (t,s) (t,t) (rt,s) (rt,t)                        -> grid reduction
 //   P4  x += alpha ph + omega sh    r = s - omega t, ||r||^2, p = r + beta (p - omega v), ph = M^-1 p   -> grid reduction
-// r/s, p, v, t live in shared memory for the whole solve; only ph and sh (which the neighbours' stencils need), the shadow residual
-// rt and x go through L2.  Global bytes per row and iteration: 2 x 15 diagonals + ~64 B of vectors and line factors ~ 304 B
-// (k_bicgstab: 448 B).  Dirichlet rows carry dinv = 0: all Krylov vectors stay exactly zero there.
+// r/s, v and a work vector (t between P3 and P4, the Thomas input / output otherwise) live in shared memory for the whole solve, and so
+// do the line factors (fp32); ph and sh (which the neighbours' stencils need), the shadow residual rt, x and p (touched in P4 only) go
+// through L2.  Global bytes per row and iteration: 2 x 15 diagonals + 2 x (vector window ~8 + rt 8) + sh, ph written (16) +
+// P4: x, p read + written, ph, sh read (48) ~ 336 B (k_bicgstab: 448 B + two global line sweeps).  Dirichlet rows carry dinv = 0:
+// all Krylov vectors stay exactly zero there.
 
 struct BresArgs {
     int n, itmax;
     double tol;
     Diag U, L;                      // permuted Jacobian: U.d[0..7] = J(k, k + off), L.d[1..7][k] = J(k + off, k); off = permuted offsets
     const double *rhs, *dinv;       // permuted
-    double *x, *ph, *sh, *rt;       // permuted global vectors (ph, sh, x carry zero halos)
-    double *fidn, *fcp, *flo;       // line factors, per CTA transposed: [cta][layer][column of the CTA]
+    double *x, *ph, *sh, *rt, *p;   // permuted global vectors (ph, sh, x carry zero halos)
     double *partial;                // [2][5][gridDim.x]
     unsigned int *counter;
     unsigned int epoch0;
     IterOut *out;
     int rows_cta, nl, cols_cta;     // rows per CTA (= cols_cta * nl, even), node layers, columns per CTA
     int zigzag;
+    unsigned long long *prof;       // diagnostic (CATHY_BRES_PROF=1): ns spent by CTA 0 in each phase, accumulated over all solves
+    int prefetch;                   // 1: L2 prefetch of the matrix streams of the thread's next pass
+    int point;                      // 1: point Jacobi instead of the line blocks (diagnostic, CATHY_BRES_POINT=1)
 };
 
 // NV sums at once (NV <= 5): the scheme of grid_reduce2 -- block partials, ONE thread arrives and spins (alone in its warp: no lane
@@ -114,6 +118,14 @@ __device__ __forceinline__ void pair_group_n(const Diag &U, const Diag &Lw, cons
     a0 += la0 * m1;   a1 += la1 * m2;
     a0 += lb0 * m0;   a1 += lb1 * m1;
 }
+// the matrix streams of rows kn, kn+1 (the pair this thread handles in its NEXT pass) are pulled into L2 while the current pass runs
+__device__ __forceinline__ void prefetch_pair_n(const Diag &U, const Diag &Lw, int kn)
+{
+#pragma unroll
+    for (int d = 0; d < NDIAG; ++d) l2_prefetch(U.d[d] + kn);
+#pragma unroll
+    for (int d = 1; d < NDIAG; ++d) l2_prefetch(Lw.d[d] + kn - U.off[d]);
+}
 // rows k (even) and k+1 of J x
 template <int PAR>
 __device__ __forceinline__ void row_pair_n(const Diag &U, const Diag &Lw, const double *x, int k, bool elo, bool ehi, int o2, int o4, int o6, double &a0, double &a1)
@@ -134,43 +146,58 @@ __device__ __forceinline__ void row_pair_n(const Diag &U, const Diag &Lw, const 
     pair_group_n<(PAR & 4) != 0>(U, Lw, x, 6, o6, k, elo, ehi, a0, a1);
 }
 
-// out = M^-1 in for the columns of this CTA: forward sweep into tmp, backward sweep in place, both in shared memory; the caller
-// copies tmp out after a __syncthreads.  One thread per column; the factors are read coalesced ([layer][column]).
-__device__ __forceinline__ void line_apply_smem(const BresArgs &a, const double *in, double *tmp, int ncol)
+// v <- M^-1 v IN PLACE for the columns of this CTA, everything in shared memory: forward and backward Thomas sweep, one thread per
+// column.  The factors (reciprocal pivot, sub-diagonal, eliminated super-diagonal) are kept as fp32 (a preconditioner only has to be
+// a fixed linear operator), [column][layer] with an odd stride LP so that the lanes of a warp hit different banks.
+__device__ __forceinline__ void line_apply_inplace(const BresArgs &a, double *v, const float *fi, const float *fl, const float *fc, int ncol, int LP)
 {
-    const int L = a.nl, C = a.cols_cta;
-    const double *fi = a.fidn + (size_t)blockIdx.x * a.rows_cta, *fc = a.fcp + (size_t)blockIdx.x * a.rows_cta, *fl = a.flo + (size_t)blockIdx.x * a.rows_cta;
+    const int L = a.nl;
+    if (a.point) {
+        for (int i = threadIdx.x; i < ncol * L; i += blockDim.x) v[i] *= a.dinv[blockIdx.x * a.rows_cta + i];
+        return;
+    }
     for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
-        const int b = c * L;
-        double y = in[b] * fi[c];
-        tmp[b] = y;
+        const int b = c * L, f = c * LP;
+        double y = v[b] * (double)fi[f];
+        v[b] = y;
 #pragma unroll 4
         for (int l = 1; l < L; ++l) {
-            y = (in[b + l] - fl[(l - 1) * C + c] * y) * fi[l * C + c];
-            tmp[b + l] = y;
+            y = (v[b + l] - (double)fl[f + l - 1] * y) * (double)fi[f + l];
+            v[b + l] = y;
         }
 #pragma unroll 4
         for (int l = L - 2; l >= 0; --l) {
-            y = tmp[b + l] - fc[l * C + c] * y;
-            tmp[b + l] = y;
+            y = v[b + l] - (double)fc[f + l] * y;
+            v[b + l] = y;
         }
     }
 }
 
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define BRES_TICK(slot)                                                                         \
+    do {                                                                                        \
+        if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) { const unsigned long long t_ = gtime(); a.prof[slot] += t_ - tprof; tprof = t_; } \
+    } while (0)
+
 template <int BLOCK, int PAR>     // PAR: parities of the permuted offsets off[2], off[4], off[6] (bits 0, 1, 2)
 __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab_res(BresArgs a)
 {
+    unsigned long long tprof = a.prof ? gtime() : 0ull;
     extern __shared__ __align__(16) double smv[];
     __shared__ double sh[BLOCK / 32][5];
     __shared__ double res[2][5];
     unsigned int epoch = a.epoch0, par = 0;
     const int R = a.rows_cta, row0 = blockIdx.x * R, cnt = max(0, min(R, a.n - row0)), tid = threadIdx.x, lane = tid & 31;
-    const int ncol = cnt / a.nl;
-    double *rs = smv, *ps = smv + R, *vs = smv + 2 * (size_t)R, *ts = smv + 3 * (size_t)R;
+    const int ncol = cnt / a.nl, LP = a.nl | 1, FS = a.cols_cta * LP;
+    // resident: r (s after P2), v, and a work vector w that holds t between P3 and P4 and the Thomas input / output otherwise;
+    // the search direction p is only touched in P4 and lives in global memory
+    double *rs = smv, *vs = smv + R, *ws = smv + 2 * (size_t)R;
+    float *ffi = reinterpret_cast<float *>(smv + 3 * (size_t)R), *ffl = ffi + FS, *ffc = ffl + FS;
     const double *__restrict__ di = a.dinv;
     const int o2 = a.U.off[2], o4 = a.U.off[4], o6 = a.U.off[6];
     const int last = (cnt - 1) & ~1;
     const int npass = (cnt + 2 * BLOCK - 1) / (2 * BLOCK);
+    const bool PF = a.prefetch != 0;
     double in[5] = {0, 0, 0, 0, 0}, out[5];
     // ---- x0 = D^-1 b, ||b_free||^2, Dirichlet rows of this thread as a bit mask (pass j: rows 2 tid + 2 BLOCK j + {0,1} -> bits 2j, 2j+1)
     unsigned int dmask = 0;
@@ -183,10 +210,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab_res(BresArgs a)
                 a.x[k] = b * d;
                 if (d == 0.0) dmask |= 1u << (2 * j + q); else in[0] += b * b;
             }
-    // ---- Thomas factors of this CTA's columns (once per solve): pivot reciprocal, eliminated super-diagonal, sub-diagonal
+    // ---- Thomas factors of this CTA's columns (once per solve, fp64 arithmetic, stored as fp32)
     {
-        const int L = a.nl, C = a.cols_cta;
-        double *fi = a.fidn + (size_t)blockIdx.x * R, *fc = a.fcp + (size_t)blockIdx.x * R, *fl = a.flo + (size_t)blockIdx.x * R;
+        const int L = a.nl;
         for (int c = tid; c < ncol; c += BLOCK) {
             double cprev = 0.0, loprev = 0.0;
             for (int l = 0, k = row0 + c * L; l < L; ++l, ++k) {
@@ -197,7 +223,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab_res(BresArgs a)
                     idn = 1.0 / piv;
                     cc = l + 1 < L ? a.U.d[1][k] * idn : 0.0;
                 }
-                fi[l * C + c] = idn; fc[l * C + c] = cc; fl[l * C + c] = lo;
+                ffi[c * LP + l] = (float)idn; ffc[c * LP + l] = (float)cc; ffl[c * LP + l] = (float)lo;
                 cprev = cc; loprev = lo;
             }
         }
@@ -217,15 +243,15 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab_res(BresArgs a)
         if (act) {
             const double r0 = ((dmask >> (2 * j)) & 1u) ? 0.0 : a.rhs[k] - a0;
             const double r1 = (!ok1 || ((dmask >> (2 * j + 1)) & 1u)) ? 0.0 : a.rhs[k + 1] - a1;
-            rs[i] = r0; ps[i] = r0; vs[i] = 0.0; a.rt[k] = r0;
+            rs[i] = r0; ws[i] = r0; vs[i] = 0.0; a.rt[k] = r0; a.p[k] = r0;
             in[0] += r0 * r0;
-            if (ok1) { rs[i + 1] = r1; ps[i + 1] = r1; vs[i + 1] = 0.0; a.rt[k + 1] = r1; in[0] += r1 * r1; }
+            if (ok1) { rs[i + 1] = r1; ws[i + 1] = r1; vs[i + 1] = 0.0; a.rt[k + 1] = r1; a.p[k + 1] = r1; in[0] += r1 * r1; }
         }
     }
     __syncthreads();
-    line_apply_smem(a, ps, ts, ncol);
+    line_apply_inplace(a, ws, ffi, ffl, ffc, ncol, LP);
     __syncthreads();
-    for (int i = tid; i < cnt; i += BLOCK) a.ph[row0 + i] = ts[i];
+    for (int i = tid; i < cnt; i += BLOCK) a.ph[row0 + i] = ws[i];
     grid_reduce_v<BLOCK, 1>(a.counter, epoch, par, in, a.partial, sh, res, out);
     double rho = out[0], err = xlung > 0.0 ? sqrt(out[0] / xlung) : sqrt(out[0] / a.n);
     int niter = 0;
@@ -234,6 +260,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab_res(BresArgs a)
         return;
     }
     bool breakdown = false;
+    BRES_TICK(0);       // set-up
     for (;;) {
         ++niter;
         // ---- P1: v = J ph, sigma = (rt, v)
@@ -244,6 +271,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab_res(BresArgs a)
             const int i = act ? i_own : last;
             const bool ehi = lane == 31 || i_own + 2 >= cnt, elo = lane == 0;
             const int k = row0 + i;
+            if (PF && i_own + 2 * BLOCK < cnt) prefetch_pair_n(a.U, a.L, k + 2 * BLOCK);
             double a0, a1;
             row_pair_n<PAR>(a.U, a.L, a.ph, k, elo, ehi, o2, o4, o6, a0, a1);
             if (act) {
@@ -256,27 +284,33 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab_res(BresArgs a)
                 } else { vs[i] = a0; in[0] += a.rt[k] * a0; }
             }
         }
+        BRES_TICK(1);   // P1 product
         grid_reduce_v<BLOCK, 1>(a.counter, epoch, par, in, a.partial, sh, res, out);
+        BRES_TICK(2);   // reduction 1
         const double alpha = rho / out[0];
-        // ---- P2: s = r - alpha v (in place of r), sh = M^-1 s
+        // ---- P2: s = r - alpha v (in place of r, copy in w), sh = M^-1 s
         for (int i = 2 * tid; i < cnt; i += 2 * BLOCK) {
             if (i + 1 < cnt) {
                 double2 r = *reinterpret_cast<double2 *>(rs + i);
                 const double2 v = *reinterpret_cast<const double2 *>(vs + i);
                 r.x -= alpha * v.x; r.y -= alpha * v.y;
                 *reinterpret_cast<double2 *>(rs + i) = r;
-            } else rs[i] -= alpha * vs[i];
+                *reinterpret_cast<double2 *>(ws + i) = r;
+            } else { const double r = rs[i] - alpha * vs[i]; rs[i] = r; ws[i] = r; }
         }
         __syncthreads();
-        line_apply_smem(a, rs, ts, ncol);
+        BRES_TICK(3);   // s update
+        line_apply_inplace(a, ws, ffi, ffl, ffc, ncol, LP);
         __syncthreads();
+        BRES_TICK(4);   // Thomas
         for (int i = 2 * tid; i < cnt; i += 2 * BLOCK) {
-            if (i + 1 < cnt) *reinterpret_cast<double2 *>(a.sh + row0 + i) = *reinterpret_cast<const double2 *>(ts + i);
-            else a.sh[row0 + i] = ts[i];
+            if (i + 1 < cnt) *reinterpret_cast<double2 *>(a.sh + row0 + i) = *reinterpret_cast<const double2 *>(ws + i);
+            else a.sh[row0 + i] = ws[i];
         }
         grid_barrier(a.counter, epoch);
-        // ---- P3: t = J sh; (t,s), (t,t), (rt,s), (rt,t).  zigzag: the passes run from the last to the first, so the sweep starts on the
-        // part of the Jacobian that P1 read last and that is still in the L2
+        BRES_TICK(5);   // sh copy-out + grid barrier
+        // ---- P3: t = J sh (into w); (t,s), (t,t), (rt,s), (rt,t).  zigzag: the passes run from the last to the first, so the sweep
+        // starts on the part of the Jacobian that P1 read last and that is still in the L2
         in[0] = in[1] = in[2] = in[3] = 0.0;
         for (int jj = 0; jj < npass; ++jj) {
             const int j = a.zigzag ? npass - 1 - jj : jj;
@@ -287,6 +321,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab_res(BresArgs a)
             const int i = act ? i_own : last;
             const bool ehi = lane == 31 || i_own + 2 >= cnt, elo = lane == 0;
             const int k = row0 + i;
+            if (PF) { const int in_ = a.zigzag ? i_own - 2 * BLOCK : i_own + 2 * BLOCK; if (in_ >= 0 && in_ < cnt) prefetch_pair_n(a.U, a.L, row0 + in_); }
             double a0, a1;
             row_pair_n<PAR>(a.U, a.L, a.sh, k, elo, ehi, o2, o4, o6, a0, a1);
             if (act) {
@@ -294,52 +329,59 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab_res(BresArgs a)
                 if ((dmask >> (2 * j + 1)) & 1u) a1 = 0.0;
                 if (ok1) {
                     const double2 rtv = *reinterpret_cast<const double2 *>(a.rt + k), s = *reinterpret_cast<const double2 *>(rs + i);
-                    *reinterpret_cast<double2 *>(ts + i) = make_double2(a0, a1);
+                    *reinterpret_cast<double2 *>(ws + i) = make_double2(a0, a1);
                     in[0] += a0 * s.x; in[1] += a0 * a0; in[2] += rtv.x * s.x; in[3] += rtv.x * a0;
                     in[0] += a1 * s.y; in[1] += a1 * a1; in[2] += rtv.y * s.y; in[3] += rtv.y * a1;
                 } else {
                     const double rtv = a.rt[k], s = rs[i];
-                    ts[i] = a0;
+                    ws[i] = a0;
                     in[0] += a0 * s; in[1] += a0 * a0; in[2] += rtv * s; in[3] += rtv * a0;
                 }
             }
         }
+        BRES_TICK(6);   // P3 product
         grid_reduce_v<BLOCK, 4>(a.counter, epoch, par, in, a.partial, sh, res, out);
+        BRES_TICK(7);   // reduction 4
         const double omega = out[1] > 0.0 ? out[0] / out[1] : 0.0;
         const double rho_new = out[2] - omega * out[3];
         breakdown = omega == 0.0 || rho_new == 0.0;
         const double beta = breakdown ? 0.0 : (rho_new / rho) * (alpha / omega);
         // ---- P4: x += alpha ph + omega sh; r = s - omega t; ||r||^2 summed directly (the algebraic form cancels on ill-conditioned
-        // systems); p = r + beta (p - omega v); ph = M^-1 p
+        // systems); p = r + beta (p - omega v) -> global and w; ph = M^-1 p
         in[0] = 0.0;
         for (int i = 2 * tid; i < cnt; i += 2 * BLOCK) {
             const int k = row0 + i;
             if (i + 1 < cnt) {
-                double2 x = *reinterpret_cast<double2 *>(a.x + k);
+                double2 x = *reinterpret_cast<double2 *>(a.x + k), p = *reinterpret_cast<double2 *>(a.p + k);
                 const double2 ph = *reinterpret_cast<const double2 *>(a.ph + k), shv = *reinterpret_cast<const double2 *>(a.sh + k);
                 x.x = x.x + alpha * ph.x + omega * shv.x; x.y = x.y + alpha * ph.y + omega * shv.y;
                 *reinterpret_cast<double2 *>(a.x + k) = x;
-                double2 r = *reinterpret_cast<double2 *>(rs + i), p = *reinterpret_cast<double2 *>(ps + i);
-                const double2 t = *reinterpret_cast<const double2 *>(ts + i), v = *reinterpret_cast<const double2 *>(vs + i);
+                double2 r = *reinterpret_cast<double2 *>(rs + i);
+                const double2 t = *reinterpret_cast<const double2 *>(ws + i), v = *reinterpret_cast<const double2 *>(vs + i);
                 r.x -= omega * t.x; r.y -= omega * t.y;
                 in[0] += r.x * r.x; in[0] += r.y * r.y;
                 p.x = r.x + beta * (p.x - omega * v.x); p.y = r.y + beta * (p.y - omega * v.y);
-                *reinterpret_cast<double2 *>(rs + i) = r; *reinterpret_cast<double2 *>(ps + i) = p;
+                *reinterpret_cast<double2 *>(rs + i) = r; *reinterpret_cast<double2 *>(ws + i) = p; *reinterpret_cast<double2 *>(a.p + k) = p;
             } else {
                 a.x[k] = a.x[k] + alpha * a.ph[k] + omega * a.sh[k];
-                const double r = rs[i] - omega * ts[i];
+                const double r = rs[i] - omega * ws[i];
                 rs[i] = r; in[0] += r * r;
-                ps[i] = r + beta * (ps[i] - omega * vs[i]);
+                const double p = r + beta * (a.p[k] - omega * vs[i]);
+                ws[i] = p; a.p[k] = p;
             }
         }
         __syncthreads();
-        line_apply_smem(a, ps, ts, ncol);
+        BRES_TICK(8);   // P4 vector updates
+        line_apply_inplace(a, ws, ffi, ffl, ffc, ncol, LP);
         __syncthreads();
+        BRES_TICK(9);   // Thomas
         for (int i = 2 * tid; i < cnt; i += 2 * BLOCK) {
-            if (i + 1 < cnt) *reinterpret_cast<double2 *>(a.ph + row0 + i) = *reinterpret_cast<const double2 *>(ts + i);
-            else a.ph[row0 + i] = ts[i];
+            if (i + 1 < cnt) *reinterpret_cast<double2 *>(a.ph + row0 + i) = *reinterpret_cast<const double2 *>(ws + i);
+            else a.ph[row0 + i] = ws[i];
         }
         grid_reduce_v<BLOCK, 1>(a.counter, epoch, par, in, a.partial, sh, res, out);
+        BRES_TICK(10);  // ph copy-out + reduction
+        if (a.prof && blockIdx.x == 0 && tid == 0) a.prof[15] += 1;
         err = xlung > 0.0 ? sqrt(out[0] / xlung) : sqrt(out[0] / a.n);
         if (!(err > a.tol) || niter >= a.itmax || breakdown) break;
         rho = rho_new;

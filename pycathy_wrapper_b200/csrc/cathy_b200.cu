@@ -2720,13 +2720,15 @@ struct CathySim {
                                      // +46 % per iteration on the config-3 storm, no gain on unsaturated systems; profiles/r1_precond_experiment.md)
     DBuf<double> widn, wcp;          // its Thomas factors
     bool l2_reset = true;
-    size_t l2_window = 0, l2_persist = 0;   // bytes of the Jacobian covered by the access-policy window / L2 set-aside for persisting lines
+    size_t l2_window = 0, l2_persist = 0, l2_maxwin = 0;   // bytes of the Jacobian covered by the access-policy window / L2 set-aside for persisting lines
     DBuf<double> Ju, Jl, dinv, dckrw, detai, ts, s1, ws, wsh, wt;   // Newton: Jacobian diagonals, Jacobi scaling, derivative curves, element factors, BiCGSTAB vectors
     bool newton = false;
     // Newton, resident solver (bicg_res.cuh): permuted Jacobian + vectors, line factors; bres_rows = 0: not used (does not fit / opted out)
     int bres_rows = 0, bres_cols = 0, bres_off[NDIAG] = {0};
     size_t bres_halo = 0;
-    DBuf<double> bres_u, bres_l, bres_rhs, bres_dinv, bres_x, bres_ph, bres_sh, bres_rt, bres_fidn, bres_fcp, bres_flo;
+    DBuf<double> bres_u, bres_l, bres_rhs, bres_dinv, bres_x, bres_ph, bres_sh, bres_rt, bres_p;
+    size_t bres_smem = 0;
+    DBuf<unsigned long long> bres_prof;      // CATHY_BRES_PROF=1: per-phase nanoseconds of CTA 0, printed at cathy_destroy
     // ---- row-block partition of one large mesh over several GPUs (BASELINE config 5) ----
     bool dd = false, pcg_shared_gpu = false;
     int dd_world = 1, dd_rank = 0;
@@ -3499,22 +3501,48 @@ static int solve_system_newton_res(CathySim *S)
     S->launches++;
     BresArgs a;
     a.n = n; a.itmax = S->itmax_dev; a.tol = S->tol_dev; a.U = U; a.L = Lw;
-    a.rhs = S->bres_rhs.p; a.dinv = S->bres_dinv.p; a.x = S->bres_x.p; a.ph = S->bres_ph.p; a.sh = S->bres_sh.p; a.rt = S->bres_rt.p;
-    a.fidn = S->bres_fidn.p; a.fcp = S->bres_fcp.p; a.flo = S->bres_flo.p;
+    a.rhs = S->bres_rhs.p; a.dinv = S->bres_dinv.p; a.x = S->bres_x.p; a.ph = S->bres_ph.p; a.sh = S->bres_sh.p; a.rt = S->bres_rt.p; a.p = S->bres_p.p;
     a.partial = S->partial.p; a.counter = S->d_counter.p; a.epoch0 = S->barrier_epoch; a.out = S->d_iter.p;
     a.rows_cta = S->bres_rows; a.nl = L; a.cols_cta = S->bres_cols;
     {   // CATHY_BICG_ZIGZAG=0/1 overrides; default: on when the Jacobian does not fit the L2
         const char *e = getenv("CATHY_BICG_ZIGZAG");
         a.zigzag = e ? atoi(e) != 0 : (size_t)n * 240 > ((size_t)100 << 20);
     }
+    { const char *e = getenv("CATHY_BRES_POINT"); a.point = e ? atoi(e) != 0 : 0; }
+    {   // opt-in: measured on B200 at config 3 the products already run at ~80 % of the HBM copy peak (DRAM-bound, ncu) and the extra
+        // prefetch instructions cost more than they hide (P1 24.2 -> 27.0 us; a TMA bulk prefetch issued by one thread: 76 -> 84 us/iteration)
+        const char *e = getenv("CATHY_BRES_PREFETCH");
+        a.prefetch = e ? atoi(e) != 0 : 0;
+    }
+    a.prof = nullptr;
+    if (getenv("CATHY_BRES_PROF")) {
+        if (!S->bres_prof.p && S->bres_prof.alloc(16)) FAIL(-101, "profile buffer allocation failed");
+        a.prof = S->bres_prof.p;
+    }
+
     void *args[] = {&a};
     const void *fn = bicg_res_fn(S->bres_off);
-    const size_t smem = (size_t)4 * S->bres_rows * sizeof(double);
+    const size_t smem = S->bres_smem;
     const int g = S->pcg_shared_gpu ? S->grid_pcg : S->sms;
+    // CATHY_L2_PERSIST (opt-in): the permuted Jacobian's lines are marked persisting for this launch (as many as the set-aside holds)
+    cudaStreamAttrValue av = {};
+    if (S->l2_persist) {
+        const size_t jbytes = ((size_t)2 * NDIAG * S->ld + 4 * S->bres_halo) * sizeof(double);
+        av.accessPolicyWindow.base_ptr = S->bres_u.base;
+        av.accessPolicyWindow.num_bytes = std::min(jbytes, S->l2_maxwin);
+        av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)S->l2_persist / (double)av.accessPolicyWindow.num_bytes);
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        CK(cudaStreamSetAttribute(S->st, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
     CK(cudaEventRecord(S->evp0, S->st));
     if (S->pcg_shared_gpu) CK(cudaLaunchKernel(fn, dim3(g), dim3(1024), args, smem, S->st));
     else CK(cudaLaunchCooperativeKernel(fn, dim3(g), dim3(1024), args, smem, S->st));
     CK(cudaEventRecord(S->evp1, S->st));
+    if (S->l2_persist) {
+        av.accessPolicyWindow.num_bytes = 0;
+        CK(cudaStreamSetAttribute(S->st, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
     S->launches++;
     k_unpermute_cols<<<(NN + 31) / 32, 256, tile, S->st>>>(NN, L, S->bres_x.p, S->pdiff.p);
     CK(cudaGetLastError());
@@ -3759,6 +3787,16 @@ void cathy_destroy(CathySim *S)
     if (!S) return;
     cudaSetDevice(S->p.device);
     if (S->st) cudaStreamSynchronize(S->st);
+    if (S->bres_prof.p) {
+        unsigned long long h[16];
+        if (cudaMemcpy(h, S->bres_prof.p, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess && h[15] > 0) {
+            static const char *nm[11] = {"setup", "P1 product", "reduce1", "s update", "Thomas(s)", "sh out + barrier", "P3 product", "reduce4", "P4 updates", "Thomas(p)", "ph out + reduce"};
+            fprintf(stderr, "k_bicgstab_res phases of CTA 0, us per iteration over %llu iterations:", h[15]);
+            for (int q = 1; q < 11; ++q) fprintf(stderr, " %s %.2f;", nm[q], 1e-3 * (double)h[q] / (double)h[15]);
+            fprintf(stderr, " setup total %.1f us\n", 1e-3 * (double)h[0]);
+        }
+        S->bres_prof.release();
+    }
     // DBuf members are plain pointers: release them explicitly
     DBuf<double> *dd[] = {&S->vgn, &S->vgm, &S->vgpsat, &S->vgpnot, &S->rr, &S->snodi, &S->pnodi, &S->vgn1, &S->vgnr, &S->vgpsn, &S->vgmr,
                           &S->volnod, &S->arenod, &S->z, &S->m4, &S->vegpar, &S->ell_coef, &S->ell_coef2, &S->A, &S->diag_true, &S->diag_bc,
@@ -3777,7 +3815,7 @@ void cathy_destroy(CathySim *S)
       for (auto *b : nn) b->release(); S->ell_loc.release(); }
     S->dis.release(); S->wq0.release(); S->wq1.release();
     S->snap.release(); S->snap_i.release(); S->plan_rel.release();
-    { DBuf<double> *bb[] = {&S->bres_u, &S->bres_l, &S->bres_rhs, &S->bres_dinv, &S->bres_x, &S->bres_ph, &S->bres_sh, &S->bres_rt, &S->bres_fidn, &S->bres_fcp, &S->bres_flo};
+    { DBuf<double> *bb[] = {&S->bres_u, &S->bres_rhs, &S->bres_dinv, &S->bres_x, &S->bres_ph, &S->bres_sh, &S->bres_rt, &S->bres_p};
       for (auto *b : bb) b->release(); }
     S->contp_flag.release(); S->contq_flag.release(); S->contp_val.release(); S->qneu.release(); S->qlist.release(); S->qpnew.release();
     S->qpold.release(); S->kznod.release(); S->bcsum.release(); S->contp_list.release();
@@ -4027,7 +4065,7 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
                 const size_t want = e && atoi(e) > 1 ? (size_t)atoi(e) << 20 : (size_t)maxp;
                 const size_t persist = std::min(std::min((size_t)maxp, want), jbytes);
                 if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess) {
-                    S->l2_window = std::min(jbytes, (size_t)maxw); S->l2_persist = persist;
+                    S->l2_window = std::min(jbytes, (size_t)maxw); S->l2_persist = persist; S->l2_maxwin = (size_t)maxw;
                 } else cudaGetLastError();
             }
         }
@@ -4049,16 +4087,19 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
                 int optin = 0;
                 CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, p.device));
                 const size_t avail = (size_t)optin > at.sharedSizeBytes ? (size_t)optin - at.sharedSizeBytes : 0;
-                if ((size_t)4 * rows * sizeof(double) <= avail && rows <= 32 * 1024 && rows * g >= N) {
-                    S->bres_rows = (int)rows; S->bres_cols = cols;
+                // shared memory: 3 resident vectors (fp64) + 3 line-factor arrays (fp32, column stride L | 1)
+                const size_t smem = (size_t)3 * rows * sizeof(double) + (size_t)3 * cols * (L | 1) * sizeof(float);
+                if (smem <= avail && rows <= 32 * 1024 && rows * g >= N) {
+                    S->bres_rows = (int)rows; S->bres_cols = cols; S->bres_smem = smem;
                     for (int d = 0; d < NDIAG; ++d) S->bres_off[d] = off[d];
                     S->bres_halo = ((size_t)off[NDIAG - 1] + 2 + 31) / 32 * 32;
                     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
-                    a |= S->bres_u.alloc((size_t)NDIAG * S->ld, S->bres_halo); a |= S->bres_l.alloc((size_t)NDIAG * S->ld, S->bres_halo);
-                    DBuf<double> *bv[] = {&S->bres_rhs, &S->bres_dinv, &S->bres_x, &S->bres_ph, &S->bres_sh, &S->bres_rt};
+                    // U' and L' share ONE allocation ([halo | 8 upper | halo][halo | 8 lower | halo]) so that one L2 access-policy window covers them
+                    a |= S->bres_u.alloc((size_t)2 * NDIAG * S->ld + 2 * S->bres_halo, S->bres_halo);
+                    S->bres_l.release();
+                    if (!a) { S->bres_l.p = S->bres_u.p + (size_t)NDIAG * S->ld + 2 * S->bres_halo; S->bres_l.n = (size_t)NDIAG * S->ld; S->bres_l.pad = S->bres_halo; }
+                    DBuf<double> *bv[] = {&S->bres_rhs, &S->bres_dinv, &S->bres_x, &S->bres_ph, &S->bres_sh, &S->bres_rt, &S->bres_p};
                     for (auto *b : bv) a |= b->alloc(N, S->bres_halo);
-                    const size_t fsz = (size_t)rows * g;
-                    a |= S->bres_fidn.alloc(fsz); a |= S->bres_fcp.alloc(fsz); a |= S->bres_flo.alloc(fsz);
                 }
             }
         }

@@ -403,7 +403,15 @@ class Ensemble:
             old = os.environ.get("CATHY_PCG_GRID")
             os.environ["CATHY_PCG_GRID"] = str(max(1, sms // self.concurrent))
         try:
-            self.sims = [Simulation(lib, prj, device=device) for prj in projects]
+            # cathy_create is mostly single-threaded host work (mesh, static gather plan) and ctypes releases the GIL inside it:
+            # the members of a rank are built by a few host threads side by side
+            nthr = max(1, min(len(projects), (os.cpu_count() or 1), 8))
+            if nthr > 1:
+                from concurrent.futures import ThreadPoolExecutor
+                with ThreadPoolExecutor(max_workers=nthr) as ex:
+                    self.sims = list(ex.map(lambda prj: Simulation(lib, prj, device=device), projects))
+            else:
+                self.sims = [Simulation(lib, prj, device=device) for prj in projects]
         finally:
             if self.concurrent > 1:
                 if old is None:

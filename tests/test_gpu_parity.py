@@ -489,6 +489,10 @@ def test_newton_boustrophedon_sweeps(gpu_lib, oracle_mod, monkeypatch):
     from pycathy_wrapper_b200.project import load_project
     monkeypatch.setenv("CATHY_BICG_ZIGZAG", "1")
     prj = load_project(os.path.join(GOLDEN, "newton20"))
+    from pycathy_wrapper_b200.capi import Simulation
+    probe = Simulation(gpu_lib, prj)
+    assert probe.solver_info()["kernel"] == 11          # resident-vector solver (bicg_res.cuh), zigzag forced on
+    probe.close()
     g, c, rg, rc = _run_both(gpu_lib, oracle_mod, prj)
     assert rg.nstep == 130
     ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
@@ -501,27 +505,49 @@ def test_newton_boustrophedon_sweeps(gpu_lib, oracle_mod, monkeypatch):
 
 
 def test_newton_coupled_storm(gpu_lib, oracle_mod):
-    """Newton + surface routing (BASELINE config 3 in small): the first step back-steps 9 times in the reference because its
-    third linear solve fails -- the device must fail there too -- and the following accepted steps (ponding, routing
-    sub-steps, atmospheric switching every iteration) must match exactly with heads inside the 1e-6 / 1e-8 m band: checked
-    for the first 150 of the 556 steps.  Further on the reference's own nonlinear convergence is non-monotone with
-    switching at every iteration (e.g. PINF 3.6e-4, 4.0e-4, 9.3e-5 at step 154, accepted at TOLUNS = 1e-4), so the two
-    linear solvers' different roundoff shows up at the 1e-4 m level in single iterates and eventually in one iteration
-    count (measured: step 388 of 556); from there only the end state is compared: same end time, storage to 1e-6
-    relative, heads to 1e-3 m (measured 1.5e-5 m)."""
+    """Newton + surface routing (BASELINE config 3 in small, 556 accepted steps in the reference): the first step back-steps 9 times
+    in the reference because its third linear solve fails -- the device must fail there too -- and every following accepted step
+    (ponding, routing sub-steps, atmospheric switching at every iteration) must match exactly: (NSTEP, Newton iterations,
+    back-steps, routing sub-steps, DELTAT) are asserted for ALL steps up to 387.
+
+    Step 388 is a knife-edge of the reference's own algorithm, not of the device solver: the reference restatement run with
+    TOLCG halved leaves its own trajectory at exactly that step (tests/test_oracle_golden.py::
+    test_oracle_coupled_storm_is_sensitive_at_step_388: 2 instead of 4 Newton iterations, 543 instead of 556 steps, heads 4e-3 m
+    apart at the end), because with switching at every iteration a rounding-level perturbation grows ~10x every 40 steps
+    (oracle against itself: 3.6e-9 m at step 150, 5e-7 at 300, 2.6e-4 at 380).  The device (vertical-line BiCGSTAB, residual
+    1e-13) follows the same curve: heads inside the 1e-6 / 1e-8 m band at step 150 (measured 6e-9 m), 1.7e-6 m at step 300,
+    8e-4 m at step 380, fork at 388.  After the fork only what any two runs of the reference itself share is asserted: same end
+    time, same stored volume, heads within the reference's own sensitivity (5e-3 m)."""
+    from pycathy_wrapper_b200.capi import Simulation
     from pycathy_wrapper_b200.project import load_project
     prj = load_project(os.path.join(GOLDEN, "storm20n"))
-    g, c, rg, rc = _run_both(gpu_lib, oracle_mod, prj, nsteps=150, store_rtol=1e-8)
-    assert rg.nstep == 150 and g.state()["ifatm"].tolist() == c.state()["ifatm"].tolist()
-    ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
-    assert ok, dmax
+    g, c = Simulation(gpu_lib, prj), oracle_mod.simulation(prj)
+    bounds = {150: None, 300: 1e-5, 380: 3e-3}           # None: the parity band itself
+    rg = rc = None
+    for k in range(1, 388):
+        rg, rc = g.step(), c.step()
+        assert (rg.nstep, rg.iter, rg.kbackt, rg.nsurf) == (rc.nstep, rc.iter, rc.kbackt, rc.nsurf), \
+            f"step {k}: gpu (nstep,iter,back,nsurf)={(rg.nstep, rg.iter, rg.kbackt, rg.nsurf)} oracle={(rc.nstep, rc.iter, rc.kbackt, rc.nsurf)}"
+        assert abs(rg.deltat - rc.deltat) <= 1e-12 * rc.deltat and abs(rg.time - rc.time) <= 1e-12 * rc.time
+        if k <= 300:
+            assert abs(rg.store1 - rc.store1) <= 1e-8 * abs(rc.store1)
+        if k in bounds:
+            pg, pc = g.state()["psi"], c.state()["psi"]
+            if bounds[k] is None:
+                ok, dmax = psi_close(pg, pc)
+                assert ok, dmax
+                assert g.state()["ifatm"].tolist() == c.state()["ifatm"].tolist()
+            else:
+                assert np.max(np.abs(pg - pc)) <= bounds[k], (k, np.max(np.abs(pg - pc)))
+    assert rg.nstep == 387 and rg.kback_total == rc.kback_total == 9
     while not rg.finished:
         rg = g.step()
     while not rc.finished:
         rc = c.step()
-    assert abs(rg.time - rc.time) <= 1e-9 * rc.time
+    assert abs(rg.time - rc.time) <= 1e-9 * rc.time and rg.noback == rc.noback == 0
+    assert abs(rg.nstep - rc.nstep) <= 20 and rc.nstep == 556
     assert abs(rg.store1 - rc.store1) <= 1e-6 * rc.store1
-    assert np.max(np.abs(g.state()["psi"] - c.state()["psi"])) <= 1e-3
+    assert np.max(np.abs(g.state()["psi"] - c.state()["psi"])) <= 5e-3
 
 
 def test_vtk_and_velocities_against_reference(gpu_lib, oracle_mod, tmp_path):
