@@ -484,7 +484,8 @@ __global__ void k_spmv(int n, Diag A, const double *__restrict__ diag0, const do
 struct DDBox {                               // lives in each rank's device memory, mapped by all peers
     unsigned int ar_flag[DD_MAXW];           // sequence number of the last all-reduce contribution of rank r
     unsigned int halo_flag[2];               // [0]: from the north neighbour, [1]: from the south neighbour
-    unsigned int pad[6];
+    int geom[4];                             // column-major layout of this rank: first owned row lo, end hi, local rows, halo rows (k_pcg_tma)
+    unsigned int pad[2];
     double ar_slot[2][DD_MAXW][DD_NRED];     // [parity][rank][value]
 };
 struct DDCtx {
@@ -666,6 +667,7 @@ struct PcgArgs {
     DDCtx dd;
     int rows_cta;               // k_pcg_res: rows owned by one CTA (multiple of 32)
     int xres;                   // k_pcg_res: 1 = the solution vector lives in shared memory too
+    int cm;                     // k_pcg: 1 = the arrays are in the column-major permutation (Dirichlet rows are recognised by their penalty diagonal)
 };
 
 // Grid-wide barrier for the persistent kernel: one arrival per block on a monotonically increasing counter
@@ -784,7 +786,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_pcg(PcgArgs a)
     for (int k = t0; k < n; k += stride) {
         double b = a.rhs[k];
         a.x[k] = b / dg[k];
-        if ((!DD || (own[k] & 1)) && !is_dirichlet(k, a.nnod, a.ifatm, a.contp_flag)) xl += b * b;
+        if ((!DD || (own[k] & 1)) && !(a.cm ? dg[k] > 1.0e80 : is_dirichlet(k, a.nnod, a.ifatm, a.contp_flag))) xl += b * b;
     }
     double xlung, d1, d2;
     grid_reduce3<BLOCK, CUSTOM>(grid, a.counter, epoch, xl, 0.0, 0.0, a.partial, sh, xlung, d1, d2);
@@ -865,7 +867,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_pcg(PcgArgs a)
             a.z[k] = zz;
             if (!DD || (own[k] & 1)) {
                 s_bz += bk * zz;
-                if (!is_dirichlet(k, a.nnod, a.ifatm, a.contp_flag)) s_rr += r * r;
+                if (!(a.cm ? dg[k] > 1.0e80 : is_dirichlet(k, a.nnod, a.ifatm, a.contp_flag))) s_rr += r * r;
             }
             if (DD && (own[k] & 6)) {
                 const DDCtx &c = a.dd;
@@ -1772,6 +1774,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab(BicgArgs a)
 }
 
 #include "bicg_res.cuh"
+#include "pcg_tma.cuh"
 
 // ------------------------------------------------------------------------------------------
 // after the solve: PNEW += PDIFF and SHLPIC's Dirichlet reset (SRC/picard.f:185-198, SRC/shlpic.f:30-56)
@@ -2722,6 +2725,15 @@ struct CathySim {
     bool l2_reset = true;
     size_t l2_window = 0, l2_persist = 0, l2_maxwin = 0;   // bytes of the Jacobian covered by the access-policy window / L2 set-aside for persisting lines
     DBuf<double> Ju, Jl, dinv, dckrw, detai, ts, s1, ws, wsh, wt;   // Newton: Jacobian diagonals, Jacobi scaling, derivative curves, element factors, BiCGSTAB vectors
+    // Picard, streaming PCG in the column-major permutation (meshes too large for the resident kernels): cm_on, permuted arrays
+    bool cm_on = false;
+    int cm_off[NDIAG] = {0};
+    size_t cm_halo = 0;
+    DBuf<double> cm_A, cm_diag, cm_rhs, cm_x, cm_r, cm_z, cm_p0, cm_p1, cm_bv;
+    bool tma_on = false;             // k_pcg_tma (pcg_tma.cuh) instead of k_pcg on the permuted arrays; cm_p1 holds the reciprocal diagonal
+    size_t tma_smem = 0;
+    double *tma_zpeer_n = nullptr, *tma_zpeer_s = nullptr;
+    long long tma_ndst0 = 0, tma_sdst0 = 0;
     bool newton = false;
     // Newton, resident solver (bicg_res.cuh): permuted Jacobian + vectors, line factors; bres_rows = 0: not used (does not fit / opted out)
     int bres_rows = 0, bres_cols = 0, bres_off[NDIAG] = {0};
@@ -3396,11 +3408,102 @@ static const void *pcg_res2_fn(const CathySim *S)
     const int nc1 = S->ncol + 1, o2 = nc1, o4 = S->nnod - nc1 - 1, o6 = S->nnod - 1;    // = off[2], off[4], off[6] (set later, by the mesh builder)
     return fn[(o2 & 1) | ((o4 & 1) << 1) | ((o6 & 1) << 2)];
 }
+// streaming PCG on the column-major permutation of the system (see create_impl); the same kernel, other offsets
+static int solve_system_cm(CathySim *S)
+{
+    const int n = S->n, NN = S->nnod, L = S->nstr + 1;
+    Diag A = make_diag(S, S->A.p), P;
+    for (int d = 0; d < NDIAG; ++d) { P.d[d] = S->cm_A.p + (size_t)d * S->ld; P.off[d] = S->cm_off[d]; }
+    // old family d -> permuted family; 4, 5, 6 point to a LOWER permuted index: the (symmetric) entry is stored at its other end
+    static const int newd[NDIAG] = {0, 3, 5, 7, 6, 4, 2, 1};
+    PermArgs pa;
+    int q = 0;
+    for (int d = 1; d < NDIAG; ++d) {
+        const bool swp = d >= 4 && d <= 6;
+        pa.src[q] = A.d[d]; pa.dst[q] = P.d[newd[d]]; pa.shift[q] = swp ? S->cm_off[newd[d]] : 0; ++q;
+    }
+    pa.src[q] = S->diag_bc.p; pa.dst[q] = S->cm_diag.p; pa.shift[q] = 0; ++q;
+    pa.src[q] = S->rhs.p; pa.dst[q] = S->cm_rhs.p; pa.shift[q] = 0; ++q;
+    pa.nnod = NN; pa.nl = L; pa.n = n;
+    const size_t tile = (size_t)L * 33 * sizeof(double);
+    k_permute_cols<<<dim3((NN + 31) / 32, q), 256, tile, S->st>>>(pa);
+    CK(cudaGetLastError());
+    S->launches++;
+    PcgArgs a;
+    a.rows_cta = 0; a.xres = 0; a.cm = 1;
+    a.n = n; a.nnod = NN; a.itmax = S->itmax_dev; a.tol = S->tol_dev;
+    a.A = P; a.diag = S->cm_diag.p; a.rhs = S->cm_rhs.p;
+    a.x = S->cm_x.p; a.r = S->cm_r.p; a.z = S->cm_z.p; a.p0 = S->cm_p0.p; a.p1 = S->cm_p1.p; a.bv = S->cm_bv.p;
+    a.ifatm = nullptr; a.contp_flag = nullptr; a.partial = S->partial.p; a.out = S->d_iter.p;
+    a.counter = S->d_counter.p; a.epoch0 = S->barrier_epoch; a.own = nullptr; a.prefetch = S->pcg_prefetch;
+    void *args[] = {&a};
+    CK(cudaEventRecord(S->evp0, S->st));
+    if (S->pcg_shared_gpu) { k_pcg<1024, true, false><<<S->grid_pcg, 1024, 0, S->st>>>(a); CK(cudaGetLastError()); }
+    else CK(cudaLaunchCooperativeKernel((void *)k_pcg<1024, true, false>, dim3(S->sms), dim3(1024), args, 0, S->st));
+    CK(cudaEventRecord(S->evp1, S->st));
+    S->launches++;
+    k_unpermute_cols<<<(NN + 31) / 32, 256, tile, S->st>>>(NN, L, S->cm_x.p, S->pdiff.p);
+    CK(cudaGetLastError());
+    S->launches++;
+    return 0;
+}
+// k_pcg_tma on the permuted system (pcg_tma.cuh): TMA-staged tiles, also the partitioned solver
+static int solve_system_tma(CathySim *S)
+{
+    const int n = S->n, NN = S->nnod, L = S->nstr + 1;
+    Diag A = make_diag(S, S->A.p), P;
+    for (int d = 0; d < NDIAG; ++d) { P.d[d] = S->cm_A.p + (size_t)d * S->ld; P.off[d] = S->cm_off[d]; }
+    static const int newd[NDIAG] = {0, 3, 5, 7, 6, 4, 2, 1};
+    PermArgs pa;
+    int q = 0;
+    for (int d = 1; d < NDIAG; ++d) {
+        const bool swp = d >= 4 && d <= 6;
+        pa.src[q] = A.d[d]; pa.dst[q] = P.d[newd[d]]; pa.shift[q] = swp ? S->cm_off[newd[d]] : 0; ++q;
+    }
+    pa.src[q] = S->diag_bc.p; pa.dst[q] = S->cm_diag.p; pa.shift[q] = 0; ++q;
+    pa.src[q] = S->rhs.p; pa.dst[q] = S->cm_rhs.p; pa.shift[q] = 0; ++q;
+    pa.nnod = NN; pa.nl = L; pa.n = n;
+    const size_t tile = (size_t)L * 33 * sizeof(double);
+    k_permute_cols<<<dim3((NN + 31) / 32, q), 256, tile, S->st>>>(pa);
+    CK(cudaGetLastError());
+    S->launches++;
+    TmaArgs a;
+    const int rowlen = S->nc1 * L;
+    a.n = n; a.lo = S->dd ? S->own_a * rowlen : 0; a.hi = S->dd ? S->own_b * rowlen : n;
+    a.itmax = S->itmax_dev; a.tol = S->tol_dev; a.A = P; a.dg = S->cm_diag.p; a.rhs = S->cm_rhs.p;
+    a.dinv = S->cm_p1.p; a.x = S->cm_x.p; a.r = S->cm_r.p; a.z = S->cm_z.p; a.p = S->cm_p0.p; a.bv = S->cm_bv.p;
+    a.partial = S->partial.p; a.counter = S->d_counter.p; a.epoch0 = S->barrier_epoch; a.out = S->d_iter.p;
+    const int g = S->pcg_shared_gpu ? S->grid_pcg : S->sms;
+    const int ntile = (a.hi - a.lo + TMA_T - 1) / TMA_T;
+    a.tiles_cta = std::max(1, (ntile + g - 1) / g);
+    a.nl = L;
+    a.dd_on = S->dd ? 1 : 0;
+    a.zpeer_n = S->tma_zpeer_n; a.zpeer_s = S->tma_zpeer_s; a.ndst0 = S->tma_ndst0; a.sdst0 = S->tma_sdst0; a.nbr = DD_W * rowlen;
+    if (S->dd) a.dd = S->comm->ctx; else memset(&a.dd, 0, sizeof a.dd);
+    a.prof = nullptr;
+    if (getenv("CATHY_TMA_PROF")) {
+        if (!S->bres_prof.p && S->bres_prof.alloc(16)) FAIL(-101, "profile buffer allocation failed");
+        a.prof = S->bres_prof.p;
+    }
+    void *args[] = {&a};
+    const void *fn = S->dd ? (const void *)k_pcg_tma<true> : (const void *)k_pcg_tma<false>;
+    CK(cudaEventRecord(S->evp0, S->st));
+    if (S->pcg_shared_gpu) CK(cudaLaunchKernel(fn, dim3(g), dim3(TMA_BLOCK), args, S->tma_smem, S->st));
+    else CK(cudaLaunchCooperativeKernel(fn, dim3(g), dim3(TMA_BLOCK), args, S->tma_smem, S->st));
+    CK(cudaEventRecord(S->evp1, S->st));
+    S->launches++;
+    k_unpermute_cols<<<(NN + 31) / 32, 256, tile, S->st>>>(NN, L, S->cm_x.p, S->pdiff.p);
+    CK(cudaGetLastError());
+    S->launches++;
+    return 0;
+}
 static int solve_system(CathySim *S)
 {
     if (!S->dd && S->pcg_algo == 2) return solve_system2(S);
+    if (S->tma_on) return solve_system_tma(S);
+    if (S->cm_on) return solve_system_cm(S);
     PcgArgs a;
-    a.rows_cta = 0; a.xres = 0;
+    a.rows_cta = 0; a.xres = 0; a.cm = 0;
     a.n = S->n; a.nnod = S->nnod; a.itmax = S->itmax_dev; a.tol = S->tol_dev;
     a.A = make_diag(S, S->A.p); a.diag = S->diag_bc.p; a.rhs = S->rhs.p;
     a.x = S->pdiff.p; a.r = S->wr.p; a.z = S->wz.p; a.p0 = S->wp0.p; a.p1 = S->wp1.p; a.bv = S->wbv.p;
@@ -3789,7 +3892,10 @@ void cathy_destroy(CathySim *S)
     if (S->st) cudaStreamSynchronize(S->st);
     if (S->bres_prof.p) {
         unsigned long long h[16];
-        if (cudaMemcpy(h, S->bres_prof.p, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess && h[15] > 0) {
+        if (cudaMemcpy(h, S->bres_prof.p, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess && h[15] > 0 && S->tma_on)
+            fprintf(stderr, "k_pcg_tma phases of CTA 0, us per iteration over %llu iterations: phase A %.2f; reduce %.2f; phase B %.2f; reduce %.2f\n", h[15],
+                    1e-3 * h[0] / h[15], 1e-3 * h[1] / h[15], 1e-3 * h[2] / h[15], 1e-3 * h[3] / h[15]);
+        else if (h[15] > 0) {
             static const char *nm[11] = {"setup", "P1 product", "reduce1", "s update", "Thomas(s)", "sh out + barrier", "P3 product", "reduce4", "P4 updates", "Thomas(p)", "ph out + reduce"};
             fprintf(stderr, "k_bicgstab_res phases of CTA 0, us per iteration over %llu iterations:", h[15]);
             for (int q = 1; q < 11; ++q) fprintf(stderr, " %s %.2f;", nm[q], 1e-3 * (double)h[q] / (double)h[15]);
@@ -3815,6 +3921,9 @@ void cathy_destroy(CathySim *S)
       for (auto *b : nn) b->release(); S->ell_loc.release(); }
     S->dis.release(); S->wq0.release(); S->wq1.release();
     S->snap.release(); S->snap_i.release(); S->plan_rel.release();
+    { DBuf<double> *cc[] = {&S->cm_A, &S->cm_diag, &S->cm_rhs, &S->cm_x, &S->cm_r, &S->cm_p0, &S->cm_p1, &S->cm_bv};
+      for (auto *b : cc) b->release();
+      if (!S->dd) S->cm_z.release(); }
     { DBuf<double> *bb[] = {&S->bres_u, &S->bres_rhs, &S->bres_dinv, &S->bres_x, &S->bres_ph, &S->bres_sh, &S->bres_rt, &S->bres_p};
       for (auto *b : bb) b->release(); }
     S->contp_flag.release(); S->contq_flag.release(); S->contp_val.release(); S->qneu.release(); S->qlist.release(); S->qpnew.release();
@@ -3862,7 +3971,7 @@ static int preload_kernels()
                          (const void *)k_div_area, (const void *)k_nod_cell, (const void *)k_cell_nod, (const void *)k_route, (const void *)k_route_static, (const void *)k_pond_zero,
                          (const void *)k_step_partial, (const void *)k_step_final, (const void *)k_weight, (const void *)k_atmone, (const void *)k_mbinit,
                          (const void *)k_pack_col, (const void *)k_unpack_col, (const void *)k_vel3d, (const void *)k_vnod3d, (const void *)k_recharge, (const void *)k_wtdepth, (const void *)k_curves_alt, (const void *)k_chvelo_alt, (const void *)k_curves_xvg, (const void *)k_chvelo_xvg,
-                         (const void *)k_curves_newton_alt, (const void *)k_sw_pair_alt, (const void *)k_relax, (const void *)k_pcg_res<1024>, (const void *)k_permute_cols, (const void *)k_unpermute_cols};
+                         (const void *)k_curves_newton_alt, (const void *)k_sw_pair_alt, (const void *)k_relax, (const void *)k_pcg_res<1024>, (const void *)k_permute_cols, (const void *)k_unpermute_cols, (const void *)k_pcg_tma<true>, (const void *)k_pcg_tma<false>};
     for (const void *f : fns) CK(cudaFuncGetAttributes(&at, f));
     done = true;
     return 0;
@@ -4043,6 +4152,42 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
     a |= S->dis.alloc(N, S->halo); a |= S->wq0.alloc(N, S->halo); a |= S->wq1.alloc(N, S->halo);
     a |= S->krt.alloc(S->nt); a |= S->e1t.alloc(S->nt);
     a |= S->partial.alloc(10 * (size_t)std::max(S->grid_pcg, 1));
+    {   // Streaming PCG in the column-major permutation k' = s L + l.  In the layer-major numbering the stencil reaches NNOD rows up and
+        // down, and once NNOD rows of matrix + vectors (~100 B each) exceed the L2 (config 5: 1 M rows = 100 MB) the z / p gathers and
+        // the lower-triangle reads of the neighbouring layers miss and come from HBM a second and third time.  Column-major, the
+        // half bandwidth is (NC1 + 1) L rows (config 5: 31 k rows = 3 MB): every operand is read from HBM once per phase.
+        // Default: on whenever the resident kernels do not apply and the mesh is large, and for every partitioned handle;
+        // CATHY_PCG_CM=0/1 overrides.  CATHY_PCG_TMA=0 keeps k_pcg (direct loads) on the permuted arrays instead of k_pcg_tma.
+        const char *e = getenv("CATHY_PCG_CM"), *et = getenv("CATHY_PCG_TMA");
+        const bool want = e ? atoi(e) != 0 : (S->dd || (size_t)N * 100 > ((size_t)48 << 20));
+        const bool streaming = S->dd || (!((S->pcg_algo == 3 || S->pcg_algo == 4) && S->res_rows > 0) && S->pcg_algo != 2);
+        const bool tma = !(et && atoi(et) == 0);
+        if (!S->newton && streaming && want && S->nstr >= 2 && (!S->dd || tma)) {
+            const int L = S->nstr + 1, nc1 = S->ncol + 1;
+            const int off[NDIAG] = {0, 1, L - 1, L, nc1 * L - 1, nc1 * L, (nc1 + 1) * L - 1, (nc1 + 1) * L};
+            for (int d = 0; d < NDIAG; ++d) S->cm_off[d] = off[d];
+            S->cm_halo = ((size_t)off[NDIAG - 1] + TMA_T + 34 + 31) / 32 * 32;
+            a |= S->cm_A.alloc((size_t)NDIAG * S->ld, S->cm_halo);
+            DBuf<double> *cv[] = {&S->cm_diag, &S->cm_rhs, &S->cm_x, &S->cm_r, &S->cm_p0, &S->cm_p1, &S->cm_bv};
+            for (auto *b : cv) a |= b->alloc(N, S->cm_halo);
+            if (!S->dd) a |= S->cm_z.alloc(N, S->cm_halo);      // partitioned: z lives in the peer-mapped communication block (below)
+            S->cm_on = !a;
+            if (S->cm_on && tma) {
+                const TmaLayout ly = tma_layout(off, L);
+                S->tma_smem = (size_t)TMA_NS * ly.total * sizeof(double);
+                int optin = 0;
+                CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, p.device));
+                cudaFuncAttributes at;
+                CK(cudaFuncGetAttributes(&at, (const void *)k_pcg_tma<false>));
+                if (S->tma_smem + at.sharedSizeBytes <= (size_t)optin) {
+                    CK(cudaFuncSetAttribute((const void *)k_pcg_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->tma_smem));
+                    CK(cudaFuncSetAttribute((const void *)k_pcg_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->tma_smem));
+                    S->tma_on = true;
+                }
+            }
+            if (S->dd && !S->tma_on) FAIL(-2, "row-block partition: the node layers do not fit the shared-memory tiles of k_pcg_tma (NSTR = %d); set CATHY_PCG_CM=0 for the layer-major kernel", S->nstr);
+        }
+    }
     if (S->newton) {
         // Ju and Jl share ONE allocation ([halo | 8 upper diagonals | halo][halo | 8 lower | halo]) so that one L2 access-policy
         // window covers the whole Jacobian (see solve_system_newton); Jl is a non-owning view
@@ -4128,8 +4273,17 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
         S->comm = c;
         const long long hcap = (long long)DD_W * (S->nstr + 1) * S->nc1;
         c->bytes = sizeof(DDBox) + (size_t)4 * hcap * sizeof(double);
+        if (S->cm_on) c->bytes += ((size_t)N + 2 * S->cm_halo) * sizeof(double);      // z of k_pcg_tma: the neighbours store their boundary rows into its ghost rows
         CK(cudaMalloc(&c->base, c->bytes));
         CK(cudaMemset(c->base, 0, c->bytes));
+        if (S->cm_on) {
+            S->cm_z.release();
+            S->cm_z.p = (double *)((char *)c->base + sizeof(DDBox) + (size_t)4 * hcap * sizeof(double)) + S->cm_halo;      // non-owning view
+            S->cm_z.n = (size_t)N; S->cm_z.pad = S->cm_halo;
+            const int rowlen = S->nc1 * (S->nstr + 1);
+            const int geom[4] = {S->own_a * rowlen, S->own_b * rowlen, N, DD_W * rowlen};
+            CK(cudaMemcpy(&((DDBox *)c->base)->geom[0], geom, sizeof geom, cudaMemcpyHostToDevice));
+        }
         CK(cudaMalloc((void **)&c->seq, 2 * sizeof(unsigned int))); CK(cudaMemset(c->seq, 0, 2 * sizeof(unsigned int)));
         CK(cudaMalloc((void **)&c->err, sizeof(int))); CK(cudaMemset(c->err, 0, sizeof(int)));
         CK(cudaMalloc((void **)&c->recv_counter, sizeof(unsigned int))); CK(cudaMemset(c->recv_counter, 0, sizeof(unsigned int)));
@@ -4656,6 +4810,25 @@ int32_t cathy_set_atm_table(CathySim *S, int32_t natm, const double *times, cons
 }
 
 // ---- row-block partition: peer-memory wiring -------------------------------------------------
+// k_pcg_tma: where the neighbours' z arrays are and where my boundary rows go in them (their geometry sits in their DDBox)
+static int dd_wire_tma(CathySim *S)
+{
+    if (!S->cm_on) return 0;
+    const DDCtx &x = S->comm->ctx;
+    const long long hcap = x.hcap;
+    auto zof = [&](DDBox *box) { return (double *)((char *)box + sizeof(DDBox) + (size_t)4 * hcap * sizeof(double)) + S->cm_halo; };
+    int g[4];
+    S->tma_zpeer_n = S->tma_zpeer_s = nullptr;
+    if (x.north >= 0) {
+        CK(cudaMemcpy(g, &x.peer[x.north]->geom[0], sizeof g, cudaMemcpyDeviceToHost));
+        S->tma_zpeer_n = zof(x.peer[x.north]); S->tma_ndst0 = g[1];                 // its south ghost rows start at its hi
+    }
+    if (x.south >= 0) {
+        CK(cudaMemcpy(g, &x.peer[x.south]->geom[0], sizeof g, cudaMemcpyDeviceToHost));
+        S->tma_zpeer_s = zof(x.peer[x.south]); S->tma_sdst0 = (long long)g[0] - g[3];   // its north ghost rows end at its lo
+    }
+    return 0;
+}
 int32_t cathy_dd_export(CathySim *S, void *handle64)
 {
     if (!S->dd) FAIL(-1, "cathy_dd_export: the handle is not partitioned (dd_world = 1)");
@@ -4679,6 +4852,7 @@ int32_t cathy_dd_connect(CathySim *S, const void *handles)
         c->ctx.inbox_peer[r] = (double *)((char *)ptr + sizeof(DDBox));
     }
     c->connected = true;
+    { int rct = dd_wire_tma(S); if (rct) return rct; }
     return init_atm_and_storage(S);      // collective: ATMONE / MBINIT / initial storage sums are combined across the ranks
 }
 // Same-process variant (all ranks are handles of ONE process, e.g. one host thread per GPU): direct pointers, no IPC.
@@ -4700,7 +4874,7 @@ int32_t cathy_dd_connect_local(CathySim *S, CathySim *const *all)
         c->ctx.inbox_peer[r] = (double *)((char *)o->comm->base + sizeof(DDBox));
     }
     c->connected = true;
-    return 0;
+    return dd_wire_tma(S);
 }
 // second half of the local connection: the collective part of the set-up, to be called concurrently (one thread per handle)
 int32_t cathy_dd_start(CathySim *S)
@@ -4712,7 +4886,7 @@ int32_t cathy_dd_start(CathySim *S)
 int32_t cathy_solver_info(const CathySim *S, int64_t info[4])
 {
     const bool res = !S->dd && (S->pcg_algo == 3 || S->pcg_algo == 4) && S->res_rows > 0;
-    info[0] = S->newton ? (S->bres_rows > 0 ? 11 : 10) : res ? S->pcg_algo : (!S->dd && S->pcg_algo == 2) ? 2 : 1;
+    info[0] = S->newton ? (S->bres_rows > 0 ? 11 : 10) : res ? S->pcg_algo : (!S->dd && S->pcg_algo == 2) ? 2 : S->tma_on ? 6 : S->cm_on ? 5 : 1;
     info[1] = res ? S->res_rows : (S->newton ? S->bres_rows : 0); info[2] = res ? S->res_x : 0; info[3] = S->grid_pcg;
     return 0;
 }

@@ -103,8 +103,22 @@ def test_pcg_kernel_variants_agree(gpu_lib, tmp_path, monkeypatch, size):
         sim.debug_assemble(7.0)
         sols[algo] = sim.debug_solve()[:3]
         sim.close()
+    # the streaming kernels on the column-major permutation of the same system (k' = s L + l; default for meshes beyond the resident
+    # kernels' reach and for partitioned runs): other stencil offsets, other summation order, same recurrence.  5 = k_pcg (direct
+    # loads), 6 = k_pcg_tma (tiles staged by TMA bulk copies: windows, lower-triangle slices, two-stage mbarrier pipeline)
+    monkeypatch.setenv("CATHY_PCG_ALGO", "1")
+    monkeypatch.setenv("CATHY_PCG_CM", "1")
+    for kern, tma in ((5, "0"), (6, "1")):
+        monkeypatch.setenv("CATHY_PCG_TMA", tma)
+        sim = Simulation(gpu_lib, prj)
+        assert sim.solver_info()["kernel"] == kern
+        sim.debug_assemble(7.0)
+        sols[kern] = sim.debug_solve()[:3]
+        sim.close()
+    monkeypatch.delenv("CATHY_PCG_CM")
+    monkeypatch.delenv("CATHY_PCG_TMA")
     x1, n1, e1 = sols[1]
-    for algo in (3, 4):
+    for algo in (3, 4, 5, 6):
         x, nit, err = sols[algo]
         assert abs(nit - n1) <= 1 and err <= 1e-10
         assert np.max(np.abs(x - x1)) <= 1e-10 * max(np.abs(x1).max(), 1e-300), (algo, np.abs(x - x1).max(), np.abs(x1).max())

@@ -29,12 +29,16 @@ def test_partitioned_run_equals_single_domain(gpu_lib, world):
     prj = _project()
     os.environ["CATHY_PCG_GRID"] = str(148 // (world + 1))      # world partitioned kernels + nothing else must be co-resident
     try:
-        os.environ["CATHY_PCG_ALGO"] = "1"      # the streamed-vector k_pcg: the recurrence the partitioned kernel shares, so that PCG
-        try:                                    # iteration counts are comparable one to one (the default k_pcg_res forms B = A z + beta B)
+        os.environ["CATHY_PCG_ALGO"] = "1"      # the unpartitioned reference runs the SAME kernel as the ranks (k_pcg_tma on the column-major
+        os.environ["CATHY_PCG_CM"] = "1"        # permutation), so that PCG iteration counts are comparable one to one
+        try:
             ref = Simulation(gpu_lib, prj)
+            assert ref.solver_info()["kernel"] == 6
         finally:
             os.environ.pop("CATHY_PCG_ALGO", None)
+            os.environ.pop("CATHY_PCG_CM", None)
         part = LocalPartition(gpu_lib, prj, [0] * world)
+        assert all(s_.solver_info()["kernel"] == 6 for s_ in part.sims)
         assert sum(i["own_row1"] - i["own_row0"] for i in part.infos) == prj.nrow + 1
         k = 0
         while True:
