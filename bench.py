@@ -391,7 +391,8 @@ def run_roofline_hbm(ctx: Ctx, args) -> dict:
     ach = b / (pcg_ms / 1e3) / 1e9
     sp = SPMV_BYTES_PER_ROW * n / (spmv_ms / 1e3) / 1e9
     return {"bound": "hbm", "mesh": "400x400 DEM x 20 layers, %d nodes: matrix %.0f MB, %.0f MB touched per PCG iteration (L2: 126 MB)" % (n, n * 64 / 1e6, n * 168 / 1e6),
-            "kernel": {1: "k_pcg (streaming)", 5: "k_pcg_tma (streaming, cp.async.bulk staged)"}.get(solver["kernel"], "kernel %d" % solver["kernel"]),
+            "kernel": {1: "k_pcg (streaming, layer-major)", 5: "k_pcg on the column-major permutation (streaming, direct loads)",
+                       6: "k_pcg_tma (column-major permutation; tiles staged by cp.async.bulk + mbarrier, producer warp, round-robin tiles)"}.get(solver["kernel"], "kernel %d" % solver["kernel"]),
             "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
             "bytes_per_row_iter": PCG_BYTES_PER_ROW_ITER, "us_per_iter": 1e3 * pcg_ms / max(iters, 1), "pcg_iters": iters, "pcg_solves": solves,
             "flush": "inputs larger than L2; 4.3 GB of assembly traffic between two solves",
@@ -588,7 +589,7 @@ def run_partitioned(ctx: Ctx, args, size, steps: int, warm: int) -> dict:
            "step_sequence": seq,
            "device_ms_per_step": 1e3 * ctx.rmax(gpu_ms / 1e3) / steps, "pcg_us_per_iteration": 1e3 * pcg_ms_max / max(pcg_iters, 1),
            "gpu_launches": launches, "setup_s_per_rank": ctx.rmax(t_build), "io_s_per_rank": ctx.rmax(t_io), "clocks": sampler.summary(),
-           "roofline": {"bound": "hbm", "kernel": "solver kernel %d (persistent PCG, per rank; 1 = k_pcg, 5 = k_pcg_tma)" % solver["kernel"], "achieved": achieved, "peak": peak, "peak_source": peak_src,
+           "roofline": {"bound": "hbm", "kernel": "solver kernel %d (persistent PCG, per rank; 1 = k_pcg layer-major, 5 = k_pcg column-major, 6 = k_pcg_tma column-major with TMA-staged tiles)" % solver["kernel"], "achieved": achieved, "peak": peak, "peak_source": peak_src,
                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "bytes_per_row_iter": PCG_BYTES_PER_ROW_ITER,
                         "served_from": "HBM (per-rank matrix %.0f MB)" % (n_local * 64 / 1e6), "traffic": None}}
     sim.close()
