@@ -2281,8 +2281,9 @@ __device__ __forceinline__ void route_cell(const RouteArgs &a, const RouteCell &
         if (cu > best_cu || (cu == best_cu && sq > best_seq)) { best_cu = cu; best_ak = ak; best_seq = sq; }
     }
 }
-__global__ void __launch_bounds__(ROUTE_BLOCK) k_route(RouteArgs a)
+__global__ void __launch_bounds__(ROUTE_BLOCK) k_route(RouteArgs a, const int *handled)
 {
+    if (handled && *handled) return;             // k_route_wave (route_wave.cuh) did this step
     __shared__ double s_cu[32], s_ak[32];
     __shared__ int s_seq[32];
     __shared__ double s_akmax;
@@ -2358,6 +2359,8 @@ __global__ void __launch_bounds__(ROUTE_BLOCK) k_route(RouteArgs a)
     }
     if (threadIdx.x == 0) { *a.ak_max = s_akmax; *a.nsurf_out = nsurf; }
 }
+
+#include "route_wave.cuh"
 
 // end-of-step surface bookkeeping: PONDNOD=0 where PNEW<=0 (SRC/cathy_main.f:3181-3184)
 __global__ void k_pond_zero(int nnod, const double *__restrict__ pnew, double *__restrict__ pondnod)
@@ -2767,6 +2770,13 @@ struct CathySim {
     DBuf<unsigned char> don_dir;
     DBuf<double> r_w1, r_w2, r_sl1, r_sl2, r_epl1, r_epl2, r_ks1, r_ks2, r_ws1, r_ws2, r_b1, r_y1, r_nrc, r_ckf1, r_ckf2, r_dhd1, r_dhd2;
     bool route_static_done = false;
+    DBuf<RouteS> r_rs;               // k_route_wave: per-cell records in level order, overflow donor codes, histories
+    DBuf<int> r_dcx, r_handled;
+    DBuf<double> r_qo, r_qin_ring, r_vol_ring, r_best;
+    DBuf<unsigned long long> r_prof;
+    bool route_wave = false;
+    int route_last_nsurf = 1;        // sub-steps of the previous routing call (sizes the next launch)
+    int route_cluster = 8;           // CTAs of the k_route_wave cluster (16 when the device allows the non-portable size)
     DBuf<double> sw_sn, q_in_kk, q_in_kkp1, q_out_kk_1, q_out_kk_2, q_out_kkp1_1, q_out_kkp1_2, volume_kk, volume_kkp1, h_water;
     DBuf<double> q_in_kk_sav, q_out_kk_1_sav, q_out_kk_2_sav, volume_kk_sav, q_in_kk_p, q_out_kk_1_p, q_out_kk_2_p, volume_kk_p;
     DBuf<double> d_akmax;   // [3]: ak_max, ak_max_p, ak_max_sav
@@ -3183,7 +3193,60 @@ static int build_surface(CathySim *S)
             }
     }
     S->nlevel = nlev; S->outlet_cell = qoi[nc - 1];
+    if (getenv("CATHY_ROUTE_DEBUG")) {
+        int big = 0, mx = 0; long long sq = 0;
+        for (int l = 0; l < nlev; ++l) { const int c = lptr[l + 1] - lptr[l]; mx = std::max(mx, c); if (c > 1024) ++big; sq += (long long)c * c; }
+        fprintf(stderr, "routing: %d cells, %d levels, largest level %d cells, %d levels > 1024 cells, level 0..7:", nc, nlev, mx, big);
+        for (int l = 0; l < std::min(nlev, 8); ++l) fprintf(stderr, " %d", lptr[l + 1] - lptr[l]);
+        fprintf(stderr, " ... last 4:");
+        for (int l = std::max(0, nlev - 4); l < nlev; ++l) fprintf(stderr, " %d", lptr[l + 1] - lptr[l]);
+        fprintf(stderr, "\n");
+    }
     int rc = 0;
+    {   // k_route_wave: one record per cell in level order; donors referenced by level-order position
+        std::vector<int> posof(nc);
+        for (int q = 0; q < nc; ++q) posof[lcell[q]] = q;
+        std::vector<double> epl1 = to_route(S, p.dtm_epl_1), epl2 = to_route(S, p.dtm_epl_2), nrcv = to_route(S, p.dtm_nrc), b1v = to_route(S, p.dtm_b1_sf), y1v = to_route(S, p.dtm_y1_sf);
+        std::vector<RouteS> rs(nc);
+        std::vector<int> dcx;
+        for (int q = 0; q < nc; ++q) {
+            const int ib = lcell[q];
+            RouteS &R = rs[q];
+            memset(&R, 0, sizeof R);
+            R.w[0] = w1[ib]; R.w[1] = w2[ib]; R.epl[0] = epl1[ib]; R.epl[1] = epl2[ib]; R.nrc = nrcv[ib]; R.b1 = b1v[ib]; R.y1 = y1v[ib];
+            R.ib = ib; R.seq = seq[ib]; R.nd = dptr[ib + 1] - dptr[ib]; R.d0 = (int)dcx.size();
+            for (int j = 0; j < R.nd; ++j) {
+                const int dn = dptr[ib] + j, code = (posof[dcell[dn]] << 1) | ddir[dn];
+                if (j < 4) R.dc[j] = code; else dcx.push_back(code);
+            }
+        }
+        if (dcx.empty()) dcx.push_back(0);
+        const char *e = getenv("CATHY_ROUTE_WAVE");
+        S->route_wave = !(e && atoi(e) == 0) && (long long)nc < (1LL << 30);
+        if (S->route_wave) {
+            int rw = 0;
+            rw |= S->r_rs.upload(rs); rw |= S->r_dcx.upload(dcx); rw |= S->r_handled.alloc(1);
+            rw |= S->r_qo.alloc((size_t)2 * ROUTE_NSMAX * nc); rw |= S->r_qin_ring.alloc((size_t)2 * nc); rw |= S->r_vol_ring.alloc((size_t)2 * nc);
+            rw |= S->r_best.alloc(3 * 16);
+            if (rw) { cudaGetLastError(); S->route_wave = false; }      // no memory for the histories: k_route alone
+            else {
+                // cluster of 16 CTAs if this device schedules it (non-portable size), else 8
+                S->route_cluster = 8;
+                if (const char *ec = getenv("CATHY_ROUTE_CLUSTER")) S->route_cluster = std::max(1, std::min(16, atoi(ec)));
+                else if (cudaFuncSetAttribute((const void *)k_route_wave, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+                    cudaLaunchConfig_t cfg = {};
+                    cudaLaunchAttribute at[1];
+                    cfg.gridDim = dim3(16); cfg.blockDim = dim3(ROUTE_WBLOCK);
+                    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    cfg.attrs = at; cfg.numAttrs = 1;
+                    int ncl = 0;
+                    if (cudaOccupancyMaxActiveClusters(&ncl, (const void *)k_route_wave, &cfg) == cudaSuccess && ncl >= 1) S->route_cluster = 16;
+                    else cudaGetLastError();
+                } else cudaGetLastError();
+                if (S->route_cluster > 8) cudaFuncSetAttribute((const void *)k_route_wave, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            }
+        }
+    }
     rc |= S->don_code.upload(dcode);
     rc |= S->lv_ptr.upload(lptr); rc |= S->lv_cell.upload(lcell); rc |= S->seqpos.upload(seq); rc |= S->don_ptr.upload(dptr);
     rc |= S->don_cell.upload(dcell); rc |= S->don_dir.upload(ddir);
@@ -3831,8 +3894,38 @@ static int surf_flowtra(CathySim *S)
     a.q_out_kkp1_1 = S->q_out_kkp1_1.p; a.q_out_kkp1_2 = S->q_out_kkp1_2.p; a.volume_kk = S->volume_kk.p; a.volume_kkp1 = S->volume_kkp1.p;
     a.h_water = S->h_water.p; a.ak_max = S->d_akmax.p; a.nsurf_out = S->d_nsurf.p; a.deltat = S->deltat; a.cellarea = S->p.dx * S->p.dy;
     a.ckf1 = S->r_ckf1.p; a.ckf2 = S->r_ckf2.p; a.dhd1 = S->r_dhd1.p; a.dhd2 = S->r_dhd2.p;
-    if (!S->route_static_done) { LAUNCH(S, k_route_static, nblk(S->ncell, S->grid_n), RED_BLOCK, a); S->route_static_done = true; }
-    LAUNCH(S, k_route, 1, ROUTE_BLOCK, a);
+    if (!S->route_static_done) {
+        LAUNCH(S, k_route_static, nblk(S->ncell, S->grid_n), RED_BLOCK, a);
+        if (S->route_wave) LAUNCH(S, k_route_fill_static, nblk(S->ncell, S->grid_n), RED_BLOCK, S->ncell, S->r_rs.p, S->r_ckf1.p, S->r_ckf2.p, S->r_dhd1.p, S->r_dhd2.p);
+        S->route_static_done = true;
+    }
+    const bool wave = S->route_wave && (S->route_last_nsurf >= 2 || getenv("CATHY_ROUTE_WAVE_ALWAYS"));
+    if (S->route_wave) CK(cudaMemsetAsync(S->r_handled.p, 0, sizeof(int), S->st));
+    if (wave) {
+        RouteWArgs wa;
+        wa.r = a; wa.rs = S->r_rs.p; wa.dcx = S->r_dcx.p; wa.qo = S->r_qo.p; wa.qin_ring = S->r_qin_ring.p; wa.vol_ring = S->r_vol_ring.p;
+        wa.handled = S->r_handled.p; wa.nsmax = ROUTE_NSMAX; wa.best = S->r_best.p;
+        wa.prof = nullptr;
+        if (getenv("CATHY_ROUTE_DEBUG")) {
+            if (!S->r_prof.p) S->r_prof.alloc(1024);
+            wa.prof = S->r_prof.p;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute at[1];
+        // tasks per wavefront ~ sub-steps x cells per level x 4 lanes: one CTA while they fit it (no cluster barrier, L1 prefetch),
+        // else as many CTAs of the cluster as they fill
+        const long long lanes = 4LL * std::max(1, S->route_last_nsurf) * ((S->ncell + S->nlevel - 1) / std::max(1, S->nlevel));
+        int ccl = (int)std::min<long long>(S->route_cluster, std::max<long long>(1, (lanes + ROUTE_WBLOCK - 1) / ROUTE_WBLOCK));
+        while (ccl & (ccl - 1)) ++ccl;               // power of two
+        ccl = std::min(ccl, S->route_cluster);
+        cfg.gridDim = dim3(ccl); cfg.blockDim = dim3(ROUTE_WBLOCK); cfg.stream = S->st;
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = ccl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, k_route_wave, wa));
+        S->launches++;
+    }
+    LAUNCH(S, k_route, 1, ROUTE_BLOCK, a, S->route_wave ? S->r_handled.p : (const int *)nullptr);
     LAUNCH(S, k_cell_nod, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nrow, S->ncol, S->h_water.p, S->pondnod.p);
     cudaMemsetAsync(S->d_flags.p, 0, sizeof(int), S->st);
     LAUNCH(S, k_pondupd, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, S->p.pondh_min, 1.0 / S->deltat, S->pondnod.p, S->arenod.p, S->atmpot.p,
@@ -3842,6 +3935,7 @@ static int surf_flowtra(CathySim *S)
     CK(cudaMemcpyAsync(&h[1], S->d_nsurf.p, sizeof(int), cudaMemcpyDeviceToHost, S->st));
     CK(cudaStreamSynchronize(S->st));
     S->ponding = h[0];
+    S->route_last_nsurf = std::max(1, h[1]);
     return h[1];
 }
 static void copy_cells(CathySim *S, DBuf<double> &dst, DBuf<double> &src) { cudaMemcpyAsync(dst.p, src.p, (size_t)S->ncell * sizeof(double), cudaMemcpyDeviceToDevice, S->st); }
@@ -3890,6 +3984,15 @@ void cathy_destroy(CathySim *S)
     if (!S) return;
     cudaSetDevice(S->p.device);
     if (S->st) cudaStreamSynchronize(S->st);
+    if (S->r_prof.p) {
+        std::vector<unsigned long long> h(1024);
+        if (cudaMemcpy(h.data(), S->r_prof.p, 1024 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            fprintf(stderr, "k_route_wave, last launch: ns per wavefront:");
+            for (int w = 1; w < 1024 && h[w] > h[w - 1]; ++w) if (w < 12 || w % 50 == 0) fprintf(stderr, " [%d] %llu", w, h[w] - h[w - 1]);
+            fprintf(stderr, "\n");
+        }
+        S->r_prof.release();
+    }
     if (S->bres_prof.p) {
         unsigned long long h[16];
         if (cudaMemcpy(h, S->bres_prof.p, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess && h[15] > 0 && S->tma_on)
@@ -3928,6 +4031,7 @@ void cathy_destroy(CathySim *S)
       for (auto *b : bb) b->release(); }
     S->contp_flag.release(); S->contq_flag.release(); S->contp_val.release(); S->qneu.release(); S->qlist.release(); S->qpnew.release();
     S->qpold.release(); S->kznod.release(); S->bcsum.release(); S->contp_list.release();
+    S->r_rs.release(); S->r_dcx.release(); S->r_handled.release(); S->r_qo.release(); S->r_qin_ring.release(); S->r_vol_ring.release(); S->r_best.release();
     S->d_counter.release(); S->tet.release(); S->don_dir.release(); S->npart.release(); S->spart.release(); S->d_iter.release(); S->d_step.release();
     if (S->comm) {
         for (int r = 0; r < DD_MAXW; ++r) if (S->comm->opened[r]) cudaIpcCloseMemHandle(S->comm->peer_base[r]);
@@ -3971,7 +4075,7 @@ static int preload_kernels()
                          (const void *)k_div_area, (const void *)k_nod_cell, (const void *)k_cell_nod, (const void *)k_route, (const void *)k_route_static, (const void *)k_pond_zero,
                          (const void *)k_step_partial, (const void *)k_step_final, (const void *)k_weight, (const void *)k_atmone, (const void *)k_mbinit,
                          (const void *)k_pack_col, (const void *)k_unpack_col, (const void *)k_vel3d, (const void *)k_vnod3d, (const void *)k_recharge, (const void *)k_wtdepth, (const void *)k_curves_alt, (const void *)k_chvelo_alt, (const void *)k_curves_xvg, (const void *)k_chvelo_xvg,
-                         (const void *)k_curves_newton_alt, (const void *)k_sw_pair_alt, (const void *)k_relax, (const void *)k_pcg_res<1024>, (const void *)k_permute_cols, (const void *)k_unpermute_cols, (const void *)k_pcg_tma<true>, (const void *)k_pcg_tma<false>};
+                         (const void *)k_curves_newton_alt, (const void *)k_sw_pair_alt, (const void *)k_relax, (const void *)k_pcg_res<1024>, (const void *)k_permute_cols, (const void *)k_unpermute_cols, (const void *)k_pcg_tma<true>, (const void *)k_pcg_tma<false>, (const void *)k_route_wave, (const void *)k_route_fill_static};
     for (const void *f : fns) CK(cudaFuncGetAttributes(&at, f));
     done = true;
     return 0;
