@@ -37,6 +37,8 @@ struct BresArgs {
     int rows_cta, nl, cols_cta;     // rows per CTA (= cols_cta * nl, even), node layers, columns per CTA
     int zigzag;
     unsigned long long *prof;       // diagnostic (CATHY_BRES_PROF=1): ns spent by CTA 0 in each phase, accumulated over all solves
+    const unsigned char *symf;      // [CTA][pass][warp]: 1 = for the 64 rows of that warp-pass every lower-triangle entry equals its transpose
+                                    // (k_bres_sym_flags): the product reads the upper arrays instead -- see row_pair_n
     int prefetch;                   // 1: L2 prefetch of the matrix streams of the thread's next pass
     int point;                      // 1: point Jacobi instead of the line blocks (diagnostic, CATHY_BRES_POINT=1)
 };
@@ -173,6 +175,35 @@ __device__ __forceinline__ void line_apply_inplace(const BresArgs &a, double *v,
     }
 }
 
+// Where the derivative part of the Jacobian vanishes (saturated zones: d kr / d psi = d eta / d psi = 0, SRC/assnew.f) J is
+// symmetric, J(k, k - o) = J(k - o, k): the product can take the lower-triangle entry of row k from the UPPER array at k - o, which
+// another row streams anyway.  One flag per group of 64 rows (a warp-pass of k_bicgstab_res): on a fully saturated system (the coupled
+// storm of BASELINE config 3) the solve then touches 8 diagonals (54 MB at 848 k rows, L2-resident) instead of 15 (102 MB, streamed
+// from HBM twice per iteration).  Same arithmetic, same operands bit for bit -- the flag only says where they are equal.
+__global__ void k_bres_sym_flags(int n, int rows_cta, int npass, Diag U, Diag L, unsigned char *flags)
+{
+    // one warp per group; group g = (cta, pass, warp): rows cta * rows_cta + pass * 2048 + warp * 64 + [0, 64)
+    const int lane = threadIdx.x & 31;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long ngroup = (long long)gridDim.y * npass * 32;
+    (void)ngroup;
+    for (long long g = gw; g < (long long)((n + rows_cta - 1) / rows_cta) * npass * 32; g += nwarp) {
+        const int cta = (int)(g / (npass * 32)), rem = (int)(g % (npass * 32)), pass = rem >> 5, warp = rem & 31;
+        const int i0 = pass * 2048 + warp * 64, cnt = min(rows_cta, n - cta * rows_cta);
+        bool ok = true;
+        for (int q = 0; q < 2; ++q) {
+            const int i = i0 + 2 * lane + q;
+            if (i < cnt) {
+                const int k = cta * rows_cta + i;
+#pragma unroll
+                for (int d = 1; d < NDIAG; ++d) { const int c = k - U.off[d]; ok = ok && (L.d[d][c] == U.d[d][c]); }
+            }
+        }
+        ok = __all_sync(0xffffffffu, ok);
+        if (lane == 0) flags[g] = ok ? 1 : 0;
+    }
+}
+
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define BRES_TICK(slot)                                                                         \
     do {                                                                                        \
@@ -196,8 +227,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab_res(BresArgs a)
     const double *__restrict__ di = a.dinv;
     const int o2 = a.U.off[2], o4 = a.U.off[4], o6 = a.U.off[6];
     const int last = (cnt - 1) & ~1;
-    const int npass = (cnt + 2 * BLOCK - 1) / (2 * BLOCK);
+    const int npass = (cnt + 2 * BLOCK - 1) / (2 * BLOCK), npass_max = (R + 2 * BLOCK - 1) / (2 * BLOCK);
     const bool PF = a.prefetch != 0;
+    const unsigned char *__restrict__ symf = a.symf + (size_t)blockIdx.x * npass_max * 32;
     double in[5] = {0, 0, 0, 0, 0}, out[5];
     // ---- x0 = D^-1 b, ||b_free||^2, Dirichlet rows of this thread as a bit mask (pass j: rows 2 tid + 2 BLOCK j + {0,1} -> bits 2j, 2j+1)
     unsigned int dmask = 0;
@@ -239,7 +271,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab_res(BresArgs a)
         const bool ehi = lane == 31 || i_own + 2 >= cnt, elo = lane == 0;
         const int k = row0 + i;
         double a0, a1;
-        row_pair_n<PAR>(a.U, a.L, a.x, k, elo, ehi, o2, o4, o6, a0, a1);
+        row_pair_n<PAR>(a.U, symf[j * 32 + (tid >> 5)] ? a.U : a.L, a.x, k, elo, ehi, o2, o4, o6, a0, a1);
         if (act) {
             const double r0 = ((dmask >> (2 * j)) & 1u) ? 0.0 : a.rhs[k] - a0;
             const double r1 = (!ok1 || ((dmask >> (2 * j + 1)) & 1u)) ? 0.0 : a.rhs[k + 1] - a1;
@@ -273,7 +305,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab_res(BresArgs a)
             const int k = row0 + i;
             if (PF && i_own + 2 * BLOCK < cnt) prefetch_pair_n(a.U, a.L, k + 2 * BLOCK);
             double a0, a1;
-            row_pair_n<PAR>(a.U, a.L, a.ph, k, elo, ehi, o2, o4, o6, a0, a1);
+            row_pair_n<PAR>(a.U, symf[j * 32 + (tid >> 5)] ? a.U : a.L, a.ph, k, elo, ehi, o2, o4, o6, a0, a1);
             if (act) {
                 if ((dmask >> (2 * j)) & 1u) a0 = 0.0;
                 if ((dmask >> (2 * j + 1)) & 1u) a1 = 0.0;
@@ -323,7 +355,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_bicgstab_res(BresArgs a)
             const int k = row0 + i;
             if (PF) { const int in_ = a.zigzag ? i_own - 2 * BLOCK : i_own + 2 * BLOCK; if (in_ >= 0 && in_ < cnt) prefetch_pair_n(a.U, a.L, row0 + in_); }
             double a0, a1;
-            row_pair_n<PAR>(a.U, a.L, a.sh, k, elo, ehi, o2, o4, o6, a0, a1);
+            row_pair_n<PAR>(a.U, symf[j * 32 + (tid >> 5)] ? a.U : a.L, a.sh, k, elo, ehi, o2, o4, o6, a0, a1);
             if (act) {
                 if ((dmask >> (2 * j)) & 1u) a0 = 0.0;
                 if ((dmask >> (2 * j + 1)) & 1u) a1 = 0.0;

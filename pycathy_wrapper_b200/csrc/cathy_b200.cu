@@ -2743,6 +2743,7 @@ struct CathySim {
     size_t bres_halo = 0;
     DBuf<double> bres_u, bres_l, bres_rhs, bres_dinv, bres_x, bres_ph, bres_sh, bres_rt, bres_p;
     size_t bres_smem = 0;
+    DBuf<unsigned char> bres_symf;           // k_bres_sym_flags: one byte per (CTA, pass, warp) group of 64 rows
     DBuf<unsigned long long> bres_prof;      // CATHY_BRES_PROF=1: per-phase nanoseconds of CTA 0, printed at cathy_destroy
     // ---- row-block partition of one large mesh over several GPUs (BASELINE config 5) ----
     bool dd = false, pcg_shared_gpu = false;
@@ -3665,7 +3666,14 @@ static int solve_system_newton_res(CathySim *S)
     k_permute_cols<<<dim3((NN + 31) / 32, q), 256, tile, S->st>>>(pa);
     CK(cudaGetLastError());
     S->launches++;
+    {   // symmetric groups of 64 rows (CATHY_BRES_SYM=0: never use the upper arrays for the lower triangle)
+        const char *e = getenv("CATHY_BRES_SYM");
+        const int npass = (S->bres_rows + 2047) / 2048, gg = S->pcg_shared_gpu ? S->grid_pcg : S->sms;
+        if (e && atoi(e) == 0) CK(cudaMemsetAsync(S->bres_symf.p, 0, (size_t)gg * npass * 32, S->st));
+        else LAUNCH(S, k_bres_sym_flags, S->grid_n, RED_BLOCK, n, S->bres_rows, npass, U, Lw, S->bres_symf.p);
+    }
     BresArgs a;
+    a.symf = S->bres_symf.p;
     a.n = n; a.itmax = S->itmax_dev; a.tol = S->tol_dev; a.U = U; a.L = Lw;
     a.rhs = S->bres_rhs.p; a.dinv = S->bres_dinv.p; a.x = S->bres_x.p; a.ph = S->bres_ph.p; a.sh = S->bres_sh.p; a.rt = S->bres_rt.p; a.p = S->bres_p.p;
     a.partial = S->partial.p; a.counter = S->d_counter.p; a.epoch0 = S->barrier_epoch; a.out = S->d_iter.p;
@@ -4027,6 +4035,7 @@ void cathy_destroy(CathySim *S)
     { DBuf<double> *cc[] = {&S->cm_A, &S->cm_diag, &S->cm_rhs, &S->cm_x, &S->cm_r, &S->cm_p0, &S->cm_p1, &S->cm_bv};
       for (auto *b : cc) b->release();
       if (!S->dd) S->cm_z.release(); }
+    S->bres_symf.release();
     { DBuf<double> *bb[] = {&S->bres_u, &S->bres_rhs, &S->bres_dinv, &S->bres_x, &S->bres_ph, &S->bres_sh, &S->bres_rt, &S->bres_p};
       for (auto *b : bb) b->release(); }
     S->contp_flag.release(); S->contq_flag.release(); S->contp_val.release(); S->qneu.release(); S->qlist.release(); S->qpnew.release();
@@ -4075,7 +4084,7 @@ static int preload_kernels()
                          (const void *)k_div_area, (const void *)k_nod_cell, (const void *)k_cell_nod, (const void *)k_route, (const void *)k_route_static, (const void *)k_pond_zero,
                          (const void *)k_step_partial, (const void *)k_step_final, (const void *)k_weight, (const void *)k_atmone, (const void *)k_mbinit,
                          (const void *)k_pack_col, (const void *)k_unpack_col, (const void *)k_vel3d, (const void *)k_vnod3d, (const void *)k_recharge, (const void *)k_wtdepth, (const void *)k_curves_alt, (const void *)k_chvelo_alt, (const void *)k_curves_xvg, (const void *)k_chvelo_xvg,
-                         (const void *)k_curves_newton_alt, (const void *)k_sw_pair_alt, (const void *)k_relax, (const void *)k_pcg_res<1024>, (const void *)k_permute_cols, (const void *)k_unpermute_cols, (const void *)k_pcg_tma<true>, (const void *)k_pcg_tma<false>, (const void *)k_route_wave, (const void *)k_route_fill_static};
+                         (const void *)k_curves_newton_alt, (const void *)k_sw_pair_alt, (const void *)k_relax, (const void *)k_pcg_res<1024>, (const void *)k_permute_cols, (const void *)k_unpermute_cols, (const void *)k_pcg_tma<true>, (const void *)k_pcg_tma<false>, (const void *)k_route_wave, (const void *)k_route_fill_static, (const void *)k_bres_sym_flags};
     for (const void *f : fns) CK(cudaFuncGetAttributes(&at, f));
     done = true;
     return 0;
@@ -4349,6 +4358,7 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
                     if (!a) { S->bres_l.p = S->bres_u.p + (size_t)NDIAG * S->ld + 2 * S->bres_halo; S->bres_l.n = (size_t)NDIAG * S->ld; S->bres_l.pad = S->bres_halo; }
                     DBuf<double> *bv[] = {&S->bres_rhs, &S->bres_dinv, &S->bres_x, &S->bres_ph, &S->bres_sh, &S->bres_rt, &S->bres_p};
                     for (auto *b : bv) a |= b->alloc(N, S->bres_halo);
+                    a |= S->bres_symf.alloc((size_t)g * ((rows + 2047) / 2048) * 32);
                 }
             }
         }
