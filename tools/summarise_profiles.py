@@ -1,5 +1,5 @@
 """Turn the ncu outputs of a bench run (gpurun_out/) into the tracked summaries under profiles/.
-usage: python tools/summarise_profiles.py <launch_csv> <tag> [<name>=<ncu-rep> ...]"""
+usage: python tools/summarise_profiles.py <launch_csv> <tag> [<name>=<ncu-rep | raw-page csv> ...]"""
 import csv
 import json
 import subprocess
@@ -40,7 +40,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def ncu_summary(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a raw page already exported on the GPU box (the .ncu-rep files exceed what gpurun brings back) or a report file
+    out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     res = []
