@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CATHY_ABI_VERSION 5
+#define CATHY_ABI_VERSION 6
 #define CATHY_MAXIT 64 /* upper bound on ITUNS kept in a step report (CATHY.H MAXIT=30) */
 
 /* Everything DATIN / INITAL read from the project files (SRC/datin.f:80-514,
@@ -102,6 +102,14 @@ typedef struct CathyProblem {
      * <= 0 selects the documented default: itmxcg_scale 20; tolcg_scale 1 (Picard) / 1e-3 (Newton).  The effective
      * values are returned by cathy_solver_limits and printed in the header of output/iter. */
     double itmxcg_scale;
+    /* --- seepage faces (input/sfbc, SRC/sfvone.f:42-66; parm line ISFONE ISFCVG DUPUIT, SRC/datin.f:110): face i owns the entries
+     * [sf_ptr[i], sf_ptr[i+1]) of sf_node (1-based 3-D node ids, elevations descending along a face).  Only the node set in force
+     * at time 0 is supported (a later record of sfbc must lie beyond TMAX).  Actual seepage nodes (SFEX = 1) are Dirichlet nodes at
+     * psi = 0 (SRC/bcpic.f:46-58), potential ones carry zero flux; EXTALL (SRC/extall.f:32-66) moves nodes between the two sets
+     * after every nonlinear iteration, ISFCVG = 1 makes an unchanged set a condition of convergence (SRC/flow3d.f:237-270). */
+    int32_t nsf, isfone, isfcvg, dupuit;
+    const int32_t *sf_ptr;   /* [nsf+1]                                             */
+    const int32_t *sf_node;  /* [sf_ptr[nsf]]                                       */
 } CathyProblem;
 
 /* One nonlinear iteration line of output/iter (SRC/conver.f:44 FORMAT 1070). */

@@ -12,7 +12,7 @@ import numpy as np
 
 from .project import CathyProject
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAXIT = 64
 _D = C.POINTER(C.c_double)
 _I = C.POINTER(C.c_int32)
@@ -62,6 +62,8 @@ class CathyProblem(C.Structure):
         ("hualfa", C.c_double), ("hubeta", C.c_double), ("hugama", C.c_double), ("hupsia", C.c_double), ("huswr", C.c_double),
         ("hun", C.c_double), ("hua", C.c_double), ("hub", C.c_double), ("bcbeta", C.c_double), ("bcrmc", C.c_double), ("bcpsat", C.c_double),
         ("itmxcg_scale", C.c_double),
+        ("nsf", C.c_int32), ("isfone", C.c_int32), ("isfcvg", C.c_int32), ("dupuit", C.c_int32),
+        ("sf_ptr", _I), ("sf_node", _I),
     ]
 
 
@@ -171,6 +173,14 @@ class ProblemHolder:
         elif int(p["ISIMGR"]) == 2:
             raise ValueError("ISIMGR=2 needs the prepro rasters")
         s.precond, s.device, s.tolcg_scale, s.itmxcg_scale = precond, device, tolcg_scale, itmxcg_scale
+        # seepage faces (input/sfbc, SRC/sfvone.f): list of node-id arrays, one per face
+        faces = getattr(prj, "seepage_faces", None) or []
+        s.nsf = len(faces)
+        s.isfone, s.isfcvg, s.dupuit = int(p.get("ISFONE", 0)), int(p.get("ISFCVG", 0)), int(p.get("DUPUIT", 0))
+        if faces:
+            ptr = np.zeros(len(faces) + 1, dtype=np.int32)
+            ptr[1:] = np.cumsum([len(f) for f in faces])
+            s.sf_ptr, s.sf_node = fi(ptr), fi(np.concatenate([np.asarray(f, dtype=np.int32) for f in faces]))
         if dd is not None:      # (world, rank, row0, row1): row-block partition, see partition_rows()
             s.dd_world, s.dd_rank, s.dd_row0, s.dd_row1 = (int(v) for v in dd)
         else:

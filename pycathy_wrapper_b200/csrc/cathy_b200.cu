@@ -1871,6 +1871,8 @@ __global__ void k_free_drain_list(int nnod, int nstr, const double *__restrict__
     }
 }
 
+#include "seepage.cuh"
+
 // norms (NORMS, SRC/norms.f:18-38) + storage change (STORMB, SRC/stormb.f) + boundary flux sums
 // (FLUXMB, SRC/fluxmb.f:29-88): block partials in fixed order
 struct NormPartial { double pl2, fl2, dstore, pinf, finf, adin, adout, anin, anout; int ik; int pad; };
@@ -2669,6 +2671,15 @@ struct CathySim {
     DBuf<double> contp_val, qneu, qlist, qpnew, qpold, kznod, bcsum;
     DBuf<int> contp_list;
     double ndin = 0, ndout = 0, nnin = 0, nnout = 0, vndin = 0, vndout = 0, vnnin = 0, vnnout = 0;
+    // seepage faces (seepage.cuh): flattened node list and its per-node state
+    int sf_n = 0, sfchek = 0, ksfzer = 1, ksfcv = 0, ksfcvt = 0;
+    DBuf<int> sf_node, sf_ex, sf_exp, sf_exit;
+    DBuf<double> sf_q, sf_qp;
+    DBuf<SfOut> d_sf;
+    double sfflw = 0, sfflwp = 0, vsfflw = 0;
+    // dense Dirichlet flag / value arrays as the kernels see them: prescribed-head nodes (bit 0) and actual seepage nodes (bit 1)
+    const unsigned char *flagp() const { return (have_dir || sf_n > 0) ? contp_flag.p : nullptr; }
+    const double *valp() const { return (have_dir || sf_n > 0) ? contp_val.p : nullptr; }
     int nrow, ncol, nc1, nstr, nnod, n, ntri, nt, ncell;
     bool surf;
     cudaStream_t st = nullptr;
@@ -3374,6 +3385,7 @@ static void atmnxt(CathySim *S)
     if (S->have_dir || S->have_neu)
         LAUNCH(S, k_mark_nonatm, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, S->have_dir ? S->contp_flag.p : nullptr,
                S->have_neu ? S->contq_flag.p : nullptr, S->ifatm.p, (int *)nullptr);
+    if (S->sf_n > 0) LAUNCH(S, k_sf_mark_nonatm, nblk(S->sf_n, S->grid_n), RED_BLOCK, S->sf_n, S->sf_node.p, S->nnod, S->ifatm.p, (int *)nullptr);
 }
 static void atmbak(CathySim *S)
 {
@@ -3422,6 +3434,7 @@ static int assemble_system(CathySim *S, double deltat)
 {
     const int n = S->n;
     S->scaled = false;
+    if (S->sf_n > 0) LAUNCH(S, k_sf_apply, nblk(S->sf_n, S->grid_n), RED_BLOCK, S->sf_n, S->sf_node.p, S->sf_ex.p, S->contp_flag.p, S->contp_val.p);
     Diag A = make_diag(S, S->A.p);
     if (S->cm.ivghu == 1)
         LAUNCH(S, k_curves_xvg, nblk(n, S->grid_n), RED_BLOCK, n, make_soil(S), S->ptnew.p, S->pnew.p, S->ptimep.p, S->timep_dirty, S->sw.p, S->ckrw.p, S->et1.p, S->et2.p,
@@ -3436,7 +3449,7 @@ static int assemble_system(CathySim *S, double deltat)
     if (S->geom.rel) LAUNCH(S, k_assemble_a, nblk(n, 4 * S->grid_n), RED_BLOCK, n, S->plan, S->geom, S->krt.p, S->e1t.p, A, S->grav.p, S->m2.p);
     else LAUNCH(S, k_assemble, nblk(n, 4 * S->grid_n), RED_BLOCK, n, S->plan, S->krt.p, S->e1t.p, A, S->grav.p, S->m2.p);
     LAUNCH(S, k_rhs_lhs, nblk(n, S->grid_n), RED_BLOCK, n, S->nnod, A, S->tetaf, 1.0 / deltat, S->ptnew.p, S->pnew.p, S->ptimep.p, S->swnew.p,
-           S->swtimep.p, S->m2.p, S->m4.p, S->et2.p, S->grav.p, S->ifatm.p, S->have_dir ? S->contp_flag.p : (const unsigned char *)nullptr,
+           S->swtimep.p, S->m2.p, S->m4.p, S->et2.p, S->grav.p, S->ifatm.p, S->flagp(),
            S->have_neu ? S->qneu.p : (const double *)nullptr, S->atmact.p, S->atmold.p, S->qtranie.p, S->rhs.p, S->xt5.p, S->diag_true.p, S->diag_bc.p);
     if (S->tetaf != 1.0)   // off-diagonals of the LHS are TETAF * stiffness (SRC/cfmatp.f:24-26)
         LAUNCH(S, k_scale, nblk((long long)(NDIAG - 1) * S->ld, 8 * S->grid_n), RED_BLOCK, (long long)(NDIAG - 1) * S->ld, S->tetaf, S->A.p + S->ld);
@@ -3455,7 +3468,7 @@ static int solve_system2(CathySim *S)
     a.n = n; a.nnod = S->nnod; a.itmax = S->itmax_dev; a.prefetch = S->pcg_prefetch; a.tol = S->tol_dev;
     a.A = A; a.dis = S->dis.p; a.rhs = S->rhs.p;
     a.y = S->pdiff.p; a.p = S->wbv.p; a.r0 = S->wr.p; a.r1 = S->wz.p; a.w0 = S->wp0.p; a.w1 = S->wp1.p; a.s0 = S->wq0.p; a.s1 = S->wq1.p;
-    a.ifatm = S->ifatm.p; a.contp_flag = S->have_dir ? S->contp_flag.p : nullptr; a.partial = S->partial.p; a.out = S->d_iter.p;
+    a.ifatm = S->ifatm.p; a.contp_flag = S->flagp(); a.partial = S->partial.p; a.out = S->d_iter.p;
     a.counter = S->d_counter.p; a.epoch0 = S->barrier_epoch;
     void *args[] = {&a};
     CK(cudaEventRecord(S->evp0, S->st));
@@ -3571,7 +3584,7 @@ static int solve_system(CathySim *S)
     a.n = S->n; a.nnod = S->nnod; a.itmax = S->itmax_dev; a.tol = S->tol_dev;
     a.A = make_diag(S, S->A.p); a.diag = S->diag_bc.p; a.rhs = S->rhs.p;
     a.x = S->pdiff.p; a.r = S->wr.p; a.z = S->wz.p; a.p0 = S->wp0.p; a.p1 = S->wp1.p; a.bv = S->wbv.p;
-    a.ifatm = S->ifatm.p; a.contp_flag = S->have_dir ? S->contp_flag.p : nullptr; a.partial = S->partial.p; a.out = S->d_iter.p;
+    a.ifatm = S->ifatm.p; a.contp_flag = S->flagp(); a.partial = S->partial.p; a.out = S->d_iter.p;
     a.counter = S->d_counter.p; a.epoch0 = S->barrier_epoch;
     void *args[] = {&a};
     CK(cudaEventRecord(S->evp0, S->st));
@@ -3621,6 +3634,7 @@ static int assemble_system_newton(CathySim *S, double deltat)
     // the previous solve's persisting L2 lines go back to normal, so that the gathers below have the whole cache (the device is idle
     // here: the host has just read the previous iteration's scalars)
     if (S->l2_window && S->l2_reset) cudaCtxResetPersistingL2Cache();
+    if (S->sf_n > 0) LAUNCH(S, k_sf_apply, nblk(S->sf_n, S->grid_n), RED_BLOCK, S->sf_n, S->sf_node.p, S->sf_ex.p, S->contp_flag.p, S->contp_val.p);
     if (S->cm.ivghu != 0)
         LAUNCH(S, k_curves_newton_alt, nblk(n, S->grid_n), RED_BLOCK, n, S->cm, make_soil(S), S->ptnew.p, S->sw.p, S->ckrw.p, S->et1.p, S->dckrw.p, S->detai.p);
     else
@@ -3632,7 +3646,7 @@ static int assemble_system_newton(CathySim *S, double deltat)
     else LAUNCH(S, k_assemble_newton<false>, nblk(n, 4 * S->grid_n), RED_BLOCK, n, S->nt, S->plan, S->geom, S->ell_loc.p, S->krt.p, S->e1t.p, S->ts.p, S->s1.p,
            S->dckrw.p, S->detai.p, A, Ju, Jl, S->grav.p, S->m2.p);
     LAUNCH(S, k_rhs_lhs_newton, nblk(n, S->grid_n), RED_BLOCK, n, S->nnod, A, Ju, Jl, S->tetaf, 1.0 / deltat, S->ptnew.p, S->pnew.p, S->ptimep.p,
-           S->m2.p, S->grav.p, S->ifatm.p, S->have_dir ? S->contp_flag.p : (const unsigned char *)nullptr,
+           S->m2.p, S->grav.p, S->ifatm.p, S->flagp(),
            S->have_neu ? S->qneu.p : (const double *)nullptr, S->atmact.p, S->atmold.p, S->rhs.p, S->xt5.p, S->diag_true.p, S->dinv.p);
     return 0;
 }
@@ -3771,8 +3785,8 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
     Diag A = make_diag(S, S->A.p);
     const bool fuse_update = !S->newton;     // Picard: PNEW += PDIFF happens inside k_norms
     if (!fuse_update)
-    LAUNCH(S, k_update, nblk(n, S->grid_n), RED_BLOCK, n, S->nnod, S->pdiff.p, S->pold.p, S->ifatm.p, S->have_dir ? S->contp_flag.p : (const unsigned char *)nullptr,
-           S->have_dir ? S->contp_val.p : (const double *)nullptr, S->pnew.p);
+    LAUNCH(S, k_update, nblk(n, S->grid_n), RED_BLOCK, n, S->nnod, S->pdiff.p, S->pold.p, S->ifatm.p, S->flagp(),
+           S->valp(), S->pnew.p);
     if (S->newton) {
         Diag Ju = make_diag(S, S->Ju.p), Jl = make_diag(S, S->Jl.p);
         LAUNCH(S, k_bkflux_n, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, Ju, Jl, S->pdiff.p, S->xt5.p, S->ifatm.p, S->tetaf, S->atmold.p, S->atmact.p);
@@ -3796,11 +3810,20 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
         LAUNCH(S, k_flux_sums, 1, RED_BLOCK, m, S->qpnew.p, S->bcsum.p);
     }
     }
+    if (S->sf_n > 0) {   // SFQ of the actual seepage nodes and their sum SFFLW (BKPIC / BKNEW, FLUXMB)
+        if (S->newton) {
+            Diag Ju = make_diag(S, S->Ju.p), Jl = make_diag(S, S->Jl.p);
+            LAUNCH(S, k_sf_flux<true>, 1, RED_BLOCK, S->sf_n, n, S->sf_node.p, S->sf_ex.p, Ju, Jl, (const double *)nullptr, (const double *)nullptr, S->pdiff.p,
+                   S->xt5.p, S->tetaf, S->sf_qp.p, S->sf_q.p, S->d_sf.p);
+        } else
+            LAUNCH(S, k_sf_flux<false>, 1, RED_BLOCK, S->sf_n, n, S->sf_node.p, S->sf_ex.p, A, A, S->diag_true.p, S->scaled ? S->dis.p : (const double *)nullptr,
+                   S->pdiff.p, S->xt5.p, S->tetaf, S->sf_qp.p, S->sf_q.p, S->d_sf.p);
+    }
     if (S->have_neu) LAUNCH(S, k_flux_sums, 1, RED_BLOCK, S->neu.anbc(), S->qlist.p, S->bcsum.p + 2);
     LAUNCH(S, k_norms, S->grid_n, RED_BLOCK, n, S->nnod, S->pnew.p, S->pold.p, S->rhs.p, S->ptimep.p, S->swnew.p, S->swtimep.p, S->volnod.p,
            S->snodi.p, S->pnodi.p, S->ifatm.p, S->atmact.p, S->npart.p, S->dd ? S->own.p : (const unsigned char *)nullptr,
            S->p.nlrelx == 1 ? S->p.omega : 1.0, fuse_update ? S->pdiff.p : (const double *)nullptr,
-           S->have_dir ? S->contp_flag.p : (const unsigned char *)nullptr, S->have_dir ? S->contp_val.p : (const double *)nullptr);
+           S->flagp(), S->valp());
     if (S->p.nlrelx == 1) LAUNCH(S, k_relax, nblk(n, S->grid_n), RED_BLOCK, n, S->p.omega, S->pold.p, S->pnew.p);
     LAUNCH(S, k_norms_final, 1, RED_BLOCK, S->grid_n, S->npart.p, S->pnew.p, S->pold.p, S->d_iter.p);
     if (S->dd) LAUNCH(S, k_dd_combine_iter, 1, 32, S->comm->ctx, S->d_iter.p, S->gnnod, S->grow0 * S->nc1);
@@ -3816,6 +3839,13 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
         }
     };
     if (switch_always) launch_switch();
+    // EXTALL after the switch (SRC/conver.f:76-99); the two touch disjoint nodes (potential seepage nodes on the surface are IFATM = -1),
+    // so it may also run ahead of a switch that the host decides on below
+    SfOut h_sf = {0.0, 0, 0};
+    if (S->sf_n > 0) {
+        LAUNCH(S, k_sf_extall, 1, RED_BLOCK, S->sf_n, S->sf_node.p, S->sf_ex.p, S->sf_exit.p, S->sf_q.p, S->pnew.p, S->d_sf.p);
+        CK(cudaMemcpyAsync(&h_sf, S->d_sf.p, sizeof(SfOut), cudaMemcpyDeviceToHost, S->st));
+    }
     CK(cudaMemcpyAsync(S->h_iter, S->d_iter.p, sizeof(IterOut), cudaMemcpyDeviceToHost, S->st));
     int h_pond = 0;
     if (switch_always && S->surf) CK(cudaMemcpyAsync(&S->h_iter->ponding, S->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, S->st));
@@ -3854,8 +3884,11 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
     S->nnin = S->have_neu ? h_bc[2] : 0.0; S->nnout = S->have_neu ? h_bc[3] : 0.0;
     S->vndin = (S->ndin + S->ndinp) * dm; S->vndout = (S->ndout + S->ndoutp) * dm;
     S->vnnin = (S->nnin + S->nninp) * dm; S->vnnout = (S->nnout + S->nnoutp) * dm;
+    S->sfflw = h_sf.sfflw;
+    S->vsfflw = (S->sfflw + S->sfflwp) * dm;
+    if (S->sf_n > 0) { if (h_sf.ksf > 0) { S->ksfcv++; S->ksfcvt += h_sf.ksf; S->ksfzer = 0; } else S->ksfzer = 1; }
     S->vin = vadin + S->vndin + vanin + S->vnnin + 0.0;
-    S->vout = vadout + S->vndout + vanout + S->vnnout + 0.0 + 0.0;
+    S->vout = vadout + S->vndout + vanout + S->vnnout + S->vsfflw + 0.0;
     S->erras = S->vin + S->vout - S->dstore;
     S->errel = (S->vin + S->vout) != 0.0 ? 100.0 * S->erras / (S->vin + S->vout) : 0.0;
     S->itlin += o.pcg_niter; S->nitert += o.pcg_niter;
@@ -3877,13 +3910,15 @@ static int flow3d(CathySim *S, int *status)
         bool itagen = S->iter < p.ituns;
         bool errgmx = (r->pl2 >= p.ernlmx || r->pinf >= p.ernlmx || r->fl2 >= p.ernlmx || r->finf >= p.ernlmx);
         bool normcv = p.l2norm == 0 ? (r->pinf <= p.toluns) : (r->pl2 <= p.toluns);
-        if (!S->lsfail && !errgmx && !normcv && itagen) {
+        const bool sfwait = S->sf_n > 0 && S->sfchek && !S->ksfzer;   // ISFCVG = 1: the exit points must have settled too (SRC/flow3d.f:237-270)
+        if ((!S->lsfail && !errgmx && !normcv && itagen) || (!S->lsfail && !errgmx && itagen && sfwait)) {
+            if (S->sf_n > 0) cudaMemcpyAsync(S->sf_exit.p, S->sf_ex.p, (size_t)S->sf_n * sizeof(int), cudaMemcpyDeviceToDevice, S->st);
             weight_and_copy(S);
             S->iter++;
             continue;
         }
         S->itrtot += S->iter;
-        if (!S->lsfail && !errgmx && normcv) { *status = 0; return 0; }
+        if (!S->lsfail && !errgmx && normcv && !sfwait) { *status = 0; return 0; }
         *status = S->dtgmin ? 1 : 2;
         return 0;
     }
@@ -3963,6 +3998,11 @@ static void bkstep(CathySim *S)
     S->time = S->time + S->deltat;
     S->kbackt++; S->kback++; S->iter = 1; S->nitert = 0;
     if (S->have_dir) cudaMemcpyAsync(S->qpnew.p, S->qpold.p, (size_t)S->dir.anbc() * sizeof(double), cudaMemcpyDeviceToDevice, S->st);
+    if (S->sf_n > 0) {   // SFEX = SFEXIT = SFEXP, SFQ = SFQP (SRC/bkstep.f:56-66)
+        cudaMemcpyAsync(S->sf_ex.p, S->sf_exp.p, (size_t)S->sf_n * sizeof(int), cudaMemcpyDeviceToDevice, S->st);
+        cudaMemcpyAsync(S->sf_exit.p, S->sf_exp.p, (size_t)S->sf_n * sizeof(int), cudaMemcpyDeviceToDevice, S->st);
+        cudaMemcpyAsync(S->sf_q.p, S->sf_qp.p, (size_t)S->sf_n * sizeof(double), cudaMemcpyDeviceToDevice, S->st);
+    }
     bc_next_both(S, true);
     if (S->time > S->atmtim[1]) atmnxt(S); else atmbak(S);
     if (!S->surf) LAUNCH(S, k_switch_old, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, p.pmin, S->atmpot.p, S->ifatm.p, S->atmact.p, S->pnew.p);
@@ -4040,6 +4080,7 @@ void cathy_destroy(CathySim *S)
       for (auto *b : bb) b->release(); }
     S->contp_flag.release(); S->contq_flag.release(); S->contp_val.release(); S->qneu.release(); S->qlist.release(); S->qpnew.release();
     S->qpold.release(); S->kznod.release(); S->bcsum.release(); S->contp_list.release();
+    S->sf_node.release(); S->sf_ex.release(); S->sf_exp.release(); S->sf_exit.release(); S->sf_q.release(); S->sf_qp.release(); S->d_sf.release();
     S->r_rs.release(); S->r_dcx.release(); S->r_handled.release(); S->r_qo.release(); S->r_qin_ring.release(); S->r_vol_ring.release(); S->r_best.release();
     S->d_counter.release(); S->tet.release(); S->don_dir.release(); S->npart.release(); S->spart.release(); S->d_iter.release(); S->d_step.release();
     if (S->comm) {
@@ -4227,6 +4268,13 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
         S->bc_any = (S->dir.nrec > 0 && S->dir.ptr[S->dir.nrec] > 0) || (S->neu.nrec > 0 && S->neu.ptr[S->neu.nrec] > 0);
         for (int r = 0; r < S->neu.nrec; ++r) if (S->neu.n2d[r] < 0) S->free_drain = true;
     }
+    S->sf_n = (p.nsf > 0 && p.sf_ptr) ? p.sf_ptr[p.nsf] : 0;
+    if (S->sf_n > 0) {   // SFVONE (SRC/sfvone.f:42-66), SFINIT's DUPUIT stop (SRC/sfinit.f:32-36), CONVER's ISFONE stop (SRC/conver.f:77-90)
+        if (S->dd) FAIL(-2, "row-block partition: seepage faces are not partitioned yet");
+        if (p.dupuit != 0) FAIL(-2, "ONLY DUPUIT = 0 FOR THIS CODE (SRC/sfinit.f:36)");
+        if (p.isfone != 0) FAIL(-2, "ISFONE = 1 is disabled in the reference (SRC/conver.f:89)");
+        S->bc_any = true;
+    }
     S->ld = ((size_t)S->n + 31) / 32 * 32;
     if (!S->dd && S->pcg_algo == 4) {
         // k_pcg_res2 pairs the stencil offsets (o, o+1); the prism-split DEM mesh always yields {1 | NC1, NC1+1 | NNOD-NC1-1, NNOD-NC1 | NNOD-1, NNOD}
@@ -4371,6 +4419,22 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
         a |= S->contp_flag.alloc(N); a |= S->contq_flag.alloc(N); a |= S->contp_val.alloc(N); a |= S->qneu.alloc(N);
         a |= S->qlist.alloc(N); a |= S->qpnew.alloc(N); a |= S->qpold.alloc(N); a |= S->contp_list.alloc(N); a |= S->bcsum.alloc(4);
     }
+    if (S->sf_n > 0) {
+        std::vector<int> nodes((size_t)S->sf_n);
+        std::vector<unsigned char> seen((size_t)N, 0);
+        for (int i = 0; i < p.nsf; ++i)
+            for (int j = p.sf_ptr[i]; j < p.sf_ptr[i + 1]; ++j) {
+                int k = p.sf_node[j] - 1;
+                if (k < 0 || k >= N) FAIL(-4, "seepage face %d: node %d out of range", i + 1, p.sf_node[j]);
+                if (seen[k]) FAIL(-4, "seepage face %d: node %d is listed twice", i + 1, p.sf_node[j]);
+                seen[k] = 1;
+                if (j > p.sf_ptr[i] && S->hz[nodes[j - 1]] < S->hz[k])
+                    FAIL(-4, "input error : elevation values not in descending order on seepage face %d", i + 1);
+                nodes[j] = k;
+            }
+        a |= S->sf_node.upload(nodes); a |= S->sf_ex.alloc(S->sf_n); a |= S->sf_exp.alloc(S->sf_n); a |= S->sf_exit.alloc(S->sf_n);
+        a |= S->sf_q.alloc(S->sf_n); a |= S->sf_qp.alloc(S->sf_n); a |= S->d_sf.alloc(1);
+    }
     if (a) FAIL(-101, "device allocation failed (N=%d): %s", N, cudaGetErrorString(cudaGetLastError()));
     if (S->dd) {
         std::vector<unsigned char> own((size_t)N, 0);
@@ -4460,6 +4524,12 @@ static int init_atm_and_storage(CathySim *S)
         CK(cudaMemsetAsync(S->qpold.p, 0, (size_t)N * sizeof(double), S->st));
         CK(cudaMemsetAsync(S->qpnew.p, 0, (size_t)N * sizeof(double), S->st));
     }
+    if (S->sf_n > 0) {   // SFINIT (SRC/inital.f:215-230): SFQP = 0, exit points from the initial heads
+        CK(cudaMemsetAsync(S->sf_q.p, 0, (size_t)S->sf_n * sizeof(double), S->st));
+        CK(cudaMemsetAsync(S->sf_qp.p, 0, (size_t)S->sf_n * sizeof(double), S->st));
+        LAUNCH(S, k_sf_init, nblk(S->sf_n, S->grid_n), RED_BLOCK, S->sf_n, S->sf_node.p, S->sf_ex.p, S->sf_exp.p, S->sf_exit.p, S->ptimep.p, S->pnew.p);
+        S->sfchek = p.isfcvg == 1; S->ksfzer = 1; S->sfflw = S->sfflwp = S->vsfflw = 0.0;
+    }
     CK(cudaMemsetAsync(S->atmpot.p, 0, (size_t)NN * sizeof(double), S->st));
     CK(cudaMemsetAsync(S->atmact.p, 0, (size_t)NN * sizeof(double), S->st));
     CK(cudaMemsetAsync(S->atmold.p, 0, (size_t)NN * sizeof(double), S->st));
@@ -4484,6 +4554,7 @@ static int init_atm_and_storage(CathySim *S)
         if (S->have_dir || S->have_neu)
             LAUNCH(S, k_mark_nonatm, nblk(NN, S->grid_n), RED_BLOCK, NN, S->have_dir ? S->contp_flag.p : nullptr,
                    S->have_neu ? S->contq_flag.p : nullptr, S->ifatm.p, S->ifatmp.p);
+        if (S->sf_n > 0) LAUNCH(S, k_sf_mark_nonatm, nblk(S->sf_n, S->grid_n), RED_BLOCK, S->sf_n, S->sf_node.p, NN, S->ifatm.p, S->ifatmp.p);
         LAUNCH(S, k_atmone, nblk(NN, S->grid_n), RED_BLOCK, NN, p.pmin, p.pondh_min, p.scf, S->atmpot.p, S->atmold.p, S->atmact.p, S->pnew.p,
                S->ptimep.p, S->ifatm.p, S->ifatmp.p);
     }
@@ -4783,6 +4854,11 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
     CK(cudaMemcpyAsync(S->ptimep.p, S->pnew.p, bn, cudaMemcpyDeviceToDevice, S->st));
     if (S->have_dir) CK(cudaMemcpyAsync(S->qpold.p, S->qpnew.p, (size_t)S->dir.anbc() * sizeof(double), cudaMemcpyDeviceToDevice, S->st));
     if (S->free_drain) CK(cudaMemcpyAsync(S->ckrwp.p, S->ckrw.p, bn, cudaMemcpyDeviceToDevice, S->st));
+    if (S->sf_n > 0) {   // SFEXP = SFEXIT = SFEX, SFQP = SFQ (SRC/cathy_main.f:3294-3300)
+        CK(cudaMemcpyAsync(S->sf_exp.p, S->sf_ex.p, (size_t)S->sf_n * sizeof(int), cudaMemcpyDeviceToDevice, S->st));
+        CK(cudaMemcpyAsync(S->sf_exit.p, S->sf_ex.p, (size_t)S->sf_n * sizeof(int), cudaMemcpyDeviceToDevice, S->st));
+        CK(cudaMemcpyAsync(S->sf_qp.p, S->sf_q.p, (size_t)S->sf_n * sizeof(double), cudaMemcpyDeviceToDevice, S->st));
+    }
     S->timep_dirty = 1;
     if (S->surf) {
         S->pondp = S->ponding;
@@ -4809,6 +4885,7 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
     rep->erras = S->erras; rep->errel = S->errel; rep->adin = S->adin; rep->adout = S->adout; rep->anin = S->anin; rep->anout = S->anout;
     rep->ndin = S->ndin; rep->ndout = S->ndout; rep->nnin = S->nnin; rep->nnout = S->nnout;
     rep->vndin = S->vndin; rep->vndout = S->vndout; rep->vnnin = S->vnnin; rep->vnnout = S->vnnout;
+    rep->sfflw = S->sfflw; rep->vsfflw = S->vsfflw;
     rep->apot = so.apot; rep->aact = so.aact; rep->ovflow = so.ovflow; rep->reflow = so.reflow;
     rep->aact_prev = S->aactp; S->aactp = so.aact;      // AACTP = AACT, SRC/cathy_main.f:3695
     rep->areatot = S->areatot;
@@ -4820,6 +4897,7 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
     if (S->surf) { rep->q_outlet_1 = so.q_out1; rep->q_outlet_2 = so.q_out2; rep->ak_max = so.ak_max; }
     S->adinp = S->adin; S->adoutp = S->adout; S->aninp = S->anin; S->anoutp = S->anout;
     S->ndinp = S->ndin; S->ndoutp = S->ndout; S->nninp = S->nnin; S->nnoutp = S->nnout;
+    S->sfflwp = S->sfflw;
     if (status == 2) S->finished = 1;
     else if (std::fabs(S->time - S->tmax) <= 0.001 * S->deltat) S->finished = 1;
     else {   // TIMUPD + TIMNXT (SRC/timupd.f, SRC/timnxt.f)

@@ -467,13 +467,24 @@ def load_project(prj: str, skip_transport: bool | None = None) -> CathyProject:
     P.dirbc = read_bc_table(fn["IIN8"], nnod, nstr)
     P.neubc = read_bc_table(fn["IIN9"], nnod, nstr)
 
-    # ---- seepage faces: only "none" is implemented (SRC/sfvone.f)
+    # ---- seepage faces (SRC/sfvone.f:27-66): TIME, NSF, then per face its node count and node ids; the record after it gives the
+    # time from which a new set would apply (SRC/sfvnxt.f) -- only a set that holds for the whole run is supported
+    P.seepage_faces = []
     rd = ListDirectedReader(fn["IIN7"])
     if not rd.eof():
-        rd.read(1)                                # TIME
+        t0 = float(rd.read(1)[0])                 # SFVTIM(1)
         nsf = int(rd.read(1)[0])
-        if nsf != 0:
-            raise CathyInputError("seepage faces (sfbc NSF>0) are not implemented yet")
+        if nsf > 0 and t0 <= 0.0:                 # sfvone returns before reading anything when SFVTIM(1) > TIME = 0
+            for _ in range(nsf):
+                cnt = int(rd.read(1)[0])
+                P.seepage_faces.append(np.asarray(rd.read_i(cnt), dtype=np.int32))
+            t1 = float(rd.read(1)[0]) if not rd.eof() else 1.0e30
+            if t1 <= float(P.parm["TMAX"]):
+                raise CathyInputError("input/sfbc: a second seepage-face record at TIME=%g <= TMAX; time-varying seepage-face sets "
+                                      "(SRC/sfvnxt.f) are not implemented" % t1)
+        elif nsf > 0:
+            raise CathyInputError("input/sfbc: first record at TIME=%g > 0 (the reference would start without seepage faces and "
+                                  "switch them on later, SRC/sfvnxt.f); not implemented" % t0)
 
     # ---- surface routing inputs (SRC/datin.f:325-372)
     if isim == 2:

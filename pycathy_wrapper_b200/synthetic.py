@@ -140,7 +140,7 @@ def write_hapin(path: str, nrow: int, ncol: int, dx: float, dy: float) -> None:
 def make_project(path: str, nrow: int, ncol: int, nstr: int, dx: float = 0.5, dy: float = 0.5, base: float = 3.0,
                  zratio=None, dem=None, soil_rows=None, ic=("uniform", -1.0), atmbc=None, hspatm: int = 1, ieto: int = 0,
                  pmin: float = -5.0, dirbc_text: str | None = None, neubc_text: str | None = None, ivghu: int = 0,
-                 hu=(0.02, 2, 2, 0, 0.333), hun=1, huab=(-5, 1), bc=(1.2, 0, -0.345), zone=None, ivert: int = 0, pond: float | None = None, **parm) -> str:
+                 hu=(0.02, 2, 2, 0, 0.333), hun=1, huab=(-5, 1), bc=(1.2, 0, -0.345), zone=None, ivert: int = 0, pond: float | None = None, seepage_faces=None, **parm) -> str:
     """Write a full project directory.  `ic` = ("uniform", psi) | ("hydrostatic",) | ("wt", position);
     `atmbc` = list of (time, rate) pairs (homogeneous) -- rate in m/s, +ve = rain."""
     for sub in ("input", "prepro", "output", "vtk"):
@@ -199,7 +199,13 @@ def make_project(path: str, nrow: int, ncol: int, nstr: int, dx: float = 0.5, dy
         with open(os.path.join(path, "input", nm), "w") as fh:
             fh.write(txt if txt is not None else "0.0\tTIME\n0 0\n1.0e9\tTIME\n0 0\n")
     with open(os.path.join(path, "input", "sfbc"), "w") as fh:
-        fh.write("0\n0\n1.0e9\n0\n")
+        if seepage_faces:           # list of faces, each a list of 1-based 3-D node ids with descending elevation (SRC/sfvone.f)
+            fh.write("0.0\n%d\n" % len(seepage_faces))
+            for f in seepage_faces:
+                fh.write("%d\n%s\n" % (len(f), " ".join(str(int(v)) for v in f)))
+            fh.write("1.0e30\n0\n")
+        else:
+            fh.write("0\n0\n1.0e9\n0\n")
     with open(os.path.join(path, "input", "posizione_serb"), "w") as fh:
         fh.write("0\n")
     for nm in ("grid", "retctab", "livelli_iniz_s", "effraininp", "mesh", "base_map", "transp", "transp_ic",

@@ -3,6 +3,7 @@
   weill_exemple/   inputs + prepro rasters of the reference's bundled hillslope (BASELINE config 1,
                    /root/reference/examples/SSHydro/weill_exemple) and the outputs COMMITTED in the
                    reference next to them (mbeconv, cumflowvol, hgraph, vp verbatim; psi/sw as .npz).
+  seep9, seep9n/   one-node seepage face switching on and off (Picard / Newton ELF), see seepage()
   storm20/         a synthetic 20x20x15 storm on a saturated hillslope (rain -> ponding, runoff routing, back-steps);
                    prepro rasters from the reference's pre-processor ELF, outputs from the reference's
                    processor ELF (oracle/_ref), both run by this script.
@@ -155,8 +156,41 @@ def mid82k():
         np.savez_compressed(os.path.join(dst, f + ".npz"), nstep=s, time=t, values=b)
 
 
+def seepage_project(path, newton=False):
+    """8 x 9 x 5 hillslope with ONE potential seepage-face node 0.82 m deep at the foot of the slope (what the shipped ELFs, built with
+    NSFMAX = NNSFMX = 1, can hold) just below the initial water table, and from t = 300 s a prescribed head of -0.6 m at the node
+    under it: the seepage node is switched on by EXTALL, drains, is switched off when its back-calculated flux turns positive, and
+    so on (95 transitions in 298 accepted steps under Picard, with back-steps at the start)."""
+    nnod = 10 * 9
+    node = 2 * nnod + 10 * 8 + 5
+    kw = dict(IOPT=2, ISOLV=0) if newton else {}
+    return synthetic.make_project(path, 8, 9, 5, ic=("wt", 2.2), ISIMGR=1, TMAX=1800.0, TIMPRT=[900.0, 1800.0], DELTAT=1.0, DTMIN=1e-4,
+                                  DTMAX=50.0, NODVP=[4], atmbc=[(0.0, 0.0), (60.0, 0.0), (900.0, 0.0), (960.0, -3e-5), (1.0e9, -3e-5)],
+                                  ISFCVG=1, seepage_faces=[[node]],
+                                  dirbc_text="0.0 TIME\n0 0\n300.0 TIME\n0 1\n%d\n-0.6\n1e9 TIME\n0 1\n%d\n-0.6\n" % (node + nnod, node + nnod), **kw)
+
+
+def seepage():
+    """Seepage-face fixtures from the reference ELFs (Picard and Newton builds).  The ELFs run SFINIT over zero faces and with SFCHEK
+    false because SFVONE's sentinel store overruns NSFNOD (see ORACLE_SF_ELF_QUIRK in oracle/cathy_oracle.c); everything after the
+    initialisation -- BCPIC/SHLPIC, BKPIC, FLUXMB, EXTALL, MASBAL's VSFFLW, hgsfdet -- is the reference's own arithmetic."""
+    global VERBATIM
+    keep = VERBATIM
+    VERBATIM = keep + ["hgsfdet", "hgatmsf"]
+    for name, newton, which in (("seep9", False, "20x20x15"), ("seep9n", True, "20x20x15_newton")):
+        tmp = "/tmp/golden_" + name
+        shutil.rmtree(tmp, ignore_errors=True)
+        shutil.rmtree(tmp + "_ref", ignore_errors=True)
+        seepage_project(tmp, newton)
+        oracle.run_reference(tmp, tmp + "_ref", which, timeout=600)
+        stash(tmp, os.path.join(tmp + "_ref", "output"), os.path.join(HERE, name))
+    VERBATIM = keep
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "newton":
+    if len(sys.argv) > 1 and sys.argv[1] == "seepage":
+        seepage()
+    elif len(sys.argv) > 1 and sys.argv[1] == "newton":
         newton()
     elif len(sys.argv) > 1 and sys.argv[1] == "mid82k":
         mid82k()

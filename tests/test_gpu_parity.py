@@ -728,3 +728,43 @@ def test_constant_relaxation(gpu_lib, oracle_mod, tmp_path):
     assert rg.nstep == 276
     ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
     assert ok, dmax
+
+
+@pytest.mark.parametrize("case", ["faces_picard", "faces_newton", "seep9", "seep9n"])
+def test_seepage_faces_match_oracle(gpu_lib, oracle_mod, tmp_path, case):
+    """Seepage faces on the device (seepage.cuh; SRC/extall.f, sfinit.f, the SFEX branches of bcpic.f / bcnew.f, bkpic.f / bknew.f,
+    fluxmb.f): two ten-node faces on the 20x20x15 hillslope (SFINIT, exit points moving up and down, ISFCVG = 1) under Picard and
+    Newton, and the two one-node projects on which the oracle is pinned against the reference ELFs (tests/golden/seep9, seep9n;
+    here without the ELFs' SFINIT quirk).  Same accepted steps, nonlinear iterations and back-steps; seepage flux SFFLW and volume
+    VSFFLW of every step; heads 1e-6 / 1e-8 m."""
+    from pycathy_wrapper_b200.capi import Simulation
+    from pycathy_wrapper_b200.project import load_project
+    from test_oracle_golden import seepage_hillslope
+    if case.startswith("faces"):
+        prj = load_project(seepage_hillslope(str(tmp_path / "p"), iopt=2 if case.endswith("newton") else 1))
+    else:
+        prj = load_project(os.path.join(GOLDEN, case))
+    g, c = Simulation(gpu_lib, prj), oracle_mod.simulation(prj)
+    ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])       # after SFINIT
+    assert ok, dmax
+    k, vsf, active, idle = 0, 0.0, 0, 0
+    while True:
+        rg, rc = g.step(), c.step()
+        k += 1
+        assert (rg.nstep, rg.iter, rg.kbackt) == (rc.nstep, rc.iter, rc.kbackt), f"step {k}: gpu {(rg.nstep, rg.iter, rg.kbackt)} oracle {(rc.nstep, rc.iter, rc.kbackt)}"
+        assert abs(rg.deltat - rc.deltat) <= 1e-12 * rc.deltat
+        assert abs(rg.sfflw - rc.sfflw) <= 1e-7 * abs(rc.sfflw) + 1e-16, (k, rg.sfflw, rc.sfflw)
+        assert abs(rg.vsfflw - rc.vsfflw) <= 1e-7 * abs(rc.vsfflw) + 1e-16
+        assert abs(rg.vout - rc.vout) <= 1e-7 * abs(rc.vout) + 1e-14
+        vsf += rg.vsfflw
+        active += rc.sfflw < 0.0
+        idle += rc.sfflw == 0.0
+        if rg.finished:
+            assert rc.finished
+            break
+    assert vsf < 0.0 and active > 10
+    if not case.startswith("faces"):
+        assert idle > 10            # the one-node face was switched off as well
+    ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
+    assert ok, dmax
+    g.close()

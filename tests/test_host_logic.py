@@ -96,3 +96,31 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".h", ".cpp")):
                 src = open(os.path.join(r, f)).read()
                 assert "oracle" not in src.replace("CPU oracle", "").replace("the oracle", ""), os.path.join(r, f)
+
+
+def test_reader_parses_seepage_faces(tmp_path):
+    """input/sfbc (SRC/sfvone.f:27-66): TIME, NSF, then per face its node count and node ids; a set that changes during the run
+    (SRC/sfvnxt.f) is refused; elevations must descend along a face (checked where the mesh is built: the oracle / the device)."""
+    from pycathy_wrapper_b200 import synthetic
+    from pycathy_wrapper_b200.project import CathyInputError, load_project
+    nnod = 5 * 6
+    faces = [[2 * nnod + 30, 3 * nnod + 30], [1 * nnod + 27, 2 * nnod + 27, 3 * nnod + 27]]
+    d = synthetic.make_project(str(tmp_path / "a"), 4, 5, 3, seepage_faces=faces, ISFCVG=1, TMAX=100.0)
+    p = load_project(d)
+    assert [list(f) for f in p.seepage_faces] == faces and p.parm["ISFCVG"] == 1
+    assert load_project(synthetic.make_project(str(tmp_path / "b"), 4, 5, 3)).seepage_faces == []
+    with open(os.path.join(d, "input", "sfbc"), "w") as fh:
+        fh.write("0.0\n1\n2\n%d %d\n50.0\n1\n2\n%d %d\n1e30\n0\n" % (faces[0][0], faces[0][1], faces[0][0], faces[0][1]))
+    with pytest.raises(CathyInputError, match="time-varying"):
+        load_project(d)
+
+
+def test_oracle_checks_seepage_face_order(tmp_path):
+    from oracle import oracle
+    from pycathy_wrapper_b200 import synthetic
+    from pycathy_wrapper_b200.capi import CathyLibraryError
+    from pycathy_wrapper_b200.project import load_project
+    nnod = 5 * 6
+    d = synthetic.make_project(str(tmp_path / "a"), 4, 5, 3, seepage_faces=[[3 * nnod + 30, 2 * nnod + 30]], TMAX=100.0)
+    with pytest.raises(CathyLibraryError, match="descending"):
+        oracle.simulation(load_project(d))
