@@ -767,6 +767,40 @@ __device__ __forceinline__ void grid_reduce2(unsigned int *counter, unsigned int
     ra = res[par][0]; rb = res[par][1];
     par ^= 1u;
 }
+// The same two sums when the whole solve runs in ONE thread-block cluster (small meshes): every CTA pushes its pair of partial sums
+// into the slot it owns in every CTA's shared memory (st.shared::cluster), one hardware cluster barrier (release / acquire at
+// cluster scope, ~0.2 us instead of the ~2 us of the global-memory barrier above), then every thread adds the slots in rank order
+// -> the same value in all CTAs, bit-reproducible.  Double-buffered like grid_reduce2: one barrier per reduction suffices.
+constexpr int PCG_CL_MAX = 16;
+template <int BLOCK>
+__device__ __forceinline__ void cluster_reduce2(cg::cluster_group &cl, unsigned int &par, double a, double b, double (*sh)[2],
+                                                double (*cp)[PCG_CL_MAX][2], double &ra, double &rb)
+{
+    static_assert(BLOCK == 1024, "32 warps: the second level is one half-warp butterfly");
+    const int nc = (int)cl.num_blocks(), lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool hi = lane >= 16;
+    double keep = hi ? b : a, send = hi ? a : b;
+    keep += __shfl_xor_sync(FULLMASK, send, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(FULLMASK, keep, o);
+    if ((lane & 15) == 0) sh[w][hi] = keep;
+    __syncthreads();
+    if (w == 0) {
+        double v = hi ? sh[lane - 16][1] + sh[lane][1] : sh[lane][0] + sh[lane + 16][0];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+        const double va = __shfl_sync(FULLMASK, v, 0), vb = __shfl_sync(FULLMASK, v, 16);
+        if (lane < nc) {
+            double *dst = cl.map_shared_rank(&cp[par][cl.block_rank()][0], lane);
+            *reinterpret_cast<double2 *>(dst) = make_double2(va, vb);
+        }
+    }
+    cl.sync();
+    double s0 = 0.0, s1 = 0.0;
+    for (int c = 0; c < nc; ++c) { const double2 q = *reinterpret_cast<const double2 *>(&cp[par][c][0]); s0 += q.x; s1 += q.y; }
+    ra = s0; rb = s1;
+    par ^= 1u;
+}
 __device__ __forceinline__ void l2_prefetch(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <int BLOCK, bool CUSTOM, bool DD, int MINB = 1024 / BLOCK>
 __global__ void __launch_bounds__(BLOCK, MINB) k_pcg(PcgArgs a)
@@ -1057,12 +1091,17 @@ __device__ __forceinline__ void pair_group(const Diag &A, const double *z, int d
     a0 += la0 * m1;   a1 += la1 * m2;
     a0 += lb0 * m0;   a1 += lb1 * m1;
 }
-template <int BLOCK, int PAR>     // PAR: parities of the offsets off[2], off[4], off[6] (bits 0, 1, 2)
+// CL = true: the grid is ONE thread-block cluster (meshes of a few thousand to a few ten thousand rows, e.g. BASELINE config 1 and the
+// members of small-catchment ensembles): reductions and barriers are cluster-scope (cluster_reduce2), so an iteration costs ~2 us
+// instead of ~7 us, and a solve occupies only its cluster's SMs -- other members' solves run beside it.
+template <int BLOCK, int PAR, bool CL = false>     // PAR: parities of the offsets off[2], off[4], off[6] (bits 0, 1, 2)
 __global__ void __launch_bounds__(BLOCK, 1) k_pcg_res2(PcgArgs a)
 {
     extern __shared__ __align__(16) double smv[];
     __shared__ double sh[BLOCK / 32][2];
     __shared__ double res[2][2];
+    __shared__ __align__(16) double cpart[2][PCG_CL_MAX][2];
+    cg::cluster_group cl = cg::this_cluster();
     unsigned int epoch = a.epoch0, par = 0;
     const int R = a.rows_cta, row0 = blockIdx.x * R, cnt = max(0, min(R, a.n - row0)), tid = threadIdx.x, lane = tid & 31;
     double *rs = smv, *ps = smv + R, *bs = smv + 2 * (size_t)R, *xs = a.xres ? smv + 3 * (size_t)R : a.x + row0;
@@ -1082,7 +1121,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pcg_res2(PcgArgs a)
                 if (is_dirichlet(k, a.nnod, a.ifatm, a.contp_flag)) dmask |= 1u << (2 * j + q); else xl += b * b;
             }
     double xlung, d1;
-    grid_reduce2<BLOCK>(a.counter, epoch, par, xl, 0.0, a.partial, sh, res, xlung, d1);
+    if (CL) cluster_reduce2<BLOCK>(cl, par, xl, 0.0, sh, cpart, xlung, d1);
+    else grid_reduce2<BLOCK>(a.counter, epoch, par, xl, 0.0, a.partial, sh, res, xlung, d1);
     // r = b - A x0 ; z = M^-1 r ; p = B = 0
     for (int i = tid; i < cnt; i += BLOCK) {
         const int k = row0 + i;
@@ -1093,7 +1133,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pcg_res2(PcgArgs a)
         bs[i] = 0.0;
         if (a.xres) xs[i] = a.x[k];
     }
-    grid_barrier(a.counter, epoch);
+    if (CL) cl.sync(); else grid_barrier(a.counter, epoch);
     double beta = 0.0, err = 0.0;
     int niter = 1;
     const double *z = a.z;      // NOT __restrict__/read-only: rewritten every iteration by other SMs
@@ -1139,7 +1179,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pcg_res2(PcgArgs a)
             }
         }
         double pr, pb;
-        grid_reduce2<BLOCK>(a.counter, epoch, par, s_pr, s_pb, a.partial, sh, res, pr, pb);
+        if (CL) cluster_reduce2<BLOCK>(cl, par, s_pr, s_pb, sh, cpart, pr, pb);
+        else grid_reduce2<BLOCK>(a.counter, epoch, par, s_pr, s_pb, a.partial, sh, res, pr, pb);
         const double alfa = pr / pb;
         // ---- phase B: r -= alfa B, x += alfa p, z = M^-1 r, (B.z), ||r_free||^2
         double s_bz = 0.0, s_rr = 0.0;
@@ -1164,7 +1205,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pcg_res2(PcgArgs a)
             } else { xs[i] += alfa * pv.x; rs[i] = rv.x; a.z[k] = zz.x; }
         }
         double bz, rr;
-        grid_reduce2<BLOCK>(a.counter, epoch, par, s_bz, s_rr, a.partial, sh, res, bz, rr);
+        if (CL) cluster_reduce2<BLOCK>(cl, par, s_bz, s_rr, sh, cpart, bz, rr);
+        else grid_reduce2<BLOCK>(a.counter, epoch, par, s_bz, s_rr, a.partial, sh, res, bz, rr);
         beta = -bz / pb;
         err = xlung > 0.0 ? sqrt(rr / xlung) : sqrt(rr / a.n);
         if (err > a.tol && niter < a.itmax) { ++niter; continue; }
@@ -1173,6 +1215,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pcg_res2(PcgArgs a)
     if (a.xres) for (int i = tid; i < cnt; i += BLOCK) a.x[row0 + i] = xs[i];
     if (blockIdx.x == 0 && tid == 0) { a.out->pcg_niter = niter; a.out->pcg_err = err; a.out->pad = (int)epoch; }
 }
+
+#include "pcg_cluster.cuh"
 
 // ------------------------------------------------------------------------------------------
 // SYMSLV, second formulation (opt-in, CATHY_PCG_ALGO=2; measured slower than k_pcg on B200 except on tiny meshes, see
@@ -2687,6 +2731,9 @@ struct CathySim {
     double pcg_ms = 0;
     int64_t pcg_iters = 0, pcg_solves = 0;
     int sms = 148, grid_n = 0, grid_pcg = 0, pcg_block = 1024, pcg_custom = 1, pcg_minb = 0, pcg_prefetch = 1;
+    int pcg_cluster = 0;                     // > 0: k_pcg_res2 runs as ONE thread-block cluster of that many CTAs (small meshes)
+    int pcl_c = 0, pcl_rows = 0;             // > 0: k_pcg_cl (pcg_cluster.cuh): cluster size and rows per CTA
+    size_t pcl_smem = 0;
     unsigned int barrier_epoch = 0;
     cudaStream_t st_copy = nullptr;          // cathy_get_state_async: drain stream, snapshot buffers
     cudaEvent_t ev_snap = nullptr, ev_drained = nullptr;
@@ -3482,8 +3529,10 @@ static const void *pcg_res2_fn(const CathySim *S)
 {
     static const void *const fn[8] = {(const void *)k_pcg_res2<1024, 0>, (const void *)k_pcg_res2<1024, 1>, (const void *)k_pcg_res2<1024, 2>, (const void *)k_pcg_res2<1024, 3>,
                                       (const void *)k_pcg_res2<1024, 4>, (const void *)k_pcg_res2<1024, 5>, (const void *)k_pcg_res2<1024, 6>, (const void *)k_pcg_res2<1024, 7>};
+    static const void *const fc[8] = {(const void *)k_pcg_res2<1024, 0, true>, (const void *)k_pcg_res2<1024, 1, true>, (const void *)k_pcg_res2<1024, 2, true>, (const void *)k_pcg_res2<1024, 3, true>,
+                                      (const void *)k_pcg_res2<1024, 4, true>, (const void *)k_pcg_res2<1024, 5, true>, (const void *)k_pcg_res2<1024, 6, true>, (const void *)k_pcg_res2<1024, 7, true>};
     const int nc1 = S->ncol + 1, o2 = nc1, o4 = S->nnod - nc1 - 1, o6 = S->nnod - 1;    // = off[2], off[4], off[6] (set later, by the mesh builder)
-    return fn[(o2 & 1) | ((o4 & 1) << 1) | ((o6 & 1) << 2)];
+    return (S->pcg_cluster > 0 ? fc : fn)[(o2 & 1) | ((o4 & 1) << 1) | ((o6 & 1) << 2)];
 }
 // streaming PCG on the column-major permutation of the system (see create_impl); the same kernel, other offsets
 static int solve_system_cm(CathySim *S)
@@ -3574,8 +3623,29 @@ static int solve_system_tma(CathySim *S)
     S->launches++;
     return 0;
 }
+// small meshes: the whole solve in one thread-block cluster, matrix and vectors in shared memory (pcg_cluster.cuh)
+static int solve_system_cl(CathySim *S)
+{
+    PclArgs a;
+    a.n = S->n; a.nnod = S->nnod; a.itmax = S->itmax_dev; a.tol = S->tol_dev; a.R = S->pcl_rows; a.H = S->nnod;
+    a.A = make_diag(S, S->A.p); a.diag = S->diag_bc.p; a.rhs = S->rhs.p; a.x = S->pdiff.p; a.z = S->wz.p;
+    a.ifatm = S->ifatm.p; a.contp_flag = S->flagp(); a.out = S->d_iter.p; a.epoch0 = S->barrier_epoch;
+    void *args[] = {&a};
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    cfg.gridDim = dim3(S->pcl_c); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = S->pcl_smem; cfg.stream = S->st;
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = S->pcl_c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CK(cudaEventRecord(S->evp0, S->st));
+    CK(cudaLaunchKernelExC(&cfg, (const void *)k_pcg_cl, args));
+    CK(cudaEventRecord(S->evp1, S->st));
+    S->launches++;
+    return 0;
+}
 static int solve_system(CathySim *S)
 {
+    if (S->pcl_c > 0) return solve_system_cl(S);
     if (!S->dd && S->pcg_algo == 2) return solve_system2(S);
     if (S->tma_on) return solve_system_tma(S);
     if (S->cm_on) return solve_system_cm(S);
@@ -3606,6 +3676,15 @@ static int solve_system(CathySim *S)
         a.rows_cta = S->res_rows; a.xres = S->res_x; a.prefetch = S->res_prefetch;
         const size_t smem = (size_t)(3 + S->res_x) * S->res_rows * sizeof(double);
         const void *fres = S->pcg_algo == 4 ? pcg_res2_fn(S) : (const void *)k_pcg_res<1024>;
+        if (S->pcg_cluster > 0) {     // the whole solve in one thread-block cluster
+            cudaLaunchConfig_t cfg = {};
+            cudaLaunchAttribute at[1];
+            cfg.gridDim = dim3(S->pcg_cluster); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem; cfg.stream = S->st;
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = S->pcg_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CK(cudaLaunchKernelExC(&cfg, fres, args));
+        } else
         if (S->pcg_shared_gpu) CK(cudaLaunchKernel(fres, dim3(S->grid_pcg), dim3(1024), args, smem, S->st));
         else CK(cudaLaunchCooperativeKernel(fres, dim3(S->grid_pcg), dim3(1024), args, smem, S->st));
         CK(cudaEventRecord(S->evp1, S->st));
@@ -4281,6 +4360,33 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
         const int nc1 = S->ncol + 1, o[NDIAG] = {0, 1, nc1, nc1 + 1, S->nnod - nc1 - 1, S->nnod - nc1, S->nnod - 1, S->nnod};
         if (!(o[3] == o[2] + 1 && o[5] == o[4] + 1 && o[7] == o[6] + 1 && S->grid_pcg <= 160)) S->pcg_algo = 3;
     }
+    // Small meshes: one cluster instead of the whole grid (see k_pcg_res2<.., CL>).  Default: meshes up to 32 Ki rows, with the
+    // smallest power-of-two cluster that gives every thread at most one pair of rows (2048 rows per CTA); CATHY_PCG_CLUSTER = 0 / C
+    // switches it off / forces C CTAs (1..16).
+    if (!S->dd && !S->newton && S->pcg_algo == 4) {
+        int c = 0;      // opt-in (measured on config 1: 7.0 -> 5.4 us per iteration with 8 CTAs; k_pcg_cl below does 4x better)
+        if (const char *e = getenv("CATHY_PCG_CLUSTER")) { c = atoi(e); if (c < 0 || c > PCG_CL_MAX || (c & (c - 1))) FAIL(-2, "CATHY_PCG_CLUSTER must be 0, 1, 2, 4, 8 or 16"); }
+        if (c > 0) { S->pcg_cluster = c; S->grid_pcg = c; S->pcg_block = 1024; S->pcg_custom = 1; S->pcg_minb = 0; }
+    }
+    // k_pcg_cl (pcg_cluster.cuh): default for Picard meshes of up to 16 Ki rows whose cluster-resident working set fits -- one row per
+    // thread, the smallest power-of-two cluster with <= 1024 rows per CTA.  CATHY_PCG_CL=0 switches it off; an explicit
+    // CATHY_PCG_ALGO or CATHY_PCG_CLUSTER keeps the kernel it names.
+    if (!S->dd && !S->newton && S->pcg_cluster == 0 && !getenv("CATHY_PCG_ALGO") && !(getenv("CATHY_PCG_CL") && atoi(getenv("CATHY_PCG_CL")) == 0)) {
+        int c = 1;
+        while (c < PCG_CL_MAX && (long long)c * 1024 < S->n) c *= 2;
+        if (const char *e = getenv("CATHY_PCG_CL")) { int v = atoi(e); if (v >= 1 && v <= PCG_CL_MAX && !(v & (v - 1)) && (long long)v * 1024 >= S->n) c = v; }
+        const int rows = (int)((((size_t)S->n + c - 1) / c + 31) / 32 * 32);
+        const size_t smem = ((size_t)NDIAG * (rows + S->nnod) + (size_t)5 * rows) * sizeof(double);
+        cudaFuncAttributes at;
+        CK(cudaFuncGetAttributes(&at, (const void *)k_pcg_cl));
+        int optin = 0;
+        CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, p.device));
+        if ((long long)c * 1024 >= S->n && rows <= 1024 && smem + at.sharedSizeBytes <= (size_t)optin) {
+            S->pcl_c = c; S->pcl_rows = rows; S->pcl_smem = smem;
+            CK(cudaFuncSetAttribute((const void *)k_pcg_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)optin - at.sharedSizeBytes)));
+            if (c > 8) CK(cudaFuncSetAttribute((const void *)k_pcg_cl, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        }
+    }
     if (!S->dd && (S->pcg_algo == 3 || S->pcg_algo == 4)) {
         // k_pcg_res*: r, p, B (and x if there is room) of a CTA's rows stay in its shared memory for the whole solve
         const void *fres = S->pcg_algo == 4 ? pcg_res2_fn(S) : (const void *)k_pcg_res<1024>;
@@ -4299,7 +4405,9 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
             S->res_prefetch = S->pcg_prefetch && (size_t)S->n * 64 > ((size_t)64 << 20);
             if (const char *e = getenv("CATHY_PCG_RES_PREFETCH")) S->res_prefetch = atoi(e);
             CK(cudaFuncSetAttribute(fres, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
+            if (S->pcg_cluster > 8) CK(cudaFuncSetAttribute(fres, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         }
+        if (S->pcg_cluster > 0 && S->res_rows == 0) FAIL(-2, "CATHY_PCG_CLUSTER=%d: %d rows per CTA do not fit in shared memory", S->pcg_cluster, rows);
     }
     S->halo = ((size_t)S->nnod + 1 + 31) / 32 * 32;
     int rc = build_static(S);
@@ -5078,8 +5186,9 @@ int32_t cathy_dd_start(CathySim *S)
 int32_t cathy_solver_info(const CathySim *S, int64_t info[4])
 {
     const bool res = !S->dd && (S->pcg_algo == 3 || S->pcg_algo == 4) && S->res_rows > 0;
-    info[0] = S->newton ? (S->bres_rows > 0 ? 11 : 10) : res ? S->pcg_algo : (!S->dd && S->pcg_algo == 2) ? 2 : S->tma_on ? 6 : S->cm_on ? 5 : 1;
+    info[0] = S->newton ? (S->bres_rows > 0 ? 11 : 10) : S->pcl_c > 0 ? 7 : res ? S->pcg_algo : (!S->dd && S->pcg_algo == 2) ? 2 : S->tma_on ? 6 : S->cm_on ? 5 : 1;
     info[1] = res ? S->res_rows : (S->newton ? S->bres_rows : 0); info[2] = res ? S->res_x : 0; info[3] = S->grid_pcg;
+    if (!S->newton && S->pcl_c > 0) { info[1] = S->pcl_rows; info[2] = 1; info[3] = S->pcl_c; }
     return 0;
 }
 int32_t cathy_solver_limits(const CathySim *S, double lim[5])

@@ -82,7 +82,7 @@ def test_pcg_solution_matches_oracle(gpu_lib, oracle_mod, weill, dt):
     assert np.max(np.abs(xg - xc)) <= 1e-7 * max(np.abs(xc).max(), 1e-12), (np.abs(xg - xc).max(), np.abs(xc).max(), ng, nc)
 
 
-@pytest.mark.parametrize("size", [(6, 7, 4), (7, 6, 5), (7, 7, 3), (6, 6, 4), (60, 50, 8), (120, 120, 20)])
+@pytest.mark.parametrize("size", [(6, 7, 4), (7, 6, 5), (7, 7, 3), (6, 6, 4), (20, 20, 15), (31, 30, 15), (60, 50, 8), (120, 120, 20)])
 def test_pcg_kernel_variants_agree(gpu_lib, tmp_path, monkeypatch, size):
     """k_pcg (streaming), k_pcg_res (resident, one row per thread) and k_pcg_res2 (resident, paired rows: aligned 16-byte loads +
     lane shuffles) run the same recurrence: same iteration count, solutions equal to rounding.  The sizes cover the three possible
@@ -117,8 +117,25 @@ def test_pcg_kernel_variants_agree(gpu_lib, tmp_path, monkeypatch, size):
         sim.close()
     monkeypatch.delenv("CATHY_PCG_CM")
     monkeypatch.delenv("CATHY_PCG_TMA")
+    monkeypatch.delenv("CATHY_PCG_ALGO")
+    algos = [3, 4, 5, 6]
+    if prj.n <= 16 * 1024:
+        # small meshes, the default: k_pcg_cl -- one thread-block cluster, matrix + vectors in shared memory, cluster-scope reductions;
+        # k_pcg_res2 inside one cluster (cluster barrier instead of the global-memory grid barrier) is the opt-in middle step
+        for kern, env in ((7, {}), (8, {"CATHY_PCG_CLUSTER": "4"})):
+            for kk, vv in env.items():
+                monkeypatch.setenv(kk, vv)
+            sim = Simulation(gpu_lib, prj)
+            info = sim.solver_info()
+            assert info["kernel"] == (7 if kern == 7 else 4) and (kern == 7 or info["grid"] == 4), info
+            sim.debug_assemble(7.0)
+            sols[kern] = sim.debug_solve()[:3]
+            sim.close()
+            for kk in env:
+                monkeypatch.delenv(kk)
+        algos += [7, 8]
     x1, n1, e1 = sols[1]
-    for algo in (3, 4, 5, 6):
+    for algo in algos:
         x, nit, err = sols[algo]
         assert abs(nit - n1) <= 1 and err <= 1e-10
         assert np.max(np.abs(x - x1)) <= 1e-10 * max(np.abs(x1).max(), 1e-300), (algo, np.abs(x - x1).max(), np.abs(x1).max())
