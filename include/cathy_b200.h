@@ -215,7 +215,7 @@ int32_t cathy_dd_info(const CathySim *sim, int64_t info[8]);
 
 /* Which linear-solver kernel this handle launches (for bench.py's roofline bookkeeping; no reference counterpart):
  * info[0] = 1 k_pcg (CG vectors streamed), 2 k_pcg2, 3 k_pcg_res / 4 k_pcg_res2 (CG vectors resident in shared memory), 5 k_pcg / 6 k_pcg_tma on the
- * column-major permutation, 7 k_pcg_cl (small meshes: one thread-block cluster, matrix and vectors in shared memory), 10 k_bicgstab / 11 k_bicgstab_res (Newton);
+ * column-major permutation, 7 k_pcg_cl / 8 k_pcg_cl2 (small meshes: one thread-block cluster, matrix and vectors in shared memory; 8 = one cluster barrier per iteration), 10 k_bicgstab / 11 k_bicgstab_res (Newton);
  * info[1] = rows per CTA (k_pcg_res), info[2] = 1 if the solution vector is resident too, info[3] = CTAs of the solver grid. */
 int32_t cathy_solver_info(const CathySim *sim, int64_t info[4]);
 /* Effective stopping rule of this handle's linear solver: lim[0] = iteration limit (ITMXCG x itmxcg_scale), lim[1] = relative

@@ -2732,7 +2732,8 @@ struct CathySim {
     int64_t pcg_iters = 0, pcg_solves = 0;
     int sms = 148, grid_n = 0, grid_pcg = 0, pcg_block = 1024, pcg_custom = 1, pcg_minb = 0, pcg_prefetch = 1;
     int pcg_cluster = 0;                     // > 0: k_pcg_res2 runs as ONE thread-block cluster of that many CTAs (small meshes)
-    int pcl_c = 0, pcl_rows = 0;             // > 0: k_pcg_cl (pcg_cluster.cuh): cluster size and rows per CTA
+    int pcl_block = 256;                     // threads per CTA of k_pcg_cl2 (CATHY_PCG_CL_BLOCK)
+    int pcl_c = 0, pcl_rows = 0, pcl_v2 = 0; // > 0: k_pcg_cl / k_pcg_cl2 (pcg_cluster.cuh): cluster size, rows per CTA, single-barrier variant
     size_t pcl_smem = 0;
     unsigned int barrier_epoch = 0;
     cudaStream_t st_copy = nullptr;          // cathy_get_state_async: drain stream, snapshot buffers
@@ -3633,12 +3634,12 @@ static int solve_system_cl(CathySim *S)
     void *args[] = {&a};
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
-    cfg.gridDim = dim3(S->pcl_c); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = S->pcl_smem; cfg.stream = S->st;
+    cfg.gridDim = dim3(S->pcl_c); cfg.blockDim = dim3(S->pcl_v2 ? S->pcl_block : 1024); cfg.dynamicSmemBytes = S->pcl_smem; cfg.stream = S->st;
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = S->pcl_c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     CK(cudaEventRecord(S->evp0, S->st));
-    CK(cudaLaunchKernelExC(&cfg, (const void *)k_pcg_cl, args));
+    CK(cudaLaunchKernelExC(&cfg, S->pcl_v2 ? (const void *)k_pcg_cl2 : (const void *)k_pcg_cl, args));
     CK(cudaEventRecord(S->evp1, S->st));
     S->launches++;
     return 0;
@@ -4374,17 +4375,26 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
     if (!S->dd && !S->newton && S->pcg_cluster == 0 && !getenv("CATHY_PCG_ALGO") && !(getenv("CATHY_PCG_CL") && atoi(getenv("CATHY_PCG_CL")) == 0)) {
         int c = 1;
         while (c < PCG_CL_MAX && (long long)c * 1024 < S->n) c *= 2;
+        // more CTAs = fewer rows per warp on the serial path of an iteration (config 1: 4.07 us per iteration with 8 CTAs, 3.46 with 16),
+        // as long as a CTA's rows still cover the stencil reach (k_pcg_cl2's window condition NNOD <= rows)
+        while (c < PCG_CL_MAX && (S->n + 2 * c - 1) / (2 * c) >= S->nnod) c *= 2;
         if (const char *e = getenv("CATHY_PCG_CL")) { int v = atoi(e); if (v >= 1 && v <= PCG_CL_MAX && !(v & (v - 1)) && (long long)v * 1024 >= S->n) c = v; }
         const int rows = (int)((((size_t)S->n + c - 1) / c + 31) / 32 * 32);
         const size_t smem = ((size_t)NDIAG * (rows + S->nnod) + (size_t)5 * rows) * sizeof(double);
-        cudaFuncAttributes at;
+        // k_pcg_cl2 (one barrier per iteration, nothing but shared memory inside the iteration): window vectors for R + 2 H rows
+        const size_t smem2 = ((size_t)NDIAG * (rows + S->nnod) + (size_t)6 * (rows + 2 * (size_t)S->nnod) + (size_t)3 * rows) * sizeof(double);
+        cudaFuncAttributes at, at2;
         CK(cudaFuncGetAttributes(&at, (const void *)k_pcg_cl));
+        CK(cudaFuncGetAttributes(&at2, (const void *)k_pcg_cl2));
         int optin = 0;
         CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, p.device));
-        if ((long long)c * 1024 >= S->n && rows <= 1024 && smem + at.sharedSizeBytes <= (size_t)optin) {
-            S->pcl_c = c; S->pcl_rows = rows; S->pcl_smem = smem;
-            CK(cudaFuncSetAttribute((const void *)k_pcg_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)optin - at.sharedSizeBytes)));
-            if (c > 8) CK(cudaFuncSetAttribute((const void *)k_pcg_cl, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        const bool v2 = !(getenv("CATHY_PCG_CL2") && atoi(getenv("CATHY_PCG_CL2")) == 0) && S->nnod <= rows && smem2 + at2.sharedSizeBytes <= (size_t)optin;
+        if ((long long)c * 1024 >= S->n && rows <= 1024 && (v2 || smem + at.sharedSizeBytes <= (size_t)optin)) {
+            const void *fk = v2 ? (const void *)k_pcg_cl2 : (const void *)k_pcg_cl;
+            S->pcl_c = c; S->pcl_rows = rows; S->pcl_smem = v2 ? smem2 : smem; S->pcl_v2 = v2;
+            if (const char *e = getenv("CATHY_PCG_CL_BLOCK")) { int b = atoi(e); if (b >= 32 && b <= 1024 && b % 32 == 0) S->pcl_block = b; }
+            CK(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)optin - (v2 ? at2 : at).sharedSizeBytes)));
+            if (c > 8) CK(cudaFuncSetAttribute(fk, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         }
     }
     if (!S->dd && (S->pcg_algo == 3 || S->pcg_algo == 4)) {
@@ -5186,7 +5196,7 @@ int32_t cathy_dd_start(CathySim *S)
 int32_t cathy_solver_info(const CathySim *S, int64_t info[4])
 {
     const bool res = !S->dd && (S->pcg_algo == 3 || S->pcg_algo == 4) && S->res_rows > 0;
-    info[0] = S->newton ? (S->bres_rows > 0 ? 11 : 10) : S->pcl_c > 0 ? 7 : res ? S->pcg_algo : (!S->dd && S->pcg_algo == 2) ? 2 : S->tma_on ? 6 : S->cm_on ? 5 : 1;
+    info[0] = S->newton ? (S->bres_rows > 0 ? 11 : 10) : S->pcl_c > 0 ? (S->pcl_v2 ? 8 : 7) : res ? S->pcg_algo : (!S->dd && S->pcg_algo == 2) ? 2 : S->tma_on ? 6 : S->cm_on ? 5 : 1;
     info[1] = res ? S->res_rows : (S->newton ? S->bres_rows : 0); info[2] = res ? S->res_x : 0; info[3] = S->grid_pcg;
     if (!S->newton && S->pcl_c > 0) { info[1] = S->pcl_rows; info[2] = 1; info[3] = S->pcl_c; }
     return 0;

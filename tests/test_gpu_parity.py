@@ -122,18 +122,22 @@ def test_pcg_kernel_variants_agree(gpu_lib, tmp_path, monkeypatch, size):
     if prj.n <= 16 * 1024:
         # small meshes, the default: k_pcg_cl -- one thread-block cluster, matrix + vectors in shared memory, cluster-scope reductions;
         # k_pcg_res2 inside one cluster (cluster barrier instead of the global-memory grid barrier) is the opt-in middle step
-        for kern, env in ((7, {}), (8, {"CATHY_PCG_CLUSTER": "4"})):
+        # (8: k_pcg_cl2, one cluster barrier per iteration, when the stencil window fits; 7: k_pcg_cl; 9 here = k_pcg_res2 inside a cluster)
+        for kern, env in ((8, {}), (7, {"CATHY_PCG_CL2": "0"}), (9, {"CATHY_PCG_CLUSTER": "4"})):
             for kk, vv in env.items():
                 monkeypatch.setenv(kk, vv)
             sim = Simulation(gpu_lib, prj)
             info = sim.solver_info()
-            assert info["kernel"] == (7 if kern == 7 else 4) and (kern == 7 or info["grid"] == 4), info
+            if kern == 9:
+                assert info["kernel"] == 4 and info["grid"] == 4, info
+            else:
+                assert info["kernel"] in ((7, 8) if kern == 8 else (7,)), info
             sim.debug_assemble(7.0)
             sols[kern] = sim.debug_solve()[:3]
             sim.close()
             for kk in env:
                 monkeypatch.delenv(kk)
-        algos += [7, 8]
+        algos += [7, 8, 9]
     x1, n1, e1 = sols[1]
     for algo in algos:
         x, nit, err = sols[algo]
