@@ -441,8 +441,9 @@ __global__ void k_rhs_lhs(int n, int nnod, Diag A, double tetaf, double rdt, con
                           const unsigned char *__restrict__ contp_flag, const double *__restrict__ qneu,
                           const double *__restrict__ atmact, const double *__restrict__ atmold,
                           const double *__restrict__ qtranie, double *__restrict__ rhs, double *__restrict__ xt5,
-                          double *__restrict__ diag_true, double *__restrict__ diag_bc)
+                          double *__restrict__ diag_true, double *__restrict__ diag_bc, const double *__restrict__ dtp)
 {
+    if (dtp) rdt = dtp[1];      // graph replay: {DELTAT, 1/DELTAT} of the current step live in device memory (the launch arguments are frozen)
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         double ax = dia_row(A, A.d[0], ptnew, k, n);
         double b = -ax - m2[k] * rdt * (pnew[k] - ptimep[k]) - m4[k] * rdt * (swnew[k] - swtimep[k]) - grav[k];
@@ -2035,8 +2036,9 @@ __global__ void k_norms_final(int nb, const NormPartial *__restrict__ part, cons
 __global__ void k_switch(int nnod, double deltat, double pmin, double ph, const double *__restrict__ arenod,
                          const double *__restrict__ pondnod, const double *__restrict__ atmpot,
                          const double *__restrict__ qtranie, int *__restrict__ ifatm, double *__restrict__ atmact,
-                         double *__restrict__ pnew, double *__restrict__ ovfl, int *__restrict__ ponding)
+                         double *__restrict__ pnew, double *__restrict__ ovfl, int *__restrict__ ponding, const double *__restrict__ dtp)
 {
+    if (dtp) deltat = dtp[0];   // graph replay, see k_rhs_lhs
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnod; i += gridDim.x * blockDim.x) {
         int f = ifatm[i];
         if (f == -1) { ovfl[i] = 0.0; continue; }
@@ -2733,6 +2735,16 @@ struct CathySim {
     int sms = 148, grid_n = 0, grid_pcg = 0, pcg_block = 1024, pcg_custom = 1, pcg_minb = 0, pcg_prefetch = 1;
     int pcg_cluster = 0;                     // > 0: k_pcg_res2 runs as ONE thread-block cluster of that many CTAs (small meshes)
     int pcl_block = 256;                     // threads per CTA of k_pcg_cl2 (CATHY_PCG_CL_BLOCK)
+    // CUDA-graph replay of one Picard iteration (small meshes, see picard_iteration): [0] = later iterations of a step, [1] = the first
+    // (it also evaluates Sw at the previous time level); the step-dependent scalars {DELTAT, 1/DELTAT} are read from d_dt
+    int graph_mode = 0, graph_capturing = 0;
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    int64_t glaunches[2] = {0, 0};
+    DBuf<double> d_dt;
+    double *h_dt = nullptr, dt_uploaded = -1.0;
+    struct HostReadback { SfOut sf; int pond; int pad; double bc[4]; } *h_rb = nullptr;      // page-locked targets of the per-iteration read-backs
+    const double *graph_dt() const { return graph_capturing ? d_dt.p : nullptr; }
+    void graph_drop() { for (auto &g : gexec) { if (g) cudaGraphExecDestroy(g); g = nullptr; } }
     int pcl_c = 0, pcl_rows = 0, pcl_v2 = 0; // > 0: k_pcg_cl / k_pcg_cl2 (pcg_cluster.cuh): cluster size, rows per CTA, single-barrier variant
     size_t pcl_smem = 0;
     unsigned int barrier_epoch = 0;
@@ -3366,6 +3378,7 @@ static void bc_one(HostBc &b, double time, int &want)
 static int bc_upload(CathySim *S, int want_dir, int want_neu)
 {
     const int n = S->n;
+    if (want_dir != S->dir.active || want_neu != S->neu.active) S->graph_drop();      // launch sizes follow the node lists
     if (want_dir != S->dir.active) {
         S->dir.active = want_dir;
         int m = S->dir.anbc();
@@ -3498,7 +3511,7 @@ static int assemble_system(CathySim *S, double deltat)
     else LAUNCH(S, k_assemble, nblk(n, 4 * S->grid_n), RED_BLOCK, n, S->plan, S->krt.p, S->e1t.p, A, S->grav.p, S->m2.p);
     LAUNCH(S, k_rhs_lhs, nblk(n, S->grid_n), RED_BLOCK, n, S->nnod, A, S->tetaf, 1.0 / deltat, S->ptnew.p, S->pnew.p, S->ptimep.p, S->swnew.p,
            S->swtimep.p, S->m2.p, S->m4.p, S->et2.p, S->grav.p, S->ifatm.p, S->flagp(),
-           S->have_neu ? S->qneu.p : (const double *)nullptr, S->atmact.p, S->atmold.p, S->qtranie.p, S->rhs.p, S->xt5.p, S->diag_true.p, S->diag_bc.p);
+           S->have_neu ? S->qneu.p : (const double *)nullptr, S->atmact.p, S->atmold.p, S->qtranie.p, S->rhs.p, S->xt5.p, S->diag_true.p, S->diag_bc.p, S->graph_dt());
     if (S->tetaf != 1.0)   // off-diagonals of the LHS are TETAF * stiffness (SRC/cfmatp.f:24-26)
         LAUNCH(S, k_scale, nblk((long long)(NDIAG - 1) * S->ld, 8 * S->grid_n), RED_BLOCK, (long long)(NDIAG - 1) * S->ld, S->tetaf, S->A.p + S->ld);
     return 0;
@@ -3855,7 +3868,18 @@ static int solve_system_newton(CathySim *S)
     S->launches++;
     return 0;
 }
-static int picard_iteration(CathySim *S, CathyIterRecord *rec)
+// atmospheric switching (SRC/switch_old.f / SRC/switch.f), evaluated inside CONVER (SRC/conver.f:58-71)
+static void launch_switch(CathySim *S)
+{
+    if (!S->surf) LAUNCH(S, k_switch_old, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, S->p.pmin, S->atmpot.p, S->ifatm.p, S->atmact.p, S->pnew.p);
+    else {
+        cudaMemsetAsync(S->d_flags.p, 0, sizeof(int), S->st);
+        LAUNCH(S, k_switch, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, S->deltat, S->p.pmin, S->p.pondh_min, S->arenod.p, S->pondnod.p,
+               S->atmpot.p, S->qtranie.p, S->ifatm.p, S->atmact.p, S->pnew.p, S->ovflnod.p, S->d_flags.p, S->graph_dt());
+    }
+}
+// everything one nonlinear iteration puts on the stream, up to and including the read-backs (no synchronisation, no host decision)
+static int enqueue_iteration(CathySim *S)
 {
     const int n = S->n;
     int rc = S->newton ? assemble_system_newton(S, S->deltat) : assemble_system(S, S->deltat);
@@ -3909,29 +3933,72 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
     if (S->dd) LAUNCH(S, k_dd_combine_iter, 1, 32, S->comm->ctx, S->d_iter.p, S->gnnod, S->grow0 * S->nc1);
     // atmospheric switching is evaluated every iteration when TOLSWI is large (SRC/conver.f:58-71); when it is
     // conditional the host decides after the read-back below.
-    bool switch_always = S->p.tolswi >= 1.0e29;
-    auto launch_switch = [&]() {
-        if (!S->surf) LAUNCH(S, k_switch_old, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, S->p.pmin, S->atmpot.p, S->ifatm.p, S->atmact.p, S->pnew.p);
-        else {
-            cudaMemsetAsync(S->d_flags.p, 0, sizeof(int), S->st);
-            LAUNCH(S, k_switch, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, S->deltat, S->p.pmin, S->p.pondh_min, S->arenod.p, S->pondnod.p,
-                   S->atmpot.p, S->qtranie.p, S->ifatm.p, S->atmact.p, S->pnew.p, S->ovflnod.p, S->d_flags.p);
-        }
-    };
-    if (switch_always) launch_switch();
+    const bool switch_always = S->p.tolswi >= 1.0e29;
+    if (switch_always) launch_switch(S);
     // EXTALL after the switch (SRC/conver.f:76-99); the two touch disjoint nodes (potential seepage nodes on the surface are IFATM = -1),
-    // so it may also run ahead of a switch that the host decides on below
-    SfOut h_sf = {0.0, 0, 0};
+    // so it may also run ahead of a switch that the host decides on after the read-back
     if (S->sf_n > 0) {
         LAUNCH(S, k_sf_extall, 1, RED_BLOCK, S->sf_n, S->sf_node.p, S->sf_ex.p, S->sf_exit.p, S->sf_q.p, S->pnew.p, S->d_sf.p);
-        CK(cudaMemcpyAsync(&h_sf, S->d_sf.p, sizeof(SfOut), cudaMemcpyDeviceToHost, S->st));
+        CK(cudaMemcpyAsync(&S->h_rb->sf, S->d_sf.p, sizeof(SfOut), cudaMemcpyDeviceToHost, S->st));
     }
     CK(cudaMemcpyAsync(S->h_iter, S->d_iter.p, sizeof(IterOut), cudaMemcpyDeviceToHost, S->st));
-    int h_pond = 0;
-    if (switch_always && S->surf) CK(cudaMemcpyAsync(&S->h_iter->ponding, S->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, S->st));
-    double h_bc[4] = {0, 0, 0, 0};
-    if (S->have_dir || S->have_neu) CK(cudaMemcpyAsync(h_bc, S->bcsum.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+    if (switch_always && S->surf) CK(cudaMemcpyAsync(&S->h_rb->pond, S->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, S->st));
+    if (S->have_dir || S->have_neu) CK(cudaMemcpyAsync(S->h_rb->bc, S->bcsum.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+    return 0;
+}
+
+// One nonlinear iteration (SRC/picard.f:74-198 / SRC/newton.f:52-123, then MASBAL, NORMS, CONVER's switching): the device work is
+// enqueue_iteration; the host reads a few scalars back and takes FLOW3D's decisions.
+// Small Picard meshes (the cluster solvers of pcg_cluster.cuh): the ~12 launches and copies of an iteration are captured ONCE into
+// a CUDA graph and replayed with one cudaGraphLaunch per iteration -- the arguments are frozen, the step-dependent scalars
+// {DELTAT, 1/DELTAT} are read from device memory instead.  On large meshes the whole linear solve already is one persistent launch
+// and device time is 99 % of the step, so nothing is captured there (and the grid-barrier kernels take a per-launch epoch argument).
+// CATHY_GRAPH=0 switches the replay off.  A new BC record drops the graphs (its node lists change launch sizes).
+static int picard_iteration(CathySim *S, CathyIterRecord *rec)
+{
+    const bool switch_always = S->p.tolswi >= 1.0e29;
+    S->h_rb->sf = SfOut{0.0, 0, 0}; S->h_rb->pond = 0; S->h_rb->bc[0] = S->h_rb->bc[1] = S->h_rb->bc[2] = S->h_rb->bc[3] = 0.0;
+    bool replayed = false;
+    if (S->graph_mode) {
+        const int v = S->timep_dirty ? 1 : 0;
+        if (!S->gexec[v]) {
+            cudaGraph_t g = nullptr;
+            const int64_t l0 = S->launches;
+            const int dirty0 = S->timep_dirty;
+            bool ok = cudaStreamBeginCapture(S->st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                S->graph_capturing = 1;
+                const int rce = enqueue_iteration(S);
+                S->graph_capturing = 0;
+                ok = cudaStreamEndCapture(S->st, &g) == cudaSuccess && rce == 0 && g != nullptr && S->launch_err == cudaSuccess;
+            }
+            if (ok) ok = cudaGraphInstantiate(&S->gexec[v], g, 0) == cudaSuccess;
+            if (g) cudaGraphDestroy(g);
+            S->glaunches[v] = S->launches - l0;
+            S->launches = l0; S->timep_dirty = dirty0;         // nothing ran yet
+            if (!ok) {      // not capturable on this driver / configuration: run the plain path from now on
+                cudaGetLastError(); S->launch_err = cudaSuccess;
+                S->graph_drop(); S->graph_mode = 0;
+            }
+        }
+        if (S->graph_mode) {
+            if (S->dt_uploaded != S->deltat) {
+                S->h_dt[0] = S->deltat; S->h_dt[1] = 1.0 / S->deltat;
+                CK(cudaMemcpyAsync(S->d_dt.p, S->h_dt, 2 * sizeof(double), cudaMemcpyHostToDevice, S->st));
+                S->dt_uploaded = S->deltat;
+            }
+            CK(cudaGraphLaunch(S->gexec[v], S->st));
+            S->launches += S->glaunches[v];
+            S->timep_dirty = 0; S->scaled = false;
+            replayed = true;
+        }
+    }
+    if (!replayed) { int rc = enqueue_iteration(S); if (rc) return rc; }
     CK(cudaStreamSynchronize(S->st));
+    const SfOut h_sf = S->h_rb->sf;
+    const double *h_bc = S->h_rb->bc;
+    int h_pond = 0;
+    if (switch_always && S->surf) S->h_iter->ponding = S->h_rb->pond;
     const IterOut &o = *S->h_iter;
     S->barrier_epoch = (unsigned int)o.pad;
     {   // per-launch device time of the PCG kernel (events sit on the launching stream)
@@ -3944,7 +4011,7 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
     if (!switch_always) {
         bool sw = (S->p.l2norm == 0 && o.pinf <= S->p.tolswi) || (S->p.l2norm != 0 && o.pl2 <= S->p.tolswi);
         if (sw) {
-            launch_switch();
+            launch_switch(S);
             if (S->surf) { CK(cudaMemcpyAsync(&h_pond, S->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, S->st)); CK(cudaStreamSynchronize(S->st)); S->ponding = h_pond; }
         }
     } else if (S->surf) S->ponding = o.ponding;
@@ -4173,6 +4240,9 @@ void cathy_destroy(CathySim *S)
     }
     S->own.release();
     if (S->h_iter) cudaFreeHost(S->h_iter);
+    if (S->h_rb) cudaFreeHost(S->h_rb);
+    if (S->h_dt) cudaFreeHost(S->h_dt);
+    S->graph_drop(); S->d_dt.release();
     if (S->h_step) cudaFreeHost(S->h_step);
     if (S->ev0) cudaEventDestroy(S->ev0);
     if (S->ev1) cudaEventDestroy(S->ev1);
@@ -4595,6 +4665,12 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
         CK(cudaDeviceSynchronize());
     }
     CK(cudaMallocHost((void **)&S->h_iter, sizeof(IterOut)));
+    CK(cudaMallocHost((void **)&S->h_rb, sizeof(*S->h_rb)));
+    CK(cudaMallocHost((void **)&S->h_dt, 2 * sizeof(double)));
+    if (S->d_dt.alloc(2)) FAIL(-101, "device allocation failed");
+    // graph replay of the Picard iteration: default for the small meshes the cluster solvers take (see picard_iteration)
+    S->graph_mode = (S->pcl_c > 0 && !S->newton && !S->dd) ? 1 : 0;
+    if (const char *e = getenv("CATHY_GRAPH")) S->graph_mode = S->graph_mode && atoi(e) != 0;
     CK(cudaMallocHost((void **)&S->h_step, sizeof(StepOut)));
     {
         size_t cnt = (size_t)p.natm * (p.hspatm ? 1 : NN);
@@ -5058,6 +5134,7 @@ int32_t cathy_unpack_psi(CathySim *S, const double *dX, int64_t ld, int64_t col)
 // (pyCATHY/DA/cathy_DA.py:1863-1875 update_ENS_files, pyCATHY/cathy_tools.py:593-740 run_processor).
 int32_t cathy_restart(CathySim *S, double tmax, double deltat)
 {
+    S->graph_drop();      // frozen launch arguments may refer to what this call replaces
     CK(cudaSetDevice(S->p.device));
     const CathyProblem &p = S->p;
     if (tmax > 0.0) S->p.tmax = tmax;
@@ -5090,6 +5167,7 @@ int32_t cathy_restart(CathySim *S, double tmax, double deltat)
 int32_t cathy_set_soil(CathySim *S, const double *permx, const double *permy, const double *permz, const double *elstor,
                        const double *poros, const double *vgn, const double *vgrmc, const double *vgpsat)
 {
+    S->graph_drop();      // frozen launch arguments may refer to what this call replaces
     CK(cudaSetDevice(S->p.device));
     CK(cudaStreamSynchronize(S->st));
     CathyProblem keep = S->p;
