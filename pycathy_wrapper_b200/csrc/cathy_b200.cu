@@ -3651,9 +3651,11 @@ static int solve_system_cl(CathySim *S)
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = S->pcl_c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    CK(cudaEventRecord(S->evp0, S->st));
+    // (inside a captured graph the pair would become event-record nodes, which cudaEventElapsedTime does not accept: the replayed
+    // iterations are not timed per solve -- CATHY_GRAPH=0 for a PCG time split)
+    if (!S->graph_capturing) CK(cudaEventRecord(S->evp0, S->st));
     CK(cudaLaunchKernelExC(&cfg, S->pcl_v2 ? (const void *)k_pcg_cl2 : (const void *)k_pcg_cl, args));
-    CK(cudaEventRecord(S->evp1, S->st));
+    if (!S->graph_capturing) CK(cudaEventRecord(S->evp1, S->st));
     S->launches++;
     return 0;
 }
@@ -3965,17 +3967,23 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
             cudaGraph_t g = nullptr;
             const int64_t l0 = S->launches;
             const int dirty0 = S->timep_dirty;
-            bool ok = cudaStreamBeginCapture(S->st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            cudaError_t e_begin = cudaStreamBeginCapture(S->st, cudaStreamCaptureModeThreadLocal), e_end = cudaSuccess, e_inst = cudaSuccess;
+            bool ok = e_begin == cudaSuccess;
+            int rce = 0;
             if (ok) {
                 S->graph_capturing = 1;
-                const int rce = enqueue_iteration(S);
+                rce = enqueue_iteration(S);
                 S->graph_capturing = 0;
-                ok = cudaStreamEndCapture(S->st, &g) == cudaSuccess && rce == 0 && g != nullptr && S->launch_err == cudaSuccess;
+                e_end = cudaStreamEndCapture(S->st, &g);
+                ok = e_end == cudaSuccess && rce == 0 && g != nullptr && S->launch_err == cudaSuccess;
             }
-            if (ok) ok = cudaGraphInstantiate(&S->gexec[v], g, 0) == cudaSuccess;
+            if (ok) { e_inst = cudaGraphInstantiate(&S->gexec[v], g, 0); ok = e_inst == cudaSuccess; }
+            if (getenv("CATHY_GRAPH_DEBUG")) fprintf(stderr, "cathy graph stages: begin %d, enqueue rc %d (%s), end %d, launch_err %d, instantiate %d\n", (int)e_begin, rce, g_err, (int)e_end, (int)S->launch_err, (int)e_inst);
             if (g) cudaGraphDestroy(g);
             S->glaunches[v] = S->launches - l0;
             S->launches = l0; S->timep_dirty = dirty0;         // nothing ran yet
+            if (getenv("CATHY_GRAPH_DEBUG")) fprintf(stderr, "cathy graph capture (variant %d): %s, %lld launches, last error %s\n", v, ok ? "ok" : "FAILED",
+                                                     (long long)S->glaunches[v], cudaGetErrorString(cudaPeekAtLastError()));
             if (!ok) {      // not capturable on this driver / configuration: run the plain path from now on
                 cudaGetLastError(); S->launch_err = cudaSuccess;
                 S->graph_drop(); S->graph_mode = 0;
@@ -4003,7 +4011,7 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
     S->barrier_epoch = (unsigned int)o.pad;
     {   // per-launch device time of the PCG kernel (events sit on the launching stream)
         float pm = 0.f;
-        if (cudaEventElapsedTime(&pm, S->evp0, S->evp1) == cudaSuccess) S->pcg_ms += pm;
+        if (!replayed) { if (cudaEventElapsedTime(&pm, S->evp0, S->evp1) == cudaSuccess) S->pcg_ms += pm; else cudaGetLastError(); }
         S->pcg_iters += o.pcg_niter; S->pcg_solves++;
     }
     rec->niter = o.pcg_niter; rec->ikmax = o.ikmax + 1; rec->pl2 = o.pl2; rec->pinf = o.pinf; rec->pnew_ik = o.pnew_ik;
