@@ -396,7 +396,8 @@ def run_roofline_hbm(ctx: Ctx, args) -> dict:
             "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
             "bytes_per_row_iter": PCG_BYTES_PER_ROW_ITER, "us_per_iter": 1e3 * pcg_ms / max(iters, 1), "pcg_iters": iters, "pcg_solves": solves,
             "flush": "inputs larger than L2; 4.3 GB of assembly traffic between two solves",
-            "spmv_only": {"ms": spmv_ms, "achieved": sp, "frac": sp / peak, "bytes_per_row": SPMV_BYTES_PER_ROW,
+            "spmv_only": {"kernel": "k_spmv_tma (y = A x with the TMA-staged tiles of k_pcg_tma's stencil phase)" if solver["kernel"] == 6 else "k_spmv (direct loads)",
+                          "ms": spmv_ms, "achieved": sp, "frac": sp / peak, "bytes_per_row": SPMV_BYTES_PER_ROW,
                           "csr_equivalent_gbs": (12.0 * nnz + 20.0 * n) / (spmv_ms / 1e3) / 1e9,
                           "flush": "20 back-to-back products, each streaming 270 MB (2.1 x the L2)"}}
 

@@ -4539,6 +4539,7 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
                 if (S->tma_smem + at.sharedSizeBytes <= (size_t)optin) {
                     CK(cudaFuncSetAttribute((const void *)k_pcg_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->tma_smem));
                     CK(cudaFuncSetAttribute((const void *)k_pcg_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->tma_smem));
+                    CK(cudaFuncSetAttribute((const void *)k_spmv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->tma_smem));
                     S->tma_on = true;
                 }
             }
@@ -5396,10 +5397,23 @@ int32_t cathy_debug_spmv(CathySim *S, const double *x, double *y, int32_t reps, 
         const size_t tile = (size_t)L * 33 * sizeof(double);
         k_permute_cols<<<dim3((NN + 31) / 32, q), 256, tile, S->st>>>(pa);
         CK(cudaGetLastError());
+        if (S->tma_on && !getenv("CATHY_SPMV_PLAIN")) {      // the product with the solver's own staging (k_spmv_tma, pcg_tma.cuh)
+            TmaArgs ta;
+            memset(&ta, 0, sizeof ta);
+            ta.n = n; ta.lo = 0; ta.hi = n; ta.A = P; ta.dg = S->cm_diag.p; ta.nl = L;
+            const double *xin = S->cm_p0.p;
+            double *yout = S->cm_bv.p;
+            void *targs[] = {&ta, &xin, &yout};
+            CK(cudaLaunchKernel((const void *)k_spmv_tma, dim3(S->sms), dim3(TMA_BLOCK), targs, S->tma_smem, S->st));   // warm-up
+            CK(cudaEventRecord(S->ev0, S->st));
+            for (int r = 0; r < reps; ++r) { CK(cudaLaunchKernel((const void *)k_spmv_tma, dim3(S->sms), dim3(TMA_BLOCK), targs, S->tma_smem, S->st)); S->launches++; }
+            CK(cudaEventRecord(S->ev1, S->st));
+        } else {
         LAUNCH(S, k_spmv, nblk(n, S->grid_n), RED_BLOCK, n, P, S->cm_diag.p, S->cm_p0.p, S->cm_bv.p);   // warm-up
         CK(cudaEventRecord(S->ev0, S->st));
         for (int r = 0; r < reps; ++r) LAUNCH(S, k_spmv, nblk(n, S->grid_n), RED_BLOCK, n, P, S->cm_diag.p, S->cm_p0.p, S->cm_bv.p);
         CK(cudaEventRecord(S->ev1, S->st));
+        }
         k_unpermute_cols<<<(NN + 31) / 32, 256, tile, S->st>>>(NN, L, S->cm_bv.p, S->wbv.p);
         CK(cudaGetLastError());
     } else {

@@ -115,7 +115,7 @@ __device__ __forceinline__ void tma_issue(const TmaArgs &a, const TmaLayout &ly,
 {
     const int T = TMA_T;
     const unsigned int bt = T * 8u, bl = (T + 2) * 8u;
-    const unsigned int total = 8u * bt + 7u * bl + (unsigned int)ly.wn * 8u + 2u * (unsigned int)ly.wf * 8u + (with_pb ? 2u * bt : 0u) + bt;
+    const unsigned int total = 8u * bt + 7u * bl + (unsigned int)ly.wn * 8u + 2u * (unsigned int)ly.wf * 8u + (with_pb ? 2u * bt : 0u) + (rsrc ? bt : 0u);
     mbar_expect_tx(bar, total);
 #pragma unroll
     for (int d = 1; d < NDIAG; ++d) tma_load(st + ly.up + (d - 1) * T, a.A.d[d] + k0, bt, bar);
@@ -126,7 +126,7 @@ __device__ __forceinline__ void tma_issue(const TmaArgs &a, const TmaLayout &ly,
     tma_load(st + ly.zl, gv + ((k0 - a.A.off[7]) & ~1), (unsigned int)ly.wf * 8u, bar);
     tma_load(st + ly.zh, gv + ((k0 + a.A.off[4]) & ~1), (unsigned int)ly.wf * 8u, bar);
     if (with_pb) { tma_load(st + ly.pt, a.p + k0, bt, bar); tma_load(st + ly.bt, a.bv + k0, bt, bar); }
-    tma_load(st + ly.rt, rsrc + k0, bt, bar);
+    if (rsrc) tma_load(st + ly.rt, rsrc + k0, bt, bar);
 }
 // (A gv)_k for row i of the tile in stage st
 __device__ __forceinline__ double tma_row(const TmaLayout &ly, const double *st, int i, const int *off, int L, double &zc)
@@ -377,5 +377,46 @@ __global__ void __launch_bounds__(TMA_BLOCK, 1) k_pcg_tma(TmaArgs a)
     if (blockIdx.x == 0 && tid == 0) {
         a.out->pcg_niter = niter; a.out->pcg_err = err; a.out->pad = (int)epoch;
         if (DD) { a.dd.seq[0] = seq_ar; a.dd.seq[1] = seq_h; }
+    }
+}
+
+// y = A x alone, with the same staging as phase A of k_pcg_tma (the SpMV of GRADDP, SRC/solscal-extended.f:1326-1334, on HBM-resident
+// systems): 7 upper + diagonal slices and the x windows from HBM (72 B/row), the lower slices and the two far windows from L2, y
+// written once (8 B/row).  No grid barrier: one sweep per launch.  cathy_debug_spmv's kernel whenever the solver is k_pcg_tma.
+__global__ void __launch_bounds__(TMA_BLOCK, 1) k_spmv_tma(TmaArgs a, const double *x, double *y)
+{
+    extern __shared__ __align__(128) double stg[];
+    __shared__ __align__(8) unsigned long long full[TMA_NS], empty[TMA_NS];
+    constexpr int T = TMA_T, NCW = TMA_T / 32;
+    const int tid = threadIdx.x, L = a.nl, lane = tid & 31, warp = tid >> 5;
+    int off[NDIAG];
+#pragma unroll
+    for (int d = 0; d < NDIAG; ++d) off[d] = a.A.off[d];
+    const TmaLayout ly = tma_layout(off, L);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < TMA_NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int ntile = (a.hi - a.lo + T - 1) / T, G = gridDim.x;
+    const int nq = (int)blockIdx.x < ntile ? (ntile - (int)blockIdx.x + G - 1) / G : 0;
+    if (warp == NCW) {
+        if (lane == 0)
+            for (int q = 0; q < nq; ++q) {
+                const unsigned int s = q % TMA_NS;
+                mbar_wait(&empty[s], ((q / TMA_NS) & 1u) ^ 1u);
+                tma_issue(a, ly, stg + (size_t)s * ly.total, &full[s], a.lo + ((int)blockIdx.x + q * G) * T, x, nullptr, false);
+            }
+        __syncwarp();
+    } else {
+        for (int q = 0; q < nq; ++q) {
+            const unsigned int s = q % TMA_NS;
+            mbar_wait(&full[s], (q / TMA_NS) & 1u);
+            const int k = a.lo + ((int)blockIdx.x + q * G) * T + tid;
+            if (k < a.hi) { double zc; y[k] = tma_row(ly, stg + (size_t)s * ly.total, tid, off, L, zc); }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
     }
 }

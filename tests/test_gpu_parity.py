@@ -789,3 +789,32 @@ def test_seepage_faces_match_oracle(gpu_lib, oracle_mod, tmp_path, case):
     ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
     assert ok, dmax
     g.close()
+
+
+@pytest.mark.parametrize("size", [(60, 50, 8), (33, 47, 5)])
+def test_spmv_tma_matches_plain_product(gpu_lib, tmp_path, monkeypatch, size):
+    """k_spmv_tma (the product staged by TMA bulk copies in the column-major permutation, what the HBM-resident SpMV figure of the bench
+    line is measured with) against the plain gather kernel in the same numbering and in the reference numbering."""
+    from pycathy_wrapper_b200 import synthetic
+    from pycathy_wrapper_b200.capi import Simulation
+    from pycathy_wrapper_b200.project import load_project
+    nrow, ncol, nstr = size
+    prj = load_project(synthetic.make_project(str(tmp_path / "p"), nrow, ncol, nstr, ic=("wt", 0.6), ISIMGR=1, TMAX=100.0, TIMPRT=[100.0], NODVP=[1]))
+    x = np.random.default_rng(5).standard_normal(prj.n)
+    out = {}
+    for name, env in (("layer", {"CATHY_PCG_ALGO": "1", "CATHY_PCG_CM": "0"}),
+                      ("cm_plain", {"CATHY_PCG_ALGO": "1", "CATHY_PCG_CM": "1", "CATHY_PCG_TMA": "1", "CATHY_SPMV_PLAIN": "1"}),
+                      ("cm_tma", {"CATHY_PCG_ALGO": "1", "CATHY_PCG_CM": "1", "CATHY_PCG_TMA": "1"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        sim = Simulation(gpu_lib, prj)
+        if name != "layer":
+            assert sim.solver_info()["kernel"] == 6
+        sim.debug_assemble(5.0)
+        out[name], _ = sim.debug_spmv(x, reps=2)
+        sim.close()
+        for k in env:
+            monkeypatch.delenv(k)
+    scale = np.abs(out["layer"]).max()
+    assert np.max(np.abs(out["cm_tma"] - out["cm_plain"])) <= 1e-13 * scale
+    assert np.max(np.abs(out["cm_tma"] - out["layer"])) <= 1e-12 * scale
