@@ -280,6 +280,31 @@ __global__ void k_curves(int n, Soil s, const double *__restrict__ ptnew, const 
         if (do_timep) swtimep[i] = pnot * fvgse(ptimep[i], psat, n_, m) + rr;
     }
 }
+// KSLOPE = 1, 2 (SRC/chpic1.f:26-50, SRC/chpic2.f:24-46; IVGHU = 0): dSe/dpsi as the chord slope between the current and the previous
+// nonlinear iterate wherever they differ by TOLKSL or more, else analytical (1) / centred difference over 2 TOLKSL (2)
+__global__ void k_curves_chord(int n, Soil s, int kslope, double tolksl, const double *__restrict__ ptnew, const double *__restrict__ ptold,
+                               const double *__restrict__ pnew, const double *__restrict__ ptimep, int do_timep, double *__restrict__ sw,
+                               double *__restrict__ ckrw, double *__restrict__ et1, double *__restrict__ et2,
+                               double *__restrict__ swnew, double *__restrict__ swtimep)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double n_ = s.vgn[i], m = s.vgm[i], psat = s.vgpsat[i], pnot = s.vgpnot[i], rr = s.rr[i];
+        const double psi = ptnew[i], pold = ptold[i], dp = psi - pold;
+        const bool small = fabs(dp) < tolksl;
+        double se, kr, dse;
+        vg_node(psi, psat, n_, m, s.vgn1[i], small && kslope == 1, se, kr, dse);
+        if (!small) dse = (se - fvgse(pold, psat, n_, m)) / dp;
+        else if (kslope == 2) dse = (fvgse(psi + tolksl, psat, n_, m) - fvgse(psi - tolksl, psat, n_, m)) / (2.0 * tolksl);
+        const double w = pnot * se + rr;
+        sw[i] = w;
+        et1[i] = w * s.snodi[i];
+        et2[i] = pnot * dse;
+        ckrw[i] = kr;
+        const double pn = pnew[i];
+        swnew[i] = pn == psi ? w : pnot * fvgse(pn, psat, n_, m) + rr;
+        if (do_timep) swtimep[i] = pnot * fvgse(ptimep[i], psat, n_, m) + rr;
+    }
+}
 // CHVELO (SRC/chvelo.f, IVGHU=0) fused with STORCAL's sum term (SRC/storcal.f)
 __global__ void k_chvelo(int n, Soil s, const double *__restrict__ psiv, const double *__restrict__ volnod,
                          double *__restrict__ sw, double *__restrict__ ckrw, double *__restrict__ partial, const unsigned char *__restrict__ own)
@@ -1929,11 +1954,13 @@ __global__ void k_norms(int n, int nnod, double *pnew, const double *__restrict_
                         const double *__restrict__ volnod, const double *__restrict__ snodi,
                         const double *__restrict__ pnodi, const int *__restrict__ ifatm, const double *__restrict__ atmact,
                         NormPartial *__restrict__ part, const unsigned char *__restrict__ own, double omega,
-                        const double *__restrict__ pdiff, const unsigned char *__restrict__ contp_flag, const double *__restrict__ contp_val)
+                        const double *__restrict__ pdiff, const unsigned char *__restrict__ contp_flag, const double *__restrict__ contp_val,
+                        const double *__restrict__ omega_dev)
 {
     __shared__ double sh[32];
     __shared__ double shv[RED_BLOCK / 32];
     __shared__ int shi[RED_BLOCK / 32];
+    if (omega_dev) omega = *omega_dev;      // NLRELX = 2: the relaxation parameter of this iteration was formed on the device (k_relxom_final)
     double pl2 = 0, fl2 = 0, ds = 0, pinf = 0, finf = 0, adin = 0, adout = 0, anin = 0, anout = 0;
     int ik = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -2504,8 +2531,52 @@ __global__ void k_step_final(int nbs, const StepPartial *__restrict__ spart, int
 }
 // RELAX with a constant factor (SRC/relax.f, NLRELX = 1): PNEW = (1 - OMEGA) POLD + OMEGA PNEW, after the mass balance and
 // before the convergence norms (SRC/flow3d.f:165-190)
-__global__ void k_relax(int n, double omega, const double *__restrict__ pold, double *__restrict__ pnew)
+// RELXOM (SRC/relxom.f:20-39, NLRELX = 2): the signed head change of largest magnitude (ties -> the LAST node, the sequential >= test),
+// block partials in fixed order, then OMEGA from Huyakorn's adaptation of Cooley's scheme with the previous iteration's signed maximum
+// PIKMXV(ITER-1) = PNEW(IKMAX) - POLD(IKMAX) of NORMS, still in the IterOut record on the device
+struct RelxPartial { double amax, diff; int ik, pad; };
+__global__ void k_relxom_partial(int n, const double *__restrict__ pnew, const double *__restrict__ pold, RelxPartial *__restrict__ part)
 {
+    __shared__ double sha[RED_BLOCK / 32], shd[RED_BLOCK / 32];
+    __shared__ int shi[RED_BLOCK / 32];
+    double am = 0.0, df = 0.0;
+    int ik = -1;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const double d = pnew[k] - pold[k], da = fabs(d);
+        if (da > am || (da == am && k >= ik)) { am = da; df = d; ik = k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oa = __shfl_down_sync(0xffffffffu, am, o), od = __shfl_down_sync(0xffffffffu, df, o);
+        const int oi = __shfl_down_sync(0xffffffffu, ik, o);
+        if (oa > am || (oa == am && oi > ik)) { am = oa; df = od; ik = oi; }
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { sha[w] = am; shd[w] = df; shi[w] = ik; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < RED_BLOCK / 32; ++q)
+            if (sha[q] > am || (sha[q] == am && shi[q] > ik)) { am = sha[q]; df = shd[q]; ik = shi[q]; }
+        RelxPartial p; p.amax = am; p.diff = df; p.ik = ik; p.pad = 0;
+        part[blockIdx.x] = p;
+    }
+}
+__global__ void k_relxom_final(int nb, const RelxPartial *__restrict__ part, int iter, const IterOut *__restrict__ prev, double *__restrict__ om)
+{   // om[0] = OMEGA, om[1] = OMEGAP; one thread
+    double omega = 1.0;
+    if (iter > 1) {
+        double am = 0.0, difmx = 0.0;
+        int ik = -1;
+        for (int q = 0; q < nb; ++q)
+            if (part[q].amax > am || (part[q].amax == am && part[q].ik > ik)) { am = part[q].amax; difmx = part[q].diff; ik = part[q].ik; }
+        const double difmxp = prev->pnew_ik - prev->pold_ik, zeta = difmx / (om[1] * difmxp);
+        omega = zeta >= -1.0 ? (3.0 + zeta) / (3.0 + fabs(zeta)) : 0.5 / fabs(zeta);
+    }
+    om[0] = omega; om[1] = omega;
+}
+__global__ void k_relax(int n, double omega, const double *__restrict__ pold, double *__restrict__ pnew, const double *__restrict__ omega_dev)
+{
+    if (omega_dev) omega = *omega_dev;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) pnew[k] = (1.0 - omega) * pold[k] + omega * pnew[k];
 }
 __global__ void k_weight(int n, double tetaf, const double *__restrict__ pnew, const double *__restrict__ ptimep, double *__restrict__ ptnew)
@@ -2718,6 +2789,9 @@ struct CathySim {
     DBuf<int> contp_list;
     double ndin = 0, ndout = 0, nnin = 0, nnout = 0, vndin = 0, vndout = 0, vnnin = 0, vnnout = 0;
     // seepage faces (seepage.cuh): flattened node list and its per-node state
+    DBuf<RelxPartial> relx_part;      // NLRELX = 2 (RELXOM): block partials, {OMEGA, OMEGAP}
+    DBuf<double> d_omega;
+    DBuf<double> ptold;      // previous nonlinear iterate of PTNEW, kept for the chord slopes (KSLOPE = 1, 2)
     int sf_n = 0, sfchek = 0, ksfzer = 1, ksfcv = 0, ksfcvt = 0;
     DBuf<int> sf_node, sf_ex, sf_exp, sf_exit;
     DBuf<double> sf_q, sf_qp;
@@ -3454,12 +3528,15 @@ static void atmbak(CathySim *S)
     atm_interp_launch(S, 0, 1, S->time, 1);   // ATMBAK always interpolates between slots 1 and 2 of the shifted window
 }
 
-static void weight_and_copy(CathySim *S)
-{   // POLD <- PNEW ; PTNEW = WEIGHT (SRC/weight.f)
+static void weight_and_copy(CathySim *S, bool iterate = false)
+{   // POLD <- PNEW ; PTNEW = WEIGHT (SRC/weight.f); PTOLD (kept for the chord slopes, KSLOPE != 0) is the previous iterate's PTNEW
+    // inside the nonlinear loop (SRC/flow3d.f:248-250) and the new PTNEW at the start of a step / after a back-step
     size_t b = (size_t)S->n * sizeof(double);
     cudaMemcpyAsync(S->pold.p, S->pnew.p, b, cudaMemcpyDeviceToDevice, S->st);
+    if (S->ptold.p && iterate) cudaMemcpyAsync(S->ptold.p, S->ptnew.p, b, cudaMemcpyDeviceToDevice, S->st);
     if (S->tetaf == 1.0) cudaMemcpyAsync(S->ptnew.p, S->pnew.p, b, cudaMemcpyDeviceToDevice, S->st);
     else LAUNCH(S, k_weight, nblk(S->n, S->grid_n), RED_BLOCK, S->n, S->tetaf, S->pnew.p, S->ptimep.p, S->ptnew.p);
+    if (S->ptold.p && !iterate) cudaMemcpyAsync(S->ptold.p, S->ptnew.p, b, cudaMemcpyDeviceToDevice, S->st);
 }
 
 // chvelo + storage sum -> returns STORE1 through h_step later; here just launches
@@ -3503,6 +3580,9 @@ static int assemble_system(CathySim *S, double deltat)
     else if (S->cm.ivghu != 0)
         LAUNCH(S, k_curves_alt, nblk(n, S->grid_n), RED_BLOCK, n, S->cm, S->snodi.p, S->pnodi.p, S->ptnew.p, S->pnew.p, S->ptimep.p, S->timep_dirty, S->sw.p, S->ckrw.p,
                S->et1.p, S->et2.p, S->swnew.p, S->swtimep.p);
+    else if (S->p.kslope != 0)
+        LAUNCH(S, k_curves_chord, nblk(n, S->grid_n), RED_BLOCK, n, make_soil(S), S->p.kslope, S->p.tolksl, S->ptnew.p, S->ptold.p, S->pnew.p, S->ptimep.p, S->timep_dirty,
+               S->sw.p, S->ckrw.p, S->et1.p, S->et2.p, S->swnew.p, S->swtimep.p);
     else
     LAUNCH(S, k_curves, nblk(n, S->grid_n), RED_BLOCK, n, make_soil(S), S->ptnew.p, S->pnew.p, S->ptimep.p, S->timep_dirty, S->sw.p, S->ckrw.p, S->et1.p, S->et2.p, S->swnew.p, S->swtimep.p);
     S->timep_dirty = 0;
@@ -3889,7 +3969,7 @@ static int enqueue_iteration(CathySim *S)
     rc = S->newton ? solve_system_newton(S) : solve_system(S);
     if (rc) return rc;
     Diag A = make_diag(S, S->A.p);
-    const bool fuse_update = !S->newton;     // Picard: PNEW += PDIFF happens inside k_norms
+    const bool fuse_update = !S->newton && S->p.nlrelx != 2;     // Picard: PNEW += PDIFF happens inside k_norms (not with NLRELX = 2: RELXOM needs the new heads first)
     if (!fuse_update)
     LAUNCH(S, k_update, nblk(n, S->grid_n), RED_BLOCK, n, S->nnod, S->pdiff.p, S->pold.p, S->ifatm.p, S->flagp(),
            S->valp(), S->pnew.p);
@@ -3926,11 +4006,18 @@ static int enqueue_iteration(CathySim *S)
                    S->pdiff.p, S->xt5.p, S->tetaf, S->sf_qp.p, S->sf_q.p, S->d_sf.p);
     }
     if (S->have_neu) LAUNCH(S, k_flux_sums, 1, RED_BLOCK, S->neu.anbc(), S->qlist.p, S->bcsum.p + 2);
+    const double *omd = nullptr;
+    if (S->p.nlrelx == 2) {   // RELXOM (SRC/flow3d.f:168): OMEGA of this iteration from the unrelaxed head change, kept on the device
+        const int nb = nblk(n, S->grid_n);
+        LAUNCH(S, k_relxom_partial, nb, RED_BLOCK, n, S->pnew.p, S->pold.p, S->relx_part.p);
+        LAUNCH(S, k_relxom_final, 1, 1, nb, S->relx_part.p, S->iter, S->d_iter.p, S->d_omega.p);
+        omd = S->d_omega.p;
+    }
     LAUNCH(S, k_norms, S->grid_n, RED_BLOCK, n, S->nnod, S->pnew.p, S->pold.p, S->rhs.p, S->ptimep.p, S->swnew.p, S->swtimep.p, S->volnod.p,
            S->snodi.p, S->pnodi.p, S->ifatm.p, S->atmact.p, S->npart.p, S->dd ? S->own.p : (const unsigned char *)nullptr,
-           S->p.nlrelx == 1 ? S->p.omega : 1.0, fuse_update ? S->pdiff.p : (const double *)nullptr,
-           S->flagp(), S->valp());
-    if (S->p.nlrelx == 1) LAUNCH(S, k_relax, nblk(n, S->grid_n), RED_BLOCK, n, S->p.omega, S->pold.p, S->pnew.p);
+           S->p.nlrelx == 1 ? S->p.omega : (S->p.nlrelx == 2 ? 0.5 : 1.0), fuse_update ? S->pdiff.p : (const double *)nullptr,
+           S->flagp(), S->valp(), omd);
+    if (S->p.nlrelx != 0) LAUNCH(S, k_relax, nblk(n, S->grid_n), RED_BLOCK, n, S->p.omega, S->pold.p, S->pnew.p, omd);
     LAUNCH(S, k_norms_final, 1, RED_BLOCK, S->grid_n, S->npart.p, S->pnew.p, S->pold.p, S->d_iter.p);
     if (S->dd) LAUNCH(S, k_dd_combine_iter, 1, 32, S->comm->ctx, S->d_iter.p, S->gnnod, S->grow0 * S->nc1);
     // atmospheric switching is evaluated every iteration when TOLSWI is large (SRC/conver.f:58-71); when it is
@@ -4068,7 +4155,7 @@ static int flow3d(CathySim *S, int *status)
         const bool sfwait = S->sf_n > 0 && S->sfchek && !S->ksfzer;   // ISFCVG = 1: the exit points must have settled too (SRC/flow3d.f:237-270)
         if ((!S->lsfail && !errgmx && !normcv && itagen) || (!S->lsfail && !errgmx && itagen && sfwait)) {
             if (S->sf_n > 0) cudaMemcpyAsync(S->sf_exit.p, S->sf_ex.p, (size_t)S->sf_n * sizeof(int), cudaMemcpyDeviceToDevice, S->st);
-            weight_and_copy(S);
+            weight_and_copy(S, true);
             S->iter++;
             continue;
         }
@@ -4235,6 +4322,7 @@ void cathy_destroy(CathySim *S)
       for (auto *b : bb) b->release(); }
     S->contp_flag.release(); S->contq_flag.release(); S->contp_val.release(); S->qneu.release(); S->qlist.release(); S->qpnew.release();
     S->qpold.release(); S->kznod.release(); S->bcsum.release(); S->contp_list.release();
+    S->ptold.release(); S->relx_part.release(); S->d_omega.release();
     S->sf_node.release(); S->sf_ex.release(); S->sf_exp.release(); S->sf_exit.release(); S->sf_q.release(); S->sf_qp.release(); S->d_sf.release();
     S->r_rs.release(); S->r_dcx.release(); S->r_handled.release(); S->r_qo.release(); S->r_qin_ring.release(); S->r_vol_ring.release(); S->r_best.release();
     S->d_counter.release(); S->tet.release(); S->don_dir.release(); S->npart.release(); S->spart.release(); S->d_iter.release(); S->d_step.release();
@@ -4283,7 +4371,7 @@ static int preload_kernels()
                          (const void *)k_div_area, (const void *)k_nod_cell, (const void *)k_cell_nod, (const void *)k_route, (const void *)k_route_static, (const void *)k_pond_zero,
                          (const void *)k_step_partial, (const void *)k_step_final, (const void *)k_weight, (const void *)k_atmone, (const void *)k_mbinit,
                          (const void *)k_pack_col, (const void *)k_unpack_col, (const void *)k_vel3d, (const void *)k_vnod3d, (const void *)k_recharge, (const void *)k_wtdepth, (const void *)k_curves_alt, (const void *)k_chvelo_alt, (const void *)k_curves_xvg, (const void *)k_chvelo_xvg,
-                         (const void *)k_curves_newton_alt, (const void *)k_sw_pair_alt, (const void *)k_relax, (const void *)k_pcg_res<1024>, (const void *)k_permute_cols, (const void *)k_unpermute_cols, (const void *)k_pcg_tma<true>, (const void *)k_pcg_tma<false>, (const void *)k_route_wave, (const void *)k_route_fill_static, (const void *)k_bres_sym_flags};
+                         (const void *)k_curves_newton_alt, (const void *)k_sw_pair_alt, (const void *)k_relax, (const void *)k_pcg_res<1024>, (const void *)k_permute_cols, (const void *)k_unpermute_cols, (const void *)k_pcg_tma<true>, (const void *)k_pcg_tma<false>, (const void *)k_route_wave, (const void *)k_route_fill_static, (const void *)k_bres_sym_flags, (const void *)k_curves_chord};
     for (const void *f : fns) CK(cudaFuncGetAttributes(&at, f));
     done = true;
     return 0;
@@ -4506,6 +4594,12 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
     DBuf<double> *vn[] = {&S->diag_true, &S->diag_bc, &S->grav, &S->m2, &S->pnew, &S->pold, &S->ptimep, &S->ptnew, &S->pdiff, &S->sw, &S->ckrw,
                           &S->ckrwp, &S->et1, &S->et2, &S->swnew, &S->swtimep, &S->rhs, &S->xt5, &S->qtranie, &S->wr, &S->wz, &S->wp0, &S->wp1, &S->wbv};
     for (auto *b : vn) a |= b->alloc(N, S->halo);   // halo: stencil gathers need no bounds checks
+    if (p.kslope != 0) a |= S->ptold.alloc(N);
+    if (p.nlrelx == 2) {
+        a |= S->relx_part.alloc(S->grid_n); a |= S->d_omega.alloc(2);
+        const double one2[2] = {1.0, 1.0};
+        if (!a) cudaMemcpy(S->d_omega.p, one2, sizeof one2, cudaMemcpyHostToDevice);
+    }
     a |= S->dis.alloc(N, S->halo); a |= S->wq0.alloc(N, S->halo); a |= S->wq1.alloc(N, S->halo);
     a |= S->krt.alloc(S->nt); a |= S->e1t.alloc(S->nt);
     a |= S->partial.alloc(10 * (size_t)std::max(S->grid_pcg, 1));
@@ -4678,7 +4772,7 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
     CK(cudaMallocHost((void **)&S->h_dt, 2 * sizeof(double)));
     if (S->d_dt.alloc(2)) FAIL(-101, "device allocation failed");
     // graph replay of the Picard iteration: default for the small meshes the cluster solvers take (see picard_iteration)
-    S->graph_mode = (S->pcl_c > 0 && !S->newton && !S->dd) ? 1 : 0;
+    S->graph_mode = (S->pcl_c > 0 && !S->newton && !S->dd && p.nlrelx != 2) ? 1 : 0;      // RELXOM takes the iteration number as an argument
     if (const char *e = getenv("CATHY_GRAPH")) S->graph_mode = S->graph_mode && atoi(e) != 0;
     CK(cudaMallocHost((void **)&S->h_step, sizeof(StepOut)));
     {
@@ -4792,11 +4886,13 @@ int32_t cathy_create(const CathyProblem *prob, CathySim **out)
     if (!prob || prob->abi_version != CATHY_ABI_VERSION) FAIL(-1, "ABI version mismatch");
     if (prob->iopt != 1 && prob->iopt != 2) FAIL(-2, "IOPT=%d: must be 1 (Picard) or 2 (Newton)", prob->iopt);
     if (prob->iopt == 2 && prob->tetaf != 1.0 && prob->tetaf <= 0.0) FAIL(-2, "TETAF must be positive");
-    if (prob->kslope != 0) FAIL(-2, "KSLOPE=%d: only analytical moisture-curve derivatives (0) are implemented", prob->kslope);
+    if (prob->kslope != 0 && !((prob->kslope == 1 || prob->kslope == 2) && prob->ivghu == 0 && prob->iopt == 1 && prob->dd_world <= 1))
+        FAIL(-2, "KSLOPE=%d: chord slopes (1, 2) are implemented for van Genuchten curves (IVGHU=0) under Picard on one GPU; localized slopes (3, 4) are not", prob->kslope);
     if (!(prob->ivghu >= 0 && prob->ivghu <= 4))
         FAIL(-2, "IVGHU=%d: van Genuchten (0), extended van Genuchten (1), Huyakorn (2, 3) and Brooks-Corey (4) curves are implemented; look-up tables (-1) are not", prob->ivghu);
     if (prob->lump == 0) FAIL(-2, "LUMP=0 (consistent mass matrix) is not implemented on the device");
-    if (prob->nlrelx != 0 && prob->nlrelx != 1) FAIL(-2, "NLRELX=%d: only no relaxation (0) and constant OMEGA (1) are implemented", prob->nlrelx);
+    if (prob->nlrelx < 0 || prob->nlrelx > 2) FAIL(-2, "NLRELX=%d: must be 0 (none), 1 (constant OMEGA) or 2 (RELXOM)", prob->nlrelx);
+    if (prob->nlrelx == 2 && prob->dd_world > 1) FAIL(-2, "NLRELX=2 is not available on a row-block partitioned mesh");
     if (prob->isimgr != 1 && prob->isimgr != 2) FAIL(-2, "ISIMGR=%d not supported", prob->isimgr);
     if (prob->deltat >= 1.0e15) FAIL(-2, "steady-state runs (DELTAT>=1e15) are not implemented");
     if (prob->ituns > CATHY_MAXIT) FAIL(-2, "ITUNS larger than %d", CATHY_MAXIT);

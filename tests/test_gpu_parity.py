@@ -818,3 +818,16 @@ def test_spmv_tma_matches_plain_product(gpu_lib, tmp_path, monkeypatch, size):
     scale = np.abs(out["layer"]).max()
     assert np.max(np.abs(out["cm_tma"] - out["cm_plain"])) <= 1e-13 * scale
     assert np.max(np.abs(out["cm_tma"] - out["layer"])) <= 1e-12 * scale
+
+
+@pytest.mark.parametrize("parm", [dict(KSLOPE=1, TOLKSL=0.01), dict(KSLOPE=2, TOLKSL=0.01), dict(NLRELX=2), dict(KSLOPE=1, TOLKSL=0.002, NLRELX=2)],
+                         ids=["kslope1", "kslope2", "nlrelx2", "kslope1+nlrelx2"])
+def test_chord_slopes_and_variable_relaxation(gpu_lib, oracle_mod, tmp_path, parm):
+    """KSLOPE = 1, 2 (k_curves_chord + the PTOLD copies) and NLRELX = 2 (k_relxom_*: OMEGA formed on the device from the signed
+    maximum head change) against the oracle, which is byte-identical to the ELF on the same projects (test_oracle_golden.py)."""
+    from pycathy_wrapper_b200.project import load_project
+    from test_oracle_golden import option_project
+    g, c, rg, rc = _run_both(gpu_lib, oracle_mod, load_project(option_project(str(tmp_path / "p"), **parm)))
+    ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
+    assert ok, dmax
+    assert np.max(np.abs(g.state()["sw"] - c.state()["sw"])) < 1e-6
