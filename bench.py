@@ -519,10 +519,16 @@ def run_enkf(ctx: Ctx, args, size, cycles: int, warm: int) -> dict:
     cc_b, up_b = 8.0 * n * (ne_loc + m), 8.0 * n * (2 * ne_loc + m)
     ncy = max(kern["n"], 1)
     cc_ms, up_ms = ctx.rmax(kern["crosscov_ms"] / ncy), ctx.rmax(kern["update_ms"] / ncy)
-    roof = {"bound": "hbm", "kernel": "k_enkf_crosscov + k_enkf_update (fp64 DMMA; N = %d, Ne_local = %d, m = %d)" % (n, ne_loc, m),
+    roof = {"bound": "hbm", "kernel": "k_enkf_crosscov_r8 + k_enkf_update_r8 (fp64 DMMA, small operand resident in shared memory; N = %d, Ne_local = %d, m = %d)" % (n, ne_loc, m),
             "bytes": cc_b + up_b, "ms": cc_ms + up_ms, "crosscov_ms": cc_ms, "update_ms": up_ms,
             "achieved": (cc_b + up_b) / ((cc_ms + up_ms) / 1e3) / 1e9 if cc_ms + up_ms > 0 else None, "peak": peak, "peak_source": peak_src, "unit": "GB/s"}
     roof["frac"] = roof["achieved"] / peak if roof["achieved"] else None
+    # the pair is bound by the fp64 tensor pipe, not by HBM: 2 N Ne m flop each against the DMMA rate measured on this pool's B200
+    # with tools/bench_dmma.cu (37.1 TFLOP/s for DMMA.8x8x4 with 32 warps per SM; the plain DFMA pipe does 34.1)
+    fl = 4.0 * n * ne_loc * m
+    roof["tensor"] = {"bound": "tensor", "unit": "TFLOP/s", "peak": 37.1, "peak_source": "measured (tools/bench_dmma.cu, profiles/micro/r2f_dmma_peak.log)",
+                      "achieved": fl / ((cc_ms + up_ms) / 1e3) / 1e12 if cc_ms + up_ms > 0 else None}
+    roof["tensor"]["frac"] = roof["tensor"]["achieved"] / 37.1 if roof["tensor"]["achieved"] else None
     out = {"metric": "ensemble member-steps/s", "value": steps_all / wall, "unit": "member-steps/s", "n_gpus": world, "steps": cycles,
            "warmup": max(warm, 1), "ms_per_step": 1e3 * wall / cycles, "higher_is_better": True, "scaling": "strong",
            "config": {"workload": "BASELINE config 4: EnKF DA, %d members on a %dx%d DEM x %d layers (%d nodes), %d SWC observations, window %.0f s; a step = "

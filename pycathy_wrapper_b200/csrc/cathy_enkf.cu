@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -28,6 +29,15 @@ extern "C" const char *cathy_enkf_last_error(void) { return e_err; }
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
 {   // D(8x8) += A(8x4, row) * B(4x8, col)
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// D(16x8) += A(16x16, row) * B(16x8, col): the largest fp64 tensor-core shape (PTX ISA 8.0, sm_90+).  Fragments (g = lane / 4, t = lane % 4):
+// a[i]: row g + 8 (i % 2), column t + 4 (i / 2);  b[v]: row (k) t + 4 v, column g;  d[0..3]: (g, 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1)
+__device__ __forceinline__ void dmma16816(double (&d)[4], const double (&a)[8], const double (&b)[4])
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, {%12,%13,%14,%15}, {%0,%1,%2,%3};"
+                 : "+d"(d[0]), "+d"(d[1]), "+d"(d[2]), "+d"(d[3])
+                 : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]), "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]));
 }
 
 // ---- stage 1 (tiny): S, D, C, B ------------------------------------------------------------
@@ -252,6 +262,225 @@ __global__ void __launch_bounds__(128) k_enkf_update(long long n, int ne, int m,
 }
 
 
+// ---- the same two stages with the SMALL operand resident in shared memory (default whenever it fits: m x Ne x 8 B <= ~200 KB) -------
+// k_enkf_crosscov / k_enkf_update above restage the m x Ne obs-perturbation matrix S (resp. the gain columns B) for every 32-row
+// tile of the state: at N = 163,216, Ne = 256, m = 64 that is 2 x the traffic of X itself through shared memory, with two CTA barriers
+// per 32 members -- 0.15 of the pair's roof (profiles/r2a_ncu_full_summary.json).  Here a persistent 256-thread CTA stages S (B) ONCE,
+// padded so that the DMMA B-fragment loads of a half-warp hit 16 different banks, and then streams the state: the A fragments
+// (X - mean, resp. P o L) go from global memory straight into registers (each lane one double; a warp-wide load covers 8 rows x 32
+// contiguous bytes = whole sectors), so the main loop has no barrier at all: 1 LDG + MT x (LDS + DMMA) per 4 members.
+template <int MT>
+__global__ void __launch_bounds__(512) k_enkf_crosscov_res(long long n, int ne, int m, int ld, const double *__restrict__ X, const double *__restrict__ mean,
+                                                           const double *__restrict__ S, double scale, double *__restrict__ P)
+{
+    extern __shared__ double Ss[];      // [8*MT][ld], zero beyond (m, ne); ld >= ne rounded up to 16
+    for (int e = threadIdx.x; e < 8 * MT * ld; e += blockDim.x) {
+        const int r = e / ld, c = e - r * ld;
+        Ss[e] = (r < m && c < ne) ? S[(size_t)r * ne + c] : 0.0;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, ne16 = (ne + 15) & ~15;
+    for (long long row0 = (long long)blockIdx.x * (blockDim.x >> 1); row0 < n; row0 += (long long)gridDim.x * (blockDim.x >> 1)) {
+        const long long ra = row0 + warp * 16 + g, rb = ra + 8;
+        const bool va = ra < n, vb = rb < n;
+        const double mua = va ? mean[ra] : 0.0, mub = vb ? mean[rb] : 0.0;
+        const double *xa = X + (va ? ra : 0) * ne, *xb = X + (vb ? rb : 0) * ne;
+        double acc[MT][4];
+#pragma unroll
+        for (int q = 0; q < MT; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0;
+#pragma unroll 2
+        for (int k0 = 0; k0 < ne16; k0 += 16) {
+            double a[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = k0 + t + 4 * j;
+                a[2 * j] = (va && c < ne) ? xa[c] - mua : 0.0;
+                a[2 * j + 1] = (vb && c < ne) ? xb[c] - mub : 0.0;
+            }
+            const double *sb = Ss + (size_t)g * ld + k0 + t;
+#pragma unroll
+            for (int q = 0; q < MT; ++q) {
+                const double *sq = sb + (size_t)q * 8 * ld;
+                const double b[4] = {sq[0], sq[4], sq[8], sq[12]};
+                dmma16816(acc[q], a, b);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < MT; ++q) {
+            const int c = q * 8 + t * 2;
+            if (va) { if (c < m) P[ra * m + c] = scale * acc[q][0]; if (c + 1 < m) P[ra * m + c + 1] = scale * acc[q][1]; }
+            if (vb) { if (c < m) P[rb * m + c] = scale * acc[q][2]; if (c + 1 < m) P[rb * m + c + 1] = scale * acc[q][3]; }
+        }
+    }
+}
+// X and Xa may alias: every element is read and written by the same thread
+__global__ void __launch_bounds__(512) k_enkf_update_res(long long n, int ne, int m, int ld, const double *X, const double *__restrict__ P,
+                                                         const double *__restrict__ L, long long n_loc, const double *__restrict__ B,
+                                                         const double *__restrict__ mean, const double *__restrict__ bbar, double inflate,
+                                                         long long n_infl, double inflate2, double *Xa)
+{
+    extern __shared__ double Bs[];      // [m16][ld]: B(k, member), zero beyond (m, ne)
+    const int m16 = (m + 15) & ~15;
+    for (int e = threadIdx.x; e < m16 * ld; e += blockDim.x) {
+        const int k = e / ld, c = e - k * ld;
+        Bs[e] = (k < m && c < ne) ? B[(size_t)k * ne + c] : 0.0;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const bool infl_any = inflate != 1.0 || inflate2 != 1.0;
+    for (long long row0 = (long long)blockIdx.x * (blockDim.x >> 1); row0 < n; row0 += (long long)gridDim.x * (blockDim.x >> 1)) {
+        const long long rr[2] = {row0 + warp * 16 + g, row0 + warp * 16 + g + 8};
+        bool valid[2], loc[2];
+        const double *pr[2], *lr[2];
+        double ma[2] = {0.0, 0.0}, fac[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            valid[h] = rr[h] < n; loc[h] = L != nullptr && rr[h] < n_loc;
+            pr[h] = P + (valid[h] ? rr[h] : 0) * m; lr[h] = L + (loc[h] ? rr[h] : 0) * m;
+            fac[h] = rr[h] < n_infl ? inflate : inflate2;
+            if (infl_any) {   // mean_a = mean + (P o L) bbar, summed over the observations in order by one lane of the row's group
+                if (valid[h] && t == 0) {
+                    double v = mean[rr[h]];
+                    for (int k = 0; k < m; ++k) { double p = pr[h][k]; if (loc[h]) p *= lr[h][k]; v += p * bbar[k]; }
+                    ma[h] = v;
+                }
+                ma[h] = __shfl_sync(0xffffffffu, ma[h], lane & ~3);
+            }
+        }
+        for (int c0 = 0; c0 < ne; c0 += 64) {
+            double acc[8][4];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0;
+            for (int k0 = 0; k0 < m16; k0 += 16) {
+                double a[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = k0 + t + 4 * j;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        double v = 0.0;
+                        if (valid[h] && k < m) { v = pr[h][k]; if (loc[h]) v *= lr[h][k]; }
+                        a[2 * j + h] = v;
+                    }
+                }
+                const double *bb = Bs + (size_t)(k0 + t) * ld + c0 + g;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const double b[4] = {bb[q * 8], bb[q * 8 + 4 * (size_t)ld], bb[q * 8 + 8 * (size_t)ld], bb[q * 8 + 12 * (size_t)ld]};
+                    dmma16816(acc[q], a, b);      // columns beyond ne are zero padding (ld >= c0 + 64)
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (valid[h])
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int c = c0 + q * 8 + t * 2;
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+                            if (c + e < ne) {
+                                double v = X[rr[h] * ne + c + e] + acc[q][2 * h + e];
+                                if (fac[h] != 1.0) v = ma[h] + fac[h] * (v - ma[h]);
+                                Xa[rr[h] * ne + c + e] = v;
+                            }
+                    }
+        }
+    }
+}
+
+// The same with the m8n8k4 shape (what the hardware executes: SASS DMMA.8x8x4), 8 rows per warp and 1024 threads per CTA: the loop is
+// bound by the latency of the LDS -> DMMA chains, so more, thinner warps win (tools/bench_dmma.cu: 37 TFLOP/s needs 32 warps per SM)
+template <int MT>
+__global__ void __launch_bounds__(1024) k_enkf_crosscov_r8(long long n, int ne, int m, int ld, const double *__restrict__ X, const double *__restrict__ mean,
+                                                          const double *__restrict__ S, double scale, double *__restrict__ P)
+{
+    extern __shared__ double Ss[];      // [8*MT][ld]
+    for (int e = threadIdx.x; e < 8 * MT * ld; e += blockDim.x) {
+        const int r = e / ld, c = e - r * ld;
+        Ss[e] = (r < m && c < ne) ? S[(size_t)r * ne + c] : 0.0;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, ne4 = (ne + 3) & ~3, rows_cta = blockDim.x >> 2;
+    for (long long row0 = (long long)blockIdx.x * rows_cta; row0 < n; row0 += (long long)gridDim.x * rows_cta) {
+        const long long row = row0 + warp * 8 + g;
+        const bool valid = row < n;
+        const double mu = valid ? mean[row] : 0.0;
+        const double *xr = X + (valid ? row : 0) * ne;
+        double acc[MT][2];
+#pragma unroll
+        for (int q = 0; q < MT; ++q) acc[q][0] = acc[q][1] = 0.0;
+#pragma unroll 4
+        for (int k0 = 0; k0 < ne4; k0 += 4) {
+            const double a = (valid && k0 + t < ne) ? xr[k0 + t] - mu : 0.0;
+            const double *sb = Ss + (size_t)g * ld + k0 + t;
+#pragma unroll
+            for (int q = 0; q < MT; ++q) dmma884(acc[q][0], acc[q][1], a, sb[(size_t)q * 8 * ld]);
+        }
+        if (valid)
+#pragma unroll
+            for (int q = 0; q < MT; ++q) {
+                const int c = q * 8 + t * 2;
+                if (c < m) P[row * m + c] = scale * acc[q][0];
+                if (c + 1 < m) P[row * m + c + 1] = scale * acc[q][1];
+            }
+    }
+}
+__global__ void __launch_bounds__(1024) k_enkf_update_r8(long long n, int ne, int m, int ld, const double *X, const double *__restrict__ P,
+                                                        const double *__restrict__ L, long long n_loc, const double *__restrict__ B,
+                                                        const double *__restrict__ mean, const double *__restrict__ bbar, double inflate,
+                                                        long long n_infl, double inflate2, double *Xa)
+{
+    extern __shared__ double Bs[];      // [m16][ld]: B(k, member)
+    const int m16 = (m + 15) & ~15, m4 = (m + 3) & ~3;
+    for (int e = threadIdx.x; e < m16 * ld; e += blockDim.x) {
+        const int k = e / ld, c = e - k * ld;
+        Bs[e] = (k < m && c < ne) ? B[(size_t)k * ne + c] : 0.0;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, rows_cta = blockDim.x >> 2;
+    const bool infl_any = inflate != 1.0 || inflate2 != 1.0;
+    for (long long row0 = (long long)blockIdx.x * rows_cta; row0 < n; row0 += (long long)gridDim.x * rows_cta) {
+        const long long row = row0 + warp * 8 + g;
+        const bool valid = row < n, loc = L != nullptr && row < n_loc;
+        const double *pr = P + (valid ? row : 0) * m, *lr = L + (loc ? row : 0) * m;
+        double ma = 0.0;
+        if (infl_any) {
+            if (valid && t == 0) {
+                double v = mean[row];
+                for (int k = 0; k < m; ++k) { double p = pr[k]; if (loc) p *= lr[k]; v += p * bbar[k]; }
+                ma = v;
+            }
+            ma = __shfl_sync(0xffffffffu, ma, lane & ~3);
+        }
+        const double fac = row < n_infl ? inflate : inflate2;
+        for (int c0 = 0; c0 < ne; c0 += 64) {
+            double acc[8][2];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q][0] = acc[q][1] = 0.0;
+#pragma unroll 2
+            for (int k0 = 0; k0 < m4; k0 += 4) {
+                double a = 0.0;
+                if (valid && k0 + t < m) { a = pr[k0 + t]; if (loc) a *= lr[k0 + t]; }
+                const double *bb = Bs + (size_t)(k0 + t) * ld + c0 + g;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) dmma884(acc[q][0], acc[q][1], a, bb[q * 8]);
+            }
+            if (valid)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int c = c0 + q * 8 + t * 2;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        if (c + h < ne) {
+                            double v = X[row * ne + c + h] + acc[q][h];
+                            if (fac != 1.0) v = ma + fac * (v - ma);
+                            Xa[row * ne + c + h] = v;
+                        }
+                }
+        }
+    }
+}
+
 __global__ void k_enkf_scale(long long n, double a, double *__restrict__ v)
 {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) v[i] *= a;
@@ -359,6 +588,30 @@ int32_t cathy_enkf_crosscov(const double *dX, const double *d_mean, const double
     int blocks = (int)std::min<int64_t>((n + 31) / 32, 148 * 8);
     double scale = 1.0 / (ne_total - 1);
     cudaStream_t st = (cudaStream_t)stream;
+    {   // S resident in shared memory (k_enkf_crosscov_res) when it fits; leading dimension = 4 mod 16 words: conflict-free B fragments
+        const int ne16 = (ne_local + 15) & ~15, ld = ne16 + 4, mtt = mt <= 8 ? 8 : mt <= 16 ? 16 : 32;
+        const size_t smr = (size_t)8 * mtt * ld * sizeof(double);
+        if (smr <= 200 * 1024 && !getenv("CATHY_ENKF_TILED")) {
+            const int blk = getenv("CATHY_ENKF_BLOCK") ? atoi(getenv("CATHY_ENKF_BLOCK")) : 1024, rows_cta = blk > 512 ? blk / 4 : blk / 2;
+            const int gridr = (int)std::max<int64_t>(1, std::min<int64_t>((n + rows_cta - 1) / rows_cta, 148));
+            if (blk > 512 && mtt <= 16) {      // 1024 threads x 8 rows per warp (m8n8k4): <= 64 registers per thread needs <= 16 observation tiles
+                if (mtt == 8) { ECK(cudaFuncSetAttribute(k_enkf_crosscov_r8<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+                                k_enkf_crosscov_r8<8><<<gridr, 1024, smr, st>>>(n, ne_local, m, ld, dX, d_mean, dS_local, scale, dP); }
+                else { ECK(cudaFuncSetAttribute(k_enkf_crosscov_r8<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+                       k_enkf_crosscov_r8<16><<<gridr, 1024, smr, st>>>(n, ne_local, m, ld, dX, d_mean, dS_local, scale, dP); }
+                ECK(cudaGetLastError());
+                return 0;
+            }
+            if (mtt == 8) { ECK(cudaFuncSetAttribute(k_enkf_crosscov_res<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+                            k_enkf_crosscov_res<8><<<gridr, blk, smr, st>>>(n, ne_local, m, ld, dX, d_mean, dS_local, scale, dP); }
+            else if (mtt == 16) { ECK(cudaFuncSetAttribute(k_enkf_crosscov_res<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+                                  k_enkf_crosscov_res<16><<<gridr, blk, smr, st>>>(n, ne_local, m, ld, dX, d_mean, dS_local, scale, dP); }
+            else { ECK(cudaFuncSetAttribute(k_enkf_crosscov_res<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+                   k_enkf_crosscov_res<32><<<gridr, blk, smr, st>>>(n, ne_local, m, ld, dX, d_mean, dS_local, scale, dP); }
+            ECK(cudaGetLastError());
+            return 0;
+        }
+    }
     if (mt <= 8) k_enkf_crosscov<8><<<blocks, 128, sm, st>>>(n, ne_local, m, dX, d_mean, dS_local, scale, dP);
     else if (mt <= 16) k_enkf_crosscov<16><<<blocks, 128, sm, st>>>(n, ne_local, m, dX, d_mean, dS_local, scale, dP);
     else {
@@ -373,6 +626,24 @@ int32_t cathy_enkf_update(const double *dX, const double *dP, const double *dL, 
                           uint64_t stream)
 {
     if ((inflate != 1.0 || inflate2 != 1.0) && (!d_mean || !d_bbar)) EFAIL(-1, "cathy_enkf_update: inflation needs the ensemble mean and the mean gain column");
+    {   // B resident in shared memory (k_enkf_update_res) when it fits; columns padded to whole 64-member passes
+        const int ne64 = (ne_local + 63) & ~63, ld = ne64 + 4, m16 = (m + 15) & ~15;
+        const size_t smr = (size_t)m16 * ld * sizeof(double);
+        if (smr <= 200 * 1024 && !getenv("CATHY_ENKF_TILED")) {
+            const int blk = getenv("CATHY_ENKF_BLOCK") ? atoi(getenv("CATHY_ENKF_BLOCK")) : 1024, rows_cta = blk > 512 ? blk / 4 : blk / 2;
+            const int gridr = (int)std::max<int64_t>(1, std::min<int64_t>((n + rows_cta - 1) / rows_cta, 148));
+            if (blk > 512) {
+                ECK(cudaFuncSetAttribute(k_enkf_update_r8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+                k_enkf_update_r8<<<gridr, 1024, smr, (cudaStream_t)stream>>>(n, ne_local, m, ld, dX, dP, dL, n_loc, dB_local, d_mean, d_bbar, inflate, n_infl, inflate2, dXa);
+                ECK(cudaGetLastError());
+                return 0;
+            }
+            ECK(cudaFuncSetAttribute(k_enkf_update_res, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+            k_enkf_update_res<<<gridr, blk, smr, (cudaStream_t)stream>>>(n, ne_local, m, ld, dX, dP, dL, n_loc, dB_local, d_mean, d_bbar, inflate, n_infl, inflate2, dXa);
+            ECK(cudaGetLastError());
+            return 0;
+        }
+    }
     size_t sm = (size_t)(32 + 64) * EPAD * sizeof(double);
     int blocks = (int)std::min<int64_t>((n + 31) / 32, 148 * 8);
     k_enkf_update<<<blocks, 128, sm, (cudaStream_t)stream>>>(n, ne_local, m, dX, dP, dL, n_loc, dB_local, d_mean, d_bbar, inflate, n_infl, inflate2, dXa);
