@@ -2437,6 +2437,135 @@ __global__ void __launch_bounds__(ROUTE_BLOCK) k_route(RouteArgs a, const int *h
 
 #include "route_wave.cuh"
 
+// k_route with FOUR lanes per cell: the four fp64 pow() of a cell (two directions x celerity / diffusivity) are dependent chains of
+// ~1 us each and bound the time per drainage level when one thread evaluates them one after the other (5.3 us per level, 2.1 ms per
+// call on the 200x200 bench DEM = a third of the coupled step).  Here lane q of a quad evaluates power q of its cell, the partner
+// lane's power arrives by shuffle, and the even lanes finish their direction with mc_finish (route_wave.cuh) -- operation for operation
+// the arithmetic of mc_cell.  Everything else is k_route: one CTA, level after level, next level's records fetched ahead, outflows of
+// the level just finished read from the shared stash.
+// MEASURED NEGATIVE (profiles/micro/r2f_route4.log): the coupled bench workload goes from 6.65 to 7.86 ms per step -- the compiler
+// already interleaves the four independent pow() chains of one thread, and with 128 cells per pass the 200-cell levels of the bench DEM
+// need two passes.  Kept as an opt-in (CATHY_ROUTE_LANES=4) with its parity tests green; k_route stays the default.
+constexpr int ROUTE4_BLOCK = 512, ROUTE4_CELLS = ROUTE4_BLOCK / 4;
+__global__ void __launch_bounds__(ROUTE4_BLOCK) k_route4(RouteArgs a, const int *handled)
+{
+    if (handled && *handled) return;             // k_route_wave (route_wave.cuh) did this step
+    __shared__ double s_cu[32], s_ak[32];
+    __shared__ int s_seq[32];
+    __shared__ double s_akmax;
+    __shared__ int s_nsurf;
+    __shared__ double s_dt;
+    __shared__ double s_q[2][2][ROUTE_BLOCK];      // [level parity][direction][slot]: outflows of the level's first ROUTE_BLOCK cells
+    if (threadIdx.x == 0) {
+        double akm = *a.ak_max, cu_max = akm * a.deltat, dts;
+        int ns;
+        if (cu_max > 1.0) { dts = 1.0 / akm; ns = (int)(a.deltat / dts) + 1; dts = a.deltat / ns; }
+        else { dts = a.deltat; ns = 1; }
+        s_nsurf = ns; s_dt = dts; s_akmax = akm;
+    }
+    __syncthreads();
+    const int nsurf = s_nsurf;
+    const double dt = s_dt;
+    const int *__restrict__ lp = a.level_ptr;
+    const int cell = threadIdx.x >> 2, quad = threadIdx.x & 3, dir = quad >> 1;
+    // one cell of a level: all four lanes hold the record (same addresses: one transaction), lane q raises the reference discharge of
+    // direction q / 2 to the celerity (q even) or diffusivity (q odd) exponent
+    auto do_cell = [&](const RouteCell &c, bool act, const double (*prev)[ROUTE_BLOCK], double (*mine)[ROUTE_BLOCK], int slot,
+                       double &best_cu, double &best_ak, int &best_seq) {
+        double qin = 0.0;
+        if (act) {
+#pragma unroll
+            for (int j = 0; j < ROUTE_RD; ++j)
+                if (j < c.nd) {
+                    const int code = c.dc[j], kind = code & 3, idx = code >> 3, dr = (code >> 2) & 1;
+                    const double v = kind == 0 ? c.dq[j] : kind == 1 ? prev[dr][idx] : (dr ? a.q_out_kkp1_2[idx] : a.q_out_kkp1_1[idx]);
+                    qin = qin + v;
+                }
+            for (int dn = c.d0 + ROUTE_RD; dn < c.d0 + c.nd; ++dn)
+                qin = qin + (a.don_dir[dn] ? a.q_out_kkp1_2[a.don_cell[dn]] : a.q_out_kkp1_1[a.don_cell[dn]]);
+            if (quad == 0) a.q_in_kkp1[c.ib] = qin;
+        }
+        const double nrc = act ? c.nrc : 1.0, w = act ? c.w[dir] : 0.0, epl = act ? c.epl[dir] : 1.0;
+        const bool on = act && w != 0.0;
+        const double q_in_kk = c.qik * w / nrc, q_out_kk = c.qok[dir] / nrc, q_in_kkp1 = qin * w / nrc;
+        double pw = 0.0;
+        if (on) {
+            const double qc = mc_qc(q_in_kk, q_in_kkp1, q_out_kk), g = (1.0 - c.y1 + 2.0 / 3.0 * c.b1);
+            pw = pow(qc, (quad & 1) ? 1.0 - c.b1 : 1.0 - 3.0 * g / 5.0);
+        }
+        const double p_dh = __shfl_xor_sync(0xffffffffu, pw, 1);
+        if (on && !(quad & 1)) {
+            const double swv = c.sw / nrc, q_over = swv * w * (1.0 / epl);
+            double cu, ak;
+            double qo = mc_finish(c.ckf[dir], c.dhd[dir], epl, dt, pw, p_dh, q_in_kk, q_in_kkp1, q_out_kk, q_over, cu, ak);
+            if (qo < 0.0) qo = 0.0;
+            (dir ? a.q_out_kkp1_2 : a.q_out_kkp1_1)[c.ib] = qo * nrc;
+            if (slot >= 0) mine[dir][slot] = qo * nrc;
+            const int sq = 2 * c.seq + dir;
+            if (cu > best_cu || (cu == best_cu && sq > best_seq)) { best_cu = cu; best_ak = ak; best_seq = sq; }
+        }
+    };
+    for (int sub = 1; sub <= nsurf; ++sub) {
+        double best_cu = -1.0, best_ak = 0.0;
+        int best_seq = -1;
+        RouteCell nxt;
+        bool have = cell < lp[1] - lp[0];
+        if (have) route_load(a, lp[0] + cell, nxt);
+        for (int lv = 0; lv < a.nlevel; ++lv) {
+            const int beg = lp[lv], end = lp[lv + 1];
+            const RouteCell cur = nxt;
+            const bool hc = have;
+            have = false;
+            if (lv + 1 < a.nlevel) {       // the next level's first cell of this quad: nothing here depends on this level's results
+                const int q = end + cell;
+                have = q < lp[lv + 2];
+                if (have) route_load(a, q, nxt);
+            }
+            do_cell(cur, hc, s_q[(lv + 1) & 1], s_q[lv & 1], cell, best_cu, best_ak, best_seq);
+            for (int q0 = beg + ROUTE4_CELLS; q0 < end; q0 += ROUTE4_CELLS) {      // levels wider than one pass (warp-uniform trip count)
+                const int q = q0 + cell;
+                const bool act = q < end;
+                RouteCell t;
+                if (act) route_load(a, q, t);
+                do_cell(t, act, s_q[(lv + 1) & 1], s_q[lv & 1], (act && q - beg < ROUTE_BLOCK) ? q - beg : -1, best_cu, best_ak, best_seq);
+            }
+            __syncthreads();
+        }
+        // AK_MAX = celerity of the LAST cell (in sequential order) attaining the max Courant number
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double oc = __shfl_down_sync(0xffffffffu, best_cu, o), oa = __shfl_down_sync(0xffffffffu, best_ak, o);
+            int os = __shfl_down_sync(0xffffffffu, best_seq, o);
+            if (oc > best_cu || (oc == best_cu && os > best_seq)) { best_cu = oc; best_ak = oa; best_seq = os; }
+        }
+        int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (lane == 0) { s_cu[wid] = best_cu; s_ak[wid] = best_ak; s_seq[wid] = best_seq; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int q = 1; q < (int)(blockDim.x >> 5); ++q)
+                if (s_cu[q] > best_cu || (s_cu[q] == best_cu && s_seq[q] > best_seq)) { best_cu = s_cu[q]; best_ak = s_ak[q]; best_seq = s_seq[q]; }
+            if (best_seq >= 0) s_akmax = best_ak;
+        }
+        // ALTEZZE: volume balance and water depth per cell
+        for (int c = threadIdx.x; c < a.ncell; c += blockDim.x) {
+            double dv = (a.q_in_kk[c] + a.q_in_kkp1[c]) / 2 * dt + a.sw_sn[c] * dt - (a.q_out_kk_1[c] + a.q_out_kk_2[c]) / 2 * dt
+                        - (a.q_out_kkp1_1[c] + a.q_out_kkp1_2[c]) / 2 * dt;
+            double v1 = a.volume_kk[c] + dv, h;
+            if (v1 >= 0.0) h = v1 / a.cellarea; else { v1 = 0.0; h = 0.0; }
+            a.volume_kkp1[c] = v1;
+            a.h_water[c] = h;
+            if (nsurf > 1 && sub < nsurf) {      // shift time levels for the next sub-step (:171-195)
+                a.q_in_kk[c] = a.q_in_kkp1[c]; a.q_in_kkp1[c] = 0.0;
+                a.q_out_kk_1[c] = a.q_out_kkp1_1[c]; a.q_out_kkp1_1[c] = 0.0;
+                a.q_out_kk_2[c] = a.q_out_kkp1_2[c]; a.q_out_kkp1_2[c] = 0.0;
+                a.volume_kk[c] = v1; a.volume_kkp1[c] = 0.0;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { *a.ak_max = s_akmax; *a.nsurf_out = nsurf; }
+}
+
 // end-of-step surface bookkeeping: PONDNOD=0 where PNEW<=0 (SRC/cathy_main.f:3181-3184)
 __global__ void k_pond_zero(int nnod, const double *__restrict__ pnew, double *__restrict__ pondnod)
 {
@@ -2809,6 +2938,7 @@ struct CathySim {
     int sms = 148, grid_n = 0, grid_pcg = 0, pcg_block = 1024, pcg_custom = 1, pcg_minb = 0, pcg_prefetch = 1;
     int pcg_cluster = 0;                     // > 0: k_pcg_res2 runs as ONE thread-block cluster of that many CTAs (small meshes)
     int pcl_block = 256;                     // threads per CTA of k_pcg_cl2 (CATHY_PCG_CL_BLOCK)
+    bool route_lanes4 = false;               // CATHY_ROUTE_LANES=4: k_route4 (four lanes per cell) instead of k_route -- measured slower, see k_route4
     // CUDA-graph replay of one Picard iteration (small meshes, see picard_iteration): [0] = later iterations of a step, [1] = the first
     // (it also evaluates Sw at the previous time level); the step-dependent scalars {DELTAT, 1/DELTAT} are read from d_dt
     int graph_mode = 0, graph_capturing = 0;
@@ -4210,7 +4340,8 @@ static int surf_flowtra(CathySim *S)
         CK(cudaLaunchKernelEx(&cfg, k_route_wave, wa));
         S->launches++;
     }
-    LAUNCH(S, k_route, 1, ROUTE_BLOCK, a, S->route_wave ? S->r_handled.p : (const int *)nullptr);
+    if (S->route_lanes4) LAUNCH(S, k_route4, 1, ROUTE4_BLOCK, a, S->route_wave ? S->r_handled.p : (const int *)nullptr);
+    else LAUNCH(S, k_route, 1, ROUTE_BLOCK, a, S->route_wave ? S->r_handled.p : (const int *)nullptr);
     LAUNCH(S, k_cell_nod, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nrow, S->ncol, S->h_water.p, S->pondnod.p);
     cudaMemsetAsync(S->d_flags.p, 0, sizeof(int), S->st);
     LAUNCH(S, k_pondupd, nblk(S->nnod, S->grid_n), RED_BLOCK, S->nnod, S->p.pondh_min, 1.0 / S->deltat, S->pondnod.p, S->arenod.p, S->atmpot.p,
@@ -4371,7 +4502,7 @@ static int preload_kernels()
                          (const void *)k_div_area, (const void *)k_nod_cell, (const void *)k_cell_nod, (const void *)k_route, (const void *)k_route_static, (const void *)k_pond_zero,
                          (const void *)k_step_partial, (const void *)k_step_final, (const void *)k_weight, (const void *)k_atmone, (const void *)k_mbinit,
                          (const void *)k_pack_col, (const void *)k_unpack_col, (const void *)k_vel3d, (const void *)k_vnod3d, (const void *)k_recharge, (const void *)k_wtdepth, (const void *)k_curves_alt, (const void *)k_chvelo_alt, (const void *)k_curves_xvg, (const void *)k_chvelo_xvg,
-                         (const void *)k_curves_newton_alt, (const void *)k_sw_pair_alt, (const void *)k_relax, (const void *)k_pcg_res<1024>, (const void *)k_permute_cols, (const void *)k_unpermute_cols, (const void *)k_pcg_tma<true>, (const void *)k_pcg_tma<false>, (const void *)k_route_wave, (const void *)k_route_fill_static, (const void *)k_bres_sym_flags, (const void *)k_curves_chord};
+                         (const void *)k_curves_newton_alt, (const void *)k_sw_pair_alt, (const void *)k_relax, (const void *)k_pcg_res<1024>, (const void *)k_permute_cols, (const void *)k_unpermute_cols, (const void *)k_pcg_tma<true>, (const void *)k_pcg_tma<false>, (const void *)k_route_wave, (const void *)k_route_fill_static, (const void *)k_bres_sym_flags, (const void *)k_curves_chord, (const void *)k_route4};
     for (const void *f : fns) CK(cudaFuncGetAttributes(&at, f));
     done = true;
     return 0;
@@ -4474,6 +4605,7 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
     { int rcp = preload_kernels(); if (rcp) return rcp; }
     CK(cudaStreamCreateWithFlags(&S->st, cudaStreamNonBlocking));
     CK(cudaEventCreate(&S->ev0)); CK(cudaEventCreate(&S->ev1)); CK(cudaEventCreate(&S->evp0)); CK(cudaEventCreate(&S->evp1));
+    if (const char *e = getenv("CATHY_ROUTE_LANES")) S->route_lanes4 = atoi(e) == 4;
     if (const char *e = getenv("CATHY_PCG_BLOCK")) S->pcg_block = atoi(e);
     if (const char *e = getenv("CATHY_PCG_CUSTOM_BARRIER")) S->pcg_custom = atoi(e);
     if (const char *e = getenv("CATHY_PCG_MINB")) S->pcg_minb = atoi(e);
