@@ -574,7 +574,11 @@ static int create_impl(const CathyProblem *prob, CathySim *S)
     if (S->d_dt.alloc(2)) FAIL(-101, "device allocation failed");
     // graph replay of the Picard iteration: default for the small meshes the cluster solvers take (see picard_iteration)
     S->graph_mode = (S->pcl_c > 0 && !S->newton && !S->dd && p.nlrelx != 2) ? 1 : 0;      // RELXOM takes the iteration number as an argument
-    if (const char *e = getenv("CATHY_GRAPH")) S->graph_mode = S->graph_mode && atoi(e) != 0;
+    // ... and for the resident PCG kernels when several handles share the GPU (ensemble members, CATHY_PCG_GRID): their launches from
+    // concurrent host threads contend for the driver, one graph launch per iteration instead of ~12 calls relieves that
+    const bool res_ok = !S->newton && !S->dd && p.nlrelx != 2 && S->pcg_algo == 4 && S->res_rows > 0 && S->pcl_c == 0 && S->pcg_cluster == 0 && !S->tma_on && !S->cm_on;
+    if (res_ok && S->pcg_shared_gpu) S->graph_mode = 1;
+    if (const char *e = getenv("CATHY_GRAPH")) { const int v = atoi(e); S->graph_mode = v == 0 ? 0 : (S->graph_mode || (v == 1 && res_ok)) ? 1 : 0; }
     CK(cudaMallocHost((void **)&S->h_step, sizeof(StepOut)));
     {
         size_t cnt = (size_t)p.natm * (p.hspatm ? 1 : NN);

@@ -341,8 +341,12 @@ static int solve_system(CathySim *S)
     a.x = S->pdiff.p; a.r = S->wr.p; a.z = S->wz.p; a.p0 = S->wp0.p; a.p1 = S->wp1.p; a.bv = S->wbv.p;
     a.ifatm = S->ifatm.p; a.contp_flag = S->flagp(); a.partial = S->partial.p; a.out = S->d_iter.p;
     a.counter = S->d_counter.p; a.epoch0 = S->barrier_epoch;
+    if (S->graph_mode) {      // frozen launch arguments: the barrier counter restarts from zero in every replayed solve (the memset is part of the graph)
+        CK(cudaMemsetAsync(S->d_counter.p, 0, sizeof(unsigned int), S->st));
+        a.epoch0 = 0;
+    }
     void *args[] = {&a};
-    CK(cudaEventRecord(S->evp0, S->st));
+    if (!S->graph_capturing) CK(cudaEventRecord(S->evp0, S->st));
     void *fn = nullptr;
     const bool cu = S->pcg_custom != 0;
     switch (S->pcg_block) {
@@ -372,7 +376,7 @@ static int solve_system(CathySim *S)
         } else
         if (S->pcg_shared_gpu) CK(cudaLaunchKernel(fres, dim3(S->grid_pcg), dim3(1024), args, smem, S->st));
         else CK(cudaLaunchCooperativeKernel(fres, dim3(S->grid_pcg), dim3(1024), args, smem, S->st));
-        CK(cudaEventRecord(S->evp1, S->st));
+        if (!S->graph_capturing) CK(cudaEventRecord(S->evp1, S->st));
         S->launches++;
         return 0;
     }
@@ -684,7 +688,7 @@ static int picard_iteration(CathySim *S, CathyIterRecord *rec)
     int h_pond = 0;
     if (switch_always && S->surf) S->h_iter->ponding = S->h_rb->pond;
     const IterOut &o = *S->h_iter;
-    S->barrier_epoch = (unsigned int)o.pad;
+    S->barrier_epoch = S->graph_mode ? 0u : (unsigned int)o.pad;
     {   // per-launch device time of the PCG kernel (events sit on the launching stream)
         float pm = 0.f;
         if (!replayed) { if (cudaEventElapsedTime(&pm, S->evp0, S->evp1) == cudaSuccess) S->pcg_ms += pm; else cudaGetLastError(); }
