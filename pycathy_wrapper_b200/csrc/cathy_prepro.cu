@@ -1,0 +1,761 @@
+// cathy_prepro.cu -- the CATHY pre-processor (terrain analysis: CSORT, DEPIT, CCA, SMEAN, DSF, HG) on sm_100a.
+// C ABI: include/cathy_prepro.h.  PRE = /root/reference/examples/SSHydro/weill_exemple/prepro/src (HAP v11.7).
+//
+// What is parallel and what is not.  The reference sweeps the cells in descending elevation and lets every cell push
+// area and deviation sums to its one or two receivers (PRE/dsf.f90:71-529): a cell's result depends on everything
+// upstream of it.  Here the sweep is a dependency WAVEFRONT: a cell becomes ready when all neighbours that precede it
+// in the elevation order are finished, then GATHERS the contributions of its donors in that same order, so the
+// floating-point sums are the reference's, bit for bit, while all cells of a wavefront run side by side (one persistent
+// cooperative grid, one grid barrier per wavefront, O(cells) work in total).  Window analysis (facets, curvature) and
+// hydraulic geometry are embarrassingly parallel.  Two pieces are sequential BY DEFINITION of their result and run on a
+// single device thread: the reference's unstable quicksort (PRE/qsort.f90), because the order of equal elevations is
+// part of the output (file qoi_a, the routing order of SRC/route.f:47-56), and DEPIT's in-place Gauss-Seidel raising of
+// pits (PRE/depit.f90:75-140), whose fixed point depends on the visiting order; a parallel check first proves the
+// common case "no pit at all", where DEPIT changes nothing.  There is no host fallback for any of it.
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <cfloat>
+#include "../../include/cathy_prepro.h"
+
+namespace cg = cooperative_groups;
+
+static thread_local char pp_err[512] = "";
+#define PFAIL(code, ...) do { snprintf(pp_err, sizeof pp_err, __VA_ARGS__); rc = (code); goto done; } while (0)
+#define PCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) PFAIL(-100, "CUDA error %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+// round-to-nearest operations that nvcc may not contract into FMAs: the reference binary (gfortran -O, x86-64) has none
+__device__ __forceinline__ double rmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double radd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double rsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double rdiv(double a, double b) { return __ddiv_rn(a, b); }
+
+#define EPS64 2.220446049250313e-16
+#define EPS32 1.1920929e-07f
+
+struct PP {
+    CathyPreproParams h;
+    int N, M, nb, nc;
+    double *q;               // [nb] elevation, -1 = no cell (dtm_quota, PRE/mbbio.f90:766-776)
+    unsigned char *pres;     // [nb]
+    int *order, *rank;       // [nc+1] i_basin by descending elevation; [nb] position of a cell in it
+    double *key;             // [nc+1] sort keys
+    int *lst1, *lst2, *stamp;
+    // window analysis
+    double *smax, *dev1, *dev2, *de1, *de2;
+    signed char *po1, *po2;
+    float *Kp;
+    int *dm0;
+    // sweep
+    double *Ain, *sdn, *Aout, *sd1, *sd2;
+    float *w1, *w2, *ls1, *ls2, *epl1, *epl2, *ASk;
+    int *p1, *p2, *hc, *dm, *hc_after;
+    unsigned char *sflag;    // bit 0: direction 1 carries the deviation sum, bit 1: direction 2 does
+    int *dep, *front[2];
+    int *cnt;                // [16] counters: 0..2 frontier sizes, 3 processed, 4 waves, 5 pits, 6 modifications, 7 error, 8 passes
+    double *scal;            // [4] mean_s_max
+    // hydraulic geometry
+    float *Ws1, *Ws2, *b1, *kS1, *kS2, *y1, *nrc;
+};
+
+// ------------------------------------------------------------------ QSORT (PRE/qsort.f90:9-125), arr/brr 1-based
+__device__ void pp_qsort(int n, double *arr, int *brr)
+{
+    const int MM = 7;
+    int istack[64];
+    int jstack = 0, l = 1, ir = n;
+    for (;;) {
+        if (ir - l < MM) {
+            for (int j = l + 1; j <= ir; ++j) {
+                double a = arr[j];
+                int b = brr[j];
+                int i = j - 1;
+                for (; i >= 1; --i) {
+                    if (arr[i] <= a) break;
+                    arr[i + 1] = arr[i];
+                    brr[i + 1] = brr[i];
+                }
+                arr[i + 1] = a;
+                brr[i + 1] = b;
+            }
+            if (jstack == 0) return;
+            ir = istack[jstack];
+            l = istack[jstack - 1];
+            jstack -= 2;
+        } else {
+            int k = (l + ir) / 2;
+            double t; int u;
+#define PP_SWAP(x, y) do { t = arr[x]; arr[x] = arr[y]; arr[y] = t; u = brr[x]; brr[x] = brr[y]; brr[y] = u; } while (0)
+            PP_SWAP(k, l + 1);
+            if (arr[l + 1] > arr[ir]) PP_SWAP(l + 1, ir);
+            if (arr[l] > arr[ir]) PP_SWAP(l, ir);
+            if (arr[l + 1] > arr[l]) PP_SWAP(l + 1, l);
+            int i = l + 1, j = ir;
+            double a = arr[l];
+            int b = brr[l];
+            for (;;) {
+                do { ++i; } while (arr[i] < a);
+                do { --j; } while (arr[j] > a);
+                if (j < i) break;
+                PP_SWAP(i, j);
+            }
+#undef PP_SWAP
+            arr[l] = arr[j]; arr[j] = a;
+            brr[l] = brr[j]; brr[j] = b;
+            jstack += 2;
+            if (ir - i + 1 >= j - l) { istack[jstack] = ir; istack[jstack - 1] = i; ir = j - 1; }
+            else { istack[jstack] = j - 1; istack[jstack - 1] = l; l = i; }
+        }
+    }
+}
+
+__device__ __forceinline__ void pp_ij(const PP &S, int ib, int &i, int &j)
+{
+    int jr = ib % S.M;
+    if (jr != 0) { j = jr; i = (ib - jr) / S.M + 1; } else { j = S.M; i = ib / S.M; }
+}
+
+// ------------------------------------------------------------------ load + CSORT (PRE/csort.f90:32-62)
+__global__ void k_pp_load(PP S, const double *qin, const unsigned char *present)
+{
+    for (int ib = blockIdx.x * blockDim.x + threadIdx.x + 1; ib < S.nb; ib += gridDim.x * blockDim.x) {
+        bool p = present[ib - 1] != 0;
+        double v = p ? qin[ib - 1] : -1.0;
+        if (p && !(v > 0.0)) atomicExch(&S.cnt[7], 4);
+        S.q[ib] = v;
+        S.pres[ib] = p;
+        S.rank[ib] = 0;
+        S.stamp[ib] = 0;
+    }
+}
+
+// ------------------------------------------------------------------ WBB boundary channel (PRE/wbb_sr.f90:95-160)
+// rim cells (a neighbour outside the raster or outside the catchment) are lowered to quota_min*cqm, the last of them in
+// the reference's scan (north row first, west to east) to quota_min*cqm*cqg: the outlet
+__global__ void k_pp_gronda_mark(PP S)
+{
+    for (int ib = blockIdx.x * blockDim.x + threadIdx.x + 1; ib < S.nb; ib += gridDim.x * blockDim.x) {
+        if (!S.pres[ib]) continue;
+        atomicMin((unsigned long long *)&S.scal[1], (unsigned long long)__double_as_longlong(S.q[ib]));   // positive doubles order like their bits
+        int i, j;
+        pp_ij(S, ib, i, j);
+        bool rim = false;
+        for (int di = -1; di <= 1; ++di)
+            for (int dj = -1; dj <= 1; ++dj) {
+                int ii = i + di, jj = j + dj;
+                if (ii < 1 || ii > S.N || jj < 1 || jj > S.M) { rim = true; continue; }
+                if (!S.pres[ib + S.M * di + dj]) rim = true;
+            }
+        if (rim) {
+            S.stamp[ib] = -1;
+            atomicAdd(&S.cnt[9], 1);
+            atomicMax(&S.cnt[10], (S.M - j) * S.N + (i - 1));
+        }
+    }
+}
+
+__global__ void k_pp_gronda_apply(PP S)
+{
+    const double quota_min = S.scal[1];
+    const double qg = rmul(quota_min, (double)S.h.cqm0), qc = rmul(qg, (double)S.h.cqg0);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double rise = rmul(rmul(rmul((double)S.cnt[9], S.h.delta_x0), (double)sqrtf(2.0f)), S.h.pt0);
+        if (radd(qg, rise) >= quota_min) atomicExch(&S.cnt[7], 5);                            // wbb_sr.f90:144-158
+    }
+    for (int ib = blockIdx.x * blockDim.x + threadIdx.x + 1; ib < S.nb; ib += gridDim.x * blockDim.x) {
+        if (S.stamp[ib] != -1) continue;
+        int i, j;
+        pp_ij(S, ib, i, j);
+        S.q[ib] = ((S.M - j) * S.N + (i - 1) == S.cnt[10]) ? qc : qg;
+        S.stamp[ib] = 0;
+    }
+}
+
+__global__ void k_pp_csort(PP S)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    int n = 0;
+    for (int ib = 1; ib < S.nb; ++ib)
+        if (S.pres[ib]) { ++n; S.key[n] = S.q[ib]; S.lst1[n] = ib; }
+    pp_qsort(n, S.key, S.lst1);
+    for (int l = 1; l <= n; ++l) {            // descending order (csort.f90:57-61)
+        int ib = S.lst1[n - l + 1];
+        S.order[l] = ib;
+        S.rank[ib] = l;
+    }
+}
+
+// ------------------------------------------------------------------ DEPIT
+// parallel proof that DEPIT has nothing to do: no cell but the outlet lacks a strictly lower neighbour
+__global__ void k_pp_pitcheck(PP S)
+{
+    int outlet = S.order[S.nc];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && S.nc > 1) {
+        double ql = S.q[outlet], qsl = S.q[S.order[S.nc - 1]];
+        if (rsub(qsl, ql) < rmul(EPS64, S.h.delta_x0)) atomicExch(&S.cnt[7], 2);       // depit.f90:56
+    }
+    for (int ib = blockIdx.x * blockDim.x + threadIdx.x + 1; ib < S.nb; ib += gridDim.x * blockDim.x) {
+        if (!S.pres[ib] || ib == outlet) continue;
+        int i, j;
+        pp_ij(S, ib, i, j);
+        double qc = S.q[ib];
+        bool lower = false;
+        for (int di = -1; di <= 1; ++di)
+            for (int dj = -1; dj <= 1; ++dj) {
+                int ii = i + di, jj = j + dj;
+                if ((di == 0 && dj == 0) || ii < 1 || ii > S.N || jj < 1 || jj > S.M) continue;
+                double qn = S.q[ib + S.M * di + dj];
+                if (qn >= 0.0 && qn < qc) lower = true;
+            }
+        if (!lower) atomicAdd(&S.cnt[5], 1);
+    }
+}
+
+// the reference's sweeps, one device thread (PRE/depit.f90:63-140)
+__global__ void k_pp_depit(PP S)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    const int nc = S.nc, N = S.N, M = S.M;
+    const double eps = rmul(S.h.pt0, S.h.delta_x0);
+    const int outlet = S.order[nc];
+    int *pit1 = S.lst1, *pit2 = S.lst2;
+    for (int l = 1; l <= nc; ++l) pit1[nc - l + 1] = S.order[l];
+    int n_pits = nc, total = 0, pass = 0;
+    for (;;) {
+        int nn_mod = 0, nn_pit = 0;
+        ++pass;
+        for (int n = 1; n <= n_pits; ++n) {
+            int ib = pit1[n];
+            if (ib == outlet) continue;
+            double qc = S.q[ib];
+            int i, j;
+            pp_ij(S, ib, i, j);
+            double qmin = DBL_MAX;
+            bool lower = false;
+            for (int di = -1; di <= 1 && !lower; ++di)
+                for (int dj = -1; dj <= 1; ++dj) {
+                    int ii = i + di, jj = j + dj;
+                    if ((di == 0 && dj == 0) || ii < 1 || ii > N || jj < 1 || jj > M) continue;
+                    double qn = S.q[ib + M * di + dj];
+                    if (qn < 0.0) continue;
+                    if (qn < qc) { lower = true; break; }
+                    if (qn < qmin) qmin = qn;
+                }
+            if (lower) continue;
+            if (qc <= qmin) {
+                S.q[ib] = radd(qmin, eps);
+                ++total; ++nn_mod;
+                for (int di = -1; di <= 1; ++di)
+                    for (int dj = -1; dj <= 1; ++dj) {
+                        int ii = i + di, jj = j + dj;
+                        if ((di == 0 && dj == 0) || ii < 1 || ii > N || jj < 1 || jj > M) continue;
+                        int nbr = ib + M * di + dj;
+                        if (!S.pres[nbr]) continue;
+                        if (S.stamp[nbr] != pass) { S.stamp[nbr] = pass; pit2[++nn_pit] = nbr; }
+                    }
+            }
+        }
+        if (nn_mod == 0) break;
+        for (int n = 1; n <= nn_pit; ++n) S.key[n] = S.q[pit2[n]];
+        pp_qsort(nn_pit, S.key, pit2);
+        int *t = pit1; pit1 = pit2; pit2 = t;
+        n_pits = nn_pit;
+    }
+    S.cnt[6] = total;
+    S.cnt[8] = pass;
+}
+
+// ------------------------------------------------------------------ FACET (PRE/facet.f90:10-47)
+__device__ __forceinline__ void pp_facet(double e0, double e1, double e2, double dx, double dy, double &r, double &s)
+{
+    const double pi = 4.0 * atan(1.0);
+    double s1 = rdiv(rsub(e0, e1), dx), s2 = rdiv(rsub(e1, e2), dx);
+    if (fabs(s1) < EPS64) r = (s2 >= 0.0) ? pi / 2.0 : -pi / 2.0;
+    else r = atan(rdiv(s2, s1));
+    double sp = sqrt(radd(rmul(s1, s1), rmul(s2, s2)));
+    double sd = rdiv(rsub(e0, e2), sqrt(radd(rmul(dx, dx), rmul(dy, dy))));
+    if (r >= 0.0 && r <= pi / 4.0 && s1 >= 0.0) { s = sp; return; }
+    if (s1 > sd) { s = s1; r = 0.0; } else { s = sd; r = pi / 4.0; }
+}
+
+__constant__ signed char PP_FA[8] = {2, 2, 6, 6, 8, 8, 4, 4};      // e1 of the eight facets in DSF's order (dsf.f90:103-245)
+__constant__ signed char PP_FB[8] = {1, 3, 3, 9, 9, 7, 7, 1};      // e2
+__constant__ signed char PP_DI[10] = {0, -1, -1, -1, 0, 0, 0, 1, 1, 1};   // p_outflow = 3*di + dj + 5 (dsf.f90:368-375)
+__constant__ signed char PP_DJ[10] = {0, -1, 0, 1, -1, 0, 1, -1, 0, 1};
+
+// window analysis of every cell: CCA (PRE/cca.f90:43-85), the facet search of SMEAN / DSF and the deviations (dsf.f90:247-268)
+__global__ void k_pp_local(PP S)
+{
+    const double dx = S.h.delta_x, dy = S.h.delta_y;
+    const double pi = 4.0 * atan(1.0);
+    for (int ib = blockIdx.x * blockDim.x + threadIdx.x + 1; ib < S.nb; ib += gridDim.x * blockDim.x) {
+        if (!S.pres[ib]) continue;
+        int i, j;
+        pp_ij(S, ib, i, j);
+        double e[10];
+        bool full = true;
+        int l = 0;
+        for (int di = -1; di <= 1; ++di)
+            for (int dj = -1; dj <= 1; ++dj) {
+                ++l;
+                e[l] = 0.0;
+                int ii = i + di, jj = j + dj;
+                if (ii < 1 || ii > S.N || jj < 1 || jj > S.M) { full = false; continue; }
+                double qn = S.q[ib + S.M * di + dj];
+                if (qn < 0.0) { full = false; continue; }
+                e[l] = qn;
+            }
+        // CCA: default method 2 (D8) on the rim of the catchment, curvature decides inside
+        int dm = 2;
+        float Kp = 0.f;
+        if (full) {
+            double dx2 = rmul(dx, dx);
+            double zx = rdiv(rsub(e[6], e[4]), rmul(2.0, dx)), zy = rdiv(rsub(e[2], e[8]), rmul(2.0, dx));
+            double zxx = rdiv(radd(rsub(e[6], rmul(2.0, e[5])), e[4]), dx2);
+            double zyy = rdiv(radd(rsub(e[2], rmul(2.0, e[5])), e[8]), dx2);
+            double zxy = rdiv(rsub(radd(radd(-e[1], e[3]), e[7]), e[9]), rmul(4.0, dx2));
+            double p, qq;
+            if (fabs(zx) > EPS64 || fabs(zy) > EPS64) { p = radd(rmul(zx, zx), rmul(zy, zy)); qq = radd(p, 1.0); }
+            else { p = (double)1.0e-9f; qq = radd(p, 1.0); }
+            double num = radd(rsub(rmul(rmul(zxx, zy), zy), rmul(rmul(rmul(2.0, zxy), zx), zy)), rmul(rmul(zyy, zx), zx));
+            double Kc = rdiv(num, pow(p, 1.5));
+            if (fabs(Kc) < EPS64) Kc = 0.0;
+            double nump = radd(radd(rmul(rmul(zxx, zx), zx), rmul(rmul(rmul(2.0, zxy), zx), zy)), rmul(rmul(zyy, zy), zy));
+            Kp = (float)rdiv(nump, rmul(p, pow(qq, 1.5)));
+            dm = (Kc < (double)S.h.CC_threshold) ? 1 : 2;
+        }
+        S.dm0[ib] = dm;
+        S.Kp[ib] = Kp;
+        // steepest facet
+        double e0 = e[5], smax = 0.0, rmax = 0.0, e1f = 0.0, e2f = 0.0, sigma = 1.0;
+        int po1 = 0, po2 = 0;
+        for (int f = 0; f < 8; ++f) {
+            double e1 = e[PP_FA[f]], e2 = e[PP_FB[f]];
+            if (e1 * e2 != 0.0) {
+                double r, s;
+                pp_facet(e0, e1, e2, dx, dy, r, s);
+                if (s > smax) { e1f = e1; e2f = e2; rmax = r; smax = s; po1 = PP_FA[f]; po2 = PP_FB[f]; sigma = (f & 1) ? -1.0 : 1.0; }
+            }
+        }
+        S.smax[ib] = smax;
+        if (smax > 0.0) {
+            double d1, d2;
+            if (S.h.imethod == 1) { d1 = rmax; d2 = rsub(pi / 4, rmax); }
+            else { d1 = rmul(dx, sin(rmax)); d2 = rmul(rmul(dx, sqrt(2.0)), sin(rsub(pi / 4.0, rmax))); }
+            if (sigma == 1.0) d2 = -d2; else d1 = -d1;
+            S.dev1[ib] = d1; S.dev2[ib] = d2;
+            S.de1[ib] = rsub(e0, e1f); S.de2[ib] = rsub(e0, e2f);
+            S.po1[ib] = (signed char)po1; S.po2[ib] = (signed char)po2;
+        } else {
+            // no facet with both corners inside the catchment: the lowest neighbour takes everything (dsf.f90:447-460)
+            double emin = DBL_MAX;
+            int pL = 0;
+            for (int k = 1; k <= 9; ++k)
+                if (e[k] != 0.0 && k != 5 && e[k] < emin) { emin = e[k]; pL = k; }
+            S.dev1[ib] = 0.0; S.dev2[ib] = 0.0;
+            S.de1[ib] = rsub(e0, emin); S.de2[ib] = rsub(e0, emin);
+            S.po1[ib] = (signed char)pL; S.po2[ib] = (signed char)pL;
+            if (pL == 0 && ib != S.order[S.nc]) atomicExch(&S.cnt[7], 6);
+        }
+    }
+}
+
+// SMEAN (PRE/smean.f90:33-164): the mean of the steepest slopes, summed in the reference's order by one warp
+__global__ void k_pp_smean(PP S)
+{
+    const int lane = threadIdx.x;
+    double sum = 0.0, cnt = 0.0;
+    const int outlet = S.order[S.nc];
+    for (int base = 1; base <= S.nc; base += 32) {
+        int n = base + lane;
+        int ib = (n <= S.nc) ? S.order[n] : 0;
+        double v = (ib && ib != outlet) ? S.smax[ib] : -1.0;
+        for (int k = 0; k < 32; ++k) {
+            double vk = __shfl_sync(0xffffffffu, v, k);
+            if (vk >= 0.0) { sum = radd(sum, vk); cnt += 1.0; }
+        }
+    }
+    if (lane == 0) S.scal[0] = rdiv(sum, cnt);
+}
+
+// ------------------------------------------------------------------ DSF as a dependency wavefront
+__global__ void k_pp_deps(PP S)
+{
+    for (int ib = blockIdx.x * blockDim.x + threadIdx.x + 1; ib < S.nb; ib += gridDim.x * blockDim.x) {
+        if (!S.pres[ib]) continue;
+        int i, j;
+        pp_ij(S, ib, i, j);
+        int r = S.rank[ib], d = 0;
+        for (int di = -1; di <= 1; ++di)
+            for (int dj = -1; dj <= 1; ++dj) {
+                int ii = i + di, jj = j + dj;
+                if ((di == 0 && dj == 0) || ii < 1 || ii > S.N || jj < 1 || jj > S.M) continue;
+                int nbr = ib + S.M * di + dj;
+                if (S.pres[nbr] && S.rank[nbr] < r) ++d;
+            }
+        // a cell without a usable facet reads the channel flag the reference's loop carries over from the cell before
+        // it in the order (local hcID of dsf.f90 is never reset): one more dependency
+        if (S.smax[ib] == 0.0 && r > 1 && r < S.nc) ++d;
+        S.dep[ib] = d;
+        if (d == 0) S.front[0][atomicAdd(&S.cnt[0], 1)] = ib;
+    }
+}
+
+__device__ __forceinline__ int pp_channel(const PP &S, double A_out, float ASk)
+{
+    if (S.h.nchc == 1) return (A_out <= S.h.A_threshold) ? 0 : 1;
+    return (ASk <= S.h.ASk_threshold) ? 0 : 1;
+}
+
+__device__ void pp_cell(const PP &S, int ib)
+{
+    const int N = S.N, M = S.M;
+    const double dx = S.h.delta_x;
+    const double A_cell = rmul(dx, dx);
+    const int r = S.rank[ib];
+    int i, j;
+    pp_ij(S, ib, i, j);
+    // donors, in the order the reference visits them
+    int dn[8], dr[8], dk[8], nd = 0;
+    for (int di = -1; di <= 1; ++di)
+        for (int dj = -1; dj <= 1; ++dj) {
+            int ii = i + di, jj = j + dj;
+            if ((di == 0 && dj == 0) || ii < 1 || ii > N || jj < 1 || jj > M) continue;
+            int nbr = ib + M * di + dj;
+            if (!S.pres[nbr]) continue;
+            int rn = S.rank[nbr];
+            if (rn > r) continue;
+            int p = 3 * (-di) + (-dj) + 5;      // direction from the neighbour to this cell
+            int which = (S.p1[nbr] == p) ? 1 : (S.p2[nbr] == p) ? 2 : 0;
+            if (!which) continue;
+            int k = nd++;
+            while (k > 0 && dr[k - 1] > rn) { dr[k] = dr[k - 1]; dn[k] = dn[k - 1]; dk[k] = dk[k - 1]; --k; }
+            dr[k] = rn; dn[k] = nbr; dk[k] = which;
+        }
+    double A = 0.0, Sd = 0.0;
+    int hcin = 0;
+    for (int k = 0; k < nd; ++k) {
+        int n = dn[k];
+        double w = (double)(dk[k] == 1 ? S.w1[n] : S.w2[n]);
+        double aw = rmul(S.Aout[n], w);
+        A = radd(A, aw);
+        if (S.sflag[n] & dk[k]) Sd = radd(Sd, rmul(aw, dk[k] == 1 ? S.sd1[n] : S.sd2[n]));
+        if (hcin == 0 && fabsf((float)w) > EPS32) hcin = S.hc[n];
+    }
+    S.Ain[ib] = A;
+    S.sdn[ib] = Sd;
+    if (r == S.nc) { S.hc[ib] = hcin; S.dm[ib] = S.dm0[ib]; return; }              // outlet: features assigned apart (dsf.f90:81)
+    const double A_out = radd(A, A_cell);
+    S.Aout[ib] = A_out;
+    double sumdev = (A == 0.0) ? 0.0 : rdiv(Sd, A);
+    const double smax = S.smax[ib], lam = S.h.lambda;
+    if (smax > 0.0) {
+        const double d1 = S.dev1[ib], d2 = S.dev2[ib];
+        if (fabs(d1) <= EPS64 || fabs(d2) <= EPS64) sumdev = 0.0;
+        int dm = S.dm0[ib], hc = hcin;
+        float epl1 = (float)dx, epl2 = (float)rmul(sqrt(2.0), dx);
+        float ls1 = (float)rdiv(S.de1[ib], (double)epl1), ls2 = (float)rdiv(S.de2[ib], (double)epl2);
+        float ASk = (float)rmul(A_out, pow(smax, (double)S.h.kas));
+        double sd1 = radd(rmul(lam, sumdev), d1), sd2 = radd(rmul(lam, sumdev), d2);
+        if (hc == 0) hc = pp_channel(S, A_out, ASk);
+        if (hc == 1 && S.h.ndcf == 1) dm = 2;
+        double a1 = fabs(sd1), a2 = fabs(sd2);
+        float w1, w2;
+        if (dm == 1) {
+            if (fabs(d1) <= EPS64) { w1 = 1.f; w2 = 0.f; }
+            else if (fabs(d2) <= EPS64) { w1 = 0.f; w2 = 1.f; }
+            else {
+                w1 = (float)rdiv(a2, radd(a1, a2));
+                w2 = (float)rdiv(a1, radd(a1, a2));
+                if (w1 < 1.0e-6f) { w1 = 0.f; w2 = 1.f; }
+                if (w2 < 1.0e-6f) { w1 = 1.f; w2 = 0.f; }
+            }
+        } else {
+            if (rdiv(fabs(rsub(a1, a2)), dx) < 10e-14 && S.de1[ib] > 0.0) { w1 = 1.f; w2 = 0.f; epl2 = 0.f; ls2 = 0.f; }
+            else if (a1 < a2 && S.de1[ib] > 0.0) { w1 = 1.f; w2 = 0.f; epl2 = 0.f; ls2 = 0.f; }
+            else if (a1 > a2 || S.de2[ib] > 0.0) { w1 = 0.f; w2 = 1.f; epl1 = 0.f; ls1 = 0.f; }
+            else { w1 = 0.f; w2 = 0.f; atomicExch(&S.cnt[7], 7); }
+        }
+        S.w1[ib] = w1; S.w2[ib] = w2; S.epl1[ib] = epl1; S.epl2[ib] = epl2; S.ls1[ib] = ls1; S.ls2[ib] = ls2;
+        S.sd1[ib] = sd1; S.sd2[ib] = sd2; S.sflag[ib] = 3;
+        S.dm[ib] = dm; S.hc[ib] = hc; S.hc_after[ib] = hc; S.ASk[ib] = ASk;
+        __threadfence();
+        S.p1[ib] = S.po1[ib]; S.p2[ib] = S.po2[ib];
+    } else {
+        int hc = (r > 1) ? S.hc_after[S.order[r - 1]] : 0;        // carried over, see k_pp_deps
+        const int pL = S.po1[ib];
+        S.dm[ib] = S.dm0[ib];
+        if ((pL & 1) == 0) {
+            float epl1 = (float)dx, ls1 = (float)rdiv(S.de1[ib], (double)epl1);
+            float ASk = (float)rmul(A_out, pow((double)ls1, (double)S.h.kas));
+            if (hc == 0) hc = pp_channel(S, A_out, ASk);
+            S.w1[ib] = 1.f; S.epl1[ib] = epl1; S.ls1[ib] = ls1; S.sflag[ib] = 0; S.sd1[ib] = rmul(lam, sumdev);
+            S.ASk[ib] = ASk; S.hc[ib] = hc; S.hc_after[ib] = hc;
+            __threadfence();
+            S.p1[ib] = pL;
+        } else {
+            float epl2 = (float)rmul(sqrt(2.0), dx), ls2 = (float)rdiv(S.de2[ib], (double)epl2);
+            float ASk = (float)rmul(A_out, pow((double)ls2, (double)S.h.kas));
+            S.w2[ib] = 1.f; S.epl2[ib] = epl2; S.ls2[ib] = ls2; S.sflag[ib] = 2; S.sd2[ib] = rmul(lam, sumdev);
+            S.ASk[ib] = ASk; S.hc[ib] = hc; S.hc_after[ib] = hc;
+            __threadfence();
+            S.p2[ib] = pL;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pp_sweep(PP S)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    int wave = 0;
+    for (;;) {
+        const int ncur = *((volatile int *)&S.cnt[wave % 3]);
+        if (ncur == 0) break;
+        int *cur = S.front[wave & 1], *nxt = S.front[(wave + 1) & 1];
+        int *nnext = &S.cnt[(wave + 1) % 3];
+        if (gtid == 0) { S.cnt[(wave + 2) % 3] = 0; S.cnt[3] += ncur; S.cnt[4] = wave + 1; }
+        for (int t = gtid; t < ncur; t += gsz) {
+            const int ib = cur[t];
+            pp_cell(S, ib);
+            __threadfence();
+            const int r = S.rank[ib];
+            int i, j;
+            pp_ij(S, ib, i, j);
+            for (int di = -1; di <= 1; ++di)
+                for (int dj = -1; dj <= 1; ++dj) {
+                    int ii = i + di, jj = j + dj;
+                    if ((di == 0 && dj == 0) || ii < 1 || ii > S.N || jj < 1 || jj > S.M) continue;
+                    int nbr = ib + S.M * di + dj;
+                    if (S.pres[nbr] && S.rank[nbr] > r && atomicSub(&S.dep[nbr], 1) == 1) nxt[atomicAdd(nnext, 1)] = nbr;
+                }
+            if (r + 1 < S.nc) {
+                int nx = S.order[r + 1];
+                if (S.smax[nx] == 0.0 && atomicSub(&S.dep[nx], 1) == 1) nxt[atomicAdd(nnext, 1)] = nx;
+            }
+        }
+        grid.sync();
+        ++wave;
+    }
+}
+
+// phantom channel end of the outlet cell (PRE/dsf.f90:531-600)
+__global__ void k_pp_outlet(PP S)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    const int N = S.N, M = S.M, ib = S.order[S.nc];
+    const double dx = S.h.delta_x, A_cell = rmul(dx, dx);
+    int i, j;
+    pp_ij(S, ib, i, j);
+    int nvo = 0, p_out = 0;
+    double A_max = 0.0;
+    float ls_out = 0.f;
+    for (int ii = i - 1; ii <= i + 1; ++ii)
+        for (int jj = j - 1; jj <= j + 1; ++jj) {
+            if (ii < 1 || ii > N || jj < 1 || jj > M) continue;
+            int nbr = (ii - 1) * M + jj;
+            if (!S.pres[nbr]) continue;
+            int p_in = 3 * (ii - i) + (jj - j) + 5;
+            for (int k = 1; k <= 2; ++k) {
+                int pk = (k == 1) ? S.p1[nbr] : S.p2[nbr];
+                if (p_in + pk != 10) continue;
+                double Ao = rmul(radd(S.Ain[nbr], A_cell), (double)((k == 1) ? S.w1[nbr] : S.w2[nbr]));
+                if (Ao > A_max) {
+                    A_max = Ao;
+                    p_out = pk;
+                    ls_out = (k == 1) ? S.ls1[nbr] : S.ls2[nbr];
+                    int ivo = i + PP_DI[p_out], jvo = j + PP_DJ[p_out];
+                    nvo = (ivo < 1 || ivo > N || jvo < 1 || jvo > M || !S.pres[(ivo - 1) * M + jvo]) ? 1 : 0;
+                }
+            }
+        }
+    if (nvo == 0) p_out = S.h.p_outflow_vo;
+    if ((p_out & 1) == 0) { S.p1[ib] = p_out; S.w1[ib] = 1.f; S.epl1[ib] = (float)dx; S.ls1[ib] = ls_out; }
+    else { S.p2[ib] = p_out; S.w2[ib] = 1.f; S.epl2[ib] = (float)rmul(sqrt(2.0), dx); S.ls2[ib] = ls_out; }
+}
+
+// ------------------------------------------------------------------ HG (PRE/hg.f90:39-113)
+__device__ __forceinline__ float pp_law(float c, float Q, float ex1, float ex2, float wexp, double RA, float w)
+{
+    // c * Q**(-ex1) in single precision, (RA*w)**(wexp*(ex2-ex1)) in double, product stored in single precision
+    float lead = __fmul_rn(c, (float)pow((double)Q, (double)(-ex1)));
+    float ex = __fmul_rn(wexp, __fsub_rn(ex2, ex1));
+    return (float)rmul((double)lead, pow(rmul(RA, (double)w), (double)ex));
+}
+
+__global__ void k_pp_hg(PP S)
+{
+    const CathyPreproParams &h = S.h;
+    const double A_cell = rmul(h.delta_x, h.delta_y);
+    for (int ib = blockIdx.x * blockDim.x + threadIdx.x + 1; ib < S.nb; ib += gridDim.x * blockDim.x) {
+        if (!S.pres[ib]) continue;
+        const double A_out = radd(S.Ain[ib], A_cell);
+        const float w1 = S.w1[ib], w2 = S.w2[ib];
+        const bool rill = S.hc[ib] == 0;
+        const double RA = rdiv(A_out, rill ? h.As_rf : h.As_cf);
+        const float Q = rill ? h.Qsf_rf : h.Qsf_cf, we = rill ? h.w_rf : h.w_cf, Wsf = rill ? h.Wsf_rf : h.Wsf_cf;
+        const float b1 = rill ? h.b1_rf : h.b1_cf, b2 = rill ? h.b2_rf : h.b2_cf;
+        const float kS = rill ? h.kSsf_rf : h.kSsf_cf, y1 = rill ? h.y1_rf : h.y1_cf, y2 = rill ? h.y2_rf : h.y2_cf;
+        S.b1[ib] = b1;
+        S.y1[ib] = y1;
+        S.Ws1[ib] = (fabsf(w1) > EPS32) ? pp_law(Wsf, Q, b1, b2, we, RA, w1) : 0.f;
+        S.Ws2[ib] = (fabsf(w2) > EPS32) ? pp_law(Wsf, Q, b1, b2, we, RA, w2) : 0.f;
+        S.kS1[ib] = (fabsf(w1) > EPS32) ? pp_law(kS, Q, y1, y2, we, RA, w1) : 0.f;
+        S.kS2[ib] = (fabsf(w2) > EPS32) ? pp_law(kS, Q, y1, y2, we, RA, w2) : 0.f;
+        S.nrc[ib] = rill ? (float)rdiv(h.delta_x, h.dr) : 1.f;
+    }
+}
+
+// ------------------------------------------------------------------ host driver
+template <class T>
+static cudaError_t pp_alloc(T **p, size_t n, bool zero = true)
+{
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e == cudaSuccess && zero) e = cudaMemset(*p, 0, n * sizeof(T));
+    return e;
+}
+
+extern "C" const char *cathy_prepro_last_error(void) { return pp_err; }
+
+extern "C" int32_t cathy_prepro_run(const CathyPreproParams *p, const double *quota_in, const uint8_t *present, int32_t device,
+                                    CathyPreproOut *out)
+{
+    int32_t rc = 0;
+    PP S;
+    memset(&S, 0, sizeof S);
+    void *all[64];
+    int nall = 0;
+    double *d_qin = nullptr;
+    unsigned char *d_present = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int cnt[16];
+    int launches = 0;
+    pp_err[0] = 0;
+    if (!p || !quota_in || !present || !out) PFAIL(-1, "cathy_prepro_run: null argument");
+    if (p->abi_version != CATHY_PREPRO_ABI_VERSION) PFAIL(-1, "cathy_prepro_run: ABI version %d, library has %d", p->abi_version, CATHY_PREPRO_ABI_VERSION);
+    if (p->N < 1 || p->M < 1 || (long long)p->N * p->M > 2000000000LL) PFAIL(-1, "cathy_prepro_run: bad raster size %d x %d", p->N, p->M);
+    if (p->imethod != 1 && p->imethod != 2) PFAIL(-1, "unespected imethod!");
+    if (p->nchc == 3) PFAIL(-1, "channel initiation by normalised divergence (nchc = 3) is not built: the reference reads an uninitialised curvature on the rim cells (PRE/cca.f90:24,87)");
+    if (p->nchc != 1 && p->nchc != 2) PFAIL(-1, "nchc out of range!");
+    if (!(p->delta_x > 0.0) || !(p->delta_x0 > 0.0)) PFAIL(-1, "cathy_prepro_run: grid spacing must be positive");
+    {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) PFAIL(-100, "cathy_prepro_run: no CUDA device (there is no CPU path)");
+    }
+    PCK(cudaSetDevice(device));
+    {
+        S.h = *p;
+        S.N = p->N; S.M = p->M; S.nb = p->N * p->M + 1;
+        long long nc = 0;
+        for (long long k = 0; k < (long long)p->N * p->M; ++k) nc += present[k] != 0;
+        if (nc < 1) PFAIL(-1, "cathy_prepro_run: no catchment cell");
+        S.nc = (int)nc;
+        const size_t nb = (size_t)S.nb, n1 = (size_t)S.nc + 1;
+#define PA(field, n) do { PCK(pp_alloc(&S.field, (n))); all[nall++] = (void *)S.field; } while (0)
+        PA(q, nb); PA(pres, nb); PA(order, n1); PA(rank, nb); PA(key, n1); PA(lst1, n1); PA(lst2, n1); PA(stamp, nb);
+        PA(smax, nb); PA(dev1, nb); PA(dev2, nb); PA(de1, nb); PA(de2, nb); PA(po1, nb); PA(po2, nb); PA(Kp, nb); PA(dm0, nb);
+        PA(Ain, nb); PA(sdn, nb); PA(Aout, nb); PA(sd1, nb); PA(sd2, nb);
+        PA(w1, nb); PA(w2, nb); PA(ls1, nb); PA(ls2, nb); PA(epl1, nb); PA(epl2, nb); PA(ASk, nb);
+        PA(p1, nb); PA(p2, nb); PA(hc, nb); PA(dm, nb); PA(hc_after, nb); PA(sflag, nb);
+        PA(dep, nb); PA(front[0], n1); PA(front[1], n1); PA(cnt, 16); PA(scal, 4);
+        PA(Ws1, nb); PA(Ws2, nb); PA(b1, nb); PA(kS1, nb); PA(kS2, nb); PA(y1, nb); PA(nrc, nb);
+#undef PA
+        PCK(pp_alloc(&d_qin, nb - 1, false));
+        PCK(pp_alloc(&d_present, nb - 1, false));
+        PCK(cudaMemcpy(d_qin, quota_in, (nb - 1) * sizeof(double), cudaMemcpyHostToDevice));
+        PCK(cudaMemcpy(d_present, present, nb - 1, cudaMemcpyHostToDevice));
+        PCK(cudaEventCreate(&ev0));
+        PCK(cudaEventCreate(&ev1));
+        for (int k = 0; k < 8; ++k) PCK(cudaEventCreate(&evs[k]));
+        PCK(cudaEventRecord(ev0, 0));
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+        const int TPB = 256;
+        const int GRID = nsm * 8;
+        k_pp_load<<<GRID, TPB>>>(S, d_qin, d_present); ++launches;
+        if (p->bcc != 0) {
+            const double everest = (double)8844.43f;                            // wbb_sr.f90:185, a single-precision literal
+            PCK(cudaMemcpy(&S.scal[1], &everest, sizeof(double), cudaMemcpyHostToDevice));
+            k_pp_gronda_mark<<<GRID, TPB>>>(S); ++launches;
+            k_pp_gronda_apply<<<GRID, TPB>>>(S); ++launches;
+        }
+        PCK(cudaEventRecord(evs[0], 0));
+        k_pp_csort<<<1, 32>>>(S); ++launches;
+        PCK(cudaEventRecord(evs[1], 0));
+        k_pp_pitcheck<<<GRID, TPB>>>(S); ++launches;
+        PCK(cudaMemcpy(cnt, S.cnt, sizeof cnt, cudaMemcpyDeviceToHost));
+        if (cnt[7] == 4) PFAIL(-4, "non-positive elevation inside the catchment: the reference uses 0 and negative values as 'no cell' marks");
+        if (cnt[7] == 5) PFAIL(-5, "boundary channel: after the depitting the highest boundary channel cell would be above the lowest dem cell; a smaller coefficient for boundary channel elevation definition is needed");
+        if (cnt[7] == 2) PFAIL(-2, "catchment with more than one outlet cell!");
+        PCK(cudaEventRecord(evs[2], 0));
+        if (cnt[5] > 0) {
+            k_pp_depit<<<1, 32>>>(S); ++launches;
+            PCK(cudaEventRecord(evs[3], 0));
+            k_pp_csort<<<1, 32>>>(S); ++launches;
+        } else PCK(cudaEventRecord(evs[3], 0));
+        PCK(cudaEventRecord(evs[4], 0));
+        k_pp_local<<<GRID, TPB>>>(S); ++launches;
+        k_pp_smean<<<1, 32>>>(S); ++launches;
+        PCK(cudaEventRecord(evs[5], 0));
+        k_pp_deps<<<GRID, TPB>>>(S); ++launches;
+        {
+            int per_sm = 0;
+            PCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pp_sweep, TPB, 0));
+            if (per_sm < 1) PFAIL(-100, "k_pp_sweep does not fit on an SM");
+            if (per_sm > 4) per_sm = 4;
+            void *args[] = {(void *)&S};
+            PCK(cudaLaunchCooperativeKernel((void *)k_pp_sweep, dim3(nsm * per_sm), dim3(TPB), args, 0, 0)); ++launches;
+        }
+        PCK(cudaEventRecord(evs[6], 0));
+        k_pp_outlet<<<1, 32>>>(S); ++launches;
+        k_pp_hg<<<GRID, TPB>>>(S); ++launches;
+        PCK(cudaGetLastError());
+        PCK(cudaEventRecord(ev1, 0));
+        PCK(cudaDeviceSynchronize());
+        PCK(cudaMemcpy(cnt, S.cnt, sizeof cnt, cudaMemcpyDeviceToHost));
+        if (cnt[7] == 6) PFAIL(-1, "s_max = 0, unexpected case! (a cell without any neighbour)");
+        if (cnt[7] == 7) PFAIL(-1, "s_max < 0, unexpected case!");
+        if (cnt[3] != S.nc) PFAIL(-1, "drainage sweep finished %d of %d cells (dependency cycle?)", cnt[3], S.nc);
+        float ms = 0.f;
+        PCK(cudaEventElapsedTime(&ms, ev0, ev1));
+        const size_t ncell = nb - 1;
+#define PD(dst, src, T) do { if (out->dst) PCK(cudaMemcpy(out->dst, S.src + 1, ncell * sizeof(T), cudaMemcpyDeviceToHost)); } while (0)
+        PD(quota, q, double); PD(A_inflow, Ain, double);
+        PD(w_1, w1, float); PD(w_2, w2, float); PD(local_slope_1, ls1, float); PD(local_slope_2, ls2, float);
+        PD(epl_1, epl1, float); PD(epl_2, epl2, float);
+        PD(Ws1_sf_1, Ws1, float); PD(Ws1_sf_2, Ws2, float); PD(b1_sf, b1, float); PD(kSs1_sf_1, kS1, float); PD(kSs1_sf_2, kS2, float);
+        PD(y1_sf, y1, float); PD(nrc, nrc, float);
+        PD(p_outflow_1, p1, int32_t); PD(p_outflow_2, p2, int32_t); PD(hcID, hc, int32_t); PD(dmID, dm, int32_t);
+#undef PD
+        if (out->order) PCK(cudaMemcpy(out->order, S.order + 1, (size_t)S.nc * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        double scal[4];
+        PCK(cudaMemcpy(scal, S.scal, sizeof scal, cudaMemcpyDeviceToHost));
+        out->n_cells = S.nc;
+        out->n_modifications = cnt[6];
+        out->n_waves = cnt[4];
+        out->n_launches = launches;
+        out->mean_s_max = scal[0];
+        out->device_ms = ms;
+        {
+            // csort, pit check, depit, second csort, window analysis + smean, drainage sweep, outlet + hg
+            const int a[7] = {0, 1, 2, 3, 4, 5, 6};
+            for (int k = 0; k < 7; ++k) {
+                float t = 0.f;
+                PCK(cudaEventElapsedTime(&t, evs[a[k]], k == 6 ? ev1 : evs[a[k] + 1]));
+                out->stage_ms[k] = t;
+            }
+            out->stage_ms[7] = cnt[8];
+        }
+    }
+done:
+    for (int k = 0; k < nall; ++k) cudaFree(all[k]);
+    if (d_qin) cudaFree(d_qin);
+    if (d_present) cudaFree(d_present);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    for (int k = 0; k < 8; ++k) if (evs[k]) cudaEventDestroy(evs[k]);
+    return rc;
+}

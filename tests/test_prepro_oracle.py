@@ -1,0 +1,172 @@
+"""CPU: the pre-processor oracle (oracle/prepro_oracle.py) against golden vectors of the reference's own ELF `pycppp`
+(tests/golden/prepro/*.tar.xz, made by tests/golden/make_golden_prepro.py; weill_exemple/prepro = the files COMMITTED in
+the reference next to its bundled project), and the product's host side (hap.in parser / rewriter, raster writers of
+pycathy_wrapper_b200/preprocessor.py) against the same files.  No device work here."""
+import glob
+import os
+import shutil
+import subprocess
+import tarfile
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+CASES = sorted(os.path.basename(p)[:-7] for p in glob.glob(os.path.join(GOLDEN, "prepro", "*.tar.xz")))
+DEEP = {"deep_pits"}                                   # 1e5 DEPIT modifications: slow in the pure-Python oracle
+
+
+def unpack(case, tmp_path):
+    d = str(tmp_path / case)
+    os.makedirs(d, exist_ok=True)
+    with tarfile.open(os.path.join(GOLDEN, "prepro", case + ".tar.xz")) as tf:
+        tf.extractall(d, filter="data")
+    return d
+
+
+def golden_files(d):
+    return sorted(f for f in os.listdir(d) if f not in ("hap.in.orig", "dtm_13.val"))
+
+
+def test_fixture_set_is_complete():
+    assert {"plane17", "rough_lad", "rough_ltd_pbm_d8", "rough_pbm", "chan_ndcf", "chan_ask", "mask", "mask_d8", "deep_pits", "bcc"} <= set(CASES)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_reproduces_pycppp_byte_for_byte(case, tmp_path):
+    from oracle import prepro_oracle as po
+    d = unpack(case, tmp_path)
+    p = po.Prepro(open(d + "/hap.in.orig").read(), open(d + "/dtm_13.val").read()).run()
+    assert p.hap_text_out == open(d + "/hap.in").read()
+    assert p.qoi_a() == open(d + "/qoi_a").read()
+    for name in po.RASTERS:
+        assert p.raster(name) == open(os.path.join(d, name)).read(), name
+
+
+def test_oracle_reproduces_the_prepro_files_committed_in_the_reference(tmp_path):
+    """tests/golden/weill_exemple/prepro: dem, dtm_*, qoi_a as shipped with the reference's bundled project; its
+    dtm_13.val is the `dem` raster itself (the DEM has no pit, so DEPIT leaves it alone)."""
+    from oracle import prepro_oracle as po
+    src = os.path.join(GOLDEN, "weill_exemple", "prepro")
+    dem = np.loadtxt(os.path.join(src, "dem"), skiprows=6)
+    dtm = "\n".join("\t".join("%.3f" % v for v in row) for row in dem) + "\n"
+    p = po.Prepro(open(os.path.join(src, "hap.in")).read(), dtm).run()
+    assert p.n_modifiche == 0
+    for name in po.RASTERS:
+        f = os.path.join(src, name)
+        if os.path.exists(f):
+            assert p.raster(name) == open(f).read(), name
+    assert p.qoi_a() == open(os.path.join(src, "qoi_a")).read()
+
+
+def test_oracle_against_pycppp_elf_when_available(tmp_path):
+    """Live cross-check on a DEM no fixture holds (only where oracle/_ref is staged)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "bin", "pycppp")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref not staged (no /root/reference on this box)")
+    from oracle import prepro_oracle as po
+    from pycathy_wrapper_b200 import synthetic
+    rng = np.random.default_rng(99)
+    r, c = np.mgrid[0:27, 0:22]
+    z = 3.0 - 0.02 * c - 0.013 * r + 0.01 * rng.standard_normal((27, 22))
+    z[:4, :5] = -9999.0
+    a, b = str(tmp_path / "ref"), str(tmp_path / "ora")
+    for d in (a, b):
+        os.makedirs(d)
+        synthetic.write_hapin(d + "/hap.in", 27, 22, 0.5, 0.5)
+        t = open(d + "/hap.in").read().replace("0.130E-06", "0.200E-02")
+        open(d + "/hap.in", "w").write(t)
+        np.savetxt(d + "/dtm_13.val", z, fmt="%.6f")
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "oracle", "_ref", "lib") + ":" + env.get("LD_LIBRARY_PATH", "")
+    subprocess.run([exe], cwd=a, env=env, input="2\n0\n1\n", text=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+    p = po.run_directory(b)
+    assert p.n_modifiche > 0
+    for name in list(po.RASTERS) + ["qoi_a", "hap.in"]:
+        assert open(os.path.join(a, name)).read() == open(os.path.join(b, name)).read(), name
+
+
+def test_oracle_quicksort_is_the_reference_permutation_on_ties():
+    """The order of equal elevations is part of qoi_a; the bundled plane has 400 cells on 96 distinct levels."""
+    from oracle import prepro_oracle as po
+    src = os.path.join(GOLDEN, "weill_exemple", "prepro")
+    order = np.loadtxt(os.path.join(src, "qoi_a"), dtype=int)[1:]
+    dem = np.loadtxt(os.path.join(src, "dem"), skiprows=6)
+    M, N = dem.shape
+    q = dem[::-1].T.reshape(-1)                       # [(i-1)*M + j - 1]
+    keys = [0.0] + [float(v) for v in q]
+    ids = [0] + list(range(1, N * M + 1))
+    po.qsort(N * M, keys, ids)
+    assert ids[:0:-1] == list(order)
+    assert len(np.unique(q)) < N * M and sorted(ids[1:]) == list(range(1, N * M + 1))
+
+
+# ------------------------------------------------------------------ host side of the product (no device)
+@pytest.mark.parametrize("case", ["rough_ltd_pbm_d8", "chan_ask", "mask", "bcc"])
+def test_product_hapin_reader_and_rewriter(case, tmp_path):
+    from oracle import prepro_oracle as po
+    from pycathy_wrapper_b200 import preprocessor as pp
+    d = unpack(case, tmp_path)
+    text = open(d + "/hap.in.orig").read()
+    h, ho = pp.read_hapin(text), po.parse_hap(text)
+    assert set(h) == set(ho)
+    for k in ho:
+        assert float(h[k]) == float(ho[k]), k
+    h["N_celle"] = pp.read_hapin(open(d + "/hap.in").read())["N_celle"]
+    assert pp.write_hapin(h) == open(d + "/hap.in").read()
+
+
+def test_product_hapin_refuses_a_rivulet_spacing_that_does_not_divide_the_cell():
+    from pycathy_wrapper_b200 import preprocessor as pp
+    text = open(os.path.join(GOLDEN, "weill_exemple", "prepro", "hap.in")).read().replace("Rivulet spacing =                                    0.500",
+                                                                                        "Rivulet spacing =                                    0.300")
+    with pytest.raises(pp.PreproError, match="not a multiple of the rivulet spacing"):
+        pp.read_hapin(text)
+
+
+@pytest.mark.parametrize("case", ["plane17", "rough_pbm", "mask_d8", "chan_ndcf"])
+def test_product_raster_writers_reproduce_pycppp_files(case, tmp_path):
+    """PreproResult.write fed with the ORACLE's cell records must give the ELF's files: pins the text side of the product."""
+    from oracle import prepro_oracle as po
+    from pycathy_wrapper_b200 import preprocessor as pp
+    d = unpack(case, tmp_path)
+    p = po.Prepro(open(d + "/hap.in.orig").read(), open(d + "/dtm_13.val").read()).run()
+    names = {"quota": "quota", "A_inflow": "A_inflow", "w_1": "w_1", "w_2": "w_2", "local_slope_1": "ls_1", "local_slope_2": "ls_2",
+             "epl_1": "epl_1", "epl_2": "epl_2", "Ws1_sf_1": "Ws_1", "Ws1_sf_2": "Ws_2", "b1_sf": "b1", "kSs1_sf_1": "kSs_1",
+             "kSs1_sf_2": "kSs_2", "y1_sf": "y1", "nrc": "nrc", "p_outflow_1": "p1", "p_outflow_2": "p2", "hcID": "hcID", "dmID": "dmID"}
+    fields = {k: np.array(getattr(p, v)[1:]) for k, v in names.items()}
+    fields["order"] = np.array(p.qoi[1:], dtype=np.int32)
+    hap = pp.read_hapin(open(d + "/hap.in").read())
+    res = pp.PreproResult(hap, np.array(p.present[1:]), fields, {"n_cells": p.N_celle, "hap_text": pp.write_hapin(hap)})
+    out = str(tmp_path / "out")
+    os.makedirs(out)
+    res.write(out)
+    for f in golden_files(d):
+        assert open(os.path.join(out, f)).read() == open(os.path.join(d, f)).read(), f
+    # the other header types / pointer system of MRBB_SR against the oracle's restatement
+    for ht, nodata, ips in ((1, -9999.0, 2), (0, -1.0, 1)):
+        for name in ("dtm_p_outflow_1", "dtm_w_1", "dtm_A_inflow", "dtm_hcID", "dem"):
+            assert res.raster_text(name, ht, nodata, ips) == p.raster(name, ht, nodata, ips), (name, ht)
+
+
+def test_prepro_library_exports_the_declared_symbols():
+    """include/cathy_prepro.h <-> libcathy_b200.so, struct sizes included (no compute call: runs without a GPU)."""
+    import re
+    import ctypes as C
+    from pycathy_wrapper_b200 import preprocessor as pp
+    lib, run, err = pp.load_prepro_library()
+    hdr = open(os.path.join(ROOT, "include", "cathy_prepro.h")).read()
+    declared = set(re.findall(r"\b(cathy_prepro_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == {"cathy_prepro_run", "cathy_prepro_last_error"}
+    for name in declared:
+        assert getattr(lib, name)
+    assert C.sizeof(pp.CathyPreproParams) == 8 * 4 + 2 * 8 + 2 * 4 + 4 * 8 + 4 * 4 + 3 * 8 + 16 * 4
+    # a bad argument is refused before any device work
+    assert run(None, None, None, 0, None) == -1 and b"null argument" in err()
+
+
+def test_product_preprocessor_never_imports_the_oracle():
+    src = open(os.path.join(ROOT, "pycathy_wrapper_b200", "preprocessor.py")).read()
+    assert "oracle" not in src.replace("no CPU path", "")
+    assert shutil.which("nvcc") is None or "cathy_prepro.cu" in open(os.path.join(ROOT, "__graft_entry__.py")).read()
