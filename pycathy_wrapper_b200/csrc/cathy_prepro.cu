@@ -173,14 +173,161 @@ __global__ void k_pp_gronda_apply(PP S)
     }
 }
 
-__global__ void k_pp_csort(PP S)
+// ------------------------------------------------------------------ the reference's quicksort, in parallel, exactly
+// QSORT (PRE/qsort.f90) is unstable and the permutation it leaves among equal elevations is part of the output, so the
+// device must replay THAT algorithm, not merely sort.  Two facts make the replay parallel:
+//  (1) Hoare's partition loop (qsort.f90:79-96) is a function of the INCOMING values: with pivot a, the k-th element
+//      >= a from the left (u_k) is exchanged with the k-th element <= a from the right (v_k) for as long as u_k < v_k,
+//      because each pointer only ever reads positions no exchange has touched yet, except the last one written by the
+//      other pointer, which stops it.  So one partition = two flag scans, a pairing, and independent exchanges.
+//  (2) Sorting a sub-array [l, ir] is self-contained -- the insertion scan of qsort.f90:29 runs down to index 1 but
+//      stops at l-1, where every element is <= those of the sub-array -- so sub-arrays can be sorted in any order and
+//      side by side without changing the permutation.
+// k_pp_qsplit (one 1024-thread CTA) partitions every range longer than PP_CAP that way and lists the shorter ranges;
+// k_pp_qsmall sorts each of those in shared memory, one CTA per range, replaying qsort.f90 literally (pp_qsort).
+#define PP_CAP 12288
+#define PP_QT 1024
+#define PP_STK 4096
+
+__device__ __forceinline__ int pp_block_exscan(int v, int *ws, int &total)
 {
-    if (blockIdx.x || threadIdx.x) return;
+    // exclusive prefix sum over the PP_QT threads of the CTA; ws = 33 ints of shared memory
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int x = v;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    __syncthreads();
+    if (lane == 31) ws[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int w = ws[lane], z = w;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += y; }
+        ws[lane] = z - w;
+        if (lane == 31) ws[32] = z;
+    }
+    __syncthreads();
+    total = ws[32];
+    return ws[wid] + x - v;
+}
+
+// keys S.key[1..n] / ids S.lst1[1..n]; U = S.lst2, V = S.front[0] as scratch; tasks (l, len) -> S.front[1], count -> cnt[12]
+__global__ void __launch_bounds__(PP_QT) k_pp_qsplit(PP S, int n)
+{
+    __shared__ int stk[PP_STK];
+    __shared__ int ws[33];
+    __shared__ int sh_l, sh_ir, sh_sp, sh_nt;
+    __shared__ double sh_a;
+    double *arr = S.key;
+    int *brr = S.lst1, *U = S.lst2, *V = S.front[0], *task = S.front[1];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        sh_sp = 0; sh_nt = 0;
+        if (n > PP_CAP) { stk[0] = 1; stk[1] = n; sh_sp = 2; }
+        else if (n >= 2) { task[0] = 1; task[1] = n; sh_nt = 1; }
+    }
+    __syncthreads();
+    for (;;) {
+        if (sh_sp == 0) break;
+        __syncthreads();
+        if (tid == 0) {
+            sh_sp -= 2;
+            const int l = stk[sh_sp], ir = stk[sh_sp + 1];
+            // median of three (qsort.f90:49-76)
+            const int k = (l + ir) / 2;
+            double t; int u;
+#define PP_SWAP(x, y) do { t = arr[x]; arr[x] = arr[y]; arr[y] = t; u = brr[x]; brr[x] = brr[y]; brr[y] = u; } while (0)
+            PP_SWAP(k, l + 1);
+            if (arr[l + 1] > arr[ir]) PP_SWAP(l + 1, ir);
+            if (arr[l] > arr[ir]) PP_SWAP(l, ir);
+            if (arr[l + 1] > arr[l]) PP_SWAP(l + 1, l);
+#undef PP_SWAP
+            sh_l = l; sh_ir = ir; sh_a = arr[l];
+        }
+        __syncthreads();
+        const int l = sh_l, ir = sh_ir;
+        const double a = sh_a;
+        const int lo = l + 2, hi = ir - 1, cnt = hi - lo + 1;
+        const int chunk = (cnt + PP_QT - 1) / PP_QT;
+        const int p0 = min(lo + tid * chunk, hi + 1), p1 = min(p0 + chunk, hi + 1);
+        int cL = 0, cR = 0;
+        for (int p = p0; p < p1; ++p) { double v = arr[p]; cL += (v >= a); cR += (v <= a); }
+        int nu, nv;
+        const int exL = pp_block_exscan(cL, ws, nu);
+        const int exR = pp_block_exscan(cR, ws, nv);
+        int kL = exL;
+        for (int p = p0; p < p1; ++p) if (arr[p] >= a) U[++kL] = p;
+        int kR = nv - exR - cR;                                     // candidates <= a to the right of my chunk
+        for (int p = p1 - 1; p >= p0; --p) if (arr[p] <= a) V[++kR] = p;
+        __syncthreads();
+        const int Kmin = min(nu, nv);
+        int c = 0;
+        for (int k = 1 + tid; k <= Kmin; k += PP_QT) c += (U[k] < V[k]);
+        int K;
+        pp_block_exscan(c, ws, K);
+        for (int k = 1 + tid; k <= K; k += PP_QT) {
+            const int x = U[k], y = V[k];
+            double t = arr[x]; arr[x] = arr[y]; arr[y] = t;
+            int u = brr[x]; brr[x] = brr[y]; brr[y] = u;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int uK = K >= 1 ? U[K] : l + 1, vK = K >= 1 ? V[K] : ir;
+            const int E = (K + 1 <= Kmin && U[K + 1] == V[K + 1]) ? 1 : 0;
+            const int kk = K + 1 + E;
+            const int i = min(kk <= nu ? U[kk] : 0x7fffffff, vK);
+            const int j = max(kk <= nv ? V[kk] : -1, uK);
+            arr[l] = arr[j]; arr[j] = a;                           // qsort.f90:97-100
+            { int b = brr[l]; brr[l] = brr[j]; brr[j] = b; }
+            const int rl[2] = {l, i}, rr[2] = {j - 1, ir};
+            for (int h = 0; h < 2; ++h) {
+                const int len = rr[h] - rl[h] + 1;
+                if (len > PP_CAP) {
+                    if (sh_sp + 2 > PP_STK) { atomicExch(&S.cnt[7], 8); continue; }
+                    stk[sh_sp] = rl[h]; stk[sh_sp + 1] = rr[h]; sh_sp += 2;
+                } else if (len >= 2) { task[2 * sh_nt] = rl[h]; task[2 * sh_nt + 1] = len; ++sh_nt; }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) S.cnt[12] = sh_nt;
+}
+
+__global__ void __launch_bounds__(256) k_pp_qsmall(PP S)
+{
+    extern __shared__ double pp_sm[];
+    double *sk = pp_sm;                                  // [PP_CAP + 1], 1-based
+    int *si = (int *)(pp_sm + PP_CAP + 1);
+    const int *task = S.front[1];
+    const int nt = S.cnt[12];
+    for (int t = blockIdx.x; t < nt; t += gridDim.x) {
+        const int l = task[2 * t], len = task[2 * t + 1];
+        for (int k = threadIdx.x; k < len; k += blockDim.x) { sk[1 + k] = S.key[l + k]; si[1 + k] = S.lst1[l + k]; }
+        __syncthreads();
+        if (threadIdx.x == 0) pp_qsort(len, sk, si);
+        __syncthreads();
+        for (int k = threadIdx.x; k < len; k += blockDim.x) { S.key[l + k] = sk[1 + k]; S.lst1[l + k] = si[1 + k]; }
+        __syncthreads();
+    }
+}
+
+// CSORT's records in ascending cell number (csort.f90:39-48): ordered compaction, one CTA
+__global__ void __launch_bounds__(PP_QT) k_pp_records(PP S)
+{
+    __shared__ int ws[33];
     int n = 0;
-    for (int ib = 1; ib < S.nb; ++ib)
-        if (S.pres[ib]) { ++n; S.key[n] = S.q[ib]; S.lst1[n] = ib; }
-    pp_qsort(n, S.key, S.lst1);
-    for (int l = 1; l <= n; ++l) {            // descending order (csort.f90:57-61)
+    for (int base = 1; base < S.nb; base += PP_QT) {
+        const int ib = base + threadIdx.x;
+        const int p = (ib < S.nb && S.pres[ib]) ? 1 : 0;
+        int tot;
+        const int ex = pp_block_exscan(p, ws, tot);
+        if (p) { S.key[n + ex + 1] = S.q[ib]; S.lst1[n + ex + 1] = ib; }
+        n += tot;
+    }
+}
+
+__global__ void k_pp_order(PP S)
+{
+    const int n = S.nc;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x + 1; l <= n; l += gridDim.x * blockDim.x) {      // descending (csort.f90:57-61)
         int ib = S.lst1[n - l + 1];
         S.order[l] = ib;
         S.rank[ib] = l;
@@ -209,25 +356,58 @@ __global__ void k_pp_pitcheck(PP S)
                 double qn = S.q[ib + S.M * di + dj];
                 if (qn >= 0.0 && qn < qc) lower = true;
             }
-        if (!lower) atomicAdd(&S.cnt[5], 1);
+        if (!lower) { S.dep[ib] = 1; S.front[0][atomicAdd(&S.cnt[5], 1)] = ib; }
     }
 }
 
-// the reference's sweeps, one device thread (PRE/depit.f90:63-140)
+// the reference's sweeps, one device thread (PRE/depit.f90:63-140).  The first sweep visits ALL cells in ascending
+// elevation, but a cell can only be raised if it is a pit on the incoming elevations or if a neighbour was raised earlier
+// in the same sweep; every other visit is a no-op.  So the first sweep pops a min-heap of list positions seeded with the
+// pits k_pp_pitcheck found and fed with the later neighbours of every raised cell: same visits that matter, same order.
+__device__ __forceinline__ void pp_heap_push(int *h, int &n, int v)
+{
+    int c = n++;
+    while (c > 0) { int p = (c - 1) >> 1; if (h[p] <= v) break; h[c] = h[p]; c = p; }
+    h[c] = v;
+}
+
+__device__ __forceinline__ int pp_heap_pop(int *h, int &n)
+{
+    int top = h[0], v = h[--n], c = 0;
+    for (;;) {
+        int l = 2 * c + 1;
+        if (l >= n) break;
+        if (l + 1 < n && h[l + 1] < h[l]) ++l;
+        if (h[l] >= v) break;
+        h[c] = h[l]; c = l;
+    }
+    if (n > 0) h[c] = v;
+    return top;
+}
+
 __global__ void k_pp_depit(PP S)
 {
     if (blockIdx.x || threadIdx.x) return;
     const int nc = S.nc, N = S.N, M = S.M;
     const double eps = rmul(S.h.pt0, S.h.delta_x0);
     const int outlet = S.order[nc];
-    int *pit1 = S.lst1, *pit2 = S.lst2;
-    for (int l = 1; l <= nc; ++l) pit1[nc - l + 1] = S.order[l];
+    int *pit1 = S.lst1, *pit2 = S.lst2, *heap = S.front[1];
+    int hn = 0;
+    for (int t = 0; t < S.cnt[5]; ++t) pp_heap_push(heap, hn, nc - S.rank[S.front[0][t]] + 1);
     int n_pits = nc, total = 0, pass = 0;
     for (;;) {
-        int nn_mod = 0, nn_pit = 0;
+        int nn_mod = 0, nn_pit = 0, n = 0;
         ++pass;
-        for (int n = 1; n <= n_pits; ++n) {
-            int ib = pit1[n];
+        for (;;) {
+            int ib, pos = 0;
+            if (pass == 1) {
+                if (hn == 0) break;
+                pos = pp_heap_pop(heap, hn);
+                ib = S.order[nc - pos + 1];
+            } else {
+                if (++n > n_pits) break;
+                ib = pit1[n];
+            }
             if (ib == outlet) continue;
             double qc = S.q[ib];
             int i, j;
@@ -254,11 +434,15 @@ __global__ void k_pp_depit(PP S)
                         int nbr = ib + M * di + dj;
                         if (!S.pres[nbr]) continue;
                         if (S.stamp[nbr] != pass) { S.stamp[nbr] = pass; pit2[++nn_pit] = nbr; }
+                        if (pass == 1 && S.dep[nbr] == 0) {
+                            int pn = nc - S.rank[nbr] + 1;
+                            if (pn > pos) { S.dep[nbr] = 1; pp_heap_push(heap, hn, pn); }
+                        }
                     }
             }
         }
         if (nn_mod == 0) break;
-        for (int n = 1; n <= nn_pit; ++n) S.key[n] = S.q[pit2[n]];
+        for (int k = 1; k <= nn_pit; ++k) S.key[k] = S.q[pit2[k]];
         pp_qsort(nn_pit, S.key, pit2);
         int *t = pit1; pit1 = pit2; pit2 = t;
         n_pits = nn_pit;
@@ -617,6 +801,16 @@ static cudaError_t pp_alloc(T **p, size_t n, bool zero = true)
     return e;
 }
 
+// CSORT on the device (PRE/csort.f90:32-62)
+static cudaError_t pp_csort(PP &S, int grid, int tpb, int nsm, int &launches)
+{
+    k_pp_records<<<1, PP_QT>>>(S); ++launches;
+    k_pp_qsplit<<<1, PP_QT>>>(S, S.nc); ++launches;
+    k_pp_qsmall<<<nsm, 256, (PP_CAP + 1) * (sizeof(double) + sizeof(int))>>>(S); ++launches;
+    k_pp_order<<<grid, tpb>>>(S); ++launches;
+    return cudaGetLastError();
+}
+
 extern "C" const char *cathy_prepro_last_error(void) { return pp_err; }
 
 extern "C" int32_t cathy_prepro_run(const CathyPreproParams *p, const double *quota_in, const uint8_t *present, int32_t device,
@@ -646,6 +840,7 @@ extern "C" int32_t cathy_prepro_run(const CathyPreproParams *p, const double *qu
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) PFAIL(-100, "cathy_prepro_run: no CUDA device (there is no CPU path)");
     }
     PCK(cudaSetDevice(device));
+    PCK(cudaFuncSetAttribute(k_pp_qsmall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((PP_CAP + 1) * (sizeof(double) + sizeof(int)))));
     {
         S.h = *p;
         S.N = p->N; S.M = p->M; S.nb = p->N * p->M + 1;
@@ -683,7 +878,7 @@ extern "C" int32_t cathy_prepro_run(const CathyPreproParams *p, const double *qu
             k_pp_gronda_apply<<<GRID, TPB>>>(S); ++launches;
         }
         PCK(cudaEventRecord(evs[0], 0));
-        k_pp_csort<<<1, 32>>>(S); ++launches;
+        PCK(pp_csort(S, GRID, TPB, nsm, launches));
         PCK(cudaEventRecord(evs[1], 0));
         k_pp_pitcheck<<<GRID, TPB>>>(S); ++launches;
         PCK(cudaMemcpy(cnt, S.cnt, sizeof cnt, cudaMemcpyDeviceToHost));
@@ -694,7 +889,7 @@ extern "C" int32_t cathy_prepro_run(const CathyPreproParams *p, const double *qu
         if (cnt[5] > 0) {
             k_pp_depit<<<1, 32>>>(S); ++launches;
             PCK(cudaEventRecord(evs[3], 0));
-            k_pp_csort<<<1, 32>>>(S); ++launches;
+            PCK(pp_csort(S, GRID, TPB, nsm, launches));
         } else PCK(cudaEventRecord(evs[3], 0));
         PCK(cudaEventRecord(evs[4], 0));
         k_pp_local<<<GRID, TPB>>>(S); ++launches;
@@ -716,6 +911,7 @@ extern "C" int32_t cathy_prepro_run(const CathyPreproParams *p, const double *qu
         PCK(cudaEventRecord(ev1, 0));
         PCK(cudaDeviceSynchronize());
         PCK(cudaMemcpy(cnt, S.cnt, sizeof cnt, cudaMemcpyDeviceToHost));
+        if (cnt[7] == 8) PFAIL(-1, "quicksort range stack overflow (raster too large for PP_STK)");
         if (cnt[7] == 6) PFAIL(-1, "s_max = 0, unexpected case! (a cell without any neighbour)");
         if (cnt[7] == 7) PFAIL(-1, "s_max < 0, unexpected case!");
         if (cnt[3] != S.nc) PFAIL(-1, "drainage sweep finished %d of %d cells (dependency cycle?)", cnt[3], S.nc);

@@ -170,3 +170,69 @@ def test_product_preprocessor_never_imports_the_oracle():
     src = open(os.path.join(ROOT, "pycathy_wrapper_b200", "preprocessor.py")).read()
     assert "oracle" not in src.replace("no CPU path", "")
     assert shutil.which("nvcc") is None or "cathy_prepro.cu" in open(os.path.join(ROOT, "__graft_entry__.py")).read()
+
+
+def test_parallel_partition_formulation_equals_the_reference_quicksort():
+    """The claim csrc/cathy_prepro.cu:k_pp_qsplit rests on, checked on the CPU: Hoare's partition loop of QSORT
+    (PRE/qsort.f90:79-96) exchanges the k-th element >= pivot from the left with the k-th element <= pivot from the right
+    while they have not crossed, and sub-arrays can be finished in any order -- same permutation as the sequential
+    algorithm, ties included."""
+    import random
+    from oracle.prepro_oracle import qsort
+
+    def par_qsort(n, arr, brr, cap, rnd):
+        stack, tasks = [], []
+        if n > cap:
+            stack.append((1, n))
+        elif n >= 2:
+            tasks.append((1, n))
+
+        def sw(x, y):
+            arr[x], arr[y] = arr[y], arr[x]
+            brr[x], brr[y] = brr[y], brr[x]
+        while stack:
+            l, ir = stack.pop()
+            sw((l + ir) // 2, l + 1)
+            if arr[l + 1] > arr[ir]:
+                sw(l + 1, ir)
+            if arr[l] > arr[ir]:
+                sw(l, ir)
+            if arr[l + 1] > arr[l]:
+                sw(l + 1, l)
+            a = arr[l]
+            U = [0] + [p for p in range(l + 2, ir) if arr[p] >= a]
+            V = [0] + [p for p in range(ir - 1, l + 1, -1) if arr[p] <= a]
+            nu, nv = len(U) - 1, len(V) - 1
+            K = sum(1 for k in range(1, min(nu, nv) + 1) if U[k] < V[k])
+            for k in range(1, K + 1):
+                sw(U[k], V[k])
+            uK, vK = (U[K], V[K]) if K >= 1 else (l + 1, ir)
+            kk = K + 1 + (1 if (K + 1 <= min(nu, nv) and U[K + 1] == V[K + 1]) else 0)
+            i = min(U[kk] if kk <= nu else 1 << 60, vK)
+            j = max(V[kk] if kk <= nv else -1, uK)
+            arr[l], arr[j] = arr[j], a
+            brr[l], brr[j] = brr[j], brr[l]
+            for x, y in ((l, j - 1), (i, ir)):
+                if y - x + 1 > cap:
+                    stack.append((x, y))
+                elif y - x + 1 >= 2:
+                    tasks.append((x, y - x + 1))
+        rnd.shuffle(tasks)
+        for l, ln in tasks:
+            sk, si = [0.0] + arr[l:l + ln], [0] + brr[l:l + ln]
+            qsort(ln, sk, si)
+            arr[l:l + ln], brr[l:l + ln] = sk[1:], si[1:]
+
+    rnd = random.Random(3)
+    for trial in range(600):
+        n = rnd.randint(1, 300)
+        keys = [float(rnd.randint(0, rnd.choice([3, 10, 50, 10 ** 6]))) for _ in range(n)]
+        if trial % 7 == 0:
+            keys.sort()
+        if trial % 11 == 0:
+            keys.sort(reverse=True)
+        a1, b1 = [0.0] + keys, [0] + list(range(1, n + 1))
+        a2, b2 = list(a1), list(b1)
+        qsort(n, a1, b1)
+        par_qsort(n, a2, b2, rnd.choice([8, 9, 16, 33, 100]), rnd)
+        assert a1 == a2 and b1 == b2, (trial, n)
