@@ -8,7 +8,7 @@ A "step" is one ACCEPTED time step of the hot path (all its Picard iterations, l
 mass balance, boundary switching and any back-stepped attempts).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size NROWxNCOLxNSTR]
-                  [--workload picard|newton|coupled|enkf|partitioned] [--sharded auto|off|enkf|partitioned|enkf,partitioned]
+                  [--workload picard|newton|coupled|enkf|partitioned|prepro] [--sharded auto|off|enkf|partitioned|enkf,partitioned]
 
 The ONE JSON line of the default run carries, next to the headline `value` / `e2e` / `roofline` / `cpu_baseline`:
   * `sharded` -- the two shardings BASELINE.json's north_star names, measured in the SAME invocation at the same N:
@@ -88,12 +88,14 @@ def make_workload(size, member: int = 0, iopt: int = 1, routing: bool = False):
         # BASELINE config 3: Newton + coupled surface routing.  A storm (1e-4 m/s for 10 min) on a saturated hillslope (water table
         # at the surface) that starts with 5 mm of ponded water, so that SURF_FLOWTRA routes runoff from the first step on.  The
         # routing rasters of the 200 x 200 DEM come from the reference's own pre-processor (tests/golden/make_route200.py).
-        if (nrow, ncol) != (200, 200):
-            raise SystemExit("bench.py: the coupled workload ships routing rasters for the 200x200 DEM only")
         rain = [(0.0, 0.0), (60.0, 1.0e-4), (600.0, 1.0e-4), (660.0, 0.0), (1.0e9, 0.0)]
         synthetic.make_project(d, nrow, ncol, nstr, ic=("hydrostatic",), pond=0.005, ISIMGR=2, DELTAT=1.0, DTMIN=1e-4, DTMAX=100.0, TMAX=7200.0, TIMPRT=[7200.0],
                                NODVP=[1], soil_rows=[row] * nstr, IOPT=iopt, ISOLV=0 if iopt == 2 else 2, atmbc=rain)
-        subprocess.run(["tar", "-xJf", ROUTE200, "-C", os.path.join(d, "prepro")], check=True)
+        if (nrow, ncol) == (200, 200):
+            subprocess.run(["tar", "-xJf", ROUTE200, "-C", os.path.join(d, "prepro")], check=True)       # the reference ELF's own files
+        else:
+            from pycathy_wrapper_b200 import preprocessor                                                  # any other DEM: the device pre-processor
+            preprocessor.run_preprocessor(os.path.join(d, "prepro"))
         prj = load_project(d)
         shutil.rmtree(d, ignore_errors=True)
         return prj
@@ -655,6 +657,8 @@ def run_reference(args, size):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "prepro":
+        return run_prepro_reference(args, size)
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], check=True)
     newton = args.workload in ("newton", "coupled")
@@ -687,10 +691,130 @@ def run_reference(args, size):
     }), flush=True)
 
 
+# ======================================================================================================
+# pre-processor: hap.in + dtm_13.val -> routing rasters, one pass = one "step"
+
+def _prepro_project(size):
+    """<project>/prepro with hap.in and dtm_13.val of the synthetic DEM (the DEM of BASELINE config 5 at 1000x1000)."""
+    nrow, ncol = size[0], size[1]
+    d = tempfile.mkdtemp(prefix="cathy_prepro_")
+    synthetic.write_hapin(os.path.join(d, "hap.in"), nrow, ncol, 0.5, 0.5)
+    z = synthetic.synthetic_dem(nrow, ncol)
+    np.savetxt(os.path.join(d, "dtm_13.val"), z, fmt="%.9f", delimiter="\t")
+    shutil.copy(os.path.join(d, "hap.in"), os.path.join(d, "hap.in.orig"))
+    return d
+
+
+def _pycppp_seconds(d):
+    """The reference's own ELF on the same directory (oracle/_ref/bin/pycppp, answers 2 / 0 / 1 as pyCATHY gives them)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "bin", "pycppp")
+    if not os.path.exists(exe):
+        return None
+    run = tempfile.mkdtemp(prefix="cathy_prepro_ref_")
+    shutil.copy(os.path.join(d, "hap.in.orig"), os.path.join(run, "hap.in"))
+    shutil.copy(os.path.join(d, "dtm_13.val"), os.path.join(run, "dtm_13.val"))
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "oracle", "_ref", "lib") + ":" + env.get("LD_LIBRARY_PATH", "")
+    t0 = time.perf_counter()
+    subprocess.run([exe], cwd=run, env=env, input="2\n0\n1\n", text=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=1800)
+    dt = time.perf_counter() - t0
+    ok = os.path.exists(os.path.join(run, "qoi_a"))
+    same = None
+    if ok:
+        same = all(open(os.path.join(run, f)).read() == open(os.path.join(d, f)).read()
+                   for f in ("qoi_a", "dem", "dtm_w_1", "dtm_w_2", "dtm_p_outflow_1", "dtm_p_outflow_2", "dtm_local_slope_1", "dtm_epl_2",
+                             "dtm_kSs1_sf_1", "dtm_Ws1_sf_2", "dtm_nrc") if os.path.exists(os.path.join(d, f)))
+    shutil.rmtree(run, ignore_errors=True)
+    return {"seconds": dt, "ok": ok, "files_identical_to_ours": same}
+
+
+def run_prepro(ctx: Ctx, args, size) -> dict:
+    from pycathy_wrapper_b200 import preprocessor as pp
+    torch = ctx.torch
+    d = _prepro_project(size)
+    hap = open(os.path.join(d, "hap.in")).read()
+    dtm = open(os.path.join(d, "dtm_13.val")).read()
+    for _ in range(args.warmup):
+        res = pp.terrain_analysis(hap, dtm, device=ctx.local)
+    sampler = ClockSampler(ctx.local)
+    sampler.start()
+    ctx.barrier()
+    dev_ms, stages = [], []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = pp.terrain_analysis(hap, dtm, device=ctx.local)          # text -> device -> cell records (H2D + D2H inside)
+        dev_ms.append(res.info["device_ms"])
+        stages.append(res.info["stage_ms"])
+    ctx.barrier()
+    t_api = (time.perf_counter() - t0) / args.steps
+    # end to end = the call a pyCATHY user makes: ./pycppp in <project>/prepro, files in, files out
+    t0 = time.perf_counter()
+    for _ in range(max(1, min(args.steps, 3))):
+        shutil.copy(os.path.join(d, "hap.in.orig"), os.path.join(d, "hap.in"))
+        res = pp.run_preprocessor(d, device=ctx.local)
+    t_e2e = (time.perf_counter() - t0) / max(1, min(args.steps, 3))
+    sampler.stop()
+    n = res.info["n_cells"]
+    ms = float(np.mean(dev_ms))
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak = float(peaks.get("hbm_gbps_burst", peaks.get("hbm_gbps", 6547.5))) if isinstance(peaks, dict) else 6547.5
+    st = {k: float(np.mean([s_[k] for s_ in stages])) for k in stages[0]}
+    top = max(st, key=st.get)
+    bytes_cell = 9 * 8 + 19 * 4 + 2 * 8 + 60            # 3x3 window of doubles in, 19 cell fields out, donor gathers
+    out = {
+        "metric": "pre-processor cells/s (hap.in + dtm_13.val -> routing rasters)", "value": n / (ms * 1e-3), "unit": "cells/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "CATHY pre-processor on the synthetic %dx%d DEM (%d cells; the DEM of BASELINE config 5 at 1000x1000): CSORT, DEPIT, CSORT, CCA, SMEAN, "
+                               "DSF, HG on the device; value = cells / CUDA-event time of the device part; inputs larger than L2 are not the point here: the path is "
+                               "bound by dependency chains (DEPIT's sequential sweeps, %d drainage wavefronts), not by bandwidth" % (size[0], size[1], n, res.info["n_waves"])},
+        "e2e": {"value": n / t_e2e, "unit": "cells/s", "seconds": t_e2e, "what": "run_preprocessor(<project>/prepro): parse hap.in + dtm_13.val, device, write 21 rasters + qoi_a + hap.in",
+                "api_only_cells_per_s": n / t_api, "h2d_bytes_per_step": 9 * n, "d2h_bytes_per_step": (2 * 8 + 13 * 4 + 5 * 4) * n},
+        "gpu_launches": int(res.info["n_launches"]) * args.steps,
+        "stage_ms": st, "depit": {"modifications": res.info["n_modifications"], "sweeps": res.info["depit_sweeps"]}, "drainage_wavefronts": res.info["n_waves"],
+        "roofline": {"bound": "hbm", "achieved": n * bytes_cell / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": n * bytes_cell / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                     "kernel": top, "note": "algorithmic bytes (%d B/cell) over the whole device part; the dominant stage `%s` is a chain of dependent steps by definition of its result "
+                                            "(DESIGN section 9), so the HBM roof is not what bounds it" % (bytes_cell, top)},
+        "clocks": sampler.summary(),
+    }
+    if not args.no_cpu:
+        ref = _pycppp_seconds(d)
+        if ref and ref["ok"]:
+            out["cpu_baseline"] = {"value": n / ref["seconds"], "unit": "cells/s", "cores": 1, "kind": "reference",
+                                   "sample": "the reference's own ELF pycppp on the same hap.in + dtm_13.val, whole DEM, %.1f s; files identical to ours: %s" % (ref["seconds"], ref["files_identical_to_ours"])}
+        else:
+            out["cpu_baseline"] = {"value": None, "unit": "cells/s", "cores": 1, "kind": "reference", "sample": "oracle/_ref/bin/pycppp not staged on this box"}
+    shutil.rmtree(d, ignore_errors=True)
+    return out
+
+
+def run_prepro_reference(args, size):
+    d = _prepro_project(size)
+    times = []
+    for _ in range(max(1, min(args.steps, 2))):
+        ref = _pycppp_seconds(d)
+        if not ref or not ref["ok"]:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bin/pycppp not staged or failed"}), flush=True)
+            return
+        times.append(ref["seconds"])
+    n = size[0] * size[1]
+    v = n / float(np.mean(times))
+    print(json.dumps({"impl": "reference", "metric": "pre-processor cells/s (hap.in + dtm_13.val -> routing rasters)", "value": v, "unit": "cells/s", "n_gpus": 1,
+                      "steps": len(times), "warmup": 0, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f64", "data": "synthetic", "config": {"workload": "the reference ELF pycppp on the synthetic %dx%d DEM, text in, text out" % (size[0], size[1])},
+                      "cpu_baseline": {"value": v, "unit": "cells/s", "cores": 1, "kind": "reference", "sample": "whole DEM, %d run(s)" % len(times)},
+                      "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+    shutil.rmtree(d, ignore_errors=True)
+
+
 def run_ours(args, size):
     ctx = Ctx()
     elapsed = lambda: time.perf_counter() - T_START      # noqa: E731
-    if args.workload == "enkf":
+    if args.workload == "prepro":
+        if ctx.world > 1:
+            raise SystemExit("bench.py: the pre-processor is a one-off set-up step of one DEM: replicas only, run it with --gpus 1")
+        out = run_prepro(ctx, args, size)
+    elif args.workload == "enkf":
         out = run_enkf(ctx, args, size, cycles=args.steps, warm=args.warmup)
         out.update({"vs_baseline": None, "dtype": "f64", "data": "synthetic"})
     elif args.workload == "partitioned":
@@ -750,7 +874,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", default=None)
-    ap.add_argument("--workload", default="picard", choices=["picard", "newton", "coupled", "enkf", "partitioned"], help="picard: BASELINE config 2 (headline); newton: config 3's linearisation on the same mesh; coupled: config 3 (Newton + surface routing); enkf: config 4; partitioned: config 5")
+    ap.add_argument("--workload", default="picard", choices=["picard", "newton", "coupled", "enkf", "partitioned", "prepro"], help="picard: BASELINE config 2 (headline); newton: config 3's linearisation on the same mesh; coupled: config 3 (Newton + surface routing); enkf: config 4; partitioned: config 5")
     ap.add_argument("--sharded", default="auto", help="picard workload: which sharded legs run in the same invocation (auto = enkf,partitioned; off)")
     ap.add_argument("--partition-size", default="1000x1000x30", help="mesh of the `partitioned` leg (BASELINE config 5)")
     ap.add_argument("--members", type=int, default=256)
@@ -762,7 +886,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" and args.workload not in ("enkf", "partitioned") else args.warmup
     if args.size is None:
-        args.size = {"picard": "200x200x20", "newton": "200x200x20", "coupled": "200x200x20", "enkf": "100x100x15", "partitioned": "1000x1000x30"}[args.workload]
+        args.size = {"picard": "200x200x20", "newton": "200x200x20", "coupled": "200x200x20", "enkf": "100x100x15", "partitioned": "1000x1000x30", "prepro": "1000x1000x1"}[args.workload]
     size = tuple(int(v) for v in args.size.lower().split("x"))
     if args.impl == "reference":
         run_reference(args, size)

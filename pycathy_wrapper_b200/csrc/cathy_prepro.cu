@@ -18,6 +18,10 @@
 #include <cstring>
 #include <cmath>
 #include <cfloat>
+#include <cstdlib>
+#include <thread>
+#include <vector>
+#include <atomic>
 #include "../../include/cathy_prepro.h"
 
 namespace cg = cooperative_groups;
@@ -394,7 +398,8 @@ __global__ void k_pp_depit(PP S)
     int *pit1 = S.lst1, *pit2 = S.lst2, *heap = S.front[1];
     int hn = 0;
     for (int t = 0; t < S.cnt[5]; ++t) pp_heap_push(heap, hn, nc - S.rank[S.front[0][t]] + 1);
-    int n_pits = nc, total = 0, pass = 0;
+    int n_pits = nc, total = 0, pass = 0, max_list = 0;
+    long long sort_cycles = 0, t_start = clock64();
     for (;;) {
         int nn_mod = 0, nn_pit = 0, n = 0;
         ++pass;
@@ -442,13 +447,19 @@ __global__ void k_pp_depit(PP S)
             }
         }
         if (nn_mod == 0) break;
+        long long t0 = clock64();
         for (int k = 1; k <= nn_pit; ++k) S.key[k] = S.q[pit2[k]];
         pp_qsort(nn_pit, S.key, pit2);
+        sort_cycles += clock64() - t0;
+        if (nn_pit > max_list) max_list = nn_pit;
         int *t = pit1; pit1 = pit2; pit2 = t;
         n_pits = nn_pit;
     }
     S.cnt[6] = total;
     S.cnt[8] = pass;
+    S.cnt[13] = max_list;
+    S.scal[2] = (double)sort_cycles;
+    S.scal[3] = (double)(clock64() - t_start);
 }
 
 // ------------------------------------------------------------------ FACET (PRE/facet.f90:10-47)
@@ -900,7 +911,7 @@ extern "C" int32_t cathy_prepro_run(const CathyPreproParams *p, const double *qu
             int per_sm = 0;
             PCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pp_sweep, TPB, 0));
             if (per_sm < 1) PFAIL(-100, "k_pp_sweep does not fit on an SM");
-            if (per_sm > 4) per_sm = 4;
+            if (per_sm > 1) per_sm = 1;      // a wavefront holds a few hundred cells: one CTA per SM keeps the grid barrier short
             void *args[] = {(void *)&S};
             PCK(cudaLaunchCooperativeKernel((void *)k_pp_sweep, dim3(nsm * per_sm), dim3(TPB), args, 0, 0)); ++launches;
         }
@@ -934,6 +945,9 @@ extern "C" int32_t cathy_prepro_run(const CathyPreproParams *p, const double *qu
         out->n_waves = cnt[4];
         out->n_launches = launches;
         out->mean_s_max = scal[0];
+        if (getenv("CATHY_PREPRO_DEBUG"))
+            fprintf(stderr, "[prepro] DEPIT: %d sweeps, %d raises, longest list %d, sort share of the kernel %.2f\n", cnt[8], cnt[6], cnt[13],
+                    scal[3] > 0 ? scal[2] / scal[3] : 0.0);
         out->device_ms = ms;
         {
             // csort, pit check, depit, second csort, window analysis + smean, drainage sweep, outlet + hg
@@ -954,4 +968,107 @@ done:
     if (ev1) cudaEventDestroy(ev1);
     for (int k = 0; k < 8; ++k) if (evs[k]) cudaEventDestroy(evs[k]);
     return rc;
+}
+
+// ------------------------------------------------------------------ host side: the fixed-width text of RBB (PRE/mrbb_sr.f90:445-470)
+// A raster file of a million cells is 21 MB of Fortran-formatted numbers; formatting is exact decimal conversion
+// (snprintf), done row-parallel on host threads.  Every row is ncols fields of width w plus a newline, so rows are
+// written at fixed offsets.
+static bool pp_fmt_e(double x, int w, int d, char *dst)
+{
+    char buf[64], body[64];
+    if (!(x == x) || x - x != 0.0) return false;
+    int len;
+    if (x == 0.0) {
+        len = snprintf(body, sizeof body, "0.%0*dE+00", d, 0);
+    } else {
+        int n = snprintf(buf, sizeof buf, "%.*E", d - 1, x < 0 ? -x : x);      // D.DDDDE+XX
+        char *e = strchr(buf, 'E');
+        if (!e || n <= 0) return false;
+        int ex = atoi(e + 1) + 1;
+        if (ex > 99 || ex < -99) return false;
+        char *o = body;
+        if (x < 0) *o++ = '-';
+        *o++ = '0'; *o++ = '.';
+        *o++ = buf[0];
+        for (char *c = buf + 2; c < e; ++c) *o++ = *c;
+        o += snprintf(o, 8, "E%c%02d", ex < 0 ? '-' : '+', ex < 0 ? -ex : ex);
+        len = (int)(o - body);
+    }
+    char *b = body;
+    if (len > w) {                                    // gfortran drops the optional leading zero before giving up
+        if (b[0] == '0') { ++b; --len; }
+        else if (b[0] == '-' && b[1] == '0') { b[1] = '-'; ++b; --len; }
+    }
+    if (len > w) { memset(dst, '*', w); return true; }
+    memset(dst, ' ', w - len);
+    memcpy(dst + (w - len), b, len);
+    return true;
+}
+
+static bool pp_fmt_f(double x, int w, int d, char *dst)
+{
+    char body[400];
+    if (!(x == x) || x - x != 0.0) return false;
+    int len = snprintf(body, sizeof body, "%.*f", d, x);
+    if (len <= 0 || len >= (int)sizeof body) return false;
+    char *b = body;
+    if (len > w) {
+        if (b[0] == '0' && b[1] == '.') { ++b; --len; }
+        else if (b[0] == '-' && b[1] == '0' && b[2] == '.') { b[1] = '-'; ++b; --len; }
+    }
+    if (len > w) { memset(dst, '*', w); return true; }
+    memset(dst, ' ', w - len);
+    memcpy(dst + (w - len), b, len);
+    return true;
+}
+
+template <class F>
+static int64_t pp_rows_parallel(int64_t nrows, int32_t nthreads, F row)
+{
+    int hw = (int)std::thread::hardware_concurrency();
+    int nt = nthreads > 0 ? nthreads : (hw > 16 ? 16 : (hw < 1 ? 1 : hw));
+    if ((int64_t)nt > nrows) nt = (int)(nrows < 1 ? 1 : nrows);
+    std::atomic<int> bad(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back([&, t]() {
+            for (int64_t r = t; r < nrows; r += nt) if (!row(r)) bad = 1;
+        });
+    for (auto &x : th) x.join();
+    return bad ? -1 : 0;
+}
+
+// kind 0: Ew.d, 1: Fw.d.  out holds nrows * (ncols * w + 1) bytes.  Returns the byte count, -1 if a value needs a
+// form this routine does not write (NaN, infinity, three-digit exponent): the caller formats that file itself.
+extern "C" int64_t cathy_prepro_format_real(const double *v, int64_t nrows, int64_t ncols, int32_t w, int32_t d, int32_t kind,
+                                            char *out, int32_t nthreads)
+{
+    if (!v || !out || nrows < 0 || ncols < 0 || w < 1 || w > 60 || d < 0 || d > 40) return -1;
+    const int64_t stride = ncols * w + 1;
+    int64_t rc = pp_rows_parallel(nrows, nthreads, [&](int64_t r) {
+        char *o = out + r * stride;
+        for (int64_t c = 0; c < ncols; ++c)
+            if (!(kind == 0 ? pp_fmt_e(v[r * ncols + c], w, d, o + c * w) : pp_fmt_f(v[r * ncols + c], w, d, o + c * w))) return false;
+        o[ncols * w] = '\n';
+        return true;
+    });
+    return rc < 0 ? -1 : nrows * stride;
+}
+
+extern "C" int64_t cathy_prepro_format_int(const int32_t *v, int64_t nrows, int64_t ncols, int32_t w, char *out, int32_t nthreads)
+{
+    if (!v || !out || nrows < 0 || ncols < 0 || w < 1 || w > 30) return -1;
+    const int64_t stride = ncols * w + 1;
+    pp_rows_parallel(nrows, nthreads, [&](int64_t r) {
+        char *o = out + r * stride, body[32];
+        for (int64_t c = 0; c < ncols; ++c) {
+            int len = snprintf(body, sizeof body, "%d", v[r * ncols + c]);
+            if (len > w) memset(o + c * w, '*', w);
+            else { memset(o + c * w, ' ', w - len); memcpy(o + c * w + (w - len), body, len); }
+        }
+        o[ncols * w] = '\n';
+        return true;
+    });
+    return nrows * stride;
 }

@@ -79,6 +79,10 @@ def load_prepro_library():
         run.argtypes = [C.POINTER(CathyPreproParams), _D, C.POINTER(C.c_uint8), C.c_int32, C.POINTER(CathyPreproOut)]
         run.restype = C.c_int32
         err.restype = C.c_char_p
+        lib.cathy_prepro_format_real.argtypes = [_D, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
+        lib.cathy_prepro_format_real.restype = C.c_int64
+        lib.cathy_prepro_format_int.argtypes = [_I, C.c_int64, C.c_int64, C.c_int32, C.c_char_p, C.c_int32]
+        lib.cathy_prepro_format_int.restype = C.c_int64
         _LIB = (lib, run, err)
     return _LIB
 
@@ -193,6 +197,14 @@ def write_hapin(hap: dict) -> str:
 
 def read_dtm13(text: str, N: int, M: int) -> np.ndarray:
     """dtm_13.val (PRE/wbb_sr.f90:66-88): M list-directed records of N values, north row first -> array [M][N]."""
+    if "D" not in text and "d" not in text and "," not in text:
+        # the common case, every record on its own line with exactly N values: one strtod pass over the text
+        try:
+            flat = np.fromstring(text, dtype=np.float64, sep=" ")
+        except (ValueError, DeprecationWarning):
+            flat = np.empty(0)
+        if flat.size == N * M and text.count("\n") in (M, M - 1):
+            return flat.reshape(M, N)
     rows = np.empty((M, N))
     it = iter(text.splitlines())
     for r in range(M):
@@ -236,6 +248,31 @@ def _e_column(v: np.ndarray, w: int, d: int) -> np.ndarray:
             return np.array([_E(float(x), w, d) for x in v])
         out[neg, o - 1] = ord("-")
     return out.view("S%d" % w).reshape(len(v)).astype(str)
+
+
+def _block_real(v2d: np.ndarray, w: int, d: int, kind: int) -> str:
+    """[M][N] doubles -> M records of N fields Ew.d (kind 0) / Fw.d (kind 1): native row-parallel formatter of the library,
+    numpy when a value needs a form it does not write."""
+    lib = load_prepro_library()[0]
+    v = np.ascontiguousarray(v2d, dtype=np.float64)
+    M, N = v.shape
+    buf = C.create_string_buffer(M * (N * w + 1))
+    if lib.cathy_prepro_format_real(v.ctypes.data_as(_D), M, N, w, d, kind, buf, 0) == M * (N * w + 1):
+        return buf.raw.decode("ascii")
+    if kind == 1:
+        txt = np.char.mod("%%%d.%df" % (w, d), v)
+    else:
+        txt = _e_column(v.ravel(), w, d).reshape(M, N)
+    return "\n".join("".join(row) for row in txt) + "\n"
+
+
+def _block_int(v2d: np.ndarray, w: int) -> str:
+    lib = load_prepro_library()[0]
+    v = np.ascontiguousarray(v2d, dtype=np.int32)
+    M, N = v.shape
+    buf = C.create_string_buffer(M * (N * w + 1))
+    lib.cathy_prepro_format_int(v.ctypes.data_as(_I), M, N, w, buf, 0)
+    return buf.raw.decode("ascii")
 
 
 def _header(hap: dict, ht: int) -> str:
@@ -294,20 +331,17 @@ class PreproResult:
             imax = max(int(vi[pres].max()), abs(int(nodata32)))
             imin = min(int(vi[pres].min()), int(nodata32))
             w = 2 if imax == 0 else int(math.log10(float(np.float32(imax)))) + (3 if imin < 0 else 2)
-            txt = np.char.mod("%%%dd" % w, np.where(pres, vi, int(nodata32)))
-        else:
-            vr = np.where(pres, g.astype(np.float64), nodata32)
-            neg = min(float(vr[pres].min()), nodata32) < 0.0
-            if kind == "a":
-                txt = np.char.mod("%15.2f" if neg else "%14.2f", vr)
-            else:
-                txt = _e_column(vr.ravel(), 20 if neg else 21, 12).reshape(M, N)
-        return _header(self.hap, ht) + "\n".join("".join(row) for row in txt) + "\n"
+            return _header(self.hap, ht) + _block_int(np.where(pres, vi, int(nodata32)), w)
+        vr = np.where(pres, g.astype(np.float64), nodata32)
+        neg = min(float(vr[pres].min()), nodata32) < 0.0
+        if kind == "a":
+            return _header(self.hap, ht) + _block_real(vr, 15 if neg else 14, 2, 1)
+        return _header(self.hap, ht) + _block_real(vr, 20 if neg else 21, 12, 0)
 
     def qoi_a_text(self) -> str:
         """hg.f90:31-37: N_celle then the cells in descending elevation, list-directed INTEGER*4 (width 12)."""
-        v = np.concatenate(([self.info["n_cells"]], self.order[:self.info["n_cells"]]))
-        return "\n".join(np.char.mod("%12d", v)) + "\n"
+        v = np.concatenate(([self.info["n_cells"]], self.order[:self.info["n_cells"]])).astype(np.int32)
+        return _block_int(v.reshape(-1, 1), 12)
 
     def write(self, directory: str, ht: int = 2, nodata: float = 0.0, ips: int = 1) -> None:
         with open(os.path.join(directory, "hap.in"), "w") as fh:

@@ -158,7 +158,7 @@ def test_prepro_library_exports_the_declared_symbols():
     lib, run, err = pp.load_prepro_library()
     hdr = open(os.path.join(ROOT, "include", "cathy_prepro.h")).read()
     declared = set(re.findall(r"\b(cathy_prepro_[a-z_0-9]+)\s*\(", hdr))
-    assert declared == {"cathy_prepro_run", "cathy_prepro_last_error"}
+    assert declared == {"cathy_prepro_run", "cathy_prepro_last_error", "cathy_prepro_format_real", "cathy_prepro_format_int"}
     for name in declared:
         assert getattr(lib, name)
     assert C.sizeof(pp.CathyPreproParams) == 8 * 4 + 2 * 8 + 2 * 4 + 4 * 8 + 4 * 4 + 3 * 8 + 16 * 4
@@ -236,3 +236,40 @@ def test_parallel_partition_formulation_equals_the_reference_quicksort():
         qsort(n, a1, b1)
         par_qsort(n, a2, b2, rnd.choice([8, 9, 16, 33, 100]), rnd)
         assert a1 == a2 and b1 == b2, (trial, n)
+
+
+def test_native_text_formatters_equal_the_fortran_edit_descriptors():
+    """cathy_prepro_format_real / _int (row-parallel host code of the library) against the oracle's Ew.d / Fw.d / Iw."""
+    from oracle import prepro_oracle as po
+    from pycathy_wrapper_b200 import preprocessor as pp
+    rng = np.random.default_rng(11)
+    v = np.concatenate([rng.standard_normal(400) * 10.0 ** rng.integers(-30, 30, 400), [0.0, -0.0, 1.0, -1.0, 0.5, 9.9999999999995, 0.099999999999996,
+                        1e-99, 123456.789, -9999.0, float(np.float32(0.1)), 2.5e-7, 0.999999999999949]]).reshape(-1, 7)
+    for w, d in ((21, 12), (20, 12), (10, 3), (16, 9)):
+        got = pp._block_real(v, w, d, 0)
+        want = "".join("".join(po.fmt_e(x, w, d) for x in row) + "\n" for row in v)
+        assert got == want, (w, d)
+    f = np.concatenate([rng.uniform(-1e6, 1e6, 200), [0.0, 0.004999, 0.005, 0.015, 1e9, -0.25, 0.25, 12345678901.0]]).reshape(-1, 8)
+    for w, d in ((14, 2), (15, 2), (10, 3), (5, 2)):
+        got = pp._block_real(f, w, d, 1)
+        want = "".join("".join(po.fmt_f(x, w, d) for x in row) + "\n" for row in f)
+        assert got == want, (w, d)
+    i = rng.integers(-99999, 99999, (30, 9)).astype(np.int32)
+    for w in (2, 5, 7, 12):
+        assert pp._block_int(i, w) == "".join("".join(po.fmt_i(x, w) for x in row) + "\n" for row in i)
+    # values the native routine hands back to the caller (three-digit exponent): numpy path, same text
+    big = np.array([[1e120, 1.0]])
+    assert pp._block_real(big, 21, 12, 0) == "".join(pp._E(x, 21, 12) for x in big[0]) + "\n"
+
+
+def test_dtm13_reader_fast_and_record_paths_agree():
+    from pycathy_wrapper_b200 import preprocessor as pp
+    rng = np.random.default_rng(2)
+    z = np.round(rng.uniform(1, 9, (7, 5)), 4)
+    plain = "\n".join("\t".join("%.4f" % v for v in row) for row in z) + "\n"
+    ragged = "\n".join(" ".join("%.4f" % v for v in row[:3]) + "\n" + " ".join("%.4f" % v for v in row[3:]) + " 77.0 88.0" for row in z) + "\n"
+    fortran = plain.replace(".", ".0D0 ").replace("\t", " ") if False else "\n".join(", ".join("%.4fD0" % v for v in row) for row in z) + "\n"
+    for text in (plain, ragged, fortran):
+        assert np.array_equal(pp.read_dtm13(text, 5, 7), z)
+    with pytest.raises(pp.PreproError, match="insufficient data"):
+        pp.read_dtm13(plain, 5, 8)
