@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CATHY_ABI_VERSION 6
+#define CATHY_ABI_VERSION 7
 #define CATHY_MAXIT 64 /* upper bound on ITUNS kept in a step report (CATHY.H MAXIT=30) */
 
 /* Everything DATIN / INITAL read from the project files (SRC/datin.f:80-514,
@@ -110,6 +110,9 @@ typedef struct CathyProblem {
     int32_t nsf, isfone, isfcvg, dupuit;
     const int32_t *sf_ptr;   /* [nsf+1]                                             */
     const int32_t *sf_node;  /* [sf_ptr[nsf]]                                       */
+    /* --- localized slopes KSLOPE = 3, 4 (parm line PKRL PKRR PSEL PSER, SRC/datin.f:108): inside [psel, pser] the storage term
+     * uses CHPIC3's / CHPIC4's forms (SRC/chpic3.f:30-57, SRC/chpic4.f:27-45 with DSETAN of SRC/chtanp.f:22-26) */
+    double psel, pser;
 } CathyProblem;
 
 /* One nonlinear iteration line of output/iter (SRC/conver.f:44 FORMAT 1070). */

@@ -12,7 +12,7 @@ import numpy as np
 
 from .project import CathyProject
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAXIT = 64
 _D = C.POINTER(C.c_double)
 _I = C.POINTER(C.c_int32)
@@ -64,6 +64,7 @@ class CathyProblem(C.Structure):
         ("itmxcg_scale", C.c_double),
         ("nsf", C.c_int32), ("isfone", C.c_int32), ("isfcvg", C.c_int32), ("dupuit", C.c_int32),
         ("sf_ptr", _I), ("sf_node", _I),
+        ("psel", C.c_double), ("pser", C.c_double),
     ]
 
 
@@ -143,6 +144,7 @@ class ProblemHolder:
         for name in ["pondh_min", "tolksl", "tetaf", "omega", "toluns", "tolswi", "ernlmx", "tolcg", "deltat",
                      "dtmin", "dtmax", "tmax", "dtmaga", "dtmagm", "dtreds", "dtredm"]:
             setattr(s, name, float(p[name.upper()]))
+        s.psel, s.pser = float(p.get("PSEL", 0.0)), float(p.get("PSER", 0.0))
         s.indp, s.ipond, s.wtposition = prj.indp, prj.ipond, prj.wtposition
         s.ic_psi, s.ic_pond = fd(prj.ic_psi), fd(prj.ic_pond)
         s.atm_none, s.hspatm, s.ieto = int(prj.atm_none), prj.hspatm, prj.ieto

@@ -691,8 +691,9 @@ int32_t cathy_create(const CathyProblem *prob, CathySim **out)
     if (!prob || prob->abi_version != CATHY_ABI_VERSION) FAIL(-1, "ABI version mismatch");
     if (prob->iopt != 1 && prob->iopt != 2) FAIL(-2, "IOPT=%d: must be 1 (Picard) or 2 (Newton)", prob->iopt);
     if (prob->iopt == 2 && prob->tetaf != 1.0 && prob->tetaf <= 0.0) FAIL(-2, "TETAF must be positive");
-    if (prob->kslope != 0 && !((prob->kslope == 1 || prob->kslope == 2) && prob->ivghu == 0 && prob->iopt == 1 && prob->dd_world <= 1))
-        FAIL(-2, "KSLOPE=%d: chord slopes (1, 2) are implemented for van Genuchten curves (IVGHU=0) under Picard on one GPU; localized slopes (3, 4) are not", prob->kslope);
+    if (prob->kslope != 0 && !(prob->kslope >= 1 && prob->kslope <= 4 && prob->ivghu == 0 && prob->iopt == 1 && prob->dd_world <= 1))
+        FAIL(-2, "KSLOPE=%d: chord and localized slopes (1-4) are implemented for van Genuchten curves (IVGHU=0) under Picard on one GPU", prob->kslope);
+    if (prob->kslope == 4 && !(prob->pser > prob->psel)) FAIL(-2, "KSLOPE=4 needs PSEL < PSER (parm line PKRL PKRR PSEL PSER)");
     if (!(prob->ivghu >= 0 && prob->ivghu <= 4))
         FAIL(-2, "IVGHU=%d: van Genuchten (0), extended van Genuchten (1), Huyakorn (2, 3) and Brooks-Corey (4) curves are implemented; look-up tables (-1) are not", prob->ivghu);
     if (prob->lump == 0) FAIL(-2, "LUMP=0 (consistent mass matrix) is not implemented on the device");

@@ -170,7 +170,7 @@ static int assemble_system(CathySim *S, double deltat)
         LAUNCH(S, k_curves_alt, nblk(n, S->grid_n), RED_BLOCK, n, S->cm, S->snodi.p, S->pnodi.p, S->ptnew.p, S->pnew.p, S->ptimep.p, S->timep_dirty, S->sw.p, S->ckrw.p,
                S->et1.p, S->et2.p, S->swnew.p, S->swtimep.p);
     else if (S->p.kslope != 0)
-        LAUNCH(S, k_curves_chord, nblk(n, S->grid_n), RED_BLOCK, n, make_soil(S), S->p.kslope, S->p.tolksl, S->ptnew.p, S->ptold.p, S->pnew.p, S->ptimep.p, S->timep_dirty,
+        LAUNCH(S, k_curves_chord, nblk(n, S->grid_n), RED_BLOCK, n, make_soil(S), S->p.kslope, S->p.tolksl, S->p.psel, S->p.pser, S->ptnew.p, S->ptold.p, S->pnew.p, S->ptimep.p, S->timep_dirty,
                S->sw.p, S->ckrw.p, S->et1.p, S->et2.p, S->swnew.p, S->swtimep.p);
     else
     LAUNCH(S, k_curves, nblk(n, S->grid_n), RED_BLOCK, n, make_soil(S), S->ptnew.p, S->pnew.p, S->ptimep.p, S->timep_dirty, S->sw.p, S->ckrw.p, S->et1.p, S->et2.p, S->swnew.p, S->swtimep.p);

@@ -237,8 +237,12 @@ __global__ void k_curves(int n, Soil s, const double *__restrict__ ptnew, const 
     }
 }
 // KSLOPE = 1, 2 (SRC/chpic1.f:26-50, SRC/chpic2.f:24-46; IVGHU = 0): dSe/dpsi as the chord slope between the current and the previous
-// nonlinear iterate wherever they differ by TOLKSL or more, else analytical (1) / centred difference over 2 TOLKSL (2)
-__global__ void k_curves_chord(int n, Soil s, int kslope, double tolksl, const double *__restrict__ ptnew, const double *__restrict__ ptold,
+// nonlinear iterate wherever they differ by TOLKSL or more, else analytical (1) / centred difference over 2 TOLKSL (2).
+// KSLOPE = 3, 4 (localized slopes, SRC/chpic3.f:30-57, SRC/chpic4.f:27-45), restated as written: under KSLOPE = 3 the chord slope only
+// reaches ETAI, which the Picard system never reads -- ET2 stays analytical inside [PSEL, PSER] and carries an extra factor PNODI
+// outside it; under KSLOPE = 4 ET2 takes the tangent slope DSETAN(1) of SRC/chtanp.f:22-26 (node 1's curve) inside the range.
+__global__ void k_curves_chord(int n, Soil s, int kslope, double tolksl, double psel, double pser, const double *__restrict__ ptnew,
+                               const double *__restrict__ ptold,
                                const double *__restrict__ pnew, const double *__restrict__ ptimep, int do_timep, double *__restrict__ sw,
                                double *__restrict__ ckrw, double *__restrict__ et1, double *__restrict__ et2,
                                double *__restrict__ swnew, double *__restrict__ swtimep)
@@ -248,13 +252,21 @@ __global__ void k_curves_chord(int n, Soil s, int kslope, double tolksl, const d
         const double psi = ptnew[i], pold = ptold[i], dp = psi - pold;
         const bool small = fabs(dp) < tolksl;
         double se, kr, dse;
-        vg_node(psi, psat, n_, m, s.vgn1[i], small && kslope == 1, se, kr, dse);
-        if (!small) dse = (se - fvgse(pold, psat, n_, m)) / dp;
-        else if (kslope == 2) dse = (fvgse(psi + tolksl, psat, n_, m) - fvgse(psi - tolksl, psat, n_, m)) / (2.0 * tolksl);
+        vg_node(psi, psat, n_, m, s.vgn1[i], (small && kslope == 1) || kslope >= 3, se, kr, dse);
+        double e2;
+        if (kslope >= 3) {
+            const bool inside = psi >= psel && psi <= pser;
+            if (kslope == 3) e2 = inside ? pnot * dse : s.pnodi[i] * pnot * dse;
+            else e2 = pnot * (inside ? (fvgse(pser, s.vgpsat[0], s.vgn[0], s.vgm[0]) - fvgse(psel, s.vgpsat[0], s.vgn[0], s.vgm[0])) / (pser - psel) : dse);
+        } else {
+            if (!small) dse = (se - fvgse(pold, psat, n_, m)) / dp;
+            else if (kslope == 2) dse = (fvgse(psi + tolksl, psat, n_, m) - fvgse(psi - tolksl, psat, n_, m)) / (2.0 * tolksl);
+            e2 = pnot * dse;
+        }
         const double w = pnot * se + rr;
         sw[i] = w;
         et1[i] = w * s.snodi[i];
-        et2[i] = pnot * dse;
+        et2[i] = e2;
         ckrw[i] = kr;
         const double pn = pnew[i];
         swnew[i] = pn == psi ? w : pnot * fvgse(pn, psat, n_, m) + rr;

@@ -191,3 +191,28 @@ def test_drainage_network_properties_at_one_million_cells(pp, tmp_path):
                 A[c + M * di[p[c]] + dj[p[c]]] += Aout[c] * float(wk[c])
     assert np.max(np.abs(A - g.A_inflow) / np.maximum(A, 1.0)) < 1e-12
     print("1000x1000: device %.1f ms, %d waves, %d launches, stages %s" % (g.info["device_ms"], g.info["n_waves"], g.info["n_launches"], g.info["stage_ms"]))
+
+
+def test_coupled_run_on_a_dem_preprocessed_on_the_device(pp, gpu_lib, oracle_mod, tmp_path):
+    """What the pre-processor is for: a coupled surface / subsurface run (ISIMGR = 2) on a DEM no raster set was
+    shipped for.  30 x 24 rough DEM -> device pre-processor -> the processor reads its files (project.py, SRC/datin.f:325-372) ->
+    ponded storm routed over the drainage network, device against oracle step by step."""
+    from pycathy_wrapper_b200 import synthetic
+    from pycathy_wrapper_b200.project import load_project
+    from test_gpu_parity import _run_both, psi_close
+    rng = np.random.default_rng(17)
+    nr, nc = 30, 24
+    r, c = np.mgrid[0:nr, 0:nc]
+    dem = 2.0 - 0.02 * r - 0.011 * c + 0.004 * rng.standard_normal((nr, nc))
+    d = synthetic.make_project(str(tmp_path / "prj"), nr, nc, 6, dem=dem, ic=("hydrostatic",), pond=0.004, ISIMGR=2, DELTAT=1.0, DTMIN=1e-4,
+                               DTMAX=20.0, TMAX=240.0, TIMPRT=[240.0], NODVP=[1], atmbc=[(0.0, 0.0), (30.0, 6.0e-5), (150.0, 6.0e-5), (160.0, 0.0), (1e9, 0.0)])
+    text = set_hap(open(os.path.join(d, "prepro", "hap.in")).read(), **{"Depit threshold slope": "0.500E-03"})
+    open(os.path.join(d, "prepro", "hap.in"), "w").write(text)
+    res = pp.run_preprocessor(os.path.join(d, "prepro"))
+    assert res.info["n_modifications"] > 0                                   # the noise leaves pits: the processor gets the DEPITTED dem
+    prj = load_project(d)
+    assert np.array_equal(np.asarray(prj.dem).reshape(nr, nc), res.north_first("quota"))
+    g, c, rg, rc = _run_both(gpu_lib, oracle_mod, prj)
+    ok, dmax = psi_close(g.state()["psi"], c.state()["psi"])
+    assert ok, dmax
+    assert rg.nsurf > 0 and rg.q_outlet_1 > 0
