@@ -192,6 +192,8 @@ __global__ void k_pp_gronda_apply(PP S)
 #define PP_CAP 12288
 #define PP_QT 1024
 #define PP_STK 4096
+#define PP_DSORT 8                                   /* concurrent sorters inside k_pp_depit */
+#define PP_DCAP ((PP_CAP + 1) / PP_DSORT - 1)        /* their range length: the staging buffer split PP_DSORT ways */
 
 __device__ __forceinline__ int pp_block_exscan(int v, int *ws, int &total)
 {
@@ -213,19 +215,19 @@ __device__ __forceinline__ int pp_block_exscan(int v, int *ws, int &total)
     return ws[wid] + x - v;
 }
 
-// keys S.key[1..n] / ids S.lst1[1..n]; U = S.lst2, V = S.front[0] as scratch; tasks (l, len) -> S.front[1], count -> cnt[12]
-__global__ void __launch_bounds__(PP_QT) k_pp_qsplit(PP S, int n)
+// One CTA of PP_QT threads: partitions every range of arr[1..n] / brr[1..n] longer than cap, lists the others as tasks
+// (l, len) and returns their number.  U, V: scratch of n ints each.
+__device__ int pp_qsplit_block(double *arr, int *brr, int *U, int *V, int *task, int n, int cap, int *err)
 {
     __shared__ int stk[PP_STK];
     __shared__ int ws[33];
     __shared__ int sh_l, sh_ir, sh_sp, sh_nt;
     __shared__ double sh_a;
-    double *arr = S.key;
-    int *brr = S.lst1, *U = S.lst2, *V = S.front[0], *task = S.front[1];
     const int tid = threadIdx.x;
+    __syncthreads();
     if (tid == 0) {
         sh_sp = 0; sh_nt = 0;
-        if (n > PP_CAP) { stk[0] = 1; stk[1] = n; sh_sp = 2; }
+        if (n > cap) { stk[0] = 1; stk[1] = n; sh_sp = 2; }
         else if (n >= 2) { task[0] = 1; task[1] = n; sh_nt = 1; }
     }
     __syncthreads();
@@ -284,15 +286,23 @@ __global__ void __launch_bounds__(PP_QT) k_pp_qsplit(PP S, int n)
             const int rl[2] = {l, i}, rr[2] = {j - 1, ir};
             for (int h = 0; h < 2; ++h) {
                 const int len = rr[h] - rl[h] + 1;
-                if (len > PP_CAP) {
-                    if (sh_sp + 2 > PP_STK) { atomicExch(&S.cnt[7], 8); continue; }
+                if (len > cap) {
+                    if (sh_sp + 2 > PP_STK) { atomicExch(err, 8); continue; }
                     stk[sh_sp] = rl[h]; stk[sh_sp + 1] = rr[h]; sh_sp += 2;
                 } else if (len >= 2) { task[2 * sh_nt] = rl[h]; task[2 * sh_nt + 1] = len; ++sh_nt; }
             }
         }
         __syncthreads();
     }
-    if (tid == 0) S.cnt[12] = sh_nt;
+    __syncthreads();
+    return sh_nt;
+}
+
+// keys S.key[1..n] / ids S.lst1[1..n]; scratch S.lst2, S.front[0]; tasks -> S.front[1], their number -> cnt[12]
+__global__ void __launch_bounds__(PP_QT) k_pp_qsplit(PP S, int n)
+{
+    const int nt = pp_qsplit_block(S.key, S.lst1, S.lst2, S.front[0], S.front[1], n, PP_CAP, &S.cnt[7]);
+    if (threadIdx.x == 0) S.cnt[12] = nt;
 }
 
 __global__ void __launch_bounds__(256) k_pp_qsmall(PP S)
@@ -364,10 +374,16 @@ __global__ void k_pp_pitcheck(PP S)
     }
 }
 
-// the reference's sweeps, one device thread (PRE/depit.f90:63-140).  The first sweep visits ALL cells in ascending
-// elevation, but a cell can only be raised if it is a pit on the incoming elevations or if a neighbour was raised earlier
-// in the same sweep; every other visit is a no-op.  So the first sweep pops a min-heap of list positions seeded with the
-// pits k_pp_pitcheck found and fed with the later neighbours of every raised cell: same visits that matter, same order.
+// the reference's sweeps (PRE/depit.f90:63-140) by ONE CTA.  The order of the visits is the reference's: the fixed point of
+// this in-place Gauss-Seidel raising depends on it.  What is parallel is what does not change it:
+//  * one visit: the eight neighbours are read by eight lanes of warp 0 at once ("some neighbour is lower" and "the lowest
+//    neighbour" do not depend on the order they are read in); the list of the next sweep is appended in the reference's
+//    neighbour order through a ballot;
+//  * the first sweep visits ALL cells in ascending elevation, but a cell can only be raised if it is a pit on the incoming
+//    elevations or if a neighbour was raised earlier in the same sweep -- every other visit is a no-op.  So it pops a
+//    min-heap of list positions seeded with the pits k_pp_pitcheck found and fed with the later neighbours of every raised
+//    cell: same visits that matter, same order;
+//  * the re-sort of a long list between two sweeps is the parallel quicksort replay (pp_qsplit_block + staged pp_qsort).
 __device__ __forceinline__ void pp_heap_push(int *h, int &n, int v)
 {
     int c = n++;
@@ -389,77 +405,128 @@ __device__ __forceinline__ int pp_heap_pop(int *h, int &n)
     return top;
 }
 
-__global__ void k_pp_depit(PP S)
+__global__ void __launch_bounds__(PP_QT) k_pp_depit(PP S)
 {
-    if (blockIdx.x || threadIdx.x) return;
+    extern __shared__ double pp_sm[];
+    double *sk = pp_sm;                                  // [PP_CAP + 1], staging of the short ranges
+    int *si = (int *)(pp_sm + PP_CAP + 1);
+    __shared__ int sh_cmd, sh_n;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nc = S.nc, N = S.N, M = S.M;
     const double eps = rmul(S.h.pt0, S.h.delta_x0);
     const int outlet = S.order[nc];
-    int *pit1 = S.lst1, *pit2 = S.lst2, *heap = S.front[1];
-    int hn = 0;
-    for (int t = 0; t < S.cnt[5]; ++t) pp_heap_push(heap, hn, nc - S.rank[S.front[0][t]] + 1);
-    int n_pits = nc, total = 0, pass = 0, max_list = 0;
+    int *heap = S.front[1];
+    int hn = 0, n_pits = nc, total = 0, pass = 0, max_list = 0, cur = 0;     // cur: which of lst1 / lst2 holds the list being swept
     long long sort_cycles = 0, t_start = clock64();
+    if (tid == 0) for (int t = 0; t < S.cnt[5]; ++t) pp_heap_push(heap, hn, nc - S.rank[S.front[0][t]] + 1);
+    // neighbour of lane k < 8 in the reference's enumeration (ii outer, jj inner, the cell itself skipped)
+    const int kk = lane < 4 ? lane : lane + 1, ndi = kk / 3 - 1, ndj = kk % 3 - 1;
     for (;;) {
-        int nn_mod = 0, nn_pit = 0, n = 0;
         ++pass;
-        for (;;) {
-            int ib, pos = 0;
-            if (pass == 1) {
-                if (hn == 0) break;
-                pos = pp_heap_pop(heap, hn);
-                ib = S.order[nc - pos + 1];
-            } else {
-                if (++n > n_pits) break;
-                ib = pit1[n];
-            }
-            if (ib == outlet) continue;
-            double qc = S.q[ib];
-            int i, j;
-            pp_ij(S, ib, i, j);
-            double qmin = DBL_MAX;
-            bool lower = false;
-            for (int di = -1; di <= 1 && !lower; ++di)
-                for (int dj = -1; dj <= 1; ++dj) {
-                    int ii = i + di, jj = j + dj;
-                    if ((di == 0 && dj == 0) || ii < 1 || ii > N || jj < 1 || jj > M) continue;
-                    double qn = S.q[ib + M * di + dj];
-                    if (qn < 0.0) continue;
-                    if (qn < qc) { lower = true; break; }
-                    if (qn < qmin) qmin = qn;
+        int *pit1 = cur ? S.lst2 : S.lst1, *pit2 = cur ? S.lst1 : S.lst2;
+        if (wid == 0) {
+            int nn_mod = 0, nn_pit = 0, n = 0;
+            for (;;) {
+                int ib = -1, pos = 0;
+                if (lane == 0) {
+                    if (pass == 1) { if (hn > 0) { pos = pp_heap_pop(heap, hn); ib = S.order[nc - pos + 1]; } }
+                    else if (++n <= n_pits) ib = pit1[n];
                 }
-            if (lower) continue;
-            if (qc <= qmin) {
-                S.q[ib] = radd(qmin, eps);
-                ++total; ++nn_mod;
-                for (int di = -1; di <= 1; ++di)
-                    for (int dj = -1; dj <= 1; ++dj) {
-                        int ii = i + di, jj = j + dj;
-                        if ((di == 0 && dj == 0) || ii < 1 || ii > N || jj < 1 || jj > M) continue;
-                        int nbr = ib + M * di + dj;
-                        if (!S.pres[nbr]) continue;
-                        if (S.stamp[nbr] != pass) { S.stamp[nbr] = pass; pit2[++nn_pit] = nbr; }
-                        if (pass == 1 && S.dep[nbr] == 0) {
-                            int pn = nc - S.rank[nbr] + 1;
-                            if (pn > pos) { S.dep[nbr] = 1; pp_heap_push(heap, hn, pn); }
+                int nib = -1;                                    // the visit after this one, as far as it is known now
+                if (lane == 0) {
+                    if (pass == 1) { if (hn > 0) nib = S.order[nc - heap[0] + 1]; }
+                    else if (n + 1 <= n_pits) nib = pit1[n + 1];
+                }
+                ib = __shfl_sync(0xffffffffu, ib, 0);
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                nib = __shfl_sync(0xffffffffu, nib, 0);
+                if (ib < 0) break;
+                if (nib > 0 && lane >= 8 && lane < 17) {         // idle lanes pull its 3x3 window towards the SM: a hint, not a read
+                    int i2, j2;
+                    pp_ij(S, nib, i2, j2);
+                    const int k2 = lane - 8, d2i = k2 / 3 - 1, d2j = k2 % 3 - 1;
+                    if (i2 + d2i >= 1 && i2 + d2i <= N && j2 + d2j >= 1 && j2 + d2j <= M)
+                        { double sink; asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(sink) : "l"(&S.q[nib + M * d2i + d2j])); }
+                }
+                if (ib == outlet) continue;
+                const double qc = S.q[ib];
+                int i, j;
+                pp_ij(S, ib, i, j);
+                const int ii = i + ndi, jj = j + ndj;
+                const bool valid = lane < 8 && ii >= 1 && ii <= N && jj >= 1 && jj <= M;
+                const int nbr = valid ? ib + M * ndi + ndj : 0;
+                const double qn = valid ? S.q[nbr] : -1.0;
+                const bool hasq = valid && qn >= 0.0;
+                if (__any_sync(0xffffffffu, hasq && qn < qc)) continue;
+                double qmin = hasq ? qn : DBL_MAX;
+                for (int o = 4; o >= 1; o >>= 1) qmin = fmin(qmin, __shfl_xor_sync(0xffffffffu, qmin, o));
+                qmin = __shfl_sync(0xffffffffu, qmin, 0);
+                if (qc <= qmin) {
+                    if (lane == 0) S.q[ib] = radd(qmin, eps);
+                    ++total; ++nn_mod;
+                    const bool pr = hasq;                        // a catchment cell <=> a positive elevation (k_pp_load refuses the rest)
+                    const int st = pr ? S.stamp[nbr] : pass, dp = (pr && pass == 1) ? S.dep[nbr] : 1, rk = (pr && pass == 1) ? S.rank[nbr] : 0;
+                    const unsigned m = __ballot_sync(0xffffffffu, pr && st != pass);
+                    if (pr && st != pass) { S.stamp[nbr] = pass; pit2[nn_pit + 1 + __popc(m & ((1u << lane) - 1))] = nbr; }
+                    nn_pit += __popc(m);
+                    if (pass == 1) {
+                        const int pn = nc - rk + 1;
+                        const bool push = pr && dp == 0 && pn > pos;
+                        unsigned pm = __ballot_sync(0xffffffffu, push);
+                        if (push) S.dep[nbr] = 1;
+                        while (pm) {
+                            const int src = __ffs(pm) - 1;
+                            pm &= pm - 1;
+                            const int v = __shfl_sync(0xffffffffu, pn, src);
+                            if (lane == 0) pp_heap_push(heap, hn, v);
                         }
                     }
+                }
+                __syncwarp();
+            }
+            if (lane == 0) { sh_cmd = nn_mod > 0 ? 1 : 0; sh_n = nn_pit; }
+        }
+        __syncthreads();
+        if (sh_cmd == 0) break;
+        const int nn = sh_n;
+        long long t0 = clock64();
+        for (int k = 1 + tid; k <= nn; k += PP_QT) S.key[k] = S.q[pit2[k]];
+        __syncthreads();
+        if (nn <= 64) {
+            if (tid == 0) pp_qsort(nn, S.key, pit2);
+        } else {
+            // scratch: the swept list's buffer (pit1), the pit list of k_pp_pitcheck (front[0], consumed) and -- after the first
+            // sweep -- nothing else is live; the heap (front[1]) is empty whenever a sweep has ended
+            int *task = S.front[1];
+            const int nt = pp_qsplit_block(S.key, pit2, pit1, S.front[0], task, nn, PP_DCAP, &S.cnt[7]);
+            // the short ranges: PP_DSORT warps at a time, each with its own slice of the staging buffer
+            if (wid < PP_DSORT) {
+                double *wk = sk + wid * (PP_DCAP + 1);
+                int *wi = si + wid * (PP_DCAP + 1);
+                for (int t = wid; t < nt; t += PP_DSORT) {
+                    const int l = task[2 * t], len = task[2 * t + 1];
+                    for (int k = lane; k < len; k += 32) { wk[1 + k] = S.key[l + k]; wi[1 + k] = pit2[l + k]; }
+                    __syncwarp();
+                    if (lane == 0) pp_qsort(len, wk, wi);
+                    __syncwarp();
+                    for (int k = lane; k < len; k += 32) { S.key[l + k] = wk[1 + k]; pit2[l + k] = wi[1 + k]; }
+                    __syncwarp();
+                }
             }
         }
-        if (nn_mod == 0) break;
-        long long t0 = clock64();
-        for (int k = 1; k <= nn_pit; ++k) S.key[k] = S.q[pit2[k]];
-        pp_qsort(nn_pit, S.key, pit2);
         sort_cycles += clock64() - t0;
-        if (nn_pit > max_list) max_list = nn_pit;
-        int *t = pit1; pit1 = pit2; pit2 = t;
-        n_pits = nn_pit;
+        __syncthreads();
+        if (nn > max_list) max_list = nn;
+        n_pits = nn;
+        cur ^= 1;
     }
-    S.cnt[6] = total;
-    S.cnt[8] = pass;
-    S.cnt[13] = max_list;
-    S.scal[2] = (double)sort_cycles;
-    S.scal[3] = (double)(clock64() - t_start);
+    if (tid == 0) {
+        S.cnt[6] = total;
+        S.cnt[8] = pass;
+        S.cnt[13] = max_list;
+        S.scal[2] = (double)sort_cycles;
+        S.scal[3] = (double)(clock64() - t_start);
+    }
 }
 
 // ------------------------------------------------------------------ FACET (PRE/facet.f90:10-47)
@@ -561,18 +628,19 @@ __global__ void k_pp_local(PP S)
 __global__ void k_pp_smean(PP S)
 {
     const int lane = threadIdx.x;
-    double sum = 0.0, cnt = 0.0;
+    double sum = 0.0;
     const int outlet = S.order[S.nc];
     for (int base = 1; base <= S.nc; base += 32) {
-        int n = base + lane;
-        int ib = (n <= S.nc) ? S.order[n] : 0;
-        double v = (ib && ib != outlet) ? S.smax[ib] : -1.0;
-        for (int k = 0; k < 32; ++k) {
-            double vk = __shfl_sync(0xffffffffu, v, k);
-            if (vk >= 0.0) { sum = radd(sum, vk); cnt += 1.0; }
-        }
+        const int n = base + lane;
+        const int ib = (n <= S.nc) ? S.order[n] : 0;
+        const double v = (ib && ib != outlet) ? S.smax[ib] : 0.0;      // s_max >= 0: a skipped cell adds +0, which changes nothing
+        double w[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) w[k] = __shfl_sync(0xffffffffu, v, k);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) sum = radd(sum, w[k]);
     }
-    if (lane == 0) S.scal[0] = rdiv(sum, cnt);
+    if (lane == 0) S.scal[0] = rdiv(sum, (double)(S.nc - 1));
 }
 
 // ------------------------------------------------------------------ DSF as a dependency wavefront
@@ -704,7 +772,9 @@ __device__ void pp_cell(const PP &S, int ib)
 __global__ void __launch_bounds__(256) k_pp_sweep(PP S)
 {
     cg::grid_group grid = cg::this_grid();
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    // cell t of a wavefront goes to CTA t mod gridDim.x: a wavefront holds a few hundred cells, each a chain of dependent loads,
+    // so they are spread over all SMs instead of filling the first CTA
+    const int gtid = blockIdx.x + gridDim.x * threadIdx.x, gsz = gridDim.x * blockDim.x;
     int wave = 0;
     for (;;) {
         const int ncur = *((volatile int *)&S.cnt[wave % 3]);
@@ -851,6 +921,7 @@ extern "C" int32_t cathy_prepro_run(const CathyPreproParams *p, const double *qu
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) PFAIL(-100, "cathy_prepro_run: no CUDA device (there is no CPU path)");
     }
     PCK(cudaSetDevice(device));
+    PCK(cudaFuncSetAttribute(k_pp_depit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((PP_CAP + 1) * (sizeof(double) + sizeof(int)))));
     PCK(cudaFuncSetAttribute(k_pp_qsmall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((PP_CAP + 1) * (sizeof(double) + sizeof(int)))));
     {
         S.h = *p;
@@ -898,7 +969,7 @@ extern "C" int32_t cathy_prepro_run(const CathyPreproParams *p, const double *qu
         if (cnt[7] == 2) PFAIL(-2, "catchment with more than one outlet cell!");
         PCK(cudaEventRecord(evs[2], 0));
         if (cnt[5] > 0) {
-            k_pp_depit<<<1, 32>>>(S); ++launches;
+            k_pp_depit<<<1, PP_QT, (PP_CAP + 1) * (sizeof(double) + sizeof(int))>>>(S); ++launches;
             PCK(cudaEventRecord(evs[3], 0));
             PCK(pp_csort(S, GRID, TPB, nsm, launches));
         } else PCK(cudaEventRecord(evs[3], 0));
