@@ -78,7 +78,7 @@ const char *cathy_prepro_last_error(void);
 
 /* Host-side text of the raster files (RBB, PRE/mrbb_sr.f90:445-470): nrows records of ncols fields in Fortran Ew.d
  * (kind 0) or Fw.d (kind 1), resp. Iw, each record ending in a newline, formatted row-parallel on `nthreads` host
- * threads (0 = up to 16).  out holds nrows * (ncols * w + 1) bytes; returns the bytes written, -1 if a value needs a
+ * threads (0 = up to 32).  out holds nrows * (ncols * w + 1) bytes; returns the bytes written, -1 if a value needs a
  * form these routines do not write (NaN, infinity, three-digit exponent). */
 int64_t cathy_prepro_format_real(const double *v, int64_t nrows, int64_t ncols, int32_t w, int32_t d, int32_t kind, char *out,
                                  int32_t nthreads);

@@ -1098,7 +1098,7 @@ template <class F>
 static int64_t pp_rows_parallel(int64_t nrows, int32_t nthreads, F row)
 {
     int hw = (int)std::thread::hardware_concurrency();
-    int nt = nthreads > 0 ? nthreads : (hw > 16 ? 16 : (hw < 1 ? 1 : hw));
+    int nt = nthreads > 0 ? nthreads : (hw > 32 ? 32 : (hw < 1 ? 1 : hw));
     if ((int64_t)nt > nrows) nt = (int)(nrows < 1 ? 1 : nrows);
     std::atomic<int> bad(0);
     std::vector<std::thread> th;

@@ -250,29 +250,29 @@ def _e_column(v: np.ndarray, w: int, d: int) -> np.ndarray:
     return out.view("S%d" % w).reshape(len(v)).astype(str)
 
 
-def _block_real(v2d: np.ndarray, w: int, d: int, kind: int) -> str:
+def _block_real(v2d: np.ndarray, w: int, d: int, kind: int) -> bytes:
     """[M][N] doubles -> M records of N fields Ew.d (kind 0) / Fw.d (kind 1): native row-parallel formatter of the library,
     numpy when a value needs a form it does not write."""
     lib = load_prepro_library()[0]
     v = np.ascontiguousarray(v2d, dtype=np.float64)
     M, N = v.shape
-    buf = C.create_string_buffer(M * (N * w + 1))
-    if lib.cathy_prepro_format_real(v.ctypes.data_as(_D), M, N, w, d, kind, buf, 0) == M * (N * w + 1):
-        return buf.raw.decode("ascii")
+    buf = np.empty(M * (N * w + 1), dtype=np.uint8)
+    if lib.cathy_prepro_format_real(v.ctypes.data_as(_D), M, N, w, d, kind, buf.ctypes.data_as(C.c_char_p), 0) == buf.size:
+        return buf.tobytes()
     if kind == 1:
         txt = np.char.mod("%%%d.%df" % (w, d), v)
     else:
         txt = _e_column(v.ravel(), w, d).reshape(M, N)
-    return "\n".join("".join(row) for row in txt) + "\n"
+    return ("\n".join("".join(row) for row in txt) + "\n").encode("ascii")
 
 
-def _block_int(v2d: np.ndarray, w: int) -> str:
+def _block_int(v2d: np.ndarray, w: int) -> bytes:
     lib = load_prepro_library()[0]
     v = np.ascontiguousarray(v2d, dtype=np.int32)
     M, N = v.shape
-    buf = C.create_string_buffer(M * (N * w + 1))
-    lib.cathy_prepro_format_int(v.ctypes.data_as(_I), M, N, w, buf, 0)
-    return buf.raw.decode("ascii")
+    buf = np.empty(M * (N * w + 1), dtype=np.uint8)
+    lib.cathy_prepro_format_int(v.ctypes.data_as(_I), M, N, w, buf.ctypes.data_as(C.c_char_p), 0)
+    return buf.tobytes()
 
 
 def _header(hap: dict, ht: int) -> str:
@@ -316,6 +316,9 @@ class PreproResult:
         return getattr(self, field).reshape(N, M).T[::-1]
 
     def raster_text(self, name: str, ht: int = 2, nodata: float = 0.0, ips: int = 1) -> str:
+        return self.raster_bytes(name, ht, nodata, ips).decode("ascii")
+
+    def raster_bytes(self, name: str, ht: int = 2, nodata: float = 0.0, ips: int = 1) -> bytes:
         """RBB (PRE/mrbb_sr.f90:243-470)."""
         kind, field = next((k, f) for n, k, f in RASTERS if n == name)
         N, M = self.hap["N"], self.hap["M"]
@@ -331,24 +334,24 @@ class PreproResult:
             imax = max(int(vi[pres].max()), abs(int(nodata32)))
             imin = min(int(vi[pres].min()), int(nodata32))
             w = 2 if imax == 0 else int(math.log10(float(np.float32(imax)))) + (3 if imin < 0 else 2)
-            return _header(self.hap, ht) + _block_int(np.where(pres, vi, int(nodata32)), w)
+            return _header(self.hap, ht).encode("ascii") + _block_int(np.where(pres, vi, int(nodata32)), w)
         vr = np.where(pres, g.astype(np.float64), nodata32)
         neg = min(float(vr[pres].min()), nodata32) < 0.0
         if kind == "a":
-            return _header(self.hap, ht) + _block_real(vr, 15 if neg else 14, 2, 1)
-        return _header(self.hap, ht) + _block_real(vr, 20 if neg else 21, 12, 0)
+            return _header(self.hap, ht).encode("ascii") + _block_real(vr, 15 if neg else 14, 2, 1)
+        return _header(self.hap, ht).encode("ascii") + _block_real(vr, 20 if neg else 21, 12, 0)
 
     def qoi_a_text(self) -> str:
         """hg.f90:31-37: N_celle then the cells in descending elevation, list-directed INTEGER*4 (width 12)."""
         v = np.concatenate(([self.info["n_cells"]], self.order[:self.info["n_cells"]])).astype(np.int32)
-        return _block_int(v.reshape(-1, 1), 12)
+        return _block_int(v.reshape(-1, 1), 12).decode("ascii")
 
     def write(self, directory: str, ht: int = 2, nodata: float = 0.0, ips: int = 1) -> None:
         with open(os.path.join(directory, "hap.in"), "w") as fh:
             fh.write(self.info["hap_text"])
         for name, _, _ in RASTERS:
-            with open(os.path.join(directory, name), "w") as fh:
-                fh.write(self.raster_text(name, ht, nodata, ips))
+            with open(os.path.join(directory, name), "wb") as fh:
+                fh.write(self.raster_bytes(name, ht, nodata, ips))
         with open(os.path.join(directory, "qoi_a"), "w") as fh:
             fh.write(self.qoi_a_text())
 

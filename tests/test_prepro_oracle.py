@@ -246,20 +246,20 @@ def test_native_text_formatters_equal_the_fortran_edit_descriptors():
     v = np.concatenate([rng.standard_normal(400) * 10.0 ** rng.integers(-30, 30, 400), [0.0, -0.0, 1.0, -1.0, 0.5, 9.9999999999995, 0.099999999999996,
                         1e-99, 123456.789, -9999.0, float(np.float32(0.1)), 2.5e-7, 0.999999999999949]]).reshape(-1, 7)
     for w, d in ((21, 12), (20, 12), (10, 3), (16, 9)):
-        got = pp._block_real(v, w, d, 0)
+        got = pp._block_real(v, w, d, 0).decode()
         want = "".join("".join(po.fmt_e(x, w, d) for x in row) + "\n" for row in v)
         assert got == want, (w, d)
     f = np.concatenate([rng.uniform(-1e6, 1e6, 200), [0.0, 0.004999, 0.005, 0.015, 1e9, -0.25, 0.25, 12345678901.0]]).reshape(-1, 8)
     for w, d in ((14, 2), (15, 2), (10, 3), (5, 2)):
-        got = pp._block_real(f, w, d, 1)
+        got = pp._block_real(f, w, d, 1).decode()
         want = "".join("".join(po.fmt_f(x, w, d) for x in row) + "\n" for row in f)
         assert got == want, (w, d)
     i = rng.integers(-99999, 99999, (30, 9)).astype(np.int32)
     for w in (2, 5, 7, 12):
-        assert pp._block_int(i, w) == "".join("".join(po.fmt_i(x, w) for x in row) + "\n" for row in i)
+        assert pp._block_int(i, w).decode() == "".join("".join(po.fmt_i(x, w) for x in row) + "\n" for row in i)
     # values the native routine hands back to the caller (three-digit exponent): numpy path, same text
     big = np.array([[1e120, 1.0]])
-    assert pp._block_real(big, 21, 12, 0) == "".join(pp._E(x, 21, 12) for x in big[0]) + "\n"
+    assert pp._block_real(big, 21, 12, 0).decode() == "".join(pp._E(x, 21, 12) for x in big[0]) + "\n"
 
 
 def test_dtm13_reader_fast_and_record_paths_agree():
