@@ -67,8 +67,7 @@ typedef struct CathyPreproOut {
 /* CSORT + DEPIT + CSORT + CCA + SMEAN + DSF + HG on cuda device `device`.
  * quota_in[N*M]: elevations, present[N*M]: 1 = catchment cell (dtm_13.val value > -9999, PRE/wbb_sr.f90:76).
  * Returns 0, or a negative code with a text in cathy_prepro_last_error():
- *  -1 bad arguments / unsupported option, -2 "catchment with more than one outlet cell!" (PRE/depit.f90:56-61),
- *  -3 a cell drains onto a cell outside the catchment (the reference stops in dtm_A_inflow, PRE/mbbio.f90:814-824),
+ *  -1 bad arguments / unsupported option (nchc = 3, a raster one cell wide: both undefined in the reference), -2 "catchment with more than one outlet cell!" (PRE/depit.f90:56-61),
  *  -4 non-positive elevation inside the catchment (the reference uses 0 and negative values as "no cell" marks,
  *     PRE/dsf.f90:87-99), -5 boundary-channel check of PRE/wbb_sr.f90:147-158, -100 CUDA error. */
 int32_t cathy_prepro_run(const CathyPreproParams *p, const double *quota_in, const uint8_t *present, int32_t device,

@@ -235,6 +235,12 @@ def qsort(n: int, arr: list, brr: list) -> None:
                 l = i
 
 
+def _div32(a, b) -> np.float32:
+    """a / b with IEEE semantics (x / 0 = inf or NaN, as the Fortran executable computes it), rounded to REAL(4)."""
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        return np.float32(np.float64(a) / np.float64(b))
+
+
 def facet(e0: float, e1: float, e2: float, dx: float, dy: float):
     """FACET (PRE/facet.f90:10-47): aspect r and slope of the steepest direction inside one triangular facet."""
     pi = 4.0 * math.atan(1.0)
@@ -580,7 +586,7 @@ class Prepro:
                 ASk = F32(A_out * math.pow(s_max, kas))
                 sumdev_1 = lam * sumdev + dev_1
                 sumdev_2 = lam * sumdev + dev_2
-                DN = F32(float(Kp) / (-self.mean_s_max))
+                DN = _div32(Kp, -self.mean_s_max)
                 if hcID == 0:
                     hcID = self.channel_initiation(A_out, ASk, DN)
                 if hcID == 1 and h["ndcf"] == 1:
@@ -646,7 +652,7 @@ class Prepro:
                     epl_1 = F32(dx)
                     ls_1 = F32((e0 - emin) / float(epl_1))
                     ASk = F32(A_out * math.pow(float(ls_1), kas))
-                    DN = F32(float(Kp) / (-self.mean_s_max))
+                    DN = _div32(Kp, -self.mean_s_max)
                     if hcID == 0:
                         hcID = self.channel_initiation(A_out, ASk, DN)
                     cv1 = ib + M * _DI[pL] + _DJ[pL]
@@ -658,7 +664,7 @@ class Prepro:
                     epl_2 = F32(dxy)
                     ls_2 = F32((e0 - emin) / float(epl_2))
                     ASk = F32(A_out * math.pow(float(ls_2), kas))
-                    DN = F32(float(Kp) / (-self.mean_s_max))
+                    DN = _div32(Kp, -self.mean_s_max)
                     sumdev_2 = lam * sumdev
                     cv2 = ib + M * _DI[pL] + _DJ[pL]
                     self.A_inflow[cv2] = float(self.A_inflow[cv2]) + A_out * 1.0

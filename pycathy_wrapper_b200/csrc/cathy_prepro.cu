@@ -912,6 +912,7 @@ extern "C" int32_t cathy_prepro_run(const CathyPreproParams *p, const double *qu
     if (!p || !quota_in || !present || !out) PFAIL(-1, "cathy_prepro_run: null argument");
     if (p->abi_version != CATHY_PREPRO_ABI_VERSION) PFAIL(-1, "cathy_prepro_run: ABI version %d, library has %d", p->abi_version, CATHY_PREPRO_ABI_VERSION);
     if (p->N < 1 || p->M < 1 || (long long)p->N * p->M > 2000000000LL) PFAIL(-1, "cathy_prepro_run: bad raster size %d x %d", p->N, p->M);
+    if (p->N < 2 || p->M < 2) PFAIL(-1, "a raster one cell wide has no facet: the reference then carries an uninitialised channel flag from cell to cell (PRE/dsf.f90:64,470), its result is undefined");
     if (p->imethod != 1 && p->imethod != 2) PFAIL(-1, "unespected imethod!");
     if (p->nchc == 3) PFAIL(-1, "channel initiation by normalised divergence (nchc = 3) is not built: the reference reads an uninitialised curvature on the rim cells (PRE/cca.f90:24,87)");
     if (p->nchc != 1 && p->nchc != 2) PFAIL(-1, "nchc out of range!");

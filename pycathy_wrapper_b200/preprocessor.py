@@ -349,9 +349,13 @@ class PreproResult:
     def write(self, directory: str, ht: int = 2, nodata: float = 0.0, ips: int = 1) -> None:
         with open(os.path.join(directory, "hap.in"), "w") as fh:
             fh.write(self.info["hap_text"])
-        for name, _, _ in RASTERS:
+        def one(name):
             with open(os.path.join(directory, name), "wb") as fh:
                 fh.write(self.raster_bytes(name, ht, nodata, ips))
+        # 21 independent files: numpy, the native formatter and the file writes all release the GIL
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+            list(pool.map(one, [name for name, _, _ in RASTERS]))
         with open(os.path.join(directory, "qoi_a"), "w") as fh:
             fh.write(self.qoi_a_text())
 

@@ -55,6 +55,16 @@ def cases():
     yield "mask_d8", z, {"pt": "0.100E-02", "cc": "-0.100E+11", "A_thr": "0.100000000E+01"}
     yield "deep_pits", rough(rng, 16, 14, 0.02), {}                   # pt = 1.3e-7: thousands of DEPIT sweeps
     yield "bcc", rough(rng, 30, 30, 0.02), {"pt": "0.100E-02", "bcc": 1}
+    # edge shapes (appended so that the random stream of the cases above is unchanged)
+    yield "tiny_2x3", rough(rng, 2, 3, 0.0), {}
+    # rasters one cell wide have no facet at all: the ELF then carries an UNINITIALISED channel flag from cell to cell
+    # (PRE/dsf.f90:64,470; 32565 in dtm_hcID here) -- not a fixture; the draws stay so that `split` keeps its random stream
+    rough(rng, 1, 12, 0.001)
+    rough(rng, 9, 1, 0.02)
+    z2 = rough(rng, 12, 10, 0.01)
+    z2[:, 4] = -9999.0                                               # a null column splits the raster: two basins, one sort order
+    z2[5, 4] = 4.7
+    yield "split", z2, {"pt": "0.100E-02"}
 
 
 def main():

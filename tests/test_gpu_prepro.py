@@ -142,6 +142,10 @@ def test_device_preprocessor_refuses_what_it_does_not_build(pp, tmp_path):
     t3 = set_hap(t, **{"Channel initiation method": "3"})
     with pytest.raises(pp.PreproError, match="nchc = 3"):
         pp.terrain_analysis(t3, open(d + "/dtm_13.val").read())
+    from pycathy_wrapper_b200 import synthetic
+    synthetic.write_hapin(str(tmp_path / "strip.in"), 1, 12, 0.5, 0.5)
+    with pytest.raises(pp.PreproError, match="one cell wide"):
+        pp.terrain_analysis(open(str(tmp_path / "strip.in")).read(), " ".join("%.3f" % (2.0 - 0.01 * k) for k in range(12)) + "\n")
     z = np.loadtxt(d + "/dtm_13.val")
     z[3, 3] = 0.0
     with pytest.raises(pp.PreproError, match="non-positive elevation"):

@@ -30,7 +30,7 @@ def golden_files(d):
 
 
 def test_fixture_set_is_complete():
-    assert {"plane17", "rough_lad", "rough_ltd_pbm_d8", "rough_pbm", "chan_ndcf", "chan_ask", "mask", "mask_d8", "deep_pits", "bcc"} <= set(CASES)
+    assert {"plane17", "rough_lad", "rough_ltd_pbm_d8", "rough_pbm", "chan_ndcf", "chan_ask", "mask", "mask_d8", "deep_pits", "bcc", "tiny_2x3", "split"} <= set(CASES)
 
 
 @pytest.mark.parametrize("case", CASES)
