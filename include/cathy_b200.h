@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CATHY_ABI_VERSION 7
+#define CATHY_ABI_VERSION 8
 #define CATHY_MAXIT 64 /* upper bound on ITUNS kept in a step report (CATHY.H MAXIT=30) */
 
 /* Everything DATIN / INITAL read from the project files (SRC/datin.f:80-514,
@@ -174,6 +174,13 @@ double cathy_initial_storage(const CathySim *sim);
 /* One pass of the time loop body SRC/cathy_main.f:2882-3829 up to and including TIMUPD:
  * BC update, surface routing, FLOW3D with back-stepping, mass balance, hydrograph terms. */
 int32_t cathy_step(CathySim *sim, CathyStepReport *rep);
+
+/* Nonlinear iterations of the FAILED attempts of the last cathy_step: the reference lists them in output/iter before those of the
+ * accepted attempt, each under its own "(NSTEP: ..  DELTAT: ..  TIME: ..)" line (SRC/cathy_main.f FORMAT 1060/1065, SRC/conver.f
+ * FORMAT 1070).  Attempt a (0-based, in the order they were made) ran nrec[a] iterations with time step deltat[a] ending at time[a];
+ * its records are rec[a*CATHY_MAXIT .. a*CATHY_MAXIT + nrec[a]).  Returns the number of failed attempts (= kbackt of the report);
+ * at most max_attempts of them are copied. */
+int32_t cathy_attempt_log(CathySim *sim, int32_t max_attempts, int32_t *nrec, double *deltat, double *time, CathyIterRecord *rec);
 
 /* State after the last accepted step (what DETOUT prints, SRC/detout.f:29-128).
  * Any pointer may be NULL.  psi,sw,ckrw,qtranie: [N]; pond,atmact,atmpot,ovfl: [NNOD]; ifatm [NNOD]. */

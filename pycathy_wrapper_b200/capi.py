@@ -12,7 +12,7 @@ import numpy as np
 
 from .project import CathyProject
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAXIT = 64
 _D = C.POINTER(C.c_double)
 _I = C.POINTER(C.c_int32)
@@ -198,7 +198,7 @@ class CathyLib:
     """Binds one shared library exporting the cathy_b200.h entry points under ``prefix``."""
 
     SYMBOLS = ["sizeof_problem", "sizeof_report", "last_error", "create", "destroy", "get_dims", "get_mesh",
-               "initial_storage", "step", "get_state", "get_velocity", "get_recharge", "get_wtdepth", "set_psi", "upload_atm_record", "debug_assemble", "debug_spmv", "debug_solve"]
+               "initial_storage", "step", "attempt_log", "get_state", "get_velocity", "get_recharge", "get_wtdepth", "set_psi", "upload_atm_record", "debug_assemble", "debug_spmv", "debug_solve"]
 
     # entry points only the product library has (in-process ensemble support); bound when present
     PRODUCT_ONLY = ["pack_state", "unpack_psi", "restart", "set_soil", "set_atm_table", "dd_export", "dd_connect", "dd_connect_local", "dd_start", "dd_info", "solver_info", "solver_limits", "plan_info", "get_state_async", "state_wait"]
@@ -251,6 +251,7 @@ class CathyLib:
         f["initial_storage"].argtypes = [C.c_void_p]
         f["initial_storage"].restype = C.c_double
         f["step"].argtypes = [C.c_void_p, C.POINTER(CathyStepReport)]
+        f["attempt_log"].argtypes = [C.c_void_p, C.c_int32, _I, _D, _D, C.POINTER(CathyIterRecord)]
         f["get_state"].argtypes = [C.c_void_p, _D, _D, _D, _D, _D, _D, _D, _D, _I]
         f["get_velocity"].argtypes = [C.c_void_p, _D, _D, _D, _D, _D, _D]
         f["get_recharge"].argtypes = [C.c_void_p, _D, _D]
@@ -311,6 +312,18 @@ class Simulation:
         if rc != 0:
             raise CathyLibraryError(f"{self.lib.prefix}step failed ({rc}): {self.lib.error()}")
         return rep
+
+    def attempt_log(self) -> list:
+        """Failed attempts of the last step, in the order they were made: [(deltat, time, [CathyIterRecord, ...]), ...] -- what the
+        reference lists in output/iter before the accepted attempt (cathy_attempt_log)."""
+        na = self.lib.f["attempt_log"](self.h, 0, None, None, None, None)
+        if na <= 0:
+            return []
+        nrec = np.zeros(na, dtype=np.int32)
+        dt, tm = np.zeros(na), np.zeros(na)
+        rec = (CathyIterRecord * (MAXIT * na))()
+        self.lib.f["attempt_log"](self.h, na, nrec.ctypes.data_as(_I), dt.ctypes.data_as(_D), tm.ctypes.data_as(_D), rec)
+        return [(float(dt[a]), float(tm[a]), [rec[a * MAXIT + k] for k in range(int(nrec[a]))]) for a in range(na)]
 
     def state_buffers(self, pinned: bool = False) -> dict:
         """Host arrays for ``state(out=...)``; pinned (page-locked, via torch) buffers make the device-to-host copies DMA at

@@ -68,6 +68,19 @@ const char *cathy_last_error(void) { return g_err; }
 int64_t cathy_sizeof_problem(void) { return (int64_t)sizeof(CathyProblem); }
 int64_t cathy_sizeof_report(void) { return (int64_t)sizeof(CathyStepReport); }
 int32_t cathy_abi_version(void) { return CATHY_ABI_VERSION; }
+int32_t cathy_attempt_log(CathySim *S, int32_t max_attempts, int32_t *nrec, double *deltat, double *time, CathyIterRecord *rec)
+{
+    if (!S) return -1;
+    const int na = (int)S->attempts.size();
+    for (int a = 0; a < na && a < max_attempts; ++a) {
+        const CathySim::Attempt &t = S->attempts[a];
+        if (nrec) nrec[a] = t.n;
+        if (deltat) deltat[a] = t.deltat;
+        if (time) time[a] = t.time;
+        if (rec) memcpy(rec + (size_t)a * CATHY_MAXIT, t.rec, sizeof(CathyIterRecord) * t.n);
+    }
+    return na;
+}
 
 void cathy_destroy(CathySim *S)
 {
@@ -916,6 +929,7 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
     else LAUNCH(S, k_adrstn, nblk(NN, S->grid_n), RED_BLOCK, NN, p.pmin, S->atmpot.p, S->ifatm.p, S->atmact.p, S->pnew.p);
     weight_and_copy(S);
     int nsurf = 0, status = 0;
+    S->attempts.clear();
     for (;;) {
         nsurf = 0;
         if (S->surf && S->ponding) {
@@ -935,6 +949,12 @@ int32_t cathy_step(CathySim *S, CathyStepReport *rep)
             copy_cells(S, S->q_in_kk_p, S->q_in_kk_sav); copy_cells(S, S->q_out_kk_1_p, S->q_out_kk_1_sav);
             copy_cells(S, S->q_out_kk_2_p, S->q_out_kk_2_sav); copy_cells(S, S->volume_kk_p, S->volume_kk_sav);
             zero_cells(S, S->q_in_kkp1); zero_cells(S, S->q_out_kkp1_1); zero_cells(S, S->q_out_kkp1_2); zero_cells(S, S->volume_kkp1);
+        }
+        {   // the failed attempt, as output/iter lists it
+            CathySim::Attempt a;
+            a.deltat = S->deltat; a.time = S->time; a.n = std::min(S->iter, (int)CATHY_MAXIT);
+            memcpy(a.rec, S->itrec, sizeof(CathyIterRecord) * a.n);
+            S->attempts.push_back(a);
         }
         bkstep(S);
         if (S->have_neu) neumann_device(S, S->ckrwp.p);

@@ -215,6 +215,8 @@ struct CathySim {
     double store0 = 0, store1 = 0, store2 = 0;
     int hgflag[9] = {0};
     CathyIterRecord itrec[CATHY_MAXIT];
+    struct Attempt { double deltat, time; int n; CathyIterRecord rec[CATHY_MAXIT]; };
+    std::vector<Attempt> attempts;   // failed attempts of the step being made (cathy_attempt_log)
     int itmax_dev = 0;
     double tol_dev = 0, itmxcg_scale = 0, tolcg_scale = 0;
 };

@@ -231,8 +231,12 @@ def run_processor(project_dir: str, lib: CathyLib | None = None, write_files: bo
                                     niter=[rep.it[k].niter for k in range(rep.n_iter_rec)],
                                     q_outlet=rep.q_outlet_1 + rep.q_outlet_2, gpu_ms=rep.gpu_ms))
         if write_files:
-            # the reference prints one (NSTEP..) header per attempt; back-stepped attempts are not
-            # reported by the library, so only the accepted attempt is listed here
+            # the reference prints one (NSTEP..) header per attempt: the back-stepped ones first (cathy_attempt_log)
+            if rep.kbackt > 0:
+                for dt_a, time_a, recs in sim.attempt_log():
+                    fh["iter"].write(O.iter_step_line(rep.nstep, dt_a, time_a))
+                    for k, r in enumerate(recs):
+                        fh["iter"].write(O.iter_line(k + 1, r))
             fh["iter"].write(O.iter_step_line(rep.nstep, rep.deltat, rep.time))
             for k in range(rep.n_iter_rec):
                 fh["iter"].write(O.iter_line(k + 1, rep.it[k]))

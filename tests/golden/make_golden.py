@@ -25,7 +25,7 @@ from pycathy_wrapper_b200 import synthetic  # noqa: E402
 KEEP_PREPRO = ["dem", "zone", "lakes_map", "qoi_a", "dtm_w_1", "dtm_w_2", "dtm_p_outflow_1", "dtm_p_outflow_2",
                "dtm_local_slope_1", "dtm_local_slope_2", "dtm_epl_1", "dtm_epl_2", "dtm_kSs1_sf_1", "dtm_kSs1_sf_2",
                "dtm_Ws1_sf_1", "dtm_Ws1_sf_2", "dtm_b1_sf", "dtm_y1_sf", "dtm_nrc", "hap.in"]
-VERBATIM = ["mbeconv", "cumflowvol", "hgraph", "vp"]
+VERBATIM = ["mbeconv", "cumflowvol", "hgraph", "vp", "iter"]
 AUX = ["hgatmsf", "hgnansf", "hgsfdet", "hgnansfdirdet", "hgnansfneudet", "wtdepth", "recharge", "fort.777", "psisurf", "satsurf", "swsurf",
        "velnod", "velelt", "hgflag", "dtcoupling"]
 

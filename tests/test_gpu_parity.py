@@ -331,6 +331,13 @@ def _run_both(gpu_lib, oracle_mod, prj, nsteps=None, store_rtol=1e-9):
         assert abs(rg.store1 - rc.store1) <= store_rtol * abs(rc.store1)
         assert abs(rg.erras) <= max(2.0 * abs(rc.erras), 1e-9 * abs(rc.store1)), (rg.erras, rc.erras)
         assert rg.finished == rc.finished
+        if rc.kbackt > 0:       # the failed attempts as output/iter lists them (cathy_attempt_log): same attempts, same nonlinear iterations
+            ag, ac = g.attempt_log(), c.attempt_log()
+            assert len(ag) == len(ac) == rc.kbackt
+            for (dg, tg, recg), (dc, tc, recc) in zip(ag, ac):
+                assert abs(dg - dc) <= 1e-12 * dc and abs(tg - tc) <= 1e-12 * tc and len(recg) == len(recc)
+                for a, b in zip(recg, recc):
+                    assert abs(a.pinf - b.pinf) <= 1e-4 * abs(b.pinf) + 1e-9, (a.pinf, b.pinf)
         if rg.finished or (nsteps and k >= nsteps):
             break
     return g, c, rg, rc
