@@ -828,7 +828,7 @@ def test_spmv_tma_matches_plain_product(gpu_lib, tmp_path, monkeypatch, size):
 
 
 @pytest.mark.parametrize("parm", [dict(KSLOPE=1, TOLKSL=0.01), dict(KSLOPE=2, TOLKSL=0.01), dict(NLRELX=2), dict(KSLOPE=1, TOLKSL=0.002, NLRELX=2),
-                                  dict(KSLOPE=3, TOLKSL=0.01, PSEL=-0.6, PSER=-0.2), dict(KSLOPE=4, PSEL=-0.6, PSER=-0.2)],
+                                  dict(KSLOPE=3, TOLKSL=0.01, PSEL=-0.7, PSER=5.0), dict(KSLOPE=4, PSEL=-0.6, PSER=-0.2)],
                          ids=["kslope1", "kslope2", "nlrelx2", "kslope1+nlrelx2", "kslope3", "kslope4"])
 def test_chord_slopes_and_variable_relaxation(gpu_lib, oracle_mod, tmp_path, parm):
     """KSLOPE = 1, 2 (k_curves_chord + the PTOLD copies) and NLRELX = 2 (k_relxom_*: OMEGA formed on the device from the signed
