@@ -273,3 +273,24 @@ def test_dtm13_reader_fast_and_record_paths_agree():
         assert np.array_equal(pp.read_dtm13(text, 5, 7), z)
     with pytest.raises(pp.PreproError, match="insufficient data"):
         pp.read_dtm13(plain, 5, 8)
+
+
+def test_product_preprocessor_fails_loudly_without_a_gpu(tmp_path, monkeypatch, capsys):
+    """No CPU path: on a machine without a CUDA device the call raises instead of computing anything on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from pycathy_wrapper_b200 import preprocessor as pp
+    d = unpack("plane17", tmp_path)
+    with pytest.raises(pp.PreproError, match="no CUDA device"):
+        pp.terrain_analysis(open(d + "/hap.in.orig").read(), open(d + "/dtm_13.val").read())
+    # and through the launcher's entry: message on stdout, non-zero exit, nothing written
+    run = str(tmp_path / "run")
+    os.makedirs(run)
+    shutil.copy(d + "/hap.in.orig", run + "/hap.in")
+    shutil.copy(d + "/dtm_13.val", run + "/dtm_13.val")
+    import io
+    monkeypatch.setattr("sys.stdin", io.StringIO("2\n0\n1\n"))
+    assert pp.main([run]) == 1
+    assert "no CUDA device" in capsys.readouterr().out
+    assert not os.path.exists(run + "/qoi_a") and not os.path.exists(run + "/dtm_w_1")
