@@ -18,7 +18,8 @@ The ONE JSON line of the default run carries, next to the headline `value` / `e2
                     reduction scalars through peer memory inside the PCG kernel (strong scaling).
     The headline keeps one independent forward run per rank (`scaling: weak`, no collective), so N=1 equals the plain bench.
   * at N=1: `roofline_hbm` (the same PCG and SpMV on a mesh of 3.4 M nodes, 3.4 x the L2, HBM-resident), `full_run`
-    (the whole TMAX = 7200 s of the headline workload), `setup_s`, `io_s`.
+    (the whole TMAX = 7200 s of the headline workload), `setup_s`, `io_s`, `prepro` (one short pass of --workload prepro: the
+    pre-processor on a 1000x1000 DEM with the reference's own ELF timed beside it).
 """
 from __future__ import annotations
 
@@ -858,6 +859,14 @@ def run_ours(args, size):
                 out["full_run"] = run_full(ctx, args, size)
             except Exception as e:      # noqa: BLE001
                 out["full_run"] = {"failed": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        if ctx.world == 1 and args.workload == "picard" and (not args.quick or args.prepro_leg):
+            # SURVEY 8f-3 in the driver's own record: one short pass of `--workload prepro` (1000x1000 DEM, the reference ELF timed beside it)
+            try:
+                r = run_prepro(ctx, argparse.Namespace(steps=3, warmup=1, no_cpu=args.no_cpu), (1000, 1000, 1))
+                out["prepro"] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "stage_ms", "depit", "drainage_wavefronts", "gpu_launches", "cpu_baseline") if k in r}
+                out["prepro"]["workload"] = r["config"]["workload"]
+            except Exception as e:      # noqa: BLE001
+                out["prepro"] = {"failed": "%s: %s" % (type(e).__name__, str(e)[:300])}
         if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu:
             newton = args.workload in ("newton", "coupled")
             out["cpu_baseline"] = cpu_baseline(size, budget_s=args.cpu_budget, iopt=2 if newton else 1, routing=args.workload == "coupled")
@@ -880,7 +889,8 @@ def main():
     ap.add_argument("--members", type=int, default=256)
     ap.add_argument("--concurrent", type=int, default=4, help="enkf workload: ensemble members advancing concurrently per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--quick", action="store_true", help="skip roofline_hbm and full_run")
+    ap.add_argument("--quick", action="store_true", help="skip roofline_hbm, full_run and the pre-processor leg")
+    ap.add_argument("--prepro-leg", action="store_true", help="run the pre-processor leg even with --quick")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--budget-s", type=float, default=540.0, help="wall-clock budget of the whole invocation; sharded legs that do not fit are skipped")
     args = ap.parse_args()
