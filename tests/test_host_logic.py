@@ -124,3 +124,23 @@ def test_oracle_checks_seepage_face_order(tmp_path):
     d = synthetic.make_project(str(tmp_path / "a"), 4, 5, 3, seepage_faces=[[3 * nnod + 30, 2 * nnod + 30]], TMAX=100.0)
     with pytest.raises(CathyLibraryError, match="descending"):
         oracle.simulation(load_project(d))
+
+
+def test_bench_reference_arm_of_the_preprocessor_workload_prints_the_contract_line():
+    """bench.py --impl reference --workload prepro runs the reference's own ELF (CPU only) and prints one JSON line with the
+    keys of the bench contract; without oracle/_ref it must say `unavailable` and exit 0."""
+    import json
+    import subprocess
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "prepro", "--size", "40x40x1", "--steps", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-500:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference"
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "bin", "pycppp")):
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+                  "cpu_baseline", "e2e"):
+            assert k in line, k
+        assert line["unit"] == "cells/s" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "reference"
+    else:
+        assert "unavailable" in line
