@@ -1,17 +1,21 @@
 // cathy_prepro.cu -- the CATHY pre-processor (terrain analysis: CSORT, DEPIT, CCA, SMEAN, DSF, HG) on sm_100a.
 // C ABI: include/cathy_prepro.h.  PRE = /root/reference/examples/SSHydro/weill_exemple/prepro/src (HAP v11.7).
 //
-// What is parallel and what is not.  The reference sweeps the cells in descending elevation and lets every cell push
-// area and deviation sums to its one or two receivers (PRE/dsf.f90:71-529): a cell's result depends on everything
-// upstream of it.  Here the sweep is a dependency WAVEFRONT: a cell becomes ready when all neighbours that precede it
-// in the elevation order are finished, then GATHERS the contributions of its donors in that same order, so the
-// floating-point sums are the reference's, bit for bit, while all cells of a wavefront run side by side (one persistent
-// cooperative grid, one grid barrier per wavefront, O(cells) work in total).  Window analysis (facets, curvature) and
-// hydraulic geometry are embarrassingly parallel.  Two pieces are sequential BY DEFINITION of their result and run on a
-// single device thread: the reference's unstable quicksort (PRE/qsort.f90), because the order of equal elevations is
-// part of the output (file qoi_a, the routing order of SRC/route.f:47-56), and DEPIT's in-place Gauss-Seidel raising of
-// pits (PRE/depit.f90:75-140), whose fixed point depends on the visiting order; a parallel check first proves the
-// common case "no pit at all", where DEPIT changes nothing.  There is no host fallback for any of it.
+// What is parallel and what is not.  The reference is a chain of sequential sweeps whose RESULTS depend on their order; the work
+// here is finding the parallelism that leaves every result bit-identical:
+//  * CSORT: the reference's unstable quicksort is REPLAYED, not replaced -- the permutation it leaves among equal elevations reaches
+//    qoi_a, the routing order of SRC/route.f:47-56.  Hoare's partition loop is a function of the incoming values (flag scans + pairing
+//    + independent exchanges, one 1024-thread CTA) and sub-arrays are finished side by side in shared memory (k_pp_qsplit / k_pp_qsmall).
+//  * DEPIT: in-place Gauss-Seidel raising of pits; its fixed point depends on the visiting order, so ONE CTA visits in the reference's
+//    order, with eight lanes per visit, a heap-driven first sweep that skips the visits that cannot change anything, and the parallel
+//    quicksort replay between sweeps.  A parallel check first proves the common case "no pit at all".
+//  * DSF: the reference sweeps the cells in descending elevation and lets every cell push area and deviation sums to its receivers
+//    (PRE/dsf.f90:71-529).  Here a dependency WAVEFRONT: a cell is ready when all neighbours that precede it in the elevation order are
+//    finished, then GATHERS the contributions of its donors in that same order, so the floating-point sums are the reference's while
+//    all cells of a wavefront run side by side (persistent cooperative grid, one grid barrier per wavefront, O(cells) work).
+//  * window analysis (facets, curvature), hydraulic geometry: one thread per cell; SMEAN: one warp adding in the reference's order.
+// All arithmetic that decides something goes through __dmul_rn / __dadd_rn / __ddiv_rn: nvcc would contract a*b+c into FMAs, the
+// reference binary (gfortran -O, x86-64) has none.  There is no host fallback for any of it.
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #include <cstdio>
@@ -446,7 +450,7 @@ __global__ void __launch_bounds__(PP_QT) k_pp_depit(PP S)
                     pp_ij(S, nib, i2, j2);
                     const int k2 = lane - 8, d2i = k2 / 3 - 1, d2j = k2 % 3 - 1;
                     if (i2 + d2i >= 1 && i2 + d2i <= N && j2 + d2j >= 1 && j2 + d2j <= M)
-                        { double sink; asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(sink) : "l"(&S.q[nib + M * d2i + d2j])); }
+                        { double sink; asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(sink) : "l"(&S.q[nib + M * d2i + d2j])); (void)sink; }
                 }
                 if (ib == outlet) continue;
                 const double qc = S.q[ib];
