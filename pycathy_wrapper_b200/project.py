@@ -490,8 +490,11 @@ def load_project(prj: str, skip_transport: bool | None = None) -> CathyProject:
     if isim == 2:
         S: dict = {}
         rdq = ListDirectedReader(fn["IIN23"])
-        rdq.skip_record()
         ncell = P.nrow * P.ncol
+        n_listed = int(rdq.read_i(1)[0])            # first record of qoi_a: the number of catchment cells (PRE/hg.f90:31)
+        if n_listed != ncell:
+            raise CathyInputError("prepro/qoi_a lists %d catchment cells for a %d x %d DEM: the pre-processor saw null cells (irregular "
+                                  "catchment outline), which the processor does not implement" % (n_listed, P.nrow, P.ncol))
         S["qoi"] = rdq.read_i(ncell)
         names = ["w_1", "w_2", "p_outflow_1", "p_outflow_2", "local_slope_1", "local_slope_2", "epl_1",
                  "epl_2", "kSs1_sf_1", "kSs1_sf_2", "Ws1_sf_1", "Ws1_sf_2", "b1_sf", "y1_sf", "nrc"]

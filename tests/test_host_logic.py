@@ -144,3 +144,19 @@ def test_bench_reference_arm_of_the_preprocessor_workload_prints_the_contract_li
         assert line["unit"] == "cells/s" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "reference"
     else:
         assert "unavailable" in line
+
+
+def test_loader_names_null_cells_when_only_qoi_a_reveals_them(tmp_path):
+    """A project whose dem / zone rasters were rewritten as full rectangles but whose pre-processor saw an irregular catchment
+    (shipped example: examples/SSHydro/meshing_from_subcachment): qoi_a then lists fewer cells than NROW x NCOL -- a clear refusal,
+    not an end-of-file error."""
+    import shutil
+    import pytest
+    from pycathy_wrapper_b200.project import CathyInputError, load_project
+    dst = str(tmp_path / "prj")
+    shutil.copytree(os.path.join(ROOT, "tests", "golden", "weill_exemple"), dst)
+    q = os.path.join(dst, "prepro", "qoi_a")
+    lines = open(q).read().splitlines()
+    open(q, "w").write("\n".join(["%12d" % 390] + lines[1:391]) + "\n")
+    with pytest.raises(CathyInputError, match="qoi_a lists 390 catchment cells for a 20 x 20 DEM"):
+        load_project(dst)
